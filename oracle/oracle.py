@@ -1,0 +1,307 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes loaders for the two CPU oracles.
+
+* ``RefKernel``  — the UNMODIFIED reference SIMD kernel compiled into ``oracle/_ref/libref_phmm_<isa>.so``
+  (``oracle/ref_driver.cpp``, built by ``oracle/Makefile`` from /root/reference where it lies).
+* ``COracle``    — the plain-C restatement ``oracle/liboctopus_oracle.so`` (``oracle/phmm_oracle.c``).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module. The product package ``octopus_b200`` never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, "_ref")
+
+_i8p = C.POINTER(C.c_int8)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+def cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def available_ref_isas():
+    """ISA builds of the reference kernel this host can execute, best first."""
+    flags = cpu_flags()
+    out = []
+    if {"avx512f", "avx512bw", "avx512vl", "avx512dq"} <= flags:
+        out.append("avx512")
+    if "avx2" in flags:
+        out.append("avx2")
+    if "sse4_1" in flags:
+        out.append("sse")
+    return [i for i in out if os.path.exists(os.path.join(REF_DIR, "libref_phmm_%s.so" % i))]
+
+
+def build(ref=True, quiet=True):
+    """(Re)build the oracle libraries. The reference build only happens where /root/reference exists."""
+    target = ["all"] if ref else ["liboctopus_oracle.so"]
+    subprocess.run(["make", "-C", _HERE] + target, check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _b(x):
+    """bytes / str / uint8-or-int8 ndarray → a ctypes char buffer that keeps its storage alive."""
+    if isinstance(x, str):
+        x = x.encode()
+    if isinstance(x, (bytes, bytearray)):
+        return C.create_string_buffer(bytes(x), len(x) + 1)
+    a = np.ascontiguousarray(x)
+    return C.create_string_buffer(a.tobytes(), a.nbytes + 1)
+
+
+def _i8(x):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.int8))
+    return a, a.ctypes.data_as(_i8p)
+
+
+class RefKernel:
+    """The reference kernel for one ISA build ('sse' | 'avx2' | 'avx512'). isa_force_sse2 → SSE2 policy even in a wider build."""
+
+    def __init__(self, isa=None):
+        isas = available_ref_isas()
+        if isa is None:
+            if not isas:
+                raise RuntimeError("no oracle/_ref library usable on this host (build with `make -C oracle` where /root/reference exists)")
+            isa = isas[0]
+        elif isa not in isas:
+            raise RuntimeError("reference ISA build %r not available on this host (have %s)" % (isa, isas))
+        self.isa = isa
+        self.lib = C.CDLL(os.path.join(REF_DIR, "libref_phmm_%s.so" % isa))
+        L = self.lib
+        L.ref_isa_name.restype = C.c_char_p
+        L.ref_isa_name.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ref_align.restype = C.c_int
+        L.ref_align.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, _i8p, C.c_int, C.c_int,
+                                C.c_char_p, _i8p, _i8p, _i8p, C.c_int, C.c_int]
+        L.ref_align_tb.restype = C.c_int
+        L.ref_align_tb.argtypes = L.ref_align.argtypes + [_i32p, C.c_char_p, C.c_char_p]
+        L.ref_flank_score.restype = C.c_int
+        L.ref_flank_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, _i8p,
+                                      C.c_char_p, _i8p, _i8p, _i8p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, _i32p]
+        L.ref_align_batch.restype = C.c_int
+        L.ref_align_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long,
+                                      C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+
+    def name(self, band, bits=16, force_sse2=False):
+        return self.lib.ref_isa_name(band, bits, int(force_sse2)).decode()
+
+    def _args(self, band, bits, force_sse2, truth, read, quals, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior):
+        keep = []
+        t, r = _b(truth), _b(read)
+        q, qp = _i8(quals)
+        go, gop = _i8(gap_open)
+        keep += [t, r, q, go]
+        if snv_mask is not None:
+            m = _b(snv_mask)
+            sp, spp = _i8(snv_prior)
+            keep += [m, sp]
+        else:
+            m, spp = None, None
+        if np.ndim(gap_extend) == 0:
+            gep, ges = None, int(gap_extend)
+        else:
+            ge, gep = _i8(gap_extend)
+            keep.append(ge)
+            ges = 0
+        W, L = len(t) - 1, len(r) - 1
+        assert W == L + 2 * band - 1, "truth window must be L + 2*band - 1 long"
+        return keep, [band, bits, int(force_sse2), t, r, qp, W, L, m, spp, gop, gep, ges, int(nuc_prior)]
+
+    def align(self, band, truth, read, quals, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None,
+              bits=16, force_sse2=False):
+        keep, a = self._args(band, bits, force_sse2, truth, read, quals, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior)
+        s = self.lib.ref_align(*a)
+        if s == -1000000:
+            raise ValueError("unsupported (band, bits)")
+        return s
+
+    def align_tb(self, band, truth, read, quals, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None,
+                 bits=16, force_sse2=False):
+        keep, a = self._args(band, bits, force_sse2, truth, read, quals, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior)
+        n = 2 * (len(read) + band) + 1
+        a1, a2 = C.create_string_buffer(n + 8), C.create_string_buffer(n + 8)
+        fp = C.c_int32(-7)
+        s = self.lib.ref_align_tb(*(a + [C.byref(fp), a1, a2]))
+        if s == -1000000:
+            raise ValueError("unsupported (band, bits)")
+        return s, fp.value, a1.value.decode(), a2.value.decode()
+
+    def flank_score(self, band, truth_len, lhs, rhs, read, quals, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior,
+                    first_pos, align1, align2, bits=16, force_sse2=False):
+        r, m = _b(read), _b(snv_mask)
+        q, qp = _i8(quals)
+        sp, spp = _i8(snv_prior)
+        go, gop = _i8(gap_open)
+        if np.ndim(gap_extend) == 0:
+            gep, ges = None, int(gap_extend)
+        else:
+            ge, gep = _i8(gap_extend)
+            ges = 0
+        ms = C.c_int32(0)
+        s = self.lib.ref_flank_score(band, bits, int(force_sse2), truth_len, lhs, rhs, r, qp, m, spp, gop, gep, ges, int(nuc_prior),
+                                     first_pos, _b(align1), _b(align2), C.byref(ms))
+        return s, ms.value
+
+    def align_batch(self, band, batch, read_idx, hap_idx, win_off, nuc_prior=2, nthreads=1, bits=16, force_sse2=False, strand_rev=False):
+        """batch: dict of packed numpy arrays (see octopus_b200.synth.pack_*). Returns int32 scores."""
+        read_idx = np.ascontiguousarray(read_idx, dtype=np.int32)
+        hap_idx = np.ascontiguousarray(hap_idx, dtype=np.int32)
+        win_off = np.ascontiguousarray(win_off, dtype=np.int32)
+        n = len(read_idx)
+        out = np.empty(n, dtype=np.int32)
+        mask = batch["hap_mask_rev"] if strand_rev else batch["hap_mask_fwd"]
+        prior = batch["hap_prior_rev"] if strand_rev else batch["hap_prior_fwd"]
+        arrs = [batch["read_bases"], batch["read_quals"], batch["read_off"], batch["hap_seq"], mask, prior,
+                batch["hap_gap_open"], batch["hap_gap_extend"], batch["hap_off"], read_idx, hap_idx, win_off]
+        for a in (batch["read_off"], batch["hap_off"]):
+            assert a.dtype == np.int64
+        rc = self.lib.ref_align_batch(band, bits, int(force_sse2), n, *[a.ctypes.data for a in arrs[:12]],
+                                      int(nuc_prior), int(nthreads), out.ctypes.data)
+        if rc != 0:
+            raise ValueError("unsupported (band, bits)")
+        return out
+
+
+class _Model(C.Structure):
+    _fields_ = [("snv_mask", C.c_char_p), ("snv_prior", _i8p), ("gap_open", _i8p), ("gap_extend", _i8p),
+                ("gap_open_scalar", C.c_int), ("gap_extend_scalar", C.c_int), ("nuc_prior", C.c_int)]
+
+
+LOWEST = -1.7976931348623157e308
+
+
+class COracle:
+    """The plain-C restatement (oracle/phmm_oracle.c)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "liboctopus_oracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.lib = L = C.CDLL(path)
+        mp = C.POINTER(_Model)
+        L.oracle_align.restype = C.c_int
+        L.oracle_align.argtypes = [C.c_int, C.c_char_p, C.c_char_p, _i8p, C.c_int, C.c_int, mp]
+        L.oracle_align_tb.restype = C.c_int
+        L.oracle_align_tb.argtypes = L.oracle_align.argtypes + [_i32p, C.c_char_p, C.c_char_p]
+        L.oracle_flank_score.restype = C.c_int
+        L.oracle_flank_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, _i8p, mp, C.c_int, C.c_char_p, C.c_char_p, _i32p]
+        L.oracle_try_naive_evaluate.restype = C.c_int
+        L.oracle_try_naive_evaluate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_int, mp,
+                                                C.c_int, C.c_int, C.c_int, _i32p]
+        L.oracle_evaluate.restype = C.c_double
+        L.oracle_evaluate.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_int, mp,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p]
+        L.oracle_model_evaluate.restype = C.c_int
+        L.oracle_model_evaluate.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, mp,
+                                            C.c_int, C.c_int, C.c_int, _i64p, C.c_int, C.c_int64,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _i32p]
+        L.oracle_kmer_map.restype = C.c_int
+        L.oracle_kmer_map.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, _i64p]
+
+    @staticmethod
+    def model(gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
+        """Returns (struct, keepalive). gap_open / gap_extend may be arrays or scalars."""
+        keep = []
+        m = _Model()
+        if snv_mask is not None:
+            b = _b(snv_mask)
+            sp, spp = _i8(snv_prior)
+            keep += [b, sp]
+            m.snv_mask = C.cast(b, C.c_char_p)
+            m.snv_prior = spp
+        if np.ndim(gap_open) == 0:
+            m.gap_open_scalar = int(gap_open)
+        else:
+            a, p = _i8(gap_open)
+            keep.append(a)
+            m.gap_open = p
+        if np.ndim(gap_extend) == 0:
+            m.gap_extend_scalar = int(gap_extend)
+        else:
+            a, p = _i8(gap_extend)
+            keep.append(a)
+            m.gap_extend = p
+        m.nuc_prior = int(nuc_prior)
+        return m, keep
+
+    def align(self, band, truth, read, quals, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
+        m, keep = self.model(gap_open, gap_extend, nuc_prior, snv_mask, snv_prior)
+        t, r = _b(truth), _b(read)
+        q, qp = _i8(quals)
+        return self.lib.oracle_align(band, t, r, qp, len(t) - 1, len(r) - 1, C.byref(m))
+
+    def align_tb(self, band, truth, read, quals, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
+        m, keep = self.model(gap_open, gap_extend, nuc_prior, snv_mask, snv_prior)
+        t, r = _b(truth), _b(read)
+        q, qp = _i8(quals)
+        n = 2 * (len(r) - 1 + band) + 1
+        a1, a2 = C.create_string_buffer(n + 8), C.create_string_buffer(n + 8)
+        fp = C.c_int32(-7)
+        s = self.lib.oracle_align_tb(band, t, r, qp, len(t) - 1, len(r) - 1, C.byref(m), C.byref(fp), a1, a2)
+        return s, fp.value, a1.value.decode(), a2.value.decode()
+
+    def flank_score(self, truth_len, lhs, rhs, read, quals, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior,
+                    first_pos, align1, align2):
+        m, keep = self.model(gap_open, gap_extend, nuc_prior, snv_mask, snv_prior)
+        q, qp = _i8(quals)
+        ms = C.c_int32(0)
+        s = self.lib.oracle_flank_score(truth_len, lhs, rhs, _b(read), qp, C.byref(m), first_pos, _b(align1), _b(align2), C.byref(ms))
+        return s, ms.value
+
+    def try_naive_evaluate(self, truth, read, quals, offset, gap_open, gap_extend, snv_mask=None, snv_prior=None,
+                           flanks=None):
+        m, keep = self.model(gap_open, gap_extend, 2, snv_mask, snv_prior)
+        t, r = _b(truth), _b(read)
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.uint8))
+        ph = C.c_int32(0)
+        uf, lhs, rhs = (0, 0, 0) if flanks is None else (1, flanks[0], flanks[1])
+        hit = self.lib.oracle_try_naive_evaluate(t, len(t) - 1, r, q.ctypes.data, len(r) - 1, offset, C.byref(m), uf, lhs, rhs, C.byref(ph))
+        return bool(hit), ph.value
+
+    def evaluate(self, band, truth, read, quals, offset, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None,
+                 flanks=None, dp_only=False, details=False):
+        m, keep = self.model(gap_open, gap_extend, nuc_prior, snv_mask, snv_prior)
+        t, r = _b(truth), _b(read)
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.uint8))
+        used, raw = C.c_int32(0), C.c_int32(0)
+        uf, lhs, rhs = (0, 0, 0) if flanks is None else (1, flanks[0], flanks[1])
+        v = self.lib.oracle_evaluate(band, t, len(t) - 1, r, q.ctypes.data, len(r) - 1, offset, C.byref(m), uf, lhs, rhs,
+                                     int(dp_only), C.byref(used), C.byref(raw))
+        return (v, used.value, raw.value) if details else v
+
+    def model_evaluate(self, band, hap, read, quals, gap_open, gap_extend, snv_mask, snv_prior, positions, original_pos,
+                       mapping_quality=60, nuc_prior=2, flanks=None, use_mapping_quality=True, mapq_cap=120,
+                       mapq_cap_trigger=-1, dp_only=False):
+        """Returns (status, value, required_extension); status 1 == ShortHaplotypeError."""
+        m, keep = self.model(gap_open, gap_extend, nuc_prior, snv_mask, snv_prior)
+        h, r = _b(hap), _b(read)
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.uint8))
+        pos = np.ascontiguousarray(np.asarray(positions, dtype=np.int64))
+        out, ext = C.c_double(0), C.c_int32(0)
+        uf, lhs, rhs = (0, 0, 0) if flanks is None else (1, flanks[0], flanks[1])
+        st = self.lib.oracle_model_evaluate(band, h, len(h) - 1, r, q.ctypes.data, len(r) - 1, C.byref(m), uf, lhs, rhs,
+                                            pos.ctypes.data_as(_i64p), len(pos), int(original_pos), int(use_mapping_quality),
+                                            int(mapping_quality), int(mapq_cap), int(mapq_cap_trigger), int(dp_only),
+                                            C.byref(out), C.byref(ext))
+        return st, out.value, ext.value
+
+    def kmer_map(self, query, target, max_positions=10):
+        qb, tb = _b(query), _b(target)
+        out = np.zeros(max(1, max_positions), dtype=np.int64)
+        n = self.lib.oracle_kmer_map(qb, len(qb) - 1, tb, len(tb) - 1, max_positions, out.ctypes.data_as(_i64p))
+        return out[:n].tolist()
