@@ -1,0 +1,144 @@
+/*
+ * phmm_b200.h — C ABI of the B200-native pair-HMM haplotype-likelihood engine.
+ *
+ * Drop-in boundary for ONE path of luntergroup/octopus (v0.7.4): the banded pair-HMM that scores every
+ * (read, haplotype) pair and fills HaplotypeLikelihoodArray. The reference has no FFI layer; the seams this
+ * ABI replaces are (paths relative to the reference tree):
+ *
+ *   raw kernel    simd::PairHMM::align(truth, target, quals, truth_len, target_len, snv_mask, snv_prior,
+ *                 gap_open, gap_extend, nuc_prior)            src/core/models/pairhmm/simd_pair_hmm.hpp:454-470
+ *                 → phmm_align_scores()           (one integer score per (read, haplotype window) task)
+ *   per read      hmm::evaluate(truth, target, quals, offset, hmm, params)      pair_hmm.hpp:827-841
+ *                 HaplotypeLikelihoodModel::evaluate(read, first_pos, last_pos) haplotype_likelihood_model.cpp:261-304
+ *   batch         HaplotypeLikelihoodArray::populate(reads, haplotypes, flank_state, workers)
+ *                                                              haplotype_likelihood_array.cpp:51-103
+ *                 → phmm_populate()               (the [H][R] matrix of ln-likelihoods, double)
+ *
+ * Conventions: plain pointers and sizes only; every pointer of one call lives in the memory space named by
+ * `space` (host memory, or device memory of the engine's GPU); the caller owns all buffers; calls are
+ * synchronous (results complete on return) unless stated; functions return PHMM_OK or a negative error code
+ * and never throw — the C++ adapter (octopus_b200/cpp/phmm_b200.hpp) re-throws the reference's exceptions.
+ * An engine handle is not re-entrant (one per host thread, like the reference's per-thread model copies,
+ * haplotype_likelihood_array.cpp:172).
+ * There is no CPU fallback: every entry point that computes fails with PHMM_ERR_CUDA when no B200 is usable.
+ */
+#ifndef PHMM_B200_H
+#define PHMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHMM_OK                  0
+#define PHMM_ERR_INVALID        -1   /* bad argument (message in phmm_last_error) */
+#define PHMM_ERR_CUDA           -2   /* CUDA runtime / no device */
+#define PHMM_ERR_BAND           -3   /* band > 256: reference TooLargeBandSizeError (simd_pair_hmm_wrapper.hpp:45-61) */
+#define PHMM_ERR_SHORT_HAPLOTYPE -4  /* reference ShortHaplotypeError (haplotype_likelihood_model.cpp:238-256); see status[] */
+#define PHMM_ERR_NOMEM          -5
+
+#define PHMM_SPACE_HOST   0
+#define PHMM_SPACE_DEVICE 1
+
+/* per-pair status written by phmm_populate (optional output) */
+#define PHMM_STATUS_OK          0
+#define PHMM_STATUS_OVERFLOW    1   /* every candidate returned lowest(): pair_hmm.hpp:736-738,750-752 */
+#define PHMM_STATUS_SHORT_HAP   2   /* ShortHaplotypeError; required extension in the high 16 bits */
+
+typedef struct phmm_engine phmm_engine;
+
+/* mirrors HaplotypeLikelihoodModel::Config (haplotype_likelihood_model.hpp:36-44) + hmm::Parameters::nuc_prior */
+typedef struct {
+    int32_t max_indel_error;             /* requested band; rounded up to 8,16,32,...,256 (simd_pair_hmm_wrapper.hpp:218-241) */
+    int32_t use_int_scores;              /* reference: int32 SIMD lanes. Here: forces the 32-bit kernel */
+    int32_t use_mapping_quality;         /* default 1 */
+    int32_t mapping_quality_cap;         /* default 120 */
+    int32_t mapping_quality_cap_trigger; /* < 0: none (boost::none) */
+    int32_t use_flank_state;             /* default 1 */
+    int32_t nuc_prior;                   /* default 2 (pair_hmm.hpp:86) */
+    int32_t disable_naive_shortcut;      /* 1: every candidate goes through the DP (benchmark mode; NOT reference behaviour) */
+} phmm_config;
+
+/* H haplotypes, struct of arrays. Per-base arrays are concatenated; haplotype h owns [off[h], off[h+1]).
+ * These are exactly the members HaplotypeLikelihoodModel::reset fills (haplotype_likelihood_model.cpp:60-78). */
+typedef struct {
+    int32_t        n;
+    const int64_t* off;            /* [n+1] */
+    const char*    seq;            /* Haplotype::sequence() */
+    const char*    snv_mask_fwd;   /* haplotype_snv_forward_mask_ */
+    const int8_t*  snv_prior_fwd;  /* haplotype_snv_forward_priors_ */
+    const char*    snv_mask_rev;
+    const int8_t*  snv_prior_rev;
+    const int8_t*  gap_open;       /* haplotype_gap_open_penalities_ */
+    const int8_t*  gap_extend;     /* haplotype_gap_extend_penalities_ */
+    const int64_t* begin;          /* [n] mapped_begin(haplotype), or NULL (= 0) */
+} phmm_haplotypes;
+
+/* R reads, struct of arrays (AlignedRead fields: basics/aligned_read.hpp:36-39,120-146). */
+typedef struct {
+    int32_t        n;
+    const int64_t* off;            /* [n+1] */
+    const char*    bases;          /* AlignedRead::sequence() */
+    const uint8_t* quals;          /* AlignedRead::base_qualities() */
+    const uint8_t* mapq;           /* [n] AlignedRead::mapping_quality() */
+    const uint8_t* reverse;        /* [n] AlignedRead::is_marked_reverse_mapped() */
+    const int64_t* begin;          /* [n] mapped_begin(read): original position = begin[r] - haplotype begin[h] */
+} phmm_reads;
+
+/* Candidate mapping positions per (haplotype, read) pair, CSR in [H][R] order
+ * (what map_query_to_target emits, utils/kmer_mapper.hpp:120-159). NULL → only the original position is tried. */
+typedef struct {
+    const int64_t* off;            /* [H*R + 1] */
+    const int32_t* pos;
+} phmm_positions;
+
+/* HaplotypeLikelihoodModel::FlankState (haplotype_likelihood_model.hpp:46-49); has_flank = 0 ↔ boost::none */
+typedef struct {
+    int32_t has_flank;
+    int64_t lhs_flank, rhs_flank;
+} phmm_flank_state;
+
+/* One raw-kernel task: read `read` against the window of haplotype `hap` starting at `win_off`
+ * (window length = read length + 2*band - 1), SNV mask/prior of strand `reverse`. */
+typedef struct {
+    int32_t read;
+    int32_t hap;
+    int32_t win_off;
+    int32_t reverse;
+} phmm_task;
+
+const char* phmm_version(void);
+void        phmm_default_config(phmm_config* cfg);
+
+/* device < 0: current CUDA device. Creates the engine's stream and scratch pools. */
+int         phmm_create(phmm_engine** out, int device);
+void        phmm_destroy(phmm_engine* e);
+const char* phmm_last_error(const phmm_engine* e);   /* valid until the next call on e; e may be NULL */
+
+/* Number of kernels of this library launched by the last call / in total (bench.py's gpu_launches). */
+int64_t     phmm_launch_count(const phmm_engine* e, int total);
+
+/* CUDA events around the dominant DP kernel of the last call, in milliseconds (0 if none ran). */
+double      phmm_last_dp_kernel_ms(const phmm_engine* e);
+/* Banded cells 2*(L+band)*band summed over the DP tasks of the last call (the GCUPS numerator). */
+int64_t     phmm_last_dp_cells(const phmm_engine* e);
+
+/* Raw kernel boundary: scores[j] == reference hmm.align(hap window, read, ...) for task j (integer phred).
+ * band must be one of 8,16,32,...,256. precision_bits: 16 (packed s16x2 fast path where it is exact, else 32) or 32. */
+int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prior,
+                      const phmm_haplotypes* haps, const phmm_reads* reads,
+                      const phmm_task* tasks, int64_t n_tasks, int32_t* scores, int space);
+
+/* Batch boundary: out[h*R + r] == HaplotypeLikelihoodArray likelihoods_[h][sample][r] for a single-sample ReadMap
+ * (haplotype_likelihood_array.cpp:77-95). status (optional, [H*R]) receives PHMM_STATUS_*.
+ * Returns PHMM_ERR_SHORT_HAPLOTYPE if any pair raised ShortHaplotypeError (the reference throws out of populate). */
+int phmm_populate(phmm_engine* e, const phmm_config* cfg,
+                  const phmm_haplotypes* haps, const phmm_reads* reads,
+                  const phmm_positions* positions, const phmm_flank_state* flank,
+                  double* out, int32_t* status, int space);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHMM_B200_H */

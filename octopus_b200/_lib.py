@@ -1,0 +1,74 @@
+"""ctypes binding of include/phmm_b200.h. Fails loudly when the extension is missing: there is no fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphmm_b200.so")
+
+PHMM_OK, PHMM_ERR_INVALID, PHMM_ERR_CUDA, PHMM_ERR_BAND, PHMM_ERR_SHORT_HAPLOTYPE, PHMM_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+SPACE_HOST, SPACE_DEVICE = 0, 1
+
+EXPORTS = ["phmm_version", "phmm_default_config", "phmm_create", "phmm_destroy", "phmm_last_error", "phmm_launch_count",
+           "phmm_last_dp_kernel_ms", "phmm_last_dp_cells", "phmm_align_scores", "phmm_populate"]
+
+
+class Config(C.Structure):
+    _fields_ = [("max_indel_error", C.c_int32), ("use_int_scores", C.c_int32), ("use_mapping_quality", C.c_int32),
+                ("mapping_quality_cap", C.c_int32), ("mapping_quality_cap_trigger", C.c_int32),
+                ("use_flank_state", C.c_int32), ("nuc_prior", C.c_int32), ("disable_naive_shortcut", C.c_int32)]
+
+
+class Haplotypes(C.Structure):
+    _fields_ = [("n", C.c_int32), ("off", C.c_void_p), ("seq", C.c_void_p), ("snv_mask_fwd", C.c_void_p),
+                ("snv_prior_fwd", C.c_void_p), ("snv_mask_rev", C.c_void_p), ("snv_prior_rev", C.c_void_p),
+                ("gap_open", C.c_void_p), ("gap_extend", C.c_void_p), ("begin", C.c_void_p)]
+
+
+class Reads(C.Structure):
+    _fields_ = [("n", C.c_int32), ("off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p),
+                ("mapq", C.c_void_p), ("reverse", C.c_void_p), ("begin", C.c_void_p)]
+
+
+class Positions(C.Structure):
+    _fields_ = [("off", C.c_void_p), ("pos", C.c_void_p)]
+
+
+class FlankState(C.Structure):
+    _fields_ = [("has_flank", C.c_int32), ("lhs_flank", C.c_int64), ("rhs_flank", C.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load libphmm_b200.so (building it first if the sources are newer). Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("octopus_b200: CUDA extension %s is missing and could not be built" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.phmm_version.restype = C.c_char_p
+    lib.phmm_default_config.argtypes = [C.POINTER(Config)]
+    lib.phmm_create.restype = C.c_int
+    lib.phmm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.phmm_destroy.argtypes = [C.c_void_p]
+    lib.phmm_last_error.restype = C.c_char_p
+    lib.phmm_last_error.argtypes = [C.c_void_p]
+    lib.phmm_launch_count.restype = C.c_int64
+    lib.phmm_launch_count.argtypes = [C.c_void_p, C.c_int]
+    lib.phmm_last_dp_kernel_ms.restype = C.c_double
+    lib.phmm_last_dp_kernel_ms.argtypes = [C.c_void_p]
+    lib.phmm_last_dp_cells.restype = C.c_int64
+    lib.phmm_last_dp_cells.argtypes = [C.c_void_p]
+    lib.phmm_align_scores.restype = C.c_int
+    lib.phmm_align_scores.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Haplotypes), C.POINTER(Reads),
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    lib.phmm_populate.restype = C.c_int
+    lib.phmm_populate.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Haplotypes), C.POINTER(Reads),
+                                  C.POINTER(Positions), C.POINTER(FlankState), C.c_void_p, C.c_void_p, C.c_int]
+    _lib = lib
+    return lib

@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference interface for this path, over the C ABI (include/phmm_b200.h).
+
+Names and argument meaning follow the reference:
+  * ``PairHMMEngine.align_scores``            ↔ simd::PairHMM::align  (simd_pair_hmm.hpp:454-470), batched
+  * ``HaplotypeLikelihoodModel.Config``       ↔ HaplotypeLikelihoodModel::Config (haplotype_likelihood_model.hpp:36-44)
+  * ``HaplotypeLikelihoodArray.populate``     ↔ HaplotypeLikelihoodArray::populate (haplotype_likelihood_array.cpp:51-103)
+  * ``ShortHaplotypeError``                   ↔ HaplotypeLikelihoodModel::ShortHaplotypeError (:123-139)
+Every computing call goes through libphmm_b200.so to the GPU; nothing here computes likelihoods on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .batch import HaplotypeBlock, ReadBlock
+
+
+class PhmmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("phmm error %d: %s" % (code, message))
+        self.code = code
+
+
+class ShortHaplotypeError(PhmmError):
+    """Haplotype is too short for alignment (reference: thrown out of populate, caller.cpp:1182-1188 skips the region)."""
+
+
+class TooLargeBandSizeError(PhmmError):
+    """Requested band > 256 (simd_pair_hmm_wrapper.hpp:45-61)."""
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr")
+
+
+class PairHMMEngine:
+    """One engine handle (not re-entrant; one per host thread, like the reference's per-thread model copies)."""
+
+    def __init__(self, device=-1):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.phmm_create(C.byref(h), int(device))
+        if rc != _lib.PHMM_OK:
+            raise PhmmError(rc, self._lib.phmm_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.phmm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _raise(self, rc):
+        msg = self._lib.phmm_last_error(self._h).decode()
+        if rc == _lib.PHMM_ERR_SHORT_HAPLOTYPE:
+            raise ShortHaplotypeError(rc, msg)
+        if rc == _lib.PHMM_ERR_BAND:
+            raise TooLargeBandSizeError(rc, msg)
+        raise PhmmError(rc, msg)
+
+    # -- statistics of the last call -------------------------------------------------------------------------
+    def launch_count(self, total=False):
+        return int(self._lib.phmm_launch_count(self._h, int(total)))
+
+    def last_dp_kernel_ms(self):
+        return float(self._lib.phmm_last_dp_kernel_ms(self._h))
+
+    def last_dp_cells(self):
+        return int(self._lib.phmm_last_dp_cells(self._h))
+
+    # -- raw kernel boundary -----------------------------------------------------------------------------------
+    def align_scores(self, band, haps: HaplotypeBlock, reads: ReadBlock, tasks, nuc_prior=2, precision_bits=16):
+        """tasks: (n, 4) int32 rows (read, hap, win_off, reverse). Returns the integer score of every task, i.e.
+        reference ``hmm.align(hap_window, read, quals, L+2*band-1, L, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior)``."""
+        dev = haps.on_device
+        assert dev == reads.on_device, "haplotypes and reads must live in the same memory space"
+        hs, rs = haps.c_struct(), reads.c_struct()
+        if dev:
+            import torch
+            t = tasks if _is_torch(tasks) else torch.as_tensor(np.ascontiguousarray(tasks, dtype=np.int32), device=haps.seq.device)
+            t = t.to(torch.int32).contiguous()
+            n = t.shape[0]
+            out = torch.empty(n, dtype=torch.int32, device=t.device)
+            tp, op = t.data_ptr(), out.data_ptr()
+        else:
+            t = np.ascontiguousarray(tasks, dtype=np.int32).reshape(-1, 4)
+            n = t.shape[0]
+            out = np.empty(n, dtype=np.int32)
+            tp, op = t.ctypes.data, out.ctypes.data
+        rc = self._lib.phmm_align_scores(self._h, int(band), int(precision_bits), int(nuc_prior), C.byref(hs), C.byref(rs),
+                                         tp, n, op, _lib.SPACE_DEVICE if dev else _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+        return out
+
+    # -- batch boundary ----------------------------------------------------------------------------------------
+    def populate(self, config, haps: HaplotypeBlock, reads: ReadBlock, positions=None, flank_state=None, out=None,
+                 want_status=False):
+        """Returns the (H, R) matrix of ln-likelihoods (numpy float64, or a torch CUDA tensor for device-resident blocks).
+        positions: None or (off[H*R+1] int64, pos int32) CSR in [H][R] order. flank_state: None or (lhs_flank, rhs_flank)."""
+        dev = haps.on_device
+        assert dev == reads.on_device, "haplotypes and reads must live in the same memory space"
+        H, R = haps.n, reads.n
+        hs, rs = haps.c_struct(), reads.c_struct()
+        cfg = config.c_struct() if hasattr(config, "c_struct") else config
+        keep = []
+        pstruct = None
+        if positions is not None:
+            off, pos = positions
+            if dev:
+                import torch
+                off = off if _is_torch(off) else torch.as_tensor(np.ascontiguousarray(off, dtype=np.int64), device=haps.seq.device)
+                pos = pos if _is_torch(pos) else torch.as_tensor(np.ascontiguousarray(pos, dtype=np.int32), device=haps.seq.device)
+                pstruct = _lib.Positions(off.data_ptr(), pos.data_ptr())
+            else:
+                off = np.ascontiguousarray(off, dtype=np.int64)
+                pos = np.ascontiguousarray(pos, dtype=np.int32)
+                pstruct = _lib.Positions(off.ctypes.data, pos.ctypes.data)
+            keep += [off, pos]
+        fstruct = None
+        if flank_state is not None:
+            fstruct = _lib.FlankState(1, int(flank_state[0]), int(flank_state[1]))
+        status = None
+        if dev:
+            import torch
+            if out is None:
+                out = torch.empty((H, R), dtype=torch.float64, device=haps.seq.device)
+            if want_status:
+                status = torch.empty((H, R), dtype=torch.int32, device=haps.seq.device)
+            op, sp = out.data_ptr(), (status.data_ptr() if want_status else None)
+        else:
+            if out is None:
+                out = np.empty((H, R), dtype=np.float64)
+            if want_status:
+                status = np.empty((H, R), dtype=np.int32)
+            op, sp = out.ctypes.data, (status.ctypes.data if want_status else None)
+        rc = self._lib.phmm_populate(self._h, C.byref(cfg), C.byref(hs), C.byref(rs),
+                                     C.byref(pstruct) if pstruct is not None else None,
+                                     C.byref(fstruct) if fstruct is not None else None,
+                                     op, sp, _lib.SPACE_DEVICE if dev else _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK:
+            if rc == _lib.PHMM_ERR_SHORT_HAPLOTYPE and want_status:
+                return out, status
+            self._raise(rc)
+        return (out, status) if want_status else out
+
+
+class HaplotypeLikelihoodModel:
+    """Configuration holder with the reference's names (the per-haplotype state lives in the HaplotypeBlock)."""
+
+    class Config:
+        def __init__(self, use_mapping_quality=True, mapping_quality_cap_trigger=None, mapping_quality_cap=120,
+                     use_flank_state=True, max_indel_error=8, use_int_scores=False, nuc_prior=2,
+                     disable_naive_shortcut=False):
+            self.use_mapping_quality = use_mapping_quality
+            self.mapping_quality_cap_trigger = mapping_quality_cap_trigger
+            self.mapping_quality_cap = mapping_quality_cap
+            self.use_flank_state = use_flank_state
+            self.max_indel_error = max_indel_error
+            self.use_int_scores = use_int_scores
+            self.nuc_prior = nuc_prior
+            self.disable_naive_shortcut = disable_naive_shortcut
+
+        def c_struct(self):
+            trig = self.mapping_quality_cap_trigger
+            # haplotype_likelihood_model.cpp:50-52: a trigger >= the cap is dropped
+            if trig is not None and trig >= self.mapping_quality_cap:
+                trig = None
+            return _lib.Config(int(self.max_indel_error), int(self.use_int_scores), int(self.use_mapping_quality),
+                               int(self.mapping_quality_cap), -1 if trig is None else int(trig),
+                               int(self.use_flank_state), int(self.nuc_prior), int(self.disable_naive_shortcut))
+
+    def __init__(self, config=None):
+        self.config = config or HaplotypeLikelihoodModel.Config()
+
+    def pad_requirement(self):
+        """hmm_.band_size() (haplotype_likelihood_model.cpp:55-58): smallest of 8,16,...,256 >= max_indel_error."""
+        b = 8
+        while b < self.config.max_indel_error:
+            b *= 2
+        return b
+
+
+class HaplotypeLikelihoodArray:
+    """The (haplotype x read) ln-likelihood matrix of one sample (haplotype_likelihood_array.hpp:123)."""
+
+    mapperKmerSize = 6          # haplotype_likelihood_array.hpp:103
+    maxMappingPositions = 10    # :104
+
+    def __init__(self, likelihood_model=None, engine=None):
+        self.likelihood_model = likelihood_model or HaplotypeLikelihoodModel()
+        self.engine = engine or PairHMMEngine()
+        self.likelihoods = None
+
+    def populate(self, reads: ReadBlock, haplotypes: HaplotypeBlock, flank_state=None, positions=None):
+        self.likelihoods = self.engine.populate(self.likelihood_model.config, haplotypes, reads, positions, flank_state)
+        return self
+
+    def is_empty(self):
+        return self.likelihoods is None
+
+    def clear(self):
+        self.likelihoods = None
+
+    def __getitem__(self, haplotype_index):
+        """likelihoods_[haplotype][sample] (haplotype_likelihood_array.cpp:212-236)."""
+        return self.likelihoods[haplotype_index]

@@ -1,0 +1,462 @@
+// Device-side building blocks of the B200 pair-HMM engine (sm_100a).
+//
+// Recurrence: the integer min-plus banded DP of the reference kernel
+//   /root/reference/src/core/models/pairhmm/simd_pair_hmm.hpp:240-324 (align_helper)
+// restated in (x, y) prefix coordinates (x truth-window bases, y read bases consumed; band 0 <= x-y <= 2B-1):
+//   S          = min(m, i, d)                                    (:284, :308)
+//   m(x+1,y+1) = S + sub(x, y)                                   (:121-132 update_match_state)
+//   d(x+1,y)   = min(d + gap_extend[x], min(mg, i) + gap_open[x])            (:293, :317; I→D allowed)
+//   i(x,y+1)   = min(i + gap_extend[x-1], mg + gap_open[x-1]) + nuc_prior    (:295, :318-319; no D→I)
+//   y == 0: m = 0 (free start, rolling_initializer.hpp:39-51); mg = 0 for odd x, +inf for even x (the gap
+//   transitions of even-x cells are computed before the initialiser touches them, :282-283 vs :317-319)
+//   result = min over x of S(x, L)                               (:285-291, :309-315, :323)
+//
+// Two implementations live here:
+//   * dp_pair<BAND>  — the fast path. One THREAD owns TWO alignments packed as s16x2 in every register and sweeps
+//     the band column by column (x outer, diagonal k = x-y unrolled in registers). No shuffles, no shared-memory
+//     DP state. The per-cell work is 10 integer instructions for 2 cells using Blackwell's DPX packed-16 ops
+//     (VIMNMX3.S16x2, VIADDMNMX.S16x2, VIMNMX.S16x2) and PRMT byte-table lookups for the emission.
+//   * generic_align  — int32, any band, any alphabet, optional traceback + flank replay. Exactness fallback.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace phmm {
+
+// ---------------------------------------------------------------------------------------------------------
+// Encodings shared by the preparation kernels and the DP kernels
+// ---------------------------------------------------------------------------------------------------------
+
+// Haplotype column table entry (8 bytes per haplotype base per strand):
+//   .x = four emission caps, byte b = cost cap when the read base has code b (A0 C1 G2 T3):
+//          0                                   if truth[x] == base
+//          min(snv_prior[x] if snv_mask[x]==base else 127,  2 if truth[x]=='N' else 127)   otherwise
+//        sub(x, y) = min(qual[y], cap[x][read[y]])  — identical to update_match_state for quals, priors in [0,127].
+//        All caps are < 0x80, which lets PRMT's sign-replicate mode manufacture the zero bytes of the packed lanes.
+//   .y = gap_open[x] | gap_extend[x] << 8   (upper 16 bits zero)
+typedef uint2 ColEntry;
+
+constexpr uint32_t kCapInf   = 127u;      // "no cap": min(q, 127) == q for every int8 quality
+constexpr uint32_t kInf16    = 0x7000u;   // +inf of the packed 16-bit lanes; kInf16 + 2*127 + nuc stays < 0x8000
+constexpr uint32_t kInf16x2  = kInf16 | (kInf16 << 16);
+constexpr int      kInf32    = 1 << 28;   // +inf of the int32 kernel
+constexpr int      kMaxScore16 = 0x7000 - 1024;  // a read whose sum of qualities is below this cannot overflow a 16-bit lane
+
+// Read row half-word: code | qual << 8 (code: A0 C1 G2 T3). Reads containing any other byte take the generic path.
+__host__ __device__ inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+// The DP cores are __host__ __device__ so that tests/ can run the very same code on the CPU (with the few
+// sm_100a instructions emulated below) against the CPU checker without a GPU. The product library never calls the
+// host instantiations: every exported entry point launches kernels.
+#define PHMM_HD __host__ __device__ __forceinline__
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }                              // VIMNMX.S16x2
+__device__ __forceinline__ uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }       // VIMNMX3.S16x2
+__device__ __forceinline__ uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }   // VIADDMNMX.S16x2: min(a+b, c)
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+#else
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)   // PTX prmt.b32 default mode, incl. sign replication (nibble bit 3)
+{
+    const uint64_t src = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t d = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t n = (sel >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(src >> (8 * (n & 7))) & 0xFF;
+        if (n & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        d |= byte << (8 * i);
+    }
+    return d;
+}
+inline uint32_t emu_pack(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | (((uint32_t)hi & 0xFFFFu) << 16); }
+inline int emu_lo(uint32_t v) { return (int16_t)(v & 0xFFFF); }
+inline int emu_hi(uint32_t v) { return (int16_t)(v >> 16); }
+inline int emu_min(int a, int b) { return a < b ? a : b; }
+inline uint32_t vmin2(uint32_t a, uint32_t b) { return emu_pack(emu_min(emu_lo(a), emu_lo(b)), emu_min(emu_hi(a), emu_hi(b))); }
+inline uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return vmin2(vmin2(a, b), c); }
+inline uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c)
+{
+    return emu_pack(emu_min((int16_t)(emu_lo(a) + emu_lo(b)), emu_lo(c)), emu_min((int16_t)(emu_hi(a) + emu_hi(b)), emu_hi(c)));
+}
+template <typename T> inline T ldg(const T* p) { return *p; }
+#endif
+
+// Row word of a read PAIR (one per read position y, shared by every lane that aligns this pair):
+//   bits  0..15  PRMT selector: nibble0 = code0, nibble1 = 8 (sign-replicate → 0x00), nibble2 = 4|code1, nibble3 = 8
+//   bits 16..23  qual0      bits 24..31  qual1
+// so that  cap  = prmt(caps0, caps1, w)          = cap0[code0] | cap1[code1] << 16
+//          qual = prmt(w, 0, 0x4342)             = qual0       | qual1       << 16
+PHMM_HD uint32_t make_row_word(uint32_t half0, uint32_t half1)
+{
+    // half = code | qual << 8  →  bytes [code0, code1, qual0, qual1], then set the selector flag bits
+    return prmt(half0, half1, 0x5140) | 0x8480u;
+}
+constexpr uint32_t kPadRowWord = 0x8480u;
+
+// Column table entry of one haplotype base (prior, go, ge must be in [0,127]; checked by the preparation kernel).
+PHMM_HD ColEntry make_col_entry(const char truth, const char snv_mask, const int snv_prior, const int gap_open, const int gap_extend)
+{
+    const uint32_t ncost = truth == 'N' ? 2u : kCapInf;
+    uint32_t caps = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const char base = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'G' : 'T';
+        uint32_t cap = 0;
+        if (truth != base) {
+            cap = snv_mask == base ? (uint32_t)snv_prior : kCapInf;
+            if (ncost < cap) cap = ncost;
+        }
+        caps |= cap << (8 * b);
+    }
+    ColEntry e;
+    e.x = caps;
+    e.y = (uint32_t)gap_open | ((uint32_t)gap_extend << 8);
+    return e;
+}   // code 0 / qual 0 for both halves: sub = min(0, cap) = 0
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast path: two alignments per thread, s16x2 lanes, band state in registers
+// ---------------------------------------------------------------------------------------------------------
+//
+// rows : shared-memory row words of this lane's read pair, rows[0..L-1] real, rows[L] = kPadRowWord
+// t0/t1: column tables of the two haplotype windows (already offset to the window start); W = L + 2*BAND - 1
+//        entries are read at indices 0..W-1 only
+// Returns best0 | best1 << 16 (each the integer phred score of reference hmm.align()).
+//
+// Column x holds the cells k = x - y, k in [max(0, x-L), min(2B-1, x)], processed in DESCENDING k so that the
+// insertion chain i(x, y+1) ← (x, y) runs through one register (i_run); M[k] / D[k] carry the match / deletion
+// arrivals to the next column in place. Row L uses the pad row word (qual 0 → sub 0), so after the cell
+// (x, L) is processed M[x-L] holds S(x, L) and is never touched again: the end-row minimum is min_k M[k].
+template <int BAND>
+PHMM_HD uint32_t dp_pair(const uint32_t* __restrict__ rows, const int L,
+                                            const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+                                            const uint32_t nucp /* nuc_prior in both halves */)
+{
+    constexpr int K = 2 * BAND;
+    uint32_t M[K], D[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kInf16x2; }
+    const int W = L + K - 1;
+    ColEntry e0 = ldg(t0), e1 = ldg(t1);
+    uint32_t go_prev = 0u, ge_prev = 0u;
+    const uint32_t w0 = rows[0];
+
+#define PHMM_CELL(k)                                                                        \
+    {                                                                                       \
+        const uint32_t w   = rp[-(k)];                                                      \
+        const uint32_t cap = prmt(caps0, caps1, w);                                         \
+        const uint32_t q   = prmt(w, 0u, 0x4342u);                                          \
+        const uint32_t sub = vmin2(q, cap);                                              \
+        const uint32_t m = M[k], d = D[k];                                                  \
+        M[k] = vmin3(m, i_run, d) + sub;                                           \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = vaddmin(d, ge, vmin2(m, i_run) + go); \
+        i_run = vaddmin(i_run, gep, m + gop);                                      \
+    }
+
+    for (int x = 0; x <= W; ++x) {
+        const int xn = (x + 1 < W) ? x + 1 : W - 1;
+        const ColEntry n0 = ldg(t0 + xn), n1 = ldg(t1 + xn);
+        const uint32_t caps0 = e0.x, caps1 = e1.x;
+        const uint32_t go = prmt(e0.y, e1.y, 0x2420u);   // gap_open[x]   of both halves
+        const uint32_t ge = prmt(e0.y, e1.y, 0x2521u);   // gap_extend[x]
+        const uint32_t gop = go_prev + nucp;             // gap_open[x-1] + nuc_prior
+        const uint32_t gep = ge_prev + nucp;             // gap_extend[x-1] + nuc_prior
+        const uint32_t* rp = rows + x;
+        uint32_t i_run = kInf16x2;
+        if (x >= K && x <= L) {
+            // steady state: every cell of the column exists
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) PHMM_CELL(k)
+        } else {
+            // first 2B columns (row 0 enters at k == x) and last 2B-1 columns (rows beyond L are skipped)
+            const int klo = x - L;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                if (k == x) {
+                    // cell (x, 0): S = 0. m(x+1, 1) = sub(x, 0); i(x, 1) = gap_open[x-1] + nuc for odd x, +inf for even x
+                    M[k] = vmin2(prmt(w0, 0u, 0x4342u), prmt(caps0, caps1, w0));
+                    i_run = (x & 1) ? gop : kInf16x2;
+                } else if (k < x && k >= klo) {
+                    PHMM_CELL(k)
+                }
+            }
+        }
+        go_prev = go; ge_prev = ge; e0 = n0; e1 = n1;
+    }
+#undef PHMM_CELL
+    uint32_t best = M[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) best = vmin2(best, M[k]);
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Generic path: int32, any band / alphabet, optional traceback + flank replay (one thread per alignment)
+// ---------------------------------------------------------------------------------------------------------
+
+struct GenericModel {
+    const char*   truth;       // window start
+    const char*   snv_mask;    // window start (never null on this path)
+    const int8_t* snv_prior;
+    const int8_t* gap_open;
+    const int8_t* gap_extend;
+    int nuc_prior;
+};
+
+PHMM_HD int generic_sub(const GenericModel& m, const char* target, const int8_t* quals, int x, int y)
+{
+    const char t = m.truth[x], r = target[y];
+    if (r == t) return 0;
+    int q = quals[y];
+    if (m.snv_mask[x] == r && (int)m.snv_prior[x] < q) q = (int)m.snv_prior[x];
+    return q < (t == 'N' ? 2 : kInf32) ? q : (t == 'N' ? 2 : kInf32);
+}
+
+constexpr int kGenericMaxDiag = 512;   // 2 * 256, the reference's widest band (simd_pair_hmm_wrapper.hpp:207-211)
+
+// Score-only or traceback. State values are (score << 2) | label exactly like the reference (labels only set when TB).
+// Row sweep: Mc[k] / Ic[k] hold the match / insertion arrivals of row y at diagonal k and are overwritten in place
+// with row y+1's (m moves k → k, i moves k → k-1, whose slot is already consumed); d runs along the row in a scalar.
+// bp: TB only — one byte per cell, (L+1) * K bytes at stride bps (cell c lives at bp[c * bps], so a grid of threads
+//     can interleave their scratch for coalescing): bits 0-1 / 2-3 / 4-5 = predecessor label of the M / I / D arrival.
+//     The M bits are stored first (plain store), the I and D bits are OR-ed in later by the same thread.
+// Returns the score; TB additionally returns first_pos, the flank score and the in-flank read-base count
+// (simd_pair_hmm.hpp:165-231 set_alignments fused with :352-430 calculate_flank_score_helper).
+template <bool TB, int MAXK>
+__host__ __device__ inline int generic_align(const int band, const GenericModel& gm, const char* target, const int8_t* quals, const int L,
+                             unsigned char* __restrict__ bp, const size_t bps, const int lhs_flank, const int rhs_flank,
+                             int* first_pos, int* flank_score, int* mask_size)
+{
+    const int K = 2 * band, W = L + K - 1;
+    int Mc[MAXK], Ic[MAXK];
+    constexpr int LM = 0, LI = 1, LD = 3;
+    const int infp = kInf32 << 2;
+    for (int k = 0; k < K; ++k) { Mc[k] = infp | (TB ? LM : 0); Ic[k] = infp | (TB ? LI : 0); }
+    const int nuc = gm.nuc_prior << 2;
+    int best = infp + (1 << 20), best_x = -1;
+    for (int y = 0; y <= L; ++y) {
+        int dd = infp | (TB ? LD : 0);          // d arrival of (y, y): nothing to the left inside the band
+        for (int k = 0; k < K; ++k) {
+            const int x = y + k;
+            int mm = Mc[k];
+            const int ii = Ic[k];
+            int mg;
+            if (y == 0) { mm = 0; mg = (x & 1) ? 0 : infp; } else mg = mm;
+            const int S = min(mm, min(ii, dd));
+            if (y == L && S < best) { best = S; best_x = x; }
+            int dnext = infp | (TB ? LD : 0);
+            if (x < W) {
+                if (y < L) {   // match / mismatch → (x+1, y+1), diagonal k of the next row
+                    const int v = S + (generic_sub(gm, target, quals, x, y) << 2);
+                    if (TB) { bp[((size_t)(y + 1) * K + k) * bps] = (unsigned char)(v & 3); Mc[k] = (v & ~3) | LM; } else Mc[k] = v;
+                }
+                if (k + 1 < K) {   // deletion → (x+1, y)
+                    const int v = min(dd + ((int)gm.gap_extend[x] << 2), min(mg, ii) + ((int)gm.gap_open[x] << 2));
+                    if (TB) { bp[((size_t)y * K + (k + 1)) * bps] |= (unsigned char)((v & 3) << 4); dnext = (v & ~3) | LD; } else dnext = v;
+                }
+            }
+            if (k >= 1 && y < L) {   // insertion → (x, y+1), diagonal k-1 of the next row
+                const int v = min(ii + ((int)gm.gap_extend[x - 1] << 2), mg + ((int)gm.gap_open[x - 1] << 2)) + nuc;
+                if (TB) { bp[((size_t)(y + 1) * K + (k - 1)) * bps] |= (unsigned char)((v & 3) << 2); Ic[k - 1] = (v & ~3) | LI; } else Ic[k - 1] = v;
+            }
+            dd = dnext;
+        }
+        Ic[K - 1] = infp | (TB ? LI : 0);   // top diagonal of the next row has no insertion predecessor
+    }
+    const int score = best >> 2;
+    if (TB) {
+        if (best_x < 0) { *first_pos = -1; *flank_score = 0; *mask_size = 0; return score; }
+        // Walk the path backwards, accumulating the flank score with the forward replay's rules. The replay charges
+        // gap OPEN for the first op of a run (prev_state != state, in forward order) and EXTEND otherwise; walking
+        // backwards the "first op of a run" is the one whose predecessor state differs, which is ns below.
+        const int rhs_begin = W - rhs_flank;
+        int x = best_x, y = L, state = best & 3, fs = 0, ms = 0;
+        bool ok = true;
+        while (y > 0) {
+            const int k = x - y;
+            if (k < 0 || k >= K) { ok = false; break; }
+            const unsigned char b = bp[((size_t)y * K + k) * bps];
+            int ns;
+            if (state == LM) {
+                ns = b & 3; --x; --y;
+                const bool inf = x < lhs_flank || x >= rhs_begin;     // truth_idx of this op == x after the decrement
+                if (inf) {
+                    const char t = gm.truth[x], r = target[y];
+                    if (t != r) {
+                        if (t != 'N') { int q = quals[y]; if (gm.snv_mask[x] == r) q = min(q, (int)gm.snv_prior[x]); fs += q; }
+                        else fs += 2;
+                    }
+                    ++ms;
+                }
+            } else if (state == LI) {
+                ns = (b >> 2) & 3; --y;
+                const bool inf = x < lhs_flank || x >= rhs_begin;     // truth_idx of an insertion == current x
+                if (inf) { fs += (ns == LI ? (int)gm.gap_extend[x - 1] : (int)gm.gap_open[x - 1]) + gm.nuc_prior; ++ms; }
+            } else {
+                ns = (b >> 4) & 3; --x;
+                const bool inf = x < lhs_flank || x >= rhs_begin;
+                if (inf) fs += (ns == LD ? (int)gm.gap_extend[x] : (int)gm.gap_open[x]);
+            }
+            state = ns;
+        }
+        if (!ok) { *first_pos = -1; *flank_score = 0; *mask_size = 0; return score; }
+        *first_pos = x; *flank_score = fs; *mask_size = ms;
+    }
+    return score;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-candidate logic above the kernel (shared by the fused populate kernels; __host__ __device__ for CPU tests)
+// ---------------------------------------------------------------------------------------------------------
+
+struct HapView {            // one haplotype, strand-selected model arrays (HaplotypeLikelihoodModel::evaluate :269-275)
+    const char*   seq;
+    const char*   snv_mask;
+    const int8_t* snv_prior;
+    const int8_t* gap_open;
+    const int8_t* gap_extend;
+    int len;
+};
+struct ReadView {
+    const char*    bases;
+    const uint8_t* quals;
+    int len;
+};
+
+constexpr int kBestInf = 0x7fffffff;   // "no candidate produced a value" == std::numeric_limits<double>::lowest()
+
+enum CandKind { CAND_VALUE = 0, CAND_DP = 1, CAND_DP_FLANK = 2, CAND_LOWEST = 3 };
+
+// haplotype_likelihood_model.cpp:187-201 num_out_of_range_bases (required pad == band, pair_hmm.hpp:33-38)
+PHMM_HD int num_out_of_range_bases(const long long pos, const int read_len, const int hap_len, const int band)
+{
+    if (pos < band) return (int)(band - pos);
+    const long long end = pos + read_len + band;
+    if (end > hap_len) return (int)((long long)hap_len - end);
+    return 0;
+}
+
+// pair_hmm.hpp:275-319 try_naive_evaluate (MutationModel: SNV mask + per-base gap arrays; flanks optional)
+PHMM_HD bool naive_evaluate(const HapView& h, const ReadView& r, const int offset, const bool use_flanks,
+                            const int lhs_flank, const int rhs_flank, int* phred)
+{
+    const char* t = h.seq + offset;
+    const int L = r.len;
+    int i = 0;
+    while (i < L && r.bases[i] == t[i]) ++i;
+    if (i == L) { *phred = 0; return true; }
+    int j = i + 1;
+    while (j < L && r.bases[j] == t[j]) ++j;
+    if (j != L) return false;
+    const int tidx = i + offset;
+    if (use_flanks && (tidx < lhs_flank || tidx >= h.len - rhs_flank)) { *phred = 0; return true; }   // :206-214, :298
+    int mp = r.quals[i];
+    if (h.snv_mask[tidx] == r.bases[i]) { const int cap = (uint8_t)h.snv_prior[tidx]; if (cap < mp) mp = cap; }   // :250-263
+    const int go = h.gap_open[tidx];
+    if (mp <= go) { *phred = mp; return true; }
+    bool eq = true;
+    for (int a = i + 1; a < L; ++a) if (r.bases[a] != h.seq[tidx + (a - i - 1)]) { eq = false; break; }   // :305-308
+    if (eq) { *phred = go; return true; }
+    eq = true;
+    for (int a = i; a < L; ++a) if (r.bases[a] != h.seq[tidx + 1 + (a - i)]) { eq = false; break; }       // :309-312
+    if (eq) { *phred = go; return true; }
+    if (mp <= go + (int)h.gap_extend[tidx]) { *phred = mp; return true; }                                  // :313-315
+    return false;
+}
+
+// hmm::evaluate for one mapping position up to the point where a DP is needed (pair_hmm.hpp:827-841, :723-766).
+//   CAND_VALUE    *out = integer phred penalty (result is -ln10/10 * *out)
+//   CAND_DP       *out = window offset a = max(0, p - band); score-only DP suffices
+//   CAND_DP_FLANK *out = a; traceback + flank discount needed (read within band of a flank, :123-130)
+//   CAND_LOWEST   window does not fit: lowest() (:736-738)
+PHMM_HD CandKind classify_candidate(const HapView& h, const ReadView& r, const int band, const int p,
+                                    const bool shortcut, const bool use_flanks, const int lhs_flank, const int rhs_flank, int* out)
+{
+    if (shortcut) {
+        int phred;
+        if (naive_evaluate(h, r, p, use_flanks, lhs_flank, rhs_flank, &phred)) { *out = phred; return CAND_VALUE; }
+    }
+    const int W = r.len + 2 * band - 1;
+    const int a = p - band > 0 ? p - band : 0;
+    if (a + W > h.len) return CAND_LOWEST;
+    *out = a;
+    const bool near_flank = use_flanks && (p < lhs_flank + band || p + r.len + band > h.len - rhs_flank);
+    return near_flank ? CAND_DP_FLANK : CAND_DP;
+}
+
+// haplotype_likelihood_model.cpp:211-259 max_score, unrolled into "slots" so that a warp can walk the candidates of
+// 32 (haplotype, read) pairs in lock-step: slot c < npos is the c-th listed mapping position, slot npos is the read's
+// original position (if it was not listed), slot npos+1 is the shifted fallback (only if nothing was in range).
+// Returns 1 with *p set when the slot yields a position to evaluate, 0 when it yields nothing, and -1 for
+// ShortHaplotypeError (*p = required extension).
+struct EnumState { bool mapped; bool has_in_range; };
+
+PHMM_HD int candidate_slot(const int c, const int npos, const int32_t* pos, const long long orig,
+                           const int read_len, const int hap_len, const int band, EnumState& st, int* p)
+{
+    if (c < npos) {
+        const int q = pos[c];
+        if (q == orig) st.mapped = true;                                               // :224-226
+        if (num_out_of_range_bases(q, read_len, hap_len, band) == 0) { st.has_in_range = true; *p = q; return 1; }
+        return 0;
+    }
+    if (c == npos) {                                                                   // :233-237
+        if (!st.mapped && num_out_of_range_bases(orig, read_len, hap_len, band) == 0) { st.has_in_range = true; *p = (int)orig; return 1; }
+        return 0;
+    }
+    if (c == npos + 1 && !st.has_in_range) {                                           // :238-256
+        const int min_shift = num_out_of_range_bases(orig, read_len, hap_len, band);
+        long long fin = orig;
+        if (min_shift > 0) {
+            fin += min_shift;
+            if (num_out_of_range_bases(fin, read_len, hap_len, band) != 0) { *p = min_shift; return -1; }
+        } else {
+            const long long left = -(long long)min_shift;
+            if (orig >= left) fin -= left;
+            else { *p = (int)(left - orig); return -1; }
+        }
+        *p = (int)fin;
+        return 1;
+    }
+    return 0;
+}
+
+// pair_hmm.hpp:755-764: combine the traceback DP's score with the flank replay (window coordinates: :573-588)
+PHMM_HD void window_flanks(const int a, const int W, const int hap_len, const int lhs_flank, const int rhs_flank, int* lhs, int* rhs)
+{
+    *lhs = lhs_flank < a ? 0 : lhs_flank - a;
+    if (a + W < hap_len - rhs_flank) *rhs = 0;
+    else { const int v = rhs_flank + a + W - hap_len; *rhs = v < 0 ? 0 : v; }
+}
+PHMM_HD int discount_flank(const int score, int flank, const int read_len, const int mask_size, const int first_pos)
+{
+    if (first_pos == -1) return kBestInf;               // :750-752 overflow → lowest()
+    if (read_len - mask_size < 2) flank = 0;            // :757-759 min_explained_bases
+    return flank <= score ? score - flank : score + flank;   // :760-764
+}
+
+// haplotype_likelihood_model.cpp:285-303: mapping-quality mixing and the > -1e-15 clamp, from the integer penalty.
+__host__ __device__ inline double finish_likelihood(const int best, const bool use_mapq, int mapq, const int mapq_cap, const int mapq_trigger)
+{
+    const double c = 0.230258509299404568401799145468436420760110148862877297603;   // utils/maths.hpp:41
+    const double ln_given_mapped = best == kBestInf ? -1.7976931348623157e308 : -c * (double)best;
+    if (use_mapq) {
+        if (mapq_trigger >= 0 && mapq >= mapq_trigger) mapq = mapq_cap;
+        const double ln_miss = -c * (double)mapq;
+        const double ln_mapped = log(1.0 - exp(ln_miss));
+        const double a = ln_mapped + ln_given_mapped, b = ln_miss;
+        const double lo = b < a ? b : a, hi = b < a ? a : b;          // std::minmax (utils/maths.hpp:294-298)
+        const double r = hi + log1p(exp(lo - hi));
+        return r > -1e-15 ? 0.0 : r;
+    }
+    return ln_given_mapped > -1e-15 ? 0.0 : ln_given_mapped;
+}
+
+} // namespace phmm

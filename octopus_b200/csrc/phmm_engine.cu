@@ -1,0 +1,577 @@
+// C ABI of the B200 pair-HMM engine (include/phmm_b200.h): host-side orchestration only. All arithmetic of the
+// hot path runs in the kernels of phmm_kernels.cuh; there is no CPU fallback — without a usable GPU every
+// computing entry point returns PHMM_ERR_CUDA.
+#include "../../include/phmm_b200.h"
+#include "phmm_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace phmm;
+
+namespace {
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+int round_band(int requested)
+{
+    // simd_pair_hmm_wrapper.hpp:218-241: smallest supported band >= request, from {8,16,32,64,128,256}
+    for (int b = 8; b <= 256; b <<= 1) if (requested <= b) return b;
+    return -1;
+}
+
+} // namespace
+
+struct phmm_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches_last = 0, launches_total = 0;
+    double last_dp_ms = 0.0;
+    int64_t last_dp_cells = 0;
+    // device copies of caller arrays (host-space calls)
+    DBuf h_off, h_seq, h_mf, h_pf, h_mr, h_pr, h_go, h_ge, h_begin;
+    DBuf r_off, r_bases, r_quals, r_mapq, r_rev, r_begin;
+    DBuf c_off, c_pos;
+    // derived / scratch
+    DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, bp;
+    DBuf tasks_lane, tasks_generic, works, scores;
+    std::vector<int2> info_host;
+};
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+            return _e == cudaErrorMemoryAllocation ? PHMM_ERR_NOMEM : PHMM_ERR_CUDA;               \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCHED() do { ++e->launches_last; ++e->launches_total; } while (0)
+
+namespace {
+
+// Bring one caller array into device memory (copy for host space, alias for device space).
+template <typename T>
+int stage(phmm_engine* e, DBuf& buf, const T* src, size_t count, int space, const T** dev)
+{
+    if (src == nullptr) { *dev = nullptr; return PHMM_OK; }
+    if (space == PHMM_SPACE_DEVICE) { *dev = src; return PHMM_OK; }
+    CU(buf.ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    *dev = buf.as<T>();
+    return PHMM_OK;
+}
+
+struct Staged {
+    DevHaps hp {};
+    DevReads rd {};
+    long long hap_bases = 0, read_bases = 0;
+    std::vector<long long> hap_off_host, read_off_host;   // offsets on the host (needed for sizes / scheduling)
+};
+
+int fetch_offsets(phmm_engine* e, const int64_t* off, int n, int space, std::vector<long long>& out)
+{
+    out.resize((size_t)n + 1);
+    if (space == PHMM_SPACE_HOST) {
+        for (int i = 0; i <= n; ++i) out[i] = off[i];
+    } else {
+        static_assert(sizeof(long long) == sizeof(int64_t), "");
+        CU(cudaMemcpyAsync(out.data(), off, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return PHMM_OK;
+}
+
+// Upload (or alias) the batch and run the preparation kernels: column tables, row half-words, read info.
+int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* reads, int space, Staged& s)
+{
+    if (!haps || !reads || haps->n <= 0 || reads->n <= 0 || !haps->off || !reads->off) {
+        e->err = "empty or null haplotype / read block";
+        return PHMM_ERR_INVALID;
+    }
+    if (!haps->seq || !haps->snv_mask_fwd || !haps->snv_prior_fwd || !haps->snv_mask_rev || !haps->snv_prior_rev ||
+        !haps->gap_open || !haps->gap_extend || !reads->bases || !reads->quals) {
+        e->err = "null per-base array";
+        return PHMM_ERR_INVALID;
+    }
+    int rc;
+    if ((rc = fetch_offsets(e, haps->off, haps->n, space, s.hap_off_host)) != PHMM_OK) return rc;
+    if ((rc = fetch_offsets(e, reads->off, reads->n, space, s.read_off_host)) != PHMM_OK) return rc;
+    s.hap_bases = s.hap_off_host[haps->n];
+    s.read_bases = s.read_off_host[reads->n];
+    if (s.hap_off_host[0] != 0 || s.read_off_host[0] != 0 || s.hap_bases <= 0 || s.read_bases <= 0) {
+        e->err = "offset arrays must start at 0 and be increasing";
+        return PHMM_ERR_INVALID;
+    }
+    DevHaps& hp = s.hp;
+    DevReads& rd = s.rd;
+    hp.n = haps->n; rd.n = reads->n;
+    const long long* tmp_ll;
+    if ((rc = stage(e, e->h_off, (const long long*)haps->off, (size_t)haps->n + 1, space, &tmp_ll))) return rc; hp.off = tmp_ll;
+    if ((rc = stage(e, e->h_seq, haps->seq, s.hap_bases, space, &hp.seq))) return rc;
+    if ((rc = stage(e, e->h_mf, haps->snv_mask_fwd, s.hap_bases, space, &hp.mask_f))) return rc;
+    if ((rc = stage(e, e->h_pf, haps->snv_prior_fwd, s.hap_bases, space, &hp.prior_f))) return rc;
+    if ((rc = stage(e, e->h_mr, haps->snv_mask_rev, s.hap_bases, space, &hp.mask_r))) return rc;
+    if ((rc = stage(e, e->h_pr, haps->snv_prior_rev, s.hap_bases, space, &hp.prior_r))) return rc;
+    if ((rc = stage(e, e->h_go, haps->gap_open, s.hap_bases, space, &hp.gap_open))) return rc;
+    if ((rc = stage(e, e->h_ge, haps->gap_extend, s.hap_bases, space, &hp.gap_extend))) return rc;
+    if ((rc = stage(e, e->h_begin, (const long long*)haps->begin, haps->n, space, &tmp_ll))) return rc; hp.begin = tmp_ll;
+    if ((rc = stage(e, e->r_off, (const long long*)reads->off, (size_t)reads->n + 1, space, &tmp_ll))) return rc; rd.off = tmp_ll;
+    if ((rc = stage(e, e->r_bases, reads->bases, s.read_bases, space, &rd.bases))) return rc;
+    if ((rc = stage(e, e->r_quals, reads->quals, s.read_bases, space, &rd.quals))) return rc;
+    if ((rc = stage(e, e->r_mapq, reads->mapq, reads->n, space, &rd.mapq))) return rc;
+    if ((rc = stage(e, e->r_rev, reads->reverse, reads->n, space, &rd.reverse))) return rc;
+    if ((rc = stage(e, e->r_begin, (const long long*)reads->begin, reads->n, space, &tmp_ll))) return rc; rd.begin = tmp_ll;
+
+    CU(e->tab_f.ensure((size_t)s.hap_bases * sizeof(ColEntry)));
+    CU(e->tab_r.ensure((size_t)s.hap_bases * sizeof(ColEntry)));
+    CU(e->rowhalf.ensure((size_t)s.read_bases * sizeof(uint16_t)));
+    CU(e->info.ensure((size_t)rd.n * sizeof(int2)));
+    CU(e->flags.ensure(64));
+    CU(cudaMemsetAsync(e->flags.p, 0, 64, e->stream));
+    k_build_tables<<<(unsigned)((s.hap_bases + 255) / 256), 256, 0, e->stream>>>(s.hap_bases, hp.seq, hp.mask_f, hp.prior_f, hp.mask_r, hp.prior_r,
+                                                                                 hp.gap_open, hp.gap_extend, e->tab_f.as<ColEntry>(),
+                                                                                 e->tab_r.as<ColEntry>(), e->flags.as<int>());
+    LAUNCHED();
+    k_read_info<<<(unsigned)(((long long)rd.n * 32 + 255) / 256), 256, 0, e->stream>>>(rd.n, rd.off, rd.bases, rd.quals, e->rowhalf.as<uint16_t>(),
+                                                                                       e->info.as<int2>());
+    LAUNCHED();
+    CU(cudaGetLastError());
+    hp.tab_f = e->tab_f.as<ColEntry>(); hp.tab_r = e->tab_r.as<ColEntry>();
+    rd.rowhalf = e->rowhalf.as<uint16_t>(); rd.info = e->info.as<int2>();
+    // read info is needed on the host for scheduling (8 bytes per read)
+    e->info_host.resize(rd.n);
+    CU(cudaMemcpyAsync(e->info_host.data(), e->info.p, (size_t)rd.n * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+    int flags_host[1] = {0};
+    CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (flags_host[0] & 1) {
+        e->err = "snv prior / gap penalty outside [0,127]";
+        return PHMM_ERR_INVALID;
+    }
+    return PHMM_OK;
+}
+
+template <typename F>
+int fast_smem_attr(phmm_engine* e, F kernel, size_t bytes)
+{
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PHMM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* phmm_version(void) { return "octopus_b200 phmm 0.1 (sm_100a)"; }
+
+void phmm_default_config(phmm_config* c)
+{
+    if (!c) return;
+    c->max_indel_error = 8;                 // HaplotypeLikelihoodModel::Config defaults, haplotype_likelihood_model.hpp:36-44
+    c->use_int_scores = 0;
+    c->use_mapping_quality = 1;
+    c->mapping_quality_cap = 120;
+    c->mapping_quality_cap_trigger = -1;
+    c->use_flank_state = 1;
+    c->nuc_prior = 2;
+    c->disable_naive_shortcut = 0;
+}
+
+static std::string g_create_error;
+
+int phmm_create(phmm_engine** out, int device)
+{
+    if (!out) return PHMM_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+        return PHMM_ERR_CUDA;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= count) { g_create_error = "device ordinal out of range"; return PHMM_ERR_INVALID; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_create_error = "cudaGetDeviceProperties failed"; return PHMM_ERR_CUDA; }
+    if (prop.major < 10) {
+        g_create_error = "this library is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        return PHMM_ERR_CUDA;
+    }
+    phmm_engine* e = new phmm_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+        g_create_error = "stream / event creation failed";
+        delete e;
+        return PHMM_ERR_CUDA;
+    }
+    *out = e;
+    return PHMM_OK;
+}
+
+void phmm_destroy(phmm_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    DBuf* all[] = {&e->h_off, &e->h_seq, &e->h_mf, &e->h_pf, &e->h_mr, &e->h_pr, &e->h_go, &e->h_ge, &e->h_begin,
+                   &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
+                   &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
+                   &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores};
+    for (DBuf* b : all) b->release();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char* phmm_last_error(const phmm_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int64_t phmm_launch_count(const phmm_engine* e, int total) { return e ? (total ? e->launches_total : e->launches_last) : 0; }
+double phmm_last_dp_kernel_ms(const phmm_engine* e) { return e ? e->last_dp_ms : 0.0; }
+int64_t phmm_last_dp_cells(const phmm_engine* e) { return e ? e->last_dp_cells : 0; }
+
+// -------------------------------------------------------------------------------------------------------------
+// phmm_align_scores
+// -------------------------------------------------------------------------------------------------------------
+int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prior,
+                      const phmm_haplotypes* haps, const phmm_reads* reads,
+                      const phmm_task* tasks, int64_t n_tasks, int32_t* scores, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    if (band > 256) { e->err = "band > 256"; return PHMM_ERR_BAND; }
+    if (band < 8 || (band & (band - 1))) { e->err = "band must be one of 8,16,...,256"; return PHMM_ERR_INVALID; }
+    if (precision_bits != 16 && precision_bits != 32) { e->err = "precision_bits must be 16 or 32"; return PHMM_ERR_INVALID; }
+    if (nuc_prior < 0 || nuc_prior > 127) { e->err = "nuc_prior outside [0,127]"; return PHMM_ERR_INVALID; }
+    if (n_tasks < 0 || n_tasks > 0x7fffffff) { e->err = "task count out of range"; return PHMM_ERR_INVALID; }
+    if (n_tasks == 0) return PHMM_OK;
+    if (!tasks || !scores) { e->err = "null tasks / scores"; return PHMM_ERR_INVALID; }
+    Staged s;
+    int rc = stage_batch(e, haps, reads, space, s);
+    if (rc != PHMM_OK) return rc;
+    // tasks on the host for scheduling
+    std::vector<phmm_task> th;
+    const phmm_task* tk = tasks;
+    if (space == PHMM_SPACE_DEVICE) {
+        th.resize(n_tasks);
+        CU(cudaMemcpyAsync(th.data(), tasks, (size_t)n_tasks * sizeof(phmm_task), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        tk = th.data();
+    }
+    const int n = (int)n_tasks, H = s.hp.n, R = s.rd.n;
+    std::vector<int> fast_idx;
+    std::vector<GenericTask> gen;
+    const bool fast_ok = band <= 32 && precision_bits == 16;
+    int64_t cells = 0;
+    int Lmax = 1;
+    for (int j = 0; j < n; ++j) {
+        const phmm_task& t = tk[j];
+        if (t.read < 0 || t.read >= R || t.hap < 0 || t.hap >= H) { e->err = "task index out of range"; return PHMM_ERR_INVALID; }
+        const int L = e->info_host[t.read].x;
+        const long long hl = s.hap_off_host[t.hap + 1] - s.hap_off_host[t.hap];
+        if (L < 1 || t.win_off < 0 || (long long)t.win_off + L + 2 * band - 1 > hl) { e->err = "task window outside the haplotype"; return PHMM_ERR_INVALID; }
+        cells += 2LL * (L + band) * band;
+        if (fast_ok && e->info_host[t.read].y == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
+        else gen.push_back(GenericTask {t.read, t.hap, t.win_off, t.reverse ? 1 : 0, j});
+    }
+    e->last_dp_cells = cells;
+    CU(e->scores.ensure((size_t)n * sizeof(int)));
+    int* d_scores = space == PHMM_SPACE_DEVICE ? scores : e->scores.as<int>();
+
+    if (!fast_idx.empty()) {
+        // group by (length, read); chunks of 32 tasks of one read; chunks of equal length are paired into one warp
+        std::sort(fast_idx.begin(), fast_idx.end(), [&](int a, int b) {
+            const int la = e->info_host[tk[a].read].x, lb = e->info_host[tk[b].read].x;
+            if (la != lb) return la < lb;
+            if (tk[a].read != tk[b].read) return tk[a].read < tk[b].read;
+            return a < b;
+        });
+        std::vector<LaneTask> lane(fast_idx.size());
+        struct Chunk { int read, first, n, L; };
+        std::vector<Chunk> chunks;
+        for (size_t i = 0; i < fast_idx.size(); ++i) {
+            const phmm_task& t = tk[fast_idx[i]];
+            lane[i] = LaneTask {s.hap_off_host[t.hap] + t.win_off, t.reverse ? 1 : 0, fast_idx[i]};
+            if (chunks.empty() || chunks.back().read != t.read || chunks.back().n == 32)
+                chunks.push_back(Chunk {t.read, (int)i, 0, e->info_host[t.read].x});
+            ++chunks.back().n;
+        }
+        std::vector<WarpWork> works;
+        for (size_t c = 0; c < chunks.size();) {
+            WarpWork w {};
+            w.read0 = chunks[c].read; w.first0 = chunks[c].first; w.n0 = chunks[c].n; w.L = chunks[c].L;
+            w.read1 = -1; w.first1 = chunks[c].first; w.n1 = 0;
+            if (c + 1 < chunks.size() && chunks[c + 1].L == w.L) {
+                w.read1 = chunks[c + 1].read; w.first1 = chunks[c + 1].first; w.n1 = chunks[c + 1].n;
+                c += 2;
+            } else c += 1;
+            works.push_back(w);
+        }
+        CU(e->tasks_lane.ensure(lane.size() * sizeof(LaneTask)));
+        CU(e->works.ensure(works.size() * sizeof(WarpWork)));
+        CU(cudaMemcpyAsync(e->tasks_lane.p, lane.data(), lane.size() * sizeof(LaneTask), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->works.p, works.data(), works.size() * sizeof(WarpWork), cudaMemcpyHostToDevice, e->stream));
+        const int row_stride = (Lmax + 2) & ~1;
+        const size_t smem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(uint32_t);
+        const int nw = (int)works.size();
+        const unsigned grid = (unsigned)((nw + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
+        const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
+        CU(cudaEventRecord(e->ev0, e->stream));
+        switch (band) {
+            case 8:
+                if ((rc = fast_smem_attr(e, k_packed_tasks<8>, smem))) return rc;
+                k_packed_tasks<8><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores);
+                break;
+            case 16:
+                if ((rc = fast_smem_attr(e, k_packed_tasks<16>, smem))) return rc;
+                k_packed_tasks<16><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores);
+                break;
+            default:
+                if ((rc = fast_smem_attr(e, k_packed_tasks<32>, smem))) return rc;
+                k_packed_tasks<32><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores);
+                break;
+        }
+        LAUNCHED();
+        CU(cudaEventRecord(e->ev1, e->stream));
+        CU(cudaGetLastError());
+    }
+    if (!gen.empty()) {
+        CU(e->tasks_generic.ensure(gen.size() * sizeof(GenericTask)));
+        CU(cudaMemcpyAsync(e->tasks_generic.p, gen.data(), gen.size() * sizeof(GenericTask), cudaMemcpyHostToDevice, e->stream));
+        const int ng = (int)gen.size();
+        if (fast_idx.empty()) CU(cudaEventRecord(e->ev0, e->stream));
+        if (band <= 32) k_generic_tasks<64><<<(ng + 63) / 64, 64, 0, e->stream>>>(e->tasks_generic.as<GenericTask>(), ng, s.hp, s.rd, band, nuc_prior, d_scores);
+        else k_generic_tasks<kGenericMaxDiag><<<(ng + 63) / 64, 64, 0, e->stream>>>(e->tasks_generic.as<GenericTask>(), ng, s.hp, s.rd, band, nuc_prior, d_scores);
+        LAUNCHED();
+        if (fast_idx.empty()) CU(cudaEventRecord(e->ev1, e->stream));
+        CU(cudaGetLastError());
+    }
+    if (space == PHMM_SPACE_HOST) CU(cudaMemcpyAsync(scores, d_scores, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_dp_ms = ms;
+    return PHMM_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// phmm_populate
+// -------------------------------------------------------------------------------------------------------------
+int phmm_populate(phmm_engine* e, const phmm_config* cfg,
+                  const phmm_haplotypes* haps, const phmm_reads* reads,
+                  const phmm_positions* positions, const phmm_flank_state* flank,
+                  double* out, int32_t* status, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    if (!cfg || !out) { e->err = "null config / output"; return PHMM_ERR_INVALID; }
+    if (cfg->max_indel_error > 256) { e->err = "max_indel_error > 256"; return PHMM_ERR_BAND; }
+    const int band = round_band(std::max(1, cfg->max_indel_error));
+    if (cfg->nuc_prior < 0 || cfg->nuc_prior > 127) { e->err = "nuc_prior outside [0,127]"; return PHMM_ERR_INVALID; }
+    if (!reads || !reads->mapq || !reads->reverse) { e->err = "reads->mapq / reads->reverse required"; return PHMM_ERR_INVALID; }
+    Staged s;
+    int rc = stage_batch(e, haps, reads, space, s);
+    if (rc != PHMM_OK) return rc;
+    const int H = s.hp.n, R = s.rd.n;
+    const long long HR = (long long)H * R;
+
+    PopParams p {};
+    p.hp = s.hp; p.rd = s.rd;
+    p.band = band; p.nuc_prior = cfg->nuc_prior;
+    p.shortcut = cfg->disable_naive_shortcut ? 0 : 1;
+    p.use_flanks = (flank && flank->has_flank && cfg->use_flank_state) ? 1 : 0;
+    p.lhs_flank = p.use_flanks ? (int)flank->lhs_flank : 0;
+    p.rhs_flank = p.use_flanks ? (int)flank->rhs_flank : 0;
+    int max_cand = 1;
+    if (positions && positions->off && positions->pos) {
+        // candidate lists: CSR offsets on the host (to size the copy), arrays on the device
+        std::vector<long long> ends(1);
+        if (space == PHMM_SPACE_HOST) ends[0] = positions->off[HR];
+        else { CU(cudaMemcpyAsync(ends.data(), positions->off + HR, sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream)); CU(cudaStreamSynchronize(e->stream)); }
+        const long long* po; const int32_t* pv;
+        if ((rc = stage(e, e->c_off, (const long long*)positions->off, (size_t)HR + 1, space, &po))) return rc;
+        if ((rc = stage(e, e->c_pos, positions->pos, (size_t)std::max<long long>(ends[0], 1), space, &pv))) return rc;
+        p.pos_off = po; p.pos = pv;
+        max_cand = 12;   // kmer mapper emits <= 10 (haplotype_likelihood_array.hpp:103-104) + original + fallback
+    } else {
+        max_cand = 2;
+    }
+
+    // scheduling: equal-length read pairs for the packed kernel, everything else to the generic kernel
+    const bool fast_ok = band <= 32 && !cfg->use_int_scores;
+    std::vector<int> generic_reads, pairs;
+    int Lmax_fast = 1, Lmax_all = 1;
+    {
+        std::vector<int> order;
+        order.reserve(R);
+        for (int r = 0; r < R; ++r) {
+            const int2 inf = e->info_host[r];
+            Lmax_all = std::max(Lmax_all, inf.x);
+            if (inf.x < 1) { e->err = "empty read"; return PHMM_ERR_INVALID; }
+            if (fast_ok && inf.y == 0) { order.push_back(r); Lmax_fast = std::max(Lmax_fast, inf.x); }
+            else generic_reads.push_back(r);
+        }
+        // counting sort by length keeps the pairing O(R)
+        std::vector<int> count((size_t)Lmax_fast + 2, 0);
+        for (int r : order) ++count[e->info_host[r].x + 1];
+        for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+        std::vector<int> sorted(order.size());
+        for (int r : order) sorted[count[e->info_host[r].x]++] = r;
+        pairs.reserve(sorted.size() + 2);
+        for (size_t i = 0; i < sorted.size();) {
+            const int r0 = sorted[i];
+            if (i + 1 < sorted.size() && e->info_host[sorted[i + 1]].x == e->info_host[r0].x) { pairs.push_back(r0); pairs.push_back(sorted[i + 1]); i += 2; }
+            else { pairs.push_back(r0); pairs.push_back(-1); i += 1; }
+        }
+    }
+    const int n_pairs = (int)(pairs.size() / 2), n_generic = (int)generic_reads.size();
+
+    CU(e->best.ensure((size_t)HR * sizeof(int)));
+    CU(e->status.ensure((size_t)HR * sizeof(int)));
+    CU(e->counters.ensure(256));
+    CU(cudaMemsetAsync(e->counters.p, 0, 256, e->stream));
+    CU(cudaMemsetAsync(e->status.p, 0, (size_t)HR * sizeof(int), e->stream));
+    k_fill_int<<<(unsigned)((HR + 255) / 256), 256, 0, e->stream>>>(e->best.as<int>(), HR, kBestInf);
+    LAUNCHED();
+    p.best = e->best.as<int>();
+    p.status = e->status.as<int>();
+    p.flags = e->flags.as<int>();
+    int* counters = e->counters.as<int>();
+    p.pair_cursor = counters + 0;
+    p.slow_count = counters + 1;
+    if (n_pairs) {
+        CU(e->pairs.ensure(pairs.size() * sizeof(int)));
+        CU(cudaMemcpyAsync(e->pairs.p, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    }
+    if (n_generic) {
+        CU(e->generic_reads.ensure(generic_reads.size() * sizeof(int)));
+        CU(cudaMemcpyAsync(e->generic_reads.p, generic_reads.data(), generic_reads.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    }
+
+    // near-flank (traceback) queue, processed tile by tile so that its worst case fits the budget
+    const long long slow_budget = 8LL << 20;   // entries (16 bytes each)
+    long long reads_per_tile = R;
+    const int slow_threads = e->sm_count * 256;
+    if (p.use_flanks) {
+        reads_per_tile = std::max<long long>(2, slow_budget / ((long long)H * max_cand));
+        p.slow_cap = (int)std::min<long long>(slow_budget, (long long)H * max_cand * std::min<long long>(reads_per_tile, R));
+        CU(e->slow.ensure((size_t)p.slow_cap * sizeof(int4)));
+        p.slow = e->slow.as<int4>();
+        CU(e->bp.ensure((size_t)slow_threads * (size_t)(Lmax_all + 1) * (size_t)(2 * band)));
+    } else {
+        p.slow_cap = 0;
+        CU(e->slow.ensure(sizeof(int4)));
+        p.slow = e->slow.as<int4>();
+    }
+
+    p.row_stride = (Lmax_fast + 2) & ~1;
+    const size_t smem = (size_t)kFastWarpsPerBlock * (p.row_stride + 4 * kQueueCap) * sizeof(uint32_t);
+    int blocks_per_sm = 1;
+    if (n_pairs) {
+        switch (band) {
+            case 8:  if ((rc = fast_smem_attr(e, k_populate_fast<8>, smem))) return rc;
+                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<8>, kFastWarpsPerBlock * 32, smem)); break;
+            case 16: if ((rc = fast_smem_attr(e, k_populate_fast<16>, smem))) return rc;
+                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<16>, kFastWarpsPerBlock * 32, smem)); break;
+            default: if ((rc = fast_smem_attr(e, k_populate_fast<32>, smem))) return rc;
+                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<32>, kFastWarpsPerBlock * 32, smem)); break;
+        }
+        if (blocks_per_sm < 1) { e->err = "fast kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; }
+    }
+
+    const long long pairs_per_tile = std::max<long long>(1, reads_per_tile / 2);
+    bool timed = false;
+    for (long long p0 = 0, g0 = 0; p0 < n_pairs || g0 < n_generic;) {
+        if (p0 < n_pairs) {
+            const int np = (int)std::min<long long>(pairs_per_tile, n_pairs - p0);
+            p.pair_reads = e->pairs.as<int>() + 2 * p0;
+            p.n_pairs = np;
+            CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
+            const int want_blocks = (np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock;
+            const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
+            if (!timed) CU(cudaEventRecord(e->ev0, e->stream));
+            switch (band) {
+                case 8:  k_populate_fast<8><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+                case 16: k_populate_fast<16><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+                default: k_populate_fast<32><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+            }
+            LAUNCHED();
+            if (!timed) { CU(cudaEventRecord(e->ev1, e->stream)); timed = true; }
+            p0 += np;
+        } else {
+            const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);
+            p.generic_reads = e->generic_reads.as<int>() + g0;
+            p.n_generic = ng;
+            const long long threads = (long long)ng * H;
+            if (!timed) CU(cudaEventRecord(e->ev0, e->stream));
+            if (band <= 32) k_populate_generic<64><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
+            else k_populate_generic<kGenericMaxDiag><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
+            LAUNCHED();
+            if (!timed) { CU(cudaEventRecord(e->ev1, e->stream)); timed = true; }
+            g0 += ng;
+        }
+        if (p.use_flanks) {
+            if (band <= 32) k_slow_flank<64><<<e->sm_count, 256, 0, e->stream>>>(p, e->bp.as<unsigned char>());
+            else k_slow_flank<kGenericMaxDiag><<<e->sm_count, 256, 0, e->stream>>>(p, e->bp.as<unsigned char>());
+            LAUNCHED();
+            CU(cudaMemsetAsync(p.slow_count, 0, sizeof(int), e->stream));
+        }
+        CU(cudaGetLastError());
+    }
+
+    CU(e->out.ensure((size_t)HR * sizeof(double)));
+    double* d_out = space == PHMM_SPACE_DEVICE ? out : e->out.as<double>();
+    k_epilogue<<<(unsigned)((HR + 255) / 256), 256, 0, e->stream>>>(p.best, p.status, s.rd.mapq, H, R, cfg->use_mapping_quality,
+                                                                    cfg->mapping_quality_cap, cfg->mapping_quality_cap_trigger, d_out);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    if (space == PHMM_SPACE_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, (size_t)HR * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (status) CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    } else if (status) {
+        CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+    }
+    int flags_host[1] = {0};
+    CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    if (timed && cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_dp_ms = ms;
+    // GCUPS numerator when every pair runs exactly one DP (benchmark mode); otherwise an upper bound on DP work
+    {
+        int64_t cells = 0;
+        for (int r = 0; r < R; ++r) cells += 2LL * (e->info_host[r].x + band) * band;
+        e->last_dp_cells = cells * H;
+    }
+    if (flags_host[0] & 4) { e->err = "near-flank queue overflow"; return PHMM_ERR_NOMEM; }
+    if (flags_host[0] & 2) { e->err = "Haplotype is too short for alignment"; return PHMM_ERR_SHORT_HAPLOTYPE; }
+    return PHMM_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,392 @@
+// Kernels of the B200 pair-HMM engine. See phmm_device.cuh for the DP cores and DESIGN.md for the data layout.
+#pragma once
+
+#include "phmm_device.cuh"
+
+namespace phmm {
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident batch (struct of arrays, all pointers into HBM)
+// ---------------------------------------------------------------------------------------------------------
+struct DevHaps {
+    int n;
+    const long long* off;
+    const char* seq;
+    const char* mask_f; const int8_t* prior_f;
+    const char* mask_r; const int8_t* prior_r;
+    const int8_t* gap_open; const int8_t* gap_extend;
+    const long long* begin;     // may be null
+    const ColEntry* tab_f;      // column tables, same indexing as seq
+    const ColEntry* tab_r;
+};
+struct DevReads {
+    int n;
+    const long long* off;
+    const char* bases;
+    const uint8_t* quals;
+    const uint8_t* mapq;
+    const uint8_t* reverse;
+    const long long* begin;
+    const uint16_t* rowhalf;    // code | qual << 8 per base, same indexing as bases
+    const int2* info;           // per read: .x = length, .y = flags
+};
+constexpr int kReadNonACGT  = 1;   // read holds a byte outside ACGT → generic path
+constexpr int kReadUnsafe16 = 2;   // sum of qualities too large for a 16-bit lane, or a quality > 127
+constexpr int kReadTooLong  = 4;   // longer than the fast path's shared-memory row budget
+
+constexpr int kFastMaxReadLen = 1023;
+
+// ---------------------------------------------------------------------------------------------------------
+// Preparation kernels
+// ---------------------------------------------------------------------------------------------------------
+
+// One thread per haplotype base: the two strand tables. flags[0] |= 1 if a prior / gap penalty is outside [0,127].
+__global__ void k_build_tables(const long long n_bases, const char* __restrict__ seq,
+                               const char* __restrict__ mask_f, const int8_t* __restrict__ prior_f,
+                               const char* __restrict__ mask_r, const int8_t* __restrict__ prior_r,
+                               const int8_t* __restrict__ go, const int8_t* __restrict__ ge,
+                               ColEntry* __restrict__ tab_f, ColEntry* __restrict__ tab_r, int* __restrict__ flags)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bases) return;
+    const int pf = prior_f[i], pr = prior_r[i], o = go[i], e = ge[i];
+    if ((pf | pr | o | e) < 0) atomicOr(flags, 1);
+    tab_f[i] = make_col_entry(seq[i], mask_f[i], pf & 127, o & 127, e & 127);
+    tab_r[i] = make_col_entry(seq[i], mask_r[i], pr & 127, o & 127, e & 127);
+}
+
+// One warp per read: row half-words, length and eligibility flags.
+__global__ void k_read_info(const int n_reads, const long long* __restrict__ off, const char* __restrict__ bases,
+                            const uint8_t* __restrict__ quals, uint16_t* __restrict__ rowhalf, int2* __restrict__ info)
+{
+    const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const long long b = off[r];
+    const int L = (int)(off[r + 1] - b);
+    int flags = 0, qsum = 0;
+    for (int y = lane; y < L; y += 32) {
+        const int c = base_code(bases[b + y]);
+        const int q = quals[b + y];
+        if (c < 0) flags |= kReadNonACGT;
+        if (q > 127) flags |= kReadUnsafe16;
+        qsum += q;
+        rowhalf[b + y] = (uint16_t)((c < 0 ? 0 : c) | (q << 8));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+        qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+    }
+    if (qsum > kMaxScore16) flags |= kReadUnsafe16;
+    if (L > kFastMaxReadLen || L < 1) flags |= kReadTooLong;
+    if (lane == 0) info[r] = make_int2(L, flags);
+}
+
+// Cooperative fill of one warp's shared row words for the read pair (r0, r1); r1 < 0 → second half padded.
+__device__ __forceinline__ void fill_rows(uint32_t* rows, const DevReads& rd, const int r0, const int r1, const int L, const int lane)
+{
+    const uint16_t* h0 = rd.rowhalf + rd.off[r0];
+    const uint16_t* h1 = r1 >= 0 ? rd.rowhalf + rd.off[r1] : nullptr;
+    for (int y = lane; y < L; y += 32) rows[y] = make_row_word(h0[y], h1 ? (uint32_t)h1[y] : 0u);
+    if (lane == 0) rows[L] = kPadRowWord;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Raw kernel boundary (phmm_align_scores): explicit task lists
+// ---------------------------------------------------------------------------------------------------------
+
+struct LaneTask {          // one alignment: column-table index of its window start, strand, output slot
+    long long tab_index;
+    int reverse;
+    int out_idx;
+};
+struct WarpWork {          // one warp: read pair (equal length) and the lane-task ranges of its two halves
+    int read0, read1;      // read1 < 0: second half empty
+    int first0, n0;        // lane tasks of read0: tasks[first0 .. first0+n0), n0 in 1..32
+    int first1, n1;        // n1 in 0..32
+    int L, pad;
+};
+
+constexpr int kFastWarpsPerBlock = 4;
+
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
+k_packed_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTask* __restrict__ tasks,
+               const DevHaps hp, const DevReads rd, const int row_stride, const uint32_t nucp, int* __restrict__ scores)
+{
+    extern __shared__ uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kFastWarpsPerBlock + warp;
+    if (w >= n_works) return;
+    const WarpWork ww = works[w];
+    uint32_t* rows = smem + warp * row_stride;
+    fill_rows(rows, rd, ww.read0, ww.read1, ww.L, lane);
+    const bool v0 = lane < ww.n0, v1 = lane < ww.n1;
+    const LaneTask a = tasks[v0 ? ww.first0 + lane : ww.first0];
+    const LaneTask b = v1 ? tasks[ww.first1 + lane] : a;
+    const ColEntry* t0 = (a.reverse ? hp.tab_r : hp.tab_f) + a.tab_index;
+    const ColEntry* t1 = (b.reverse ? hp.tab_r : hp.tab_f) + b.tab_index;
+    const uint32_t r = dp_pair<BAND>(rows, ww.L, t0, t1, nucp);
+    if (v0) scores[a.out_idx] = (int)(r & 0xFFFFu);
+    if (v1) scores[b.out_idx] = (int)(r >> 16);
+}
+
+struct GenericTask { int read, hap, win_off, reverse, out_idx; };
+
+template <int MAXK>
+__global__ void k_generic_tasks(const GenericTask* __restrict__ tasks, const int n, const DevHaps hp, const DevReads rd,
+                                const int band, const int nuc_prior, int* __restrict__ scores)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GenericTask t = tasks[i];
+    const long long ho = hp.off[t.hap] + t.win_off, ro = rd.off[t.read];
+    const int L = (int)(rd.off[t.read + 1] - ro);
+    const GenericModel gm {hp.seq + ho, (t.reverse ? hp.mask_r : hp.mask_f) + ho, (t.reverse ? hp.prior_r : hp.prior_f) + ho,
+                           hp.gap_open + ho, hp.gap_extend + ho, nuc_prior};
+    scores[t.out_idx] = generic_align<false, MAXK>(band, gm, rd.bases + ro, (const int8_t*)(rd.quals + ro), L,
+                                                   nullptr, 1, 0, 0, nullptr, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batch boundary (phmm_populate): fused classify → DP → min, then the floating-point epilogue
+// ---------------------------------------------------------------------------------------------------------
+
+struct PopParams {
+    DevHaps hp;
+    DevReads rd;
+    const long long* pos_off;   // CSR over [H][R] pairs, or null
+    const int32_t* pos;
+    int band, nuc_prior;
+    int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
+    int use_flanks;             // flank_state present && config.use_flank_state
+    int lhs_flank, rhs_flank;
+    int* best;                  // [H*R] integer penalties, kBestInf-initialised
+    int* status;                // [H*R] zero-initialised
+    int* flags;                 // [0] |= 2 on ShortHaplotypeError, |= 4 on slow-queue overflow
+    // near-flank candidates, resolved by k_slow_flank
+    int4* slow;                 // {read, hap, position a, unused}
+    int* slow_count;
+    int slow_cap;
+    // fast path work list: read pairs of equal length (second may be -1)
+    const int* pair_reads;
+    int n_pairs;
+    int* pair_cursor;           // persistent-warp work counter
+    int row_stride;             // shared-memory words per warp for row words
+    // generic path work list
+    const int* generic_reads;
+    int n_generic;
+};
+
+__device__ __forceinline__ HapView hap_view(const DevHaps& hp, const int h, const bool reverse)
+{
+    const long long o = hp.off[h];
+    return HapView {hp.seq + o, (reverse ? hp.mask_r : hp.mask_f) + o, (reverse ? hp.prior_r : hp.prior_f) + o,
+                    hp.gap_open + o, hp.gap_extend + o, (int)(hp.off[h + 1] - o)};
+}
+__device__ __forceinline__ ReadView read_view(const DevReads& rd, const int r)
+{
+    const long long o = rd.off[r];
+    return ReadView {rd.bases + o, rd.quals + o, (int)(rd.off[r + 1] - o)};
+}
+
+__device__ __forceinline__ void push_slow(const PopParams& p, const int r, const int h, const int a)
+{
+    const int idx = atomicAdd(p.slow_count, 1);
+    if (idx < p.slow_cap) p.slow[idx] = make_int4(r, h, a, 0);
+    else atomicOr(p.flags, 4);
+}
+
+constexpr int kQueueCap = 64;
+
+// Persistent warps. Each warp repeatedly claims one read pair (r0, r1) of equal length, stages the pair's row words in
+// shared memory once, and walks all H haplotypes 32 at a time (lane = haplotype): candidate slots are classified in
+// lock-step (shortcut values go straight to best[], near-flank ones to the slow queue) and the DP-needing ones are
+// compacted into two per-half queues in shared memory; whenever a queue holds 32 tasks the warp runs one dp_pair
+// round — 64 alignments, two per lane — and folds the scores into best[] with atomicMin.
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
+k_populate_fast(const PopParams p)
+{
+    extern __shared__ uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = p.row_stride + 4 * kQueueCap;
+    uint32_t* rows = smem + warp * per_warp;
+    int* qh = (int*)(rows + p.row_stride);          // [2][kQueueCap] haplotype index
+    int* qa = qh + 2 * kQueueCap;                   // [2][kQueueCap] window offset
+    const int H = p.hp.n, R = p.rd.n;
+    const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(p.pair_cursor, 1);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= p.n_pairs) break;
+        const int r0 = p.pair_reads[2 * j], r1 = p.pair_reads[2 * j + 1];
+        const int L = p.rd.info[r0].x;
+        __syncwarp();
+        fill_rows(rows, p.rd, r0, r1, L, lane);
+        const int rr[2] = {r0, r1 >= 0 ? r1 : r0};
+        const bool rev[2] = {p.rd.reverse[rr[0]] != 0, p.rd.reverse[rr[1]] != 0};
+        const ColEntry* tab[2] = {rev[0] ? p.hp.tab_r : p.hp.tab_f, rev[1] ? p.hp.tab_r : p.hp.tab_f};
+        const ReadView rv[2] = {read_view(p.rd, rr[0]), read_view(p.rd, rr[1])};
+        const long long rbeg[2] = {p.rd.begin ? p.rd.begin[rr[0]] : 0, p.rd.begin ? p.rd.begin[rr[1]] : 0};
+        int cnt[2] = {0, 0};
+
+        auto dp_round = [&]() {
+            const int take0 = min(32, cnt[0]), take1 = min(32, cnt[1]);
+            const int base0 = cnt[0] - take0, base1 = cnt[1] - take1;
+            const bool v0 = lane < take0, v1 = lane < take1;
+            // idle lanes replay a valid task of the same round (results discarded)
+            int h0, a0, h1, a1;
+            if (take0 > 0) { const int s = base0 + (v0 ? lane : 0); h0 = qh[s]; a0 = qa[s]; }
+            else           { const int s = kQueueCap + base1;       h0 = qh[s]; a0 = qa[s]; }
+            if (take1 > 0) { const int s = kQueueCap + base1 + (v1 ? lane : 0); h1 = qh[s]; a1 = qa[s]; }
+            else           { h1 = h0; a1 = a0; }
+            const ColEntry* t0 = (take0 > 0 ? tab[0] : tab[1]) + p.hp.off[h0] + a0;
+            const ColEntry* t1 = (take1 > 0 ? tab[1] : (take0 > 0 ? tab[0] : tab[1])) + p.hp.off[h1] + a1;
+            const uint32_t res = dp_pair<BAND>(rows, L, t0, t1, nucp);
+            if (v0) atomicMin(p.best + (size_t)h0 * R + rr[0], (int)(res & 0xFFFFu));
+            if (v1) atomicMin(p.best + (size_t)h1 * R + rr[1], (int)(res >> 16));
+            cnt[0] = base0; cnt[1] = base1;
+            __syncwarp();
+        };
+
+        for (int hb = 0; hb < H; hb += 32) {
+            const int h = hb + lane;
+            const bool act = h < H;
+            const int hc = act ? h : H - 1;
+            const int hap_len = (int)(p.hp.off[hc + 1] - p.hp.off[hc]);
+            const long long hbeg = p.hp.begin ? p.hp.begin[hc] : 0;
+            int npos[2] = {0, 0};
+            const int32_t* pp[2] = {nullptr, nullptr};
+            EnumState st[2] = {{false, false}, {false, false}};
+            int maxslots = 0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (p.pos_off && act && (s == 0 || r1 >= 0)) {
+                    const long long o = p.pos_off[(size_t)hc * R + rr[s]];
+                    npos[s] = (int)(p.pos_off[(size_t)hc * R + rr[s] + 1] - o);
+                    pp[s] = p.pos + o;
+                }
+                maxslots = max(maxslots, npos[s] + 2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxslots = max(maxslots, __shfl_xor_sync(0xffffffffu, maxslots, o));
+            for (int c = 0; c < maxslots; ++c) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    bool need_dp = false;
+                    int a = 0;
+                    if (act && (s == 0 || r1 >= 0)) {
+                        int pos;
+                        const int k = candidate_slot(c, npos[s], pp[s], rbeg[s] - hbeg, L, hap_len, p.band, st[s], &pos);
+                        if (k < 0) {
+                            p.status[(size_t)h * R + rr[s]] = 2 | (pos << 16);
+                            atomicOr(p.flags, 2);
+                        } else if (k > 0) {
+                            const HapView hv = hap_view(p.hp, h, rev[s]);
+                            int v;
+                            const CandKind kind = classify_candidate(hv, rv[s], p.band, pos, p.shortcut != 0, p.use_flanks != 0,
+                                                                     p.lhs_flank, p.rhs_flank, &v);
+                            if (kind == CAND_VALUE) atomicMin(p.best + (size_t)h * R + rr[s], v);
+                            else if (kind == CAND_DP) { need_dp = true; a = v; }
+                            else if (kind == CAND_DP_FLANK) push_slow(p, rr[s], h, v);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, need_dp);
+                    if (need_dp) {
+                        const int slot = s * kQueueCap + cnt[s] + __popc(m & lt_mask);
+                        qh[slot] = h; qa[slot] = a;
+                    }
+                    cnt[s] += __popc(m);
+                }
+                __syncwarp();
+                while (cnt[0] >= 32 || cnt[1] >= 32) dp_round();
+            }
+        }
+        while (cnt[0] > 0 || cnt[1] > 0) dp_round();
+    }
+}
+
+// Generic path of populate: reads the fast path cannot take (non-ACGT bases, 16-bit-unsafe qualities, very long reads)
+// or every read when the band is > 32 / int32 scores were requested. One thread per (haplotype, read) pair.
+template <int MAXK>
+__global__ void k_populate_generic(const PopParams p)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = p.hp.n, R = p.rd.n;
+    if (i >= (long long)p.n_generic * H) return;
+    const int r = p.generic_reads[i / H], h = (int)(i % H);
+    const bool rev = p.rd.reverse[r] != 0;
+    const HapView hv = hap_view(p.hp, h, rev);
+    const ReadView rv = read_view(p.rd, r);
+    const long long orig = (p.rd.begin ? p.rd.begin[r] : 0) - (p.hp.begin ? p.hp.begin[h] : 0);
+    int npos = 0;
+    const int32_t* pp = nullptr;
+    if (p.pos_off) { const long long o = p.pos_off[(size_t)h * R + r]; npos = (int)(p.pos_off[(size_t)h * R + r + 1] - o); pp = p.pos + o; }
+    EnumState st {false, false};
+    int best = kBestInf;
+    for (int c = 0; c < npos + 2; ++c) {
+        int pos;
+        const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
+        if (k < 0) { p.status[(size_t)h * R + r] = 2 | (pos << 16); atomicOr(p.flags, 2); continue; }
+        if (k == 0) continue;
+        int v;
+        const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, p.use_flanks != 0, p.lhs_flank, p.rhs_flank, &v);
+        if (kind == CAND_VALUE) best = min(best, v);
+        else if (kind == CAND_DP) {
+            const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
+            best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
+        } else if (kind == CAND_DP_FLANK) push_slow(p, r, h, v);
+    }
+    if (best != kBestInf) atomicMin(p.best + (size_t)h * R + r, best);
+}
+
+// Near-flank candidates: traceback DP + flank discount (pair_hmm.hpp:743-764). Grid-stride over the slow queue; each
+// thread owns an interleaved back-pointer scratch (cell c of thread t at bp[c * nthreads + t]).
+template <int MAXK>
+__global__ void k_slow_flank(const PopParams p, unsigned char* __restrict__ bp)
+{
+    const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(*p.slow_count, p.slow_cap);
+    const int R = p.rd.n;
+    for (int i = tid; i < n; i += nthreads) {
+        const int4 t = p.slow[i];
+        const int r = t.x, h = t.y, a = t.z;
+        const HapView hv = hap_view(p.hp, h, p.rd.reverse[r] != 0);
+        const ReadView rv = read_view(p.rd, r);
+        const int W = rv.len + 2 * p.band - 1;
+        const GenericModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
+        int lhs, rhs, fp, fs, ms;
+        window_flanks(a, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+        const int score = generic_align<true, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, bp + tid, (size_t)nthreads,
+                                                    lhs, rhs, &fp, &fs, &ms);
+        const int v = discount_flank(score, fs, rv.len, ms, fp);
+        if (v != kBestInf) atomicMin(p.best + (size_t)h * R + r, v);
+    }
+}
+
+__global__ void k_fill_int(int* __restrict__ p, const long long n, const int v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Floating-point epilogue (haplotype_likelihood_model.cpp:285-303): out[h][r] in double.
+__global__ void k_epilogue(const int* __restrict__ best, int* __restrict__ status, const uint8_t* __restrict__ mapq,
+                           const int H, const int R, const int use_mapq, const int mapq_cap, const int mapq_trigger,
+                           double* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * R) return;
+    const int r = (int)(i % R);
+    const int b = best[i];
+    if (b == kBestInf && status[i] == 0) status[i] = 1;
+    out[i] = finish_likelihood(b, use_mapq != 0, mapq[r], mapq_cap, mapq_trigger);
+}
+
+} // namespace phmm

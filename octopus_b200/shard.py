@@ -1,0 +1,64 @@
+"""Multi-GPU: one process per GPU, static split of the work items, one gather of the result slabs to rank 0.
+
+The path shards embarrassingly: every (read, haplotype, position) alignment is independent, so the
+reads of a region are split contiguously over the ranks, every rank holds all haplotypes (a few hundred KB), and there
+is NO collective inside the computation. The only exchange is the final gather of the [H, R_rank] ln-likelihood slabs
+to rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def split_range(n, world, rank):
+    """Contiguous static split of range(n): the first n % world ranks get one extra item."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_reads(reads, world, rank):
+    """The ReadBlock holding this rank's contiguous share of the reads (host arrays)."""
+    from .batch import ReadBlock
+    lo, hi = split_range(reads.n, world, rank)
+    a, b = int(reads.off[lo]), int(reads.off[hi])
+    return ReadBlock(reads.off[lo:hi + 1] - reads.off[lo], reads.bases[a:b], reads.quals[a:b], reads.mapq[lo:hi],
+                     reads.reverse[lo:hi], reads.begin[lo:hi]), (lo, hi)
+
+
+def shard_positions(positions, H, R, lo, hi):
+    """Column slice [lo, hi) of a [H][R] CSR of candidate positions."""
+    if positions is None:
+        return None
+    off, pos = positions
+    n = hi - lo
+    new_off = np.zeros(H * n + 1, dtype=np.int64)
+    parts = []
+    for h in range(H):
+        a, b = int(off[h * R + lo]), int(off[h * R + hi])
+        parts.append(pos[a:b])
+        new_off[h * n + 1:(h + 1) * n + 1] = new_off[h * n] + (off[h * R + lo + 1:h * R + hi + 1] - off[h * R + lo])
+    flat = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int32)
+    return new_off, (flat if len(flat) else np.zeros(1, dtype=np.int32))
+
+
+def gather_likelihoods(local, R_total, world, rank, group=None):
+    """Gather the per-rank [H, R_rank] slabs into the [H, R_total] matrix on rank 0 (returns None elsewhere).
+
+    ``local`` is a torch tensor (CUDA with the nccl backend, CPU with gloo). Slabs are padded to the largest share so a
+    single fixed-size gather suffices; the column ranges are those of ``split_range``."""
+    import torch
+    import torch.distributed as dist
+    H = local.shape[0]
+    width = (R_total + world - 1) // world
+    send = torch.zeros((H, width), dtype=local.dtype, device=local.device)
+    send[:, :local.shape[1]] = local
+    if world == 1:
+        return local
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, recv, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = torch.empty((H, R_total), dtype=local.dtype, device=local.device)
+    for k in range(world):
+        lo, hi = split_range(R_total, world, k)
+        out[:, lo:hi] = recv[k][:, :hi - lo]
+    return out

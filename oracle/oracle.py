@@ -212,6 +212,8 @@ class COracle:
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _i32p]
         L.oracle_kmer_map.restype = C.c_int
         L.oracle_kmer_map.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, _i64p]
+        L.oracle_populate.restype = C.c_int
+        L.oracle_populate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]
 
     @staticmethod
     def model(gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
@@ -305,3 +307,19 @@ class COracle:
         out = np.zeros(max(1, max_positions), dtype=np.int64)
         n = self.lib.oracle_kmer_map(qb, len(qb) - 1, tb, len(tb) - 1, max_positions, out.ctypes.data_as(_i64p))
         return out[:n].tolist()
+
+    def populate(self, band, haps, reads, positions=None, flanks=None, use_mapping_quality=True, mapq_cap=120,
+                 mapq_cap_trigger=-1, nuc_prior=2, dp_only=False):
+        """haps / reads: host HaplotypeBlock / ReadBlock (octopus_b200.batch). Returns (any_short, out[H,R], status[H,R])."""
+        H, R = haps.n, reads.n
+        out = np.empty((H, R), dtype=np.float64)
+        status = np.zeros((H, R), dtype=np.int32)
+        p = lambda a: None if a is None else a.ctypes.data
+        po, pv = (None, None) if positions is None else (np.ascontiguousarray(positions[0], dtype=np.int64), np.ascontiguousarray(positions[1], dtype=np.int32))
+        uf, lhs, rhs = (0, 0, 0) if flanks is None else (1, int(flanks[0]), int(flanks[1]))
+        rc = self.lib.oracle_populate(int(band), H, p(haps.off), p(haps.seq), p(haps.snv_mask_fwd), p(haps.snv_prior_fwd),
+                                      p(haps.snv_mask_rev), p(haps.snv_prior_rev), p(haps.gap_open), p(haps.gap_extend), p(haps.begin),
+                                      R, p(reads.off), p(reads.bases), p(reads.quals), p(reads.mapq), p(reads.reverse), p(reads.begin),
+                                      p(po), p(pv), uf, lhs, rhs, int(use_mapping_quality), int(mapq_cap), int(mapq_cap_trigger),
+                                      int(nuc_prior), int(dp_only), out.ctypes.data, status.ctypes.data)
+        return rc, out, status

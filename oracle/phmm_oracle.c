@@ -412,3 +412,50 @@ int oracle_kmer_map(const char* query, int query_len, const char* target, int ta
     free(bin_start); free(items); free(th); free(fill); free(counts);
     return n;
 }
+
+/* haplotype_likelihood_array.cpp:51-103 populate(ReadMap) for one sample: the H x R loop (haplotype outer, read inner),
+ * with the candidate mapping positions supplied as a CSR over [H][R] pairs (pos_off == NULL: none listed) instead of
+ * being produced by the k-mer mapper inline (:89-92; see oracle_kmer_map). Writes out[h*R + r]; status[h*R + r] = 0 ok,
+ * 2 | ext << 16 for ShortHaplotypeError (the reference throws on the first one; this loop records all and returns 1). */
+int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
+                    const char* mask_f, const int8_t* prior_f, const char* mask_r, const int8_t* prior_r,
+                    const int8_t* gap_open, const int8_t* gap_extend, const int64_t* hap_begin,
+                    int R, const int64_t* read_off, const char* bases, const uint8_t* quals,
+                    const uint8_t* mapq, const uint8_t* reverse, const int64_t* read_begin,
+                    const int64_t* pos_off, const int32_t* pos,
+                    int use_flanks, int lhs_flank, int rhs_flank,
+                    int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only,
+                    double* out, int32_t* status)
+{
+    int any_short = 0;
+    int64_t tmp[64];
+    for (int h = 0; h < H; ++h) {
+        const int64_t ho = hap_off[h];
+        const int hl = (int)(hap_off[h + 1] - ho);
+        for (int r = 0; r < R; ++r) {
+            const int64_t ro = read_off[r];
+            const int rl = (int)(read_off[r + 1] - ro);
+            const int rev = reverse ? reverse[r] : 0;
+            oracle_model m;
+            m.snv_mask = (rev ? mask_r : mask_f) + ho;
+            m.snv_prior = (rev ? prior_r : prior_f) + ho;
+            m.gap_open = gap_open + ho;
+            m.gap_extend = gap_extend + ho;
+            m.gap_open_scalar = 0; m.gap_extend_scalar = 0; m.nuc_prior = nuc_prior;
+            int np = 0;
+            if (pos_off) {
+                const int64_t a = pos_off[(int64_t)h * R + r], b = pos_off[(int64_t)h * R + r + 1];
+                for (int64_t i = a; i < b && np < 64; ++i) tmp[np++] = pos[i];
+            }
+            const int64_t orig = (read_begin ? read_begin[r] : 0) - (hap_begin ? hap_begin[h] : 0);
+            double v = 0; int ext = 0;
+            const int st = oracle_model_evaluate(band, seq + ho, hl, bases + ro, quals + ro, rl, &m, use_flanks, lhs_flank, rhs_flank,
+                                                 tmp, np, orig, use_mapping_quality, mapq ? mapq[r] : 60, mapq_cap, mapq_cap_trigger,
+                                                 dp_only, &v, &ext);
+            out[(int64_t)h * R + r] = st ? ORACLE_LOWEST : v;
+            if (status) status[(int64_t)h * R + r] = st ? (2 | (ext << 16)) : 0;
+            any_short |= st;
+        }
+    }
+    return any_short;
+}

@@ -66,6 +66,17 @@ int oracle_model_evaluate(int band, const char* hap, int hap_len, const char* re
 int oracle_kmer_map(const char* query, int query_len, const char* target, int target_len,
                     int max_positions, int64_t* out_positions);
 
+/* reference HaplotypeLikelihoodArray::populate(ReadMap) loop (haplotype_likelihood_array.cpp:51-103), candidate positions as CSR. */
+int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
+                    const char* mask_f, const int8_t* prior_f, const char* mask_r, const int8_t* prior_r,
+                    const int8_t* gap_open, const int8_t* gap_extend, const int64_t* hap_begin,
+                    int R, const int64_t* read_off, const char* bases, const uint8_t* quals,
+                    const uint8_t* mapq, const uint8_t* reverse, const int64_t* read_begin,
+                    const int64_t* pos_off, const int32_t* pos,
+                    int use_flanks, int lhs_flank, int rhs_flank,
+                    int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only,
+                    double* out, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

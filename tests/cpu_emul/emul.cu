@@ -1,0 +1,106 @@
+// TEST HELPER (not part of the product library): runs the engine's __host__ __device__ DP cores on the CPU, with the
+// sm_100a packed-16 instructions emulated (octopus_b200/csrc/phmm_device.cuh), so that `pytest -m "not gpu"` can check
+// the very code the kernels execute against the oracle without a GPU.
+#include <cstdint>
+#include <vector>
+#include "../../octopus_b200/csrc/phmm_device.cuh"
+
+using namespace phmm;
+
+template <int BAND>
+static uint32_t run_pair(int L, const std::vector<uint32_t>& rows, const ColEntry* t0, const ColEntry* t1, uint32_t nucp)
+{
+    return dp_pair<BAND>(rows.data(), L, t0, t1, nucp);
+}
+
+extern "C" {
+
+// Two alignments of equal read length L through dp_pair<band>. Inputs per alignment a in {0,1}: read bases/quals (L),
+// window arrays (W = L + 2*band - 1). Returns 0, or -1 if a read base is not ACGT / band unsupported.
+int emul_dp_pair(int band, int L, const char* read0, const uint8_t* q0, const char* read1, const uint8_t* q1,
+                 const char* truth0, const char* mask0, const int8_t* prior0, const int8_t* go0, const int8_t* ge0,
+                 const char* truth1, const char* mask1, const int8_t* prior1, const int8_t* go1, const int8_t* ge1,
+                 int nuc_prior, int* score0, int* score1)
+{
+    const int W = L + 2 * band - 1;
+    std::vector<uint32_t> rows(L + 1);
+    for (int y = 0; y < L; ++y) {
+        const int c0 = base_code(read0[y]), c1 = base_code(read1[y]);
+        if (c0 < 0 || c1 < 0) return -1;
+        rows[y] = make_row_word((uint32_t)c0 | ((uint32_t)q0[y] << 8), (uint32_t)c1 | ((uint32_t)q1[y] << 8));
+    }
+    rows[L] = kPadRowWord;
+    std::vector<ColEntry> t0(W), t1(W);
+    for (int x = 0; x < W; ++x) {
+        t0[x] = make_col_entry(truth0[x], mask0[x], prior0[x], go0[x], ge0[x]);
+        t1[x] = make_col_entry(truth1[x], mask1[x], prior1[x], go1[x], ge1[x]);
+    }
+    const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
+    uint32_t r;
+    switch (band) {
+        case 8:  r = run_pair<8>(L, rows, t0.data(), t1.data(), nucp); break;
+        case 16: r = run_pair<16>(L, rows, t0.data(), t1.data(), nucp); break;
+        case 32: r = run_pair<32>(L, rows, t0.data(), t1.data(), nucp); break;
+        default: return -1;
+    }
+    *score0 = (int)(r & 0xFFFF);
+    *score1 = (int)(r >> 16);
+    return 0;
+}
+
+// generic_align<TB> on the CPU. tb != 0 additionally returns first_pos / flank score / in-flank read bases.
+int emul_generic(int band, int tb, int L, const char* read, const int8_t* q,
+                 const char* truth, const char* mask, const int8_t* prior, const int8_t* go, const int8_t* ge,
+                 int nuc_prior, int lhs_flank, int rhs_flank, int* first_pos, int* flank_score, int* mask_size)
+{
+    GenericModel gm {truth, mask, prior, go, ge, nuc_prior};
+    if (2 * band > kGenericMaxDiag) return -1000000;
+    if (tb) {
+        std::vector<unsigned char> bp((size_t)(L + 1) * 2 * band, 0);
+        return generic_align<true, kGenericMaxDiag>(band, gm, read, q, L, bp.data(), 1, lhs_flank, rhs_flank, first_pos, flank_score, mask_size);
+    }
+    return generic_align<false, kGenericMaxDiag>(band, gm, read, q, L, nullptr, 1, 0, 0, nullptr, nullptr, nullptr);
+}
+
+} // extern "C"
+
+// The whole per-(haplotype, read) evaluation exactly as the populate kernels perform it, on the CPU:
+// candidate slots → classify → DP (generic_align) → flank discount → min → finish_likelihood.
+// Mirrors oracle_model_evaluate's signature. Returns 0 ok, 1 ShortHaplotypeError.
+extern "C" int emul_pair_evaluate(int band, const char* hap, int hap_len, const char* mask, const int8_t* prior,
+                                  const int8_t* go, const int8_t* ge, const char* read, const uint8_t* quals, int read_len,
+                                  int use_flanks, int lhs_flank, int rhs_flank, const int32_t* positions, int n_positions,
+                                  long long original_pos, int use_mapq, int mapq, int mapq_cap, int mapq_trigger,
+                                  int dp_only, int nuc_prior, double* out, int* required_extension)
+{
+    const HapView hv {hap, mask, prior, go, ge, hap_len};
+    const ReadView rv {read, quals, read_len};
+    EnumState st {false, false};
+    int best = kBestInf;
+    for (int c = 0; c < n_positions + 2; ++c) {
+        int p;
+        const int k = candidate_slot(c, n_positions, positions, original_pos, read_len, hap_len, band, st, &p);
+        if (k < 0) { *required_extension = p; return 1; }
+        if (k == 0) continue;
+        int v;
+        const CandKind kind = classify_candidate(hv, rv, band, p, !dp_only, use_flanks != 0, lhs_flank, rhs_flank, &v);
+        int val = kBestInf;
+        if (kind == CAND_VALUE) val = v;
+        else if (kind == CAND_DP || kind == CAND_DP_FLANK) {
+            const int a = v, W = read_len + 2 * band - 1;
+            GenericModel gm {hap + a, mask + a, prior + a, go + a, ge + a, nuc_prior};
+            if (kind == CAND_DP) {
+                val = generic_align<false, kGenericMaxDiag>(band, gm, read, (const int8_t*)quals, read_len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr);
+            } else {
+                int lhs, rhs, fp, fs, ms;
+                window_flanks(a, W, hap_len, lhs_flank, rhs_flank, &lhs, &rhs);
+                std::vector<unsigned char> bp((size_t)(read_len + 1) * 2 * band, 0);
+                const int score = generic_align<true, kGenericMaxDiag>(band, gm, read, (const int8_t*)quals, read_len, bp.data(), 1, lhs, rhs, &fp, &fs, &ms);
+                val = discount_flank(score, fs, read_len, ms, fp);
+            }
+        }
+        if (val < best) best = val;
+    }
+    *out = finish_likelihood(best, use_mapq != 0, mapq, mapq_cap, mapq_trigger);
+    return 0;
+}

@@ -1,0 +1,136 @@
+"""The engine's __host__ __device__ DP cores (octopus_b200/csrc/phmm_device.cuh) executed on the CPU with the
+sm_100a packed-16 instructions emulated, checked against the oracle. This is the same source the kernels compile."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import random_alignment_case
+
+vp = C.c_void_p
+
+
+@pytest.fixture(scope="module")
+def emul():
+    from octopus_b200.build import build_cpu_emulation
+    lib = C.CDLL(build_cpu_emulation())
+    lib.emul_dp_pair.argtypes = [C.c_int, C.c_int] + [vp] * 14 + [C.c_int, vp, vp]
+    lib.emul_generic.argtypes = [C.c_int, C.c_int, C.c_int] + [vp] * 7 + [C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.emul_pair_evaluate.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,
+                                       C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    return lib
+
+
+def P(a):
+    return a.ctypes.data
+
+
+def test_packed_dp_pair_matches_oracle(emul, coracle):
+    rng = np.random.default_rng(11)
+    for it in range(1200):
+        band = int(rng.choice([8, 16, 32]))
+        L = int(rng.integers(1, 200))
+        nuc = int(rng.integers(0, 5))
+        a = random_alignment_case(rng, band, L, qmax=93 if it % 3 == 0 else 41)
+        b = random_alignment_case(rng, band, L)
+        s0, s1 = C.c_int(0), C.c_int(0)
+        rc = emul.emul_dp_pair(band, L, P(a["read"]), P(a["quals"]), P(b["read"]), P(b["quals"]),
+                               P(a["truth"]), P(a["snv_mask"]), P(a["snv_prior"]), P(a["gap_open"]), P(a["gap_extend"]),
+                               P(b["truth"]), P(b["snv_mask"]), P(b["snv_prior"]), P(b["gap_open"]), P(b["gap_extend"]),
+                               nuc, C.byref(s0), C.byref(s1))
+        assert rc == 0
+        e = [coracle.align(band, c["truth"].tobytes(), c["read"].tobytes(), c["quals"].astype(np.int8), c["gap_open"], c["gap_extend"],
+                           nuc, c["snv_mask"].tobytes(), c["snv_prior"]) for c in (a, b)]
+        assert [s0.value, s1.value] == e, (band, L, nuc)
+
+
+def test_packed_dp_pair_reference_kats(emul, kats):
+    """The reference's KATs use the no-SNV overload with a scalar gap_extend: a mask byte that matches no base and a
+    constant gap_extend array are the same recurrence."""
+    for c in kats:
+        if c["band"] > 32:
+            continue
+        L, W = len(c["read"]), len(c["truth"])
+        read = np.frombuffer(c["read"].encode(), dtype=np.uint8)
+        truth = np.frombuffer(c["truth"].encode(), dtype=np.uint8)
+        q = np.asarray(c["quals"], dtype=np.uint8)
+        go = np.asarray(c["gap_open"], dtype=np.int8)
+        ge = np.full(W, c["gap_extend"], dtype=np.int8)
+        mask = np.zeros(W, dtype=np.uint8)
+        prior = np.full(W, 100, dtype=np.int8)
+        s0, s1 = C.c_int(0), C.c_int(0)
+        rc = emul.emul_dp_pair(c["band"], L, P(read), P(q), P(read), P(q), P(truth), P(mask), P(prior), P(go), P(ge),
+                               P(truth), P(mask), P(prior), P(go), P(ge), c["nuc_prior"], C.byref(s0), C.byref(s1))
+        assert rc == 0 and s0.value == c["score"] and s1.value == c["score"], (c["suite"], c["index"])
+
+
+def test_generic_align_with_traceback_matches_oracle(emul, coracle):
+    rng = np.random.default_rng(12)
+    for it in range(700):
+        band = int(rng.choice([8, 16, 32, 64]))
+        L = int(rng.integers(1, 120))
+        nuc = int(rng.integers(0, 5))
+        c = random_alignment_case(rng, band, L, read_n=(it % 5 == 0))
+        W = len(c["truth"])
+        lhs, rhs = int(rng.integers(0, W // 2 + 1)), int(rng.integers(0, W // 2 + 1))
+        q8 = c["quals"].astype(np.int8)
+        fp, fs, ms = C.c_int(0), C.c_int(0), C.c_int(0)
+        args = (L, P(c["read"]), P(q8), P(c["truth"]), P(c["snv_mask"]), P(c["snv_prior"]), P(c["gap_open"]), P(c["gap_extend"]), nuc)
+        s = emul.emul_generic(band, 0, *args, 0, 0, None, None, None)
+        st = emul.emul_generic(band, 1, *args, lhs, rhs, C.byref(fp), C.byref(fs), C.byref(ms))
+        t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
+        e = coracle.align(band, t, r, q8, c["gap_open"], c["gap_extend"], nuc, m, c["snv_prior"])
+        es, efp, a1, a2 = coracle.align_tb(band, t, r, q8, c["gap_open"], c["gap_extend"], nuc, m, c["snv_prior"])
+        efs, ems = coracle.flank_score(W, lhs, rhs, r, q8, m, c["snv_prior"], c["gap_open"], c["gap_extend"], nuc, efp, a1, a2)
+        assert (s, st, fp.value, fs.value, ms.value) == (e, es, efp, efs, ems)
+
+
+def test_pair_evaluation_logic_matches_oracle(emul, coracle):
+    """Candidate slots → shortcut / DP / flank discount → min → mapping-quality mix, as the populate kernels run it."""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    n_short = 0
+    for it in range(1500):
+        band = int(rng.choice([8, 16, 32]))
+        L = int(rng.integers(6, 120))
+        Lh = int(rng.integers(L + 2 * band - 4, L + 2 * band + 150))
+        hap = acgt[rng.integers(0, 4, Lh)].copy()
+        if rng.random() < 0.1:
+            hap[rng.integers(0, Lh)] = ord("N")
+        mask = np.roll(hap, 1)
+        prior = rng.integers(1, 126, Lh).astype(np.int8)
+        go = rng.integers(3, 46, Lh).astype(np.int8)
+        ge = rng.integers(1, 11, Lh).astype(np.int8)
+        p0 = int(rng.integers(0, max(1, Lh - L + 1)))
+        read = hap[p0:p0 + L].copy()
+        if len(read) < L:
+            read = np.concatenate([read, acgt[rng.integers(0, 4, L - len(read))]])
+        read[read == ord("N")] = ord("A")
+        for _ in range(int(rng.choice([0, 0, 1, 1, 2, 3, 5]))):
+            read[rng.integers(0, L)] = acgt[rng.integers(0, 4)]
+        if rng.random() < 0.2:
+            i = int(rng.integers(1, L - 1)); read = np.concatenate([read[:i], read[i + 1:], acgt[rng.integers(0, 4, 1)]])
+        q = rng.integers(2, 42, L).astype(np.uint8)
+        npos = int(rng.integers(0, 5))
+        pos = np.array([min(max(0, p0 + int(rng.integers(-20, 21))), Lh) for _ in range(npos)], dtype=np.int32)
+        if npos and rng.random() < 0.5:
+            pos[rng.integers(0, npos)] = p0
+        orig = max(0, p0 + int(rng.choice([0, 0, 0, -3, 4, -40, 40])))
+        uf = int(rng.random() < 0.6)
+        lhs, rhs = int(rng.integers(0, Lh // 2)), int(rng.integers(0, Lh // 2))
+        mq = int(rng.choice([0, 10, 29, 60, 255]))
+        usemq, trig, dpo = int(rng.random() < 0.8), int(rng.choice([-1, 40])), int(rng.random() < 0.3)
+        out, ext = C.c_double(0), C.c_int(0)
+        rc = emul.emul_pair_evaluate(band, P(hap), Lh, P(mask), P(prior), P(go), P(ge), P(read), P(q), L, uf, lhs, rhs,
+                                     P(pos) if npos else None, npos, orig, usemq, mq, 120, trig, dpo, 2, C.byref(out), C.byref(ext))
+        st, val, e = coracle.model_evaluate(band, hap.tobytes(), read.tobytes(), q, go, ge, mask.tobytes(), prior, pos.astype(np.int64), orig,
+                                            mapping_quality=mq, flanks=(lhs, rhs) if uf else None, use_mapping_quality=bool(usemq),
+                                            mapq_cap=120, mapq_cap_trigger=trig, dp_only=bool(dpo))
+        assert rc == st
+        if rc == 0:
+            assert out.value == val
+        else:
+            assert ext.value == e
+            n_short += 1
+    assert n_short > 0

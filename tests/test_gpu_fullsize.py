@@ -1,0 +1,42 @@
+"""Full-size runs (BASELINE.json's C2 shape on one GPU) checked through size-independent properties plus a random
+sample of pairs against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_full_size_properties(engine, coracle):
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    from octopus_b200.batch import ReadBlock
+    haps, reads, band = synth.make_batch("C2")           # 100k reads x 64 haplotypes, band 16: 6.4e6 alignments
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, use_mapping_quality=False)
+    m = engine.populate(cfg, haps, reads)
+    assert m.shape == (64, 100_000) and np.isfinite(m).all() and (m <= 0).all()
+    # 1. determinism
+    assert np.array_equal(m, engine.populate(cfg, haps, reads))
+    # 2. every value is -ln10/10 * (a non-negative integer phred score)
+    c = 0.230258509299404568401799145468436420760110148862877297603
+    k = np.rint(-m / c)
+    assert np.array_equal(-c * k, m) and (k >= 0).all()
+    # 3. permuting the reads permutes the columns (scheduling / pairing must not leak between reads)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(reads.n)[:20000]
+    L = 150
+    idx = (reads.off[perm][:, None] + np.arange(L)[None, :]).reshape(-1)
+    sub = ReadBlock(np.arange(len(perm) + 1, dtype=np.int64) * L, reads.bases[idx], reads.quals[idx], reads.mapq[perm], reads.reverse[perm], reads.begin[perm])
+    assert np.array_equal(engine.populate(cfg, haps, sub), m[:, perm])
+    # 4. a random sample of pairs against the oracle (bit-exact: integer score times a constant)
+    sel = rng.choice(reads.n, 300, replace=False)
+    idx = (reads.off[sel][:, None] + np.arange(L)[None, :]).reshape(-1)
+    sample = ReadBlock(np.arange(len(sel) + 1, dtype=np.int64) * L, reads.bases[idx], reads.quals[idx], reads.mapq[sel], reads.reverse[sel], reads.begin[sel])
+    rc, want, _ = coracle.populate(band, haps, sample, use_mapping_quality=False, dp_only=True)
+    assert rc == 0 and np.array_equal(m[:, sel], want)
+    # 5. a read scored against the haplotype it was copied from without errors costs nothing: spot-check exact substrings
+    hs = haps.seq.reshape(64, 300)
+    for r in sel[:50]:
+        b, _ = reads.read(int(r))
+        p = int(reads.begin[r])
+        for h in range(64):
+            if np.array_equal(hs[h, p:p + L], b):
+                assert m[h, r] == 0.0

@@ -1,0 +1,163 @@
+"""The oracle is pinned here: against the reference's own known-answer tests (tests/golden/pair_hmm_kats.json,
+extracted from test/unit/core/models/pair_hmm_tests.cpp) and against the reference's SIMD kernel compiled into
+oracle/_ref (skipped where that build is absent)."""
+import numpy as np
+import pytest
+
+from helpers import random_alignment_case
+
+C_LN10_DIV_10 = 0.230258509299404568401799145468436420760110148862877297603
+
+
+def test_c_restatement_reproduces_reference_kats(coracle, kats):
+    assert len(kats) == 22
+    for c in kats:
+        s = coracle.align(c["band"], c["truth"], c["read"], c["quals"], c["gap_open"], c["gap_extend"], c["nuc_prior"])
+        s2, fp, a1, a2 = coracle.align_tb(c["band"], c["truth"], c["read"], c["quals"], c["gap_open"], c["gap_extend"], c["nuc_prior"])
+        assert (s, s2, fp, a1, a2) == (c["score"], c["score"], c["first_pos"], c["align_truth"], c["align_read"]), (c["suite"], c["index"])
+
+
+def test_reference_build_reproduces_its_own_kats(refkernels, kats):
+    if not refkernels:
+        pytest.skip("oracle/_ref not built on this host")
+    for isa, k in refkernels.items():
+        for c in kats:
+            for bits in (16, 32):
+                s = k.align(c["band"], c["truth"], c["read"], c["quals"], c["gap_open"], c["gap_extend"], c["nuc_prior"], bits=bits)
+                s2, fp, a1, a2 = k.align_tb(c["band"], c["truth"], c["read"], c["quals"], c["gap_open"], c["gap_extend"], c["nuc_prior"], bits=bits)
+                assert (s, s2, fp, a1, a2) == (c["score"], c["score"], c["first_pos"], c["align_truth"], c["align_read"]), (isa, c["suite"], c["index"], bits)
+
+
+def test_c_restatement_matches_reference_kernel_fuzz(coracle, refkernels):
+    if not refkernels:
+        pytest.skip("oracle/_ref not built on this host")
+    rng = np.random.default_rng(20260923)
+    isas = list(refkernels)
+    for it in range(1500):
+        band = int(rng.choice([8, 16, 32, 64]))
+        L = int(rng.integers(1, 140))
+        c = random_alignment_case(rng, band, L)
+        nuc = int(rng.integers(2, 5))
+        k = refkernels[isas[it % len(isas)]]
+        bits = int(rng.choice([16, 32]))
+        q = c["quals"].astype(np.int8)
+        t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
+        snv = dict(snv_mask=m, snv_prior=c["snv_prior"]) if it % 4 else {}
+        ge = c["gap_extend"] if it % 3 else int(c["gap_extend"][0])
+        assert k.align(band, t, r, q, c["gap_open"], ge, nuc, bits=bits, **snv) == coracle.align(band, t, r, q, c["gap_open"], ge, nuc, **snv)
+        ref_tb = k.align_tb(band, t, r, q, c["gap_open"], ge, nuc, bits=bits, **snv)
+        assert ref_tb == coracle.align_tb(band, t, r, q, c["gap_open"], ge, nuc, **snv)
+        if snv:
+            W = len(t)
+            lhs, rhs = int(rng.integers(0, W // 2 + 1)), int(rng.integers(0, W // 2 + 1))
+            a = k.flank_score(band, W, lhs, rhs, r, q, m, c["snv_prior"], c["gap_open"], ge, nuc, ref_tb[1], ref_tb[2], ref_tb[3], bits=bits)
+            b = coracle.flank_score(W, lhs, rhs, r, q, m, c["snv_prior"], c["gap_open"], ge, nuc, ref_tb[1], ref_tb[2], ref_tb[3])
+            assert a == b
+
+
+def test_reference_int16_equals_int32_when_not_overflowing(refkernels):
+    """Parity domain: the engine computes exact scores; the reference's default int16 lanes agree with its int32 lanes
+    whenever the true score fits (adversarial: cheap gaps / expensive mismatches stress the un-initialised band lanes)."""
+    if not refkernels:
+        pytest.skip("oracle/_ref not built on this host")
+    k = next(iter(refkernels.values()))
+    rng = np.random.default_rng(7)
+    for it in range(1500):
+        band = int(rng.choice([8, 16, 32]))
+        L = int(rng.integers(1, 80))
+        c = random_alignment_case(rng, band, L)
+        q = rng.integers(60, 121, L).astype(np.int8)
+        go = rng.integers(1, 4, len(c["truth"])).astype(np.int8) if it % 2 else rng.integers(40, 46, len(c["truth"])).astype(np.int8)
+        ge = np.ones(len(c["truth"]), dtype=np.int8)
+        nuc = int(rng.integers(0, 3))
+        t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
+        assert k.align(band, t, r, q, go, ge, nuc, m, c["snv_prior"], bits=16) == k.align(band, t, r, q, go, ge, nuc, m, c["snv_prior"], bits=32)
+
+
+def test_naive_evaluate_shortcuts(coracle):
+    hap = "ACGTTGCAAGCTTAGGCTAACGTTAGCATCGATCGGATCTAGCTAGGATCGAT" * 3
+    L, off = 30, 20
+    go = np.full(len(hap), 40, dtype=np.int8)
+    ge = np.full(len(hap), 3, dtype=np.int8)
+    mask = ("N" * len(hap)).encode()
+    prior = np.full(len(hap), 100, dtype=np.int8)
+    read = hap[off:off + L]
+    q = np.full(L, 30, dtype=np.uint8)
+    # exact match → 0 (pair_hmm.hpp:289-291)
+    assert coracle.try_naive_evaluate(hap, read, q, off, go, ge, mask, prior) == (True, 0)
+    # one mismatch, quality <= gap open → the quality (:302-303)
+    r1 = list(read); r1[10] = "A" if r1[10] != "A" else "C"; r1 = "".join(r1)
+    assert coracle.try_naive_evaluate(hap, r1, q, off, go, ge, mask, prior) == (True, 30)
+    # ... capped by the SNV prior when the mask names the read base (:250-263)
+    mask2 = bytearray(mask); mask2[off + 10] = ord(r1[10]); prior2 = prior.copy(); prior2[off + 10] = 7
+    assert coracle.try_naive_evaluate(hap, r1, q, off, go, ge, bytes(mask2), prior2) == (True, 7)
+    # in a flank → 0 (:298)
+    assert coracle.try_naive_evaluate(hap, r1, q, off, go, ge, mask, prior, flanks=(off + 11, 0)) == (True, 0)
+    # two mismatches → no shortcut
+    r2 = list(r1); r2[20] = "A" if r2[20] != "A" else "C"; r2 = "".join(r2)
+    assert coracle.try_naive_evaluate(hap, r2, q, off, go, ge, mask, prior)[0] is False
+    # evaluate() == -ln10/10 * phred on the shortcut, and the DP otherwise
+    assert coracle.evaluate(16, hap, r1, q, off, go, ge, 2, mask, prior) == -C_LN10_DIV_10 * 30
+    v, used, raw = coracle.evaluate(16, hap, r2, q, off, go, ge, 2, mask, prior, details=True)
+    assert used == 1 and raw == 60 and v == -C_LN10_DIV_10 * 60
+
+
+def _kmer_map_python(query, target, max_positions=10):
+    """Independent restatement of utils/kmer_mapper.hpp:43-159 in pure Python (small inputs only)."""
+    K = 6
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    def h(s):
+        return sum(code.get(ch, 0) * 4 ** i for i, ch in enumerate(s))
+    if len(query) < K or len(target) < K:
+        return []
+    table = {}
+    for i in range(len(target) - K + 1):
+        table.setdefault(h(target[i:i + K]), []).append(i)
+    counts = [0] * (len(target) - K + 1)
+    max_hit, first_max, num_max = 0, 0, 0
+    for qi in range(len(query) - K + 1):
+        for ti in table.get(h(query[qi:qi + K]), []):
+            if ti >= qi:
+                mb = ti - qi
+                counts[mb] += 1
+                if counts[mb] > max_hit:
+                    max_hit, first_max, num_max = counts[mb], mb, 1
+                elif counts[mb] == max_hit:
+                    num_max += 1
+                    first_max = min(first_max, mb)
+    out = []
+    if max_hit > 0:
+        out.append(first_max); first_max += 1; num_max -= 1; max_positions -= 1
+        while max_positions > 0 and num_max > 0:
+            if counts[first_max] == max_hit:
+                out.append(first_max); num_max -= 1; max_positions -= 1
+            first_max += 1
+    return out
+
+
+def test_kmer_mapper(coracle):
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        t = "".join(rng.choice(list("ACGT"), int(rng.integers(20, 200))))
+        p = int(rng.integers(0, max(1, len(t) - 10)))
+        q = t[p:p + int(rng.integers(6, 60))]
+        if rng.random() < 0.5 and len(q) > 8:
+            q = q[:4] + "ACGT"[int(rng.integers(0, 4))] + q[5:]
+        if rng.random() < 0.3:
+            t = t[:len(t) // 2] * 2          # repeats → several equally good positions
+        assert coracle.kmer_map(q, t, 10) == _kmer_map_python(q, t, 10)
+
+
+def test_model_evaluate_mapping_quality_floor(coracle):
+    """ln p = log_sum_exp(ln(1 - 10^(-mq/10)) + lnP, -ln10/10 * mq) and the > -1e-15 clamp (haplotype_likelihood_model.cpp:285-303)."""
+    hap = "ACGTTGCAAGCTTAGGCTAACGTTAGCATCGATCGGATCTAGCTAGGATCGATACGATCGATCGTAGCTAGCTAGTCGAT"
+    n = len(hap)
+    args = dict(gap_open=np.full(n, 40, np.int8), gap_extend=np.full(n, 3, np.int8), snv_mask=("N" * n).encode(), snv_prior=np.full(n, 100, np.int8))
+    read, q = hap[20:50], np.full(30, 30, np.uint8)
+    st, v, _ = coracle.model_evaluate(16, hap, read, q, positions=[], original_pos=20, mapping_quality=60, **args)
+    assert st == 0 and v == 0.0            # exact match, clamp to 0
+    st, v, _ = coracle.model_evaluate(16, hap, read, q, positions=[], original_pos=20, mapping_quality=0, **args)
+    assert st == 0 and v == 0.0            # mq 0: ln_mapped = -inf, lse(-inf, 0) = 0
+    st, v, ext = coracle.model_evaluate(16, hap[:40], read, q, positions=[], original_pos=5, mapping_quality=60,
+                                        gap_open=args["gap_open"][:40], gap_extend=args["gap_extend"][:40], snv_mask=args["snv_mask"][:40], snv_prior=args["snv_prior"][:40])
+    assert st == 1 and ext > 0             # ShortHaplotypeError
