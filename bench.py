@@ -98,6 +98,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Host threads the CPU arm may use: the cgroup CPU quota when there is one (a 128-thread box may grant a pod only a
+    few CPUs' worth of time), else the online CPU count."""
+    n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n
+
+
+def calibrated_sample(haps, reads, band, threads, target_s):
+    """Number of reads whose (reads x all haplotypes) CPU pass takes about target_s seconds (measured on a small probe)."""
+    probe = min(reads.n, max(64, 16 * threads))
+    cpu_reference_run(haps, reads, band, probe, threads)
+    g, dt, _, _, _ = cpu_reference_run(haps, reads, band, probe, threads)
+    per_read = max(dt / probe, 1e-7)
+    return int(max(probe, min(reads.n, target_s / per_read)))
+
+
 def reference_batch_dict(haps, reads):
     return dict(read_bases=reads.bases, read_quals=reads.quals, read_off=reads.off, hap_seq=haps.seq,
                 hap_mask_fwd=haps.snv_mask_fwd, hap_prior_fwd=haps.snv_prior_fwd, hap_mask_rev=haps.snv_mask_rev,
@@ -148,11 +175,12 @@ def run_reference_arm(args):
         return
     from octopus_b200 import synth
     cfg = synth.CONFIGS[args.config]
-    threads = os.cpu_count() or 1
-    n_sample = args.cpu_sample_reads or max(256, min(cfg["n_reads"], 400 * threads))
-    haps, reads, band = synth.make_batch(args.config, n_reads=n_sample, n_haps=args.haps)
+    threads = host_threads()
+    # a bounded sample of the workload per step: sized so that the whole --steps/--warmup run takes about a minute
+    haps, reads, band = synth.make_batch(args.config, n_reads=min(cfg["n_reads"], 200_000), n_haps=args.haps)
+    n_sample = args.cpu_sample_reads or calibrated_sample(haps, reads, band, threads, 60.0 / max(1, args.steps + args.warmup))
     for _ in range(max(1, args.warmup)):
-        cpu_reference_run(haps, reads, band, max(64, n_sample // 8), threads)
+        cpu_reference_run(haps, reads, band, n_sample, threads)
     t_total, cells_total, info = 0.0, 0, None
     for _ in range(args.steps):
         g, dt, kind, name, cells = cpu_reference_run(haps, reads, band, n_sample, threads)
@@ -280,9 +308,8 @@ def main():
                          "kernel_gcups": cells / (kernel_ms / 1e3) / 1e9},
         }
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            n_sample = args.cpu_sample_reads or max(256, min(R, 400 * threads))
-            cpu_reference_run(haps, reads, band, max(64, n_sample // 8), threads)
+            threads = host_threads()
+            n_sample = args.cpu_sample_reads or calibrated_sample(haps, reads, band, threads, 12.0)
             g, dt, kind, name, _ = cpu_reference_run(haps, reads, band, n_sample, threads)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
                                     "sample": "first %d reads x %d haplotypes of the same batch, %.1f s; %s" % (n_sample, H, dt, name)}

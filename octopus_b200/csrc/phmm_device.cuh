@@ -88,17 +88,21 @@ inline uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c)
 template <typename T> inline T ldg(const T* p) { return *p; }
 #endif
 
-// Row word of a read PAIR (one per read position y, shared by every lane that aligns this pair):
-//   bits  0..15  PRMT selector: nibble0 = code0, nibble1 = 8 (sign-replicate → 0x00), nibble2 = 4|code1, nibble3 = 8
-//   bits 16..23  qual0      bits 24..31  qual1
-// so that  cap  = prmt(caps0, caps1, w)          = cap0[code0] | cap1[code1] << 16
-//          qual = prmt(w, 0, 0x4342)             = qual0       | qual1       << 16
-PHMM_HD uint32_t make_row_word(uint32_t half0, uint32_t half1)
+// Row entry of a read PAIR (one per read position y, shared by every lane that aligns this pair), 8 bytes so that one
+// LDS.64 broadcast feeds a cell:
+//   .x  PRMT selector: nibble0 = code0, nibble1 = 8 (sign-replicate → 0x00), nibble2 = 4|code1, nibble3 = 8
+//   .y  qual0 | qual1 << 16
+// so that  cap = prmt(caps0, caps1, row.x) = cap0[code0] | cap1[code1] << 16   and   qual = row.y
+typedef uint2 RowEntry;
+PHMM_HD RowEntry make_row_entry(uint32_t half0, uint32_t half1)
 {
-    // half = code | qual << 8  →  bytes [code0, code1, qual0, qual1], then set the selector flag bits
-    return prmt(half0, half1, 0x5140) | 0x8480u;
+    // half = code | qual << 8
+    RowEntry r;
+    r.x = prmt(half0, half1, 0x2240u) | 0x8480u;   // bytes [code0, code1, 0, 0] + the two sign-replicate flags
+    r.y = prmt(half0, half1, 0x2521u);             // bytes [qual0, 0, qual1, 0]
+    return r;
 }
-constexpr uint32_t kPadRowWord = 0x8480u;
+PHMM_HD RowEntry pad_row_entry() { RowEntry r; r.x = 0x8480u; r.y = 0u; return r; }   // code 0 / qual 0: sub = min(0, cap) = 0
 
 // Column table entry of one haplotype base (prior, go, ge must be in [0,127]; checked by the preparation kernel).
 PHMM_HD ColEntry make_col_entry(const char truth, const char snv_mask, const int snv_prior, const int gap_open, const int gap_extend)
@@ -125,40 +129,50 @@ PHMM_HD ColEntry make_col_entry(const char truth, const char snv_mask, const int
 // Fast path: two alignments per thread, s16x2 lanes, band state in registers
 // ---------------------------------------------------------------------------------------------------------
 //
-// rows : shared-memory row words of this lane's read pair, rows[0..L-1] real, rows[L] = kPadRowWord
+// rows : shared-memory row entries of this lane's read pair, rows[0..L-1] real, rows[L] = pad_row_entry()
 // t0/t1: column tables of the two haplotype windows (already offset to the window start); W = L + 2*BAND - 1
 //        entries are read at indices 0..W-1 only
 // Returns best0 | best1 << 16 (each the integer phred score of reference hmm.align()).
 //
 // Column x holds the cells k = x - y, k in [max(0, x-L), min(2B-1, x)], processed in DESCENDING k so that the
 // insertion chain i(x, y+1) ← (x, y) runs through one register (i_run); M[k] / D[k] carry the match / deletion
-// arrivals to the next column in place. Row L uses the pad row word (qual 0 → sub 0), so after the cell
+// arrivals to the next column in place. Row L uses the pad row entry (qual 0 → sub 0), so after the cell
 // (x, L) is processed M[x-L] holds S(x, L) and is never touched again: the end-row minimum is min_k M[k].
+//
+// Four column bodies, all fully unrolled over k with M / D in registers:
+//   steady    2B <= x <= L      every cell exists
+//   prologue  x < 2B, x <= L    cell (x, 0) is the free start; cells k < x follow — entered through a jump table
+//   epilogue  x > L, x >= 2B    cells k >= x - L; leaves the unrolled sequence after the row-L cell
+//   general   x < 2B, x > L     (reads shorter than the band) both limits, per-cell predicates
+#define PHMM_REP8(F, b)  F(b + 7) F(b + 6) F(b + 5) F(b + 4) F(b + 3) F(b + 2) F(b + 1) F(b + 0)
+#define PHMM_REP64(F)    PHMM_REP8(F, 56) PHMM_REP8(F, 48) PHMM_REP8(F, 40) PHMM_REP8(F, 32) PHMM_REP8(F, 24) PHMM_REP8(F, 16) PHMM_REP8(F, 8) PHMM_REP8(F, 0)
+
 template <int BAND>
-PHMM_HD uint32_t dp_pair(const uint32_t* __restrict__ rows, const int L,
-                                            const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
-                                            const uint32_t nucp /* nuc_prior in both halves */)
+PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
+                         const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+                         const uint32_t nucp /* nuc_prior in both halves */)
 {
     constexpr int K = 2 * BAND;
+    static_assert(K <= 64, "register band limited to 64 diagonals");
     uint32_t M[K], D[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kInf16x2; }
     const int W = L + K - 1;
     ColEntry e0 = ldg(t0), e1 = ldg(t1);
     uint32_t go_prev = 0u, ge_prev = 0u;
-    const uint32_t w0 = rows[0];
+    const RowEntry w0 = rows[0];
 
 #define PHMM_CELL(k)                                                                        \
     {                                                                                       \
-        const uint32_t w   = rp[-(k)];                                                      \
-        const uint32_t cap = prmt(caps0, caps1, w);                                         \
-        const uint32_t q   = prmt(w, 0u, 0x4342u);                                          \
-        const uint32_t sub = vmin2(q, cap);                                              \
-        const uint32_t m = M[k], d = D[k];                                                  \
-        M[k] = vmin3(m, i_run, d) + sub;                                           \
+        const RowEntry w   = rp[-(k)];                                                      \
+        const uint32_t sub = vmin2(w.y, prmt(caps0, caps1, w.x));                           \
+        const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                  \
+        M[(k) < K ? (k) : 0] = vmin3(m, i_run, d) + sub;                                    \
         if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = vaddmin(d, ge, vmin2(m, i_run) + go); \
-        i_run = vaddmin(i_run, gep, m + gop);                                      \
+        i_run = vaddmin(i_run, gep, m + gop);                                               \
     }
+#define PHMM_CASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_CELL(k)
+#define PHMM_CASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
 
     for (int x = 0; x <= W; ++x) {
         const int xn = (x + 1 < W) ? x + 1 : W - 1;
@@ -168,29 +182,45 @@ PHMM_HD uint32_t dp_pair(const uint32_t* __restrict__ rows, const int L,
         const uint32_t ge = prmt(e0.y, e1.y, 0x2521u);   // gap_extend[x]
         const uint32_t gop = go_prev + nucp;             // gap_open[x-1] + nuc_prior
         const uint32_t gep = ge_prev + nucp;             // gap_extend[x-1] + nuc_prior
-        const uint32_t* rp = rows + x;
+        const RowEntry* rp = rows + x;
         uint32_t i_run = kInf16x2;
-        if (x >= K && x <= L) {
-            // steady state: every cell of the column exists
+        if (x >= K) {
+            if (x <= L) {
+                // steady state: every cell of the column exists
 #pragma unroll
-            for (int k = K - 1; k >= 0; --k) PHMM_CELL(k)
-        } else {
-            // first 2B columns (row 0 enters at k == x) and last 2B-1 columns (rows beyond L are skipped)
-            const int klo = x - L;
+                for (int k = K - 1; k >= 0; --k) PHMM_CELL(k)
+            } else {
+                // epilogue: rows beyond L do not exist; stop after the row-L cell so that M[x-L] keeps S(x, L)
+                const int klo = x - L;
 #pragma unroll
-            for (int k = K - 1; k >= 0; --k) {
-                if (k == x) {
-                    // cell (x, 0): S = 0. m(x+1, 1) = sub(x, 0); i(x, 1) = gap_open[x-1] + nuc for odd x, +inf for even x
-                    M[k] = vmin2(prmt(w0, 0u, 0x4342u), prmt(caps0, caps1, w0));
-                    i_run = (x & 1) ? gop : kInf16x2;
-                } else if (k < x && k >= klo) {
+                for (int k = K - 1; k >= 0; --k) {
                     PHMM_CELL(k)
+                    if (k == klo) break;
                 }
+            }
+        } else {
+            // cell (x, 0): S = 0, so m(x+1, 1) = sub(x, 0), and i(x, 1) = gap_open[x-1] + nuc for odd x, +inf for even x
+            const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));
+            i_run = (x & 1) ? gop : kInf16x2;
+            if (x <= L) {
+                // prologue: cells k = x-1 .. 0 all exist — jump into the unrolled sequence at k = x-1
+                switch (x) { PHMM_REP64(PHMM_CASE_PROLOGUE) default: break; }
+                switch (x) { PHMM_REP64(PHMM_CASE_ROW0) default: break; }
+            } else {
+                // reads shorter than the band: both limits apply
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    if (k < x && k >= klo) PHMM_CELL(k)
+                }
+                switch (x) { PHMM_REP64(PHMM_CASE_ROW0) default: break; }
             }
         }
         go_prev = go; ge_prev = ge; e0 = n0; e1 = n1;
     }
 #undef PHMM_CELL
+#undef PHMM_CASE_PROLOGUE
+#undef PHMM_CASE_ROW0
     uint32_t best = M[0];
 #pragma unroll
     for (int k = 1; k < K; ++k) best = vmin2(best, M[k]);

@@ -339,7 +339,7 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         CU(cudaMemcpyAsync(e->tasks_lane.p, lane.data(), lane.size() * sizeof(LaneTask), cudaMemcpyHostToDevice, e->stream));
         CU(cudaMemcpyAsync(e->works.p, works.data(), works.size() * sizeof(WarpWork), cudaMemcpyHostToDevice, e->stream));
         const int row_stride = (Lmax + 2) & ~1;
-        const size_t smem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(uint32_t);
+        const size_t smem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
         const int nw = (int)works.size();
         const unsigned grid = (unsigned)((nw + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
         const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
@@ -492,7 +492,7 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     }
 
     p.row_stride = (Lmax_fast + 2) & ~1;
-    const size_t smem = (size_t)kFastWarpsPerBlock * (p.row_stride + 4 * kQueueCap) * sizeof(uint32_t);
+    const size_t smem = (size_t)kFastWarpsPerBlock * (p.row_stride + 2 * kQueueCap) * sizeof(RowEntry);
     int blocks_per_sm = 1;
     if (n_pairs) {
         switch (band) {

@@ -84,12 +84,12 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
 }
 
 // Cooperative fill of one warp's shared row words for the read pair (r0, r1); r1 < 0 → second half padded.
-__device__ __forceinline__ void fill_rows(uint32_t* rows, const DevReads& rd, const int r0, const int r1, const int L, const int lane)
+__device__ __forceinline__ void fill_rows(RowEntry* rows, const DevReads& rd, const int r0, const int r1, const int L, const int lane)
 {
     const uint16_t* h0 = rd.rowhalf + rd.off[r0];
     const uint16_t* h1 = r1 >= 0 ? rd.rowhalf + rd.off[r1] : nullptr;
-    for (int y = lane; y < L; y += 32) rows[y] = make_row_word(h0[y], h1 ? (uint32_t)h1[y] : 0u);
-    if (lane == 0) rows[L] = kPadRowWord;
+    for (int y = lane; y < L; y += 32) rows[y] = make_row_entry(h0[y], h1 ? (uint32_t)h1[y] : 0u);
+    if (lane == 0) rows[L] = pad_row_entry();
     __syncwarp();
 }
 
@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
 k_packed_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTask* __restrict__ tasks,
                const DevHaps hp, const DevReads rd, const int row_stride, const uint32_t nucp, int* __restrict__ scores)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * kFastWarpsPerBlock + warp;
     if (w >= n_works) return;
     const WarpWork ww = works[w];
-    uint32_t* rows = smem + warp * row_stride;
+    RowEntry* rows = smem_rows + warp * row_stride;
     fill_rows(rows, rd, ww.read0, ww.read1, ww.L, lane);
     const bool v0 = lane < ww.n0, v1 = lane < ww.n1;
     const LaneTask a = tasks[v0 ? ww.first0 + lane : ww.first0];
@@ -174,7 +174,7 @@ struct PopParams {
     const int* pair_reads;
     int n_pairs;
     int* pair_cursor;           // persistent-warp work counter
-    int row_stride;             // shared-memory words per warp for row words
+    int row_stride;             // shared-memory row entries (8 bytes) per warp
     // generic path work list
     const int* generic_reads;
     int n_generic;
@@ -207,13 +207,13 @@ constexpr int kQueueCap = 64;
 // compacted into two per-half queues in shared memory; whenever a queue holds 32 tasks the warp runs one dp_pair
 // round — 64 alignments, two per lane — and folds the scores into best[] with atomicMin.
 template <int BAND>
-__global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 2)
 k_populate_fast(const PopParams p)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = p.row_stride + 4 * kQueueCap;
-    uint32_t* rows = smem + warp * per_warp;
+    const int per_warp = p.row_stride + 2 * kQueueCap;      // in 8-byte units: row entries, then the two task queues
+    RowEntry* rows = smem_rows + warp * per_warp;
     int* qh = (int*)(rows + p.row_stride);          // [2][kQueueCap] haplotype index
     int* qa = qh + 2 * kQueueCap;                   // [2][kQueueCap] window offset
     const int H = p.hp.n, R = p.rd.n;

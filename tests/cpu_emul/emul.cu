@@ -8,7 +8,7 @@
 using namespace phmm;
 
 template <int BAND>
-static uint32_t run_pair(int L, const std::vector<uint32_t>& rows, const ColEntry* t0, const ColEntry* t1, uint32_t nucp)
+static uint32_t run_pair(int L, const std::vector<RowEntry>& rows, const ColEntry* t0, const ColEntry* t1, uint32_t nucp)
 {
     return dp_pair<BAND>(rows.data(), L, t0, t1, nucp);
 }
@@ -23,13 +23,13 @@ int emul_dp_pair(int band, int L, const char* read0, const uint8_t* q0, const ch
                  int nuc_prior, int* score0, int* score1)
 {
     const int W = L + 2 * band - 1;
-    std::vector<uint32_t> rows(L + 1);
+    std::vector<RowEntry> rows(L + 1);
     for (int y = 0; y < L; ++y) {
         const int c0 = base_code(read0[y]), c1 = base_code(read1[y]);
         if (c0 < 0 || c1 < 0) return -1;
-        rows[y] = make_row_word((uint32_t)c0 | ((uint32_t)q0[y] << 8), (uint32_t)c1 | ((uint32_t)q1[y] << 8));
+        rows[y] = make_row_entry((uint32_t)c0 | ((uint32_t)q0[y] << 8), (uint32_t)c1 | ((uint32_t)q1[y] << 8));
     }
-    rows[L] = kPadRowWord;
+    rows[L] = pad_row_entry();
     std::vector<ColEntry> t0(W), t1(W);
     for (int x = 0; x < W; ++x) {
         t0[x] = make_col_entry(truth0[x], mask0[x], prior0[x], go0[x], ge0[x]);
