@@ -130,6 +130,18 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
                       const phmm_haplotypes* haps, const phmm_reads* reads,
                       const phmm_task* tasks, int64_t n_tasks, int32_t* scores, int space);
 
+/* Per-call seam with traceback, host pointers only: the reference kernel's traceback overload
+ *   hmm.align(truth, target, quals, truth_len, target_len, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior,
+ *             first_pos, align1, align2)                                   simd_pair_hmm.hpp:491-509
+ * truth_len must be target_len + 2*band - 1; snv_mask == NULL selects the no-SNV overload (:472-489) and
+ * gap_extend == NULL the scalar-extend overload (value gap_extend_scalar). align1 / align2: caller-allocated,
+ * >= 2*(target_len + band) + 1 bytes, NUL-terminated on return ('-' marks gaps); *first_pos = -1 on overflow. */
+int phmm_align_traceback(phmm_engine* e, int band,
+                         const char* truth, const char* target, const int8_t* quals, int truth_len, int target_len,
+                         const char* snv_mask, const int8_t* snv_prior, const int8_t* gap_open,
+                         const int8_t* gap_extend, int gap_extend_scalar, int nuc_prior,
+                         int* score, int* first_pos, char* align1, char* align2);
+
 /* Batch boundary: out[h*R + r] == HaplotypeLikelihoodArray likelihoods_[h][sample][r] for a single-sample ReadMap
  * (haplotype_likelihood_array.cpp:77-95). status (optional, [H*R]) receives PHMM_STATUS_*.
  * Returns PHMM_ERR_SHORT_HAPLOTYPE if any pair raised ShortHaplotypeError (the reference throws out of populate). */

@@ -104,6 +104,31 @@ class PairHMMEngine:
             self._raise(rc)
         return out
 
+    def align(self, band, truth, target, quals, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
+        """Per-call seam with traceback ↔ simd::PairHMM::align(..., first_pos, align1, align2) (simd_pair_hmm.hpp:472-509).
+        Returns (score, first_pos, aligned_truth, aligned_target). gap_extend may be a scalar (the reference's scalar overload)."""
+        t = truth.encode() if isinstance(truth, str) else bytes(np.asarray(truth, dtype=np.uint8))
+        r = target.encode() if isinstance(target, str) else bytes(np.asarray(target, dtype=np.uint8))
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.int8))
+        go = np.ascontiguousarray(np.asarray(gap_open, dtype=np.int8))
+        if np.ndim(gap_extend) == 0:
+            ge, gep, ges = None, None, int(gap_extend)
+        else:
+            ge = np.ascontiguousarray(np.asarray(gap_extend, dtype=np.int8)); gep, ges = ge.ctypes.data, 0
+        if snv_mask is not None:
+            m = snv_mask.encode() if isinstance(snv_mask, str) else bytes(np.asarray(snv_mask, dtype=np.uint8))
+            sp = np.ascontiguousarray(np.asarray(snv_prior, dtype=np.int8)); spp = sp.ctypes.data
+        else:
+            m, spp = None, None
+        n = 2 * (len(r) + band) + 1
+        a1, a2 = C.create_string_buffer(n + 8), C.create_string_buffer(n + 8)
+        score, fp = C.c_int(0), C.c_int(0)
+        rc = self._lib.phmm_align_traceback(self._h, int(band), t, r, q.ctypes.data, len(t), len(r), m, spp, go.ctypes.data, gep, ges,
+                                            int(nuc_prior), C.byref(score), C.byref(fp), a1, a2)
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+        return score.value, fp.value, a1.value.decode(), a2.value.decode()
+
     # -- batch boundary ----------------------------------------------------------------------------------------
     def populate(self, config, haps: HaplotypeBlock, reads: ReadBlock, positions=None, flank_state=None, out=None,
                  want_status=False):

@@ -262,7 +262,7 @@ constexpr int kGenericMaxDiag = 512;   // 2 * 256, the reference's widest band (
 template <bool TB, int MAXK>
 __host__ __device__ inline int generic_align(const int band, const GenericModel& gm, const char* target, const int8_t* quals, const int L,
                              unsigned char* __restrict__ bp, const size_t bps, const int lhs_flank, const int rhs_flank,
-                             int* first_pos, int* flank_score, int* mask_size)
+                             int* first_pos, int* flank_score, int* mask_size, char* align1 = nullptr, char* align2 = nullptr)
 {
     const int K = 2 * band, W = L + K - 1;
     int Mc[MAXK], Ic[MAXK];
@@ -307,7 +307,7 @@ __host__ __device__ inline int generic_align(const int band, const GenericModel&
         // gap OPEN for the first op of a run (prev_state != state, in forward order) and EXTEND otherwise; walking
         // backwards the "first op of a run" is the one whose predecessor state differs, which is ns below.
         const int rhs_begin = W - rhs_flank;
-        int x = best_x, y = L, state = best & 3, fs = 0, ms = 0;
+        int x = best_x, y = L, state = best & 3, fs = 0, ms = 0, n = 0;
         bool ok = true;
         while (y > 0) {
             const int k = x - y;
@@ -316,6 +316,7 @@ __host__ __device__ inline int generic_align(const int band, const GenericModel&
             int ns;
             if (state == LM) {
                 ns = b & 3; --x; --y;
+                if (align1) { align1[n] = gm.truth[x]; align2[n] = target[y]; }
                 const bool inf = x < lhs_flank || x >= rhs_begin;     // truth_idx of this op == x after the decrement
                 if (inf) {
                     const char t = gm.truth[x], r = target[y];
@@ -327,14 +328,24 @@ __host__ __device__ inline int generic_align(const int band, const GenericModel&
                 }
             } else if (state == LI) {
                 ns = (b >> 2) & 3; --y;
+                if (align1) { align1[n] = '-'; align2[n] = target[y]; }
                 const bool inf = x < lhs_flank || x >= rhs_begin;     // truth_idx of an insertion == current x
                 if (inf) { fs += (ns == LI ? (int)gm.gap_extend[x - 1] : (int)gm.gap_open[x - 1]) + gm.nuc_prior; ++ms; }
             } else {
                 ns = (b >> 4) & 3; --x;
+                if (align1) { align1[n] = gm.truth[x]; align2[n] = '-'; }
                 const bool inf = x < lhs_flank || x >= rhs_begin;
                 if (inf) fs += (ns == LD ? (int)gm.gap_extend[x] : (int)gm.gap_open[x]);
             }
             state = ns;
+            ++n;
+        }
+        if (align1 && ok) {   // the strings were produced end-first: reverse and terminate (simd_pair_hmm.hpp:219-230)
+            align1[n] = 0; align2[n] = 0;
+            for (int a = 0, b = n - 1; a < b; ++a, --b) {
+                char t = align1[a]; align1[a] = align1[b]; align1[b] = t;
+                t = align2[a]; align2[a] = align2[b]; align2[b] = t;
+            }
         }
         if (!ok) { *first_pos = -1; *flank_score = 0; *mask_size = 0; return score; }
         *first_pos = x; *flank_score = fs; *mask_size = ms;

@@ -381,6 +381,52 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// phmm_align_traceback
+// -------------------------------------------------------------------------------------------------------------
+int phmm_align_traceback(phmm_engine* e, int band,
+                         const char* truth, const char* target, const int8_t* quals, int truth_len, int target_len,
+                         const char* snv_mask, const int8_t* snv_prior, const int8_t* gap_open,
+                         const int8_t* gap_extend, int gap_extend_scalar, int nuc_prior,
+                         int* score, int* first_pos, char* align1, char* align2)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    e->err.clear(); e->launches_last = 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    if (band > 256) { e->err = "band > 256"; return PHMM_ERR_BAND; }
+    if (band < 1 || !truth || !target || !quals || !gap_open || !score || !first_pos || !align1 || !align2 ||
+        target_len < 1 || truth_len != target_len + 2 * band - 1) {
+        e->err = "bad argument (truth_len must be target_len + 2*band - 1)";
+        return PHMM_ERR_INVALID;
+    }
+    const int W = truth_len, L = target_len;
+    std::vector<char> host((size_t)5 * W + 2 * L);
+    std::memcpy(host.data(), truth, W);
+    if (snv_mask) { std::memcpy(host.data() + W, snv_mask, W); std::memcpy(host.data() + 2 * W, snv_prior, W); }
+    else { std::memset(host.data() + W, 0, W); std::memset(host.data() + 2 * W, 127, W); }   // a mask byte no base equals
+    std::memcpy(host.data() + 3 * W, gap_open, W);
+    if (gap_extend) std::memcpy(host.data() + 4 * W, gap_extend, W); else std::memset(host.data() + 4 * W, gap_extend_scalar, W);
+    std::memcpy(host.data() + 5 * W, target, L);
+    std::memcpy(host.data() + 5 * W + L, quals, L);
+    const size_t nal = (size_t)2 * (L + band) + 1, nbp = (size_t)(L + 1) * 2 * band;
+    CU(e->tasks_generic.ensure(host.size()));
+    CU(e->bp.ensure(nbp + 2 * nal + 64));
+    CU(e->scores.ensure(2 * sizeof(int)));
+    CU(cudaMemcpyAsync(e->tasks_generic.p, host.data(), host.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(e->bp.p, 0, nbp + 2 * nal, e->stream));
+    unsigned char* bp = e->bp.as<unsigned char>();
+    k_align_one<<<1, 32, 0, e->stream>>>(band, L, e->tasks_generic.as<char>(), nuc_prior, bp, e->scores.as<int>(), (char*)bp + nbp, (char*)bp + nbp + nal);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    int out[2];
+    CU(cudaMemcpyAsync(out, e->scores.p, sizeof(out), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(align1, bp + nbp, nal, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(align2, bp + nbp + nal, nal, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *score = out[0]; *first_pos = out[1];
+    return PHMM_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // phmm_populate
 // -------------------------------------------------------------------------------------------------------------
 int phmm_populate(phmm_engine* e, const phmm_config* cfg,

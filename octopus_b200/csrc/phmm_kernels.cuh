@@ -370,6 +370,20 @@ __global__ void k_slow_flank(const PopParams p, unsigned char* __restrict__ bp)
     }
 }
 
+// Per-call seam with traceback (reference hmm.align(..., first_pos, align1, align2), simd_pair_hmm.hpp:491-509): one
+// thread, for parity with the reference's API — throughput comes from the batched entry points.
+// buf layout: truth[W] mask[W] prior[W] go[W] ge[W] target[L] quals[L]; out: {score, first_pos}; strings after bp.
+__global__ void k_align_one(const int band, const int L, const char* __restrict__ buf, const int nuc_prior,
+                            unsigned char* __restrict__ bp, int* __restrict__ out, char* __restrict__ align1, char* __restrict__ align2)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int W = L + 2 * band - 1;
+    const GenericModel gm {buf, buf + W, (const int8_t*)(buf + 2 * W), (const int8_t*)(buf + 3 * W), (const int8_t*)(buf + 4 * W), nuc_prior};
+    int fp, fs, ms;
+    out[0] = generic_align<true, kGenericMaxDiag>(band, gm, buf + 5 * W, (const int8_t*)(buf + 5 * W + L), L, bp, 1, 0, 0, &fp, &fs, &ms, align1, align2);
+    out[1] = fp;
+}
+
 __global__ void k_fill_int(int* __restrict__ p, const long long n, const int v)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

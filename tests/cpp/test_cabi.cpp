@@ -1,0 +1,51 @@
+// Plain C++14 client of the C ABI and the C++ adapter (no torch, no Python): built by tests/test_gpu_cpp.py with g++ and
+// run on the GPU box. Reads one KAT and one tiny populate problem from stdin-free hardcoded data, prints results.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "phmm_b200.hpp"
+
+int main()
+{
+    using namespace octopus_b200;
+    try {
+        // reference KAT: sse2_band_size_8_check_alignments test 5 (test/unit/core/models/pair_hmm_tests.cpp:290-313)
+        const std::string truth = "CCCCACGTATATATATATATATGGGGACGT", read = "CCCCACGTGGGACGT";
+        std::vector<std::int8_t> quals(read.size(), 40), gap_open(truth.size(), 90);
+        gap_open[8] = 70;
+        GpuPairHMM<8> hmm;
+        std::vector<char> a1(2 * truth.size() + 1, 0), a2(2 * truth.size() + 1, 0);
+        int first_pos = -7;
+        const int s1 = hmm.align(truth.data(), read.data(), quals.data(), (int)truth.size(), (int)read.size(), gap_open.data(), (short)1, (short)4);
+        const int s2 = hmm.align(truth.data(), read.data(), quals.data(), (int)truth.size(), (int)read.size(), gap_open.data(), (short)1, (short)4,
+                                 first_pos, a1.data(), a2.data());
+        std::printf("KAT %d %d %d %s %s\n", s1, s2, first_pos, a1.data(), a2.data());
+        // batch seam: 2 haplotypes x 2 reads
+        HaplotypeBlock haps;
+        ReadBlock reads;
+        const std::string h0 = "ACGTTGCAAGCTTAGGCTAACGTTAGCATCGATCGGATCTAGCTAGGATCGATACGATCGATCGTAGCTAGCTAGTCGATCGATTTAGCGCGATATCGCGAT";
+        std::string h1 = h0; h1[50] = h1[50] == 'A' ? 'C' : 'A';
+        for (const auto& h : {h0, h1}) {
+            std::vector<char> mf(h.begin(), h.end()), mr(h.begin(), h.end());
+            std::vector<std::int8_t> p(h.size(), 50), go(h.size(), 40), ge(h.size(), 3);
+            haps.add(h, mf, p, mr, p, go, ge, 0);
+        }
+        reads.add(h0.substr(30, 40), std::vector<std::uint8_t>(40, 30), 60, false, 30);
+        reads.add(h1.substr(35, 40), std::vector<std::uint8_t>(40, 25), 60, true, 35);
+        auto cfg = HaplotypeLikelihoodArray::default_config();
+        cfg.max_indel_error = 16;
+        HaplotypeLikelihoodArray arr {cfg};
+        arr.populate(reads, haps);
+        for (std::size_t h = 0; h < 2; ++h) { const auto row = arr[h]; std::printf("ROW %zu %.17g %.17g\n", h, row[0], row[1]); }
+        // ShortHaplotypeError must surface as the reference's exception type
+        ReadBlock longread;
+        longread.add(h0.substr(0, 95), std::vector<std::uint8_t>(95, 30), 60, false, 0);
+        try { arr.populate(longread, haps); std::printf("SHORT none\n"); }
+        catch (const ShortHaplotypeError& e) { std::printf("SHORT hap=%zu ext=%u\n", e.haplotype_index(), e.required_extension()); }
+    } catch (const std::exception& e) {
+        std::printf("EXCEPTION %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -146,3 +146,20 @@ def test_packed_16bit_path_equals_int32_path_at_scale(engine):
         a = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True), haps, reads)
         b = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, use_int_scores=True), haps, reads)
         assert np.array_equal(a, b), name
+
+
+def test_traceback_seam_reproduces_reference_kats(engine, kats, coracle):
+    """phmm_align_traceback == the reference's traceback overload: score, first_pos and both alignment strings of every KAT,
+    and the oracle's traceback on random SNV-mask inputs."""
+    for c in kats:
+        got = engine.align(c["band"], c["truth"], c["read"], c["quals"], c["gap_open"], c["gap_extend"], c["nuc_prior"])
+        assert got == (c["score"], c["first_pos"], c["align_truth"], c["align_read"]), (c["suite"], c["index"])
+    from helpers import random_alignment_case
+    rng = np.random.default_rng(77)
+    for _ in range(60):
+        band = int(rng.choice([8, 16, 32, 64]))
+        c = random_alignment_case(rng, band, int(rng.integers(1, 120)))
+        q8 = c["quals"].astype(np.int8)
+        got = engine.align(band, c["truth"].tobytes(), c["read"].tobytes(), q8, c["gap_open"], c["gap_extend"], 3, c["snv_mask"].tobytes(), c["snv_prior"])
+        want = coracle.align_tb(band, c["truth"].tobytes(), c["read"].tobytes(), q8, c["gap_open"], c["gap_extend"], 3, c["snv_mask"].tobytes(), c["snv_prior"])
+        assert got == want
