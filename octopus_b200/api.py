@@ -107,8 +107,13 @@ class PairHMMEngine:
     def align(self, band, truth, target, quals, gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
         """Per-call seam with traceback ↔ simd::PairHMM::align(..., first_pos, align1, align2) (simd_pair_hmm.hpp:472-509).
         Returns (score, first_pos, aligned_truth, aligned_target). gap_extend may be a scalar (the reference's scalar overload)."""
-        t = truth.encode() if isinstance(truth, str) else bytes(np.asarray(truth, dtype=np.uint8))
-        r = target.encode() if isinstance(target, str) else bytes(np.asarray(target, dtype=np.uint8))
+        def as_bytes(x):
+            if isinstance(x, str):
+                return x.encode()
+            if isinstance(x, (bytes, bytearray)):
+                return bytes(x)
+            return np.ascontiguousarray(np.asarray(x)).view(np.uint8).tobytes()
+        t, r = as_bytes(truth), as_bytes(target)
         q = np.ascontiguousarray(np.asarray(quals, dtype=np.int8))
         go = np.ascontiguousarray(np.asarray(gap_open, dtype=np.int8))
         if np.ndim(gap_extend) == 0:
@@ -116,7 +121,7 @@ class PairHMMEngine:
         else:
             ge = np.ascontiguousarray(np.asarray(gap_extend, dtype=np.int8)); gep, ges = ge.ctypes.data, 0
         if snv_mask is not None:
-            m = snv_mask.encode() if isinstance(snv_mask, str) else bytes(np.asarray(snv_mask, dtype=np.uint8))
+            m = as_bytes(snv_mask)
             sp = np.ascontiguousarray(np.asarray(snv_prior, dtype=np.int8)); spp = sp.ctypes.data
         else:
             m, spp = None, None
