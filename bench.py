@@ -218,7 +218,7 @@ def main():
     haps, reads, band = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=cfg["seed"] + 1000 * rank)
     H, R = haps.n, reads.n
     cells = synth.total_cells(haps, reads, band)
-    model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True)
+    model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, map_positions=False)
     eng = PairHMMEngine(local)
     d_haps, d_reads = haps.to_device(dev), reads.to_device(dev)
     d_out = torch.empty((H, R), dtype=torch.float64, device=dev)

@@ -58,6 +58,9 @@ typedef struct {
     int32_t use_flank_state;             /* default 1 */
     int32_t nuc_prior;                   /* default 2 (pair_hmm.hpp:86) */
     int32_t disable_naive_shortcut;      /* 1: every candidate goes through the DP (benchmark mode; NOT reference behaviour) */
+    int32_t map_positions;               /* 1 (default): when no candidate positions are supplied, compute them on the device with
+                                            the reference's k-mer mapper (utils/kmer_mapper.hpp:43-159, K = 6, <= 10 positions), as
+                                            populate does inline (haplotype_likelihood_array.cpp:89-92); 0: original position only */
 } phmm_config;
 
 /* H haplotypes, struct of arrays. Per-base arrays are concatenated; haplotype h owns [off[h], off[h+1]).
@@ -87,7 +90,8 @@ typedef struct {
 } phmm_reads;
 
 /* Candidate mapping positions per (haplotype, read) pair, CSR in [H][R] order
- * (what map_query_to_target emits, utils/kmer_mapper.hpp:120-159). NULL → only the original position is tried. */
+ * (what map_query_to_target emits, utils/kmer_mapper.hpp:120-159). NULL → mapped on the device (config.map_positions = 1)
+ * or only the original position is tried (map_positions = 0). */
 typedef struct {
     const int64_t* off;            /* [H*R + 1] */
     const int32_t* pos;

@@ -15,7 +15,8 @@ EXPORTS = ["phmm_version", "phmm_default_config", "phmm_create", "phmm_destroy",
 class Config(C.Structure):
     _fields_ = [("max_indel_error", C.c_int32), ("use_int_scores", C.c_int32), ("use_mapping_quality", C.c_int32),
                 ("mapping_quality_cap", C.c_int32), ("mapping_quality_cap_trigger", C.c_int32),
-                ("use_flank_state", C.c_int32), ("nuc_prior", C.c_int32), ("disable_naive_shortcut", C.c_int32)]
+                ("use_flank_state", C.c_int32), ("nuc_prior", C.c_int32), ("disable_naive_shortcut", C.c_int32),
+                ("map_positions", C.c_int32)]
 
 
 class Haplotypes(C.Structure):

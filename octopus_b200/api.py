@@ -192,7 +192,7 @@ class HaplotypeLikelihoodModel:
     class Config:
         def __init__(self, use_mapping_quality=True, mapping_quality_cap_trigger=None, mapping_quality_cap=120,
                      use_flank_state=True, max_indel_error=8, use_int_scores=False, nuc_prior=2,
-                     disable_naive_shortcut=False):
+                     disable_naive_shortcut=False, map_positions=True):
             self.use_mapping_quality = use_mapping_quality
             self.mapping_quality_cap_trigger = mapping_quality_cap_trigger
             self.mapping_quality_cap = mapping_quality_cap
@@ -201,6 +201,7 @@ class HaplotypeLikelihoodModel:
             self.use_int_scores = use_int_scores
             self.nuc_prior = nuc_prior
             self.disable_naive_shortcut = disable_naive_shortcut
+            self.map_positions = map_positions   # run the reference's k-mer mapper on the device when no positions are given
 
         def c_struct(self):
             trig = self.mapping_quality_cap_trigger
@@ -209,7 +210,8 @@ class HaplotypeLikelihoodModel:
                 trig = None
             return _lib.Config(int(self.max_indel_error), int(self.use_int_scores), int(self.use_mapping_quality),
                                int(self.mapping_quality_cap), -1 if trig is None else int(trig),
-                               int(self.use_flank_state), int(self.nuc_prior), int(self.disable_naive_shortcut))
+                               int(self.use_flank_state), int(self.nuc_prior), int(self.disable_naive_shortcut),
+                               int(self.map_positions))
 
     def __init__(self, config=None):
         self.config = config or HaplotypeLikelihoodModel.Config()

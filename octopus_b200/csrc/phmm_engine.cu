@@ -57,6 +57,7 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, bp;
     DBuf tasks_lane, tasks_generic, works, scores;
+    DBuf rhash, kbins, kitems, kpos, kcnt;
     std::vector<int2> info_host;
 };
 
@@ -199,6 +200,7 @@ void phmm_default_config(phmm_config* c)
     c->use_flank_state = 1;
     c->nuc_prior = 2;
     c->disable_naive_shortcut = 0;
+    c->map_positions = 1;
 }
 
 static std::string g_create_error;
@@ -242,7 +244,8 @@ void phmm_destroy(phmm_engine* e)
     DBuf* all[] = {&e->h_off, &e->h_seq, &e->h_mf, &e->h_pf, &e->h_mr, &e->h_pr, &e->h_go, &e->h_ge, &e->h_begin,
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
-                   &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores};
+                   &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt};
     for (DBuf* b : all) b->release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -467,7 +470,24 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
         p.pos_off = po; p.pos = pv;
         max_cand = 12;   // kmer mapper emits <= 10 (haplotype_likelihood_array.hpp:103-104) + original + fallback
     } else {
-        max_cand = 2;
+        max_cand = cfg->map_positions ? 12 : 2;
+    }
+    const bool use_mapper = !(positions && positions->off && positions->pos) && cfg->map_positions;
+    int mapper_maxt = 0;
+    if (use_mapper) {
+        long long max_hap = 0;
+        for (int h = 0; h < H; ++h) max_hap = std::max(max_hap, s.hap_off_host[h + 1] - s.hap_off_host[h]);
+        mapper_maxt = max_hap - 5 <= 512 ? 512 : 2048;
+        if (max_hap - 5 > 2048) { e->err = "haplotype longer than 2053 bp: the device k-mer mapper cannot take it (pass explicit positions)"; return PHMM_ERR_INVALID; }
+        if (s.hap_bases > 65535LL * 65535LL) { e->err = "haplotype block too large"; return PHMM_ERR_INVALID; }
+        CU(e->rhash.ensure((size_t)s.read_bases * sizeof(uint16_t)));
+        CU(e->kbins.ensure((size_t)H * (kKmerBins + 1) * sizeof(int)));
+        CU(e->kitems.ensure((size_t)s.hap_bases * sizeof(uint16_t)));
+        k_read_kmers<<<(unsigned)(((long long)R * 32 + 255) / 256), 256, 0, e->stream>>>(s.read_bases, R, s.rd.off, s.rd.bases, e->rhash.as<uint16_t>());
+        LAUNCHED();
+        k_build_kmer_table<<<H, 256, 0, e->stream>>>(H, s.hp.off, s.hp.seq, e->kbins.as<int>(), e->kitems.as<uint16_t>());
+        LAUNCHED();
+        CU(cudaGetLastError());
     }
 
     // scheduling: equal-length read pairs for the packed kernel, everything else to the generic kernel
@@ -524,9 +544,16 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     // near-flank (traceback) queue, processed tile by tile so that its worst case fits the budget
     const long long slow_budget = 8LL << 20;   // entries (16 bytes each)
     long long reads_per_tile = R;
+    if (use_mapper) {
+        // mapped candidate lists of one tile: (10 x int32 + 1 byte) per (read, haplotype) pair, at most ~1 GiB
+        reads_per_tile = std::max<long long>(2, std::min<long long>(R + 1, (1LL << 30) / (41LL * H)));
+        const size_t pairs_cap = (size_t)std::min<long long>(reads_per_tile + 2, (long long)R + 2) * H;
+        CU(e->kpos.ensure(pairs_cap * kMaxMapped * sizeof(int32_t)));
+        CU(e->kcnt.ensure(pairs_cap));
+    }
     const int slow_threads = e->sm_count * 256;
     if (p.use_flanks) {
-        reads_per_tile = std::max<long long>(2, slow_budget / ((long long)H * max_cand));
+        reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
         p.slow_cap = (int)std::min<long long>(slow_budget, (long long)H * max_cand * std::min<long long>(reads_per_tile, R));
         CU(e->slow.ensure((size_t)p.slow_cap * sizeof(int4)));
         p.slow = e->slow.as<int4>();
@@ -559,6 +586,13 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
             const int np = (int)std::min<long long>(pairs_per_tile, n_pairs - p0);
             p.pair_reads = e->pairs.as<int>() + 2 * p0;
             p.n_pairs = np;
+            if (use_mapper) {
+                const long long threads = 2LL * np * H;
+                if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                LAUNCHED();
+                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>(); p.k_first_list_index = 0;
+            }
             CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
             const int want_blocks = (np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock;
             const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
@@ -575,6 +609,13 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
             const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);
             p.generic_reads = e->generic_reads.as<int>() + g0;
             p.n_generic = ng;
+            if (use_mapper) {
+                const long long threads = (long long)ng * H;
+                if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.generic_reads, ng, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.generic_reads, ng, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                LAUNCHED();
+                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>(); p.k_first_list_index = 0;
+            }
             const long long threads = (long long)ng * H;
             if (!timed) CU(cudaEventRecord(e->ev0, e->stream));
             if (band <= 32) k_populate_generic<64><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);

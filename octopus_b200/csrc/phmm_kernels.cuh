@@ -159,6 +159,11 @@ struct PopParams {
     DevReads rd;
     const long long* pos_off;   // CSR over [H][R] pairs, or null
     const int32_t* pos;
+    // device k-mer mapper output for the current tile (utils/kmer_mapper.hpp:120-159), or null: list index li (position of the
+    // read in the tile's work list) and haplotype h own kpos[(li * H + h) * kMaxMapped .. ), kcnt[li * H + h] entries
+    const int32_t* kpos;
+    const uint8_t* kcnt;
+    int k_first_list_index;     // list index of the first read of this launch's work list
     int band, nuc_prior;
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
     int use_flanks;             // flank_state present && config.use_flank_state
@@ -200,6 +205,108 @@ __device__ __forceinline__ void push_slow(const PopParams& p, const int r, const
 }
 
 constexpr int kQueueCap = 64;
+constexpr int kMaxMapped = 10;    // HaplotypeLikelihoodArray::maxMappingPositions (haplotype_likelihood_array.hpp:104)
+constexpr int kKmer = 6;          // mapperKmerSize (:103)
+constexpr int kKmerBins = 4096;
+
+// ---------------------------------------------------------------------------------------------------------
+// k-mer mapper (utils/kmer_mapper.hpp): K = 6 perfect hash A0 C1 G2 T3 (anything else 0), little-endian base 4 (:24-53)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned kmer_base(const char b) { return b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : 0u; }
+__device__ __forceinline__ unsigned kmer_hash(const char* s)
+{
+    unsigned h = 0;
+#pragma unroll
+    for (int i = 0; i < kKmer; ++i) h |= kmer_base(s[i]) << (2 * i);
+    return h;
+}
+
+// compute_kmer_hashes<6> for every read (:57-69): hash of the 6-mer starting at each base (entries past L-6 unused)
+__global__ void k_read_kmers(const long long n_bases, const int n_reads, const long long* __restrict__ off, const char* __restrict__ bases,
+                             uint16_t* __restrict__ rhash)
+{
+    const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const long long b = off[r];
+    const int L = (int)(off[r + 1] - b);
+    for (int y = lane; y + kKmer <= L; y += 32) rhash[b + y] = (uint16_t)kmer_hash(bases + b + y);
+}
+
+// populate_kmer_hash_table<6> (:85-98) as CSR per haplotype: bin_start[h][4097], items[hap base offset + ...]. One block per haplotype.
+__global__ void k_build_kmer_table(const int H, const long long* __restrict__ off, const char* __restrict__ seq,
+                                   int* __restrict__ bin_start, uint16_t* __restrict__ items)
+{
+    __shared__ int hist[kKmerBins + 1];
+    const int h = blockIdx.x;
+    if (h >= H) return;
+    const long long o = off[h];
+    const int nt = (int)(off[h + 1] - o) - kKmer + 1;
+    for (int i = threadIdx.x; i <= kKmerBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) atomicAdd(&hist[kmer_hash(seq + o + i) + 1], 1);
+    __syncthreads();
+    // exclusive scan of 4096 bins by one warp (chunks of 32 with a running carry)
+    if (threadIdx.x < 32) {
+        int run = 0;
+        for (int base = 0; base <= kKmerBins; base += 32) {
+            const int i = base + threadIdx.x;
+            int v = i <= kKmerBins ? hist[i] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, d); if ((int)threadIdx.x >= d) v += n; }
+            if (i <= kKmerBins) hist[i] = v + run;
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    int* bs = bin_start + (size_t)h * (kKmerBins + 1);
+    for (int i = threadIdx.x; i <= kKmerBins; i += blockDim.x) bs[i] = hist[i];   // hist[b] = number of k-mers with hash < b... (inclusive scan of counts shifted by one)
+    __syncthreads();
+    // fill: cursor per bin (reuse hist as cursors = bin starts)
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        const unsigned hh = kmer_hash(seq + o + i);
+        const int slot = atomicAdd(&hist[hh], 1);
+        items[o + slot] = (uint16_t)i;
+    }
+}
+
+// map_query_to_target (:120-159) for every (read of the work list, haplotype): the first <= 10 mapping begins (ascending)
+// whose vote count equals the maximum. One thread per pair; the vote counts live in a per-thread local array.
+template <int MAXT>
+__global__ void k_kmer_map(const int* __restrict__ list, const int n_list, const int stride_in_list, const DevHaps hp, const DevReads rd,
+                           const uint16_t* __restrict__ rhash, const int* __restrict__ bin_start, const uint16_t* __restrict__ items,
+                           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = hp.n;
+    if (i >= (long long)n_list * H) return;
+    const int li = (int)(i / H), h = (int)(i % H);
+    const int r = list[(size_t)li * stride_in_list];
+    uint8_t n_out = 0;
+    if (r >= 0) {
+        const long long ro = rd.off[r], ho = hp.off[h];
+        const int nq = (int)(rd.off[r + 1] - ro) - kKmer + 1, nt = (int)(hp.off[h + 1] - ho) - kKmer + 1;
+        if (nq > 0 && nt > 0 && nt <= MAXT) {
+            uint16_t counts[MAXT];
+            for (int t = 0; t < nt; ++t) counts[t] = 0;
+            const int* bs = bin_start + (size_t)h * (kKmerBins + 1);
+            unsigned max_hit = 0;
+            for (int qi = 0; qi < nq; ++qi) {
+                const unsigned hq = rhash[ro + qi];
+                const int e1 = bs[hq + 1];
+                for (int e = bs[hq]; e < e1; ++e) {
+                    const int ti = items[ho + e];
+                    if (ti >= qi) { const unsigned c = ++counts[ti - qi]; max_hit = c > max_hit ? c : max_hit; }
+                }
+            }
+            if (max_hit > 0) {
+                int32_t* out = kpos + (size_t)i * kMaxMapped;
+                for (int t = 0; t < nt && n_out < kMaxMapped; ++t) if (counts[t] == max_hit) out[n_out++] = t;
+            }
+        }
+    }
+    kcnt[i] = n_out;
+}
 
 // Persistent warps. Each warp repeatedly claims one read pair (r0, r1) of equal length, stages the pair's row words in
 // shared memory once, and walks all H haplotypes 32 at a time (lane = haplotype): candidate slots are classified in
@@ -267,10 +374,16 @@ k_populate_fast(const PopParams p)
             int maxslots = 0;
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                if (p.pos_off && act && (s == 0 || r1 >= 0)) {
-                    const long long o = p.pos_off[(size_t)hc * R + rr[s]];
-                    npos[s] = (int)(p.pos_off[(size_t)hc * R + rr[s] + 1] - o);
-                    pp[s] = p.pos + o;
+                if (act && (s == 0 || r1 >= 0)) {
+                    if (p.pos_off) {
+                        const long long o = p.pos_off[(size_t)hc * R + rr[s]];
+                        npos[s] = (int)(p.pos_off[(size_t)hc * R + rr[s] + 1] - o);
+                        pp[s] = p.pos + o;
+                    } else if (p.kcnt) {
+                        const size_t li = (size_t)p.k_first_list_index + 2 * (size_t)j + s;
+                        npos[s] = p.kcnt[li * H + hc];
+                        pp[s] = p.kpos + (li * H + hc) * kMaxMapped;
+                    }
                 }
                 maxslots = max(maxslots, npos[s] + 2);
             }
@@ -328,6 +441,7 @@ __global__ void k_populate_generic(const PopParams p)
     int npos = 0;
     const int32_t* pp = nullptr;
     if (p.pos_off) { const long long o = p.pos_off[(size_t)h * R + r]; npos = (int)(p.pos_off[(size_t)h * R + r + 1] - o); pp = p.pos + o; }
+    else if (p.kcnt) { const size_t li = (size_t)p.k_first_list_index + (size_t)(i / H); npos = p.kcnt[li * H + h]; pp = p.kpos + (li * H + h) * kMaxMapped; }
     EnumState st {false, false};
     int best = kBestInf;
     for (int c = 0; c < npos + 2; ++c) {

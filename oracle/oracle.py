@@ -213,7 +213,7 @@ class COracle:
         L.oracle_kmer_map.restype = C.c_int
         L.oracle_kmer_map.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, _i64p]
         L.oracle_populate.restype = C.c_int
-        L.oracle_populate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]
+        L.oracle_populate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
 
     @staticmethod
     def model(gap_open, gap_extend, nuc_prior=2, snv_mask=None, snv_prior=None):
@@ -309,7 +309,7 @@ class COracle:
         return out[:n].tolist()
 
     def populate(self, band, haps, reads, positions=None, flanks=None, use_mapping_quality=True, mapq_cap=120,
-                 mapq_cap_trigger=-1, nuc_prior=2, dp_only=False):
+                 mapq_cap_trigger=-1, nuc_prior=2, dp_only=False, map_positions=False):
         """haps / reads: host HaplotypeBlock / ReadBlock (octopus_b200.batch). Returns (any_short, out[H,R], status[H,R])."""
         H, R = haps.n, reads.n
         out = np.empty((H, R), dtype=np.float64)
@@ -321,5 +321,5 @@ class COracle:
                                       p(haps.snv_mask_rev), p(haps.snv_prior_rev), p(haps.gap_open), p(haps.gap_extend), p(haps.begin),
                                       R, p(reads.off), p(reads.bases), p(reads.quals), p(reads.mapq), p(reads.reverse), p(reads.begin),
                                       p(po), p(pv), uf, lhs, rhs, int(use_mapping_quality), int(mapq_cap), int(mapq_cap_trigger),
-                                      int(nuc_prior), int(dp_only), out.ctypes.data, status.ctypes.data)
+                                      int(nuc_prior), int(dp_only), int(map_positions), out.ctypes.data, status.ctypes.data)
         return rc, out, status

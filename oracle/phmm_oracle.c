@@ -415,7 +415,7 @@ int oracle_kmer_map(const char* query, int query_len, const char* target, int ta
 
 /* haplotype_likelihood_array.cpp:51-103 populate(ReadMap) for one sample: the H x R loop (haplotype outer, read inner),
  * with the candidate mapping positions supplied as a CSR over [H][R] pairs (pos_off == NULL: none listed) instead of
- * being produced by the k-mer mapper inline (:89-92; see oracle_kmer_map). Writes out[h*R + r]; status[h*R + r] = 0 ok,
+ * being produced by the k-mer mapper inline (:89-92) — or, with pos_off == NULL and map_positions != 0, by oracle_kmer_map. Writes out[h*R + r]; status[h*R + r] = 0 ok,
  * 2 | ext << 16 for ShortHaplotypeError (the reference throws on the first one; this loop records all and returns 1). */
 int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
                     const char* mask_f, const int8_t* prior_f, const char* mask_r, const int8_t* prior_r,
@@ -424,7 +424,7 @@ int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
                     const uint8_t* mapq, const uint8_t* reverse, const int64_t* read_begin,
                     const int64_t* pos_off, const int32_t* pos,
                     int use_flanks, int lhs_flank, int rhs_flank,
-                    int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only,
+                    int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only, int map_positions,
                     double* out, int32_t* status)
 {
     int any_short = 0;
@@ -446,6 +446,9 @@ int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
             if (pos_off) {
                 const int64_t a = pos_off[(int64_t)h * R + r], b = pos_off[(int64_t)h * R + r + 1];
                 for (int64_t i = a; i < b && np < 64; ++i) tmp[np++] = pos[i];
+            } else if (map_positions) {
+                /* :89-92 map_query_to_target(read_hashes, haplotype_hashes, counts, first, maxMappingPositions = 10) */
+                np = oracle_kmer_map(bases + ro, rl, seq + ho, hl, 10, tmp);
             }
             const int64_t orig = (read_begin ? read_begin[r] : 0) - (hap_begin ? hap_begin[h] : 0);
             double v = 0; int ext = 0;

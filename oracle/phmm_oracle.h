@@ -74,7 +74,7 @@ int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
                     const uint8_t* mapq, const uint8_t* reverse, const int64_t* read_begin,
                     const int64_t* pos_off, const int32_t* pos,
                     int use_flanks, int lhs_flank, int rhs_flank,
-                    int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only,
+                    int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only, int map_positions,
                     double* out, int32_t* status);
 
 #ifdef __cplusplus

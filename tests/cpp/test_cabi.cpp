@@ -35,6 +35,7 @@ int main()
         reads.add(h1.substr(35, 40), std::vector<std::uint8_t>(40, 25), 60, true, 35);
         auto cfg = HaplotypeLikelihoodArray::default_config();
         cfg.max_indel_error = 16;
+        cfg.map_positions = 0;   // the check below evaluates the original position only
         HaplotypeLikelihoodArray arr {cfg};
         arr.populate(reads, haps);
         for (std::size_t h = 0; h < 2; ++h) { const auto row = arr[h]; std::printf("ROW %zu %.17g %.17g\n", h, row[0], row[1]); }

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     from octopus_b200 import _lib
-    assert C.sizeof(_lib.Config) == 32
+    assert C.sizeof(_lib.Config) == 36
     assert C.sizeof(_lib.Haplotypes) == 8 + 9 * 8
     assert C.sizeof(_lib.Reads) == 8 + 6 * 8
     assert C.sizeof(_lib.Positions) == 16
@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     cfg = _lib.Config()
     _lib.load().phmm_default_config(C.byref(cfg))
     assert (cfg.max_indel_error, cfg.use_mapping_quality, cfg.mapping_quality_cap, cfg.mapping_quality_cap_trigger,
-            cfg.use_flank_state, cfg.nuc_prior, cfg.use_int_scores, cfg.disable_naive_shortcut) == (8, 1, 120, -1, 1, 2, 0, 0)
+            cfg.use_flank_state, cfg.nuc_prior, cfg.use_int_scores, cfg.disable_naive_shortcut, cfg.map_positions) == (8, 1, 120, -1, 1, 2, 0, 0, 1)
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -10,7 +10,7 @@ def test_c2_full_size_properties(engine, coracle):
     from octopus_b200 import HaplotypeLikelihoodModel, synth
     from octopus_b200.batch import ReadBlock
     haps, reads, band = synth.make_batch("C2")           # 100k reads x 64 haplotypes, band 16: 6.4e6 alignments
-    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, use_mapping_quality=False)
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, use_mapping_quality=False, map_positions=False)
     m = engine.populate(cfg, haps, reads)
     assert m.shape == (64, 100_000) and np.isfinite(m).all() and (m <= 0).all()
     # 1. determinism

@@ -101,10 +101,12 @@ def test_populate_matches_oracle(engine, coracle, band_req):
         flanks = (int(rng.integers(0, 90)), int(rng.integers(0, 90))) if trial % 2 else None
         for dp_only in (False, True):
             for use_mq in (True, False):
+                mapit = (trial % 3 == 0) and (trial % 2 == 0 or dp_only)      # positions=None: k-mer mapped on the device, or original only
                 cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, use_mapping_quality=use_mq,
-                                                      mapping_quality_cap_trigger=40 if trial % 2 else None, disable_naive_shortcut=dp_only)
+                                                      mapping_quality_cap_trigger=40 if trial % 2 else None, disable_naive_shortcut=dp_only,
+                                                      map_positions=mapit)
                 rc, want, wst = coracle.populate(band, haps, reads, positions, flanks, use_mapping_quality=use_mq,
-                                                 mapq_cap_trigger=40 if trial % 2 else -1, dp_only=dp_only)
+                                                 mapq_cap_trigger=40 if trial % 2 else -1, dp_only=dp_only, map_positions=mapit)
                 got, st = engine.populate(cfg, haps, reads, positions, flanks, want_status=True)
                 ok_pairs = wst == 0
                 assert np.array_equal((st & 0xFFFF) == 2, (wst & 0xFFFF) == 2)
@@ -123,7 +125,7 @@ def test_populate_raises_short_haplotype_error(engine):
     haps = pack_haplotypes([s], [s], [np.full(60, 50, np.int8)], [s], [np.full(60, 50, np.int8)], [np.full(60, 30, np.int8)], [np.full(60, 3, np.int8)])
     reads = pack_reads([s[5:55]], [np.full(50, 30, np.uint8)], begin=np.array([5]))
     with pytest.raises(ShortHaplotypeError):
-        engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=16), haps, reads)
+        engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=16, map_positions=False), haps, reads)
 
 
 def test_populate_device_resident_inputs_equal_host_inputs(engine):
@@ -143,8 +145,8 @@ def test_packed_16bit_path_equals_int32_path_at_scale(engine):
     from octopus_b200 import HaplotypeLikelihoodModel, synth
     for name, nr, nh in (("C2", 20000, 64), ("C4", 6000, 24)):
         haps, reads, band = synth.make_batch(name, n_reads=nr, n_haps=nh)
-        a = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True), haps, reads)
-        b = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, use_int_scores=True), haps, reads)
+        a = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, map_positions=False), haps, reads)
+        b = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, use_int_scores=True, map_positions=False), haps, reads)
         assert np.array_equal(a, b), name
 
 
@@ -163,3 +165,39 @@ def test_traceback_seam_reproduces_reference_kats(engine, kats, coracle):
         got = engine.align(band, c["truth"].tobytes(), c["read"].tobytes(), q8, c["gap_open"], c["gap_extend"], 3, c["snv_mask"].tobytes(), c["snv_prior"])
         want = coracle.align_tb(band, c["truth"].tobytes(), c["read"].tobytes(), q8, c["gap_open"], c["gap_extend"], 3, c["snv_mask"].tobytes(), c["snv_prior"])
         assert got == want
+
+
+def test_populate_with_device_kmer_mapper_matches_reference_loop(engine, coracle):
+    """positions = None and map_positions = 1: the engine maps every (haplotype, read) pair with the reference's K=6 k-mer
+    mapper on the device, exactly as HaplotypeLikelihoodArray::populate does inline (haplotype_likelihood_array.cpp:89-92)."""
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    haps, reads, band = synth.make_batch("C2", n_reads=700, n_haps=24)
+    for flanks in (None, (40, 30)):
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band)
+        got = engine.populate(cfg, haps, reads, flank_state=flanks)
+        rc, want, _ = coracle.populate(band, haps, reads, None, flanks, map_positions=True)
+        assert rc == 0
+        ok, worst = _close(got, want)
+        assert ok, worst
+    # repetitive haplotypes: many equally good mapping positions (exercises the <= 10 cap and the tie order)
+    rng = np.random.default_rng(4)
+    unit = np.frombuffer(b"ACGTTGCAAG", dtype=np.uint8)
+    rep = np.tile(unit, 40)[:360]
+    from octopus_b200.batch import pack_haplotypes, pack_reads
+    seqs = []
+    for h in range(5):
+        s = rep.copy(); s[rng.integers(0, 360, 3)] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 3)]; seqs.append(s)
+    n = 360
+    haps2 = pack_haplotypes(seqs, [np.roll(s, 1) for s in seqs], [np.full(n, 60, np.int8)] * 5, [np.roll(s, -1) for s in seqs], [np.full(n, 60, np.int8)] * 5,
+                            [rng.integers(3, 46, n).astype(np.int8) for _ in range(5)], [rng.integers(1, 11, n).astype(np.int8) for _ in range(5)])
+    rb, rq, rbeg = [], [], []
+    for r in range(40):
+        p = int(rng.integers(20, 200)); L = int(rng.choice([50, 100]))
+        b = seqs[int(rng.integers(0, 5))][p:p + L].copy()
+        if r % 2: b[rng.integers(0, L)] = ord("A")
+        rb.append(b); rq.append(rng.integers(10, 41, L).astype(np.uint8)); rbeg.append(p)
+    reads2 = pack_reads(rb, rq, begin=np.asarray(rbeg))
+    got = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=16), haps2, reads2)
+    rc, want, _ = coracle.populate(16, haps2, reads2, None, None, map_positions=True)
+    ok, worst = _close(got, want)
+    assert rc == 0 and ok, worst
