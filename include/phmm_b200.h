@@ -112,6 +112,15 @@ typedef struct {
     int32_t reverse;
 } phmm_task;
 
+/* One (read, haplotype) pair of phmm_align_reads. */
+typedef struct {
+    int32_t read;
+    int32_t hap;
+} phmm_pair;
+
+#define PHMM_STATUS_CIGAR_TRUNCATED 3   /* phmm_align_reads: cigar_stride too small */
+#define PHMM_STATUS_HMM_OVERFLOW    4   /* reference HMMOverflow (pair_hmm.hpp:47-64, 815-817) */
+
 const char* phmm_version(void);
 void        phmm_default_config(phmm_config* cfg);
 
@@ -145,6 +154,18 @@ int phmm_align_traceback(phmm_engine* e, int band,
                          const char* snv_mask, const int8_t* snv_prior, const int8_t* gap_open,
                          const int8_t* gap_extend, int gap_extend_scalar, int nuc_prior,
                          int* score, int* first_pos, char* align1, char* align2);
+
+/* Best alignment of explicit (read, haplotype) pairs: HaplotypeLikelihoodModel::align (haplotype_likelihood_model.cpp:397-431 →
+ * compute_optimal_alignment :335-395 → hmm::align pair_hmm.hpp:858-874), the call ReadRealigner / ReadAssigner make
+ * (core/tools/read_realigner.cpp:100-150). positions: CSR over the PAIR LIST (off[n_pairs+1]) or NULL.
+ * Outputs per pair: mapping_position (Alignment::mapping_position), likelihood (after mapping-quality mixing), the CIGAR as
+ * text with the reference's operation letters (= X I D; basics/cigar_string.hpp:27-31) in cigar[j*cigar_stride ..),
+ * status[j] (PHMM_STATUS_*; SHORT_HAP / HMM_OVERFLOW correspond to the reference's exceptions). */
+int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* haps, const phmm_reads* reads,
+                     const phmm_pair* pairs, int64_t n_pairs,
+                     const phmm_positions* positions, const phmm_flank_state* flank,
+                     int64_t* mapping_position, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space);
 
 /* Batch boundary: out[h*R + r] == HaplotypeLikelihoodArray likelihoods_[h][sample][r] for a single-sample ReadMap
  * (haplotype_likelihood_array.cpp:77-95). status (optional, [H*R]) receives PHMM_STATUS_*.

@@ -134,6 +134,34 @@ class PairHMMEngine:
             self._raise(rc)
         return score.value, fp.value, a1.value.decode(), a2.value.decode()
 
+    def align_reads(self, config, haps: HaplotypeBlock, reads: ReadBlock, pairs, positions=None, flank_state=None, cigar_stride=None):
+        """HaplotypeLikelihoodModel::align for explicit (read, haplotype) pairs (host blocks). pairs: (n, 2) int32 rows (read, hap);
+        positions: None or (off[n+1], pos) CSR over the pair list. Returns (mapping_position[n], likelihood[n], cigars[list of str], status[n])."""
+        assert not haps.on_device and not reads.on_device
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        hs, rs = haps.c_struct(), reads.c_struct()
+        cfg = config.c_struct()
+        if cigar_stride is None:
+            cigar_stride = 4 * int(np.diff(reads.off).max()) + 64
+        pstruct = None
+        if positions is not None:
+            off = np.ascontiguousarray(positions[0], dtype=np.int64)
+            pos = np.ascontiguousarray(positions[1], dtype=np.int32)
+            pstruct = _lib.Positions(off.ctypes.data, pos.ctypes.data)
+        fstruct = None if flank_state is None else _lib.FlankState(1, int(flank_state[0]), int(flank_state[1]))
+        mp = np.zeros(n, dtype=np.int64)
+        lk = np.zeros(n, dtype=np.float64)
+        st = np.zeros(n, dtype=np.int32)
+        cg = np.zeros(n * cigar_stride, dtype=np.uint8)
+        rc = self._lib.phmm_align_reads(self._h, C.byref(cfg), C.byref(hs), C.byref(rs), pr.ctypes.data, n,
+                                        C.byref(pstruct) if pstruct is not None else None, C.byref(fstruct) if fstruct is not None else None,
+                                        mp.ctypes.data, lk.ctypes.data, cg.ctypes.data, cigar_stride, st.ctypes.data, _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+        cigars = [bytes(cg[j * cigar_stride:(j + 1) * cigar_stride]).split(b"\0", 1)[0].decode() for j in range(n)]
+        return mp, lk, cigars, st
+
     # -- batch boundary ----------------------------------------------------------------------------------------
     def populate(self, config, haps: HaplotypeBlock, reads: ReadBlock, positions=None, flank_state=None, out=None,
                  want_status=False):

@@ -430,6 +430,81 @@ int phmm_align_traceback(phmm_engine* e, int band,
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// phmm_align_reads
+// -------------------------------------------------------------------------------------------------------------
+int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* haps, const phmm_reads* reads,
+                     const phmm_pair* pairs, int64_t n_pairs,
+                     const phmm_positions* positions, const phmm_flank_state* flank,
+                     int64_t* mapping_position, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    if (!cfg || !pairs || !mapping_position || !likelihood || !cigar || !status || cigar_stride < 8) { e->err = "null argument / cigar_stride < 8"; return PHMM_ERR_INVALID; }
+    if (cfg->max_indel_error > 256) { e->err = "max_indel_error > 256"; return PHMM_ERR_BAND; }
+    if (n_pairs < 0 || n_pairs > 0x7fffffff) { e->err = "pair count out of range"; return PHMM_ERR_INVALID; }
+    if (n_pairs == 0) return PHMM_OK;
+    if (!reads || !reads->mapq || !reads->reverse) { e->err = "reads->mapq / reads->reverse required"; return PHMM_ERR_INVALID; }
+    const int band = round_band(std::max(1, cfg->max_indel_error));
+    Staged s;
+    int rc = stage_batch(e, haps, reads, space, s);
+    if (rc != PHMM_OK) return rc;
+    const int n = (int)n_pairs;
+    AlignParams p {};
+    p.hp = s.hp; p.rd = s.rd; p.n_pairs = n;
+    p.band = band; p.nuc_prior = cfg->nuc_prior;
+    p.use_flanks = (flank && flank->has_flank && cfg->use_flank_state) ? 1 : 0;
+    p.lhs_flank = p.use_flanks ? (int)flank->lhs_flank : 0;
+    p.rhs_flank = p.use_flanks ? (int)flank->rhs_flank : 0;
+    p.use_mapq = cfg->use_mapping_quality; p.mapq_cap = cfg->mapping_quality_cap; p.mapq_trigger = cfg->mapping_quality_cap_trigger;
+    const int2* d_pairs;
+    if ((rc = stage(e, e->pairs, (const int2*)pairs, (size_t)n, space, &d_pairs))) return rc;
+    p.pairs = d_pairs;
+    if (positions && positions->off && positions->pos) {
+        std::vector<long long> ends(1);
+        if (space == PHMM_SPACE_HOST) ends[0] = positions->off[n];
+        else { CU(cudaMemcpyAsync(ends.data(), positions->off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream)); CU(cudaStreamSynchronize(e->stream)); }
+        const long long* po; const int32_t* pv;
+        if ((rc = stage(e, e->c_off, (const long long*)positions->off, (size_t)n + 1, space, &po))) return rc;
+        if ((rc = stage(e, e->c_pos, positions->pos, (size_t)std::max<long long>(ends[0], 1), space, &pv))) return rc;
+        p.pos_off = po; p.pos = pv;
+    }
+    int Lmax = 1;
+    for (int r = 0; r < s.rd.n; ++r) Lmax = std::max(Lmax, e->info_host[r].x);
+    const int threads_total = std::min(e->sm_count * 256, ((n + 63) / 64) * 64);
+    p.str_cap = 2 * (Lmax + band) + 2;
+    CU(e->bp.ensure((size_t)threads_total * (size_t)(Lmax + 1) * (size_t)(2 * band)));
+    CU(e->slow.ensure((size_t)threads_total * 4 * p.str_cap));
+    p.bp = e->bp.as<unsigned char>();
+    p.strings = e->slow.as<char>();
+    // outputs
+    const bool dev = space == PHMM_SPACE_DEVICE;
+    CU(e->best.ensure((size_t)n * sizeof(long long)));
+    CU(e->out.ensure((size_t)n * sizeof(double)));
+    CU(e->status.ensure((size_t)n * sizeof(int)));
+    CU(e->kpos.ensure((size_t)n * cigar_stride));
+    p.mapping_position = dev ? (long long*)mapping_position : e->best.as<long long>();
+    p.likelihood = dev ? likelihood : e->out.as<double>();
+    p.status = dev ? status : e->status.as<int>();
+    p.cigar = dev ? cigar : e->kpos.as<char>();
+    p.cigar_stride = cigar_stride;
+    const unsigned grid = (unsigned)(threads_total / 64);
+    if (band <= 32) k_align_reads<64><<<grid, 64, 0, e->stream>>>(p);
+    else k_align_reads<kGenericMaxDiag><<<grid, 64, 0, e->stream>>>(p);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    if (!dev) {
+        CU(cudaMemcpyAsync(mapping_position, p.mapping_position, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(likelihood, p.likelihood, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(status, p.status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(cigar, p.cigar, (size_t)n * cigar_stride, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    return PHMM_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // phmm_populate
 // -------------------------------------------------------------------------------------------------------------
 int phmm_populate(phmm_engine* e, const phmm_config* cfg,

@@ -498,6 +498,128 @@ __global__ void k_align_one(const int band, const int L, const char* __restrict_
     out[1] = fp;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// HaplotypeLikelihoodModel::align for explicit (read, haplotype) pairs (haplotype_likelihood_model.cpp:335-431):
+// best alignment over the candidate mapping positions, with CIGAR (pair_hmm.hpp:152-188, 321-340, 784-823).
+// ---------------------------------------------------------------------------------------------------------
+struct AlignParams {
+    DevHaps hp;
+    DevReads rd;
+    const int2* pairs;          // {read, hap}
+    int n_pairs;
+    const long long* pos_off;   // CSR over the pair list, or null
+    const int32_t* pos;
+    int band, nuc_prior, use_flanks, lhs_flank, rhs_flank;
+    int use_mapq, mapq_cap, mapq_trigger;
+    long long* mapping_position;
+    double* likelihood;
+    char* cigar;
+    int cigar_stride;
+    int* status;
+    unsigned char* bp;          // interleaved back-pointer scratch: cell c of thread t at bp[c * nthreads + t]
+    char* strings;              // per thread 4 * str_cap bytes
+    int str_cap;
+};
+
+__device__ __forceinline__ int cigar_emit(char* out, int w, const int cap, int len, const char op)
+{
+    char tmp[12];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + len % 10); len /= 10; } while (len > 0);
+    while (n > 0 && w < cap - 1) out[w++] = tmp[--n];
+    if (w < cap - 1) out[w++] = op;
+    return w;
+}
+
+// make_cigar (pair_hmm.hpp:152-188) as text; returns false if it did not fit
+__device__ inline bool make_cigar_text(const char* a1, const char* a2, char* out, const int cap)
+{
+    int n = 0;
+    while (a1[n]) ++n;
+    int i = 0, w = 0;
+    while (i < n) {
+        int j = i;
+        while (j < n && a1[j] == a2[j]) ++j;
+        if (j != i) { w = cigar_emit(out, w, cap, j - i, '='); if (j == n) break; }
+        i = j;
+        if (a1[i] == '-') { j = i + 1; while (j < n && a1[j] == '-') ++j; w = cigar_emit(out, w, cap, j - i, 'I'); }
+        else if (a2[i] == '-') { j = i + 1; while (j < n && a2[j] == '-') ++j; w = cigar_emit(out, w, cap, j - i, 'D'); }
+        else { j = i + 1; while (j < n && a1[j] != a2[j] && a1[j] != '-' && a2[j] != '-') ++j; w = cigar_emit(out, w, cap, j - i, 'X'); }
+        i = j;
+    }
+    out[w < cap ? w : cap - 1] = 0;
+    return w < cap - 1;
+}
+
+template <int MAXK>
+__global__ void k_align_reads(const AlignParams p)
+{
+    const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    char* s0 = p.strings + (size_t)tid * 4 * p.str_cap;
+    for (int i = tid; i < p.n_pairs; i += nthreads) {
+        const int r = p.pairs[i].x, h = p.pairs[i].y;
+        const HapView hv = hap_view(p.hp, h, p.rd.reverse[r] != 0);
+        const ReadView rv = read_view(p.rd, r);
+        const long long orig = (p.rd.begin ? p.rd.begin[r] : 0) - (p.hp.begin ? p.hp.begin[h] : 0);
+        int npos = 0;
+        const int32_t* pp = nullptr;
+        if (p.pos_off) { const long long o = p.pos_off[i]; npos = (int)(p.pos_off[i + 1] - o); pp = p.pos + o; }
+        char *cur1 = s0, *cur2 = s0 + p.str_cap, *best1 = s0 + 2 * p.str_cap, *best2 = s0 + 3 * p.str_cap;
+        EnumState st {false, false};
+        int best = kBestInf, status = 0;
+        long long best_off = 0;
+        bool best_exact = false, have = false;
+        for (int c = 0; c < npos + 2 && status == 0; ++c) {
+            int pos;
+            const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
+            if (k < 0) { status = 2 | (pos << 16); break; }
+            if (k == 0) continue;
+            int v; long long off; bool exact = false;
+            bool eq = true;                                                   // try_naive_align (:321-340)
+            for (int a = 0; a < rv.len; ++a) if (rv.bases[a] != hv.seq[pos + a]) { eq = false; break; }
+            if (eq) { v = 0; off = pos; exact = true; }
+            else {
+                const int W = rv.len + 2 * p.band - 1;
+                const int a = pos - p.band > 0 ? pos - p.band : 0;
+                if (a + W > hv.len) { v = kBestInf; off = 0; cur1[0] = 0; cur2[0] = 0; }          // :802-807
+                else {
+                    const GenericModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
+                    const bool near_flank = p.use_flanks && (pos < p.lhs_flank + p.band || pos + rv.len + p.band > hv.len - p.rhs_flank);
+                    int lhs = 0, rhs = 0, fp, fs, ms;
+                    if (near_flank) window_flanks(a, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+                    int score = generic_align<true, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, p.bp + tid, (size_t)nthreads,
+                                                          lhs, rhs, &fp, &fs, &ms, cur1, cur2);
+                    if (fp == -1) { status = 4; break; }                                             // HMMOverflow (:815-817)
+                    if (near_flank) { if (rv.len - ms < 2) fs = 0; score = fs <= score ? score - fs : score + fs; }   // :659-672
+                    v = score; off = (long long)pos - p.band + fp;                                    // :820
+                }
+            }
+            // :355 listed positions win on '>', :365 the original position on '>=', :388-391 the fallback unconditionally
+            const bool take = c < npos ? (v < best) : (c == npos ? (v <= best) : true);
+            if (take || !have) {
+                if (take) {
+                    best = v; best_off = off; best_exact = exact; have = true;
+                    char* t = cur1; cur1 = best1; best1 = t; t = cur2; cur2 = best2; best2 = t;
+                }
+            }
+        }
+        p.status[i] = status;
+        char* cg = p.cigar + (size_t)i * p.cigar_stride;
+        cg[0] = 0;
+        if (status == 0) {
+            p.mapping_position[i] = best_off;
+            p.likelihood[i] = finish_likelihood(best, p.use_mapq != 0, p.rd.mapq[r], p.mapq_cap, p.mapq_trigger);
+            bool ok = true;
+            if (best_exact) { const int w = cigar_emit(cg, 0, p.cigar_stride, rv.len, '='); cg[w] = 0; }
+            else if (best != kBestInf) ok = make_cigar_text(best1, best2, cg, p.cigar_stride);
+            if (!ok) p.status[i] = 3;
+        } else {
+            p.mapping_position[i] = 0;
+            p.likelihood[i] = -1.7976931348623157e308;
+        }
+    }
+}
+
 __global__ void k_fill_int(int* __restrict__ p, const long long n, const int v)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

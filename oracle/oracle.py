@@ -212,6 +212,10 @@ class COracle:
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _i32p]
         L.oracle_kmer_map.restype = C.c_int
         L.oracle_kmer_map.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, _i64p]
+        L.oracle_model_align.restype = C.c_int
+        L.oracle_model_align.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, mp, C.c_int, C.c_int, C.c_int,
+                                         _i64p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         _i64p, C.POINTER(C.c_double), C.c_char_p, C.c_int, _i32p]
         L.oracle_populate.restype = C.c_int
         L.oracle_populate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
 
@@ -323,3 +327,19 @@ class COracle:
                                       p(po), p(pv), uf, lhs, rhs, int(use_mapping_quality), int(mapq_cap), int(mapq_cap_trigger),
                                       int(nuc_prior), int(dp_only), int(map_positions), out.ctypes.data, status.ctypes.data)
         return rc, out, status
+
+    def model_align(self, band, hap, read, quals, gap_open, gap_extend, snv_mask, snv_prior, positions, original_pos,
+                    mapping_quality=60, nuc_prior=2, flanks=None, use_mapping_quality=True, mapq_cap=120, mapq_cap_trigger=-1):
+        """HaplotypeLikelihoodModel::align. Returns (status, mapping_position, likelihood, cigar_text, required_extension)."""
+        m, keep = self.model(gap_open, gap_extend, nuc_prior, snv_mask, snv_prior)
+        h, r = _b(hap), _b(read)
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.uint8))
+        pos = np.ascontiguousarray(np.asarray(positions, dtype=np.int64))
+        mp_, lk, ext = C.c_int64(0), C.c_double(0), C.c_int32(0)
+        cap = 4 * (len(r) + 2 * band) + 64
+        cig = C.create_string_buffer(cap)
+        uf, lhs, rhs = (0, 0, 0) if flanks is None else (1, flanks[0], flanks[1])
+        st = self.lib.oracle_model_align(band, h, len(h) - 1, r, q.ctypes.data, len(r) - 1, C.byref(m), uf, lhs, rhs,
+                                         pos.ctypes.data_as(_i64p), len(pos), int(original_pos), int(use_mapping_quality), int(mapping_quality),
+                                         int(mapq_cap), int(mapq_cap_trigger), C.byref(mp_), C.byref(lk), cig, cap, C.byref(ext))
+        return st, mp_.value, lk.value, cig.value.decode(), ext.value

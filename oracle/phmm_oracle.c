@@ -22,6 +22,7 @@
 #include "phmm_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -461,4 +462,117 @@ int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
         }
     }
     return any_short;
+}
+
+/* pair_hmm.hpp:152-188 make_cigar: "=" sequence match, "X" substitution, "I" insertion (align1 == '-'), "D" deletion. */
+static int make_cigar_text(const char* a1, const char* a2, char* out, int cap)
+{
+    int n = (int)strlen(a1), i = 0, w = 0;
+    while (i < n) {
+        int j = i;
+        while (j < n && a1[j] == a2[j]) ++j;
+        if (j != i) { w += snprintf(out + w, cap - w, "%d=", j - i); if (j == n) break; }
+        i = j;
+        if (a1[i] == '-') { j = i + 1; while (j < n && a1[j] == '-') ++j; w += snprintf(out + w, cap - w, "%dI", j - i); i = j; }
+        else if (a2[i] == '-') { j = i + 1; while (j < n && a2[j] == '-') ++j; w += snprintf(out + w, cap - w, "%dD", j - i); i = j; }
+        else { j = i + 1; while (j < n && a1[j] != a2[j] && a1[j] != '-' && a2[j] != '-') ++j; w += snprintf(out + w, cap - w, "%dX", j - i); i = j; }
+    }
+    if (w < cap) out[w] = 0;
+    return w;
+}
+
+/* hmm::align for one mapping position (pair_hmm.hpp:858-874 → :321-340 try_naive_align, :784-823 simd_align, :642-673
+ * discount_flank_score). value = integer penalty (likelihood = -ln10/10 * value) or INT_MAX for lowest();
+ * target_offset as the reference computes it (size_t arithmetic mirrored in int64). Returns 0, or 1 for HMMOverflow. */
+static int align_one_position(int band, const char* hap, int hap_len, const char* read, const uint8_t* quals, int read_len,
+                              int offset, const oracle_model* m, int use_flanks, int lhs_flank, int rhs_flank,
+                              int* value, int64_t* target_offset, char* cigar, int cigar_cap)
+{
+    if (memcmp(read, hap + offset, (size_t)read_len) == 0) {   /* :332-336 */
+        *value = 0; *target_offset = offset; snprintf(cigar, cigar_cap, "%d=", read_len);
+        return 0;
+    }
+    const int W = read_len + 2 * band - 1;
+    const int a = offset - band > 0 ? offset - band : 0;
+    if (a + W > hap_len) { *value = 0x7fffffff; *target_offset = 0; cigar[0] = 0; return 0; }   /* :802-807 */
+    const oracle_model om = offset_model(m, a);
+    const int n = 2 * (read_len + band) + 1;
+    char* a1 = (char*)calloc((size_t)n + 1, 1);
+    char* a2 = (char*)calloc((size_t)n + 1, 1);
+    int first_pos = 0;
+    int score = oracle_align_tb(band, hap + a, read, (const int8_t*)quals, W, read_len, &om, &first_pos, a1, a2);
+    if (first_pos == -1) { free(a1); free(a2); return 1; }   /* :815-817 HMMOverflow */
+    const int near_flank = use_flanks && (offset < lhs_flank + band || offset + read_len + band > hap_len - rhs_flank);
+    if (near_flank) {   /* :659-672 */
+        int lhs = lhs_flank < a ? 0 : lhs_flank - a, rhs;
+        if (a + W < hap_len - rhs_flank) rhs = 0; else { rhs = rhs_flank + a + W - hap_len; if (rhs < 0) rhs = 0; }
+        int mask_size = 0;
+        int flank = oracle_flank_score(W, lhs, rhs, read, (const int8_t*)quals, &om, first_pos, a1, a2, &mask_size);
+        if (read_len - mask_size < 2) flank = 0;
+        if (flank <= score) score -= flank; else score += flank;
+    }
+    *value = score;
+    *target_offset = (int64_t)offset - band + first_pos;   /* :820 */
+    make_cigar_text(a1, a2, cigar, cigar_cap);
+    free(a1); free(a2);
+    return 0;
+}
+
+/* haplotype_likelihood_model.cpp:335-431 compute_optimal_alignment + HaplotypeLikelihoodModel::align.
+ * Returns 0 ok, 1 ShortHaplotypeError (*required_extension), 2 HMMOverflow. */
+int oracle_model_align(int band, const char* hap, int hap_len, const char* read, const uint8_t* quals, int read_len,
+                       const oracle_model* m, int use_flanks, int lhs_flank, int rhs_flank,
+                       const int64_t* positions, int n_positions, int64_t original_pos,
+                       int use_mapping_quality, int mapping_quality, int mapq_cap, int mapq_cap_trigger,
+                       int64_t* mapping_position, double* likelihood, char* cigar, int cigar_cap, int* required_extension)
+{
+    int best = 0x7fffffff, have = 0;   /* result.likelihood = lowest() */
+    int64_t best_off = 0;
+    char* tmp = (char*)malloc((size_t)cigar_cap);
+    cigar[0] = 0;
+    int original_mapped = 0, has_in_range = 0;
+    for (int p = 0; p < n_positions; ++p) {
+        if (positions[p] == original_pos) original_mapped = 1;
+        if (num_out_of_range_bases(positions[p], read_len, hap_len, band) == 0) {
+            has_in_range = 1;
+            int v; int64_t off;
+            if (align_one_position(band, hap, hap_len, read, quals, read_len, (int)positions[p], m, use_flanks, lhs_flank, rhs_flank, &v, &off, tmp, cigar_cap)) { free(tmp); return 2; }
+            if (v < best) { best = v; best_off = off; strcpy(cigar, tmp); have = 1; }   /* :355 likelihood > result.likelihood */
+        }
+    }
+    if (!original_mapped && num_out_of_range_bases(original_pos, read_len, hap_len, band) == 0) {
+        has_in_range = 1;
+        int v; int64_t off;
+        if (align_one_position(band, hap, hap_len, read, quals, read_len, (int)original_pos, m, use_flanks, lhs_flank, rhs_flank, &v, &off, tmp, cigar_cap)) { free(tmp); return 2; }
+        if (v <= best) { best = v; best_off = off; strcpy(cigar, tmp); have = 1; }      /* :365 >= */
+    }
+    if (!has_in_range) {
+        const int min_shift = num_out_of_range_bases(original_pos, read_len, hap_len, band);
+        int64_t fin = original_pos;
+        if (min_shift > 0) {
+            fin += min_shift;
+            if (num_out_of_range_bases(fin, read_len, hap_len, band) != 0) { *required_extension = min_shift; free(tmp); return 1; }
+        } else {
+            const unsigned left = (unsigned)(-min_shift);
+            if (original_pos >= (int64_t)left) fin -= left; else { *required_extension = (int)(left - original_pos); free(tmp); return 1; }
+        }
+        int v; int64_t off;
+        if (align_one_position(band, hap, hap_len, read, quals, read_len, (int)fin, m, use_flanks, lhs_flank, rhs_flank, &v, &off, tmp, cigar_cap)) { free(tmp); return 2; }
+        best = v; best_off = off; strcpy(cigar, tmp); have = 1;
+    }
+    (void)have;
+    free(tmp);
+    *mapping_position = best_off;
+    const double ln_given = best == 0x7fffffff ? ORACLE_LOWEST : -LN10_DIV_10 * (double)best;
+    if (use_mapping_quality) {
+        int mq = mapping_quality;
+        if (mapq_cap_trigger >= 0 && mq >= mapq_cap_trigger) mq = mapq_cap;
+        const double ln_miss = -LN10_DIV_10 * (double)mq;
+        const double ln_mapped = log(1.0 - exp(ln_miss));
+        const double r = log_sum_exp2(ln_mapped + ln_given, ln_miss);
+        *likelihood = r > -1e-15 ? 0.0 : r;
+    } else {
+        *likelihood = ln_given > -1e-15 ? 0.0 : ln_given;
+    }
+    return 0;
 }

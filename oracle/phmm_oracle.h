@@ -66,6 +66,15 @@ int oracle_model_evaluate(int band, const char* hap, int hap_len, const char* re
 int oracle_kmer_map(const char* query, int query_len, const char* target, int target_len,
                     int max_positions, int64_t* out_positions);
 
+/* reference compute_optimal_alignment + HaplotypeLikelihoodModel::align (haplotype_likelihood_model.cpp:335-431) over
+ * hmm::align (pair_hmm.hpp:321-340, 784-823, 858-874) and make_cigar (:152-188). cigar: text such as "37=1X12=2I98=".
+ * Returns 0 ok, 1 ShortHaplotypeError, 2 HMMOverflow. */
+int oracle_model_align(int band, const char* hap, int hap_len, const char* read, const uint8_t* quals, int read_len,
+                       const oracle_model* m, int use_flanks, int lhs_flank, int rhs_flank,
+                       const int64_t* positions, int n_positions, int64_t original_pos,
+                       int use_mapping_quality, int mapping_quality, int mapq_cap, int mapq_cap_trigger,
+                       int64_t* mapping_position, double* likelihood, char* cigar, int cigar_cap, int* required_extension);
+
 /* reference HaplotypeLikelihoodArray::populate(ReadMap) loop (haplotype_likelihood_array.cpp:51-103), candidate positions as CSR. */
 int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
                     const char* mask_f, const int8_t* prior_f, const char* mask_r, const int8_t* prior_r,

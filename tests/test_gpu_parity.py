@@ -201,3 +201,36 @@ def test_populate_with_device_kmer_mapper_matches_reference_loop(engine, coracle
     rc, want, _ = coracle.populate(16, haps2, reads2, None, None, map_positions=True)
     ok, worst = _close(got, want)
     assert rc == 0 and ok, worst
+
+
+def test_align_reads_matches_reference_align(engine, coracle):
+    """phmm_align_reads == HaplotypeLikelihoodModel::align: mapping position, likelihood and CIGAR of the best alignment."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    rng = np.random.default_rng(31)
+    for trial in range(4):
+        band_req = [8, 16, 30, 16][trial]
+        band = HaplotypeLikelihoodModel(HaplotypeLikelihoodModel.Config(max_indel_error=band_req)).pad_requirement()
+        haps, reads = random_region(rng, band, n_haps=6, n_reads=40, hap_len=300, read_len_choices=[40, 76, 120], read_n_rate=0.1,
+                                    edge_reads=(trial % 2 == 0))
+        pairs = np.array([(int(rng.integers(0, reads.n)), int(rng.integers(0, haps.n))) for _ in range(300)], dtype=np.int32)
+        lists, off = [], [0]
+        for r, h in pairs:
+            p0 = int(reads.begin[r])
+            ps = sorted({int(np.clip(p0 + rng.integers(-10, 11), 0, haps.length(h))) for _ in range(int(rng.integers(0, 4)))})
+            lists.extend(ps); off.append(len(lists))
+        positions = (np.asarray(off, np.int64), np.asarray(lists if lists else [0], np.int32))
+        flanks = (int(rng.integers(0, 80)), int(rng.integers(0, 80))) if trial % 2 else None
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, mapping_quality_cap_trigger=40 if trial == 3 else None)
+        mp, lk, cig, st = engine.align_reads(cfg, haps, reads, pairs, positions, flanks)
+        for j, (r, h) in enumerate(pairs):
+            hp = haps.hap(int(h)); b, q = reads.read(int(r)); rev = bool(reads.reverse[r])
+            wst, wmp, wlk, wcig, wext = coracle.model_align(band, hp["seq"].tobytes(), b.tobytes(), q, hp["gap_open"], hp["gap_extend"],
+                                                            hp["snv_mask_rev" if rev else "snv_mask_fwd"].tobytes(), hp["snv_prior_rev" if rev else "snv_prior_fwd"],
+                                                            positions[1][off[j]:off[j + 1]], int(reads.begin[r]), mapping_quality=int(reads.mapq[r]),
+                                                            flanks=flanks, mapq_cap_trigger=40 if trial == 3 else -1)
+            if wst == 1:
+                assert (st[j] & 0xFFFF) == 2 and (st[j] >> 16) == wext
+                continue
+            assert wst == 0 and st[j] == 0, (trial, j, wst, st[j])
+            assert mp[j] == wmp and cig[j] == wcig, (trial, j, mp[j], wmp, cig[j], wcig)
+            assert abs(lk[j] - wlk) <= REL_TOL * max(abs(wlk), 1e-300)
