@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace phmm;
@@ -57,8 +58,13 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, bp;
     DBuf tasks_lane, tasks_generic, works, scores;
-    DBuf rhash, kbins, kitems, kpos, kcnt;
+    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt;
+    std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
+    // host-space calls on large batches are pipelined over two sub-engines (own stream + buffers each), driven by two host
+    // threads, so that the H2D / D2H copies of one read chunk overlap the kernels of the other
+    phmm_engine* sub[2] = {nullptr, nullptr};
+    bool is_sub = false;
 };
 
 #define CU(call)                                                                                   \
@@ -240,13 +246,15 @@ int phmm_create(phmm_engine** out, int device)
 void phmm_destroy(phmm_engine* e)
 {
     if (!e) return;
+    for (phmm_engine*& sub : e->sub) { if (sub) phmm_destroy(sub); sub = nullptr; }
     cudaSetDevice(e->device);
     DBuf* all[] = {&e->h_off, &e->h_seq, &e->h_mf, &e->h_pf, &e->h_mr, &e->h_pr, &e->h_go, &e->h_ge, &e->h_begin,
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
                    &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
-                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt};
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt};
     for (DBuf* b : all) b->release();
+    for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -507,10 +515,12 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
 // -------------------------------------------------------------------------------------------------------------
 // phmm_populate
 // -------------------------------------------------------------------------------------------------------------
-int phmm_populate(phmm_engine* e, const phmm_config* cfg,
-                  const phmm_haplotypes* haps, const phmm_reads* reads,
-                  const phmm_positions* positions, const phmm_flank_state* flank,
-                  double* out, int32_t* status, int space)
+// One synchronous pass over (all haplotypes) x (the given reads). out / status are written with a row pitch of out_pitch
+// elements (0: dense [H][R]) so that a read chunk can land in its column block of the caller's [H][R_total] matrix.
+static int populate_impl(phmm_engine* e, const phmm_config* cfg,
+                         const phmm_haplotypes* haps, const phmm_reads* reads,
+                         const phmm_positions* positions, const phmm_flank_state* flank,
+                         double* out, int32_t* status, int space, long long out_pitch)
 {
     if (!e) return PHMM_ERR_INVALID;
     e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
@@ -566,7 +576,10 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     }
 
     // scheduling: equal-length read pairs for the packed kernel, everything else to the generic kernel
-    const bool fast_ok = band <= 32 && !cfg->use_int_scores;
+    long long max_hap_len = 0;
+    for (int h = 0; h < H; ++h) max_hap_len = std::max(max_hap_len, s.hap_off_host[h + 1] - s.hap_off_host[h]);
+    // the fast path packs (haplotype, window offset) into 16 + 16 bits
+    const bool fast_ok = band <= 32 && !cfg->use_int_scores && H <= 65535 && max_hap_len <= 65535;
     std::vector<int> generic_reads, pairs;
     int Lmax_fast = 1, Lmax_all = 1;
     {
@@ -626,6 +639,17 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
         CU(e->kpos.ensure(pairs_cap * kMaxMapped * sizeof(int32_t)));
         CU(e->kcnt.ensure(pairs_cap));
     }
+    // fast-path task lists of one tile: every (read, haplotype) pair can contribute one DP task per candidate position
+    const int max_dp_per_pair = (p.pos_off || use_mapper) ? 11 : 1;
+    p.fcap = H * max_dp_per_pair;
+    if (n_pairs) {
+        reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (64LL << 20) / p.fcap));
+        const size_t list_cap = (size_t)std::min<long long>(reads_per_tile + 2, 2LL * n_pairs);
+        CU(e->ftasks.ensure(list_cap * p.fcap * sizeof(uint32_t)));
+        CU(e->fcnt.ensure(list_cap * sizeof(int)));
+        p.ftasks = e->ftasks.as<uint32_t>();
+        p.fcnt = e->fcnt.as<int>();
+    }
     const int slow_threads = e->sm_count * 256;
     if (p.use_flanks) {
         reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
@@ -640,7 +664,7 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     }
 
     p.row_stride = (Lmax_fast + 2) & ~1;
-    const size_t smem = (size_t)kFastWarpsPerBlock * (p.row_stride + 2 * kQueueCap) * sizeof(RowEntry);
+    const size_t smem = (size_t)kFastWarpsPerBlock * p.row_stride * sizeof(RowEntry);
     int blocks_per_sm = 1;
     if (n_pairs) {
         switch (band) {
@@ -656,6 +680,7 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
 
     const long long pairs_per_tile = std::max<long long>(1, reads_per_tile / 2);
     bool timed = false;
+    size_t n_timed = 0;
     for (long long p0 = 0, g0 = 0; p0 < n_pairs || g0 < n_generic;) {
         if (p0 < n_pairs) {
             const int np = (int)std::min<long long>(pairs_per_tile, n_pairs - p0);
@@ -669,16 +694,24 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>(); p.k_first_list_index = 0;
             }
             CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
+            CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
+            {   // classify pass: shortcut values → best[], near-flank candidates → slow queue, DP candidates → task lists
+                const long long threads = 2LL * np * H;
+                k_populate_generic<64, true><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p);
+                LAUNCHED();
+            }
             const int want_blocks = (np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock;
             const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
-            if (!timed) CU(cudaEventRecord(e->ev0, e->stream));
+            while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); }
+            CU(cudaEventRecord(e->tile_events[2 * n_timed], e->stream));
             switch (band) {
                 case 8:  k_populate_fast<8><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
                 case 16: k_populate_fast<16><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
                 default: k_populate_fast<32><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
             }
             LAUNCHED();
-            if (!timed) { CU(cudaEventRecord(e->ev1, e->stream)); timed = true; }
+            CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
+            ++n_timed; timed = true;
             p0 += np;
         } else {
             const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);
@@ -692,11 +725,12 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>(); p.k_first_list_index = 0;
             }
             const long long threads = (long long)ng * H;
-            if (!timed) CU(cudaEventRecord(e->ev0, e->stream));
-            if (band <= 32) k_populate_generic<64><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
-            else k_populate_generic<kGenericMaxDiag><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
+            const bool time_generic = n_pairs == 0 && n_timed == 0;
+            if (time_generic) CU(cudaEventRecord(e->ev0, e->stream));
+            if (band <= 32) k_populate_generic<64, false><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
+            else k_populate_generic<kGenericMaxDiag, false><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
             LAUNCHED();
-            if (!timed) { CU(cudaEventRecord(e->ev1, e->stream)); timed = true; }
+            if (time_generic) { CU(cudaEventRecord(e->ev1, e->stream)); timed = true; }
             g0 += ng;
         }
         if (p.use_flanks) {
@@ -715,24 +749,90 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     LAUNCHED();
     CU(cudaGetLastError());
     if (space == PHMM_SPACE_HOST) {
-        CU(cudaMemcpyAsync(out, d_out, (size_t)HR * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        if (status) CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        if (out_pitch == 0 || out_pitch == R) {
+            CU(cudaMemcpyAsync(out, d_out, (size_t)HR * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            if (status) CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        } else {
+            CU(cudaMemcpy2DAsync(out, (size_t)out_pitch * sizeof(double), d_out, (size_t)R * sizeof(double), (size_t)R * sizeof(double), H, cudaMemcpyDeviceToHost, e->stream));
+            if (status) CU(cudaMemcpy2DAsync(status, (size_t)out_pitch * sizeof(int), p.status, (size_t)R * sizeof(int), (size_t)R * sizeof(int), H, cudaMemcpyDeviceToHost, e->stream));
+        }
     } else if (status) {
         CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
     }
     int flags_host[1] = {0};
     CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    float ms = 0.f;
-    if (timed && cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_dp_ms = ms;
+    if (n_timed) {
+        double total = 0.0;
+        for (size_t t = 0; t < n_timed; ++t) { float ms = 0.f; if (cudaEventElapsedTime(&ms, e->tile_events[2 * t], e->tile_events[2 * t + 1]) == cudaSuccess) total += ms; }
+        e->last_dp_ms = total;
+    } else if (timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_dp_ms = ms;
+    }
     // GCUPS numerator when every pair runs exactly one DP (benchmark mode); otherwise an upper bound on DP work
     {
         int64_t cells = 0;
         for (int r = 0; r < R; ++r) cells += 2LL * (e->info_host[r].x + band) * band;
         e->last_dp_cells = cells * H;
     }
-    if (flags_host[0] & 4) { e->err = "near-flank queue overflow"; return PHMM_ERR_NOMEM; }
+    if (flags_host[0] & (4 | 8)) { e->err = "internal task queue overflow"; return PHMM_ERR_NOMEM; }
     if (flags_host[0] & 2) { e->err = "Haplotype is too short for alignment"; return PHMM_ERR_SHORT_HAPLOTYPE; }
+    return PHMM_OK;
+}
+
+int phmm_populate(phmm_engine* e, const phmm_config* cfg,
+                  const phmm_haplotypes* haps, const phmm_reads* reads,
+                  const phmm_positions* positions, const phmm_flank_state* flank,
+                  double* out, int32_t* status, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    // Pipelined path: host-resident batch, no caller-supplied position lists (a [H][R] CSR cannot be sliced by columns
+    // without a pass over it), enough pairs to amortise the per-chunk overheads.
+    const long long kChunkPairs = 4LL << 20;
+    const bool can_chunk = !e->is_sub && space == PHMM_SPACE_HOST && haps && reads && cfg && out && haps->n > 0 && reads->n > 1 &&
+                           reads->off && reads->mapq && reads->reverse && !(positions && positions->off && positions->pos) &&
+                           (long long)haps->n * reads->n >= 2 * kChunkPairs;
+    if (!can_chunk) return populate_impl(e, cfg, haps, reads, positions, flank, out, status, space, 0);
+    e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
+    for (phmm_engine*& sub : e->sub) {
+        if (!sub) {
+            const int rc = phmm_create(&sub, e->device);
+            if (rc != PHMM_OK) { e->err = std::string("sub-engine: ") + phmm_last_error(nullptr); return rc; }
+            sub->is_sub = true;
+        }
+    }
+    const int R = reads->n, H = haps->n;
+    const long long reads_per_chunk = std::max<long long>(64, kChunkPairs / H);
+    const int n_chunks = (int)((R + reads_per_chunk - 1) / reads_per_chunk);
+    int rcs[2] = {PHMM_OK, PHMM_OK};
+    std::string errs[2];
+    int64_t cells[2] = {0, 0}, launches[2] = {0, 0};
+    auto worker = [&](int k) {
+        phmm_engine* se = e->sub[k];
+        std::vector<int64_t> off;
+        for (int c = k; c < n_chunks; c += 2) {
+            const long long lo = (long long)c * reads_per_chunk, hi = std::min<long long>(R, lo + reads_per_chunk);
+            const int n = (int)(hi - lo);
+            off.resize((size_t)n + 1);
+            const int64_t base = reads->off[lo];
+            for (int i = 0; i <= n; ++i) off[i] = reads->off[lo + i] - base;
+            phmm_reads sub_reads {n, off.data(), reads->bases + base, reads->quals + base, reads->mapq + lo, reads->reverse + lo,
+                                  reads->begin ? reads->begin + lo : nullptr};
+            const int rc = populate_impl(se, cfg, haps, &sub_reads, nullptr, flank, out + lo, status ? status + lo : nullptr, PHMM_SPACE_HOST, R);
+            cells[k] += se->last_dp_cells; launches[k] += se->launches_last;
+            if (rc != PHMM_OK && rc != PHMM_ERR_SHORT_HAPLOTYPE) { rcs[k] = rc; errs[k] = se->err; return; }
+            if (rc == PHMM_ERR_SHORT_HAPLOTYPE) { rcs[k] = rc; errs[k] = se->err; }   // keep going: every pair's status is still written
+        }
+    };
+    std::thread t1(worker, 1);
+    worker(0);
+    t1.join();
+    e->last_dp_cells = cells[0] + cells[1];
+    e->launches_last = launches[0] + launches[1];
+    e->launches_total += e->launches_last;
+    for (int k = 0; k < 2; ++k) if (rcs[k] != PHMM_OK && rcs[k] != PHMM_ERR_SHORT_HAPLOTYPE) { e->err = errs[k]; return rcs[k]; }
+    for (int k = 0; k < 2; ++k) if (rcs[k] == PHMM_ERR_SHORT_HAPLOTYPE) { e->err = errs[k]; return rcs[k]; }
     return PHMM_OK;
 }
 

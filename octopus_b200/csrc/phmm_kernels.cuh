@@ -164,6 +164,11 @@ struct PopParams {
     const int32_t* kpos;
     const uint8_t* kcnt;
     int k_first_list_index;     // list index of the first read of this launch's work list
+    // fast-path DP tasks produced by the classify pass for the current tile: list slot li owns
+    // ftasks[li * fcap .. li * fcap + fcnt[li]) entries (haplotype | window offset << 16)
+    uint32_t* ftasks;
+    int* fcnt;
+    int fcap;
     int band, nuc_prior;
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
     int use_flanks;             // flank_state present && config.use_flank_state
@@ -308,132 +313,66 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list, const
     kcnt[i] = n_out;
 }
 
-// Persistent warps. Each warp repeatedly claims one read pair (r0, r1) of equal length, stages the pair's row words in
-// shared memory once, and walks all H haplotypes 32 at a time (lane = haplotype): candidate slots are classified in
-// lock-step (shortcut values go straight to best[], near-flank ones to the slow queue) and the DP-needing ones are
-// compacted into two per-half queues in shared memory; whenever a queue holds 32 tasks the warp runs one dp_pair
-// round — 64 alignments, two per lane — and folds the scores into best[] with atomicMin.
+// Fast-path DP over the task lists the classify pass (k_populate_generic<.., true>) produced. Persistent warps: each warp
+// repeatedly claims one read pair (r0, r1) of equal length, stages the pair's row entries in shared memory once, and runs
+// dp_pair over the two reads' task lists 32 + 32 tasks at a time — 64 alignments per round, two per lane — folding the
+// scores into best[] with atomicMin. Nothing but the DP lives in this kernel: the register-resident band gets the whole
+// register budget.
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 2)
 k_populate_fast(const PopParams p)
 {
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = p.row_stride + 2 * kQueueCap;      // in 8-byte units: row entries, then the two task queues
-    RowEntry* rows = smem_rows + warp * per_warp;
-    int* qh = (int*)(rows + p.row_stride);          // [2][kQueueCap] haplotype index
-    int* qa = qh + 2 * kQueueCap;                   // [2][kQueueCap] window offset
-    const int H = p.hp.n, R = p.rd.n;
+    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int R = p.rd.n;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
-    const unsigned lt_mask = (1u << lane) - 1u;
-
     for (;;) {
         int j = 0;
         if (lane == 0) j = atomicAdd(p.pair_cursor, 1);
         j = __shfl_sync(0xffffffffu, j, 0);
         if (j >= p.n_pairs) break;
         const int r0 = p.pair_reads[2 * j], r1 = p.pair_reads[2 * j + 1];
+        const int n0 = p.fcnt[2 * j], n1 = r1 >= 0 ? p.fcnt[2 * j + 1] : 0;
+        const int nmax = max(n0, n1);
+        if (nmax == 0) continue;
         const int L = p.rd.info[r0].x;
         __syncwarp();
         fill_rows(rows, p.rd, r0, r1, L, lane);
-        const int rr[2] = {r0, r1 >= 0 ? r1 : r0};
-        const bool rev[2] = {p.rd.reverse[rr[0]] != 0, p.rd.reverse[rr[1]] != 0};
-        const ColEntry* tab[2] = {rev[0] ? p.hp.tab_r : p.hp.tab_f, rev[1] ? p.hp.tab_r : p.hp.tab_f};
-        const ReadView rv[2] = {read_view(p.rd, rr[0]), read_view(p.rd, rr[1])};
-        const long long rbeg[2] = {p.rd.begin ? p.rd.begin[rr[0]] : 0, p.rd.begin ? p.rd.begin[rr[1]] : 0};
-        int cnt[2] = {0, 0};
-
-        auto dp_round = [&]() {
-            const int take0 = min(32, cnt[0]), take1 = min(32, cnt[1]);
-            const int base0 = cnt[0] - take0, base1 = cnt[1] - take1;
-            const bool v0 = lane < take0, v1 = lane < take1;
-            // idle lanes replay a valid task of the same round (results discarded)
-            int h0, a0, h1, a1;
-            if (take0 > 0) { const int s = base0 + (v0 ? lane : 0); h0 = qh[s]; a0 = qa[s]; }
-            else           { const int s = kQueueCap + base1;       h0 = qh[s]; a0 = qa[s]; }
-            if (take1 > 0) { const int s = kQueueCap + base1 + (v1 ? lane : 0); h1 = qh[s]; a1 = qa[s]; }
-            else           { h1 = h0; a1 = a0; }
-            const ColEntry* t0 = (take0 > 0 ? tab[0] : tab[1]) + p.hp.off[h0] + a0;
-            const ColEntry* t1 = (take1 > 0 ? tab[1] : (take0 > 0 ? tab[0] : tab[1])) + p.hp.off[h1] + a1;
-            const uint32_t res = dp_pair<BAND>(rows, L, t0, t1, nucp);
-            if (v0) atomicMin(p.best + (size_t)h0 * R + rr[0], (int)(res & 0xFFFFu));
-            if (v1) atomicMin(p.best + (size_t)h1 * R + rr[1], (int)(res >> 16));
-            cnt[0] = base0; cnt[1] = base1;
-            __syncwarp();
-        };
-
-        for (int hb = 0; hb < H; hb += 32) {
-            const int h = hb + lane;
-            const bool act = h < H;
-            const int hc = act ? h : H - 1;
-            const int hap_len = (int)(p.hp.off[hc + 1] - p.hp.off[hc]);
-            const long long hbeg = p.hp.begin ? p.hp.begin[hc] : 0;
-            int npos[2] = {0, 0};
-            const int32_t* pp[2] = {nullptr, nullptr};
-            EnumState st[2] = {{false, false}, {false, false}};
-            int maxslots = 0;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (act && (s == 0 || r1 >= 0)) {
-                    if (p.pos_off) {
-                        const long long o = p.pos_off[(size_t)hc * R + rr[s]];
-                        npos[s] = (int)(p.pos_off[(size_t)hc * R + rr[s] + 1] - o);
-                        pp[s] = p.pos + o;
-                    } else if (p.kcnt) {
-                        const size_t li = (size_t)p.k_first_list_index + 2 * (size_t)j + s;
-                        npos[s] = p.kcnt[li * H + hc];
-                        pp[s] = p.kpos + (li * H + hc) * kMaxMapped;
-                    }
-                }
-                maxslots = max(maxslots, npos[s] + 2);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) maxslots = max(maxslots, __shfl_xor_sync(0xffffffffu, maxslots, o));
-            for (int c = 0; c < maxslots; ++c) {
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    bool need_dp = false;
-                    int a = 0;
-                    if (act && (s == 0 || r1 >= 0)) {
-                        int pos;
-                        const int k = candidate_slot(c, npos[s], pp[s], rbeg[s] - hbeg, L, hap_len, p.band, st[s], &pos);
-                        if (k < 0) {
-                            p.status[(size_t)h * R + rr[s]] = 2 | (pos << 16);
-                            atomicOr(p.flags, 2);
-                        } else if (k > 0) {
-                            const HapView hv = hap_view(p.hp, h, rev[s]);
-                            int v;
-                            const CandKind kind = classify_candidate(hv, rv[s], p.band, pos, p.shortcut != 0, p.use_flanks != 0,
-                                                                     p.lhs_flank, p.rhs_flank, &v);
-                            if (kind == CAND_VALUE) atomicMin(p.best + (size_t)h * R + rr[s], v);
-                            else if (kind == CAND_DP) { need_dp = true; a = v; }
-                            else if (kind == CAND_DP_FLANK) push_slow(p, rr[s], h, v);
-                        }
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, need_dp);
-                    if (need_dp) {
-                        const int slot = s * kQueueCap + cnt[s] + __popc(m & lt_mask);
-                        qh[slot] = h; qa[slot] = a;
-                    }
-                    cnt[s] += __popc(m);
-                }
-                __syncwarp();
-                while (cnt[0] >= 32 || cnt[1] >= 32) dp_round();
-            }
+        const int rb = r1 >= 0 ? r1 : r0;
+        const ColEntry* tab0 = p.rd.reverse[r0] ? p.hp.tab_r : p.hp.tab_f;
+        const ColEntry* tab1 = p.rd.reverse[rb] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q0 = p.ftasks + (size_t)(2 * j) * p.fcap;
+        const uint32_t* q1 = q0 + p.fcap;
+        for (int c = 0; c < nmax; c += 32) {
+            const bool v0 = c + lane < n0, v1 = c + lane < n1;
+            // idle half-lanes replay a valid task of the same pair (result discarded)
+            const uint32_t t0 = n0 > 0 ? q0[v0 ? c + lane : 0] : q1[0];
+            const uint32_t t1 = n1 > 0 ? q1[v1 ? c + lane : 0] : t0;
+            const int h0 = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1 = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
+            const ColEntry* c0 = (n0 > 0 ? tab0 : tab1) + p.hp.off[h0] + a0;
+            const ColEntry* c1 = (n1 > 0 ? tab1 : tab0) + p.hp.off[h1] + a1;
+            const uint32_t res = dp_pair<BAND>(rows, L, c0, c1, nucp);
+            if (v0) atomicMin(p.best + (size_t)h0 * R + r0, (int)(res & 0xFFFFu));
+            if (v1) atomicMin(p.best + (size_t)h1 * R + r1, (int)(res >> 16));
         }
-        while (cnt[0] > 0 || cnt[1] > 0) dp_round();
     }
 }
 
 // Generic path of populate: reads the fast path cannot take (non-ACGT bases, 16-bit-unsafe qualities, very long reads)
 // or every read when the band is > 32 / int32 scores were requested. One thread per (haplotype, read) pair.
-template <int MAXK>
+// With FASTQ it is the classify pass of the fast path instead: the same candidate walk over the fast work list (the pair
+// list, entries may be -1), but score-only DP candidates are appended to the read's task list for k_populate_fast.
+template <int MAXK, bool FASTQ>
 __global__ void k_populate_generic(const PopParams p)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int H = p.hp.n, R = p.rd.n;
-    if (i >= (long long)p.n_generic * H) return;
-    const int r = p.generic_reads[i / H], h = (int)(i % H);
+    const int n_list = FASTQ ? 2 * p.n_pairs : p.n_generic;
+    if (i >= (long long)n_list * H) return;
+    const int li = (int)(i / H);
+    const int r = FASTQ ? p.pair_reads[li] : p.generic_reads[li], h = (int)(i % H);
+    if (r < 0) return;
     const bool rev = p.rd.reverse[r] != 0;
     const HapView hv = hap_view(p.hp, h, rev);
     const ReadView rv = read_view(p.rd, r);
@@ -441,7 +380,7 @@ __global__ void k_populate_generic(const PopParams p)
     int npos = 0;
     const int32_t* pp = nullptr;
     if (p.pos_off) { const long long o = p.pos_off[(size_t)h * R + r]; npos = (int)(p.pos_off[(size_t)h * R + r + 1] - o); pp = p.pos + o; }
-    else if (p.kcnt) { const size_t li = (size_t)p.k_first_list_index + (size_t)(i / H); npos = p.kcnt[li * H + h]; pp = p.kpos + (li * H + h) * kMaxMapped; }
+    else if (p.kcnt) { npos = p.kcnt[(size_t)li * H + h]; pp = p.kpos + ((size_t)li * H + h) * kMaxMapped; }
     EnumState st {false, false};
     int best = kBestInf;
     for (int c = 0; c < npos + 2; ++c) {
@@ -453,8 +392,14 @@ __global__ void k_populate_generic(const PopParams p)
         const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, p.use_flanks != 0, p.lhs_flank, p.rhs_flank, &v);
         if (kind == CAND_VALUE) best = min(best, v);
         else if (kind == CAND_DP) {
-            const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
-            best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
+            if (FASTQ) {
+                const int slot = atomicAdd(p.fcnt + li, 1);
+                if (slot < p.fcap) p.ftasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
+                else atomicOr(p.flags, 8);
+            } else {
+                const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
+                best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
+            }
         } else if (kind == CAND_DP_FLANK) push_slow(p, r, h, v);
     }
     if (best != kBestInf) atomicMin(p.best + (size_t)h * R + r, best);
