@@ -38,6 +38,10 @@ def parse_args():
     ap.add_argument("--haps", type=int, default=None)
     ap.add_argument("--cpu-sample-reads", type=int, default=None, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # non-headline modes (diagnostics; the headline is the default: one position per pair, DP for every pair, no flank state)
+    ap.add_argument("--flank", default=None, help="LHS,RHS flank sizes: exercises the traceback + flank-discount path")
+    ap.add_argument("--shortcut", action="store_true", help="enable the reference's naive shortcut (reference behaviour)")
+    ap.add_argument("--map", action="store_true", help="candidate positions from the device k-mer mapper (reference behaviour)")
     return ap.parse_args()
 
 
@@ -51,6 +55,15 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def issue_roofline(kernel_gcups, reads, band, clocks):
+    lens = np.diff(np.asarray(reads.off))
+    mean_ratio = float(((lens + band) / lens).mean())
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * mhz * 1e6 * (64.0 / 3.0) * mean_ratio / 1e9
+    return {"bound": "alu-pipe (DPX packed-16)", "achieved": kernel_gcups, "peak": peak, "unit": "GCUPS", "frac": kernel_gcups / peak,
+            "alu_instr_per_cell_pair": 6, "alu_thread_instr_per_clk_per_sm": 64, "sm_mhz": mhz}
 
 
 class ClockSampler:
@@ -218,14 +231,15 @@ def main():
     haps, reads, band = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=cfg["seed"] + 1000 * rank)
     H, R = haps.n, reads.n
     cells = synth.total_cells(haps, reads, band)
-    model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, map_positions=False)
+    model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=not args.shortcut, map_positions=args.map)
+    flank_state = tuple(int(x) for x in args.flank.split(",")) if args.flank else None
     eng = PairHMMEngine(local)
     d_haps, d_reads = haps.to_device(dev), reads.to_device(dev)
     d_out = torch.empty((H, R), dtype=torch.float64, device=dev)
     R_total = R * world
 
     def step():
-        eng.populate(model_cfg, d_haps, d_reads, out=d_out)
+        eng.populate(model_cfg, d_haps, d_reads, flank_state=flank_state, out=d_out)
         if world > 1:
             return shard.gather_likelihoods(d_out, R_total, world, rank)   # NCCL gather of the slabs to rank 0
         return d_out
@@ -263,12 +277,12 @@ def main():
     p_out_t = torch.empty((H, R), dtype=torch.float64).pin_memory()
     p_out = p_out_t.numpy()
     for _ in range(2):
-        eng.populate(model_cfg, p_haps, p_reads, out=p_out)
+        eng.populate(model_cfg, p_haps, p_reads, flank_state=flank_state, out=p_out)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.populate(model_cfg, p_haps, p_reads, out=p_out)
+        eng.populate(model_cfg, p_haps, p_reads, flank_state=flank_state, out=p_out)
     e1.record()
     sync_all()
     ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -297,7 +311,8 @@ def main():
                                    % (args.config, R, "/".join(map(str, cfg["read_lens"])), H, cfg["hap_len"], band),
                        "alignments_per_step": H * R * world, "cells_per_step": cells * world,
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
-                       "parallelism": "reads sharded over %d rank(s), haplotypes replicated, NCCL gather to rank 0" % world},
+                       "parallelism": "reads sharded over %d rank(s), haplotypes replicated, NCCL gather to rank 0" % world,
+                       "mode": {"flank_state": flank_state, "naive_shortcut": bool(args.shortcut), "kmer_mapper": bool(args.map)}},
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -306,6 +321,10 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the path is integer-issue bound, not HBM bound (SURVEY.md F3); see DESIGN.md for the issue-rate roofline",
                          "kernel_gcups": cells / (kernel_ms / 1e3) / 1e9},
+            # The binding roofline: the packed cell costs 6 ALU-pipe instructions per 2 cells and the ALU pipe
+            # issues 64 thread-instructions/clk/SM (profiles/r01_ubench_int.txt). In the reference's cell count 2(L+B)B per
+            # alignment (the column sweep itself touches 2LB cells) the peak is 148 SMs x clock x 64/3 x (L+B)/L.
+            "issue_roofline": issue_roofline(cells / (kernel_ms / 1e3) / 1e9, reads, band, clocks),
         }
         if not args.no_cpu_baseline:
             threads = host_threads()

@@ -228,6 +228,125 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Flank-aware path: one alignment per thread, 32-bit lanes = score | label | payload, band state in registers
+// ---------------------------------------------------------------------------------------------------------
+//
+// hmm::evaluate needs, for a read within `band` of a haplotype flank, the penalty the OPTIMAL path accrues inside the
+// flanks (pair_hmm.hpp:743-764 via simd_pair_hmm.hpp:352-430). In window coordinates the flanks are the truth indices
+// < xl and >= xr; the path is monotone in x, so its in-flank penalty is  V(first arrival at column xl) +
+// (total - V(first arrival at column xr))  and the in-flank read bases are  y_l + (L - y_r). Instead of storing
+// back-pointers, every DP value carries a payload naming the cell through which ITS OWN best path crossed into
+// column xl / xr (diagonal k and arrival type M/D); the arrival values of those two columns are kept aside.
+// A payload is only meaningful if the DP picks predecessors exactly as the reference's traceback does: the reference
+// breaks score ties by state label (M 0 < I 1 < D 3 in the two low bits, simd_pair_hmm.hpp:147-163), so values are
+// laid out  [31:18] score  [17:16] label  [15:8] payload R  [7:0] payload L  and compared as whole words — the three
+// candidates of every min carry distinct labels, so the payload never takes part in a decision.
+constexpr uint32_t kF32ScoreShift = 18;
+constexpr uint32_t kF32LabelMask  = 3u << 16;
+constexpr uint32_t kF32LabI       = 1u << 16;
+constexpr uint32_t kF32LabD       = 3u << 16;
+constexpr uint32_t kF32Inf        = 0x3800u << kF32ScoreShift;       // +inf score (14336), leaves room for +2*127+nuc below 2^14
+constexpr int      kMaxScoreFlank32 = 0x3800 - 1024;                  // read quality-sum bound for this path
+constexpr uint32_t kF32Valid = 0x80u, kF32TypeD = 0x40u;
+
+PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// rows: shared-memory row entries built with make_row_entry(half, 0): .x low nibble = base code, .y low 16 bits = qual.
+// tab : column table of the window. xl / xr: first non-flank column and first right-flank column (0 <= xl < xr <= W);
+// xl == 0 / xr == W mean "no left / right flank". Outputs the integer score, the in-flank penalty and the in-flank read bases.
+template <int BAND>
+PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ tab, const int nuc_prior,
+                        const int xl, const int xr, int* score_out, int* flank_out, int* mask_out)
+{
+    constexpr int K = 2 * BAND;
+    static_assert(K <= 64, "register band limited to 64 diagonals");
+    uint32_t M[K], D[K];
+    uint32_t bnd[4][K];          // arrivals at columns xl (M, D) and xr (M, D)
+    uint32_t end_s[K];           // S(L + k, L) with label and payload
+#pragma unroll
+    for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kF32Inf | kF32LabD; end_s[k] = 0xFFFFFFFFu; }
+    const int W = L + K - 1;
+    const uint32_t nucS = (uint32_t)nuc_prior << kF32ScoreShift;
+    ColEntry e = ldg(tab);
+    uint32_t go_prev = 0u, ge_prev = 0u;
+    const RowEntry w0 = rows[0];
+
+#define PHMM_FCELL(k, CAPTURE)                                                                          \
+    {                                                                                                   \
+        const RowEntry w = rp[-(k)];                                                                    \
+        const uint32_t sub = umin32(w.y & 0xFFu, prmt(caps, 0u, (w.x & 3u) | 0x4440u));                 \
+        const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                              \
+        const uint32_t S = umin32(umin32(m, i_run), d);                                                 \
+        CAPTURE                                                                                         \
+        M[(k) < K ? (k) : 0] = (S & ~kF32LabelMask) + (sub << kF32ScoreShift);                          \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = (umin32(d + geS, umin32(m, i_run) + goS) & ~kF32LabelMask) | kF32LabD; \
+        i_run = (umin32(i_run + gepS, m + gopS) & ~kF32LabelMask) | kF32LabI;                           \
+    }
+
+    for (int x = 0; x <= W; ++x) {
+        const int xn = (x + 1 < W) ? x + 1 : W - 1;
+        const ColEntry nx = ldg(tab + xn);
+        const uint32_t caps = e.x;
+        const uint32_t goS = (e.y & 0xFFu) << kF32ScoreShift, geS = ((e.y >> 8) & 0xFFu) << kF32ScoreShift;
+        const uint32_t gopS = go_prev + nucS, gepS = ge_prev + nucS;
+        const RowEntry* rp = rows + x;
+        uint32_t i_run = kF32Inf | kF32LabI;
+        if (x >= K && x < L) {   // steady state (column L holds the first end cell and takes the general body)
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) PHMM_FCELL(k, )
+        } else {
+            const int klo = x - L;
+            if (x < K) i_run = (x & 1) ? (gopS | kF32LabI) : (kF32Inf | kF32LabI);   // i(x, 1) out of the free-start cell
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                if (k == x) {
+                    M[k] = umin32(w0.y & 0xFFu, prmt(caps, 0u, (w0.x & 3u) | 0x4440u)) << kF32ScoreShift;   // m(x+1, 1) = sub(x, 0)
+                } else if (k < x && k >= klo) {
+                    // row L (k == klo): keep the labelled S — the end-cell choice compares it with its label (unlike the
+                    // score-only kernel, whose captured M[k] has the label cleared)
+                    PHMM_FCELL(k, if (k == klo) end_s[k] = S;)
+                }
+            }
+        }
+        // the arrivals now held in M[k] / D[k] belong to column x+1: at the two flank boundaries record them and stamp
+        // the crossing (diagonal, arrival type) into their payload
+        if (x + 1 == xl || x + 1 == xr) {
+            const int which = (x + 1 == xl) ? 0 : 2;
+            const int shift = (x + 1 == xl) ? 0 : 8;
+            const int klo1 = x + 1 - L;             // cells of column x+1 exist for max(0, klo1) <= k <= min(K-1, x)  (row 0 excluded)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k >= klo1 && k <= x) {
+                    bnd[which][k] = M[k]; bnd[which + 1][k] = D[k];
+                    M[k] |= (kF32Valid | (uint32_t)k) << shift;
+                    D[k] |= (kF32Valid | kF32TypeD | (uint32_t)k) << shift;
+                }
+            }
+        }
+        go_prev = goS; ge_prev = geS; e = nx;
+    }
+#undef PHMM_FCELL
+    // end row: minimum over (score, label), earliest end on ties (simd_pair_hmm.hpp:285-291, 309-315 compare the labelled values)
+    uint32_t best = end_s[0];
+    int kbest = 0;
+    for (int k = 1; k < K; ++k) if ((end_s[k] >> 16) < (best >> 16)) { best = end_s[k]; kbest = k; }
+    const int total = (int)(best >> kF32ScoreShift), x_end = L + kbest;
+    const uint32_t pl = best & 0xFFu, pr = (best >> 8) & 0xFFu;
+    int v_l, y_l, v_r, y_r;
+    if (xl <= 0) { v_l = 0; y_l = 0; }
+    else if (pl & kF32Valid) { const int k = pl & 0x3F; v_l = (int)(bnd[(pl & kF32TypeD) ? 1 : 0][k] >> kF32ScoreShift); y_l = xl - k; }
+    else if (x_end < xl) { v_l = total; y_l = L; }      // the whole path lies in the left flank
+    else { v_l = 0; y_l = 0; }                          // the path starts at or beyond xl
+    if (xr > W) { v_r = total; y_r = L; }
+    else if (pr & kF32Valid) { const int k = pr & 0x3F; v_r = (int)(bnd[(pr & kF32TypeD) ? 3 : 2][k] >> kF32ScoreShift); y_r = xr - k; }
+    else if (x_end >= xr) { v_r = 0; y_r = 0; }         // the path starts inside the right flank
+    else { v_r = total; y_r = L; }                      // the path never reaches the right flank
+    *score_out = total;
+    *flank_out = v_l + (total - v_r);
+    *mask_out = y_l + (L - y_r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Generic path: int32, any band / alphabet, optional traceback + flank replay (one thread per alignment)
 // ---------------------------------------------------------------------------------------------------------
 

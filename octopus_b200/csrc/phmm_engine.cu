@@ -58,7 +58,7 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, bp;
     DBuf tasks_lane, tasks_generic, works, scores;
-    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt;
+    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, gcnt;
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
     // host-space calls on large batches are pipelined over two sub-engines (own stream + buffers each), driven by two host
@@ -252,7 +252,7 @@ void phmm_destroy(phmm_engine* e)
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
                    &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
-                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt};
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->gcnt};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -309,7 +309,7 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         const long long hl = s.hap_off_host[t.hap + 1] - s.hap_off_host[t.hap];
         if (L < 1 || t.win_off < 0 || (long long)t.win_off + L + 2 * band - 1 > hl) { e->err = "task window outside the haplotype"; return PHMM_ERR_INVALID; }
         cells += 2LL * (L + band) * band;
-        if (fast_ok && e->info_host[t.read].y == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
+        if (fast_ok && (e->info_host[t.read].y & kReadGenericMask) == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
         else gen.push_back(GenericTask {t.read, t.hap, t.win_off, t.reverse ? 1 : 0, j});
     }
     e->last_dp_cells = cells;
@@ -589,7 +589,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             const int2 inf = e->info_host[r];
             Lmax_all = std::max(Lmax_all, inf.x);
             if (inf.x < 1) { e->err = "empty read"; return PHMM_ERR_INVALID; }
-            if (fast_ok && inf.y == 0) { order.push_back(r); Lmax_fast = std::max(Lmax_fast, inf.x); }
+            if (fast_ok && (inf.y & kReadGenericMask) == 0) { order.push_back(r); Lmax_fast = std::max(Lmax_fast, inf.x); }
             else generic_reads.push_back(r);
         }
         // counting sort by length keeps the pairing O(R)
@@ -649,7 +649,14 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(e->fcnt.ensure(list_cap * sizeof(int)));
         p.ftasks = e->ftasks.as<uint32_t>();
         p.fcnt = e->fcnt.as<int>();
+        if (p.use_flanks) {
+            CU(e->gtasks.ensure(list_cap * p.fcap * sizeof(uint32_t)));
+            CU(e->gcnt.ensure(list_cap * sizeof(int)));
+            p.gtasks = e->gtasks.as<uint32_t>();
+            p.gcnt = e->gcnt.as<int>();
+        }
     }
+    p.flank_cursor = counters + 2;
     const int slow_threads = e->sm_count * 256;
     if (p.use_flanks) {
         reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
@@ -695,6 +702,10 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             }
             CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
+            if (p.use_flanks) {
+                CU(cudaMemsetAsync(p.gcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
+                CU(cudaMemsetAsync(p.flank_cursor, 0, sizeof(int), e->stream));
+            }
             {   // classify pass: shortcut values → best[], near-flank candidates → slow queue, DP candidates → task lists
                 const long long threads = 2LL * np * H;
                 k_populate_generic<64, true><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p);
@@ -712,6 +723,15 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             LAUNCHED();
             CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             ++n_timed; timed = true;
+            if (p.use_flanks) {   // near-flank candidates of the fast-path reads: payload-carrying 32-bit DP
+                const unsigned fgrid = (unsigned)std::max(1, std::min((2 * np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
+                switch (band) {
+                    case 8:  k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+                    case 16: k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+                    default: k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+                }
+                LAUNCHED();
+            }
             p0 += np;
         } else {
             const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);

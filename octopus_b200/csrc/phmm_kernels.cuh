@@ -33,6 +33,8 @@ struct DevReads {
 constexpr int kReadNonACGT  = 1;   // read holds a byte outside ACGT → generic path
 constexpr int kReadUnsafe16 = 2;   // sum of qualities too large for a 16-bit lane, or a quality > 127
 constexpr int kReadTooLong  = 4;   // longer than the fast path's shared-memory row budget
+constexpr int kReadUnsafeFlank32 = 8;   // quality sum too large for the 14-bit score field of the flank-aware kernel (fast path still fine)
+constexpr int kReadGenericMask = 7;     // any of these → the read takes the generic (int32) path
 
 constexpr int kFastMaxReadLen = 1023;
 
@@ -79,6 +81,7 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
         qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
     }
     if (qsum > kMaxScore16) flags |= kReadUnsafe16;
+    if (qsum > kMaxScoreFlank32) flags |= kReadUnsafeFlank32;
     if (L > kFastMaxReadLen || L < 1) flags |= kReadTooLong;
     if (lane == 0) info[r] = make_int2(L, flags);
 }
@@ -169,6 +172,10 @@ struct PopParams {
     uint32_t* ftasks;
     int* fcnt;
     int fcap;
+    // near-flank candidates of fast-path reads, same layout (consumed by k_populate_flank)
+    uint32_t* gtasks;
+    int* gcnt;
+    int* flank_cursor;
     int band, nuc_prior;
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
     int use_flanks;             // flank_state present && config.use_flank_state
@@ -359,6 +366,51 @@ k_populate_fast(const PopParams p)
     }
 }
 
+// Near-flank candidates of fast-path reads: the payload-carrying 32-bit DP (dp_flank32), one alignment per lane, one READ
+// per warp (row entries broadcast from shared memory), persistent warps over the tile's work list.
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
+k_populate_flank(const PopParams p)
+{
+    extern __shared__ RowEntry smem_rows[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int R = p.rd.n;
+    constexpr int K = 2 * BAND;
+    for (;;) {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(p.flank_cursor, 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li >= 2 * p.n_pairs) break;
+        const int r = p.pair_reads[li];
+        const int n = r >= 0 ? p.gcnt[li] : 0;
+        if (n == 0) continue;
+        const int L = p.rd.info[r].x;
+        __syncwarp();
+        fill_rows(rows, p.rd, r, -1, L, lane);
+        const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q = p.gtasks + (size_t)li * p.fcap;
+        const int W = L + K - 1;
+        for (int c = 0; c < n; c += 32) {
+            const bool valid = c + lane < n;
+            const uint32_t t = q[valid ? c + lane : 0];
+            const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
+            const int hap_len = (int)(p.hp.off[h + 1] - p.hp.off[h]);
+            int lhs, rhs;
+            window_flanks(a, W, hap_len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+            int xl = lhs, xr = W - rhs;
+            const bool all_flank = xr <= xl;        // flanks overlap: every operation is inside a flank
+            if (all_flank) { xl = 0; xr = W + 1; }
+            if (xr >= W) xr = W + 1;
+            int score, flank, mask;
+            dp_flank32<BAND>(rows, L, tab + p.hp.off[h] + a, p.nuc_prior, xl, xr, &score, &flank, &mask);
+            if (all_flank) { flank = score; mask = L; }
+            const int v = discount_flank(score, flank, L, mask, 0);
+            if (valid) atomicMin(p.best + (size_t)h * R + r, v);
+        }
+    }
+}
+
 // Generic path of populate: reads the fast path cannot take (non-ACGT bases, 16-bit-unsafe qualities, very long reads)
 // or every read when the band is > 32 / int32 scores were requested. One thread per (haplotype, read) pair.
 // With FASTQ it is the classify pass of the fast path instead: the same candidate walk over the fast work list (the pair
@@ -400,7 +452,13 @@ __global__ void k_populate_generic(const PopParams p)
                 const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
                 best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
             }
-        } else if (kind == CAND_DP_FLANK) push_slow(p, r, h, v);
+        } else if (kind == CAND_DP_FLANK) {
+            if (FASTQ && !(p.rd.info[r].y & kReadUnsafeFlank32)) {
+                const int slot = atomicAdd(p.gcnt + li, 1);
+                if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
+                else atomicOr(p.flags, 8);
+            } else push_slow(p, r, h, v);
+        }
     }
     if (best != kBestInf) atomicMin(p.best + (size_t)h * R + r, best);
 }

@@ -104,3 +104,31 @@ extern "C" int emul_pair_evaluate(int band, const char* hap, int hap_len, const 
     *out = finish_likelihood(best, use_mapq != 0, mapq, mapq_cap, mapq_trigger);
     return 0;
 }
+
+// dp_flank32<band> on the CPU: one alignment, flanks in window coordinates. Returns 0 / -1.
+extern "C" int emul_dp_flank32(int band, int L, const char* read, const uint8_t* q, const char* truth, const char* mask, const int8_t* prior,
+                               const int8_t* go, const int8_t* ge, int nuc_prior, int lhs_flank, int rhs_flank,
+                               int* score, int* flank, int* mask_size)
+{
+    const int W = L + 2 * band - 1;
+    std::vector<RowEntry> rows(L + 1);
+    for (int y = 0; y < L; ++y) {
+        const int c = base_code(read[y]);
+        if (c < 0) return -1;
+        rows[y] = make_row_entry((uint32_t)c | ((uint32_t)q[y] << 8), 0u);
+    }
+    rows[L] = pad_row_entry();
+    std::vector<ColEntry> t(W);
+    for (int x = 0; x < W; ++x) t[x] = make_col_entry(truth[x], mask[x], prior[x], go[x], ge[x]);
+    int xl = lhs_flank, xr = W - rhs_flank;
+    if (xr <= xl) { xl = 0; xr = W + 1; }   // overlapping flanks: every op is in a flank (caller treats the score as the flank score)
+    if (xr >= W) xr = W + 1;
+    switch (band) {
+        case 8:  dp_flank32<8>(rows.data(), L, t.data(), nuc_prior, xl, xr, score, flank, mask_size); break;
+        case 16: dp_flank32<16>(rows.data(), L, t.data(), nuc_prior, xl, xr, score, flank, mask_size); break;
+        case 32: dp_flank32<32>(rows.data(), L, t.data(), nuc_prior, xl, xr, score, flank, mask_size); break;
+        default: return -1;
+    }
+    if (W - rhs_flank <= lhs_flank) { *flank = *score; *mask_size = L; }
+    return 0;
+}
