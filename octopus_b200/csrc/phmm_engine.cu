@@ -581,6 +581,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     // the fast path packs (haplotype, window offset) into 16 + 16 bits
     const bool fast_ok = band <= 32 && !cfg->use_int_scores && H <= 65535 && max_hap_len <= 65535;
     std::vector<int> generic_reads, pairs;
+    // lane groups per warp of the fast kernel: with few haplotypes a read has few DP tasks, so several read pairs share a warp
+    const size_t groups = H >= 17 ? 1 : (H >= 9 ? 2 : 4);
     int Lmax_fast = 1, Lmax_all = 1;
     {
         std::vector<int> order;
@@ -598,12 +600,19 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
         std::vector<int> sorted(order.size());
         for (int r : order) sorted[count[e->info_host[r].x]++] = r;
-        pairs.reserve(sorted.size() + 2);
+        pairs.reserve(sorted.size() + 2 * groups + 2);
+        int cur_len = -1;
         for (size_t i = 0; i < sorted.size();) {
             const int r0 = sorted[i];
-            if (i + 1 < sorted.size() && e->info_host[sorted[i + 1]].x == e->info_host[r0].x) { pairs.push_back(r0); pairs.push_back(sorted[i + 1]); i += 2; }
+            const int len = e->info_host[r0].x;
+            if (len != cur_len) {   // a warp's G pairs must share one read length: pad to a multiple of G at every length boundary
+                while ((pairs.size() / 2) % groups) { pairs.push_back(-1); pairs.push_back(-1); }
+                cur_len = len;
+            }
+            if (i + 1 < sorted.size() && e->info_host[sorted[i + 1]].x == len) { pairs.push_back(r0); pairs.push_back(sorted[i + 1]); i += 2; }
             else { pairs.push_back(r0); pairs.push_back(-1); i += 1; }
         }
+        while ((pairs.size() / 2) % groups) { pairs.push_back(-1); pairs.push_back(-1); }
     }
     const int n_pairs = (int)(pairs.size() / 2), n_generic = (int)generic_reads.size();
 
@@ -671,21 +680,22 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
 
     p.row_stride = (Lmax_fast + 2) & ~1;
-    const size_t smem = (size_t)kFastWarpsPerBlock * p.row_stride * sizeof(RowEntry);
+    const size_t smem = (size_t)kFastWarpsPerBlock * groups * p.row_stride * sizeof(RowEntry);
     int blocks_per_sm = 1;
     if (n_pairs) {
-        switch (band) {
-            case 8:  if ((rc = fast_smem_attr(e, k_populate_fast<8>, smem))) return rc;
-                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<8>, kFastWarpsPerBlock * 32, smem)); break;
-            case 16: if ((rc = fast_smem_attr(e, k_populate_fast<16>, smem))) return rc;
-                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<16>, kFastWarpsPerBlock * 32, smem)); break;
-            default: if ((rc = fast_smem_attr(e, k_populate_fast<32>, smem))) return rc;
-                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<32>, kFastWarpsPerBlock * 32, smem)); break;
-        }
+#define PHMM_FAST_SETUP(B, GG) \
+        { if ((rc = fast_smem_attr(e, k_populate_fast<B, GG>, smem))) return rc; \
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<B, GG>, kFastWarpsPerBlock * 32, smem)); }
+#define PHMM_FAST_DISPATCH(MACRO) \
+        switch (band * 10 + (int)groups) { \
+            case 81: MACRO(8, 1) break;   case 82: MACRO(8, 2) break;   case 84: MACRO(8, 4) break; \
+            case 161: MACRO(16, 1) break; case 162: MACRO(16, 2) break; case 164: MACRO(16, 4) break; \
+            case 321: MACRO(32, 1) break; case 322: MACRO(32, 2) break; default: MACRO(32, 4) break; }
+        PHMM_FAST_DISPATCH(PHMM_FAST_SETUP)
         if (blocks_per_sm < 1) { e->err = "fast kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; }
     }
 
-    const long long pairs_per_tile = std::max<long long>(1, reads_per_tile / 2);
+    const long long pairs_per_tile = std::max<long long>((long long)groups, (reads_per_tile / 2) / (long long)groups * (long long)groups);
     bool timed = false;
     size_t n_timed = 0;
     for (long long p0 = 0, g0 = 0; p0 < n_pairs || g0 < n_generic;) {
@@ -711,24 +721,25 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 k_populate_generic<64, true><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p);
                 LAUNCHED();
             }
-            const int want_blocks = (np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock;
+            const int want_blocks = (int)((np / (int)groups + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
             const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
             while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); }
             CU(cudaEventRecord(e->tile_events[2 * n_timed], e->stream));
-            switch (band) {
-                case 8:  k_populate_fast<8><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
-                case 16: k_populate_fast<16><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
-                default: k_populate_fast<32><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
-            }
+#define PHMM_FAST_LAUNCH(B, GG) k_populate_fast<B, GG><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p);
+            PHMM_FAST_DISPATCH(PHMM_FAST_LAUNCH)
             LAUNCHED();
             CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             ++n_timed; timed = true;
             if (p.use_flanks) {   // near-flank candidates of the fast-path reads: payload-carrying 32-bit DP
                 const unsigned fgrid = (unsigned)std::max(1, std::min((2 * np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
+                const size_t fsmem = (size_t)kFastWarpsPerBlock * p.row_stride * sizeof(RowEntry);
                 switch (band) {
-                    case 8:  k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
-                    case 16: k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
-                    default: k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p); break;
+                    case 8:  if ((rc = fast_smem_attr(e, k_populate_flank<8>, fsmem))) return rc;
+                             k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                    case 16: if ((rc = fast_smem_attr(e, k_populate_flank<16>, fsmem))) return rc;
+                             k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                    default: if ((rc = fast_smem_attr(e, k_populate_flank<32>, fsmem))) return rc;
+                             k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
                 }
                 LAUNCHED();
             }

@@ -321,45 +321,67 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list, const
 }
 
 // Fast-path DP over the task lists the classify pass (k_populate_generic<.., true>) produced. Persistent warps: each warp
-// repeatedly claims one read pair (r0, r1) of equal length, stages the pair's row entries in shared memory once, and runs
-// dp_pair over the two reads' task lists 32 + 32 tasks at a time — 64 alignments per round, two per lane — folding the
+// repeatedly claims G consecutive read pairs of equal length (G = 1, 2 or 4 lane groups; G > 1 keeps the lanes busy when a
+// read has fewer than 32 tasks, i.e. few haplotypes), stages each pair's row entries in shared memory once, and runs
+// dp_pair over the pairs' task lists (32/G + 32/G tasks per group and round, two alignments per lane), folding the
 // scores into best[] with atomicMin. Nothing but the DP lives in this kernel: the register-resident band gets the whole
-// register budget.
-template <int BAND>
+// register budget. The host pads the pair list so that the G pairs of a warp share one read length ((-1,-1) = idle group).
+template <int BAND, int G>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 2)
 k_populate_fast(const PopParams p)
 {
     extern __shared__ RowEntry smem_rows[];
+    constexpr int LG = 32 / G;                          // lanes per group
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int grp = lane / LG, gl = lane % LG;
+    RowEntry* rows = smem_rows + (warp * G + grp) * p.row_stride;
     const int R = p.rd.n;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     for (;;) {
-        int j = 0;
-        if (lane == 0) j = atomicAdd(p.pair_cursor, 1);
-        j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= p.n_pairs) break;
-        const int r0 = p.pair_reads[2 * j], r1 = p.pair_reads[2 * j + 1];
-        const int n0 = p.fcnt[2 * j], n1 = r1 >= 0 ? p.fcnt[2 * j + 1] : 0;
-        const int nmax = max(n0, n1);
+        int jb = 0;
+        if (lane == 0) jb = atomicAdd(p.pair_cursor, G);
+        jb = __shfl_sync(0xffffffffu, jb, 0);
+        if (jb >= p.n_pairs) break;
+        const int j = jb + grp;
+        const int r0 = j < p.n_pairs ? p.pair_reads[2 * j] : -1;
+        const int r1 = r0 >= 0 ? p.pair_reads[2 * j + 1] : -1;
+        const int n0 = r0 >= 0 ? p.fcnt[2 * j] : 0, n1 = r1 >= 0 ? p.fcnt[2 * j + 1] : 0;
+        int nmax = max(n0, n1), L = r0 >= 0 ? p.rd.info[r0].x : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); L = max(L, __shfl_xor_sync(0xffffffffu, L, o)); }
         if (nmax == 0) continue;
-        const int L = p.rd.info[r0].x;
         __syncwarp();
-        fill_rows(rows, p.rd, r0, r1, L, lane);
+        if (r0 >= 0) {   // cooperative fill by the group's lanes
+            const uint16_t* h0 = p.rd.rowhalf + p.rd.off[r0];
+            const uint16_t* h1 = r1 >= 0 ? p.rd.rowhalf + p.rd.off[r1] : nullptr;
+            for (int y = gl; y < L; y += LG) rows[y] = make_row_entry(h0[y], h1 ? (uint32_t)h1[y] : 0u);
+            if (gl == 0) rows[L] = pad_row_entry();
+        }
+        __syncwarp();
         const int rb = r1 >= 0 ? r1 : r0;
-        const ColEntry* tab0 = p.rd.reverse[r0] ? p.hp.tab_r : p.hp.tab_f;
-        const ColEntry* tab1 = p.rd.reverse[rb] ? p.hp.tab_r : p.hp.tab_f;
-        const uint32_t* q0 = p.ftasks + (size_t)(2 * j) * p.fcap;
+        const ColEntry* tab0 = (r0 >= 0 && p.rd.reverse[r0]) ? p.hp.tab_r : p.hp.tab_f;
+        const ColEntry* tab1 = (rb >= 0 && p.rd.reverse[rb]) ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q0 = p.ftasks + (size_t)(2 * (size_t)max(j, 0)) * p.fcap;
         const uint32_t* q1 = q0 + p.fcap;
-        for (int c = 0; c < nmax; c += 32) {
-            const bool v0 = c + lane < n0, v1 = c + lane < n1;
-            // idle half-lanes replay a valid task of the same pair (result discarded)
-            const uint32_t t0 = n0 > 0 ? q0[v0 ? c + lane : 0] : q1[0];
-            const uint32_t t1 = n1 > 0 ? q1[v1 ? c + lane : 0] : t0;
+        for (int c = 0; c < nmax; c += LG) {
+            const bool v0 = c + gl < n0, v1 = c + gl < n1;
+            // idle half-lanes replay a valid task (result discarded): of their own group if it has one, else of any lane
+            const bool have = (n0 > 0) || (n1 > 0);
+            uint32_t t0 = 0, t1 = 0;
+            const ColEntry *b0 = tab0, *b1 = tab1;
+            if (have) {
+                t0 = n0 > 0 ? q0[v0 ? c + gl : 0] : q1[0];
+                t1 = n1 > 0 ? q1[v1 ? c + gl : 0] : t0;
+                if (n0 == 0) b0 = tab1;
+                if (n1 == 0) b1 = tab0;
+            }
+            const unsigned anyone = __ballot_sync(0xffffffffu, have);
+            const int src = __ffs(anyone) - 1;
+            const uint32_t s0 = __shfl_sync(0xffffffffu, t0, src), s1 = __shfl_sync(0xffffffffu, t1, src);
+            const unsigned long long sb0 = __shfl_sync(0xffffffffu, (unsigned long long)b0, src), sb1 = __shfl_sync(0xffffffffu, (unsigned long long)b1, src);
+            if (!have) { t0 = s0; t1 = s1; b0 = (const ColEntry*)sb0; b1 = (const ColEntry*)sb1; }
             const int h0 = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1 = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
-            const ColEntry* c0 = (n0 > 0 ? tab0 : tab1) + p.hp.off[h0] + a0;
-            const ColEntry* c1 = (n1 > 0 ? tab1 : tab0) + p.hp.off[h1] + a1;
-            const uint32_t res = dp_pair<BAND>(rows, L, c0, c1, nucp);
+            const uint32_t res = dp_pair<BAND>(rows, L, b0 + p.hp.off[h0] + a0, b1 + p.hp.off[h1] + a1, nucp);
             if (v0) atomicMin(p.best + (size_t)h0 * R + r0, (int)(res & 0xFFFFu));
             if (v1) atomicMin(p.best + (size_t)h1 * R + r1, (int)(res >> 16));
         }
