@@ -155,7 +155,7 @@ def cpu_reference_run(haps, reads, band, n_sample_reads, threads):
     cells = int((2 * (lens + band) * band).sum()) * H
     isas = available_ref_isas()
     if isas:
-        isa = "avx2" if "avx2" in isas else isas[0]
+        isa = isas[0]   # the widest build this host runs == what the reference's -march=native build would select (AVX2 for band 16)
         k = RefKernel(isa)
         batch = reference_batch_dict(haps, reads)
         ridx = np.repeat(np.arange(n, dtype=np.int32), H)

@@ -175,6 +175,13 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
                   const phmm_positions* positions, const phmm_flank_state* flank,
                   double* out, int32_t* status, int space);
 
+/* Consumer of the matrix ("next" row N1): ConstantMixtureGenotypeLikelihoodModel::evaluate for G genotypes of one ploidy
+ * (core/models/genotype/constant_mixture_genotype_likelihood_model.cpp:30-140) over a [H][R] matrix in `space`:
+ *   out[g] = sum_r ( log_sum_exp_{h in genotype g} lnl[h*R + r] - ln ploidy ),   genotypes[g*ploidy + k] = haplotype index.
+ * Keeping the matrix on the device and returning G numbers instead of H*R removes the D2H / gather volume. */
+int phmm_genotype_likelihoods(phmm_engine* e, const double* lnl, int32_t n_haplotypes, int32_t n_reads,
+                              const int32_t* genotypes, int32_t n_genotypes, int32_t ploidy, double* out, int space);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,6 +162,26 @@ class PairHMMEngine:
         cigars = [bytes(cg[j * cigar_stride:(j + 1) * cigar_stride]).split(b"\0", 1)[0].decode() for j in range(n)]
         return mp, lk, cigars, st
 
+    def genotype_likelihoods(self, lnl, genotypes):
+        """ConstantMixtureGenotypeLikelihoodModel::evaluate for every row of `genotypes` ((G, ploidy) haplotype indices) over the
+        (H, R) matrix `lnl` (numpy on the host, or a torch CUDA tensor left where populate produced it). Returns G doubles."""
+        if _is_torch(lnl):
+            import torch
+            m = lnl.contiguous()
+            gt = torch.as_tensor(np.ascontiguousarray(genotypes, dtype=np.int32), device=m.device)
+            out = torch.empty(gt.shape[0], dtype=torch.float64, device=m.device)
+            rc = self._lib.phmm_genotype_likelihoods(self._h, m.data_ptr(), m.shape[0], m.shape[1], gt.data_ptr(), gt.shape[0], gt.shape[1],
+                                                     out.data_ptr(), _lib.SPACE_DEVICE)
+        else:
+            m = np.ascontiguousarray(lnl, dtype=np.float64)
+            gt = np.ascontiguousarray(genotypes, dtype=np.int32)
+            out = np.empty(gt.shape[0], dtype=np.float64)
+            rc = self._lib.phmm_genotype_likelihoods(self._h, m.ctypes.data, m.shape[0], m.shape[1], gt.ctypes.data, gt.shape[0], gt.shape[1],
+                                                     out.ctypes.data, _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+        return out
+
     # -- batch boundary ----------------------------------------------------------------------------------------
     def populate(self, config, haps: HaplotypeBlock, reads: ReadBlock, positions=None, flank_state=None, out=None,
                  want_status=False):

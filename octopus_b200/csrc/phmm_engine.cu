@@ -438,6 +438,34 @@ int phmm_align_traceback(phmm_engine* e, int band,
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// phmm_genotype_likelihoods
+// -------------------------------------------------------------------------------------------------------------
+int phmm_genotype_likelihoods(phmm_engine* e, const double* lnl, int32_t H, int32_t R,
+                              const int32_t* genotypes, int32_t G, int32_t ploidy, double* out, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    e->err.clear(); e->launches_last = 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    if (!lnl || !genotypes || !out || H <= 0 || R <= 0 || G < 0 || ploidy < 0 || ploidy > 64) { e->err = "bad argument"; return PHMM_ERR_INVALID; }
+    if (G == 0) return PHMM_OK;
+    const double* d_lnl; const int32_t* d_gt;
+    int rc;
+    if ((rc = stage(e, e->out, lnl, (size_t)H * R, space, &d_lnl))) return rc;
+    if ((rc = stage(e, e->pairs, genotypes, (size_t)G * std::max(ploidy, 1), space, &d_gt))) return rc;
+    if (space == PHMM_SPACE_HOST) {   // haplotype indices are checked where they are cheap to read
+        for (long long i = 0; i < (long long)G * ploidy; ++i) if (genotypes[i] < 0 || genotypes[i] >= H) { e->err = "haplotype index out of range"; return PHMM_ERR_INVALID; }
+    }
+    CU(e->scores.ensure((size_t)G * sizeof(double)));
+    double* d_out = space == PHMM_SPACE_DEVICE ? out : e->scores.as<double>();
+    k_genotype_likelihoods<<<G, 256, 0, e->stream>>>(d_lnl, R, d_gt, ploidy, d_out);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    if (space == PHMM_SPACE_HOST) CU(cudaMemcpyAsync(out, d_out, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PHMM_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // phmm_align_reads
 // -------------------------------------------------------------------------------------------------------------
 int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,

@@ -327,7 +327,7 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list, const
 // scores into best[] with atomicMin. Nothing but the DP lives in this kernel: the register-resident band gets the whole
 // register budget. The host pads the pair list so that the G pairs of a warp share one read length ((-1,-1) = idle group).
 template <int BAND, int G>
-__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 2)
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 3)
 k_populate_fast(const PopParams p)
 {
     extern __shared__ RowEntry smem_rows[];
@@ -643,6 +643,33 @@ __global__ void k_align_reads(const AlignParams p)
             p.likelihood[i] = -1.7976931348623157e308;
         }
     }
+}
+
+// N1: ConstantMixtureGenotypeLikelihoodModel::evaluate on the resident [H][R] matrix
+// (core/models/genotype/constant_mixture_genotype_likelihood_model.cpp:30-140): one block per genotype,
+// ln p(reads | g) = sum_r ( log_sum_exp_{h in g} lnl[h][r] - ln ploidy ); homozygous genotypes reduce to a plain sum.
+__global__ void __launch_bounds__(256)
+k_genotype_likelihoods(const double* __restrict__ lnl, const int R, const int* __restrict__ genotypes, const int ploidy, double* __restrict__ out)
+{
+    __shared__ double partial[256];
+    const int g = blockIdx.x;
+    const int* gt = genotypes + (size_t)g * ploidy;
+    bool homo = true;
+    for (int k = 1; k < ploidy; ++k) homo = homo && gt[k] == gt[0];
+    const double ln_ploidy = log((double)ploidy);
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        if (homo) { acc += lnl[(size_t)gt[0] * R + r]; continue; }
+        double mx = lnl[(size_t)gt[0] * R + r];
+        for (int k = 1; k < ploidy; ++k) mx = fmax(mx, lnl[(size_t)gt[k] * R + r]);
+        double sum = 0.0;
+        for (int k = 0; k < ploidy; ++k) sum += exp(lnl[(size_t)gt[k] * R + r] - mx);
+        acc += mx + log(sum) - ln_ploidy;
+    }
+    partial[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) partial[threadIdx.x] += partial[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) out[g] = ploidy == 0 ? 0.0 : partial[0];
 }
 
 __global__ void k_fill_int(int* __restrict__ p, const long long n, const int v)

@@ -216,6 +216,8 @@ class COracle:
         L.oracle_model_align.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, mp, C.c_int, C.c_int, C.c_int,
                                          _i64p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                          _i64p, C.POINTER(C.c_double), C.c_char_p, C.c_int, _i32p]
+        L.oracle_genotype_likelihoods.restype = None
+        L.oracle_genotype_likelihoods.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_populate.restype = C.c_int
         L.oracle_populate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
 
@@ -343,3 +345,10 @@ class COracle:
                                          pos.ctypes.data_as(_i64p), len(pos), int(original_pos), int(use_mapping_quality), int(mapping_quality),
                                          int(mapq_cap), int(mapq_cap_trigger), C.byref(mp_), C.byref(lk), cig, cap, C.byref(ext))
         return st, mp_.value, lk.value, cig.value.decode(), ext.value
+
+    def genotype_likelihoods(self, lnl, genotypes):
+        lnl = np.ascontiguousarray(lnl, dtype=np.float64)
+        gt = np.ascontiguousarray(genotypes, dtype=np.int32)
+        out = np.empty(gt.shape[0], dtype=np.float64)
+        self.lib.oracle_genotype_likelihoods(lnl.ctypes.data, lnl.shape[0], lnl.shape[1], gt.ctypes.data, gt.shape[0], gt.shape[1], out.ctypes.data)
+        return out

@@ -576,3 +576,34 @@ int oracle_model_align(int band, const char* hap, int hap_len, const char* read,
     }
     return 0;
 }
+
+/* N1 — ConstantMixtureGenotypeLikelihoodModel::evaluate (core/models/genotype/constant_mixture_genotype_likelihood_model.cpp:30-140)
+ * over a [H][R] matrix: ln p(reads | genotype) = sum_r ( ln sum_{h in g} p(r | h) - ln ploidy ), sequential accumulation like
+ * std::accumulate / std::inner_product; homozygous → plain sum (:87-89), diploid → log_sum_exp(a, b) - ln 2 (:90-96),
+ * otherwise max + log(sum exp(x - max)) - ln ploidy (:131-140; the triploid special forms :98-129 are the same quantity). */
+void oracle_genotype_likelihoods(const double* lnl, int H, int R, const int32_t* genotypes, int G, int ploidy, double* out)
+{
+    (void)H;
+    for (int g = 0; g < G; ++g) {
+        const int32_t* gt = genotypes + (size_t)g * ploidy;
+        int homo = 1;
+        for (int k = 1; k < ploidy; ++k) if (gt[k] != gt[0]) homo = 0;
+        double acc = 0.0;
+        if (ploidy == 0) { out[g] = 0.0; continue; }
+        if (homo) {
+            for (int r = 0; r < R; ++r) acc += lnl[(size_t)gt[0] * R + r];
+        } else if (ploidy == 2) {
+            for (int r = 0; r < R; ++r) acc += log_sum_exp2(lnl[(size_t)gt[0] * R + r], lnl[(size_t)gt[1] * R + r]) - 0.693147180559945309417232121458176568;
+        } else {
+            const double ln_ploidy = log((double)ploidy);
+            for (int r = 0; r < R; ++r) {
+                double mx = lnl[(size_t)gt[0] * R + r];
+                for (int k = 1; k < ploidy; ++k) { const double v = lnl[(size_t)gt[k] * R + r]; if (v > mx) mx = v; }
+                double sum = 0.0;
+                for (int k = 0; k < ploidy; ++k) sum += exp(lnl[(size_t)gt[k] * R + r] - mx);
+                acc += mx + log(sum) - ln_ploidy;
+            }
+        }
+        out[g] = acc;
+    }
+}

@@ -86,6 +86,9 @@ int oracle_populate(int band, int H, const int64_t* hap_off, const char* seq,
                     int use_mapping_quality, int mapq_cap, int mapq_cap_trigger, int nuc_prior, int dp_only, int map_positions,
                     double* out, int32_t* status);
 
+/* N1: ConstantMixtureGenotypeLikelihoodModel::evaluate over a [H][R] matrix for G genotypes of one ploidy. */
+void oracle_genotype_likelihoods(const double* lnl, int H, int R, const int32_t* genotypes, int G, int ploidy, double* out);
+
 #ifdef __cplusplus
 }
 #endif

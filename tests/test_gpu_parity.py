@@ -234,3 +234,21 @@ def test_align_reads_matches_reference_align(engine, coracle):
             assert wst == 0 and st[j] == 0, (trial, j, wst, st[j])
             assert mp[j] == wmp and cig[j] == wcig, (trial, j, mp[j], wmp, cig[j], wcig)
             assert abs(lk[j] - wlk) <= REL_TOL * max(abs(wlk), 1e-300)
+
+
+def test_genotype_likelihood_reduction_on_the_resident_matrix(engine, coracle):
+    """N1: ConstantMixtureGenotypeLikelihoodModel::evaluate over the matrix populate left on the device."""
+    import itertools
+    import torch
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    haps, reads, band = synth.make_batch("C2", n_reads=4000, n_haps=12)
+    m_dev = engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=band), haps.to_device("cuda:0"), reads.to_device("cuda:0"))
+    m = m_dev.cpu().numpy()
+    for ploidy in (1, 2, 3, 4):
+        gts = np.array(list(itertools.combinations_with_replacement(range(12), ploidy))[:400], dtype=np.int32)
+        want = coracle.genotype_likelihoods(m, gts)
+        got_dev = engine.genotype_likelihoods(m_dev, gts)
+        got_host = engine.genotype_likelihoods(m, gts)
+        assert isinstance(got_dev, torch.Tensor)
+        for got in (got_dev.cpu().numpy(), got_host):
+            assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(np.abs(want), 1.0)), ploidy
