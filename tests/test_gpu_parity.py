@@ -252,3 +252,49 @@ def test_genotype_likelihood_reduction_on_the_resident_matrix(engine, coracle):
         assert isinstance(got_dev, torch.Tensor)
         for got in (got_dev.cpu().numpy(), got_host):
             assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(np.abs(want), 1.0)), ploidy
+
+
+def test_populate_edge_cases(engine, coracle):
+    """Single pair; qualities above 127 (the reference reinterprets them as int8, pair_hmm.hpp:372); reads longer than the
+    fast path's row budget; wide bands (generic int32 kernels); int32 scores requested."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from octopus_b200.batch import pack_haplotypes, pack_reads
+    rng = np.random.default_rng(99)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+
+    def region(hap_len, read_lens, n_haps, qmax):
+        seqs = [acgt[rng.integers(0, 4, hap_len)] for _ in range(n_haps)]
+        haps = pack_haplotypes(seqs, [np.roll(s, 1) for s in seqs], [rng.integers(1, 126, hap_len).astype(np.int8) for _ in seqs],
+                               [np.roll(s, -1) for s in seqs], [rng.integers(1, 126, hap_len).astype(np.int8) for _ in seqs],
+                               [rng.integers(3, 46, hap_len).astype(np.int8) for _ in seqs], [rng.integers(1, 11, hap_len).astype(np.int8) for _ in seqs])
+        bases, quals, begin = [], [], []
+        for L in read_lens:
+            p = int(rng.integers(0, hap_len - L + 1))
+            b = seqs[int(rng.integers(0, n_haps))][p:p + L].copy()
+            for _ in range(3):
+                b[rng.integers(0, L)] = acgt[rng.integers(0, 4)]
+            bases.append(b); quals.append(rng.integers(2, qmax + 1, L).astype(np.uint8)); begin.append(p)
+        return haps, pack_reads(bases, quals, begin=np.asarray(begin))
+
+    cases = [
+        (dict(hap_len=120, read_lens=[40], n_haps=1, qmax=41), dict(max_indel_error=8)),
+        (dict(hap_len=300, read_lens=[100, 100, 60, 151], n_haps=3, qmax=255), dict(max_indel_error=16)),
+        (dict(hap_len=2600, read_lens=[1500, 1200, 150], n_haps=2, qmax=41), dict(max_indel_error=16)),
+        (dict(hap_len=700, read_lens=[150, 100, 250], n_haps=3, qmax=41), dict(max_indel_error=64)),
+        (dict(hap_len=900, read_lens=[150, 100], n_haps=2, qmax=41), dict(max_indel_error=100)),
+        (dict(hap_len=300, read_lens=[100, 150, 150], n_haps=4, qmax=41), dict(max_indel_error=16, use_int_scores=True)),
+    ]
+    for rk, ck in cases:
+        haps, reads = region(**rk)
+        cfg = HaplotypeLikelihoodModel.Config(map_positions=False, **ck)
+        band = HaplotypeLikelihoodModel(cfg).pad_requirement()
+        for flanks in (None, (30, 25)):
+            rc, want, wst = coracle.populate(band, haps, reads, None, flanks)
+            got, st = engine.populate(cfg, haps, reads, flank_state=flanks, want_status=True)
+            ok = wst == 0
+            assert np.array_equal((st & 0xFFFF) == 2, (wst & 0xFFFF) == 2), (rk, ck)
+            good, worst = _close(got[ok], want[ok])
+            assert good, (rk, ck, flanks, worst)
+    with pytest.raises(Exception) as ei:
+        engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=300), *region(hap_len=120, read_lens=[40], n_haps=1, qmax=41))
+    assert "256" in str(ei.value)
