@@ -175,6 +175,16 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
                   const phmm_positions* positions, const phmm_flank_state* flank,
                   double* out, int32_t* status, int space);
 
+/* Paired / linked reads: HaplotypeLikelihoodArray::populate(TemplateMap) (haplotype_likelihood_array.cpp:105-199). Template t owns
+ * the reads [template_off[t], template_off[t+1]) and its value is the sum of its reads' values
+ * (HaplotypeLikelihoodModel::evaluate(AlignedTemplate), haplotype_likelihood_model.cpp:306-320). out is [H][n_templates];
+ * status (optional) stays per read, [H][R]. Everything else as phmm_populate. */
+int phmm_populate_templates(phmm_engine* e, const phmm_config* cfg,
+                            const phmm_haplotypes* haps, const phmm_reads* reads,
+                            const int64_t* template_off, int32_t n_templates,
+                            const phmm_positions* positions, const phmm_flank_state* flank,
+                            double* out, int32_t* status, int space);
+
 /* Consumer of the matrix ("next" row N1): ConstantMixtureGenotypeLikelihoodModel::evaluate for G genotypes of one ploidy
  * (core/models/genotype/constant_mixture_genotype_likelihood_model.cpp:30-140) over a [H][R] matrix in `space`:
  *   out[g] = sum_r ( log_sum_exp_{h in genotype g} lnl[h*R + r] - ln ploidy ),   genotypes[g*ploidy + k] = haplotype index.

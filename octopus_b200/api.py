@@ -183,6 +183,21 @@ class PairHMMEngine:
         return out
 
     # -- batch boundary ----------------------------------------------------------------------------------------
+    def populate_templates(self, config, haps: HaplotypeBlock, reads: ReadBlock, template_off, flank_state=None):
+        """HaplotypeLikelihoodArray::populate(TemplateMap): host blocks; template t = reads [template_off[t], template_off[t+1]).
+        Returns the (H, T) matrix: each entry the sum of the template's reads' ln-likelihoods."""
+        assert not haps.on_device and not reads.on_device
+        toff = np.ascontiguousarray(template_off, dtype=np.int64)
+        T = len(toff) - 1
+        hs, rs, cfg = haps.c_struct(), reads.c_struct(), config.c_struct()
+        fstruct = None if flank_state is None else _lib.FlankState(1, int(flank_state[0]), int(flank_state[1]))
+        out = np.empty((haps.n, T), dtype=np.float64)
+        rc = self._lib.phmm_populate_templates(self._h, C.byref(cfg), C.byref(hs), C.byref(rs), toff.ctypes.data, T, None,
+                                               C.byref(fstruct) if fstruct is not None else None, out.ctypes.data, None, _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+        return out
+
     def populate(self, config, haps: HaplotypeBlock, reads: ReadBlock, positions=None, flank_state=None, out=None,
                  want_status=False):
         """Returns the (H, R) matrix of ln-likelihoods (numpy float64, or a torch CUDA tensor for device-resident blocks).

@@ -5,6 +5,8 @@
 #include "phmm_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -58,7 +60,7 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, bp;
     DBuf tasks_lane, tasks_generic, works, scores;
-    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, gcnt;
+    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, gcnt, sched, sorted;
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
     // host-space calls on large batches are pipelined over two sub-engines (own stream + buffers each), driven by two host
@@ -113,7 +115,7 @@ int fetch_offsets(phmm_engine* e, const int64_t* off, int n, int space, std::vec
 }
 
 // Upload (or alias) the batch and run the preparation kernels: column tables, row half-words, read info.
-int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* reads, int space, Staged& s)
+int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* reads, int space, Staged& s, bool need_info_host = true)
 {
     if (!haps || !reads || haps->n <= 0 || reads->n <= 0 || !haps->off || !reads->off) {
         e->err = "empty or null haplotype / read block";
@@ -169,9 +171,11 @@ int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* r
     CU(cudaGetLastError());
     hp.tab_f = e->tab_f.as<ColEntry>(); hp.tab_r = e->tab_r.as<ColEntry>();
     rd.rowhalf = e->rowhalf.as<uint16_t>(); rd.info = e->info.as<int2>();
-    // read info is needed on the host for scheduling (8 bytes per read)
-    e->info_host.resize(rd.n);
-    CU(cudaMemcpyAsync(e->info_host.data(), e->info.p, (size_t)rd.n * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+    // read info is needed on the host where the host schedules (8 bytes per read); phmm_populate schedules on the device
+    if (need_info_host) {
+        e->info_host.resize(rd.n);
+        CU(cudaMemcpyAsync(e->info_host.data(), e->info.p, (size_t)rd.n * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+    }
     int flags_host[1] = {0};
     CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -252,7 +256,7 @@ void phmm_destroy(phmm_engine* e)
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
                    &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
-                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->gcnt};
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->gcnt, &e->sched, &e->sorted};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -548,9 +552,15 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
 static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                          const phmm_haplotypes* haps, const phmm_reads* reads,
                          const phmm_positions* positions, const phmm_flank_state* flank,
-                         double* out, int32_t* status, int space, long long out_pitch)
+                         double* out, int32_t* status, int space, long long out_pitch,
+                         const int64_t* template_off = nullptr, int n_templates = 0)
 {
     if (!e) return PHMM_ERR_INVALID;
+    static const bool trace = std::getenv("PHMM_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) std::fprintf(stderr, "[phmm] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
     if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
     if (!cfg || !out) { e->err = "null config / output"; return PHMM_ERR_INVALID; }
@@ -559,10 +569,11 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     if (cfg->nuc_prior < 0 || cfg->nuc_prior > 127) { e->err = "nuc_prior outside [0,127]"; return PHMM_ERR_INVALID; }
     if (!reads || !reads->mapq || !reads->reverse) { e->err = "reads->mapq / reads->reverse required"; return PHMM_ERR_INVALID; }
     Staged s;
-    int rc = stage_batch(e, haps, reads, space, s);
+    int rc = stage_batch(e, haps, reads, space, s, false);
     if (rc != PHMM_OK) return rc;
     const int H = s.hp.n, R = s.rd.n;
     const long long HR = (long long)H * R;
+    lap("staged+info");
 
     PopParams p {};
     p.hp = s.hp; p.rd = s.rd;
@@ -608,41 +619,38 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     for (int h = 0; h < H; ++h) max_hap_len = std::max(max_hap_len, s.hap_off_host[h + 1] - s.hap_off_host[h]);
     // the fast path packs (haplotype, window offset) into 16 + 16 bits
     const bool fast_ok = band <= 32 && !cfg->use_int_scores && H <= 65535 && max_hap_len <= 65535;
-    std::vector<int> generic_reads, pairs;
     // lane groups per warp of the fast kernel: with few haplotypes a read has few DP tasks, so several read pairs share a warp
-    const size_t groups = H >= 17 ? 1 : (H >= 9 ? 2 : 4);
-    int Lmax_fast = 1, Lmax_all = 1;
+    const int groups = H >= 17 ? 1 : (H >= 9 ? 2 : 4);
+    // device-side scheduling: length buckets → equal-length read pairs (padded to multiples of `groups` per bucket) + generic list
+    const size_t pairs_cap = (size_t)R / 2 + (size_t)kLenBins * groups + 8;
+    SchedTotals tot {};
     {
-        std::vector<int> order;
-        order.reserve(R);
-        for (int r = 0; r < R; ++r) {
-            const int2 inf = e->info_host[r];
-            Lmax_all = std::max(Lmax_all, inf.x);
-            if (inf.x < 1) { e->err = "empty read"; return PHMM_ERR_INVALID; }
-            if (fast_ok && (inf.y & kReadGenericMask) == 0) { order.push_back(r); Lmax_fast = std::max(Lmax_fast, inf.x); }
-            else generic_reads.push_back(r);
-        }
-        // counting sort by length keeps the pairing O(R)
-        std::vector<int> count((size_t)Lmax_fast + 2, 0);
-        for (int r : order) ++count[e->info_host[r].x + 1];
-        for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
-        std::vector<int> sorted(order.size());
-        for (int r : order) sorted[count[e->info_host[r].x]++] = r;
-        pairs.reserve(sorted.size() + 2 * groups + 2);
-        int cur_len = -1;
-        for (size_t i = 0; i < sorted.size();) {
-            const int r0 = sorted[i];
-            const int len = e->info_host[r0].x;
-            if (len != cur_len) {   // a warp's G pairs must share one read length: pad to a multiple of G at every length boundary
-                while ((pairs.size() / 2) % groups) { pairs.push_back(-1); pairs.push_back(-1); }
-                cur_len = len;
-            }
-            if (i + 1 < sorted.size() && e->info_host[sorted[i + 1]].x == len) { pairs.push_back(r0); pairs.push_back(sorted[i + 1]); i += 2; }
-            else { pairs.push_back(r0); pairs.push_back(-1); i += 1; }
-        }
-        while ((pairs.size() / 2) % groups) { pairs.push_back(-1); pairs.push_back(-1); }
+        CU(e->sched.ensure((size_t)(4 * (kLenBins + 1) + 16) * sizeof(int) + sizeof(SchedTotals)));
+        CU(e->sorted.ensure((size_t)R * sizeof(int)));
+        CU(e->pairs.ensure(2 * pairs_cap * sizeof(int)));
+        CU(e->generic_reads.ensure((size_t)R * sizeof(int)));
+        int* base = e->sched.as<int>();
+        int* hist = base, *read_start = base + (kLenBins + 1), *pair_start = base + 2 * (kLenBins + 1), *cursors = base + 3 * (kLenBins + 1);
+        int* misc = base + 4 * (kLenBins + 1);          // [0] n_generic, [1] lmax_all, [2] bad
+        SchedTotals* d_tot = (SchedTotals*)(misc + 16);
+        CU(cudaMemsetAsync(base, 0, (size_t)(4 * (kLenBins + 1) + 16) * sizeof(int), e->stream));
+        k_sched_hist<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, fast_ok ? 1 : 0, hist, e->generic_reads.as<int>(), misc + 0, misc + 1, misc + 2);
+        LAUNCHED();
+        k_sched_scan<<<1, kLenBins, 0, e->stream>>>(hist, groups, band, H, read_start, pair_start, cursors, misc + 0, misc + 1, misc + 2, s.rd.info,
+                                                    e->generic_reads.as<int>(), d_tot);
+        LAUNCHED();
+        k_sched_scatter<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, fast_ok ? 1 : 0, read_start, cursors, e->sorted.as<int>());
+        LAUNCHED();
+        k_sched_pairs<<<(unsigned)((pairs_cap + 255) / 256), 256, 0, e->stream>>>(d_tot, read_start, pair_start, e->sorted.as<int>(), e->pairs.as<int>());
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&tot, d_tot, sizeof(SchedTotals), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (tot.bad) { e->err = "empty read"; return PHMM_ERR_INVALID; }
     }
-    const int n_pairs = (int)(pairs.size() / 2), n_generic = (int)generic_reads.size();
+    const int Lmax_fast = tot.lmax_fast, Lmax_all = tot.lmax_all;
+    const int n_pairs = tot.n_pairs, n_generic = tot.n_generic;
+    lap("scheduled");
 
     CU(e->best.ensure((size_t)HR * sizeof(int)));
     CU(e->status.ensure((size_t)HR * sizeof(int)));
@@ -657,14 +665,6 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     int* counters = e->counters.as<int>();
     p.pair_cursor = counters + 0;
     p.slow_count = counters + 1;
-    if (n_pairs) {
-        CU(e->pairs.ensure(pairs.size() * sizeof(int)));
-        CU(cudaMemcpyAsync(e->pairs.p, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    }
-    if (n_generic) {
-        CU(e->generic_reads.ensure(generic_reads.size() * sizeof(int)));
-        CU(cudaMemcpyAsync(e->generic_reads.p, generic_reads.data(), generic_reads.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    }
 
     // near-flank (traceback) queue, processed tile by tile so that its worst case fits the budget
     const long long slow_budget = 8LL << 20;   // entries (16 bytes each)
@@ -749,7 +749,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 k_populate_generic<64, true><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p);
                 LAUNCHED();
             }
-            const int want_blocks = (int)((np / (int)groups + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
+            p.units_per_pair = std::max(1, (p.fcap + (32 / groups) * kRoundsPerUnit - 1) / ((32 / groups) * kRoundsPerUnit));
+            const int want_blocks = (int)std::min<long long>(1LL << 30, ((long long)(np / groups) * p.units_per_pair + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
             const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
             while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); }
             CU(cudaEventRecord(e->tile_events[2 * n_timed], e->stream));
@@ -802,12 +803,28 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
 
     CU(e->out.ensure((size_t)HR * sizeof(double)));
-    double* d_out = space == PHMM_SPACE_DEVICE ? out : e->out.as<double>();
+    double* d_out = (space == PHMM_SPACE_DEVICE && !template_off) ? out : e->out.as<double>();
     k_epilogue<<<(unsigned)((HR + 255) / 256), 256, 0, e->stream>>>(p.best, p.status, s.rd.mapq, H, R, cfg->use_mapping_quality,
                                                                     cfg->mapping_quality_cap, cfg->mapping_quality_cap_trigger, d_out);
     LAUNCHED();
     CU(cudaGetLastError());
-    if (space == PHMM_SPACE_HOST) {
+    if (template_off) {
+        // paired / linked reads: one value per (haplotype, template)
+        const long long* d_toff;
+        if ((rc = stage(e, e->tasks_lane, (const long long*)template_off, (size_t)n_templates + 1, space, &d_toff))) return rc;
+        const long long HT = (long long)H * n_templates;
+        CU(e->tasks_generic.ensure((size_t)HT * sizeof(double)));
+        double* d_tout = space == PHMM_SPACE_DEVICE ? out : e->tasks_generic.as<double>();
+        k_template_sum<<<(unsigned)((HT + 255) / 256), 256, 0, e->stream>>>(d_out, H, R, d_toff, n_templates, d_tout);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        if (space == PHMM_SPACE_HOST) {
+            CU(cudaMemcpyAsync(out, d_tout, (size_t)HT * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            if (status) CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        } else if (status) {
+            CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+        }
+    } else if (space == PHMM_SPACE_HOST) {
         if (out_pitch == 0 || out_pitch == R) {
             CU(cudaMemcpyAsync(out, d_out, (size_t)HR * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
             if (status) CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -820,7 +837,9 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
     int flags_host[1] = {0};
     CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    lap("enqueued");
     CU(cudaStreamSynchronize(e->stream));
+    lap("done");
     if (n_timed) {
         double total = 0.0;
         for (size_t t = 0; t < n_timed; ++t) { float ms = 0.f; if (cudaEventElapsedTime(&ms, e->tile_events[2 * t], e->tile_events[2 * t + 1]) == cudaSuccess) total += ms; }
@@ -830,14 +849,25 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_dp_ms = ms;
     }
     // GCUPS numerator when every pair runs exactly one DP (benchmark mode); otherwise an upper bound on DP work
-    {
-        int64_t cells = 0;
-        for (int r = 0; r < R; ++r) cells += 2LL * (e->info_host[r].x + band) * band;
-        e->last_dp_cells = cells * H;
-    }
+    e->last_dp_cells = tot.cells;
     if (flags_host[0] & (4 | 8)) { e->err = "internal task queue overflow"; return PHMM_ERR_NOMEM; }
     if (flags_host[0] & 2) { e->err = "Haplotype is too short for alignment"; return PHMM_ERR_SHORT_HAPLOTYPE; }
     return PHMM_OK;
+}
+
+int phmm_populate_templates(phmm_engine* e, const phmm_config* cfg,
+                            const phmm_haplotypes* haps, const phmm_reads* reads,
+                            const int64_t* template_off, int32_t n_templates,
+                            const phmm_positions* positions, const phmm_flank_state* flank,
+                            double* out, int32_t* status, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    if (!template_off || n_templates <= 0 || !reads) { e->err = "null / empty template offsets"; return PHMM_ERR_INVALID; }
+    if (space == PHMM_SPACE_HOST) {
+        if (template_off[0] != 0 || template_off[n_templates] != reads->n) { e->err = "template offsets must cover the reads exactly"; return PHMM_ERR_INVALID; }
+        for (int t = 0; t < n_templates; ++t) if (template_off[t + 1] < template_off[t]) { e->err = "template offsets must be non-decreasing"; return PHMM_ERR_INVALID; }
+    }
+    return populate_impl(e, cfg, haps, reads, positions, flank, out, status, space, 0, template_off, n_templates);
 }
 
 int phmm_populate(phmm_engine* e, const phmm_config* cfg,

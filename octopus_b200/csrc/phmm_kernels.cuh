@@ -86,6 +86,100 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
     if (lane == 0) info[r] = make_int2(L, flags);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-side scheduling of the fast path: bucket the eligible reads by length (counting sort), pair reads of equal
+// length, pad every length bucket to a multiple of G pairs (a warp's G pairs share one read length). Replaces a host
+// pass over all reads; the host only reads back a handful of totals.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLenBins = kFastMaxReadLen + 1;
+struct SchedTotals { int n_pairs, n_generic, lmax_fast, lmax_all, n_eligible, bad; long long cells; };
+
+__global__ void k_sched_hist(const int R, const int2* __restrict__ info, const int fast_ok, int* __restrict__ hist,
+                             int* __restrict__ generic, int* __restrict__ n_generic, int* __restrict__ lmax_all, int* __restrict__ bad)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int2 inf = info[r];
+    if (inf.x < 1) atomicExch(bad, 1);
+    atomicMax(lmax_all, inf.x);
+    if (fast_ok && (inf.y & kReadGenericMask) == 0) atomicAdd(&hist[inf.x], 1);
+    else generic[atomicAdd(n_generic, 1)] = r;
+}
+
+// one block of kLenBins threads: exclusive scans of the per-length read counts and padded pair counts
+__global__ void __launch_bounds__(kLenBins)
+k_sched_scan(const int* __restrict__ hist, const int G, const int band, const int H, int* __restrict__ read_start, int* __restrict__ pair_start,
+             int* __restrict__ cursors, const int* __restrict__ n_generic, const int* __restrict__ lmax_all, const int* __restrict__ bad,
+             const int2* __restrict__ info,
+             const int* __restrict__ generic, SchedTotals* __restrict__ tot)
+{
+    __shared__ int s_reads[kLenBins], s_pairs[kLenBins];
+    __shared__ unsigned long long s_cells;
+    const int l = threadIdx.x;
+    const int c = hist[l];
+    const int pairs = ((c + 1) / 2 + G - 1) / G * G;
+    s_reads[l] = c; s_pairs[l] = pairs;
+    if (l == 0) s_cells = 0ull;
+    __syncthreads();
+    // Hillis-Steele inclusive scans (1024 elements)
+    for (int d = 1; d < kLenBins; d <<= 1) {
+        const int a = l >= d ? s_reads[l - d] : 0, b = l >= d ? s_pairs[l - d] : 0;
+        __syncthreads();
+        s_reads[l] += a; s_pairs[l] += b;
+        __syncthreads();
+    }
+    read_start[l] = s_reads[l] - c;
+    pair_start[l] = s_pairs[l] - pairs;
+    cursors[l] = 0;
+    if (c) atomicAdd(&s_cells, (unsigned long long)c * (unsigned long long)(2LL * (l + band) * band));
+    __syncthreads();
+    // generic reads contribute to the cell count too
+    const int ng = *n_generic;
+    unsigned long long mine = 0;
+    for (int i = l; i < ng; i += kLenBins) mine += (unsigned long long)(2LL * (info[generic[i]].x + band) * band);
+    if (mine) atomicAdd(&s_cells, mine);
+    int lmax = c ? l : 0;
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    __shared__ int s_lmax[kLenBins / 32];
+    if ((l & 31) == 0) s_lmax[l >> 5] = lmax;
+    __syncthreads();
+    if (l == 0) {
+        int m = 0;
+        for (int i = 0; i < kLenBins / 32; ++i) m = max(m, s_lmax[i]);
+        tot->n_pairs = s_pairs[kLenBins - 1];
+        tot->n_eligible = s_reads[kLenBins - 1];
+        tot->n_generic = ng;
+        tot->lmax_fast = max(m, 1);
+        tot->lmax_all = max(*lmax_all, 1);
+        tot->bad = *bad;
+        tot->cells = (long long)s_cells * H;
+    }
+    if (l == kLenBins - 1) { read_start[kLenBins] = s_reads[l]; pair_start[kLenBins] = s_pairs[l]; }
+}
+
+__global__ void k_sched_scatter(const int R, const int2* __restrict__ info, const int fast_ok, const int* __restrict__ read_start,
+                                int* __restrict__ cursors, int* __restrict__ sorted)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int2 inf = info[r];
+    if (fast_ok && (inf.y & kReadGenericMask) == 0) sorted[read_start[inf.x] + atomicAdd(&cursors[inf.x], 1)] = r;
+}
+
+// pair slot j → (read, read | -1) or (-1, -1) padding
+__global__ void k_sched_pairs(const SchedTotals* __restrict__ tot, const int* __restrict__ read_start, const int* __restrict__ pair_start,
+                              const int* __restrict__ sorted, int* __restrict__ pairs)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= tot->n_pairs) return;
+    int lo = 0, hi = kLenBins;                   // largest bin l with pair_start[l] <= j
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pair_start[mid] <= j) lo = mid; else hi = mid; }
+    const int local = j - pair_start[lo], first = read_start[lo], cnt = read_start[lo + 1] - first;
+    const int a = 2 * local, b = 2 * local + 1;
+    pairs[2 * j] = a < cnt ? sorted[first + a] : -1;
+    pairs[2 * j + 1] = b < cnt ? sorted[first + b] : -1;
+}
+
 // Cooperative fill of one warp's shared row words for the read pair (r0, r1); r1 < 0 → second half padded.
 __device__ __forceinline__ void fill_rows(RowEntry* rows, const DevReads& rd, const int r0, const int r1, const int L, const int lane)
 {
@@ -176,6 +270,7 @@ struct PopParams {
     uint32_t* gtasks;
     int* gcnt;
     int* flank_cursor;
+    int units_per_pair;         // fast kernel: a read pair's task lists are cut into this many work units of kRoundsPerUnit rounds
     int band, nuc_prior;
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
     int use_flanks;             // flank_state present && config.use_flank_state
@@ -217,6 +312,7 @@ __device__ __forceinline__ void push_slow(const PopParams& p, const int r, const
 }
 
 constexpr int kQueueCap = 64;
+constexpr int kRoundsPerUnit = 8;   // dp_pair rounds per work unit of the fast kernel (bounds the tail imbalance of long task lists)
 constexpr int kMaxMapped = 10;    // HaplotypeLikelihoodArray::maxMappingPositions (haplotype_likelihood_array.hpp:104)
 constexpr int kKmer = 6;          // mapperKmerSize (:103)
 constexpr int kKmerBins = 4096;
@@ -338,9 +434,10 @@ k_populate_fast(const PopParams p)
     const int R = p.rd.n;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     for (;;) {
-        int jb = 0;
-        if (lane == 0) jb = atomicAdd(p.pair_cursor, G);
-        jb = __shfl_sync(0xffffffffu, jb, 0);
+        int u = 0;
+        if (lane == 0) u = atomicAdd(p.pair_cursor, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        const int jb = (u / p.units_per_pair) * G, part = u % p.units_per_pair;
         if (jb >= p.n_pairs) break;
         const int j = jb + grp;
         const int r0 = j < p.n_pairs ? p.pair_reads[2 * j] : -1;
@@ -349,7 +446,8 @@ k_populate_fast(const PopParams p)
         int nmax = max(n0, n1), L = r0 >= 0 ? p.rd.info[r0].x : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); L = max(L, __shfl_xor_sync(0xffffffffu, L, o)); }
-        if (nmax == 0) continue;
+        const int c_begin = part * kRoundsPerUnit * LG, c_end = min(nmax, c_begin + kRoundsPerUnit * LG);
+        if (c_begin >= nmax) continue;
         __syncwarp();
         if (r0 >= 0) {   // cooperative fill by the group's lanes
             const uint16_t* h0 = p.rd.rowhalf + p.rd.off[r0];
@@ -363,7 +461,7 @@ k_populate_fast(const PopParams p)
         const ColEntry* tab1 = (rb >= 0 && p.rd.reverse[rb]) ? p.hp.tab_r : p.hp.tab_f;
         const uint32_t* q0 = p.ftasks + (size_t)(2 * (size_t)max(j, 0)) * p.fcap;
         const uint32_t* q1 = q0 + p.fcap;
-        for (int c = 0; c < nmax; c += LG) {
+        for (int c = c_begin; c < c_end; c += LG) {
             const bool v0 = c + gl < n0, v1 = c + gl < n1;
             // idle half-lanes replay a valid task (result discarded): of their own group if it has one, else of any lane
             const bool have = (n0 > 0) || (n1 > 0);
@@ -643,6 +741,19 @@ __global__ void k_align_reads(const AlignParams p)
             p.likelihood[i] = -1.7976931348623157e308;
         }
     }
+}
+
+// HaplotypeLikelihoodModel::evaluate(AlignedTemplate) (haplotype_likelihood_model.cpp:306-320): out[h][t] = sum over the
+// template's reads, accumulated in read order like std::accumulate.
+__global__ void k_template_sum(const double* __restrict__ lnl, const int H, const int R, const long long* __restrict__ toff, const int T,
+                               double* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * T) return;
+    const int h = (int)(i / T), t = (int)(i % T);
+    double acc = 0.0;
+    for (long long r = toff[t]; r < toff[t + 1]; ++r) acc += lnl[(size_t)h * R + r];
+    out[i] = acc;
 }
 
 // N1: ConstantMixtureGenotypeLikelihoodModel::evaluate on the resident [H][R] matrix

@@ -298,3 +298,23 @@ def test_populate_edge_cases(engine, coracle):
     with pytest.raises(Exception) as ei:
         engine.populate(HaplotypeLikelihoodModel.Config(max_indel_error=300), *region(hap_len=120, read_lens=[40], n_haps=1, qmax=41))
     assert "256" in str(ei.value)
+
+
+def test_populate_templates_sums_the_reads_of_each_template(engine, coracle):
+    """populate(TemplateMap): the value of a template is the sum of its reads' values, in read order."""
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    haps, reads, band = synth.make_batch("C2", n_reads=900, n_haps=10)
+    rng = np.random.default_rng(8)
+    sizes = []
+    while sum(sizes) < reads.n:
+        sizes.append(min(int(rng.choice([1, 2, 2, 2, 3])), reads.n - sum(sizes)))
+    toff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band)
+    got = engine.populate_templates(cfg, haps, reads, toff, flank_state=(50, 40))
+    rc, per_read, _ = coracle.populate(band, haps, reads, None, (50, 40), map_positions=True)
+    want = np.zeros((haps.n, len(sizes)))
+    for t in range(len(sizes)):
+        for r in range(toff[t], toff[t + 1]):
+            want[:, t] = want[:, t] + per_read[:, r]
+    ok, worst = _close(got, want)
+    assert rc == 0 and ok, worst
