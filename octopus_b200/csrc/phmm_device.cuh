@@ -251,9 +251,15 @@ constexpr uint32_t kF32Valid = 0x80u, kF32TypeD = 0x40u;
 
 PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-// rows: shared-memory row entries built with make_row_entry(half, 0): .x low nibble = base code, .y low 16 bits = qual.
+// Row entries of this kernel (one read, not a pair): .x = PRMT selector picking the cap byte of the read base into byte 0
+// and zeros elsewhere (code | 0x4440), .y = base quality.
+PHMM_HD RowEntry make_row_entry32(uint32_t half) { RowEntry r; r.x = (half & 3u) | 0x4440u; r.y = half >> 8; return r; }
+PHMM_HD RowEntry pad_row_entry32() { RowEntry r; r.x = 0x4440u; r.y = 0u; return r; }
+
+// rows: shared-memory row entries (make_row_entry32), rows[L] = pad_row_entry32().
 // tab : column table of the window. xl / xr: first non-flank column and first right-flank column (0 <= xl < xr <= W);
-// xl == 0 / xr == W mean "no left / right flank". Outputs the integer score, the in-flank penalty and the in-flank read bases.
+// xl == 0 / xr > W mean "no left / right flank". Outputs the integer score, the in-flank penalty and the in-flank read bases.
+// Column bodies as in dp_pair: steady / prologue (jump table) / epilogue (early exit after the row-L cell) / general.
 template <int BAND>
 PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ tab, const int nuc_prior,
                         const int xl, const int xr, int* score_out, int* flank_out, int* mask_out)
@@ -274,14 +280,17 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
 #define PHMM_FCELL(k, CAPTURE)                                                                          \
     {                                                                                                   \
         const RowEntry w = rp[-(k)];                                                                    \
-        const uint32_t sub = umin32(w.y & 0xFFu, prmt(caps, 0u, (w.x & 3u) | 0x4440u));                 \
+        const uint32_t sub = umin32(w.y, prmt(caps, 0u, w.x));                                          \
         const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                              \
-        const uint32_t S = umin32(umin32(m, i_run), d);                                                 \
+        const uint32_t mi = umin32(m, i_run);                                                           \
+        const uint32_t S = umin32(mi, d);                                                               \
         CAPTURE                                                                                         \
         M[(k) < K ? (k) : 0] = (S & ~kF32LabelMask) + (sub << kF32ScoreShift);                          \
-        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = (umin32(d + geS, umin32(m, i_run) + goS) & ~kF32LabelMask) | kF32LabD; \
-        i_run = (umin32(i_run + gepS, m + gopS) & ~kF32LabelMask) | kF32LabI;                           \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = umin32(d + geS, mi + goS) | kF32LabD;         \
+        i_run = umin32(i_run + gepS, m + gopS) | kF32LabI;                                              \
     }
+#define PHMM_FCASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_FCELL(k, )
+#define PHMM_FCASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
 
     for (int x = 0; x <= W; ++x) {
         const int xn = (x + 1 < W) ? x + 1 : W - 1;
@@ -291,22 +300,32 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
         const uint32_t gopS = go_prev + nucS, gepS = ge_prev + nucS;
         const RowEntry* rp = rows + x;
         uint32_t i_run = kF32Inf | kF32LabI;
-        if (x >= K && x < L) {   // steady state (column L holds the first end cell and takes the general body)
+        if (x >= K) {
+            if (x < L) {
 #pragma unroll
-            for (int k = K - 1; k >= 0; --k) PHMM_FCELL(k, )
-        } else {
-            const int klo = x - L;
-            if (x < K) i_run = (x & 1) ? (gopS | kF32LabI) : (kF32Inf | kF32LabI);   // i(x, 1) out of the free-start cell
+                for (int k = K - 1; k >= 0; --k) PHMM_FCELL(k, )
+            } else {
+                // epilogue: the row-L cell (k == x - L) keeps the labelled S — the end-cell choice compares it with its label
+                const int klo = x - L;
 #pragma unroll
-            for (int k = K - 1; k >= 0; --k) {
-                if (k == x) {
-                    M[k] = umin32(w0.y & 0xFFu, prmt(caps, 0u, (w0.x & 3u) | 0x4440u)) << kF32ScoreShift;   // m(x+1, 1) = sub(x, 0)
-                } else if (k < x && k >= klo) {
-                    // row L (k == klo): keep the labelled S — the end-cell choice compares it with its label (unlike the
-                    // score-only kernel, whose captured M[k] has the label cleared)
+                for (int k = K - 1; k >= 0; --k) {
                     PHMM_FCELL(k, if (k == klo) end_s[k] = S;)
+                    if (k == klo) break;
                 }
             }
+        } else {
+            const uint32_t sub0 = umin32(w0.y, prmt(caps, 0u, w0.x)) << kF32ScoreShift;   // m(x+1, 1) = sub(x, 0)
+            i_run = (x & 1) ? (gopS | kF32LabI) : (kF32Inf | kF32LabI);                    // i(x, 1) out of the free-start cell
+            if (x < L) {
+                switch (x) { PHMM_REP64(PHMM_FCASE_PROLOGUE) default: break; }
+            } else {
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    if (k < x && k >= klo) PHMM_FCELL(k, if (k == klo) end_s[k] = S;)
+                }
+            }
+            switch (x) { PHMM_REP64(PHMM_FCASE_ROW0) default: break; }
         }
         // the arrivals now held in M[k] / D[k] belong to column x+1: at the two flank boundaries record them and stamp
         // the crossing (diagonal, arrival type) into their payload
@@ -326,6 +345,8 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
         go_prev = goS; ge_prev = geS; e = nx;
     }
 #undef PHMM_FCELL
+#undef PHMM_FCASE_PROLOGUE
+#undef PHMM_FCASE_ROW0
     // end row: minimum over (score, label), earliest end on ties (simd_pair_hmm.hpp:285-291, 309-315 compare the labelled values)
     uint32_t best = end_s[0];
     int kbest = 0;

@@ -507,7 +507,12 @@ k_populate_flank(const PopParams p)
         if (n == 0) continue;
         const int L = p.rd.info[r].x;
         __syncwarp();
-        fill_rows(rows, p.rd, r, -1, L, lane);
+        {
+            const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
+            for (int y = lane; y < L; y += 32) rows[y] = make_row_entry32(hr[y]);
+            if (lane == 0) rows[L] = pad_row_entry32();
+            __syncwarp();
+        }
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
         const uint32_t* q = p.gtasks + (size_t)li * p.fcap;
         const int W = L + K - 1;
@@ -555,6 +560,13 @@ __global__ void k_populate_generic(const PopParams p)
     else if (p.kcnt) { npos = p.kcnt[(size_t)li * H + h]; pp = p.kpos + ((size_t)li * H + h) * kMaxMapped; }
     EnumState st {false, false};
     int best = kBestInf;
+    // DP candidates are collected first and queued after the walk: a shortcut value of 0 (exact match at some candidate
+    // position) cannot be improved on — every candidate's penalty is >= 0 and the pair's result is their minimum — so the
+    // pair's DPs are skipped without changing the result.
+    constexpr int kMaxPending = 12;
+    int pend_a[kMaxPending];
+    unsigned pend_flank = 0u;
+    int n_pend = 0;
     for (int c = 0; c < npos + 2; ++c) {
         int pos;
         const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
@@ -563,7 +575,16 @@ __global__ void k_populate_generic(const PopParams p)
         int v;
         const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, p.use_flanks != 0, p.lhs_flank, p.rhs_flank, &v);
         if (kind == CAND_VALUE) best = min(best, v);
-        else if (kind == CAND_DP) {
+        else if ((kind == CAND_DP || kind == CAND_DP_FLANK) && n_pend < kMaxPending) {
+            pend_a[n_pend] = v;
+            if (kind == CAND_DP_FLANK) pend_flank |= 1u << n_pend;
+            ++n_pend;
+        }
+    }
+    if (best == 0) n_pend = 0;
+    for (int i2 = 0; i2 < n_pend; ++i2) {
+        const int v = pend_a[i2];
+        if (!((pend_flank >> i2) & 1u)) {
             if (FASTQ) {
                 const int slot = atomicAdd(p.fcnt + li, 1);
                 if (slot < p.fcap) p.ftasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
@@ -572,7 +593,7 @@ __global__ void k_populate_generic(const PopParams p)
                 const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
                 best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
             }
-        } else if (kind == CAND_DP_FLANK) {
+        } else {
             if (FASTQ && !(p.rd.info[r].y & kReadUnsafeFlank32)) {
                 const int slot = atomicAdd(p.gcnt + li, 1);
                 if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);

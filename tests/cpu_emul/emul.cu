@@ -115,9 +115,9 @@ extern "C" int emul_dp_flank32(int band, int L, const char* read, const uint8_t*
     for (int y = 0; y < L; ++y) {
         const int c = base_code(read[y]);
         if (c < 0) return -1;
-        rows[y] = make_row_entry((uint32_t)c | ((uint32_t)q[y] << 8), 0u);
+        rows[y] = make_row_entry32((uint32_t)c | ((uint32_t)q[y] << 8));
     }
-    rows[L] = pad_row_entry();
+    rows[L] = pad_row_entry32();
     std::vector<ColEntry> t(W);
     for (int x = 0; x < W; ++x) t[x] = make_col_entry(truth[x], mask[x], prior[x], go[x], ge[x]);
     int xl = lhs_flank, xr = W - rhs_flank;

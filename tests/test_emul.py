@@ -134,3 +134,34 @@ def test_pair_evaluation_logic_matches_oracle(emul, coracle):
             assert ext.value == e
             n_short += 1
     assert n_short > 0
+
+
+def test_flank_payload_dp_matches_traceback_flank_replay(emul, coracle):
+    """dp_flank32 (no back-pointers: crossing cells carried as payload) == traceback + calculate_flank_score of the oracle:
+    score, in-flank penalty and in-flank read bases, for every flank geometry incl. overlapping / empty flanks."""
+    emul.emul_dp_flank32.argtypes = [C.c_int, C.c_int] + [vp] * 7 + [C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    rng = np.random.default_rng(21)
+    for it in range(1500):
+        band = int(rng.choice([8, 16, 32]))
+        L = int(rng.integers(1, 160))
+        nuc = int(rng.integers(0, 5))
+        c = random_alignment_case(rng, band, L)
+        W = len(c["truth"])
+        mode = it % 4
+        if mode == 0:
+            lhs, rhs = int(rng.integers(0, W // 2 + 1)), int(rng.integers(0, W // 2 + 1))
+        elif mode == 1:
+            lhs, rhs = int(rng.integers(0, W + 1)), 0
+        elif mode == 2:
+            lhs, rhs = 0, int(rng.integers(0, W + 1))
+        else:
+            lhs, rhs = int(rng.integers(0, W + 1)), int(rng.integers(0, W + 1))
+        sc, fl, ms = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = emul.emul_dp_flank32(band, L, P(c["read"]), P(c["quals"]), P(c["truth"]), P(c["snv_mask"]), P(c["snv_prior"]), P(c["gap_open"]),
+                                  P(c["gap_extend"]), nuc, lhs, rhs, C.byref(sc), C.byref(fl), C.byref(ms))
+        assert rc == 0
+        q8 = c["quals"].astype(np.int8)
+        t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
+        es, efp, a1, a2 = coracle.align_tb(band, t, r, q8, c["gap_open"], c["gap_extend"], nuc, m, c["snv_prior"])
+        efs, ems = coracle.flank_score(W, lhs, rhs, r, q8, m, c["snv_prior"], c["gap_open"], c["gap_extend"], nuc, efp, a1, a2)
+        assert (sc.value, fl.value, ms.value) == (es, efs, ems), (band, L, lhs, rhs)
