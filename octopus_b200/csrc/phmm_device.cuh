@@ -34,7 +34,8 @@ namespace phmm {
 //          min(snv_prior[x] if snv_mask[x]==base else 127,  2 if truth[x]=='N' else 127)   otherwise
 //        sub(x, y) = min(qual[y], cap[x][read[y]])  — identical to update_match_state for quals, priors in [0,127].
 //        All caps are < 0x80, which lets PRMT's sign-replicate mode manufacture the zero bytes of the packed lanes.
-//   .y = gap_open[x] | gap_extend[x] << 8   (upper 16 bits zero)
+//   .y = gap_open[x] | gap_extend[x] << 8 | capN[x] << 16   (capN: the cap for a read base 'N': 0 if truth[x] == 'N',
+//        else snv_prior[x] if snv_mask[x] == 'N', else 127; top byte zero)
 typedef uint2 ColEntry;
 
 constexpr uint32_t kCapInf   = 127u;      // "no cap": min(q, 127) == q for every int8 quality
@@ -43,8 +44,9 @@ constexpr uint32_t kInf16x2  = kInf16 | (kInf16 << 16);
 constexpr int      kInf32    = 1 << 28;   // +inf of the int32 kernel
 constexpr int      kMaxScore16 = 0x7000 - 1024;  // a read whose sum of qualities is below this cannot overflow a 16-bit lane
 
-// Read row half-word: code | qual << 8 (code: A0 C1 G2 T3). Reads containing any other byte take the generic path.
-__host__ __device__ inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+// Read row half-word: code | qual << 8 (code: A0 C1 G2 T3, N4). Reads with an 'N' are served by the 32-bit kernel (its
+// PRMT lookup has a fifth cap); reads containing any other byte take the generic path.
+__host__ __device__ inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : -1; }
 
 // The DP cores are __host__ __device__ so that tests/ can run the very same code on the CPU (with the few
 // sm_100a instructions emulated below) against the CPU checker without a GPU. The product library never calls the
@@ -119,9 +121,10 @@ PHMM_HD ColEntry make_col_entry(const char truth, const char snv_mask, const int
         }
         caps |= cap << (8 * b);
     }
+    const uint32_t cap_n = truth == 'N' ? 0u : (snv_mask == 'N' ? (uint32_t)snv_prior : kCapInf);
     ColEntry e;
     e.x = caps;
-    e.y = (uint32_t)gap_open | ((uint32_t)gap_extend << 8);
+    e.y = (uint32_t)gap_open | ((uint32_t)gap_extend << 8) | (cap_n << 16);
     return e;
 }   // code 0 / qual 0 for both halves: sub = min(0, cap) = 0
 
@@ -178,8 +181,8 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
         const int xn = (x + 1 < W) ? x + 1 : W - 1;
         const ColEntry n0 = ldg(t0 + xn), n1 = ldg(t1 + xn);
         const uint32_t caps0 = e0.x, caps1 = e1.x;
-        const uint32_t go = prmt(e0.y, e1.y, 0x2420u);   // gap_open[x]   of both halves
-        const uint32_t ge = prmt(e0.y, e1.y, 0x2521u);   // gap_extend[x]
+        const uint32_t go = prmt(e0.y, e1.y, 0x3430u);   // gap_open[x]   of both halves (byte 3 of .y is the zero source)
+        const uint32_t ge = prmt(e0.y, e1.y, 0x3531u);   // gap_extend[x]
         const uint32_t gop = go_prev + nucp;             // gap_open[x-1] + nuc_prior
         const uint32_t gep = ge_prev + nucp;             // gap_extend[x-1] + nuc_prior
         const RowEntry* rp = rows + x;
@@ -252,9 +255,9 @@ constexpr uint32_t kF32Valid = 0x80u, kF32TypeD = 0x40u;
 PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Row entries of this kernel (one read, not a pair): .x = PRMT selector picking the cap byte of the read base into byte 0
-// and zeros elsewhere (code | 0x4440), .y = base quality.
-PHMM_HD RowEntry make_row_entry32(uint32_t half) { RowEntry r; r.x = (half & 3u) | 0x4440u; r.y = half >> 8; return r; }
-PHMM_HD RowEntry pad_row_entry32() { RowEntry r; r.x = 0x4440u; r.y = 0u; return r; }
+// and zeros elsewhere (code | 0x5550 — bytes 1..3 of the second operand are zero; code 4 = 'N' picks byte 0 of the second PRMT operand, the column's capN), .y = base quality.
+PHMM_HD RowEntry make_row_entry32(uint32_t half) { RowEntry r; r.x = (half & 7u) | 0x5550u; r.y = half >> 8; return r; }
+PHMM_HD RowEntry pad_row_entry32() { RowEntry r; r.x = 0x5550u; r.y = 0u; return r; }
 
 // rows: shared-memory row entries (make_row_entry32), rows[L] = pad_row_entry32().
 // tab : column table of the window. xl / xr: first non-flank column and first right-flank column (0 <= xl < xr <= W);
@@ -280,7 +283,7 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
 #define PHMM_FCELL(k, CAPTURE)                                                                          \
     {                                                                                                   \
         const RowEntry w = rp[-(k)];                                                                    \
-        const uint32_t sub = umin32(w.y, prmt(caps, 0u, w.x));                                          \
+        const uint32_t sub = umin32(w.y, prmt(caps, cap_n, w.x));                                       \
         const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                              \
         const uint32_t mi = umin32(m, i_run);                                                           \
         const uint32_t S = umin32(mi, d);                                                               \
@@ -295,7 +298,7 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
     for (int x = 0; x <= W; ++x) {
         const int xn = (x + 1 < W) ? x + 1 : W - 1;
         const ColEntry nx = ldg(tab + xn);
-        const uint32_t caps = e.x;
+        const uint32_t caps = e.x, cap_n = (e.y >> 16) & 0xFFu;
         const uint32_t goS = (e.y & 0xFFu) << kF32ScoreShift, geS = ((e.y >> 8) & 0xFFu) << kF32ScoreShift;
         const uint32_t gopS = go_prev + nucS, gepS = ge_prev + nucS;
         const RowEntry* rp = rows + x;
@@ -314,7 +317,7 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
                 }
             }
         } else {
-            const uint32_t sub0 = umin32(w0.y, prmt(caps, 0u, w0.x)) << kF32ScoreShift;   // m(x+1, 1) = sub(x, 0)
+            const uint32_t sub0 = umin32(w0.y, prmt(caps, cap_n, w0.x)) << kF32ScoreShift;   // m(x+1, 1) = sub(x, 0)
             i_run = (x & 1) ? (gopS | kF32LabI) : (kF32Inf | kF32LabI);                    // i(x, 1) out of the free-start cell
             if (x < L) {
                 switch (x) { PHMM_REP64(PHMM_FCASE_PROLOGUE) default: break; }

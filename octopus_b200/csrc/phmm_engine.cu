@@ -313,7 +313,7 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         const long long hl = s.hap_off_host[t.hap + 1] - s.hap_off_host[t.hap];
         if (L < 1 || t.win_off < 0 || (long long)t.win_off + L + 2 * band - 1 > hl) { e->err = "task window outside the haplotype"; return PHMM_ERR_INVALID; }
         cells += 2LL * (L + band) * band;
-        if (fast_ok && (e->info_host[t.read].y & kReadGenericMask) == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
+        if (fast_ok && (e->info_host[t.read].y & (kReadGenericMask | kReadHasN)) == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
         else gen.push_back(GenericTask {t.read, t.hap, t.win_off, t.reverse ? 1 : 0, j});
     }
     e->last_dp_cells = cells;
@@ -686,7 +686,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(e->fcnt.ensure(list_cap * sizeof(int)));
         p.ftasks = e->ftasks.as<uint32_t>();
         p.fcnt = e->fcnt.as<int>();
-        if (p.use_flanks) {
+        if (p.use_flanks || tot.n_with_n > 0) {
             CU(e->gtasks.ensure(list_cap * p.fcap * sizeof(uint32_t)));
             CU(e->gcnt.ensure(list_cap * sizeof(int)));
             p.gtasks = e->gtasks.as<uint32_t>();
@@ -740,7 +740,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             }
             CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
-            if (p.use_flanks) {
+            const bool run_32bit = p.use_flanks || tot.n_with_n > 0;
+            if (run_32bit) {
                 CU(cudaMemsetAsync(p.gcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
                 CU(cudaMemsetAsync(p.flank_cursor, 0, sizeof(int), e->stream));
             }
@@ -759,7 +760,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             LAUNCHED();
             CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             ++n_timed; timed = true;
-            if (p.use_flanks) {   // near-flank candidates of the fast-path reads: payload-carrying 32-bit DP
+            if (run_32bit) {   // near-flank candidates (and every candidate of reads holding 'N'): payload-carrying 32-bit DP
                 const unsigned fgrid = (unsigned)std::max(1, std::min((2 * np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
                 const size_t fsmem = (size_t)kFastWarpsPerBlock * p.row_stride * sizeof(RowEntry);
                 switch (band) {

@@ -34,6 +34,7 @@ constexpr int kReadNonACGT  = 1;   // read holds a byte outside ACGT → generic
 constexpr int kReadUnsafe16 = 2;   // sum of qualities too large for a 16-bit lane, or a quality > 127
 constexpr int kReadTooLong  = 4;   // longer than the fast path's shared-memory row budget
 constexpr int kReadUnsafeFlank32 = 8;   // quality sum too large for the 14-bit score field of the flank-aware kernel (fast path still fine)
+constexpr int kReadHasN = 16;           // read holds 'N' (and nothing else outside ACGT): all its DPs run on the 32-bit kernel (5th cap)
 constexpr int kReadGenericMask = 7;     // any of these → the read takes the generic (int32) path
 
 constexpr int kFastMaxReadLen = 1023;
@@ -71,6 +72,7 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
         const int c = base_code(bases[b + y]);
         const int q = quals[b + y];
         if (c < 0) flags |= kReadNonACGT;
+        if (c == 4) flags |= kReadHasN;
         if (q > 127) flags |= kReadUnsafe16;
         qsum += q;
         rowhalf[b + y] = (uint16_t)((c < 0 ? 0 : c) | (q << 8));
@@ -82,6 +84,7 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
     }
     if (qsum > kMaxScore16) flags |= kReadUnsafe16;
     if (qsum > kMaxScoreFlank32) flags |= kReadUnsafeFlank32;
+    if ((flags & kReadHasN) && (flags & kReadUnsafeFlank32)) flags |= kReadNonACGT;   // an N read the 32-bit kernel cannot take → generic
     if (L > kFastMaxReadLen || L < 1) flags |= kReadTooLong;
     if (lane == 0) info[r] = make_int2(L, flags);
 }
@@ -92,7 +95,7 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
 // pass over all reads; the host only reads back a handful of totals.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kLenBins = kFastMaxReadLen + 1;
-struct SchedTotals { int n_pairs, n_generic, lmax_fast, lmax_all, n_eligible, bad; long long cells; };
+struct SchedTotals { int n_pairs, n_generic, lmax_fast, lmax_all, n_eligible, bad; long long cells; int n_with_n, pad; };
 
 __global__ void k_sched_hist(const int R, const int2* __restrict__ info, const int fast_ok, int* __restrict__ hist,
                              int* __restrict__ generic, int* __restrict__ n_generic, int* __restrict__ lmax_all, int* __restrict__ bad)
@@ -102,7 +105,7 @@ __global__ void k_sched_hist(const int R, const int2* __restrict__ info, const i
     const int2 inf = info[r];
     if (inf.x < 1) atomicExch(bad, 1);
     atomicMax(lmax_all, inf.x);
-    if (fast_ok && (inf.y & kReadGenericMask) == 0) atomicAdd(&hist[inf.x], 1);
+    if (fast_ok && (inf.y & kReadGenericMask) == 0) { atomicAdd(&hist[inf.x], 1); if (inf.y & kReadHasN) atomicAdd(bad + 1, 1); }
     else generic[atomicAdd(n_generic, 1)] = r;
 }
 
@@ -152,6 +155,7 @@ k_sched_scan(const int* __restrict__ hist, const int G, const int band, const in
         tot->lmax_fast = max(m, 1);
         tot->lmax_all = max(*lmax_all, 1);
         tot->bad = *bad;
+        tot->n_with_n = bad[1];
         tot->cells = (long long)s_cells * H;
     }
     if (l == kLenBins - 1) { read_start[kLenBins] = s_reads[l]; pair_start[kLenBins] = s_pairs[l]; }
@@ -584,7 +588,8 @@ __global__ void k_populate_generic(const PopParams p)
     if (best == 0) n_pend = 0;
     for (int i2 = 0; i2 < n_pend; ++i2) {
         const int v = pend_a[i2];
-        if (!((pend_flank >> i2) & 1u)) {
+        const bool to_32bit = FASTQ && (p.rd.info[r].y & kReadHasN);   // reads with 'N': every DP on the 32-bit kernel
+        if (!((pend_flank >> i2) & 1u) && !to_32bit) {
             if (FASTQ) {
                 const int slot = atomicAdd(p.fcnt + li, 1);
                 if (slot < p.fcap) p.ftasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);

@@ -145,7 +145,7 @@ def test_flank_payload_dp_matches_traceback_flank_replay(emul, coracle):
         band = int(rng.choice([8, 16, 32]))
         L = int(rng.integers(1, 160))
         nuc = int(rng.integers(0, 5))
-        c = random_alignment_case(rng, band, L)
+        c = random_alignment_case(rng, band, L, read_n=(it % 3 == 0))     # reads with 'N': the fifth cap of the 32-bit kernel
         W = len(c["truth"])
         mode = it % 4
         if mode == 0:
