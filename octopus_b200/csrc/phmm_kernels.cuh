@@ -308,6 +308,19 @@ __device__ __forceinline__ ReadView read_view(const DevReads& rd, const int r)
     return ReadView {rd.bases + o, rd.quals + o, (int)(rd.off[r + 1] - o)};
 }
 
+// Append one task to list slot li with a warp-aggregated counter update: the lanes of a warp that append to the same list
+// (normally all of them: consecutive threads are consecutive haplotypes of one read) share a single atomicAdd.
+__device__ __forceinline__ int list_append_slot(int* counts, const int li)
+{
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, li);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counts + li, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void push_slow(const PopParams& p, const int r, const int h, const int a)
 {
     const int idx = atomicAdd(p.slow_count, 1);
@@ -591,7 +604,7 @@ __global__ void k_populate_generic(const PopParams p)
         const bool to_32bit = FASTQ && (p.rd.info[r].y & kReadHasN);   // reads with 'N': every DP on the 32-bit kernel
         if (!((pend_flank >> i2) & 1u) && !to_32bit) {
             if (FASTQ) {
-                const int slot = atomicAdd(p.fcnt + li, 1);
+                const int slot = list_append_slot(p.fcnt, li);
                 if (slot < p.fcap) p.ftasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
                 else atomicOr(p.flags, 8);
             } else {
@@ -600,7 +613,7 @@ __global__ void k_populate_generic(const PopParams p)
             }
         } else {
             if (FASTQ && !(p.rd.info[r].y & kReadUnsafeFlank32)) {
-                const int slot = atomicAdd(p.gcnt + li, 1);
+                const int slot = list_append_slot(p.gcnt, li);
                 if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
                 else atomicOr(p.flags, 8);
             } else push_slow(p, r, h, v);
