@@ -61,9 +61,9 @@ def _qualities(rng, n, L, profile):
         return np.full((n, L), 30, dtype=np.uint8)
     # "empirical": Illumina-binned {2: 2 %, 12: 3 %, 23: 10 %, 37: 85 %}, low bins concentrated in the last 20 % of the read
     q = np.full((n, L), 37, dtype=np.uint8)
-    u = rng.random((n, L))
+    u = rng.random((n, L), dtype=np.float32)
     tail = np.arange(L) >= int(0.8 * L)
-    scale = np.where(tail, 3.0, 0.5)                          # overall mass ≈ 15 % low-quality, mostly in the tail
+    scale = np.where(tail, 3.0, 0.5).astype(np.float32)      # overall mass ≈ 15 % low-quality, mostly in the tail
     q[u < 0.15 * scale] = 23
     q[u < 0.05 * scale] = 12
     q[u < 0.02 * scale] = 2
@@ -82,9 +82,14 @@ def make_reads(rng, haps: HaplotypeBlock, n_reads, read_lens, band, profile):
     bases = np.empty(int(off[-1]), dtype=np.uint8)
     quals = np.empty(int(off[-1]), dtype=np.uint8)
     begin = np.empty(n_reads, dtype=np.int64)
+    p_err = np.power(10.0, -np.arange(256, dtype=np.float64) / 10.0).astype(np.float32)   # substitution probability by quality
+    chunk = 100_000                                                                       # keeps the temporaries cache-sized
+    work = []
     for li, L in enumerate(lens):
-        L = int(L)
-        sel = np.nonzero(which == li)[0]
+        idx_all = np.nonzero(which == li)[0]
+        for c0 in range(0, len(idx_all), chunk):
+            work.append((int(L), idx_all[c0:c0 + chunk]))
+    for L, sel in work:
         n = len(sel)
         if n == 0:
             continue
@@ -106,8 +111,8 @@ def make_reads(rng, haps: HaplotypeBlock, n_reads, read_lens, band, profile):
         if ins.any():
             rb[np.nonzero(ins)[0], ipos[ins]] = _ACGT[rng.integers(0, 4, int(ins.sum()))]
         q = _qualities(rng, n, L, profile)
-        err = rng.random((n, L)) < np.power(10.0, -q.astype(np.float64) / 10.0)
-        rb = np.where(err, _ACGT[rng.integers(0, 4, (n, L))], rb)
+        err = rng.random((n, L), dtype=np.float32) < p_err[q]
+        rb = np.where(err, _ACGT[rng.integers(0, 4, (n, L), dtype=np.uint8)], rb)
         rb = np.where(rb == ord("N"), ord("A"), rb).astype(np.uint8)
         dest = off[sel][:, None] + col[None, :]
         bases[dest] = rb
