@@ -302,6 +302,9 @@ def main():
         alg_bytes = 4 * H * R + 2 * int(reads.off[-1]) + 16 * int(haps.off[-1])
         peak, peak_src = peaks()
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernel per step, from the committed ncu --set full captures
+        # (profiles/r01d_populate_fast_c3_ncu_raw.csv: one of C3's two tile launches; profiles/r01c_*: C2), default sizes only
+        traffic = {("C3", 1_000_000, 128): 2 * (714.1e6 + 238.2e6), ("C2", 100_000, 64): 84.1e6 + 3.0e6}.get((args.config, R, H))
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -316,7 +319,7 @@ def main():
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_populate_fast<%d>" % band, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the path is integer-issue bound, not HBM bound (SURVEY.md F3); see DESIGN.md for the issue-rate roofline",

@@ -879,7 +879,11 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     if (!e) return PHMM_ERR_INVALID;
     // Pipelined path: host-resident batch, no caller-supplied position lists (a [H][R] CSR cannot be sliced by columns
     // without a pass over it), enough pairs to amortise the per-chunk overheads.
-    const long long kChunkPairs = 8LL << 20;
+    static const long long kChunkPairs = [] {
+        const char* v = std::getenv("PHMM_CHUNK_PAIRS");          // test hook: force the pipelined path on small batches
+        const long long n = v ? std::atoll(v) : 0;
+        return n > 0 ? n : (8LL << 20);
+    }();
     const bool can_chunk = !e->is_sub && space == PHMM_SPACE_HOST && haps && reads && cfg && out && haps->n > 0 && reads->n > 1 &&
                            reads->off && reads->mapq && reads->reverse && !(positions && positions->off && positions->pos) &&
                            (long long)haps->n * reads->n >= 2 * kChunkPairs;

@@ -1,5 +1,7 @@
 """Full-size runs (BASELINE.json's C2 shape on one GPU) checked through size-independent properties plus a random
 sample of pairs against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -40,3 +42,30 @@ def test_c2_full_size_properties(engine, coracle):
         for h in range(64):
             if np.array_equal(hs[h, p:p + L], b):
                 assert m[h, r] == 0.0
+
+
+def test_pipelined_host_path_equals_single_pass():
+    """Host-resident batches above a size threshold are cut into read chunks and pipelined over two sub-engines (copies of
+    one chunk overlap the kernels of the other). Forced here on a small batch through the PHMM_CHUNK_PAIRS test hook, in a
+    fresh process (the threshold is read once), and compared with the unchunked device-resident result."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+from octopus_b200 import HaplotypeLikelihoodModel, PairHMMEngine, synth
+haps, reads, band = synth.make_batch("C4", n_reads=9000, n_haps=20)          # ragged lengths, band 32
+eng = PairHMMEngine(0)
+for kw in (dict(map_positions=False, disable_naive_shortcut=True), dict(), dict(use_mapping_quality=False)):
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, **kw)
+    for flanks in (None, (70, 60)):
+        host, st = eng.populate(cfg, haps, reads, flank_state=flanks, want_status=True)          # chunked (env hook)
+        dev = eng.populate(cfg, haps.to_device("cuda:0"), reads.to_device("cuda:0"), flank_state=flanks).cpu().numpy()
+        assert np.array_equal(host, dev), (kw, flanks)
+        assert (st == 0).all()
+assert eng.launch_count(total=True) > 100
+print("PIPELINE_OK")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    env = dict(os.environ, PHMM_CHUNK_PAIRS="20000")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "PIPELINE_OK" in out.stdout, out.stdout + out.stderr
