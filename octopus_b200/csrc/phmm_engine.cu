@@ -736,7 +736,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
                 else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
                 LAUNCHED();
-                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>(); p.k_first_list_index = 0;
+                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
             CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
@@ -783,7 +783,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.generic_reads, ng, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
                 else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.generic_reads, ng, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
                 LAUNCHED();
-                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>(); p.k_first_list_index = 0;
+                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
             const long long threads = (long long)ng * H;
             const bool time_generic = n_pairs == 0 && n_timed == 0;

@@ -264,7 +264,6 @@ struct PopParams {
     // read in the tile's work list) and haplotype h own kpos[(li * H + h) * kMaxMapped .. ), kcnt[li * H + h] entries
     const int32_t* kpos;
     const uint8_t* kcnt;
-    int k_first_list_index;     // list index of the first read of this launch's work list
     // fast-path DP tasks produced by the classify pass for the current tile: list slot li owns
     // ftasks[li * fcap .. li * fcap + fcnt[li]) entries (haplotype | window offset << 16)
     uint32_t* ftasks;
@@ -328,7 +327,6 @@ __device__ __forceinline__ void push_slow(const PopParams& p, const int r, const
     else atomicOr(p.flags, 4);
 }
 
-constexpr int kQueueCap = 64;
 constexpr int kRoundsPerUnit = 8;   // dp_pair rounds per work unit of the fast kernel (bounds the tail imbalance of long task lists)
 constexpr int kMaxMapped = 10;    // HaplotypeLikelihoodArray::maxMappingPositions (haplotype_likelihood_array.hpp:104)
 constexpr int kKmer = 6;          // mapperKmerSize (:103)
