@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -63,10 +66,51 @@ struct phmm_engine {
     DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, gcnt, sched, sorted;
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
+    // per-kernel launch configuration already applied / queried (the runtime calls are not free and need not be repeated)
+    std::map<const void*, size_t> smem_set;
+    std::map<std::pair<const void*, size_t>, int> occupancy;
     // host-space calls on large batches are pipelined over two sub-engines (own stream + buffers each), driven by two host
     // threads, so that the H2D / D2H copies of one read chunk overlap the kernels of the other
     phmm_engine* sub[2] = {nullptr, nullptr};
     bool is_sub = false;
+    // Chunk c's DP kernels wait (on the device) for chunk c-1's, so that the DP kernels run back to back in chunk order —
+    // each with the whole GPU — while the other chunk's copies, preparation and classify pass fill in around them.
+    // order_ev marks "this sub-engine's DP kernels of its current chunk are done"; the parent's order state tells the other
+    // worker thread that the event has been recorded (a wait enqueued before the record would see the previous one).
+    phmm_engine* parent = nullptr;
+    phmm_engine* peer = nullptr;
+    cudaEvent_t order_ev = nullptr;
+    long long chunk_index = -1;
+    struct OrderState { std::mutex m; std::condition_variable cv; long long recorded = -1; } order;
+};
+
+// Sub-engine side of the chunk ordering; no-ops on a plain engine.
+struct ChunkOrder {
+    phmm_engine* e;
+    bool waited = false, recorded = false;
+    explicit ChunkOrder(phmm_engine* eng) : e(eng) {}
+    cudaError_t wait_for_previous()   // before this chunk's first DP launch
+    {
+        if (!e->is_sub || !e->parent || waited) return cudaSuccess;
+        waited = true;
+        if (e->chunk_index <= 0) return cudaSuccess;
+        phmm_engine::OrderState& st = e->parent->order;
+        {
+            std::unique_lock<std::mutex> lk(st.m);
+            st.cv.wait(lk, [&] { return st.recorded >= e->chunk_index - 1; });
+        }
+        return cudaStreamWaitEvent(e->stream, e->peer->order_ev, 0);
+    }
+    void publish(bool record)         // after this chunk's last DP launch (or on any exit)
+    {
+        if (!e->is_sub || !e->parent || recorded) return;
+        recorded = true;
+        if (record) cudaEventRecord(e->order_ev, e->stream);
+        phmm_engine::OrderState& st = e->parent->order;
+        { std::lock_guard<std::mutex> lk(st.m); st.recorded = std::max(st.recorded, e->chunk_index); }
+        st.cv.notify_all();
+    }
+    ~ChunkOrder() { publish(false); }
 };
 
 #define CU(call)                                                                                   \
@@ -115,7 +159,8 @@ int fetch_offsets(phmm_engine* e, const int64_t* off, int n, int space, std::vec
 }
 
 // Upload (or alias) the batch and run the preparation kernels: column tables, row half-words, read info.
-int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* reads, int space, Staged& s, bool need_info_host = true)
+int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* reads, int space, Staged& s, bool need_info_host = true,
+                bool defer_flag_check = false)
 {
     if (!haps || !reads || haps->n <= 0 || reads->n <= 0 || !haps->off || !reads->off) {
         e->err = "empty or null haplotype / read block";
@@ -176,6 +221,7 @@ int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* r
         e->info_host.resize(rd.n);
         CU(cudaMemcpyAsync(e->info_host.data(), e->info.p, (size_t)rd.n * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
     }
+    if (defer_flag_check) return PHMM_OK;   // the caller reads flags bit 0 at its own final synchronisation
     int flags_host[1] = {0};
     CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -189,7 +235,21 @@ int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* r
 template <typename F>
 int fast_smem_attr(phmm_engine* e, F kernel, size_t bytes)
 {
+    size_t& have = e->smem_set[(const void*)kernel];
+    if (bytes <= have && have != 0) return PHMM_OK;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+    return PHMM_OK;
+}
+
+template <typename F>
+int blocks_per_sm_of(phmm_engine* e, F kernel, int threads, size_t smem, int* out)
+{
+    const auto key = std::make_pair((const void*)kernel, smem);
+    const auto it = e->occupancy.find(key);
+    if (it != e->occupancy.end()) { *out = it->second; return PHMM_OK; }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, threads, smem));
+    e->occupancy[key] = *out;
     return PHMM_OK;
 }
 
@@ -261,6 +321,7 @@ void phmm_destroy(phmm_engine* e)
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->order_ev) cudaEventDestroy(e->order_ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -559,7 +620,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     static const bool trace = std::getenv("PHMM_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
-        if (trace) std::fprintf(stderr, "[phmm] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        if (trace) std::fprintf(stderr, "[phmm %p] %-18s %8.3f ms  (abs %.3f)\n", (void*)e, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(),
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count());
     };
     e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
     if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
@@ -569,11 +631,24 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     if (cfg->nuc_prior < 0 || cfg->nuc_prior > 127) { e->err = "nuc_prior outside [0,127]"; return PHMM_ERR_INVALID; }
     if (!reads || !reads->mapq || !reads->reverse) { e->err = "reads->mapq / reads->reverse required"; return PHMM_ERR_INVALID; }
     Staged s;
-    int rc = stage_batch(e, haps, reads, space, s, false);
+    int rc = stage_batch(e, haps, reads, space, s, false, true);
     if (rc != PHMM_OK) return rc;
     const int H = s.hp.n, R = s.rd.n;
     const long long HR = (long long)H * R;
-    lap("staged+info");
+    // Everything from here to the final copy-out is enqueued without waiting for the device: sizes come from upper bounds
+    // the host can derive from the offsets, the kernels clip them against the scheduler's device-resident totals.
+    long long len_min = 1LL << 40, len_max = 0;
+    {
+        const long long* off = s.read_off_host.data();
+        for (int r = 0; r < R; ++r) { const long long len = off[r + 1] - off[r]; len_min = std::min(len_min, len); len_max = std::max(len_max, len); }
+    }
+    if (len_min < 1) { e->err = "empty read"; return PHMM_ERR_INVALID; }
+    if (len_max > (1LL << 30)) { e->err = "read too long"; return PHMM_ERR_INVALID; }
+    const int Lmax_all = (int)len_max;
+    const int Lmax_fast = std::min(Lmax_all, kFastMaxReadLen);
+    // distinct read lengths the fast path can see: bounds the padding of the length-bucketed pair list
+    const long long len_bins = std::max<long long>(1, std::min<long long>({(long long)R, (long long)Lmax_fast - std::min<long long>(len_min, Lmax_fast) + 1, (long long)kLenBins}));
+    lap("staged");
 
     PopParams p {};
     p.hp = s.hp; p.rd = s.rd;
@@ -644,13 +719,13 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         k_sched_pairs<<<(unsigned)((pairs_cap + 255) / 256), 256, 0, e->stream>>>(d_tot, read_start, pair_start, e->sorted.as<int>(), e->pairs.as<int>());
         LAUNCHED();
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(&tot, d_tot, sizeof(SchedTotals), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        if (tot.bad) { e->err = "empty read"; return PHMM_ERR_INVALID; }
+        p.tot = d_tot;
     }
-    const int Lmax_fast = tot.lmax_fast, Lmax_all = tot.lmax_all;
-    const int n_pairs = tot.n_pairs, n_generic = tot.n_generic;
-    lap("scheduled");
+    const SchedTotals* d_tot = p.tot;
+    // upper bounds of the two work lists (exact counts stay on the device)
+    // (a bucket of c reads holds ceil(c / 2) pairs rounded up to a multiple of `groups`)
+    const long long n_pairs = fast_ok ? std::min<long long>((long long)pairs_cap, R / 2 + len_bins * groups + 1) : 0, n_generic = R;
+    lap("sched enqueued");
 
     CU(e->best.ensure((size_t)HR * sizeof(int)));
     CU(e->status.ensure((size_t)HR * sizeof(int)));
@@ -664,40 +739,38 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     p.flags = e->flags.as<int>();
     int* counters = e->counters.as<int>();
     p.pair_cursor = counters + 0;
-    p.slow_count = counters + 1;
+    p.flank_cursor = counters + 1;
+    p.any_flank_tasks = counters + 2;
+    p.slow_count = counters + 3;
 
-    // near-flank (traceback) queue, processed tile by tile so that its worst case fits the budget
-    const long long slow_budget = 8LL << 20;   // entries (16 bytes each)
-    long long reads_per_tile = R;
-    if (use_mapper) {
-        // mapped candidate lists of one tile: (10 x int32 + 1 byte) per (read, haplotype) pair, at most ~1 GiB
-        reads_per_tile = std::max<long long>(2, std::min<long long>(R + 1, (1LL << 30) / (41LL * H)));
-        const size_t pairs_cap = (size_t)std::min<long long>(reads_per_tile + 2, (long long)R + 2) * H;
-        CU(e->kpos.ensure(pairs_cap * kMaxMapped * sizeof(int32_t)));
-        CU(e->kcnt.ensure(pairs_cap));
-    }
-    // fast-path task lists of one tile: every (read, haplotype) pair can contribute one DP task per candidate position
+    // Tile size: the per-tile scratch (mapped candidate lists, DP task lists, traceback queue) must fit fixed budgets.
+    const long long slow_budget = 8LL << 20;   // traceback-queue entries (16 bytes each)
     const int max_dp_per_pair = (p.pos_off || use_mapper) ? 11 : 1;
-    p.fcap = H * max_dp_per_pair;
+    p.fcap = H * max_dp_per_pair;              // a read's task list: one DP task per (haplotype, candidate position)
+    long long reads_per_tile = std::max<long long>(R, 2 * n_pairs);   // one tile unless a budget says otherwise
+    if (use_mapper) reads_per_tile = std::max<long long>(2, std::min<long long>(R + 1, (1LL << 30) / (41LL * H)));   // (10 x int32 + 1 byte) per pair
+    if (n_pairs) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (64LL << 20) / p.fcap));
+    if (p.use_flanks) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
+    const long long pairs_per_tile = std::max<long long>((long long)groups, (reads_per_tile / 2) / (long long)groups * (long long)groups);
+    // work-list entries one tile can hold (pair tiles: two per pair, padding entries included)
+    const size_t tile_list_cap = (size_t)std::max<long long>(std::min<long long>(2 * pairs_per_tile, 2 * std::max<long long>(n_pairs, groups)), std::min<long long>(reads_per_tile, R)) + 2;
+    if (use_mapper) {
+        CU(e->kpos.ensure(tile_list_cap * H * kMaxMapped * sizeof(int32_t)));
+        CU(e->kcnt.ensure(tile_list_cap * H));
+    }
     if (n_pairs) {
-        reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (64LL << 20) / p.fcap));
-        const size_t list_cap = (size_t)std::min<long long>(reads_per_tile + 2, 2LL * n_pairs);
-        CU(e->ftasks.ensure(list_cap * p.fcap * sizeof(uint32_t)));
-        CU(e->fcnt.ensure(list_cap * sizeof(int)));
+        CU(e->ftasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
+        CU(e->fcnt.ensure(2 * tile_list_cap * sizeof(int)));
         p.ftasks = e->ftasks.as<uint32_t>();
         p.fcnt = e->fcnt.as<int>();
-        if (p.use_flanks || tot.n_with_n > 0) {
-            CU(e->gtasks.ensure(list_cap * p.fcap * sizeof(uint32_t)));
-            CU(e->gcnt.ensure(list_cap * sizeof(int)));
-            p.gtasks = e->gtasks.as<uint32_t>();
-            p.gcnt = e->gcnt.as<int>();
-        }
+        // the 32-bit kernel's lists (near-flank candidates, reads holding 'N'): whether any exist is only known on the device
+        CU(e->gtasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
+        p.gtasks = e->gtasks.as<uint32_t>();
+        p.gcnt = p.fcnt + tile_list_cap;
     }
-    p.flank_cursor = counters + 2;
     const int slow_threads = e->sm_count * 256;
     if (p.use_flanks) {
-        reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
-        p.slow_cap = (int)std::min<long long>(slow_budget, (long long)H * max_cand * std::min<long long>(reads_per_tile, R));
+        p.slow_cap = (int)std::min<long long>(slow_budget, (long long)H * max_cand * (long long)tile_list_cap);
         CU(e->slow.ensure((size_t)p.slow_cap * sizeof(int4)));
         p.slow = e->slow.as<int4>();
         CU(e->bp.ensure((size_t)slow_threads * (size_t)(Lmax_all + 1) * (size_t)(2 * band)));
@@ -707,13 +780,14 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         p.slow = e->slow.as<int4>();
     }
 
+    lap("buffers");
     p.row_stride = (Lmax_fast + 2) & ~1;
     const size_t smem = (size_t)kFastWarpsPerBlock * groups * p.row_stride * sizeof(RowEntry);
     int blocks_per_sm = 1;
     if (n_pairs) {
 #define PHMM_FAST_SETUP(B, GG) \
         { if ((rc = fast_smem_attr(e, k_populate_fast<B, GG>, smem))) return rc; \
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_populate_fast<B, GG>, kFastWarpsPerBlock * 32, smem)); }
+          if ((rc = blocks_per_sm_of(e, k_populate_fast<B, GG>, kFastWarpsPerBlock * 32, smem, &blocks_per_sm))) return rc; }
 #define PHMM_FAST_DISPATCH(MACRO) \
         switch (band * 10 + (int)groups) { \
             case 81: MACRO(8, 1) break;   case 82: MACRO(8, 2) break;   case 84: MACRO(8, 4) break; \
@@ -723,7 +797,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         if (blocks_per_sm < 1) { e->err = "fast kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; }
     }
 
-    const long long pairs_per_tile = std::max<long long>((long long)groups, (reads_per_tile / 2) / (long long)groups * (long long)groups);
+    lap("kernel attrs");
+    ChunkOrder chunk_order(e);
     bool timed = false;
     size_t n_timed = 0;
     for (long long p0 = 0, g0 = 0; p0 < n_pairs || g0 < n_generic;) {
@@ -731,36 +806,36 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             const int np = (int)std::min<long long>(pairs_per_tile, n_pairs - p0);
             p.pair_reads = e->pairs.as<int>() + 2 * p0;
             p.n_pairs = np;
+            p.pair_base = (int)p0;
             if (use_mapper) {
                 const long long threads = 2LL * np * H;
-                if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
-                else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, d_tot, (int)p0, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, d_tot, (int)p0, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            CU(cudaMemsetAsync(p.pair_cursor, 0, sizeof(int), e->stream));
+            CU(cudaMemsetAsync(counters, 0, 3 * sizeof(int), e->stream));                       // pair cursor, flank cursor, any-flank-tasks
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
-            const bool run_32bit = p.use_flanks || tot.n_with_n > 0;
-            if (run_32bit) {
-                CU(cudaMemsetAsync(p.gcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
-                CU(cudaMemsetAsync(p.flank_cursor, 0, sizeof(int), e->stream));
-            }
+            CU(cudaMemsetAsync(p.gcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
             {   // classify pass: shortcut values → best[], near-flank candidates → slow queue, DP candidates → task lists
                 const long long threads = 2LL * np * H;
                 k_populate_generic<64, true><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p);
                 LAUNCHED();
             }
+            lap(" classify queued");
             p.units_per_pair = std::max(1, (p.fcap + (32 / groups) * kRoundsPerUnit - 1) / ((32 / groups) * kRoundsPerUnit));
             const int want_blocks = (int)std::min<long long>(1LL << 30, ((long long)(np / groups) * p.units_per_pair + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
             const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
             while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); }
+            CU(chunk_order.wait_for_previous());
             CU(cudaEventRecord(e->tile_events[2 * n_timed], e->stream));
 #define PHMM_FAST_LAUNCH(B, GG) k_populate_fast<B, GG><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p);
             PHMM_FAST_DISPATCH(PHMM_FAST_LAUNCH)
             LAUNCHED();
             CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             ++n_timed; timed = true;
-            if (run_32bit) {   // near-flank candidates (and every candidate of reads holding 'N'): payload-carrying 32-bit DP
+            lap(" dp queued");
+            {   // near-flank candidates (and every candidate of reads holding 'N'): payload-carrying 32-bit DP; returns at once if none
                 const unsigned fgrid = (unsigned)std::max(1, std::min((2 * np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
                 const size_t fsmem = (size_t)kFastWarpsPerBlock * p.row_stride * sizeof(RowEntry);
                 switch (band) {
@@ -778,18 +853,21 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);
             p.generic_reads = e->generic_reads.as<int>() + g0;
             p.n_generic = ng;
+            p.generic_base = (int)g0;
+            // ng is an upper bound (normally there are no generic reads at all): grid-stride kernels on a bounded grid
+            const long long threads = (long long)ng * H;
+            const unsigned ggrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 63) / 64, (long long)e->sm_count * 32));
             if (use_mapper) {
-                const long long threads = (long long)ng * H;
-                if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.generic_reads, ng, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
-                else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.generic_reads, ng, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                if (mapper_maxt == 512) k_kmer_map<512><<<ggrid, 64, 0, e->stream>>>(p.generic_reads, ng, d_tot, (int)g0, 0, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                else k_kmer_map<2048><<<ggrid, 64, 0, e->stream>>>(p.generic_reads, ng, d_tot, (int)g0, 0, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            const long long threads = (long long)ng * H;
             const bool time_generic = n_pairs == 0 && n_timed == 0;
+            CU(chunk_order.wait_for_previous());
             if (time_generic) CU(cudaEventRecord(e->ev0, e->stream));
-            if (band <= 32) k_populate_generic<64, false><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
-            else k_populate_generic<kGenericMaxDiag, false><<<(unsigned)((threads + 63) / 64), 64, 0, e->stream>>>(p);
+            if (band <= 32) k_populate_generic<64, false><<<ggrid, 64, 0, e->stream>>>(p);
+            else k_populate_generic<kGenericMaxDiag, false><<<ggrid, 64, 0, e->stream>>>(p);
             LAUNCHED();
             if (time_generic) { CU(cudaEventRecord(e->ev1, e->stream)); timed = true; }
             g0 += ng;
@@ -803,6 +881,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(cudaGetLastError());
     }
 
+    chunk_order.publish(true);
+    lap("tiles enqueued");
     CU(e->out.ensure((size_t)HR * sizeof(double)));
     double* d_out = (space == PHMM_SPACE_DEVICE && !template_off) ? out : e->out.as<double>();
     k_epilogue<<<(unsigned)((HR + 255) / 256), 256, 0, e->stream>>>(p.best, p.status, s.rd.mapq, H, R, cfg->use_mapping_quality,
@@ -837,10 +917,13 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(cudaMemcpyAsync(status, p.status, (size_t)HR * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
     }
     int flags_host[1] = {0};
-    CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     lap("enqueued");
+    CU(cudaMemcpyAsync(flags_host, e->flags.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&tot, d_tot, sizeof(SchedTotals), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     lap("done");
+    if (flags_host[0] & 1) { e->err = "snv prior / gap penalty outside [0,127]"; return PHMM_ERR_INVALID; }
+    if (trace && n_timed) { float ms = 0.f; cudaEventElapsedTime(&ms, e->tile_events[0], e->tile_events[2 * n_timed - 1]); std::fprintf(stderr, "[phmm %p] dp span %.3f ms\n", (void*)e, ms); }
     if (n_timed) {
         double total = 0.0;
         for (size_t t = 0; t < n_timed; ++t) { float ms = 0.f; if (cudaEventElapsedTime(&ms, e->tile_events[2 * t], e->tile_events[2 * t + 1]) == cudaSuccess) total += ms; }
@@ -894,8 +977,12 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
             const int rc = phmm_create(&sub, e->device);
             if (rc != PHMM_OK) { e->err = std::string("sub-engine: ") + phmm_last_error(nullptr); return rc; }
             sub->is_sub = true;
+            sub->parent = e;
+            if (cudaEventCreateWithFlags(&sub->order_ev, cudaEventDisableTiming) != cudaSuccess) { e->err = "sub-engine: event creation failed"; return PHMM_ERR_CUDA; }
         }
     }
+    e->sub[0]->peer = e->sub[1]; e->sub[1]->peer = e->sub[0];
+    e->order.recorded = -1;
     const int R = reads->n, H = haps->n;
     const long long reads_per_chunk = std::max<long long>(64, kChunkPairs / H);
     const int n_chunks = (int)((R + reads_per_chunk - 1) / reads_per_chunk);
@@ -913,7 +1000,13 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
             for (int i = 0; i <= n; ++i) off[i] = reads->off[lo + i] - base;
             phmm_reads sub_reads {n, off.data(), reads->bases + base, reads->quals + base, reads->mapq + lo, reads->reverse + lo,
                                   reads->begin ? reads->begin + lo : nullptr};
+            se->chunk_index = c;
             const int rc = populate_impl(se, cfg, haps, &sub_reads, nullptr, flank, out + lo, status ? status + lo : nullptr, PHMM_SPACE_HOST, R);
+            {   // a chunk that failed before reaching its DP phase must not leave the other worker waiting for it
+                std::lock_guard<std::mutex> lk(e->order.m);
+                e->order.recorded = std::max<long long>(e->order.recorded, rc != PHMM_OK && rc != PHMM_ERR_SHORT_HAPLOTYPE ? (long long)n_chunks : (long long)c);
+            }
+            e->order.cv.notify_all();
             cells[k] += se->last_dp_cells; launches[k] += se->launches_last;
             if (rc != PHMM_OK && rc != PHMM_ERR_SHORT_HAPLOTYPE) { rcs[k] = rc; errs[k] = se->err; return; }
             if (rc == PHMM_ERR_SHORT_HAPLOTYPE) { rcs[k] = rc; errs[k] = se->err; }   // keep going: every pair's status is still written

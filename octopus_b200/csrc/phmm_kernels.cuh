@@ -285,15 +285,23 @@ struct PopParams {
     int4* slow;                 // {read, hap, position a, unused}
     int* slow_count;
     int slow_cap;
+    // The host never waits for the scheduler: it sizes tiles by upper bounds and the kernels clip them against the
+    // device-resident totals (tile_pairs / tile_generic below).
+    const SchedTotals* tot;
+    int pair_base, generic_base; // first pair / generic read of the current tile
+    int* any_flank_tasks;       // set by the classify pass when it queues a task for k_populate_flank
     // fast path work list: read pairs of equal length (second may be -1)
     const int* pair_reads;
-    int n_pairs;
+    int n_pairs;                // tile size (upper bound)
     int* pair_cursor;           // persistent-warp work counter
     int row_stride;             // shared-memory row entries (8 bytes) per warp
     // generic path work list
     const int* generic_reads;
-    int n_generic;
+    int n_generic;              // tile size (upper bound)
 };
+
+__device__ __forceinline__ int tile_pairs(const PopParams& p) { return max(0, min(p.n_pairs, p.tot->n_pairs - p.pair_base)); }
+__device__ __forceinline__ int tile_generic(const PopParams& p) { return max(0, min(p.n_generic, p.tot->n_generic - p.generic_base)); }
 
 __device__ __forceinline__ HapView hap_view(const DevHaps& hp, const int h, const bool reverse)
 {
@@ -396,15 +404,18 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
 // map_query_to_target (:120-159) for every (read of the work list, haplotype): the first <= 10 mapping begins (ascending)
 // whose vote count equals the maximum. One thread per pair; the vote counts live in a per-thread local array.
 template <int MAXT>
-__global__ void k_kmer_map(const int* __restrict__ list, const int n_list, const int stride_in_list, const DevHaps hp, const DevReads rd,
+__global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int is_pairs,
+                           const DevHaps hp, const DevReads rd,
                            const uint16_t* __restrict__ rhash, const int* __restrict__ bin_start, const uint16_t* __restrict__ items,
                            int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int H = hp.n;
-    if (i >= (long long)n_list * H) return;
+    // the tile's work list: 2 entries per read pair, or the generic reads; clipped against the scheduler's totals
+    const int n_list = max(0, min(n_list_max, is_pairs ? 2 * (tot->n_pairs - base) : tot->n_generic - base));
+    const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
     const int li = (int)(i / H), h = (int)(i % H);
-    const int r = list[(size_t)li * stride_in_list];
+    const int r = list[li];
     uint8_t n_out = 0;
     if (r >= 0) {
         const long long ro = rd.off[r], ho = hp.off[h];
@@ -429,6 +440,7 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list, const
         }
     }
     kcnt[i] = n_out;
+    }
 }
 
 // Fast-path DP over the task lists the classify pass (k_populate_generic<.., true>) produced. Persistent warps: each warp
@@ -448,14 +460,15 @@ k_populate_fast(const PopParams p)
     RowEntry* rows = smem_rows + (warp * G + grp) * p.row_stride;
     const int R = p.rd.n;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
+    const int n_pairs = tile_pairs(p);
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(p.pair_cursor, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         const int jb = (u / p.units_per_pair) * G, part = u % p.units_per_pair;
-        if (jb >= p.n_pairs) break;
+        if (jb >= n_pairs) break;
         const int j = jb + grp;
-        const int r0 = j < p.n_pairs ? p.pair_reads[2 * j] : -1;
+        const int r0 = j < n_pairs ? p.pair_reads[2 * j] : -1;
         const int r1 = r0 >= 0 ? p.pair_reads[2 * j + 1] : -1;
         const int n0 = r0 >= 0 ? p.fcnt[2 * j] : 0, n1 = r1 >= 0 ? p.fcnt[2 * j + 1] : 0;
         int nmax = max(n0, n1), L = r0 >= 0 ? p.rd.info[r0].x : 0;
@@ -512,11 +525,13 @@ k_populate_flank(const PopParams p)
     RowEntry* rows = smem_rows + warp * p.row_stride;
     const int R = p.rd.n;
     constexpr int K = 2 * BAND;
+    if (*p.any_flank_tasks == 0) return;          // the classify pass queued nothing for this kernel
+    const int n_list = 2 * tile_pairs(p);
     for (;;) {
         int li = 0;
         if (lane == 0) li = atomicAdd(p.flank_cursor, 1);
         li = __shfl_sync(0xffffffffu, li, 0);
-        if (li >= 2 * p.n_pairs) break;
+        if (li >= n_list) break;
         const int r = p.pair_reads[li];
         const int n = r >= 0 ? p.gcnt[li] : 0;
         if (n == 0) continue;
@@ -556,14 +571,10 @@ k_populate_flank(const PopParams p)
 // With FASTQ it is the classify pass of the fast path instead: the same candidate walk over the fast work list (the pair
 // list, entries may be -1), but score-only DP candidates are appended to the read's task list for k_populate_fast.
 template <int MAXK, bool FASTQ>
-__global__ void k_populate_generic(const PopParams p)
+__device__ __forceinline__ void populate_one_pair(const PopParams& p, const int li, const int h)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int H = p.hp.n, R = p.rd.n;
-    const int n_list = FASTQ ? 2 * p.n_pairs : p.n_generic;
-    if (i >= (long long)n_list * H) return;
-    const int li = (int)(i / H);
-    const int r = FASTQ ? p.pair_reads[li] : p.generic_reads[li], h = (int)(i % H);
+    const int r = FASTQ ? p.pair_reads[li] : p.generic_reads[li];
     if (r < 0) return;
     const bool rev = p.rd.reverse[r] != 0;
     const HapView hv = hap_view(p.hp, h, rev);
@@ -614,10 +625,21 @@ __global__ void k_populate_generic(const PopParams p)
                 const int slot = list_append_slot(p.gcnt, li);
                 if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
                 else atomicOr(p.flags, 8);
+                *p.any_flank_tasks = 1;
             } else push_slow(p, r, h, v);
         }
     }
     if (best != kBestInf) atomicMin(p.best + (size_t)h * R + r, best);
+}
+
+template <int MAXK, bool FASTQ>
+__global__ void k_populate_generic(const PopParams p)
+{
+    const int H = p.hp.n;
+    const int n_list = FASTQ ? 2 * tile_pairs(p) : tile_generic(p);
+    const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step)
+        populate_one_pair<MAXK, FASTQ>(p, (int)(i / H), (int)(i % H));
 }
 
 // Near-flank candidates: traceback DP + flank discount (pair_hmm.hpp:743-764). Grid-stride over the slow queue; each
