@@ -64,6 +64,22 @@ for kw in (dict(map_positions=False, disable_naive_shortcut=True), dict(), dict(
         assert np.array_equal(host, dev), (kw, flanks)
         assert (st == 0).all()
 assert eng.launch_count(total=True) > 100
+# error paths must come back from both worker threads (no chunk may be left waiting for the other's DP event)
+from octopus_b200.api import PhmmError, ShortHaplotypeError
+cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band)
+bad = synth.make_batch("C4", n_reads=9000, n_haps=20)[0]
+bad.gap_open[5] = -3                                                          # penalty outside [0, 127]
+try:
+    eng.populate(cfg, bad, reads); raise SystemExit("invalid penalty not reported")
+except PhmmError as e:
+    assert e.code == -1, e
+short_haps = synth.make_haplotypes(np.random.default_rng(1), 20, 260)         # shorter than a 250 bp read + its band-32 pad
+try:
+    eng.populate(cfg, short_haps, reads); raise SystemExit("short haplotype not reported")
+except ShortHaplotypeError:
+    pass
+host = eng.populate(cfg, haps, reads)                                         # and the engine is still usable afterwards
+assert np.array_equal(host, eng.populate(cfg, haps.to_device("cuda:0"), reads.to_device("cuda:0")).cpu().numpy())
 print("PIPELINE_OK")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     env = dict(os.environ, PHMM_CHUNK_PAIRS="20000")
