@@ -142,7 +142,8 @@ struct Staged {
     DevHaps hp {};
     DevReads rd {};
     long long hap_bases = 0, read_bases = 0;
-    std::vector<long long> hap_off_host, read_off_host;   // offsets on the host (needed for sizes / scheduling)
+    std::vector<long long> hap_off_host;                  // haplotype offsets on the host (sizes, window checks); H + 1 entries
+    long long read_len_min = 0, read_len_max = 0;         // all the host needs to know about the (possibly millions of) reads
 };
 
 int fetch_offsets(phmm_engine* e, const int64_t* off, int n, int space, std::vector<long long>& out)
@@ -173,13 +174,32 @@ int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* r
     }
     int rc;
     if ((rc = fetch_offsets(e, haps->off, haps->n, space, s.hap_off_host)) != PHMM_OK) return rc;
-    if ((rc = fetch_offsets(e, reads->off, reads->n, space, s.read_off_host)) != PHMM_OK) return rc;
+    OffsetSummary rs {};
+    if (space == PHMM_SPACE_HOST) {
+        const int64_t* off = reads->off;
+        long long lo = 1LL << 62, hi = 0;
+        for (int r = 0; r < reads->n; ++r) { const long long len = off[r + 1] - off[r]; lo = std::min(lo, len); hi = std::max(hi, len); }
+        rs.first = off[0]; rs.last = off[reads->n]; rs.len_max = hi; rs.inv_len_min = kOffsetBig - lo;
+    } else {
+        // device-resident offsets: reduce them where they are instead of copying the array back
+        CU(e->scores.ensure(sizeof(OffsetSummary)));
+        CU(cudaMemsetAsync(e->scores.p, 0, sizeof(OffsetSummary), e->stream));
+        k_offsets_summary<<<(unsigned)std::min<long long>(((long long)reads->n + 255) / 256, 1024), 256, 0, e->stream>>>((const long long*)reads->off, reads->n,
+                                                                                                                          e->scores.as<OffsetSummary>());
+        LAUNCHED();
+        CU(cudaMemcpyAsync(&rs, e->scores.p, sizeof(OffsetSummary), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
     s.hap_bases = s.hap_off_host[haps->n];
-    s.read_bases = s.read_off_host[reads->n];
-    if (s.hap_off_host[0] != 0 || s.read_off_host[0] != 0 || s.hap_bases <= 0 || s.read_bases <= 0) {
+    s.read_bases = rs.last;
+    s.read_len_min = kOffsetBig - rs.inv_len_min;
+    s.read_len_max = rs.len_max;
+    if (s.hap_off_host[0] != 0 || rs.first != 0 || s.hap_bases <= 0 || s.read_bases <= 0) {
         e->err = "offset arrays must start at 0 and be increasing";
         return PHMM_ERR_INVALID;
     }
+    if (s.read_len_min < 1) { e->err = "empty read (offsets must be strictly increasing)"; return PHMM_ERR_INVALID; }
+    if (s.read_len_max > (1LL << 30)) { e->err = "read too long"; return PHMM_ERR_INVALID; }
     DevHaps& hp = s.hp;
     DevReads& rd = s.rd;
     hp.n = haps->n; rd.n = reads->n;
@@ -637,14 +657,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     const long long HR = (long long)H * R;
     // Everything from here to the final copy-out is enqueued without waiting for the device: sizes come from upper bounds
     // the host can derive from the offsets, the kernels clip them against the scheduler's device-resident totals.
-    long long len_min = 1LL << 40, len_max = 0;
-    {
-        const long long* off = s.read_off_host.data();
-        for (int r = 0; r < R; ++r) { const long long len = off[r + 1] - off[r]; len_min = std::min(len_min, len); len_max = std::max(len_max, len); }
-    }
-    if (len_min < 1) { e->err = "empty read"; return PHMM_ERR_INVALID; }
-    if (len_max > (1LL << 30)) { e->err = "read too long"; return PHMM_ERR_INVALID; }
-    const int Lmax_all = (int)len_max;
+    const long long len_min = s.read_len_min;
+    const int Lmax_all = (int)s.read_len_max;
     const int Lmax_fast = std::min(Lmax_all, kFastMaxReadLen);
     // distinct read lengths the fast path can see: bounds the padding of the length-bucketed pair list
     const long long len_bins = std::max<long long>(1, std::min<long long>({(long long)R, (long long)Lmax_fast - std::min<long long>(len_min, Lmax_fast) + 1, (long long)kLenBins}));
@@ -749,9 +763,9 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     p.fcap = H * max_dp_per_pair;              // a read's task list: one DP task per (haplotype, candidate position)
     long long reads_per_tile = std::max<long long>(R, 2 * n_pairs);   // one tile unless a budget says otherwise
     if (use_mapper) reads_per_tile = std::max<long long>(2, std::min<long long>(R + 1, (1LL << 30) / (41LL * H)));   // (10 x int32 + 1 byte) per pair
-    if (n_pairs) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (64LL << 20) / p.fcap));
+    if (n_pairs) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (160LL << 20) / p.fcap));   // two lists of 4-byte entries: <= 1.25 GiB
     if (p.use_flanks) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
-    const long long pairs_per_tile = std::max<long long>((long long)groups, (reads_per_tile / 2) / (long long)groups * (long long)groups);
+    const long long pairs_per_tile = std::max<long long>((long long)groups, ((reads_per_tile + 1) / 2 + groups - 1) / (long long)groups * (long long)groups);
     // work-list entries one tile can hold (pair tiles: two per pair, padding entries included)
     const size_t tile_list_cap = (size_t)std::max<long long>(std::min<long long>(2 * pairs_per_tile, 2 * std::max<long long>(n_pairs, groups)), std::min<long long>(reads_per_tile, R)) + 2;
     if (use_mapper) {

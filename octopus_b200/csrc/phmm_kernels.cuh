@@ -58,6 +58,23 @@ __global__ void k_build_tables(const long long n_bases, const char* __restrict__
     tab_r[i] = make_col_entry(seq[i], mask_r[i], pr & 127, o & 127, e & 127);
 }
 
+// What the host needs to know about a device-resident offset array: ends, longest and shortest item (the shortest as
+// kOffsetBig - min so that a zero-initialised struct is the identity of all four atomicMax / store updates).
+constexpr long long kOffsetBig = 1LL << 62;
+struct OffsetSummary { long long first, last, len_max, inv_len_min; };
+__global__ void k_offsets_summary(const long long* __restrict__ off, const int n, OffsetSummary* __restrict__ out)
+{
+    long long hi = 0, inv_lo = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long len = off[i + 1] - off[i];
+        hi = max(hi, len); inv_lo = max(inv_lo, kOffsetBig - len);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); inv_lo = max(inv_lo, __shfl_xor_sync(0xffffffffu, inv_lo, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out->len_max, hi); atomicMax(&out->inv_len_min, inv_lo); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out->first = off[0]; out->last = off[n]; }
+}
+
 // One warp per read: row half-words, length and eligibility flags.
 __global__ void k_read_info(const int n_reads, const long long* __restrict__ off, const char* __restrict__ bases,
                             const uint8_t* __restrict__ quals, uint16_t* __restrict__ rowhalf, int2* __restrict__ info)
@@ -300,6 +317,13 @@ struct PopParams {
     int n_generic;              // tile size (upper bound)
 };
 
+// flat index → (list slot, haplotype); 64-bit division is an expensive software routine, the index nearly always fits 32 bits
+__device__ __forceinline__ void split_index(const long long i, const int H, int* li, int* h)
+{
+    if (i <= 0xFFFFFFFFll) { const unsigned u = (unsigned)i, q = u / (unsigned)H; *li = (int)q; *h = (int)(u - q * (unsigned)H); }
+    else { *li = (int)(i / H); *h = (int)(i % H); }
+}
+
 __device__ __forceinline__ int tile_pairs(const PopParams& p) { return max(0, min(p.n_pairs, p.tot->n_pairs - p.pair_base)); }
 __device__ __forceinline__ int tile_generic(const PopParams& p) { return max(0, min(p.n_generic, p.tot->n_generic - p.generic_base)); }
 
@@ -414,7 +438,8 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, c
     const int n_list = max(0, min(n_list_max, is_pairs ? 2 * (tot->n_pairs - base) : tot->n_generic - base));
     const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const int li = (int)(i / H), h = (int)(i % H);
+    int li, h;
+    split_index(i, H, &li, &h);
     const int r = list[li];
     uint8_t n_out = 0;
     if (r >= 0) {
@@ -638,8 +663,11 @@ __global__ void k_populate_generic(const PopParams p)
     const int H = p.hp.n;
     const int n_list = FASTQ ? 2 * tile_pairs(p) : tile_generic(p);
     const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step)
-        populate_one_pair<MAXK, FASTQ>(p, (int)(i / H), (int)(i % H));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        int li, h;
+        split_index(i, H, &li, &h);
+        populate_one_pair<MAXK, FASTQ>(p, li, h);
+    }
 }
 
 // Near-flank candidates: traceback DP + flank discount (pair_hmm.hpp:743-764). Grid-stride over the slow queue; each
@@ -855,7 +883,8 @@ __global__ void k_epilogue(const int* __restrict__ best, int* __restrict__ statu
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)H * R) return;
-    const int r = (int)(i % R);
+    int hh, r;
+    split_index(i, R, &hh, &r);
     const int b = best[i];
     if (b == kBestInf && status[i] == 0) status[i] = 1;
     out[i] = finish_likelihood(b, use_mapq != 0, mapq[r], mapq_cap, mapq_trigger);
