@@ -219,7 +219,13 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
                 switch (x) { PHMM_REP64(PHMM_CASE_ROW0) default: break; }
             }
         }
-        go_prev = go; ge_prev = ge; e0 = n0; e1 = n1;
+        go_prev = go; ge_prev = ge;
+        // The next column's entries were loaded at the top of this column and must not be waited for before its end.
+        // Left to itself ptxas copies them into e0 / e1 right after issuing the loads (a full L2 round trip per column,
+        // 13 % of the kernel's stall samples in profiles/r01d). z is always 0 — no lane ever has its sign bit set — but
+        // it is only known once the column's last cell is done, which pins the copy behind the column body.
+        const uint32_t z = i_run & 0x80008000u;
+        e0.x = n0.x + z; e0.y = n0.y + z; e1.x = n1.x + z; e1.y = n1.y + z;
     }
 #undef PHMM_CELL
 #undef PHMM_CASE_PROLOGUE
@@ -345,7 +351,10 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
                 }
             }
         }
-        go_prev = goS; ge_prev = geS; e = nx;
+        go_prev = goS; ge_prev = geS;
+        // as in dp_pair: keep the prefetched entry out of `e` until the column is done (bit 17 of an I value is always 0)
+        const uint32_t z = i_run & (2u << 16);
+        e.x = nx.x + z; e.y = nx.y + z;
     }
 #undef PHMM_FCELL
 #undef PHMM_FCASE_PROLOGUE

@@ -976,14 +976,17 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
     if (!e) return PHMM_ERR_INVALID;
     // Pipelined path: host-resident batch, no caller-supplied position lists (a [H][R] CSR cannot be sliced by columns
     // without a pass over it), enough pairs to amortise the per-chunk overheads.
-    static const long long kChunkPairs = [] {
+    static const long long kForcedChunkPairs = [] {
         const char* v = std::getenv("PHMM_CHUNK_PAIRS");          // test hook: force the pipelined path on small batches
         const long long n = v ? std::atoll(v) : 0;
-        return n > 0 ? n : (8LL << 20);
+        return n > 0 ? n : 0LL;
     }();
+    // chunk size: an eighth of the batch, between 2M pairs (below that the per-chunk launch chain shows) and 8M pairs
+    const long long all_pairs = (haps && reads) ? (long long)haps->n * reads->n : 0;
+    const long long kChunkPairs = kForcedChunkPairs ? kForcedChunkPairs : std::max<long long>(2LL << 20, std::min<long long>(8LL << 20, all_pairs / 8));
     const bool can_chunk = !e->is_sub && space == PHMM_SPACE_HOST && haps && reads && cfg && out && haps->n > 0 && reads->n > 1 &&
                            reads->off && reads->mapq && reads->reverse && !(positions && positions->off && positions->pos) &&
-                           (long long)haps->n * reads->n >= 2 * kChunkPairs;
+                           all_pairs >= 2 * kChunkPairs;
     if (!can_chunk) return populate_impl(e, cfg, haps, reads, positions, flank, out, status, space, 0);
     e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
     for (phmm_engine*& sub : e->sub) {
