@@ -236,12 +236,13 @@ def main():
     eng = PairHMMEngine(local)
     d_haps, d_reads = haps.to_device(dev), reads.to_device(dev)
     d_out = torch.empty((H, R), dtype=torch.float64, device=dev)
-    R_total = R * world
+
+    recv = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
 
     def step():
         eng.populate(model_cfg, d_haps, d_reads, flank_state=flank_state, out=d_out)
         if world > 1:
-            return shard.gather_likelihoods(d_out, R_total, world, rank)   # NCCL gather of the slabs to rank 0
+            return shard.gather_slabs(d_out, world, rank, recv=recv)        # NCCL gather of the per-rank matrices to rank 0
         return d_out
 
     def sync_all():

@@ -62,3 +62,19 @@ def gather_likelihoods(local, R_total, world, rank, group=None):
         lo, hi = split_range(R_total, world, k)
         out[:, lo:hi] = recv[k][:, :hi - lo]
     return out
+
+
+def gather_slabs(local, world, rank, recv=None, group=None):
+    """Gather equally-shaped per-rank result matrices to rank 0 as a list (rank order); returns None on the other ranks.
+
+    This is the exchange of the weak-scaling deployment (every rank calls its own regions: the per-rank matrices belong to
+    different haplotype sets and are not columns of one matrix), so nothing is padded or re-assembled: one NCCL gather
+    straight into the receive slabs. ``recv`` lets the caller reuse the world x local-shaped receive buffers."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [local]
+    if rank == 0 and recv is None:
+        recv = [torch.empty_like(local) for _ in range(world)]
+    dist.gather(local.contiguous(), recv if rank == 0 else None, dst=0, group=group)
+    return recv if rank == 0 else None

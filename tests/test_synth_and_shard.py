@@ -62,11 +62,13 @@ H, R = 5, 23
 full = torch.arange(H * R, dtype=torch.float64).reshape(H, R)
 lo, hi = shard.split_range(R, world, rank)
 got = shard.gather_likelihoods(full[:, lo:hi].clone(), R, world, rank)
+slabs = shard.gather_slabs(full * (rank + 1), world, rank)                    # weak-scaling exchange: one matrix per rank
 if rank == 0:
     assert torch.equal(got, full)
+    assert len(slabs) == world and all(torch.equal(slabs[k], full * (k + 1)) for k in range(world))
     print("GATHER_OK")
 else:
-    assert got is None
+    assert got is None and slabs is None
 dist.destroy_process_group()
 """
 
