@@ -304,8 +304,9 @@ def main():
         peak, peak_src = peaks()
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernel per step, from the committed ncu --set full captures
-        # (profiles/r01d_populate_fast_c3_ncu_raw.csv: one of C3's two tile launches; profiles/r01c_*: C2), default sizes only
-        traffic = {("C3", 1_000_000, 128): 2 * (714.1e6 + 238.2e6), ("C2", 100_000, 64): 84.1e6 + 3.0e6}.get((args.config, R, H))
+        # (profiles/r01f_populate_fast_c3_ncu_raw.csv: C3's single launch — 0.51 GB task words + 0.51 GB best[] read for the
+        # atomicMin + tables / rows in, 0.57 GB best[] out; profiles/r01c_*: C2), default sizes only
+        traffic = {("C3", 1_000_000, 128): 1.401e9 + 0.569e9, ("C2", 100_000, 64): 84.1e6 + 3.0e6}.get((args.config, R, H))
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
