@@ -698,7 +698,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(e->kitems.ensure((size_t)s.hap_bases * sizeof(uint16_t)));
         k_read_kmers<<<(unsigned)(((long long)R * 32 + 255) / 256), 256, 0, e->stream>>>(s.read_bases, R, s.rd.off, s.rd.bases, e->rhash.as<uint16_t>());
         LAUNCHED();
-        k_build_kmer_table<<<H, 256, 0, e->stream>>>(H, s.hp.off, s.hp.seq, e->kbins.as<int>(), e->kitems.as<uint16_t>());
+        k_build_kmer_table<<<H, 256, 0, e->stream>>>(H, s.hp.off, s.hp.seq, e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>());
         LAUNCHED();
         CU(cudaGetLastError());
     }
@@ -812,6 +812,19 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
 
     lap("kernel attrs");
+    // k-mer mapper variant: vote-array capacity by the longest haplotype, byte counters when no read can cast > 255 votes
+    const bool mapper_bytes = Lmax_all - kKmer + 1 <= 255;
+    auto launch_mapper = [&](unsigned grid, unsigned block, const int* list, int n_list, int base, int is_pairs) {
+#define PHMM_MAP_ARGS list, n_list, d_tot, base, is_pairs, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>()
+        if (mapper_maxt == 512) {
+            if (mapper_bytes) k_kmer_map<512, uint8_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
+            else k_kmer_map<512, uint16_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
+        } else {
+            if (mapper_bytes) k_kmer_map<2048, uint8_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
+            else k_kmer_map<2048, uint16_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
+        }
+#undef PHMM_MAP_ARGS
+    };
     ChunkOrder chunk_order(e);
     bool timed = false;
     size_t n_timed = 0;
@@ -823,8 +836,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             p.pair_base = (int)p0;
             if (use_mapper) {
                 const long long threads = 2LL * np * H;
-                if (mapper_maxt == 512) k_kmer_map<512><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, d_tot, (int)p0, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
-                else k_kmer_map<2048><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p.pair_reads, 2 * np, d_tot, (int)p0, 1, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                launch_mapper((unsigned)((threads + 127) / 128), 128, p.pair_reads, 2 * np, (int)p0, 1);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
@@ -872,8 +884,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             const long long threads = (long long)ng * H;
             const unsigned ggrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 63) / 64, (long long)e->sm_count * 32));
             if (use_mapper) {
-                if (mapper_maxt == 512) k_kmer_map<512><<<ggrid, 64, 0, e->stream>>>(p.generic_reads, ng, d_tot, (int)g0, 0, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
-                else k_kmer_map<2048><<<ggrid, 64, 0, e->stream>>>(p.generic_reads, ng, d_tot, (int)g0, 0, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<int>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+                launch_mapper(ggrid, 64, p.generic_reads, ng, (int)g0, 0);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }

@@ -388,11 +388,14 @@ __global__ void k_read_kmers(const long long n_bases, const int n_reads, const l
     for (int y = lane; y + kKmer <= L; y += 32) rhash[b + y] = (uint16_t)kmer_hash(bases + b + y);
 }
 
-// populate_kmer_hash_table<6> (:85-98) as CSR per haplotype: bin_start[h][4097], items[hap base offset + ...]. One block per haplotype.
+// populate_kmer_hash_table<6> (:85-98) per haplotype: bins[h][hash] = first item | item count << 16 (both < 2^16: a haplotype
+// the mapper takes has at most 2048 k-mers), items[hap base offset + ...] = k-mer positions, ascending within a bin.
+// One block per haplotype.
 __global__ void k_build_kmer_table(const int H, const long long* __restrict__ off, const char* __restrict__ seq,
-                                   int* __restrict__ bin_start, uint16_t* __restrict__ items)
+                                   uint32_t* __restrict__ bins, uint16_t* __restrict__ items)
 {
     __shared__ int hist[kKmerBins + 1];
+    __shared__ int cursor[kKmerBins];
     const int h = blockIdx.x;
     if (h >= H) return;
     const long long o = off[h];
@@ -401,7 +404,7 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
     __syncthreads();
     for (int i = threadIdx.x; i < nt; i += blockDim.x) atomicAdd(&hist[kmer_hash(seq + o + i) + 1], 1);
     __syncthreads();
-    // exclusive scan of 4096 bins by one warp (chunks of 32 with a running carry)
+    // inclusive scan of the shifted counts by one warp (chunks of 32 with a running carry): hist[b] = k-mers with hash < b
     if (threadIdx.x < 32) {
         int run = 0;
         for (int base = 0; base <= kKmerBins; base += 32) {
@@ -414,57 +417,76 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
         }
     }
     __syncthreads();
-    int* bs = bin_start + (size_t)h * (kKmerBins + 1);
-    for (int i = threadIdx.x; i <= kKmerBins; i += blockDim.x) bs[i] = hist[i];   // hist[b] = number of k-mers with hash < b... (inclusive scan of counts shifted by one)
+    uint32_t* bs = bins + (size_t)h * (kKmerBins + 1);
+    for (int i = threadIdx.x; i < kKmerBins; i += blockDim.x) {
+        bs[i] = (uint32_t)hist[i] | ((uint32_t)(hist[i + 1] - hist[i]) << 16);
+        cursor[i] = hist[i];
+    }
     __syncthreads();
-    // fill: cursor per bin (reuse hist as cursors = bin starts)
+    // fill in ascending position order within a bin: the vote loop relies on nothing but the set, the order keeps runs reproducible
     for (int i = threadIdx.x; i < nt; i += blockDim.x) {
         const unsigned hh = kmer_hash(seq + o + i);
-        const int slot = atomicAdd(&hist[hh], 1);
+        const int slot = atomicAdd(&cursor[hh], 1);
         items[o + slot] = (uint16_t)i;
     }
 }
 
 // map_query_to_target (:120-159) for every (read of the work list, haplotype): the first <= 10 mapping begins (ascending)
-// whose vote count equals the maximum. One thread per pair; the vote counts live in a per-thread local array.
-template <int MAXT>
+// whose vote count equals the maximum. One thread per pair; the vote counts live in a per-thread local array, handled a
+// 32-bit word at a time where possible (clear, final scan). CountT = uint8_t when no diagonal can collect more than 255
+// votes (a diagonal gets at most one vote per query k-mer, so reads of <= 260 bases), else uint16_t.
+template <int MAXT, typename CountT>
 __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int is_pairs,
                            const DevHaps hp, const DevReads rd,
-                           const uint16_t* __restrict__ rhash, const int* __restrict__ bin_start, const uint16_t* __restrict__ items,
+                           const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ bins, const uint16_t* __restrict__ items,
                            int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
 {
+    constexpr int PER = 4 / (int)sizeof(CountT);
     const int H = hp.n;
     // the tile's work list: 2 entries per read pair, or the generic reads; clipped against the scheduler's totals
     const int n_list = max(0, min(n_list_max, is_pairs ? 2 * (tot->n_pairs - base) : tot->n_generic - base));
     const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    int li, h;
-    split_index(i, H, &li, &h);
-    const int r = list[li];
-    uint8_t n_out = 0;
-    if (r >= 0) {
-        const long long ro = rd.off[r], ho = hp.off[h];
-        const int nq = (int)(rd.off[r + 1] - ro) - kKmer + 1, nt = (int)(hp.off[h + 1] - ho) - kKmer + 1;
-        if (nq > 0 && nt > 0 && nt <= MAXT) {
-            uint16_t counts[MAXT];
-            for (int t = 0; t < nt; ++t) counts[t] = 0;
-            const int* bs = bin_start + (size_t)h * (kKmerBins + 1);
-            unsigned max_hit = 0;
-            for (int qi = 0; qi < nq; ++qi) {
-                const unsigned hq = rhash[ro + qi];
-                const int e1 = bs[hq + 1];
-                for (int e = bs[hq]; e < e1; ++e) {
-                    const int ti = items[ho + e];
-                    if (ti >= qi) { const unsigned c = ++counts[ti - qi]; max_hit = c > max_hit ? c : max_hit; }
+        int li, h;
+        split_index(i, H, &li, &h);
+        const int r = list[li];
+        uint8_t n_out = 0;
+        if (r >= 0) {
+            const long long ro = rd.off[r], ho = hp.off[h];
+            const int nq = (int)(rd.off[r + 1] - ro) - kKmer + 1, nt = (int)(hp.off[h + 1] - ho) - kKmer + 1;
+            if (nq > 0 && nt > 0 && nt <= MAXT) {
+                uint32_t words[MAXT / PER];
+                CountT* counts = reinterpret_cast<CountT*>(words);
+                const int nwords = (nt + PER - 1) / PER;
+                for (int w = 0; w < nwords; ++w) words[w] = 0u;
+                const uint32_t* bs = bins + (size_t)h * (kKmerBins + 1);
+                const uint16_t* it = items + ho;
+                unsigned max_hit = 0;
+                for (int qi = 0; qi < nq; ++qi) {
+                    const uint32_t bin = bs[rhash[ro + qi]];
+                    const int e0 = (int)(bin & 0xFFFFu), e1 = e0 + (int)(bin >> 16);
+                    for (int e = e0; e < e1; ++e) {
+                        const int ti = it[e];
+                        if (ti >= qi) { const unsigned c = ++counts[ti - qi]; max_hit = c > max_hit ? c : max_hit; }
+                    }
+                }
+                if (max_hit > 0) {
+                    int32_t* out = kpos + (size_t)i * kMaxMapped;
+                    for (int w = 0; w < nwords && n_out < kMaxMapped; ++w) {
+                        uint32_t v = words[w];
+                        if (v == 0u) continue;
+#pragma unroll
+                        for (int b = 0; b < PER; ++b) {
+                            const unsigned c = v & ((1u << (8 * sizeof(CountT))) - 1u);
+                            v >>= 4 * sizeof(CountT); v >>= 4 * sizeof(CountT);
+                            const int t = w * PER + b;
+                            if (c == max_hit && t < nt && n_out < kMaxMapped) out[n_out++] = t;
+                        }
+                    }
                 }
             }
-            if (max_hit > 0) {
-                int32_t* out = kpos + (size_t)i * kMaxMapped;
-                for (int t = 0; t < nt && n_out < kMaxMapped; ++t) if (counts[t] == max_hit) out[n_out++] = t;
-            }
         }
-    }
-    kcnt[i] = n_out;
+        kcnt[i] = n_out;
     }
 }
 
