@@ -288,26 +288,147 @@ class HaplotypeLikelihoodModel:
 
 
 class HaplotypeLikelihoodArray:
-    """The (haplotype x read) ln-likelihood matrix of one sample (haplotype_likelihood_array.hpp:123)."""
+    """likelihoods_[haplotype][sample][read or template] (haplotype_likelihood_array.hpp:34-175).
+
+    All samples of a populate() go to the GPU as one batch: their reads are concatenated, one engine call fills one
+    [H, R_total] matrix and a sample is a column range of it (views, no copies)."""
 
     mapperKmerSize = 6          # haplotype_likelihood_array.hpp:103
     maxMappingPositions = 10    # :104
 
     def __init__(self, likelihood_model=None, engine=None):
         self.likelihood_model = likelihood_model or HaplotypeLikelihoodModel()
-        self.engine = engine or PairHMMEngine()
-        self.likelihoods = None
+        self._engine = engine
+        self.likelihoods = None     # [H, sum of the samples' widths]
+        self._samples = []
+        self._off = [0]
+        self._primed = None
 
-    def populate(self, reads: ReadBlock, haplotypes: HaplotypeBlock, flank_state=None, positions=None):
-        self.likelihoods = self.engine.populate(self.likelihood_model.config, haplotypes, reads, positions, flank_state)
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = PairHMMEngine()
+        return self._engine
+
+    @staticmethod
+    def _concat_reads(blocks):
+        if len(blocks) == 1:
+            return blocks[0]
+        off = [np.zeros(1, dtype=np.int64)]
+        base = 0
+        for b in blocks:
+            off.append(b.off[1:] + base)
+            base += int(b.off[-1])
+        return ReadBlock(np.concatenate(off), np.concatenate([b.bases for b in blocks]), np.concatenate([b.quals for b in blocks]),
+                         np.concatenate([b.mapq for b in blocks]), np.concatenate([b.reverse for b in blocks]),
+                         np.concatenate([b.begin for b in blocks]))
+
+    def _set_samples(self, names, widths):
+        self._samples = list(names)
+        self._off = [0]
+        for w in widths:
+            self._off.append(self._off[-1] + int(w))
+        self._primed = None
+
+    def populate(self, reads, haplotypes: HaplotypeBlock, flank_state=None, positions=None):
+        """populate(ReadMap, haplotypes, flank_state) (haplotype_likelihood_array.cpp:51-103). ``reads``: a dict
+        {sample: ReadBlock} in sample order, or one ReadBlock (a single unnamed sample, left primed)."""
+        if isinstance(reads, ReadBlock):
+            self._set_samples([""], [reads.n])
+            self.likelihoods = self.engine.populate(self.likelihood_model.config, haplotypes, reads, positions, flank_state)
+            self._primed = 0
+            return self
+        names = list(reads.keys())
+        blocks = [reads[k] for k in names]
+        self._set_samples(names, [b.n for b in blocks])
+        self.likelihoods = self.engine.populate(self.likelihood_model.config, haplotypes, self._concat_reads(blocks), positions, flank_state)
         return self
+
+    def populate_templates(self, templates, haplotypes: HaplotypeBlock, flank_state=None):
+        """populate(TemplateMap, ...) (:105-199). ``templates``: {sample: (ReadBlock, template_off)} — template t of the sample
+        owns its reads [template_off[t], template_off[t+1]); one value per (haplotype, template)."""
+        names = list(templates.keys())
+        blocks, toff, base = [], [np.zeros(1, dtype=np.int64)], 0
+        for k in names:
+            rb, off = templates[k]
+            off = np.asarray(off, dtype=np.int64)
+            assert off[0] == 0 and off[-1] == rb.n, "template offsets must cover the sample's reads"
+            blocks.append(rb)
+            toff.append(off[1:] + base)
+            base += rb.n
+        self._set_samples(names, [len(templates[k][1]) - 1 for k in names])
+        self.likelihoods = self.engine.populate_templates(self.likelihood_model.config, haplotypes, self._concat_reads(blocks),
+                                                          np.concatenate(toff), flank_state)
+        return self
+
+    # -- accessors (haplotype_likelihood_array.cpp:200-291) ----------------------------------------------------
+    def samples(self):
+        return list(self._samples)
+
+    def _sample_index(self, sample):
+        try:
+            return self._samples.index(sample)
+        except ValueError:
+            raise KeyError(sample) from None      # the reference's unordered_map::at
+
+    def num_likelihoods(self, sample=None):
+        s = self._primed_index() if sample is None else self._sample_index(sample)
+        return self._off[s + 1] - self._off[s]
+
+    def __call__(self, sample, haplotype_index):
+        s = self._sample_index(sample)
+        return self.likelihoods[haplotype_index, self._off[s]:self._off[s + 1]]
+
+    def __getitem__(self, haplotype_index):
+        """likelihoods_[haplotype][primed sample] (:224-236)."""
+        s = self._primed_index()
+        return self.likelihoods[haplotype_index, self._off[s]:self._off[s + 1]]
+
+    def extract_sample(self, sample):
+        s = self._sample_index(sample)
+        return self.likelihoods[:, self._off[s]:self._off[s + 1]]
 
     def is_empty(self):
         return self.likelihoods is None
 
     def clear(self):
         self.likelihoods = None
+        self._set_samples([], [])
 
-    def __getitem__(self, haplotype_index):
-        """likelihoods_[haplotype][sample] (haplotype_likelihood_array.cpp:212-236)."""
-        return self.likelihoods[haplotype_index]
+    def is_primed(self):
+        return self._primed is not None
+
+    def prime(self, sample):
+        self._primed = self._sample_index(sample)
+
+    def unprime(self):
+        self._primed = None
+
+    def _primed_index(self):
+        if self._primed is None:
+            raise RuntimeError("HaplotypeLikelihoodArray is not primed")      # an assert in the reference
+        return self._primed
+
+    def reset(self, haplotypes_to_keep):
+        """reset(haplotypes) (:331-360): keep a subset of the haplotypes, given by their ascending old indices."""
+        keep = [int(h) for h in haplotypes_to_keep]
+        if not keep:
+            self.clear()
+            return
+        assert all(a < b for a, b in zip(keep, keep[1:])) and 0 <= keep[0] and keep[-1] < self.likelihoods.shape[0]
+        self.likelihoods = self.likelihoods[keep]
+
+    def merge_samples(self, samples=None, new_sample=None):
+        """merge_samples (:362-409): a one-sample array holding the chosen samples' likelihoods back to back; primed."""
+        samples = self.samples() if samples is None else list(samples)
+        idx = [self._sample_index(s) for s in samples]
+        out = HaplotypeLikelihoodArray(self.likelihood_model, self._engine)
+        parts = [self.likelihoods[:, self._off[s]:self._off[s + 1]] for s in idx]
+        if isinstance(self.likelihoods, np.ndarray):
+            out.likelihoods = np.concatenate(parts, axis=1)
+        else:                                                   # device-resident matrix (torch tensor)
+            import torch
+            out.likelihoods = torch.cat(parts, dim=1)
+        out._set_samples(["".join(samples) if new_sample is None else new_sample], [out.likelihoods.shape[1]])
+        out._primed = 0
+        return out

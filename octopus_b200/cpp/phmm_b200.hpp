@@ -15,10 +15,13 @@
 #ifndef PHMM_B200_HPP
 #define PHMM_B200_HPP
 
+#include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "phmm_b200.h"
@@ -236,6 +239,16 @@ struct ReadBlock   // AlignedRead fields on the path (basics/aligned_read.hpp:36
         begin.push_back(mapped_begin);
         off.push_back(static_cast<std::int64_t>(bases.size()));
     }
+    void append(const ReadBlock& other)
+    {
+        const auto base = static_cast<std::int64_t>(bases.size());
+        bases += other.bases;
+        quals.insert(quals.end(), other.quals.begin(), other.quals.end());
+        mapq.insert(mapq.end(), other.mapq.begin(), other.mapq.end());
+        reverse.insert(reverse.end(), other.reverse.begin(), other.reverse.end());
+        begin.insert(begin.end(), other.begin.begin(), other.begin.end());
+        for (std::size_t i = 1; i < other.off.size(); ++i) off.push_back(base + other.off[i]);
+    }
     std::size_t size() const noexcept { return off.size() - 1; }
     phmm_reads view() const noexcept
     {
@@ -243,13 +256,41 @@ struct ReadBlock   // AlignedRead fields on the path (basics/aligned_read.hpp:36
     }
 };
 
+struct TemplateBlock   // AlignedTemplate containers: template t owns the reads [off[t], off[t+1]) (basics/aligned_template.hpp)
+{
+    ReadBlock reads;
+    std::vector<std::int64_t> off {0};
+    void add(const ReadBlock& template_reads) { reads.append(template_reads); off.push_back(static_cast<std::int64_t>(reads.size())); }
+    std::size_t size() const noexcept { return off.size() - 1; }
+};
+
 struct FlankState { std::int64_t lhs_flank, rhs_flank; };   // HaplotypeLikelihoodModel::FlankState
 
+using SampleName = std::string;
+
+// A read-only view of one likelihoods_[haplotype][sample] vector (the reference returns const std::vector<double>&).
+struct LikelihoodSpan
+{
+    const double* first = nullptr;
+    std::size_t count = 0;
+    const double* begin() const noexcept { return first; }
+    const double* end() const noexcept { return first + count; }
+    std::size_t size() const noexcept { return count; }
+    bool empty() const noexcept { return count == 0; }
+    double operator[](std::size_t i) const noexcept { return first[i]; }
+    operator std::vector<double>() const { return std::vector<double>(first, first + count); }
+};
+
+// HaplotypeLikelihoodArray (haplotype_likelihood_array.hpp:34-175): likelihoods_[haplotype][sample][read or template].
+// All samples of a populate() go to the GPU as ONE batch (their reads are concatenated; one phmm_populate call fills one
+// [H][R_total] matrix), a sample is a column range of that matrix.
 class HaplotypeLikelihoodArray
 {
 public:
     using LogProbability = double;
     using LikelihoodVector = std::vector<LogProbability>;
+    using ReadMap = std::vector<std::pair<SampleName, ReadBlock>>;                 // config/common.hpp:33-37, in sample order
+    using TemplateMap = std::vector<std::pair<SampleName, TemplateBlock>>;
 
     explicit HaplotypeLikelihoodArray(phmm_config config, Engine engine = Engine {}) : engine_ {std::move(engine)}, config_ {config}
     {
@@ -257,40 +298,148 @@ public:
     }
     static phmm_config default_config() noexcept { phmm_config c; phmm_default_config(&c); return c; }
 
-    // haplotype_likelihood_array.cpp:51-103. positions: optional candidate mapping positions (CSR over [H][R]); flank: optional.
+    // populate(const ReadMap&, haplotypes, flank_state) — haplotype_likelihood_array.cpp:51-103.
+    // positions: optional candidate mapping positions (CSR over [H][R_total]); without them the device k-mer mapper runs
+    // (config.map_positions), as the reference maps inline (:89-92).
+    void populate(const ReadMap& reads, const HaplotypeBlock& haplotypes, const FlankState* flank_state = nullptr,
+                  const phmm_positions* positions = nullptr)
+    {
+        ReadBlock all;
+        begin_samples(reads.size());
+        for (const auto& p : reads) { add_sample(p.first, p.second.size()); all.append(p.second); }
+        run(all, nullptr, haplotypes, flank_state, positions);
+    }
+    // single unnamed sample, primed (what the reference's single-sample callers see after prime())
     void populate(const ReadBlock& reads, const HaplotypeBlock& haplotypes, const FlankState* flank_state = nullptr,
                   const phmm_positions* positions = nullptr)
     {
-        const auto hv = haplotypes.view();
-        const auto rv = reads.view();
-        num_reads_ = reads.size();
-        likelihoods_.assign(haplotypes.size() * reads.size(), 0.0);
-        std::vector<std::int32_t> status(likelihoods_.size(), 0);
-        phmm_flank_state fs {flank_state ? 1 : 0, flank_state ? flank_state->lhs_flank : 0, flank_state ? flank_state->rhs_flank : 0};
-        const int rc = phmm_populate(engine_.get(), &config_, &hv, &rv, positions, &fs, likelihoods_.data(), status.data(), PHMM_SPACE_HOST);
-        if (rc == PHMM_ERR_SHORT_HAPLOTYPE) {
-            for (std::size_t i = 0; i < status.size(); ++i) {
-                if ((status[i] & 0xFFFF) == PHMM_STATUS_SHORT_HAP) throw ShortHaplotypeError {i / num_reads_, static_cast<unsigned>(status[i] >> 16)};
-            }
-        }
-        engine_.check(rc);
+        begin_samples(1);
+        add_sample(SampleName {}, reads.size());
+        run(reads, nullptr, haplotypes, flank_state, positions);
+        primed_ = 0;
     }
-    // likelihoods_[haplotype][sample] for the single sample (haplotype_likelihood_array.cpp:212-236)
-    LikelihoodVector operator[](std::size_t haplotype_index) const
+    // populate(const TemplateMap&, ...) — haplotype_likelihood_array.cpp:105-199: one value per (haplotype, template)
+    void populate(const TemplateMap& templates, const HaplotypeBlock& haplotypes, const FlankState* flank_state = nullptr)
     {
-        const auto first = likelihoods_.begin() + static_cast<std::ptrdiff_t>(haplotype_index * num_reads_);
-        return LikelihoodVector(first, first + static_cast<std::ptrdiff_t>(num_reads_));
+        ReadBlock all;
+        std::vector<std::int64_t> template_off {0};
+        begin_samples(templates.size());
+        for (const auto& p : templates) {
+            add_sample(p.first, p.second.size());
+            const auto base = static_cast<std::int64_t>(all.size());
+            all.append(p.second.reads);
+            for (std::size_t t = 1; t < p.second.off.size(); ++t) template_off.push_back(base + p.second.off[t]);
+        }
+        run(all, &template_off, haplotypes, flank_state, nullptr);
     }
-    const double* data() const noexcept { return likelihoods_.data(); }
-    std::size_t num_likelihoods() const noexcept { return num_reads_; }
+
+    // accessors (haplotype_likelihood_array.cpp:200-291)
+    std::size_t num_likelihoods(const SampleName& sample) const { return width(sample_index(sample)); }
+    std::size_t num_likelihoods() const { return width(primed()); }
+    LikelihoodSpan operator()(const SampleName& sample, std::size_t haplotype_index) const { return span(haplotype_index, sample_index(sample)); }
+    LikelihoodSpan operator[](std::size_t haplotype_index) const { return span(haplotype_index, primed()); }
+    const std::vector<SampleName>& samples() const noexcept { return samples_; }
+    std::size_t num_haplotypes() const noexcept { return num_haplotypes_; }
+    std::vector<LikelihoodVector> extract_sample(const SampleName& sample) const
+    {
+        const auto s = sample_index(sample);
+        std::vector<LikelihoodVector> result;
+        for (std::size_t h = 0; h < num_haplotypes_; ++h) result.push_back(span(h, s));
+        return result;
+    }
     bool is_empty() const noexcept { return likelihoods_.empty(); }
-    void clear() noexcept { likelihoods_.clear(); num_reads_ = 0; }
+    void clear() noexcept { likelihoods_.clear(); samples_.clear(); sample_off_.assign(1, 0); num_haplotypes_ = 0; unprime(); }
+    bool is_primed() const noexcept { return primed_ >= 0; }
+    void prime(const SampleName& sample) const { primed_ = static_cast<std::ptrdiff_t>(sample_index(sample)); }
+    void unprime() const noexcept { primed_ = -1; }
+
+    // reset(haplotypes) (:331-360): keep a subset of the haplotypes — here by their (ascending) old indices
+    void reset(const std::vector<std::size_t>& haplotypes_to_keep)
+    {
+        if (haplotypes_to_keep.empty()) { clear(); return; }
+        const std::size_t w = total_width();
+        std::size_t dst = 0, prev = 0;
+        for (const std::size_t h : haplotypes_to_keep) {
+            if (h >= num_haplotypes_ || (dst > 0 && h <= prev)) throw std::invalid_argument {"reset: haplotype indices must be ascending and in range"};
+            if (h != dst) std::copy_n(likelihoods_.begin() + static_cast<std::ptrdiff_t>(h * w), w, likelihoods_.begin() + static_cast<std::ptrdiff_t>(dst * w));
+            prev = h; ++dst;
+        }
+        num_haplotypes_ = dst;
+        likelihoods_.resize(dst * w);
+    }
+    // merge_samples (:362-409): one sample holding the chosen samples' likelihoods back to back; the result is primed
+    HaplotypeLikelihoodArray merge_samples(const std::vector<SampleName>& samples, const SampleName* new_sample = nullptr) const
+    {
+        SampleName name;
+        if (new_sample) name = *new_sample; else for (const auto& s : samples) name += s;
+        HaplotypeLikelihoodArray result {config_, engine_};
+        std::vector<std::size_t> idx;
+        std::size_t total = 0;
+        for (const auto& s : samples) { idx.push_back(sample_index(s)); total += width(idx.back()); }
+        result.begin_samples(1);
+        result.add_sample(name, total);
+        result.num_haplotypes_ = num_haplotypes_;
+        result.likelihoods_.resize(num_haplotypes_ * total);
+        auto dst = result.likelihoods_.begin();
+        for (std::size_t h = 0; h < num_haplotypes_; ++h) {
+            for (const std::size_t s : idx) { const auto src = span(h, s); dst = std::copy(src.begin(), src.end(), dst); }
+        }
+        result.primed_ = 0;
+        return result;
+    }
+    HaplotypeLikelihoodArray merge_samples(const SampleName* new_sample = nullptr) const { return merge_samples(samples_, new_sample); }
+
+    const double* data() const noexcept { return likelihoods_.data(); }   // [haplotype][all samples' columns], row-major
 
 private:
     Engine engine_;
     phmm_config config_;
     std::vector<double> likelihoods_;
-    std::size_t num_reads_ = 0;
+    std::vector<SampleName> samples_;
+    std::vector<std::size_t> sample_off_ {0};
+    std::size_t num_haplotypes_ = 0;
+    mutable std::ptrdiff_t primed_ = -1;
+
+    void begin_samples(std::size_t n) { samples_.clear(); samples_.reserve(n); sample_off_.assign(1, 0); unprime(); }
+    void add_sample(const SampleName& name, std::size_t n) { samples_.push_back(name); sample_off_.push_back(sample_off_.back() + n); }
+    std::size_t total_width() const noexcept { return sample_off_.back(); }
+    std::size_t width(std::size_t s) const noexcept { return sample_off_[s + 1] - sample_off_[s]; }
+    std::size_t sample_index(const SampleName& sample) const
+    {
+        for (std::size_t s = 0; s < samples_.size(); ++s) if (samples_[s] == sample) return s;
+        throw std::out_of_range {"HaplotypeLikelihoodArray: unknown sample " + sample};   // the reference's unordered_map::at
+    }
+    std::size_t primed() const
+    {
+        if (primed_ < 0) throw std::logic_error {"HaplotypeLikelihoodArray: not primed"};   // an assert in the reference
+        return static_cast<std::size_t>(primed_);
+    }
+    LikelihoodSpan span(std::size_t h, std::size_t s) const
+    {
+        if (h >= num_haplotypes_) throw std::out_of_range {"HaplotypeLikelihoodArray: haplotype index"};
+        return LikelihoodSpan {likelihoods_.data() + h * total_width() + sample_off_[s], width(s)};
+    }
+    void run(const ReadBlock& reads, const std::vector<std::int64_t>* template_off, const HaplotypeBlock& haplotypes,
+             const FlankState* flank_state, const phmm_positions* positions)
+    {
+        const auto hv = haplotypes.view();
+        const auto rv = reads.view();
+        num_haplotypes_ = haplotypes.size();
+        likelihoods_.assign(num_haplotypes_ * total_width(), 0.0);
+        if (num_haplotypes_ == 0 || reads.size() == 0) return;
+        std::vector<std::int32_t> status(num_haplotypes_ * reads.size(), 0);
+        phmm_flank_state fs {flank_state ? 1 : 0, flank_state ? flank_state->lhs_flank : 0, flank_state ? flank_state->rhs_flank : 0};
+        const int rc = template_off
+            ? phmm_populate_templates(engine_.get(), &config_, &hv, &rv, template_off->data(), static_cast<std::int32_t>(template_off->size() - 1),
+                                      positions, &fs, likelihoods_.data(), status.data(), PHMM_SPACE_HOST)
+            : phmm_populate(engine_.get(), &config_, &hv, &rv, positions, &fs, likelihoods_.data(), status.data(), PHMM_SPACE_HOST);
+        if (rc == PHMM_ERR_SHORT_HAPLOTYPE) {
+            for (std::size_t i = 0; i < status.size(); ++i) {
+                if ((status[i] & 0xFFFF) == PHMM_STATUS_SHORT_HAP) throw ShortHaplotypeError {i / reads.size(), static_cast<unsigned>(status[i] >> 16)};
+            }
+        }
+        engine_.check(rc);
+    }
 };
 
 } // namespace octopus_b200

@@ -39,6 +39,39 @@ int main()
         HaplotypeLikelihoodArray arr {cfg};
         arr.populate(reads, haps);
         for (std::size_t h = 0; h < 2; ++h) { const auto row = arr[h]; std::printf("ROW %zu %.17g %.17g\n", h, row[0], row[1]); }
+        {   // multi-sample container semantics (haplotype_likelihood_array.cpp:200-409): samples are column ranges of one batch
+            ReadBlock r0, r1;
+            r0.add(h0.substr(30, 40), std::vector<std::uint8_t>(40, 30), 60, false, 30);
+            r1.add(h1.substr(35, 40), std::vector<std::uint8_t>(40, 25), 60, true, 35);
+            r1.add(h0.substr(30, 40), std::vector<std::uint8_t>(40, 30), 60, false, 30);
+            HaplotypeLikelihoodArray multi {cfg};
+            multi.populate(HaplotypeLikelihoodArray::ReadMap {{"S1", r0}, {"S2", r1}}, haps);
+            bool ok = multi.samples().size() == 2 && multi.num_likelihoods("S1") == 1 && multi.num_likelihoods("S2") == 2 && !multi.is_primed();
+            for (std::size_t h = 0; h < 2; ++h) {
+                ok = ok && multi("S1", h)[0] == arr[h][0] && multi("S2", h)[0] == arr[h][1] && multi("S2", h)[1] == arr[h][0];
+            }
+            multi.prime("S2");
+            ok = ok && multi.is_primed() && multi.num_likelihoods() == 2 && multi[1][0] == arr[1][1];
+            const auto merged = multi.merge_samples();
+            ok = ok && merged.samples().size() == 1 && merged.samples()[0] == "S1S2" && merged.is_primed() && merged.num_likelihoods() == 3 &&
+                 merged[0][0] == arr[0][0] && merged[0][1] == arr[0][1] && merged[1][2] == arr[1][0];
+            const auto only2 = multi.merge_samples({"S2"});
+            ok = ok && only2.num_likelihoods() == 2 && only2[1][0] == arr[1][1];
+            ok = ok && multi.extract_sample("S1").size() == 2 && multi.extract_sample("S1")[1][0] == arr[1][0];
+            multi.reset({1});
+            ok = ok && multi.num_haplotypes() == 1 && multi("S1", 0)[0] == arr[1][0];
+            bool threw = false;
+            try { multi("nope", 0); } catch (const std::out_of_range&) { threw = true; }
+            // TemplateMap: a template's value is the sum of its reads' values (haplotype_likelihood_model.cpp:306-320)
+            TemplateBlock tb;
+            tb.add(reads);                  // one template holding both reads
+            tb.add(r0);                     // and one holding the first read alone
+            HaplotypeLikelihoodArray tarr {cfg};
+            tarr.populate(HaplotypeLikelihoodArray::TemplateMap {{"S1", tb}}, haps);
+            tarr.prime("S1");
+            for (std::size_t h = 0; h < 2; ++h) ok = ok && tarr.num_likelihoods() == 2 && tarr[h][0] == arr[h][0] + arr[h][1] && tarr[h][1] == arr[h][0];
+            std::printf("SAMPLES %s %s\n", ok ? "ok" : "MISMATCH", threw ? "throws" : "nothrow");
+        }
         // ShortHaplotypeError must surface as the reference's exception type
         ReadBlock longread;
         longread.add(h0.substr(0, 95), std::vector<std::uint8_t>(95, 30), 60, false, 0);

@@ -41,3 +41,4 @@ def test_cpp_client_matches_oracle(coracle):
             got = float(lines["ROW%d" % hi][2 + ri])
             assert st == 0 and abs(got - want) <= 1e-4 * max(abs(want), 1e-300)
     assert lines["SHORT"][1].startswith("hap=0")
+    assert lines["SAMPLES"][1:] == ["ok", "throws"]          # multi-sample / template container semantics of the C++ adapter

@@ -318,3 +318,27 @@ def test_populate_templates_sums_the_reads_of_each_template(engine, coracle):
             want[:, t] = want[:, t] + per_read[:, r]
     ok, worst = _close(got, want)
     assert rc == 0 and ok, worst
+
+
+def test_multi_sample_array_is_one_batch_with_per_sample_views(engine, coracle):
+    """HaplotypeLikelihoodArray::populate(ReadMap) over several samples: one engine call on the concatenated reads; each
+    sample's likelihoods_[h][sample] equals the oracle's values for that sample's reads; prime / merge_samples follow
+    haplotype_likelihood_array.cpp:200-409."""
+    from octopus_b200 import HaplotypeLikelihoodArray, HaplotypeLikelihoodModel, synth, shard
+    haps, reads, band = synth.make_batch("C2", n_reads=700, n_haps=9)
+    parts = {"NA1": shard.shard_reads(reads, 3, 0)[0], "NA2": shard.shard_reads(reads, 3, 1)[0], "NA3": shard.shard_reads(reads, 3, 2)[0]}
+    model = HaplotypeLikelihoodModel(HaplotypeLikelihoodModel.Config(max_indel_error=band))
+    before = engine.launch_count(total=True)
+    arr = HaplotypeLikelihoodArray(model, engine).populate(parts, haps, flank_state=(40, 40))
+    one_call = engine.launch_count(total=True) - before
+    rc, want, _ = coracle.populate(band, haps, reads, None, (40, 40), map_positions=True)
+    assert rc == 0 and arr.samples() == ["NA1", "NA2", "NA3"]
+    lo = 0
+    for name, block in parts.items():
+        ok, worst = _close(arr.extract_sample(name), want[:, lo:lo + block.n])
+        assert ok, (name, worst)
+        lo += block.n
+    merged = arr.merge_samples()
+    assert merged.is_primed() and merged.num_likelihoods() == reads.n and _close(np.stack([merged[h] for h in range(haps.n)]), want)[0]
+    engine.populate(model.config, haps, reads, flank_state=(40, 40))
+    assert one_call == engine.launch_count()          # the three samples cost exactly one populate call's launches
