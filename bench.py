@@ -182,6 +182,11 @@ def cpu_reference_run(haps, reads, band, n_sample_reads, threads):
     return cells / dt / 1e9, dt, "port", "scalar C restatement", cells
 
 
+def workload_name(config, R, lens, H, hap_len, band):
+    return ("%s per GPU: %d reads (L=%s) x %d haplotypes (%d bp), band=%d, one mapping position per pair, "
+            "naive shortcut disabled (every pair runs the DP), mapq mixing on, double [H][R] out" % (config, R, lens, H, hap_len, band))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -202,8 +207,10 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "%s: %d-read sample x %d haplotypes, L=%s, hap_len=%d, band=%d, one mapping position per pair, DP only"
-                                   % (args.config, n_sample, haps.n, "/".join(map(str, cfg["read_lens"])), cfg["hap_len"], band)},
+            # the same workload as the GPU arm (same generator, shapes, band and mode); each step times a bounded sample of it
+            "config": {"workload": workload_name(args.config, args.reads or cfg["n_reads"], "/".join(map(str, cfg["read_lens"])), haps.n, cfg["hap_len"], band),
+                       "sample_reads_per_step": n_sample,
+                       "mode": {"flank_state": None, "naive_shortcut": False, "kmer_mapper": False}},
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": info[0], "sample": "%d reads x %d haplotypes per step; %s" % (n_sample, haps.n, info[1])},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -311,9 +318,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "%s per GPU: %d reads (L=%s) x %d haplotypes (%d bp), band=%d, one mapping position per pair, "
-                                   "naive shortcut disabled (every pair runs the DP), mapq mixing on, double [H][R] out"
-                                   % (args.config, R, "/".join(map(str, cfg["read_lens"])), H, cfg["hap_len"], band),
+            "config": {"workload": workload_name(args.config, R, "/".join(map(str, cfg["read_lens"])), H, cfg["hap_len"], band),
                        "alignments_per_step": H * R * world, "cells_per_step": cells * world,
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
                        "parallelism": "reads sharded over %d rank(s), haplotypes replicated, NCCL gather to rank 0" % world,
