@@ -762,7 +762,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     const int max_dp_per_pair = (p.pos_off || use_mapper) ? 11 : 1;
     p.fcap = H * max_dp_per_pair;              // a read's task list: one DP task per (haplotype, candidate position)
     long long reads_per_tile = std::max<long long>(R, 2 * n_pairs);   // one tile unless a budget says otherwise
-    if (use_mapper) reads_per_tile = std::max<long long>(2, std::min<long long>(R + 1, (1LL << 30) / (41LL * H)));   // (10 x int32 + 1 byte) per pair
+    if (use_mapper) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (1LL << 30) / (41LL * H)));   // (10 x int32 + 1 byte) per pair
     if (n_pairs) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (160LL << 20) / p.fcap));   // two lists of 4-byte entries: <= 1.25 GiB
     if (p.use_flanks) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
     const long long pairs_per_tile = std::max<long long>((long long)groups, ((reads_per_tile + 1) / 2 + groups - 1) / (long long)groups * (long long)groups);
@@ -782,7 +782,10 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         p.gtasks = e->gtasks.as<uint32_t>();
         p.gcnt = p.fcnt + tile_list_cap;
     }
-    const int slow_threads = e->sm_count * 256;
+    // traceback scratch: 1 byte per band cell per resident thread; very long reads get fewer threads instead of more memory
+    const long long bp_per_thread = (long long)(Lmax_all + 1) * (2 * band);
+    const int slow_blocks = (int)std::max<long long>(1, std::min<long long>(e->sm_count, (4LL << 30) / (bp_per_thread * 256)));
+    const int slow_threads = slow_blocks * 256;
     if (p.use_flanks) {
         p.slow_cap = (int)std::min<long long>(slow_budget, (long long)H * max_cand * (long long)tile_list_cap);
         CU(e->slow.ensure((size_t)p.slow_cap * sizeof(int4)));
@@ -898,8 +901,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             g0 += ng;
         }
         if (p.use_flanks) {
-            if (band <= 32) k_slow_flank<64><<<e->sm_count, 256, 0, e->stream>>>(p, e->bp.as<unsigned char>());
-            else k_slow_flank<kGenericMaxDiag><<<e->sm_count, 256, 0, e->stream>>>(p, e->bp.as<unsigned char>());
+            if (band <= 32) k_slow_flank<64><<<slow_blocks, 256, 0, e->stream>>>(p, e->bp.as<unsigned char>());
+            else k_slow_flank<kGenericMaxDiag><<<slow_blocks, 256, 0, e->stream>>>(p, e->bp.as<unsigned char>());
             LAUNCHED();
             CU(cudaMemsetAsync(p.slow_count, 0, sizeof(int), e->stream));
         }
