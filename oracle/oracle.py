@@ -2,6 +2,8 @@
 
 * ``RefKernel``  — the UNMODIFIED reference SIMD kernel compiled into ``oracle/_ref/libref_phmm_<isa>.so``
   (``oracle/ref_driver.cpp``, built by ``oracle/Makefile`` from /root/reference where it lies).
+* ``RefHMM``     — the UNMODIFIED reference layer above the kernel (``hmm::evaluate`` / ``hmm::align`` / band choice) compiled
+  into ``oracle/_ref/libref_hmm.so`` (``oracle/ref_hmm_driver.cpp``).
 * ``COracle``    — the plain-C restatement ``oracle/liboctopus_oracle.so`` (``oracle/phmm_oracle.c``).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
@@ -175,6 +177,58 @@ class RefKernel:
         if rc != 0:
             raise ValueError("unsupported (band, bits)")
         return out
+
+
+class RefHMM:
+    """The UNMODIFIED reference layer above the kernel — hmm::evaluate, hmm::align and the band-choosing PairHMMWrapper
+    (pair_hmm.hpp, simd_pair_hmm_wrapper.hpp) — behind oracle/ref_hmm_driver.cpp (oracle/_ref/libref_hmm.so)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(REF_DIR, "libref_hmm.so")) and "sse4_1" in cpu_flags()
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(REF_DIR, "libref_hmm.so"))
+        self.lib.ref_hmm_band.restype = C.c_int
+        self.lib.ref_hmm_evaluate.restype = C.c_double
+        self.lib.ref_hmm_align.restype = C.c_int
+
+    def band(self, requested, int32=False):
+        return self.lib.ref_hmm_band(int(requested), int(int32))
+
+    def kmer_map(self, query, target, max_positions=10):
+        """utils/kmer_mapper.hpp as HaplotypeLikelihoodArray::populate calls it (K = 6, at most ``max_positions``)."""
+        q, t = _b(query), _b(target)
+        out = (C.c_longlong * max_positions)()
+        n = self.lib.ref_kmer_map(q, len(q) - 1, t, len(t) - 1, int(max_positions), out)
+        return [int(out[i]) for i in range(n)]
+
+    @staticmethod
+    def _common(truth, read, quals, gap_open, gap_extend, snv_mask, snv_prior):
+        t, r, m = _b(truth), _b(read), _b(snv_mask)
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.uint8))
+        go, gop = _i8(gap_open)
+        ge, gep = _i8(gap_extend)
+        pr, prp = _i8(snv_prior)
+        assert len(go) == len(ge) == len(pr) == len(t) - 1 == len(m) - 1 and len(q) == len(r) - 1
+        return (t, len(t) - 1, r, len(r) - 1, q.ctypes.data_as(C.c_void_p)), (gop, gep, m, prp), (t, r, m, q, go, ge, pr)
+
+    def evaluate(self, band, truth, read, quals, offset, gap_open, gap_extend, snv_mask, snv_prior, flanks=(0, 0), nuc_prior=2, int32=False):
+        seqs, model, keep = self._common(truth, read, quals, gap_open, gap_extend, snv_mask, snv_prior)
+        return self.lib.ref_hmm_evaluate(int(band), int(int32), *seqs, C.c_longlong(int(offset)), *model,
+                                         C.c_longlong(int(flanks[0])), C.c_longlong(int(flanks[1])), int(nuc_prior))
+
+    def align(self, band, truth, read, quals, offset, gap_open, gap_extend, snv_mask, snv_prior, flanks=(0, 0), nuc_prior=2, int32=False):
+        """Returns (target_offset, likelihood, cigar_text)."""
+        seqs, model, keep = self._common(truth, read, quals, gap_open, gap_extend, snv_mask, snv_prior)
+        off, lk = C.c_longlong(0), C.c_double(0)
+        cap = 8 * (seqs[3] + 2 * 256) + 64
+        cig = C.create_string_buffer(cap)
+        rc = self.lib.ref_hmm_align(int(band), int(int32), *seqs, C.c_longlong(int(offset)), *model,
+                                    C.c_longlong(int(flanks[0])), C.c_longlong(int(flanks[1])), int(nuc_prior),
+                                    C.byref(off), C.byref(lk), cig, cap)
+        assert rc == 0
+        return off.value, lk.value, cig.value.decode()
 
 
 class _Model(C.Structure):

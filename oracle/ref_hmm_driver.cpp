@@ -1,0 +1,110 @@
+// TEST INFRASTRUCTURE ONLY — never linked into or called from the product path.
+//
+// extern "C" driver around the UNMODIFIED reference layer ABOVE the SIMD kernel, compiled from where it lies:
+//   src/core/models/pairhmm/pair_hmm.hpp           hmm::evaluate (:827-841: try_naive_evaluate :275-319, simd_evaluate :694-782),
+//                                                  hmm::align (:858-874: try_naive_align :321-340, simd_align :784-823, make_cigar :152-188)
+//   src/core/models/pairhmm/simd_pair_hmm_wrapper.hpp   PairHMMWrapper: runtime band / precision choice (:85-88, :209-241)
+//   src/utils/kmer_mapper.hpp                      the candidate-position mapper populate() runs inline
+// pair_hmm.hpp's own includes that need Boost or Octopus's config (basics/cigar_string.hpp, exceptions/*.hpp, utils/maths.hpp,
+// <boost/variant.hpp>) resolve to the minimal stand-ins under oracle/ref_shim/ (each says what it replaces); the reference
+// headers themselves are untouched. Needs -std=c++17 (the boost::variant stand-in is std::variant).
+//
+// Used by tests/ only: it pins oracle/phmm_oracle.c's restatement of hmm::evaluate / hmm::align / the band rounding to the
+// reference's own code, with the MutationModel parameter set HaplotypeLikelihoodModel uses (haplotype_likelihood_model.hpp:106).
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "core/models/pairhmm/pair_hmm.hpp"
+#include "utils/kmer_mapper.hpp"          // self-contained (std only): the K = 6 vote mapper, utils/kmer_mapper.hpp:43-159
+
+namespace {
+
+using namespace octopus::hmm;
+
+struct Inputs
+{
+    std::string truth, target;
+    std::vector<std::uint8_t> quals;
+    PenaltyVector gap_open, gap_extend, snv_priors;
+    NucleotideVector snv_mask;
+    Inputs(const char* truth_, int truth_len, const char* target_, int target_len, const std::uint8_t* quals_,
+           const std::int8_t* go, const std::int8_t* ge, const char* mask, const std::int8_t* prior)
+    : truth(truth_, truth_ + truth_len), target(target_, target_ + target_len), quals(quals_, quals_ + target_len),
+      gap_open(go, go + truth_len), gap_extend(ge, ge + truth_len), snv_priors(prior, prior + truth_len), snv_mask(mask, mask + truth_len) {}
+};
+
+simd::PairHMMWrapper make_hmm(int min_band, int use_int32)
+{
+    return simd::PairHMMWrapper {min_band, use_int32 ? simd::PairHMMWrapper::ScorePrecision::int32 : simd::PairHMMWrapper::ScorePrecision::int16};
+}
+
+} // namespace
+
+extern "C" {
+
+// band the wrapper picks for a request (simd_pair_hmm_wrapper.hpp:209-241), or -1 on TooLargeBandSizeError
+int ref_hmm_band(int min_band, int use_int32)
+{
+    try { return make_hmm(min_band, use_int32).band_size(); }
+    catch (const simd::PairHMMWrapper::TooLargeBandSizeError&) { return -1; }
+}
+
+// hmm::evaluate(truth, target, qualities, target_offset, hmm, MutationModel{...}) — pair_hmm.hpp:827-841
+double ref_hmm_evaluate(int min_band, int use_int32, const char* truth, int truth_len, const char* target, int target_len,
+                        const std::uint8_t* quals, long long target_offset,
+                        const std::int8_t* gap_open, const std::int8_t* gap_extend, const char* snv_mask, const std::int8_t* snv_prior,
+                        long long lhs_flank, long long rhs_flank, int nuc_prior)
+{
+    const Inputs in {truth, truth_len, target, target_len, quals, gap_open, gap_extend, snv_mask, snv_prior};
+    const MutationModel params {in.gap_open, in.gap_extend, in.snv_mask, in.snv_priors, {}, static_cast<std::size_t>(lhs_flank),
+                                static_cast<std::size_t>(rhs_flank), static_cast<short>(nuc_prior)};
+    const auto hmm = make_hmm(min_band, use_int32);
+    return evaluate(in.truth, in.target, in.quals, static_cast<std::size_t>(target_offset), hmm, params);
+}
+
+// hmm::align(truth, target, qualities, target_offset, hmm, MutationModel{...}, result) — pair_hmm.hpp:858-874.
+// cigar: SAM text ("37=1X12=2I98="). Returns 0, or 1 if the text does not fit cigar_cap.
+int ref_hmm_align(int min_band, int use_int32, const char* truth, int truth_len, const char* target, int target_len,
+                  const std::uint8_t* quals, long long target_offset,
+                  const std::int8_t* gap_open, const std::int8_t* gap_extend, const char* snv_mask, const std::int8_t* snv_prior,
+                  long long lhs_flank, long long rhs_flank, int nuc_prior,
+                  long long* out_target_offset, double* out_likelihood, char* cigar, int cigar_cap)
+{
+    const Inputs in {truth, truth_len, target, target_len, quals, gap_open, gap_extend, snv_mask, snv_prior};
+    const MutationModel params {in.gap_open, in.gap_extend, in.snv_mask, in.snv_priors, {}, static_cast<std::size_t>(lhs_flank),
+                                static_cast<std::size_t>(rhs_flank), static_cast<short>(nuc_prior)};
+    const auto hmm = make_hmm(min_band, use_int32);
+    Alignment result {};
+    align(in.truth, in.target, in.quals, static_cast<std::size_t>(target_offset), hmm, params, result);
+    *out_target_offset = static_cast<long long>(result.target_offset);
+    *out_likelihood = result.likelihood;
+    std::string text;
+    for (const auto& op : result.cigar) { text += std::to_string(op.size()); text += static_cast<char>(op.flag()); }
+    if (static_cast<int>(text.size()) + 1 > cigar_cap) return 1;
+    std::memcpy(cigar, text.c_str(), text.size() + 1);
+    return 0;
+}
+
+// The candidate-position mapping HaplotypeLikelihoodArray::populate makes per (read, haplotype)
+// (haplotype_likelihood_array.cpp:76-93): hashes of the read, hash table + vote counts of the haplotype,
+// map_query_to_target(..., maxMappingPositions). Returns the number of positions written.
+int ref_kmer_map(const char* query, int query_len, const char* target, int target_len, int max_positions, long long* out_positions)
+{
+    constexpr unsigned char K = 6;                        // HaplotypeLikelihoodArray::mapperKmerSize (haplotype_likelihood_array.hpp:103)
+    const std::string q(query, query + query_len), t(target, target + target_len);
+    if (q.size() < K || t.size() < K) return 0;           // the reference never maps sequences shorter than a k-mer
+    const auto read_hashes = octopus::compute_kmer_hashes<K>(q);
+    const auto haplotype_hashes = octopus::make_kmer_hash_table<K>(t);
+    auto counts = octopus::init_mapping_counts(haplotype_hashes);
+    std::vector<std::size_t> positions(static_cast<std::size_t>(max_positions));
+    const auto last = octopus::map_query_to_target(read_hashes, haplotype_hashes, counts, positions.begin(), static_cast<std::size_t>(max_positions));
+    const int n = static_cast<int>(last - positions.begin());
+    for (int i = 0; i < n; ++i) out_positions[i] = static_cast<long long>(positions[i]);
+    return n;
+}
+
+} // extern "C"

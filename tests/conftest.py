@@ -27,6 +27,13 @@ def refkernels():
 
 
 @pytest.fixture(scope="session")
+def refhmm(coracle):
+    """The reference's own hmm::evaluate / hmm::align / PairHMMWrapper (oracle/_ref/libref_hmm.so), or None where it was never built."""
+    from oracle.oracle import RefHMM
+    return RefHMM() if RefHMM.available() else None
+
+
+@pytest.fixture(scope="session")
 def kats():
     import json
     with open(os.path.join(ROOT, "tests", "golden", "pair_hmm_kats.json")) as f:

@@ -4,7 +4,7 @@ oracle/_ref (skipped where that build is absent)."""
 import numpy as np
 import pytest
 
-from helpers import random_alignment_case
+from helpers import ACGT, random_alignment_case
 
 C_LN10_DIV_10 = 0.230258509299404568401799145468436420760110148862877297603
 
@@ -161,3 +161,119 @@ def test_model_evaluate_mapping_quality_floor(coracle):
     st, v, ext = coracle.model_evaluate(16, hap[:40], read, q, positions=[], original_pos=5, mapping_quality=60,
                                         gap_open=args["gap_open"][:40], gap_extend=args["gap_extend"][:40], snv_mask=args["snv_mask"][:40], snv_prior=args["snv_prior"][:40])
     assert st == 1 and ext > 0             # ShortHaplotypeError
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The layer above the kernel, pinned to the reference's own code (pair_hmm.hpp, simd_pair_hmm_wrapper.hpp compiled from
+# /root/reference behind oracle/ref_hmm_driver.cpp). The reference has no unit tests for this layer.
+# ---------------------------------------------------------------------------------------------------------------------
+def _hmm_case(rng, hap_len, L, exact_rate=0.25):
+    hap = ACGT[rng.integers(0, 4, hap_len)].copy()
+    if rng.random() < 0.2:
+        hap[rng.integers(0, hap_len)] = ord("N")
+    start = int(rng.integers(0, hap_len - L + 1))
+    read = np.where(hap[start:start + L] == ord("N"), ord("A"), hap[start:start + L]).astype(np.uint8)
+    mode = rng.random()
+    if mode > exact_rate:
+        n_sub = 1 if mode < exact_rate + 0.3 else int(rng.integers(1, 5))
+        for _ in range(n_sub):
+            read[rng.integers(0, L)] = ACGT[rng.integers(0, 4)]
+        if mode > 0.8 and L > 12:                                   # an indel
+            p = int(rng.integers(3, L - 6))
+            read = np.concatenate([read[:p], read[p + 2:], ACGT[rng.integers(0, 4, 2)]]) if rng.random() < 0.5 \
+                else np.concatenate([read[:p], ACGT[rng.integers(0, 4, 2)], read[p:-2]])
+    return dict(hap=hap, read=read, start=start, quals=rng.integers(2, 42, L).astype(np.uint8),
+                go=rng.integers(3, 46, hap_len).astype(np.int8), ge=rng.integers(1, 11, hap_len).astype(np.int8),
+                mask=np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, hap_len)].copy(),
+                prior=rng.integers(1, 126, hap_len).astype(np.int8))
+
+
+def test_band_choice_matches_reference_wrapper(refhmm):
+    """simd_pair_hmm_wrapper.hpp:209-241: smallest of 8, 16, ..., 256 that covers the request; beyond 256 it throws."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    for req in list(range(1, 70)) + [127, 128, 129, 255, 256, 257, 1000]:
+        want = next((b for b in (8, 16, 32, 64, 128, 256) if req <= b), -1)
+        assert refhmm.band(req) == want and refhmm.band(req, int32=True) == want
+
+
+def test_c_restatement_evaluate_matches_reference_hmm_evaluate(coracle, refhmm):
+    """oracle_evaluate (naive shortcuts, window placement, flank-aware discount, lowest() on out-of-range) against the
+    reference's own hmm::evaluate with the MutationModel, over seeded cases that hit every branch."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    rng = np.random.default_rng(20240923)
+    kinds = {0: 0, 1: 0, 2: 0}
+    n_lowest = 0
+    for it in range(1500):
+        band_req = int(rng.choice([3, 8, 12, 16, 30]))
+        band = next(b for b in (8, 16, 32) if band_req <= b)
+        L = int(rng.integers(8, 60))
+        hap_len = int(rng.integers(L + 2 * band + 2, L + 2 * band + 90))
+        c = _hmm_case(rng, hap_len, L)
+        # mostly the true position (+- a few bases), sometimes anywhere — including offsets whose window leaves the haplotype
+        off = int(np.clip(c["start"] + rng.integers(-3, 4), 0, hap_len - 1)) if rng.random() < 0.8 else int(rng.integers(0, hap_len))
+        flanks = (0, 0) if rng.random() < 0.4 else (int(rng.integers(0, hap_len // 2)), int(rng.integers(0, hap_len // 2)))
+        want = refhmm.evaluate(band_req, c["hap"], c["read"], c["quals"], off, c["go"], c["ge"], c["mask"], c["prior"], flanks)
+        got, used, raw = coracle.evaluate(band, c["hap"], c["read"], c["quals"], off, c["go"], c["ge"], 2, c["mask"], c["prior"],
+                                          flanks=flanks, details=True)
+        assert got == want or abs(got - want) <= 1e-12 * abs(want), (it, band, L, hap_len, off, flanks, got, want, used, raw)
+        kinds[used] += 1
+        n_lowest += want < -1e300
+    assert min(kinds.values()) > 50 and n_lowest > 5, (kinds, n_lowest)      # shortcut, score-only DP, traceback + flank DP, lowest()
+
+
+def test_c_restatement_align_matches_reference_hmm_align(coracle, refhmm):
+    """oracle_model_align at a single in-range mapping position == the reference's hmm::align there: offset, likelihood, CIGAR."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    rng = np.random.default_rng(77)
+    n_indel = 0
+    for it in range(600):
+        band = int(rng.choice([8, 16]))
+        L = int(rng.integers(10, 50))
+        hap_len = int(rng.integers(L + 2 * band + 2, L + 2 * band + 60))
+        c = _hmm_case(rng, hap_len, L, exact_rate=0.15)
+        pos = int(np.clip(c["start"] + rng.integers(-2, 3), band, hap_len - L - band))
+        flanks = (0, 0) if rng.random() < 0.5 else (int(rng.integers(0, hap_len // 3)), int(rng.integers(0, hap_len // 3)))
+        w_off, w_lk, w_cigar = refhmm.align(band, c["hap"], c["read"], c["quals"], pos, c["go"], c["ge"], c["mask"], c["prior"], flanks)
+        st, g_off, g_lk, g_cigar, _ = coracle.model_align(band, c["hap"], c["read"], c["quals"], c["go"], c["ge"], c["mask"], c["prior"],
+                                                          [pos], pos, flanks=flanks, use_mapping_quality=False)
+        assert st == 0 and (g_off, g_cigar) == (w_off, w_cigar) and abs(g_lk - w_lk) <= 1e-12 * max(abs(w_lk), 1e-300), \
+            (it, band, L, pos, flanks, (g_off, g_lk, g_cigar), (w_off, w_lk, w_cigar))
+        n_indel += ("I" in w_cigar) or ("D" in w_cigar)
+    assert n_indel > 20
+
+
+def test_c_restatement_kmer_mapper_matches_reference_mapper(coracle, refhmm):
+    """oracle_kmer_map against utils/kmer_mapper.hpp itself (compiled from /root/reference), called the way
+    HaplotypeLikelihoodArray::populate calls it: repeats (many tied diagonals), non-ACGT bases, reads longer than the
+    haplotype, sequences shorter than a k-mer, more than ten maximal diagonals."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    rng = np.random.default_rng(4242)
+    n_multi = n_trunc = 0
+    for it in range(1500):
+        kind = rng.random()
+        tl = int(rng.integers(3, 400))
+        if kind < 0.3:                       # low-complexity target: tandem repeat of a short unit
+            unit = ACGT[rng.integers(0, 4, int(rng.integers(1, 7)))]
+            target = np.tile(unit, tl // len(unit) + 1)[:tl].copy()
+        else:
+            target = ACGT[rng.integers(0, 4, tl)].copy()
+        if rng.random() < 0.2 and tl > 0:
+            target[rng.integers(0, tl)] = ord("N")
+        ql = int(rng.integers(3, 180))
+        if kind < 0.85 and tl > ql:
+            s = int(rng.integers(0, tl - ql + 1))
+            query = target[s:s + ql].copy()
+            for _ in range(int(rng.integers(0, 4))):
+                query[rng.integers(0, ql)] = ACGT[rng.integers(0, 4)]
+        else:
+            query = ACGT[rng.integers(0, 4, ql)].copy()
+        want = refhmm.kmer_map(query, target, 10)
+        got = coracle.kmer_map(query.tobytes().decode(), target.tobytes().decode(), 10)
+        assert list(got) == want, (it, query.tobytes(), target.tobytes(), got, want)
+        n_multi += len(want) > 1
+        n_trunc += len(want) == 10
+    assert n_multi > 100 and n_trunc > 20
