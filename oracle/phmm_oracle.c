@@ -7,10 +7,13 @@
  * Parity status: PINNED. oracle_align / oracle_align_tb reproduce every known-answer test the reference
  * holds for this path (tests/golden/pair_hmm_kats.json, extracted from test/unit/core/models/pair_hmm_tests.cpp)
  * and agree with the reference's own SIMD kernel compiled here (oracle/_ref, ref_driver.cpp) on seeded fuzz
- * (tests/test_oracle.py). Everything above the raw kernel (naive shortcut, flank discount, max over mapping
- * positions, mapping-quality mixing, k-mer mapper) has NO test in the reference; it is restated line by line
- * from the files cited at each function and is pinned only through the kernel it calls ("unpinned above the
- * kernel" in DESIGN.md).
+ * (tests/test_oracle.py). Above the raw kernel the reference has no tests; oracle_evaluate (naive shortcut, window
+ * placement, flank discount, lowest()), the single-position align + CIGAR, the band rounding and oracle_kmer_map are
+ * pinned to the reference's OWN code — pair_hmm.hpp, simd_pair_hmm_wrapper.hpp and utils/kmer_mapper.hpp compiled from
+ * /root/reference behind oracle/ref_hmm_driver.cpp — on seeded fuzz (tests/test_oracle.py). What is left unpinned by the
+ * reference itself is the outermost layer (max over mapping positions with the in-range rule, mapping-quality mixing,
+ * the populate loops: haplotype_likelihood_model.cpp / haplotype_likelihood_array.cpp cannot be compiled here); it is
+ * restated line by line over the pinned pieces, from the files cited at each function.
  *
  * Coordinates: cell (x, y) = x truth-window bases and y target (read) bases consumed; the band is
  * 0 <= x - y <= 2*band - 1; W = truth_len = target_len + 2*band - 1. The reference walks the same cells along
