@@ -641,7 +641,8 @@ __host__ __device__ inline double finish_likelihood(const int best, const bool u
     const double c = 0.230258509299404568401799145468436420760110148862877297603;   // utils/maths.hpp:41
     const double ln_given_mapped = best == kBestInf ? -1.7976931348623157e308 : -c * (double)best;
     if (use_mapq) {
-        if (mapq_trigger >= 0 && mapq >= mapq_trigger) mapq = mapq_cap;
+        // a trigger at or above the cap is dropped when the model is configured (haplotype_likelihood_model.cpp:49-51, 117-119)
+        if (mapq_trigger >= 0 && mapq_trigger < mapq_cap && mapq >= mapq_trigger) mapq = mapq_cap;
         const double ln_miss = -c * (double)mapq;
         const double ln_mapped = log(1.0 - exp(ln_miss));
         const double a = ln_mapped + ln_given_mapped, b = ln_miss;

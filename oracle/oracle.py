@@ -179,9 +179,21 @@ class RefKernel:
         return out
 
 
+class _ModelArgs(C.Structure):      # struct ModelArgs of oracle/ref_hmm_driver.cpp
+    _fields_ = [("max_indel_error", C.c_int), ("use_int_scores", C.c_int), ("use_mapping_quality", C.c_int), ("mapq_cap", C.c_int),
+                ("mapq_cap_trigger", C.c_int),
+                ("hap", C.c_char_p), ("hap_len", C.c_int), ("hap_begin", C.c_longlong),
+                ("mask_f", C.c_char_p), ("prior_f", _i8p), ("mask_r", C.c_char_p), ("prior_r", _i8p), ("gap_open", _i8p), ("gap_extend", _i8p),
+                ("has_flank", C.c_int), ("lhs_flank", C.c_longlong), ("rhs_flank", C.c_longlong),
+                ("read", C.c_char_p), ("quals", C.c_void_p), ("read_len", C.c_int), ("mapping_quality", C.c_int), ("reverse", C.c_int),
+                ("read_begin", C.c_longlong),
+                ("positions", C.POINTER(C.c_longlong)), ("n_positions", C.c_int), ("map_positions", C.c_int)]
+
+
 class RefHMM:
-    """The UNMODIFIED reference layer above the kernel — hmm::evaluate, hmm::align and the band-choosing PairHMMWrapper
-    (pair_hmm.hpp, simd_pair_hmm_wrapper.hpp) — behind oracle/ref_hmm_driver.cpp (oracle/_ref/libref_hmm.so)."""
+    """The UNMODIFIED reference above the kernel, behind oracle/ref_hmm_driver.cpp (oracle/_ref/libref_hmm.so): hmm::evaluate,
+    hmm::align, the band-choosing PairHMMWrapper (pair_hmm.hpp, simd_pair_hmm_wrapper.hpp), the k-mer mapper
+    (utils/kmer_mapper.hpp) and HaplotypeLikelihoodModel::{reset, evaluate, align} (haplotype_likelihood_model.cpp)."""
 
     @staticmethod
     def available():
@@ -192,9 +204,50 @@ class RefHMM:
         self.lib.ref_hmm_band.restype = C.c_int
         self.lib.ref_hmm_evaluate.restype = C.c_double
         self.lib.ref_hmm_align.restype = C.c_int
+        self.lib.ref_model_evaluate.restype = C.c_int
+        self.lib.ref_model_align.restype = C.c_int
 
     def band(self, requested, int32=False):
         return self.lib.ref_hmm_band(int(requested), int(int32))
+
+    def _model_args(self, band_request, hap, read, quals, gap_open, gap_extend, mask_f, prior_f, mask_r, prior_r, positions, hap_begin, read_begin,
+                    mapping_quality, reverse, flanks, use_mapping_quality, mapq_cap, mapq_cap_trigger, int32):
+        h, r, mf, mr = _b(hap), _b(read), _b(mask_f), _b(mask_r)
+        q = np.ascontiguousarray(np.asarray(quals, dtype=np.uint8))
+        go, gop = _i8(gap_open); ge, gep = _i8(gap_extend); pf, pfp = _i8(prior_f); pr, prp = _i8(prior_r)
+        n = len(h) - 1
+        assert len(go) == len(ge) == len(pf) == len(pr) == n == len(mf) - 1 == len(mr) - 1 and len(q) == len(r) - 1
+        map_positions = positions is None
+        pos = (C.c_longlong * max(1, 0 if map_positions else len(positions)))(*([] if map_positions else [int(x) for x in positions]))
+        a = _ModelArgs(int(band_request), int(int32), int(use_mapping_quality), int(mapq_cap), int(mapq_cap_trigger),
+                       C.cast(h, C.c_char_p), n, int(hap_begin), C.cast(mf, C.c_char_p), pfp, C.cast(mr, C.c_char_p), prp, gop, gep,
+                       0 if flanks is None else 1, 0 if flanks is None else int(flanks[0]), 0 if flanks is None else int(flanks[1]),
+                       C.cast(r, C.c_char_p), q.ctypes.data, len(r) - 1, int(mapping_quality), int(bool(reverse)), int(read_begin),
+                       pos, 0 if map_positions else len(positions), int(map_positions))
+        return a, (h, r, mf, mr, q, go, ge, pf, pr, pos)
+
+    def model_evaluate(self, band_request, hap, read, quals, gap_open, gap_extend, mask_f, prior_f, mask_r, prior_r, positions, hap_begin=0,
+                       read_begin=0, mapping_quality=60, reverse=False, flanks=None, use_mapping_quality=True, mapq_cap=120,
+                       mapq_cap_trigger=-1, int32=False):
+        """HaplotypeLikelihoodModel::reset + evaluate. positions=None → mapped by the reference's k-mer mapper as populate() does.
+        Returns (status, value, required_extension); status 1 == ShortHaplotypeError."""
+        a, keep = self._model_args(band_request, hap, read, quals, gap_open, gap_extend, mask_f, prior_f, mask_r, prior_r, positions, hap_begin,
+                                   read_begin, mapping_quality, reverse, flanks, use_mapping_quality, mapq_cap, mapq_cap_trigger, int32)
+        out, ext = C.c_double(0), C.c_int(0)
+        st = self.lib.ref_model_evaluate(C.byref(a), C.byref(out), C.byref(ext))
+        return st, out.value, ext.value
+
+    def model_align(self, band_request, hap, read, quals, gap_open, gap_extend, mask_f, prior_f, mask_r, prior_r, positions, hap_begin=0,
+                    read_begin=0, mapping_quality=60, reverse=False, flanks=None, use_mapping_quality=True, mapq_cap=120,
+                    mapq_cap_trigger=-1, int32=False):
+        """HaplotypeLikelihoodModel::reset + align. Returns (status, mapping_position, likelihood, cigar_text, required_extension)."""
+        a, keep = self._model_args(band_request, hap, read, quals, gap_open, gap_extend, mask_f, prior_f, mask_r, prior_r, positions, hap_begin,
+                                   read_begin, mapping_quality, reverse, flanks, use_mapping_quality, mapq_cap, mapq_cap_trigger, int32)
+        mp_, lk, ext = C.c_longlong(0), C.c_double(0), C.c_int(0)
+        cap = 8 * (a.read_len + 512) + 64
+        cig = C.create_string_buffer(cap)
+        st = self.lib.ref_model_align(C.byref(a), C.byref(mp_), C.byref(lk), cig, cap, C.byref(ext))
+        return st, mp_.value, lk.value, cig.value.decode(), ext.value
 
     def kmer_map(self, query, target, max_positions=10):
         """utils/kmer_mapper.hpp as HaplotypeLikelihoodArray::populate calls it (K = 6, at most ``max_positions``)."""

@@ -8,12 +8,12 @@
  * holds for this path (tests/golden/pair_hmm_kats.json, extracted from test/unit/core/models/pair_hmm_tests.cpp)
  * and agree with the reference's own SIMD kernel compiled here (oracle/_ref, ref_driver.cpp) on seeded fuzz
  * (tests/test_oracle.py). Above the raw kernel the reference has no tests; oracle_evaluate (naive shortcut, window
- * placement, flank discount, lowest()), the single-position align + CIGAR, the band rounding and oracle_kmer_map are
- * pinned to the reference's OWN code — pair_hmm.hpp, simd_pair_hmm_wrapper.hpp and utils/kmer_mapper.hpp compiled from
- * /root/reference behind oracle/ref_hmm_driver.cpp — on seeded fuzz (tests/test_oracle.py). What is left unpinned by the
- * reference itself is the outermost layer (max over mapping positions with the in-range rule, mapping-quality mixing,
- * the populate loops: haplotype_likelihood_model.cpp / haplotype_likelihood_array.cpp cannot be compiled here); it is
- * restated line by line over the pinned pieces, from the files cited at each function.
+ * placement, flank discount, lowest()), the single-position align + CIGAR, the band rounding, oracle_kmer_map and
+ * oracle_model_evaluate / oracle_model_align (in-range rule, max over mapping positions, fallback shift,
+ * ShortHaplotypeError, mapping-quality mixing) are pinned to the reference's OWN code — pair_hmm.hpp,
+ * simd_pair_hmm_wrapper.hpp, utils/kmer_mapper.hpp and haplotype_likelihood_model.cpp compiled from /root/reference behind
+ * oracle/ref_hmm_driver.cpp — on seeded fuzz (tests/test_oracle.py). Only the populate loops of
+ * haplotype_likelihood_array.cpp (per haplotype, sample, read: map, evaluate) are restated without a compiled counterpart.
  *
  * Coordinates: cell (x, y) = x truth-window bases and y target (read) bases consumed; the band is
  * 0 <= x - y <= 2*band - 1; W = truth_len = target_len + 2*band - 1. The reference walks the same cells along
@@ -354,7 +354,8 @@ int oracle_model_evaluate(int band, const char* hap, int hap_len, const char* re
     }
     if (use_mapping_quality) {
         int mq = mapping_quality;
-        if (mapq_cap_trigger >= 0 && mq >= mapq_cap_trigger) mq = mapq_cap;
+        /* set(config) / the constructor drop a trigger that is >= the cap (haplotype_likelihood_model.cpp:49-51, 117-119) */
+        if (mapq_cap_trigger >= 0 && mapq_cap_trigger < mapq_cap && mq >= mapq_cap_trigger) mq = mapq_cap;
         const double ln_miss = -LN10_DIV_10 * (double)mq;
         const double ln_mapped = log(1.0 - exp(ln_miss));
         const double r = log_sum_exp2(ln_mapped + best, ln_miss);
@@ -569,7 +570,8 @@ int oracle_model_align(int band, const char* hap, int hap_len, const char* read,
     const double ln_given = best == 0x7fffffff ? ORACLE_LOWEST : -LN10_DIV_10 * (double)best;
     if (use_mapping_quality) {
         int mq = mapping_quality;
-        if (mapq_cap_trigger >= 0 && mq >= mapq_cap_trigger) mq = mapq_cap;
+        /* set(config) / the constructor drop a trigger that is >= the cap (haplotype_likelihood_model.cpp:49-51, 117-119) */
+        if (mapq_cap_trigger >= 0 && mapq_cap_trigger < mapq_cap && mq >= mapq_cap_trigger) mq = mapq_cap;
         const double ln_miss = -LN10_DIV_10 * (double)mq;
         const double ln_mapped = log(1.0 - exp(ln_miss));
         const double r = log_sum_exp2(ln_mapped + ln_given, ln_miss);

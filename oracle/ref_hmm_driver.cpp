@@ -5,6 +5,8 @@
 //                                                  hmm::align (:858-874: try_naive_align :321-340, simd_align :784-823, make_cigar :152-188)
 //   src/core/models/pairhmm/simd_pair_hmm_wrapper.hpp   PairHMMWrapper: runtime band / precision choice (:85-88, :209-241)
 //   src/utils/kmer_mapper.hpp                      the candidate-position mapper populate() runs inline
+//   src/core/models/haplotype_likelihood_model.cpp HaplotypeLikelihoodModel::{reset, evaluate, align} (compiled alongside, with
+//                                                  error/{snv,indel}_error_model.cpp) over stand-in Haplotype / AlignedRead types
 // pair_hmm.hpp's own includes that need Boost or Octopus's config (basics/cigar_string.hpp, exceptions/*.hpp, utils/maths.hpp,
 // <boost/variant.hpp>) resolve to the minimal stand-ins under oracle/ref_shim/ (each says what it replaces); the reference
 // headers themselves are untouched. Needs -std=c++17 (the boost::variant stand-in is std::variant).
@@ -20,6 +22,10 @@
 
 #include "core/models/pairhmm/pair_hmm.hpp"
 #include "utils/kmer_mapper.hpp"          // self-contained (std only): the K = 6 vote mapper, utils/kmer_mapper.hpp:43-159
+#include "core/models/error/error_model_factory.hpp"   // stand-in: "error models" that hand back the arrays set below
+#include "core/models/haplotype_likelihood_model.hpp"  // the reference's own; its .cpp is compiled alongside (oracle/Makefile)
+
+namespace octopus { FixedPenalties& fixed_penalties() noexcept { static thread_local FixedPenalties p; return p; } }
 
 namespace {
 
@@ -105,6 +111,114 @@ int ref_kmer_map(const char* query, int query_len, const char* target, int targe
     const int n = static_cast<int>(last - positions.begin());
     for (int i = 0; i < n; ++i) out_positions[i] = static_cast<long long>(positions[i]);
     return n;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// HaplotypeLikelihoodModel (src/core/models/haplotype_likelihood_model.cpp, compiled UNMODIFIED): reset(haplotype, flank_state)
+// then evaluate(read, positions) (:187-304: in-range rule, max over mapping positions U original position, shifted fallback,
+// ShortHaplotypeError, mapping-quality mixing, clamp) or align(read, positions) (:335-431). Haplotype, AlignedRead and the error
+// models are the stand-ins of oracle/ref_shim/ (the path takes the error models' arrays as input).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ModelCall
+{
+    octopus::HaplotypeLikelihoodModel model;
+    octopus::Haplotype haplotype;
+    octopus::AlignedRead read;
+    octopus::HaplotypeLikelihoodModel::MappingPositionVector positions;
+    boost::optional<octopus::HaplotypeLikelihoodModel::FlankState> flank_state;
+};
+
+octopus::HaplotypeLikelihoodModel::Config make_config(int max_indel_error, int use_int_scores, int use_mapping_quality, int mapq_cap, int mapq_cap_trigger)
+{
+    octopus::HaplotypeLikelihoodModel::Config config {};
+    config.use_mapping_quality = use_mapping_quality != 0;
+    if (mapq_cap_trigger >= 0) config.mapping_quality_cap_trigger = static_cast<octopus::AlignedRead::MappingQuality>(mapq_cap_trigger);
+    config.mapping_quality_cap = static_cast<octopus::AlignedRead::MappingQuality>(mapq_cap);
+    config.max_indel_error = static_cast<unsigned>(max_indel_error);
+    config.use_int_scores = use_int_scores != 0;
+    return config;
+}
+
+struct ModelArgs
+{
+    int max_indel_error, use_int_scores, use_mapping_quality, mapq_cap, mapq_cap_trigger;
+    const char* hap; int hap_len; long long hap_begin;
+    const char* mask_f; const std::int8_t* prior_f; const char* mask_r; const std::int8_t* prior_r;
+    const std::int8_t* gap_open; const std::int8_t* gap_extend;
+    int has_flank; long long lhs_flank, rhs_flank;
+    const char* read; const std::uint8_t* quals; int read_len, mapping_quality, reverse; long long read_begin;
+    const long long* positions; int n_positions, map_positions;
+};
+
+ModelCall prepare(const ModelArgs& a)
+{
+    auto& p = octopus::fixed_penalties();
+    p.forward_mask.assign(a.mask_f, a.mask_f + a.hap_len); p.reverse_mask.assign(a.mask_r, a.mask_r + a.hap_len);
+    p.forward_priors.assign(a.prior_f, a.prior_f + a.hap_len); p.reverse_priors.assign(a.prior_r, a.prior_r + a.hap_len);
+    p.gap_open.assign(a.gap_open, a.gap_open + a.hap_len); p.gap_extend.assign(a.gap_extend, a.gap_extend + a.hap_len);
+    ModelCall c {octopus::HaplotypeLikelihoodModel {make_config(a.max_indel_error, a.use_int_scores, a.use_mapping_quality, a.mapq_cap, a.mapq_cap_trigger)},
+                 octopus::Haplotype {std::string(a.hap, a.hap + a.hap_len), static_cast<octopus::ContigRegion::Position>(a.hap_begin)},
+                 octopus::AlignedRead {std::string(a.read, a.read + a.read_len), std::vector<std::uint8_t>(a.quals, a.quals + a.read_len),
+                                       static_cast<std::uint8_t>(a.mapping_quality), a.reverse != 0, static_cast<octopus::ContigRegion::Position>(a.read_begin)},
+                 {}, {}};
+    if (a.map_positions) {
+        // as HaplotypeLikelihoodArray::populate does inline (haplotype_likelihood_array.cpp:76-93)
+        constexpr unsigned char K = 6;
+        if (c.read.sequence().size() >= K && c.haplotype.sequence().size() >= K) {
+            const auto read_hashes = octopus::compute_kmer_hashes<K>(c.read.sequence());
+            const auto haplotype_hashes = octopus::make_kmer_hash_table<K>(c.haplotype.sequence());
+            auto counts = octopus::init_mapping_counts(haplotype_hashes);
+            c.positions.resize(10);
+            c.positions.erase(octopus::map_query_to_target(read_hashes, haplotype_hashes, counts, c.positions.begin(), 10), c.positions.end());
+        }
+    } else {
+        for (int i = 0; i < a.n_positions; ++i) c.positions.push_back(static_cast<std::size_t>(a.positions[i]));
+    }
+    if (a.has_flank) c.flank_state = octopus::HaplotypeLikelihoodModel::FlankState {static_cast<octopus::ContigRegion::Position>(a.lhs_flank),
+                                                                                   static_cast<octopus::ContigRegion::Position>(a.rhs_flank)};
+    return c;
+}
+
+} // namespace
+
+extern "C" {
+
+// returns 0, or 1 on ShortHaplotypeError (*required_extension set)
+int ref_model_evaluate(const ModelArgs* args, double* out, int* required_extension)
+{
+    auto c = prepare(*args);
+    c.model.reset(c.haplotype, c.flank_state);
+    try {
+        *out = c.model.evaluate(c.read, c.positions);
+    } catch (const octopus::HaplotypeLikelihoodModel::ShortHaplotypeError& e) {
+        *required_extension = static_cast<int>(e.required_extension());
+        return 1;
+    }
+    return 0;
+}
+
+// returns 0, 1 on ShortHaplotypeError, 2 if the CIGAR text does not fit
+int ref_model_align(const ModelArgs* args, long long* mapping_position, double* likelihood, char* cigar, int cigar_cap, int* required_extension)
+{
+    auto c = prepare(*args);
+    c.model.reset(c.haplotype, c.flank_state);
+    try {
+        const auto a = c.model.align(c.read, c.positions);
+        *mapping_position = static_cast<long long>(a.mapping_position);
+        *likelihood = a.likelihood;
+        std::string text;
+        for (const auto& op : a.cigar) { text += std::to_string(op.size()); text += static_cast<char>(op.flag()); }
+        if (static_cast<int>(text.size()) + 1 > cigar_cap) return 2;
+        std::memcpy(cigar, text.c_str(), text.size() + 1);
+    } catch (const octopus::HaplotypeLikelihoodModel::ShortHaplotypeError& e) {
+        *required_extension = static_cast<int>(e.required_extension());
+        return 1;
+    }
+    return 0;
 }
 
 } // extern "C"

@@ -102,11 +102,13 @@ def test_populate_matches_oracle(engine, coracle, band_req):
         for dp_only in (False, True):
             for use_mq in (True, False):
                 mapit = (trial % 3 == 0) and (trial % 2 == 0 or dp_only)      # positions=None: k-mer mapped on the device, or original only
-                cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, use_mapping_quality=use_mq,
-                                                      mapping_quality_cap_trigger=40 if trial % 2 else None, disable_naive_shortcut=dp_only,
+                # trial 5: a trigger at or above the cap is ignored (haplotype_likelihood_model.cpp:49-51); trial 3: a low cap that bites
+                trig, cap = {1: (40, 120), 3: (40, 50), 5: (200, 50)}.get(trial, (None, 120))
+                cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, use_mapping_quality=use_mq, mapping_quality_cap=cap,
+                                                      mapping_quality_cap_trigger=trig, disable_naive_shortcut=dp_only,
                                                       map_positions=mapit)
-                rc, want, wst = coracle.populate(band, haps, reads, positions, flanks, use_mapping_quality=use_mq,
-                                                 mapq_cap_trigger=40 if trial % 2 else -1, dp_only=dp_only, map_positions=mapit)
+                rc, want, wst = coracle.populate(band, haps, reads, positions, flanks, use_mapping_quality=use_mq, mapq_cap=cap,
+                                                 mapq_cap_trigger=-1 if trig is None else trig, dp_only=dp_only, map_positions=mapit)
                 got, st = engine.populate(cfg, haps, reads, positions, flanks, want_status=True)
                 ok_pairs = wst == 0
                 assert np.array_equal((st & 0xFFFF) == 2, (wst & 0xFFFF) == 2)

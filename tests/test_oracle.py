@@ -277,3 +277,85 @@ def test_c_restatement_kmer_mapper_matches_reference_mapper(coracle, refhmm):
         n_multi += len(want) > 1
         n_trunc += len(want) == 10
     assert n_multi > 100 and n_trunc > 20
+
+
+def _model_case(rng):
+    band_req = int(rng.choice([3, 8, 12, 16, 30]))
+    band = next(b for b in (8, 16, 32) if band_req <= b)
+    L = int(rng.integers(8, 60))
+    # mostly long enough, sometimes too short for read + pads (ShortHaplotypeError / shifted fallback territory)
+    hap_len = int(rng.integers(L + 2 * band + 1, L + 2 * band + 80)) if rng.random() < 0.8 else int(rng.integers(max(L // 2, 8), L + 2 * band + 1))
+    c = _hmm_case(rng, hap_len, min(L, hap_len), exact_rate=0.3)
+    c["band_req"], c["band"] = band_req, band
+    c["mask_r"] = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, hap_len)].copy()
+    c["prior_r"] = rng.integers(1, 126, hap_len).astype(np.int8)
+    c["reverse"] = bool(rng.random() < 0.5)
+    c["hap_begin"] = int(rng.integers(0, 1000))
+    # the read's own mapped position: near its true origin, or anywhere over the haplotype (edges → fallback shift)
+    orig = int(np.clip(c["start"] + rng.integers(-2, 3), 0, hap_len)) if rng.random() < 0.7 else int(rng.integers(0, hap_len + 1))
+    c["orig"] = orig
+    c["mapq"] = int(rng.choice([0, 3, 20, 40, 60, 255]))
+    c["trigger"] = int(rng.choice([-1, -1, 30, 200]))
+    c["cap"] = int(rng.choice([120, 50]))
+    c["use_mq"] = bool(rng.random() < 0.8)
+    c["flanks"] = None if rng.random() < 0.5 else (int(rng.integers(0, hap_len // 2 + 1)), int(rng.integers(0, hap_len // 2 + 1)))
+    c["positions"] = None if rng.random() < 0.5 else [int(x) for x in rng.integers(0, hap_len + 5, int(rng.integers(0, 5)))]
+    return c
+
+
+def test_c_restatement_model_evaluate_matches_reference_model(coracle, refhmm):
+    """oracle_model_evaluate against the reference's own HaplotypeLikelihoodModel::reset + evaluate
+    (haplotype_likelihood_model.cpp compiled from /root/reference): in-range rule, max over mapping positions U original position,
+    shifted fallback, ShortHaplotypeError with its required extension, strand-specific SNV arrays, mapping-quality mixing with cap
+    trigger, clamp; candidate positions either explicit or mapped by the reference's k-mer mapper as populate() does."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    rng = np.random.default_rng(31337)
+    n_short = n_fallback = n_mapped = 0
+    for it in range(2500):
+        c = _model_case(rng)
+        mask, prior = (c["mask_r"], c["prior_r"]) if c["reverse"] else (c["mask"], c["prior"])
+        w = refhmm.model_evaluate(c["band_req"], c["hap"], c["read"], c["quals"], c["go"], c["ge"], c["mask"], c["prior"], c["mask_r"], c["prior_r"],
+                                  c["positions"], hap_begin=c["hap_begin"], read_begin=c["hap_begin"] + c["orig"], mapping_quality=c["mapq"],
+                                  reverse=c["reverse"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
+                                  mapq_cap_trigger=c["trigger"])
+        positions = c["positions"] if c["positions"] is not None else coracle.kmer_map(c["hap"][:0].tobytes().decode() + c["read"].tobytes().decode(), c["hap"].tobytes().decode(), 10)
+        g = coracle.model_evaluate(c["band"], c["hap"], c["read"], c["quals"], c["go"], c["ge"], mask, prior, positions, c["orig"],
+                                   mapping_quality=c["mapq"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
+                                   mapq_cap_trigger=c["trigger"])
+        assert g[0] == w[0], (it, c, g, w)
+        if w[0] == 1:
+            assert g[2] == w[2], (it, c, g, w)
+            n_short += 1
+        else:
+            assert g[1] == w[1] or abs(g[1] - w[1]) <= 1e-12 * abs(w[1]), (it, c, g, w)
+        n_mapped += c["positions"] is None
+        n_fallback += not (c["band"] <= c["orig"] and c["orig"] + len(c["read"]) + c["band"] <= len(c["hap"]))
+    assert n_short > 50 and n_fallback > 300 and n_mapped > 800, (n_short, n_fallback, n_mapped)
+
+
+def test_c_restatement_model_align_matches_reference_model(coracle, refhmm):
+    """oracle_model_align against HaplotypeLikelihoodModel::reset + align (compute_optimal_alignment, :335-431): which candidate
+    wins (> for listed positions, >= for the original position), its offset, CIGAR and mixed likelihood, ShortHaplotypeError."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    rng = np.random.default_rng(99)
+    n_short = 0
+    for it in range(1200):
+        c = _model_case(rng)
+        mask, prior = (c["mask_r"], c["prior_r"]) if c["reverse"] else (c["mask"], c["prior"])
+        w = refhmm.model_align(c["band_req"], c["hap"], c["read"], c["quals"], c["go"], c["ge"], c["mask"], c["prior"], c["mask_r"], c["prior_r"],
+                               c["positions"], hap_begin=c["hap_begin"], read_begin=c["hap_begin"] + c["orig"], mapping_quality=c["mapq"],
+                               reverse=c["reverse"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
+                               mapq_cap_trigger=c["trigger"])
+        positions = c["positions"] if c["positions"] is not None else coracle.kmer_map(c["read"].tobytes().decode(), c["hap"].tobytes().decode(), 10)
+        g = coracle.model_align(c["band"], c["hap"], c["read"], c["quals"], c["go"], c["ge"], mask, prior, positions, c["orig"],
+                                mapping_quality=c["mapq"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
+                                mapq_cap_trigger=c["trigger"])
+        assert g[0] == w[0], (it, c, g, w)
+        if w[0] == 1:
+            assert g[4] == w[4], (it, c, g, w)
+            n_short += 1
+        else:
+            assert (g[1], g[3]) == (w[1], w[3]) and (g[2] == w[2] or abs(g[2] - w[2]) <= 1e-12 * abs(w[2])), (it, c, g, w)
+    assert n_short > 20
