@@ -359,3 +359,34 @@ def test_c_restatement_model_align_matches_reference_model(coracle, refhmm):
         else:
             assert (g[1], g[3]) == (w[1], w[3]) and (g[2] == w[2] or abs(g[2] - w[2]) <= 1e-12 * abs(w[2])), (it, c, g, w)
     assert n_short > 20
+
+
+def test_model_layer_agrees_on_hostile_inputs_within_the_quality_domain(coracle, refhmm):
+    """N / IUPAC / lower-case letters in reads and haplotypes and qualities up to 127 (the int8 range the reference kernel reads):
+    the restatement still equals the compiled HaplotypeLikelihoodModel. (Above 127 the reference's own result depends on SIMD
+    wrap-around of negative penalties — out of the parity domain)"""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"NRacgtn", dtype=np.uint8)
+    for it in range(900):
+        c = _model_case(rng)
+        L = len(c["read"])
+        if it % 3 == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                c["read"][rng.integers(0, L)] = alphabet[rng.integers(0, len(alphabet))]
+        elif it % 3 == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                c["hap"][rng.integers(0, len(c["hap"]))] = alphabet[rng.integers(0, len(alphabet))]
+        else:
+            c["quals"] = rng.integers(60, 128, L).astype(np.uint8)
+        mask, prior = (c["mask_r"], c["prior_r"]) if c["reverse"] else (c["mask"], c["prior"])
+        w = refhmm.model_evaluate(c["band_req"], c["hap"], c["read"], c["quals"], c["go"], c["ge"], c["mask"], c["prior"], c["mask_r"], c["prior_r"],
+                                  c["positions"], hap_begin=c["hap_begin"], read_begin=c["hap_begin"] + c["orig"], mapping_quality=c["mapq"],
+                                  reverse=c["reverse"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
+                                  mapq_cap_trigger=c["trigger"])
+        positions = c["positions"] if c["positions"] is not None else coracle.kmer_map(c["read"].tobytes().decode("latin1"), c["hap"].tobytes().decode("latin1"), 10)
+        g = coracle.model_evaluate(c["band"], c["hap"], c["read"], c["quals"], c["go"], c["ge"], mask, prior, positions, c["orig"],
+                                   mapping_quality=c["mapq"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
+                                   mapq_cap_trigger=c["trigger"])
+        assert g[0] == w[0] and ((w[0] == 1 and g[2] == w[2]) or (w[0] == 0 and (g[1] == w[1] or abs(g[1] - w[1]) <= 1e-12 * abs(w[1])))), (it, g, w)
