@@ -1,13 +1,2 @@
-// TEST INFRASTRUCTURE ONLY — stand-in for exceptions/user_error.hpp (included by simd_pair_hmm_wrapper.hpp:11).
-#ifndef REF_SHIM_USER_ERROR_HPP
-#define REF_SHIM_USER_ERROR_HPP
+// TEST INFRASTRUCTURE ONLY — see error.hpp (stand-in for the reference header of this name).
 #include "error.hpp"
-namespace octopus {
-class UserError : public Error
-{
-    std::string do_type() const override { return "user"; }
-public:
-    virtual ~UserError() = default;
-};
-} // namespace octopus
-#endif
