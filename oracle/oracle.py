@@ -190,6 +190,18 @@ class _ModelArgs(C.Structure):      # struct ModelArgs of oracle/ref_hmm_driver.
                 ("positions", C.POINTER(C.c_longlong)), ("n_positions", C.c_int), ("map_positions", C.c_int)]
 
 
+class _ArrayArgs(C.Structure):      # struct ArrayArgs of oracle/ref_hmm_driver.cpp
+    _fields_ = [("max_indel_error", C.c_int), ("use_int_scores", C.c_int), ("use_mapping_quality", C.c_int), ("mapq_cap", C.c_int),
+                ("mapq_cap_trigger", C.c_int),
+                ("H", C.c_int), ("hap_off", C.c_void_p), ("seq", C.c_void_p), ("mask_f", C.c_void_p), ("prior_f", C.c_void_p), ("mask_r", C.c_void_p),
+                ("prior_r", C.c_void_p), ("gap_open", C.c_void_p), ("gap_extend", C.c_void_p), ("hap_begin", C.c_void_p),
+                ("S", C.c_int), ("sample_off", C.c_void_p),
+                ("R", C.c_int), ("read_off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p), ("mapq", C.c_void_p),
+                ("reverse", C.c_void_p), ("read_begin", C.c_void_p),
+                ("T", C.c_int), ("template_off", C.c_void_p),
+                ("has_flank", C.c_int), ("lhs_flank", C.c_longlong), ("rhs_flank", C.c_longlong)]
+
+
 class RefHMM:
     """The UNMODIFIED reference above the kernel, behind oracle/ref_hmm_driver.cpp (oracle/_ref/libref_hmm.so): hmm::evaluate,
     hmm::align, the band-choosing PairHMMWrapper (pair_hmm.hpp, simd_pair_hmm_wrapper.hpp), the k-mer mapper
@@ -206,6 +218,7 @@ class RefHMM:
         self.lib.ref_hmm_align.restype = C.c_int
         self.lib.ref_model_evaluate.restype = C.c_int
         self.lib.ref_model_align.restype = C.c_int
+        self.lib.ref_array_populate.restype = C.c_int
 
     def band(self, requested, int32=False):
         return self.lib.ref_hmm_band(int(requested), int(int32))
@@ -248,6 +261,27 @@ class RefHMM:
         cig = C.create_string_buffer(cap)
         st = self.lib.ref_model_align(C.byref(a), C.byref(mp_), C.byref(lk), cig, cap, C.byref(ext))
         return st, mp_.value, lk.value, cig.value.decode(), ext.value
+
+    def array_populate(self, band_request, haps, reads, sample_off=None, template_off=None, flanks=None, use_mapping_quality=True,
+                       mapq_cap=120, mapq_cap_trigger=-1, int32=False):
+        """HaplotypeLikelihoodArray::populate (haplotype_likelihood_array.cpp, unmodified) on a HaplotypeBlock / ReadBlock pair.
+        sample_off: boundaries of the samples over the reads (or over the templates when template_off is given); default one sample.
+        Returns (status, matrix [H, reads or templates], required_extension); status 1 == ShortHaplotypeError."""
+        p = lambda a: np.ascontiguousarray(a).ctypes.data
+        keep = [np.ascontiguousarray(x) for x in (haps.off, haps.seq, haps.snv_mask_fwd, haps.snv_prior_fwd, haps.snv_mask_rev, haps.snv_prior_rev,
+                                                  haps.gap_open, haps.gap_extend, haps.begin if haps.begin is not None else np.zeros(haps.n, np.int64),
+                                                  reads.off, reads.bases, reads.quals, reads.mapq, reads.reverse, reads.begin)]
+        n_items = reads.n if template_off is None else len(template_off) - 1
+        so = np.ascontiguousarray([0, n_items] if sample_off is None else sample_off, dtype=np.int64)
+        to = np.ascontiguousarray([0] if template_off is None else template_off, dtype=np.int64)
+        a = _ArrayArgs(int(band_request), int(int32), int(use_mapping_quality), int(mapq_cap), int(mapq_cap_trigger),
+                       haps.n, *[k.ctypes.data for k in keep[:9]], len(so) - 1, so.ctypes.data,
+                       reads.n, *[k.ctypes.data for k in keep[9:]], 0 if template_off is None else len(to) - 1, to.ctypes.data,
+                       0 if flanks is None else 1, 0 if flanks is None else int(flanks[0]), 0 if flanks is None else int(flanks[1]))
+        out = np.zeros((haps.n, n_items), dtype=np.float64)
+        ext = C.c_int(0)
+        st = self.lib.ref_array_populate(C.byref(a), out.ctypes.data_as(C.c_void_p), C.byref(ext))
+        return st, out, ext.value
 
     def kmer_map(self, query, target, max_positions=10):
         """utils/kmer_mapper.hpp as HaplotypeLikelihoodArray::populate calls it (K = 6, at most ``max_positions``)."""

@@ -12,8 +12,8 @@
  * oracle_model_evaluate / oracle_model_align (in-range rule, max over mapping positions, fallback shift,
  * ShortHaplotypeError, mapping-quality mixing) are pinned to the reference's OWN code — pair_hmm.hpp,
  * simd_pair_hmm_wrapper.hpp, utils/kmer_mapper.hpp and haplotype_likelihood_model.cpp compiled from /root/reference behind
- * oracle/ref_hmm_driver.cpp — on seeded fuzz (tests/test_oracle.py). Only the populate loops of
- * haplotype_likelihood_array.cpp (per haplotype, sample, read: map, evaluate) are restated without a compiled counterpart.
+ * oracle/ref_hmm_driver.cpp — on seeded fuzz (tests/test_oracle.py); oracle_populate equals the compiled
+ * HaplotypeLikelihoodArray::populate (haplotype_likelihood_array.cpp, ReadMap and TemplateMap overloads) on random regions.
  *
  * Coordinates: cell (x, y) = x truth-window bases and y target (read) bases consumed; the band is
  * 0 <= x - y <= 2*band - 1; W = truth_len = target_len + 2*band - 1. The reference walks the same cells along

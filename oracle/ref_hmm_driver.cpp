@@ -7,6 +7,7 @@
 //   src/utils/kmer_mapper.hpp                      the candidate-position mapper populate() runs inline
 //   src/core/models/haplotype_likelihood_model.cpp HaplotypeLikelihoodModel::{reset, evaluate, align} (compiled alongside, with
 //                                                  error/{snv,indel}_error_model.cpp) over stand-in Haplotype / AlignedRead types
+//   src/core/models/haplotype_likelihood_array.cpp HaplotypeLikelihoodArray::populate (ReadMap and TemplateMap) — the batch seam itself
 // pair_hmm.hpp's own includes that need Boost or Octopus's config (basics/cigar_string.hpp, exceptions/*.hpp, utils/maths.hpp,
 // <boost/variant.hpp>) resolve to the minimal stand-ins under oracle/ref_shim/ (each says what it replaces); the reference
 // headers themselves are untouched. Needs -std=c++17 (the boost::variant stand-in is std::variant).
@@ -25,7 +26,21 @@
 #include "core/models/error/error_model_factory.hpp"   // stand-in: "error models" that hand back the arrays set below
 #include "core/models/haplotype_likelihood_model.hpp"  // the reference's own; its .cpp is compiled alongside (oracle/Makefile)
 
-namespace octopus { FixedPenalties& fixed_penalties() noexcept { static thread_local FixedPenalties p; return p; } }
+#include "core/models/haplotype_likelihood_array.hpp"  // likewise (its .cpp and utils/thread_pool.cpp are compiled alongside)
+
+#include <unordered_map>
+
+namespace {
+thread_local octopus::FixedPenalties default_penalties;
+thread_local std::unordered_map<const octopus::Haplotype*, octopus::FixedPenalties> block_penalties;
+} // namespace
+namespace octopus {
+const FixedPenalties& fixed_penalties(const Haplotype& haplotype) noexcept
+{
+    const auto itr = block_penalties.find(&haplotype);
+    return itr != block_penalties.end() ? itr->second : default_penalties;
+}
+} // namespace octopus
 
 namespace {
 
@@ -156,7 +171,7 @@ struct ModelArgs
 
 ModelCall prepare(const ModelArgs& a)
 {
-    auto& p = octopus::fixed_penalties();
+    auto& p = default_penalties;
     p.forward_mask.assign(a.mask_f, a.mask_f + a.hap_len); p.reverse_mask.assign(a.mask_r, a.mask_r + a.hap_len);
     p.forward_priors.assign(a.prior_f, a.prior_f + a.hap_len); p.reverse_priors.assign(a.prior_r, a.prior_r + a.hap_len);
     p.gap_open.assign(a.gap_open, a.gap_open + a.hap_len); p.gap_extend.assign(a.gap_extend, a.gap_extend + a.hap_len);
@@ -218,6 +233,92 @@ int ref_model_align(const ModelArgs* args, long long* mapping_position, double* 
         *required_extension = static_cast<int>(e.required_extension());
         return 1;
     }
+    return 0;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// HaplotypeLikelihoodArray::populate (src/core/models/haplotype_likelihood_array.cpp, compiled UNMODIFIED): the H x S x R loop with
+// the inline k-mer mapping (:51-103), and the TemplateMap overload (:105-199). Samples are named s000, s001, ... so that the
+// stand-in ReadMap (an ordered map) iterates them in index order. out is [H][all samples' reads (or templates) back to back].
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+struct ArrayArgs
+{
+    int max_indel_error, use_int_scores, use_mapping_quality, mapq_cap, mapq_cap_trigger;
+    int H; const long long* hap_off; const char* seq; const char* mask_f; const std::int8_t* prior_f; const char* mask_r;
+    const std::int8_t* prior_r; const std::int8_t* gap_open; const std::int8_t* gap_extend; const long long* hap_begin;
+    int S; const long long* sample_off;      // reads (or templates) of sample s: [sample_off[s], sample_off[s+1])
+    int R; const long long* read_off; const char* bases; const std::uint8_t* quals; const std::uint8_t* mapq;
+    const std::uint8_t* reverse; const long long* read_begin;
+    int T; const long long* template_off;    // T == 0: ReadMap overload; else template t owns reads [template_off[t], template_off[t+1])
+    int has_flank; long long lhs_flank, rhs_flank;
+};
+
+// returns 0, or 1 on ShortHaplotypeError (*required_extension set)
+int ref_array_populate(const ArrayArgs* a, double* out, int* required_extension)
+{
+    using namespace octopus;
+    MappableBlock<Haplotype> haplotypes;
+    haplotypes.reserve(static_cast<std::size_t>(a->H));
+    for (int h = 0; h < a->H; ++h) {
+        haplotypes.emplace_back(std::string(a->seq + a->hap_off[h], a->seq + a->hap_off[h + 1]), static_cast<ContigRegion::Position>(a->hap_begin[h]));
+    }
+    block_penalties.clear();
+    for (int h = 0; h < a->H; ++h) {
+        const auto b = a->hap_off[h], e = a->hap_off[h + 1];
+        auto& p = block_penalties[&haplotypes[static_cast<std::size_t>(h)]];
+        p.forward_mask.assign(a->mask_f + b, a->mask_f + e); p.reverse_mask.assign(a->mask_r + b, a->mask_r + e);
+        p.forward_priors.assign(a->prior_f + b, a->prior_f + e); p.reverse_priors.assign(a->prior_r + b, a->prior_r + e);
+        p.gap_open.assign(a->gap_open + b, a->gap_open + e); p.gap_extend.assign(a->gap_extend + b, a->gap_extend + e);
+    }
+    const auto make_read = [a] (long long r) {
+        return AlignedRead {std::string(a->bases + a->read_off[r], a->bases + a->read_off[r + 1]),
+                            std::vector<std::uint8_t>(a->quals + a->read_off[r], a->quals + a->read_off[r + 1]),
+                            a->mapq[r], a->reverse[r] != 0, static_cast<ContigRegion::Position>(a->read_begin[r])};
+    };
+    std::vector<SampleName> samples;
+    for (int s = 0; s < a->S; ++s) { char name[16]; std::snprintf(name, sizeof name, "s%03d", s); samples.emplace_back(name); }
+    boost::optional<HaplotypeLikelihoodArray::FlankState> flank_state {};
+    if (a->has_flank) flank_state = HaplotypeLikelihoodArray::FlankState {static_cast<ContigRegion::Position>(a->lhs_flank), static_cast<ContigRegion::Position>(a->rhs_flank)};
+    HaplotypeLikelihoodArray array {HaplotypeLikelihoodModel {make_config(a->max_indel_error, a->use_int_scores, a->use_mapping_quality, a->mapq_cap, a->mapq_cap_trigger)},
+                                    static_cast<unsigned>(a->H), samples};
+    const long long width = a->sample_off[a->S];
+    try {
+        if (a->T == 0) {
+            ReadMap reads;
+            for (int s = 0; s < a->S; ++s) {
+                auto& v = reads[samples[static_cast<std::size_t>(s)]];
+                for (long long r = a->sample_off[s]; r < a->sample_off[s + 1]; ++r) v.push_back(make_read(r));
+            }
+            array.populate(reads, haplotypes, flank_state);
+        } else {
+            TemplateMap templates;
+            for (int s = 0; s < a->S; ++s) {
+                auto& v = templates[samples[static_cast<std::size_t>(s)]];
+                for (long long t = a->sample_off[s]; t < a->sample_off[s + 1]; ++t) {
+                    std::vector<AlignedRead> members;
+                    for (long long r = a->template_off[t]; r < a->template_off[t + 1]; ++r) members.push_back(make_read(r));
+                    v.emplace_back(std::move(members));
+                }
+            }
+            array.populate(templates, haplotypes, flank_state);
+        }
+    } catch (const HaplotypeLikelihoodModel::ShortHaplotypeError& e) {
+        block_penalties.clear();
+        *required_extension = static_cast<int>(e.required_extension());
+        return 1;
+    }
+    for (int h = 0; h < a->H; ++h) {
+        for (int s = 0; s < a->S; ++s) {
+            // by index (the accessor the genotype models use): haplotypes with equal sequences share one key in haplotype_indices_
+            const auto& v = array(samples[static_cast<std::size_t>(s)], IndexedHaplotype<> {haplotypes[static_cast<std::size_t>(h)], static_cast<std::size_t>(h)});
+            std::copy(v.begin(), v.end(), out + h * width + a->sample_off[s]);
+        }
+    }
+    block_penalties.clear();
     return 0;
 }
 

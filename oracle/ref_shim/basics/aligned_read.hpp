@@ -23,7 +23,11 @@ public:
     MappingQuality mapping_quality() const noexcept { return mapping_quality_; }
     bool is_marked_reverse_mapped() const noexcept { return reverse_; }
     const ContigRegion& mapped_region() const noexcept { return region_; }
+    // named by the array header's debug printers only
+    const std::string& name() const noexcept { return name_; }
+    const std::string& cigar() const noexcept { return name_; }
 private:
+    std::string name_;
     NucleotideSequence sequence_;
     BaseQualityVector qualities_;
     MappingQuality mapping_quality_;
@@ -31,5 +35,6 @@ private:
     ContigRegion region_;
 };
 inline AlignedRead::NucleotideSequence::size_type sequence_size(const AlignedRead& read) noexcept { return read.sequence().size(); }
+template <typename T> const ContigRegion& mapped_region(const T& mappable) noexcept { return mappable.mapped_region(); }
 } // namespace octopus
 #endif

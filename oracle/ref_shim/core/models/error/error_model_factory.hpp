@@ -14,15 +14,17 @@ struct FixedPenalties   // filled by the driver before HaplotypeLikelihoodModel:
     SnvErrorModel::MutationVector forward_mask, reverse_mask;
     SnvErrorModel::PenaltyVector forward_priors, reverse_priors, gap_open, gap_extend;
 };
-FixedPenalties& fixed_penalties() noexcept;   // defined in the driver (thread_local)
+// the arrays of the haplotype being reset: looked up by the address of the Haplotype object the model is handed (the driver
+// registers the elements of the block it passes to populate), else the single default set
+const FixedPenalties& fixed_penalties(const Haplotype& haplotype) noexcept;   // defined in the driver
 
 class FixedSnvErrorModel : public SnvErrorModel
 {
     std::unique_ptr<SnvErrorModel> do_clone() const override { return std::make_unique<FixedSnvErrorModel>(*this); }
-    void do_evaluate(const Haplotype&, MutationVector& forward_snv_mask, PenaltyVector& forward_snv_priors,
+    void do_evaluate(const Haplotype& haplotype, MutationVector& forward_snv_mask, PenaltyVector& forward_snv_priors,
                      MutationVector& reverse_snv_mask, PenaltyVector& reverse_snv_priors) const override
     {
-        const auto& p = fixed_penalties();
+        const auto& p = fixed_penalties(haplotype);
         forward_snv_mask = p.forward_mask; forward_snv_priors = p.forward_priors;
         reverse_snv_mask = p.reverse_mask; reverse_snv_priors = p.reverse_priors;
     }
@@ -30,13 +32,13 @@ class FixedSnvErrorModel : public SnvErrorModel
 class FixedIndelErrorModel : public IndelErrorModel
 {
     std::unique_ptr<IndelErrorModel> do_clone() const override { return std::make_unique<FixedIndelErrorModel>(*this); }
-    void do_set_penalties(const Haplotype&, PenaltyVector& gap_open_penalties, PenaltyType& gap_extend_penalty) const override
+    void do_set_penalties(const Haplotype& haplotype, PenaltyVector& gap_open_penalties, PenaltyType& gap_extend_penalty) const override
     {
-        gap_open_penalties = fixed_penalties().gap_open; gap_extend_penalty = fixed_penalties().gap_extend.front();
+        gap_open_penalties = fixed_penalties(haplotype).gap_open; gap_extend_penalty = fixed_penalties(haplotype).gap_extend.front();
     }
-    void do_set_penalties(const Haplotype&, PenaltyVector& gap_open_penalties, PenaltyVector& gap_extend_penalties) const override
+    void do_set_penalties(const Haplotype& haplotype, PenaltyVector& gap_open_penalties, PenaltyVector& gap_extend_penalties) const override
     {
-        gap_open_penalties = fixed_penalties().gap_open; gap_extend_penalties = fixed_penalties().gap_extend;
+        gap_open_penalties = fixed_penalties(haplotype).gap_open; gap_extend_penalties = fixed_penalties(haplotype).gap_extend;
     }
 };
 struct ErrorModel

@@ -2,6 +2,8 @@
 // mapped region. The real class is built from alleles over a ReferenceGenome (HTSlib).
 #ifndef REF_SHIM_HAPLOTYPE_HPP
 #define REF_SHIM_HAPLOTYPE_HPP
+#include <cstddef>
+#include <functional>
 #include <string>
 #include <utility>
 #include "basics/contig_region.hpp"
@@ -19,5 +21,27 @@ private:
     ContigRegion region_;
 };
 inline Haplotype::NucleotideSequence::size_type sequence_size(const Haplotype& haplotype) noexcept { return haplotype.sequence().size(); }
+// identity as the array's unordered_map<Haplotype, index> needs it (the real class compares region + sequence and caches a hash)
+inline bool operator==(const Haplotype& lhs, const Haplotype& rhs) noexcept
+{
+    return lhs.mapped_region().begin() == rhs.mapped_region().begin() && lhs.sequence() == rhs.sequence();
+}
+struct HaplotypeHash
+{
+    std::size_t operator()(const Haplotype& haplotype) const noexcept { return std::hash<std::string> {}(haplotype.sequence()) ^ haplotype.mapped_region().begin(); }
+};
+namespace debug {
+template <typename S> void print_variant_alleles(S&& stream, const Haplotype& haplotype) { stream << haplotype.sequence(); }
+} // namespace debug
 } // namespace octopus
+namespace std {
+template <> struct hash<octopus::Haplotype>
+{
+    size_t operator()(const octopus::Haplotype& haplotype) const noexcept { return octopus::HaplotypeHash {}(haplotype); }
+};
+template <> struct hash<reference_wrapper<const octopus::Haplotype>>
+{
+    size_t operator()(const reference_wrapper<const octopus::Haplotype> haplotype) const noexcept { return octopus::HaplotypeHash {}(haplotype.get()); }
+};
+} // namespace std
 #endif

@@ -390,3 +390,46 @@ def test_model_layer_agrees_on_hostile_inputs_within_the_quality_domain(coracle,
                                    mapping_quality=c["mapq"], flanks=c["flanks"], use_mapping_quality=c["use_mq"], mapq_cap=c["cap"],
                                    mapq_cap_trigger=c["trigger"])
         assert g[0] == w[0] and ((w[0] == 1 and g[2] == w[2]) or (w[0] == 0 and (g[1] == w[1] or abs(g[1] - w[1]) <= 1e-12 * abs(w[1])))), (it, g, w)
+
+
+def test_c_restatement_populate_matches_reference_array_populate(coracle, refhmm):
+    """oracle_populate — the checker every GPU populate test compares against — equals the reference's own
+    HaplotypeLikelihoodArray::populate (haplotype_likelihood_array.cpp compiled from /root/reference: H x S x R loop, inline k-mer
+    mapping, model reset / evaluate per haplotype), for several samples (= column ranges of one concatenated batch), with and
+    without a flank state, and for the TemplateMap overload (sum over a template's reads)."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    from helpers import random_region
+    rng = np.random.default_rng(606)
+    n_short = 0
+    for trial in range(14):
+        band_req = int(rng.choice([6, 8, 16, 20]))
+        band = next(b for b in (8, 16, 32) if band_req <= b)
+        haps, reads = random_region(rng, band, n_haps=int(rng.integers(1, 9)), n_reads=int(rng.integers(2, 40)), hap_len=int(rng.choice([150, 260])),
+                                    read_len_choices=[30, 60, 100], read_n_rate=0.05, edge_reads=(trial % 2 == 0))
+        flanks = (int(rng.integers(0, 70)), int(rng.integers(0, 70))) if trial % 2 else None
+        trig, cap = {1: (40, 120), 3: (40, 50), 5: (200, 50)}.get(trial % 6, (-1, 120))
+        use_mq = trial % 5 != 4
+        cuts = np.sort(rng.integers(0, reads.n + 1, int(rng.integers(0, 4))))
+        sample_off = np.concatenate([[0], cuts, [reads.n]]).astype(np.int64)             # empty samples allowed
+        rc, want_o, wst = coracle.populate(band, haps, reads, None, flanks, use_mapping_quality=use_mq, mapq_cap=cap, mapq_cap_trigger=trig,
+                                           map_positions=True)
+        st, got, ext = refhmm.array_populate(band_req, haps, reads, sample_off=sample_off, flanks=flanks, use_mapping_quality=use_mq,
+                                             mapq_cap=cap, mapq_cap_trigger=trig)
+        short = ((wst & 0xFFFF) == 2).any()
+        assert st == (1 if short else 0), (trial, st, rc)
+        if short:
+            n_short += 1
+            continue
+        assert np.allclose(got, want_o, rtol=1e-12, atol=0) and np.array_equal(got == 0.0, want_o == 0.0), (trial, np.abs(got - want_o).max())
+        # TemplateMap: consecutive reads grouped into templates, two "samples"
+        sizes = []
+        while sum(sizes) < reads.n:
+            sizes.append(min(int(rng.choice([1, 2, 2, 3])), reads.n - sum(sizes)))
+        toff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        t_cut = int(rng.integers(0, len(sizes) + 1))
+        st, got_t, _ = refhmm.array_populate(band_req, haps, reads, sample_off=[0, t_cut, len(sizes)], template_off=toff, flanks=flanks,
+                                             use_mapping_quality=use_mq, mapq_cap=cap, mapq_cap_trigger=trig)
+        want_t = np.stack([want_o[:, a:b].sum(axis=1) if b - a > 1 else want_o[:, a] for a, b in zip(toff[:-1], toff[1:])], axis=1)
+        assert st == 0 and np.allclose(got_t, want_t, rtol=1e-12, atol=1e-300), (trial, np.abs(got_t - want_t).max())
+    assert n_short < 10
