@@ -344,3 +344,34 @@ def test_multi_sample_array_is_one_batch_with_per_sample_views(engine, coracle):
     assert merged.is_primed() and merged.num_likelihoods() == reads.n and _close(np.stack([merged[h] for h in range(haps.n)]), want)[0]
     engine.populate(model.config, haps, reads, flank_state=(40, 40))
     assert one_call == engine.launch_count()          # the three samples cost exactly one populate call's launches
+
+
+def test_populate_matches_the_compiled_reference_populate(engine, refhmm):
+    """The CUDA engine against the reference's OWN HaplotypeLikelihoodArray::populate (haplotype_likelihood_array.cpp compiled from
+    /root/reference in the authoring container, oracle/_ref/libref_hmm.so) — no restatement in between: same haplotypes, reads,
+    flank state and configuration in, the same [H][R] ln-likelihoods out (integer penalties identical; the double epilogue to 1e-4
+    relative, in practice a few ulp)."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    rng = np.random.default_rng(8086)
+    for trial in range(8):
+        band_req = int(rng.choice([6, 8, 16, 20]))
+        band = next(b for b in (8, 16, 32) if band_req <= b)
+        if trial < 6:
+            haps, reads = random_region(rng, band, n_haps=int(rng.integers(1, 12)), n_reads=int(rng.integers(2, 50)), hap_len=int(rng.choice([200, 300])),
+                                        read_len_choices=[40, 76, 100], read_n_rate=0.05, edge_reads=(trial % 2 == 0))
+        else:
+            haps, reads, band_req = synth.make_batch("C2", n_reads=300, n_haps=12, seed=trial)
+        flanks = (int(rng.integers(0, 80)), int(rng.integers(0, 80))) if trial % 2 else None
+        trig, cap = {1: (40, 120), 3: (40, 50), 5: (200, 50)}.get(trial, (None, 120))
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, mapping_quality_cap=cap, mapping_quality_cap_trigger=trig)
+        st, want, _ = refhmm.array_populate(band_req, haps, reads, flanks=flanks, mapq_cap=cap, mapq_cap_trigger=-1 if trig is None else trig)
+        if st == 1:
+            from octopus_b200.api import ShortHaplotypeError
+            with pytest.raises(ShortHaplotypeError):
+                engine.populate(cfg, haps, reads, None, flanks)
+            continue
+        got = engine.populate(cfg, haps, reads, None, flanks)
+        ok, worst = _close(got, want)
+        assert ok and np.array_equal(got == 0.0, want == 0.0), (trial, worst)
