@@ -265,6 +265,22 @@ PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 PHMM_HD RowEntry make_row_entry32(uint32_t half) { RowEntry r; r.x = (half & 7u) | 0x5550u; r.y = half >> 8; return r; }
 PHMM_HD RowEntry pad_row_entry32() { RowEntry r; r.x = 0x5550u; r.y = 0u; return r; }
 
+// One place where the reference's flank replay does NOT re-add what its DP charged: a mismatch against a truth 'N' inside a flank
+// is replayed as exactly 2 (simd_pair_hmm.hpp:388-392) although the DP charged min(q', 2) (update_match_state, :121-142). The
+// payload DP below reports what the DP charged, so a candidate whose flanks hold an 'N' column that could have been matched for
+// less than 2 — the read has a quality below 2, or the column's SNV prior is below 2 — must take the exact traceback path
+// (generic_align<true>) instead. An 'N' column is recognisable from its table entry: all four caps <= 2 (any other column has at
+// least two caps of 127). lhs / rhs: flank sizes in window coordinates (window_flanks); overlapping flanks cover every column.
+PHMM_HD bool flank_replay_may_differ(const ColEntry* __restrict__ tab, const int W, const int lhs, const int rhs, const bool read_has_quality_below_2)
+{
+    for (int x = 0; x < W; ++x) {
+        if (x >= lhs && x < W - rhs) { x = W - rhs - 1; continue; }      // skip the non-flank middle
+        const uint32_t caps = ldg(tab + x).x;
+        if ((caps & 0xFCFCFCFCu) == 0u && (read_has_quality_below_2 || caps != 0x02020202u)) return true;
+    }
+    return false;
+}
+
 // rows: shared-memory row entries (make_row_entry32), rows[L] = pad_row_entry32().
 // tab : column table of the window. xl / xr: first non-flank column and first right-flank column (0 <= xl < xr <= W);
 // xl == 0 / xr > W mean "no left / right flank". Outputs the integer score, the in-flank penalty and the in-flank read bases.

@@ -584,12 +584,16 @@ k_populate_flank(const PopParams p)
         if (n == 0) continue;
         const int L = p.rd.info[r].x;
         __syncwarp();
+        unsigned qmin = 255u;
         {
             const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
-            for (int y = lane; y < L; y += 32) rows[y] = make_row_entry32(hr[y]);
+            for (int y = lane; y < L; y += 32) { const uint16_t half = hr[y]; rows[y] = make_row_entry32(half); qmin = min(qmin, (unsigned)half >> 8); }
             if (lane == 0) rows[L] = pad_row_entry32();
             __syncwarp();
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
         const uint32_t* q = p.gtasks + (size_t)li * p.fcap;
         const int W = L + K - 1;
@@ -608,7 +612,12 @@ k_populate_flank(const PopParams p)
             dp_flank32<BAND>(rows, L, tab + p.hp.off[h] + a, p.nuc_prior, xl, xr, &score, &flank, &mask);
             if (all_flank) { flank = score; mask = L; }
             const int v = discount_flank(score, flank, L, mask, 0);
-            if (valid) atomicMin(p.best + (size_t)h * R + r, v);
+            // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
+            const bool replay_differs = p.use_flanks != 0 && flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
+            if (valid) {
+                if (replay_differs) push_slow(p, r, h, a);
+                else atomicMin(p.best + (size_t)h * R + r, v);
+            }
         }
     }
 }

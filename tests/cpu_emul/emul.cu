@@ -130,5 +130,8 @@ extern "C" int emul_dp_flank32(int band, int L, const char* read, const uint8_t*
         default: return -1;
     }
     if (W - rhs_flank <= lhs_flank) { *flank = *score; *mask_size = L; }
-    return 0;
+    // 2: the kernel would hand this candidate to the exact traceback path (flank_replay_may_differ)
+    bool low_quality = false;
+    for (int y = 0; y < L; ++y) low_quality = low_quality || q[y] < 2;
+    return flank_replay_may_differ(t.data(), W, lhs_flank, rhs_flank, low_quality) ? 2 : 0;
 }

@@ -141,6 +141,7 @@ def test_flank_payload_dp_matches_traceback_flank_replay(emul, coracle):
     score, in-flank penalty and in-flank read bases, for every flank geometry incl. overlapping / empty flanks."""
     emul.emul_dp_flank32.argtypes = [C.c_int, C.c_int] + [vp] * 7 + [C.c_int, C.c_int, C.c_int, vp, vp, vp]
     rng = np.random.default_rng(21)
+    n_routed = 0
     for it in range(1500):
         band = int(rng.choice([8, 16, 32]))
         L = int(rng.integers(1, 160))
@@ -159,9 +160,16 @@ def test_flank_payload_dp_matches_traceback_flank_replay(emul, coracle):
         sc, fl, ms = C.c_int(0), C.c_int(0), C.c_int(0)
         rc = emul.emul_dp_flank32(band, L, P(c["read"]), P(c["quals"]), P(c["truth"]), P(c["snv_mask"]), P(c["snv_prior"]), P(c["gap_open"]),
                                   P(c["gap_extend"]), nuc, lhs, rhs, C.byref(sc), C.byref(fl), C.byref(ms))
-        assert rc == 0
+        # rc 2: an in-flank truth 'N' the DP may have charged less than the reference's replay re-adds (flank_replay_may_differ) —
+        # the kernel hands such candidates to the exact traceback path; everything else must be identical
+        assert rc in (0, 2)
+        n_routed += rc == 2
         q8 = c["quals"].astype(np.int8)
         t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
         es, efp, a1, a2 = coracle.align_tb(band, t, r, q8, c["gap_open"], c["gap_extend"], nuc, m, c["snv_prior"])
         efs, ems = coracle.flank_score(W, lhs, rhs, r, q8, m, c["snv_prior"], c["gap_open"], c["gap_extend"], nuc, efp, a1, a2)
-        assert (sc.value, fl.value, ms.value) == (es, efs, ems), (band, L, lhs, rhs)
+        if rc == 0:
+            assert (sc.value, fl.value, ms.value) == (es, efs, ems), (band, L, lhs, rhs)
+        else:
+            assert (sc.value, ms.value) == (es, ems) and fl.value <= efs, (band, L, lhs, rhs)
+    assert n_routed < 40                     # rare with ordinary penalties (needs an in-flank 'N' column with an SNV prior of 1)
