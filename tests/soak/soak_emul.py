@@ -3,7 +3,7 @@ DPX instructions emulated (tests/cpu_emul), against the plain-C oracle AND the r
 low-complexity sequences (ties everywhere), penalties at the extremes of the error-model ranges (and 0), qualities up to the
 16-bit safety bound, long reads.
 
-usage: python tools/soak_emul.py [seed] [cases]
+usage: python tests/soak/soak_emul.py [seed] [cases]
 """
 import ctypes as C
 import os
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import ACGT                                    # noqa: E402
