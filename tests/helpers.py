@@ -97,3 +97,35 @@ def random_positions(rng, haps, reads, max_listed=4):
             row.append(sorted(set(ps)))
         lists.append(row)
     return pack_positions(lists, haps.n, reads.n)
+
+
+def n_rich_flank_region(rng, hap_len=220, n_haps=6, n_reads=60):
+    """Haplotypes with several 'N's (flanks included), SNV priors and read qualities that include 0 and 1, reads over the whole
+    haplotype, and a flank state: the corner where the reference's flank replay charges a truth-'N' mismatch 2 although its DP
+    charged min(q', 2). Returns (haplotypes, reads, (lhs_flank, rhs_flank))."""
+    from octopus_b200.batch import pack_haplotypes, pack_reads
+    base = ACGT[rng.integers(0, 4, hap_len)]
+    seqs, mf, pf, mr, pr, go, ge = [], [], [], [], [], [], []
+    for h in range(n_haps):
+        s = base.copy()
+        for _ in range(int(rng.integers(0, 3))):
+            s[rng.integers(0, hap_len)] = ACGT[rng.integers(0, 4)]
+        s[rng.integers(0, hap_len, int(rng.integers(3, 12)))] = ord("N")
+        seqs.append(s)
+        mf.append(ACGT[rng.integers(0, 4, hap_len)].copy()); mr.append(np.roll(s, -1))
+        pf.append(rng.choice([0, 1, 2, 30, 125], hap_len).astype(np.int8)); pr.append(rng.choice([0, 1, 2, 30, 125], hap_len).astype(np.int8))
+        go.append(rng.integers(3, 46, hap_len).astype(np.int8)); ge.append(rng.integers(1, 11, hap_len).astype(np.int8))
+    haps = pack_haplotypes(seqs, mf, pf, mr, pr, go, ge, begin=np.zeros(n_haps, dtype=np.int64))
+    bases, quals, begins = [], [], []
+    for r in range(n_reads):
+        L = int(rng.choice([30, 50, 76]))
+        p = int(rng.integers(0, hap_len - L + 1))
+        b = base[p:p + L].copy()
+        for _ in range(int(rng.integers(0, 3))):
+            b[rng.integers(0, L)] = ACGT[rng.integers(0, 4)]
+        bases.append(b)
+        quals.append((rng.choice([0, 1, 2, 20, 40], L) if r % 2 else rng.integers(2, 42, L)).astype(np.uint8))
+        begins.append(p)
+    reads = pack_reads(bases, quals, mapq=np.full(n_reads, 60, np.uint8), reverse=(rng.random(n_reads) < 0.5).astype(np.uint8),
+                       begin=np.array(begins, dtype=np.int64))
+    return haps, reads, (int(rng.integers(40, 90)), int(rng.integers(40, 90)))

@@ -375,3 +375,23 @@ def test_populate_matches_the_compiled_reference_populate(engine, refhmm):
         got = engine.populate(cfg, haps, reads, None, flanks)
         ok, worst = _close(got, want)
         assert ok and np.array_equal(got == 0.0, want == 0.0), (trial, worst)
+
+
+def test_flank_discount_with_n_columns_matchable_below_two(engine, coracle, refhmm):
+    """The reference's flank replay charges a mismatch against a truth 'N' exactly 2 although its DP charged min(q', 2)
+    (simd_pair_hmm.hpp:388-392 vs :121-142). Haplotypes with several 'N's inside the flanks, reads with qualities 0 / 1 and SNV
+    priors 0 / 1: every near-flank candidate must still equal the reference (such candidates take the exact traceback kernel)."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from helpers import n_rich_flank_region
+    rng = np.random.default_rng(1234)
+    for trial in range(4):
+        band = [8, 16, 16, 32][trial]
+        haps, reads, flanks = n_rich_flank_region(rng)
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, use_mapping_quality=False)
+        rc, want, wst = coracle.populate(band, haps, reads, None, flanks, use_mapping_quality=False, map_positions=True)
+        got, st = engine.populate(cfg, haps, reads, None, flanks, want_status=True)
+        ok = wst == 0
+        assert np.array_equal(st[~ok], wst[~ok]) and np.array_equal(got[ok], want[ok]), (trial, np.abs(got[ok] - want[ok]).max())   # -ln10/10 * integer: exact
+        if refhmm is not None and rc == 0:
+            st_r, want_r, _ = refhmm.array_populate(band, haps, reads, flanks=flanks, use_mapping_quality=False)
+            assert st_r == 0 and np.allclose(got, want_r, rtol=1e-12, atol=0)

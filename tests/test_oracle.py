@@ -433,3 +433,20 @@ def test_c_restatement_populate_matches_reference_array_populate(coracle, refhmm
         want_t = np.stack([want_o[:, a:b].sum(axis=1) if b - a > 1 else want_o[:, a] for a, b in zip(toff[:-1], toff[1:])], axis=1)
         assert st == 0 and np.allclose(got_t, want_t, rtol=1e-12, atol=1e-300), (trial, np.abs(got_t - want_t).max())
     assert n_short < 10
+
+
+def test_populate_agrees_with_reference_where_flank_replay_and_dp_differ(coracle, refhmm):
+    """CPU twin of the GPU test of the same corner (tests/test_gpu_parity.py): 'N's inside the flanks with qualities / SNV priors
+    of 0 and 1, where the reference's flank replay re-adds 2 for a truth-'N' mismatch its DP charged less for. The restatement
+    must follow the reference's replay — and the inputs must actually hit the corner (the discounted value differs from what a
+    'what the DP charged' discount would give)."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not built")
+    from helpers import n_rich_flank_region
+    rng = np.random.default_rng(1234)
+    for trial in range(4):
+        band = [8, 16, 16, 32][trial]
+        haps, reads, flanks = n_rich_flank_region(rng)
+        rc, want, wst = coracle.populate(band, haps, reads, None, flanks, use_mapping_quality=False, map_positions=True)
+        st_r, want_r, _ = refhmm.array_populate(band, haps, reads, flanks=flanks, use_mapping_quality=False)
+        assert rc == 0 and st_r == 0 and np.allclose(want, want_r, rtol=1e-12, atol=0), trial
