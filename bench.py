@@ -42,6 +42,10 @@ def parse_args():
     ap.add_argument("--flank", default=None, help="LHS,RHS flank sizes: exercises the traceback + flank-discount path")
     ap.add_argument("--shortcut", action="store_true", help="enable the reference's naive shortcut (reference behaviour)")
     ap.add_argument("--map", action="store_true", help="candidate positions from the device k-mer mapper (reference behaviour)")
+    ap.add_argument("--band", type=int, default=None, help="override the config's band (wide-band diagnostics)")
+    ap.add_argument("--hap-len", type=int, default=None, help="override the haplotype length")
+    ap.add_argument("--read-lens", default=None, help="override the read lengths, comma separated")
+    ap.add_argument("--int-scores", action="store_true", help="HaplotypeLikelihoodModel::Config::use_int_scores (reference: int32 lanes)")
     return ap.parse_args()
 
 
@@ -235,10 +239,13 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = synth.CONFIGS[args.config]
     # weak scaling: every rank owns its own batch of the named shape (its own regions' reads), haplotypes replicated
-    haps, reads, band = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=cfg["seed"] + 1000 * rank)
+    read_lens = tuple(int(x) for x in args.read_lens.split(",")) if args.read_lens else None
+    haps, reads, band = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=cfg["seed"] + 1000 * rank,
+                                         band=args.band, hap_len=args.hap_len, read_lens=read_lens)
     H, R = haps.n, reads.n
     cells = synth.total_cells(haps, reads, band)
-    model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=not args.shortcut, map_positions=args.map)
+    model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=not args.shortcut, map_positions=args.map,
+                                                use_int_scores=args.int_scores)
     flank_state = tuple(int(x) for x in args.flank.split(",")) if args.flank else None
     eng = PairHMMEngine(local)
     d_haps, d_reads = haps.to_device(dev), reads.to_device(dev)
@@ -318,7 +325,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, R, "/".join(map(str, cfg["read_lens"])), H, cfg["hap_len"], band),
+            "config": {"workload": workload_name(args.config, R, (args.read_lens or "/".join(map(str, cfg["read_lens"]))).replace(",", "/"), H, args.hap_len or cfg["hap_len"], band),
                        "alignments_per_step": H * R * world, "cells_per_step": cells * world,
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
                        "parallelism": "reads sharded over %d rank(s), haplotypes replicated, NCCL gather to rank 0" % world,

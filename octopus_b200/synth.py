@@ -122,9 +122,16 @@ def make_reads(rng, haps: HaplotypeBlock, n_reads, read_lens, band, profile):
     return ReadBlock(off, bases, quals, np.full(n_reads, 60, dtype=np.uint8), reverse, begin)
 
 
-def make_batch(config="C1", n_reads=None, n_haps=None, seed=None):
-    """(haplotypes, reads, band) for a named BASELINE config, optionally down-sized (same shapes, fewer reads / haplotypes)."""
+def make_batch(config="C1", n_reads=None, n_haps=None, seed=None, band=None, hap_len=None, read_lens=None):
+    """(haplotypes, reads, band) for a named BASELINE config, optionally down-sized (same shapes, fewer reads / haplotypes)
+    or re-shaped (band / haplotype length / read lengths overridden: the wide-band and long-read diagnostics)."""
     c = dict(CONFIGS[config])
+    if band is not None:
+        c["band"] = int(band)
+    if hap_len is not None:
+        c["hap_len"] = int(hap_len)
+    if read_lens is not None:
+        c["read_lens"] = tuple(int(x) for x in read_lens)
     if n_reads is not None:
         c["n_reads"] = int(n_reads)
     if n_haps is not None:
