@@ -192,6 +192,35 @@ int phmm_populate_templates(phmm_engine* e, const phmm_config* cfg,
 int phmm_genotype_likelihoods(phmm_engine* e, const double* lnl, int32_t n_haplotypes, int32_t n_reads,
                               const int32_t* genotypes, int32_t n_genotypes, int32_t ploidy, double* out, int space);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * HaplotypeLikelihoodModel::reset (haplotype_likelihood_model.cpp:60-78): the per-haplotype penalty arrays of phmm_haplotypes
+ * from the haplotype sequences, by the reference's error models — host C++ (octopus_b200/csrc/phmm_error_model.cpp), no GPU
+ * needed, bit-identical to core/models/error/ (repeat_based_indel_error_model.cpp:67-83, repeat_based_snv_error_model.cpp:144-179)
+ * including the exact output of the tandem-repeat finder they call (lib/tandem).
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct phmm_error_model phmm_error_model;
+
+/* make_error_model(label) (error_model_factory.cpp:531-559): "<library>[.<sequencer>]", case-insensitive, e.g. the reference's
+ * default "PCR-free.HiSeq-2500" (config/option_parser.cpp:571-573); NULL / "" = that default. Libraries PCR, PCR-free (PCRF), 10X,
+ * MDA; sequencers HiSeq-2000/2500/4000, X10, NovaSeq, BGISEQ-500, PacBio, PacBioCCS (no SNV model for the last two). */
+int  phmm_error_model_create(phmm_error_model** out, const char* label);
+/* make_error_model(file) (:561-589): the text of a custom indel model ("MOTIF:p0,p1,..." open rows, "MOTIF+:" extension rows,
+ * '#' comments; custom_repeat_based_indel_error_model.cpp:104-158) with the default SNV model. */
+int  phmm_error_model_create_custom(phmm_error_model** out, const char* model_text);
+void phmm_error_model_destroy(phmm_error_model* m);
+const char* phmm_error_model_last_error(void);   /* thread-local message of the last failing phmm_error_model_* / phmm_reset_* call */
+
+/* reset() for n haplotypes at once: fills the six per-base arrays (same layout as phmm_haplotypes, host memory). is_substitution:
+ * optional per-base flags — bases that are substitutions in Haplotype::cigar() keep the maximum SNV prior
+ * (repeat_based_snv_error_model.cpp:128-140, 166-170); NULL = none. n_threads <= 0: one per hardware thread (at most one per haplotype). */
+int  phmm_reset_haplotypes(const phmm_error_model* m, int32_t n, const int64_t* off, const char* seq, const uint8_t* is_substitution,
+                           char* snv_mask_fwd, int8_t* snv_prior_fwd, char* snv_mask_rev, int8_t* snv_prior_rev,
+                           int8_t* gap_open, int8_t* gap_extend, int32_t n_threads);
+
+/* tandem::extract_exact_tandem_repeats(seq, min_period, max_period) (lib/tandem/tandem.hpp:504-521): (pos, length, period) triples in
+ * the library's output order. Returns the number of repeats (only the first cap are written), or a negative error code. */
+int  phmm_tandem_repeats(const char* seq, int32_t n, int32_t min_period, int32_t max_period, uint32_t* out_triples, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

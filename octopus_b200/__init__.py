@@ -5,7 +5,7 @@ the host-side mirror used by the tests and the benchmark: a ctypes binding (``_l
 (``batch``), the reference-shaped wrappers (``api``) and the synthetic workload generator (``synth``).
 There is no CPU fallback: importing works anywhere, computing requires a B200.
 """
-from .api import HaplotypeLikelihoodArray, HaplotypeLikelihoodModel, PairHMMEngine, PhmmError, ShortHaplotypeError  # noqa: F401
+from .api import ErrorModel, HaplotypeLikelihoodArray, HaplotypeLikelihoodModel, PairHMMEngine, PhmmError, ShortHaplotypeError  # noqa: F401
 from .batch import HaplotypeBlock, ReadBlock, pack_haplotypes, pack_reads  # noqa: F401
 
 __version__ = "0.1.0"

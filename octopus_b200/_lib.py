@@ -9,7 +9,9 @@ PHMM_OK, PHMM_ERR_INVALID, PHMM_ERR_CUDA, PHMM_ERR_BAND, PHMM_ERR_SHORT_HAPLOTYP
 SPACE_HOST, SPACE_DEVICE = 0, 1
 
 EXPORTS = ["phmm_version", "phmm_default_config", "phmm_create", "phmm_destroy", "phmm_last_error", "phmm_launch_count",
-           "phmm_last_dp_kernel_ms", "phmm_last_dp_cells", "phmm_align_scores", "phmm_align_traceback", "phmm_align_reads", "phmm_genotype_likelihoods", "phmm_populate", "phmm_populate_templates"]
+           "phmm_last_dp_kernel_ms", "phmm_last_dp_cells", "phmm_align_scores", "phmm_align_traceback", "phmm_align_reads", "phmm_genotype_likelihoods", "phmm_populate", "phmm_populate_templates",
+           "phmm_error_model_create", "phmm_error_model_create_custom", "phmm_error_model_destroy", "phmm_error_model_last_error",
+           "phmm_reset_haplotypes", "phmm_tandem_repeats"]
 
 
 class Config(C.Structure):
@@ -84,5 +86,15 @@ def load():
     lib.phmm_populate_templates.restype = C.c_int
     lib.phmm_populate_templates.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Haplotypes), C.POINTER(Reads), C.c_void_p, C.c_int32,
                                             C.POINTER(Positions), C.POINTER(FlankState), C.c_void_p, C.c_void_p, C.c_int]
+    lib.phmm_error_model_create.restype = C.c_int
+    lib.phmm_error_model_create.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+    lib.phmm_error_model_create_custom.restype = C.c_int
+    lib.phmm_error_model_create_custom.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+    lib.phmm_error_model_destroy.argtypes = [C.c_void_p]
+    lib.phmm_error_model_last_error.restype = C.c_char_p
+    lib.phmm_reset_haplotypes.restype = C.c_int
+    lib.phmm_reset_haplotypes.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9 + [C.c_int32]
+    lib.phmm_tandem_repeats.restype = C.c_int
+    lib.phmm_tandem_repeats.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
     _lib = lib
     return lib

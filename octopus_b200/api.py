@@ -249,6 +249,69 @@ class PairHMMEngine:
         return (out, status) if want_status else out
 
 
+class ErrorModel:
+    """The reference's sequencing-error models behind HaplotypeLikelihoodModel::reset (haplotype_likelihood_model.cpp:60-78):
+    make_error_model(label) / make_error_model(file) (core/models/error/error_model_factory.cpp:531-589). ``reset`` turns
+    haplotype sequences into the HaplotypeBlock the engine consumes (host C++ inside libphmm_b200.so, no GPU involved)."""
+
+    def __init__(self, label=None, custom_model_text=None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        if custom_model_text is not None:
+            rc = self._lib.phmm_error_model_create_custom(C.byref(h), custom_model_text.encode() if isinstance(custom_model_text, str) else custom_model_text)
+        else:
+            rc = self._lib.phmm_error_model_create(C.byref(h), None if label is None else label.encode())
+        if rc != _lib.PHMM_OK:
+            raise PhmmError(rc, self._lib.phmm_error_model_last_error().decode())
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.phmm_error_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tandem_repeats(self, sequence, min_period=1, max_period=5):
+        """tandem::extract_exact_tandem_repeats (lib/tandem/tandem.hpp:504-521): (n, 3) uint32 rows (pos, length, period)."""
+        s = np.ascontiguousarray(np.frombuffer(sequence.encode() if isinstance(sequence, str) else bytes(sequence), dtype=np.uint8))
+        cap = 4 * len(s) + 16
+        while True:
+            out = np.zeros((cap, 3), dtype=np.uint32)
+            n = self._lib.phmm_tandem_repeats(s.ctypes.data, len(s), int(min_period), int(max_period), out.ctypes.data, cap)
+            if n < 0:
+                raise PhmmError(n, self._lib.phmm_error_model_last_error().decode())
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def reset(self, sequences, begin=None, is_substitution=None, n_threads=0):
+        """HaplotypeLikelihoodModel::reset for every haplotype: sequences (list of str / bytes / uint8 arrays) → HaplotypeBlock
+        with the SNV masks / priors and gap penalties the reference's models assign. ``is_substitution``: optional list of
+        per-base flag arrays (bases that are substitutions in Haplotype::cigar())."""
+        parts = [np.frombuffer(x.encode() if isinstance(x, str) else bytes(x), dtype=np.uint8) if not isinstance(x, np.ndarray) else
+                 np.ascontiguousarray(x).view(np.uint8).reshape(-1) for x in sequences]
+        off = np.zeros(len(parts) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in parts], out=off[1:])
+        seq = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.uint8)
+        return self.reset_block(off, seq, begin, None if is_substitution is None else
+                                np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8) for x in is_substitution])), n_threads)
+
+    def reset_block(self, off, seq, begin=None, is_substitution=None, n_threads=0):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        total = int(off[-1])
+        mf, mr = np.empty(total, dtype=np.uint8), np.empty(total, dtype=np.uint8)
+        pf, pr, go, ge = (np.empty(total, dtype=np.int8) for _ in range(4))
+        rc = self._lib.phmm_reset_haplotypes(self._h, len(off) - 1, off.ctypes.data, seq.ctypes.data,
+                                             None if is_substitution is None else is_substitution.ctypes.data,
+                                             mf.ctypes.data, pf.ctypes.data, mr.ctypes.data, pr.ctypes.data, go.ctypes.data, ge.ctypes.data, int(n_threads))
+        if rc != _lib.PHMM_OK:
+            raise PhmmError(rc, self._lib.phmm_error_model_last_error().decode())
+        return HaplotypeBlock(off, seq, mf, pf, mr, pr, go, ge, begin)
+
+
 class HaplotypeLikelihoodModel:
     """Configuration holder with the reference's names (the per-haplotype state lives in the HaplotypeBlock)."""
 

@@ -6,8 +6,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libphmm_b200.so")
-SOURCES = ["phmm_engine.cu"]
-DEPS = ["phmm_engine.cu", "phmm_kernels.cuh", "phmm_device.cuh", os.path.join("..", "..", "include", "phmm_b200.h")]
+SOURCES = ["phmm_engine.cu", "phmm_error_model.cpp"]
+DEPS = ["phmm_engine.cu", "phmm_kernels.cuh", "phmm_device.cuh", "phmm_error_model.cpp", "phmm_error_model_tables.inc", os.path.join("..", "..", "include", "phmm_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -237,6 +237,217 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Multi-lane band: the 2B diagonals of one alignment (pair) split over NL neighbouring lanes of a warp
+// ---------------------------------------------------------------------------------------------------------
+//
+// Bands of 32 and more do not fit one thread's registers (band 32 = 128 band registers: the single-thread kernel spilled
+// and ran at 46 % of the ALU pipe, profiles/r02a). Here every lane owns a CHUNK of C consecutive diagonals (C = 32, or 16
+// for the 16-diagonal band) and sweeps it column by column exactly like dp_pair sweeps the whole band; NL = 2B / C lanes
+// cooperate on one alignment. The two dependencies that cross a chunk boundary:
+//   I  (x, y) -> (x, y+1): diagonal k -> k-1, SAME column  => the lane above must have finished the column first
+//   D  (x, y) -> (x+1, y): diagonal k -> k+1, NEXT column  => the lane below must have started the previous column
+// are both met when lane j+1 runs exactly ONE column ahead of lane j: in a step every lane first computes its TOP cell (whose
+// D arrival the lane above needs for the last cell of the same step: one SHFL up), then the rest of its column, and hands
+// the insertion chain leaving its bottom diagonal to the lane below for the next step (one SHFL down). Two shuffles per
+// C cells; the price is the skew (NL - 1 extra steps) and divergence while neighbouring lanes are in different column
+// bodies (prologue / steady / epilogue) — measured in profiles/.
+// The lane functions are __host__ __device__ and split at the two exchange points so that tests/cpu_emul can run NL lanes
+// in lock-step on the CPU; dp_band below is the device driver with the real shuffles.
+//
+// Traits select the value type: Lanes16 = two alignments per lane group packed s16x2 (as dp_pair), Lanes32 = one alignment
+// in 32-bit lanes (int scores, long or high-quality-sum reads, reads holding 'N': the PRMT lookup has the fifth cap).
+PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t umin3_32(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }            // VIMNMX3.U32
+__device__ __forceinline__ uint32_t uaddmin32(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u32(a, b, c); }        // VIADDMNMX.U32: min(a+b, c)
+#else
+inline uint32_t umin3_32(uint32_t a, uint32_t b, uint32_t c) { return umin32(umin32(a, b), c); }
+inline uint32_t uaddmin32(uint32_t a, uint32_t b, uint32_t c) { return umin32(a + b, c); }
+#endif
+
+struct Lanes16 {
+    typedef uint32_t V;
+    struct Tab { const ColEntry* t0; const ColEntry* t1; };
+    struct Ent { ColEntry a, b; };
+    struct Col { uint32_t caps0, caps1, go, ge; };
+    static PHMM_HD V inf() { return kInf16x2; }
+    static PHMM_HD V both(const int v) { return (uint32_t)v | ((uint32_t)v << 16); }
+    static PHMM_HD Ent load(const Tab& t, const int x) { Ent e; e.a = ldg(t.t0 + x); e.b = ldg(t.t1 + x); return e; }
+    static PHMM_HD Col decode(const Ent& e)
+    {
+        Col c; c.caps0 = e.a.x; c.caps1 = e.b.x; c.go = prmt(e.a.y, e.b.y, 0x3430u); c.ge = prmt(e.a.y, e.b.y, 0x3531u); return c;
+    }
+    // keep the prefetched entries out of the live registers until the column is done (see dp_pair); tie is never negative
+    static PHMM_HD void pin(Ent& dst, const Ent& src, const V tie)
+    {
+        const uint32_t z = tie & 0x80008000u;
+        dst.a.x = src.a.x + z; dst.a.y = src.a.y + z; dst.b.x = src.b.x + z; dst.b.y = src.b.y + z;
+    }
+    static PHMM_HD V sub(const RowEntry& w, const Col& c) { return vmin2(w.y, prmt(c.caps0, c.caps1, w.x)); }
+    static PHMM_HD V min2(V a, V b) { return vmin2(a, b); }
+    static PHMM_HD V min3(V a, V b, V c) { return vmin3(a, b, c); }
+    static PHMM_HD V addmin(V a, V b, V c) { return vaddmin(a, b, c); }
+};
+struct Lanes32 {
+    typedef uint32_t V;
+    struct Tab { const ColEntry* t0; };
+    struct Ent { ColEntry a; };
+    struct Col { uint32_t caps0, caps1, go, ge; };      // caps1 = the cap for a read 'N' (second PRMT operand, bytes 1..3 zero)
+    static PHMM_HD V inf() { return (uint32_t)kInf32; }
+    static PHMM_HD V both(const int v) { return (uint32_t)v; }
+    static PHMM_HD Ent load(const Tab& t, const int x) { Ent e; e.a = ldg(t.t0 + x); return e; }
+    static PHMM_HD Col decode(const Ent& e)
+    {
+        Col c; c.caps0 = e.a.x; c.caps1 = (e.a.y >> 16) & 0xFFu; c.go = e.a.y & 0xFFu; c.ge = (e.a.y >> 8) & 0xFFu; return c;
+    }
+    static PHMM_HD void pin(Ent& dst, const Ent& src, const V tie) { const uint32_t z = tie & 0x80000000u; dst.a.x = src.a.x + z; dst.a.y = src.a.y + z; }
+    static PHMM_HD V sub(const RowEntry& w, const Col& c) { return umin32(w.y, prmt(c.caps0, c.caps1, w.x)); }   // rows: make_row_entry32
+    static PHMM_HD V min2(V a, V b) { return umin32(a, b); }
+    static PHMM_HD V min3(V a, V b, V c) { return umin3_32(a, b, c); }
+    static PHMM_HD V addmin(V a, V b, V c) { return uaddmin32(a, b, c); }
+};
+
+#define PHMM_REP32(F)    PHMM_REP8(F, 24) PHMM_REP8(F, 16) PHMM_REP8(F, 8) PHMM_REP8(F, 0)
+
+template <class T, int C>
+struct BandLane {
+    typename T::V M[C], D[C];
+    typename T::V i_run;      // before the top phase: the I arrival entering this lane's top diagonal; after the rest phase: the one leaving its bottom diagonal
+    typename T::V d_out;      // after the top phase: the D arrival this lane's top cell sends to the bottom diagonal of the lane above
+    typename T::Ent e, next;  // table entries of the column being processed / prefetched for the next one
+    typename T::Col col;
+    typename T::V gop, gep, go_prev, ge_prev;
+    bool active;
+};
+
+// first_col: the first window column this lane processes (j * C); the penalties of the column before it feed its insertions
+template <class T, int C>
+PHMM_HD void band_lane_init(BandLane<T, C>& s, const typename T::Tab& tab, const int first_col)
+{
+#pragma unroll
+    for (int k = 0; k < C; ++k) { s.M[k] = 0u; s.D[k] = T::inf(); }
+    s.i_run = T::inf(); s.d_out = T::inf();
+    s.e = T::load(tab, first_col);
+    s.go_prev = 0u; s.ge_prev = 0u;
+    if (first_col > 0) { const typename T::Col c = T::decode(T::load(tab, first_col - 1)); s.go_prev = c.go; s.ge_prev = c.ge; }
+    s.active = false;
+}
+
+// Phase 1 of a step: column operands and the top cell (diagonal C-1 of the chunk), which exists from local column C on.
+// xl = column relative to the lane's first column, x = xl + first_col the window column, W the window length.
+template <class T, int C>
+PHMM_HD void band_lane_top(BandLane<T, C>& s, const RowEntry* __restrict__ rows, const int L, const int xl, const int x, const int W,
+                           const typename T::Tab& tab, const typename T::V nucp, const bool is_top_lane)
+{
+    s.d_out = T::inf();
+    s.active = xl >= 0 && xl <= L + C - 1;
+    if (!s.active) return;
+    s.next = T::load(tab, x + 1 < W ? x + 1 : W - 1);
+    s.col = T::decode(s.e);
+    s.gop = s.go_prev + nucp;
+    s.gep = s.ge_prev + nucp;
+    if (is_top_lane) s.i_run = T::inf();
+    if (xl >= C) {
+        const RowEntry w = rows[xl - (C - 1)];
+        const typename T::V sub = T::sub(w, s.col), m = s.M[C - 1], d = s.D[C - 1];
+        s.M[C - 1] = T::min3(m, s.i_run, d) + sub;
+        s.d_out = T::addmin(d, s.col.ge, T::min2(m, s.i_run) + s.col.go);
+        s.i_run = T::addmin(s.i_run, s.gep, m + s.gop);
+    }
+}
+
+// Phase 2: the remaining cells of the column. d_in = the d_out of the lane below (same step); ignored by the bottom lane.
+template <class T, int C>
+PHMM_HD void band_lane_rest(BandLane<T, C>& s, const RowEntry* __restrict__ rows, const int L, const int xl, const int x,
+                            const typename T::V d_in, const bool is_bottom_lane)
+{
+    if (!s.active) { s.i_run = T::inf(); return; }
+    s.D[0] = is_bottom_lane ? T::inf() : d_in;
+    const RowEntry* rp = rows + xl;
+    const typename T::Col col = s.col;
+    const typename T::V gop = s.gop, gep = s.gep;
+    typename T::V i_run = s.i_run;
+#define PHMM_BCELL(k)                                                                          \
+    {                                                                                           \
+        const RowEntry w = rp[-(k)];                                                            \
+        const typename T::V sub = T::sub(w, col);                                               \
+        const typename T::V m = s.M[(k) < C ? (k) : 0], d = s.D[(k) < C ? (k) : 0];            \
+        s.M[(k) < C ? (k) : 0] = T::min3(m, i_run, d) + sub;                                    \
+        if ((k) + 1 < C) s.D[((k) + 1) < C ? (k) + 1 : 0] = T::addmin(d, col.ge, T::min2(m, i_run) + col.go); \
+        i_run = T::addmin(i_run, gep, m + gop);                                                 \
+    }
+#define PHMM_BCASE_PROLOGUE(k) case (k) + 1: if ((k) + 1 < C) PHMM_BCELL(k)
+#define PHMM_BCASE_ROW0(k)     case (k): if ((k) < C) s.M[(k) < C ? (k) : 0] = sub0; break;
+    if (xl >= C) {
+        if (xl <= L) {
+#pragma unroll
+            for (int k = C - 2; k >= 0; --k) PHMM_BCELL(k)
+        } else {
+            const int klo = xl - L;              // the row-L cell; klo == C-1 means the top cell was it
+#pragma unroll
+            for (int k = C - 2; k >= 0; --k) {
+                if (k < klo) break;
+                PHMM_BCELL(k)
+            }
+        }
+    } else {
+        // the free-start cell (x, 0) sits on this chunk's diagonal xl
+        const typename T::V sub0 = T::sub(rows[0], col);
+        i_run = (x & 1) ? gop : T::inf();
+        if (xl <= L) {
+            switch (xl) { PHMM_REP32(PHMM_BCASE_PROLOGUE) default: break; }
+        } else {
+            const int klo = xl - L;
+#pragma unroll
+            for (int k = C - 2; k >= 0; --k) {
+                if (k < xl && k >= klo) PHMM_BCELL(k)
+            }
+        }
+        switch (xl) { PHMM_REP32(PHMM_BCASE_ROW0) default: break; }
+    }
+#undef PHMM_BCELL
+#undef PHMM_BCASE_PROLOGUE
+#undef PHMM_BCASE_ROW0
+    s.go_prev = col.go; s.ge_prev = col.ge;
+    T::pin(s.e, s.next, i_run);
+    s.i_run = i_run;
+}
+
+template <class T, int C>
+PHMM_HD typename T::V band_lane_result(const BandLane<T, C>& s)
+{
+    typename T::V best = s.M[0];
+#pragma unroll
+    for (int k = 1; k < C; ++k) best = T::min2(best, s.M[k]);
+    return best;
+}
+
+#ifdef __CUDACC__
+// Device driver. Lanes j = 0..NL-1 of a group are NL consecutive lanes of the warp (group-aligned); every lane of the warp
+// must call this with the same L (the loop and its shuffles are warp-wide). Returns the group's result in all of its lanes.
+template <class T, int C, int NL>
+__device__ __forceinline__ typename T::V dp_band(const RowEntry* __restrict__ rows, const int L, const typename T::Tab& tab,
+                                                 const typename T::V nucp, const int j)
+{
+    BandLane<T, C> s;
+    const int W = L + NL * C - 1;
+    band_lane_init<T, C>(s, tab, j * C);
+    for (int t = 0; t <= W; ++t) {
+        const int x = t - (NL - 1 - j), xl = x - j * C;
+        band_lane_top<T, C>(s, rows, L, xl, x, W, tab, nucp, j == NL - 1);
+        typename T::V d_in = T::inf();
+        if (NL > 1) d_in = __shfl_up_sync(0xffffffffu, s.d_out, 1);
+        band_lane_rest<T, C>(s, rows, L, xl, x, d_in, j == 0);
+        if (NL > 1) { const typename T::V v = __shfl_down_sync(0xffffffffu, s.i_run, 1); s.i_run = (j == NL - 1) ? T::inf() : v; }
+    }
+    typename T::V best = band_lane_result<T, C>(s);
+#pragma unroll
+    for (int o = 1; o < NL; o <<= 1) best = T::min2(best, __shfl_xor_sync(0xffffffffu, best, o));
+    return best;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
 // Flank-aware path: one alignment per thread, 32-bit lanes = score | label | payload, band state in registers
 // ---------------------------------------------------------------------------------------------------------
 //
@@ -257,8 +468,6 @@ constexpr uint32_t kF32LabD       = 3u << 16;
 constexpr uint32_t kF32Inf        = 0x3800u << kF32ScoreShift;       // +inf score (14336), leaves room for +2*127+nuc below 2^14
 constexpr int      kMaxScoreFlank32 = 0x3800 - 1024;                  // read quality-sum bound for this path
 constexpr uint32_t kF32Valid = 0x80u, kF32TypeD = 0x40u;
-
-PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Row entries of this kernel (one read, not a pair): .x = PRMT selector picking the cap byte of the read base into byte 0
 // and zeros elsewhere (code | 0x5550 — bytes 1..3 of the second operand are zero; code 4 = 'N' picks byte 0 of the second PRMT operand, the column's capN), .y = base quality.

@@ -69,6 +69,49 @@ def _i8(x):
     return a, a.ctypes.data_as(_i8p)
 
 
+class RefErrorModel:
+    """The UNMODIFIED reference error models + lib/tandem (``oracle/_ref/libref_errmodel.so``, ``oracle/ref_errmodel_driver.cpp``):
+    what HaplotypeLikelihoodModel::reset computes per haplotype. Checker for octopus_b200.ErrorModel."""
+    PATH = os.path.join(REF_DIR, "libref_errmodel.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        self.lib = C.CDLL(self.PATH)
+        self.lib.ref_tandem_repeats.restype = C.c_int
+        self.lib.ref_tandem_repeats.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        for name in ("ref_errmodel_reset", "ref_errmodel_reset_custom"):
+            f = getattr(self.lib, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p] + [C.c_void_p] * 6
+
+    def tandem_repeats(self, seq, min_period, max_period):
+        s = bytes(seq)
+        cap = 4 * len(s) + 16
+        out = np.zeros((cap, 3), dtype=np.uint32)
+        n = self.lib.ref_tandem_repeats(s, len(s), min_period, max_period, out.ctypes.data, cap)
+        assert 0 <= n <= cap
+        return out[:n]
+
+    def reset(self, seq, label="PCR-free.HiSeq-2500", is_substitution=None, custom_model_text=None):
+        """One haplotype → dict of the six arrays (+ 'rc': 1 with an SNV model, 0 without, < 0 on a model error)."""
+        s = bytes(seq)
+        n = len(s)
+        names = ("snv_mask_fwd", "snv_prior_fwd", "snv_mask_rev", "snv_prior_rev", "gap_open", "gap_extend")
+        arrs = [np.zeros(n, dtype=np.uint8 if "mask" in k else np.int8) for k in names]
+        sub = None if is_substitution is None else np.ascontiguousarray(is_substitution, dtype=np.uint8)
+        ptrs = [a.ctypes.data for a in arrs]
+        if custom_model_text is not None:
+            rc = self.lib.ref_errmodel_reset_custom(custom_model_text.encode(), s, n, None if sub is None else sub.ctypes.data, *ptrs)
+        else:
+            rc = self.lib.ref_errmodel_reset(label.encode(), s, n, None if sub is None else sub.ctypes.data, *ptrs)
+        out = dict(zip(names, arrs))
+        out["rc"] = rc
+        return out
+
+
 class RefKernel:
     """The reference kernel for one ISA build ('sse' | 'avx2' | 'avx512'). isa_force_sse2 → SSE2 policy even in a wider build."""
 

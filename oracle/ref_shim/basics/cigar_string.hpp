@@ -21,5 +21,11 @@ private:
     Flag flag_ = Flag::alignmentMatch;
 };
 using CigarString = std::vector<CigarOperation>;
+// basics/cigar_string.hpp: operations that consume read / haplotype sequence (used by the SNV error model's substitution mask)
+inline bool advances_sequence(const CigarOperation& op) noexcept
+{
+    using Flag = CigarOperation::Flag;
+    return !(op.flag() == Flag::deletion || op.flag() == Flag::hardClipped);   // basics/cigar_string.cpp:89-98
+}
 } // namespace octopus
 #endif

@@ -6,7 +6,9 @@
 #include <functional>
 #include <string>
 #include <utility>
+#include <vector>
 #include "basics/contig_region.hpp"
+#include "basics/cigar_string.hpp"
 namespace octopus {
 class Haplotype
 {
@@ -16,7 +18,23 @@ public:
     : sequence_ {std::move(sequence)}, region_ {begin, static_cast<ContigRegion::Position>(begin + sequence_.size())} {}
     const NucleotideSequence& sequence() const noexcept { return sequence_; }
     const ContigRegion& mapped_region() const noexcept { return region_; }
+    // Haplotype::cigar() (core/types/haplotype.hpp): '=' / 'X' / 'I' / 'D' against the reference. The stand-in is told which
+    // bases are substitutions (all the SNV error model reads from it, repeat_based_snv_error_model.cpp:128-140).
+    void set_substitutions(std::vector<bool> is_substitution) { substitutions_ = std::move(is_substitution); }
+    CigarString cigar() const
+    {
+        CigarString result {};
+        for (std::size_t i = 0; i < sequence_.size();) {
+            const bool sub = i < substitutions_.size() && substitutions_[i];
+            std::size_t j = i + 1;
+            while (j < sequence_.size() && (j < substitutions_.size() && substitutions_[j]) == sub) ++j;
+            result.emplace_back(static_cast<CigarOperation::Size>(j - i), sub ? CigarOperation::Flag::substitution : CigarOperation::Flag::sequenceMatch);
+            i = j;
+        }
+        return result;
+    }
 private:
+    std::vector<bool> substitutions_;
     NucleotideSequence sequence_;
     ContigRegion region_;
 };

@@ -135,3 +135,78 @@ extern "C" int emul_dp_flank32(int band, int L, const char* read, const uint8_t*
     for (int y = 0; y < L; ++y) low_quality = low_quality || q[y] < 2;
     return flank_replay_may_differ(t.data(), W, lhs_flank, rhs_flank, low_quality) ? 2 : 0;
 }
+
+// The multi-lane band core (band_lane_* in phmm_device.cuh) with its NL lanes stepped in lock-step on the CPU: the two
+// exchanges dp_band performs with shuffles are done by hand between the phases.
+template <class T, int C, int NL>
+static typename T::V run_band(const RowEntry* rows, int L, const typename T::Tab& tab, typename T::V nucp)
+{
+    static BandLane<T, C> s[NL];
+    const int W = L + NL * C - 1;
+    for (int j = 0; j < NL; ++j) band_lane_init<T, C>(s[j], tab, j * C);
+    for (int t = 0; t <= W; ++t) {
+        typename T::V d_in[NL], i_in[NL];
+        for (int j = 0; j < NL; ++j) { const int x = t - (NL - 1 - j); band_lane_top<T, C>(s[j], rows, L, x - j * C, x, W, tab, nucp, j == NL - 1); }
+        for (int j = 0; j < NL; ++j) d_in[j] = j > 0 ? s[j - 1].d_out : T::inf();
+        for (int j = 0; j < NL; ++j) { const int x = t - (NL - 1 - j); band_lane_rest<T, C>(s[j], rows, L, x - j * C, x, d_in[j], j == 0); }
+        for (int j = 0; j < NL; ++j) i_in[j] = j < NL - 1 ? s[j + 1].i_run : T::inf();
+        for (int j = 0; j < NL; ++j) s[j].i_run = i_in[j];
+    }
+    typename T::V best = band_lane_result<T, C>(s[0]);
+    for (int j = 1; j < NL; ++j) best = T::min2(best, band_lane_result<T, C>(s[j]));
+    return best;
+}
+
+template <class T>
+static int run_band_any(int band, const RowEntry* rows, int L, const typename T::Tab& tab, typename T::V nucp, typename T::V* out)
+{
+    switch (band) {
+        case 8:   *out = run_band<T, 16, 1>(rows, L, tab, nucp); return 0;
+        case 16:  *out = run_band<T, 32, 1>(rows, L, tab, nucp); return 0;
+        case 32:  *out = run_band<T, 32, 2>(rows, L, tab, nucp); return 0;
+        case 64:  *out = run_band<T, 32, 4>(rows, L, tab, nucp); return 0;
+        case 128: *out = run_band<T, 32, 8>(rows, L, tab, nucp); return 0;
+        case 256: *out = run_band<T, 32, 16>(rows, L, tab, nucp); return 0;
+        default: return -1;
+    }
+}
+
+// word32 == 0: two alignments of equal read length through the packed s16x2 lanes (read bases ACGT only);
+// word32 != 0: alignment 0 alone through the 32-bit lanes (read bases ACGTN). Same argument layout as emul_dp_pair.
+extern "C" int emul_dp_band(int word32, int band, int L, const char* read0, const uint8_t* q0, const char* read1, const uint8_t* q1,
+                            const char* truth0, const char* mask0, const int8_t* prior0, const int8_t* go0, const int8_t* ge0,
+                            const char* truth1, const char* mask1, const int8_t* prior1, const int8_t* go1, const int8_t* ge1,
+                            int nuc_prior, int* score0, int* score1)
+{
+    const int W = L + 2 * band - 1;
+    std::vector<RowEntry> rows(L + 1);
+    std::vector<ColEntry> t0(W), t1(W);
+    for (int x = 0; x < W; ++x) {
+        t0[x] = make_col_entry(truth0[x], mask0[x], prior0[x], go0[x], ge0[x]);
+        t1[x] = make_col_entry(truth1[x], mask1[x], prior1[x], go1[x], ge1[x]);
+    }
+    if (word32) {
+        for (int y = 0; y < L; ++y) {
+            const int c = base_code(read0[y]);
+            if (c < 0) return -1;
+            rows[y] = make_row_entry32((uint32_t)c | ((uint32_t)q0[y] << 8));
+        }
+        rows[L] = pad_row_entry32();
+        Lanes32::V r;
+        const Lanes32::Tab tab {t0.data()};
+        if (run_band_any<Lanes32>(band, rows.data(), L, tab, Lanes32::both(nuc_prior), &r)) return -1;
+        *score0 = (int)r; *score1 = (int)r;
+        return 0;
+    }
+    for (int y = 0; y < L; ++y) {
+        const int c0 = base_code(read0[y]), c1 = base_code(read1[y]);
+        if (c0 < 0 || c1 < 0 || c0 > 3 || c1 > 3) return -1;
+        rows[y] = make_row_entry((uint32_t)c0 | ((uint32_t)q0[y] << 8), (uint32_t)c1 | ((uint32_t)q1[y] << 8));
+    }
+    rows[L] = pad_row_entry();
+    Lanes16::V r;
+    const Lanes16::Tab tab {t0.data(), t1.data()};
+    if (run_band_any<Lanes16>(band, rows.data(), L, tab, Lanes16::both(nuc_prior), &r)) return -1;
+    *score0 = (int)(r & 0xFFFF); *score1 = (int)(r >> 16);
+    return 0;
+}
