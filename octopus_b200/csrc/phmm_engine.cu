@@ -61,7 +61,7 @@ struct phmm_engine {
     DBuf r_off, r_bases, r_quals, r_mapq, r_rev, r_begin;
     DBuf c_off, c_pos;
     // derived / scratch
-    DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, bp;
+    DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, wide_reads, bp;
     DBuf tasks_lane, tasks_generic, works, scores;
     DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, gcnt, sched, sorted;
     std::vector<cudaEvent_t> tile_events;
@@ -335,7 +335,7 @@ void phmm_destroy(phmm_engine* e)
     DBuf* all[] = {&e->h_off, &e->h_seq, &e->h_mf, &e->h_pf, &e->h_mr, &e->h_pr, &e->h_go, &e->h_ge, &e->h_begin,
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
-                   &e->counters, &e->pairs, &e->generic_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
+                   &e->counters, &e->pairs, &e->generic_reads, &e->wide_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
                    &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->gcnt, &e->sched, &e->sorted};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
@@ -382,40 +382,45 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         tk = th.data();
     }
     const int n = (int)n_tasks, H = s.hp.n, R = s.rd.n;
-    std::vector<int> fast_idx;
+    std::vector<int> fast_idx, wide_idx;
     std::vector<GenericTask> gen;
-    const bool fast_ok = band <= 32 && precision_bits == 16;
+    // packed s16x2 lanes where they are exact (precision 16, ACGT reads whose quality sum fits); 32-bit multi-lane kernel for the
+    // rest of the ACGTN reads; thread-per-task generic kernel for foreign bytes / qualities above 127 / reads beyond shared memory
+    const int NL = lanes_per_alignment(band), TPR = 32 / NL;
     int64_t cells = 0;
-    int Lmax = 1;
+    int Lmax = 1, Lmax_wide = 1;
     for (int j = 0; j < n; ++j) {
         const phmm_task& t = tk[j];
         if (t.read < 0 || t.read >= R || t.hap < 0 || t.hap >= H) { e->err = "task index out of range"; return PHMM_ERR_INVALID; }
-        const int L = e->info_host[t.read].x;
+        const int L = e->info_host[t.read].x, fl = e->info_host[t.read].y;
         const long long hl = s.hap_off_host[t.hap + 1] - s.hap_off_host[t.hap];
         if (L < 1 || t.win_off < 0 || (long long)t.win_off + L + 2 * band - 1 > hl) { e->err = "task window outside the haplotype"; return PHMM_ERR_INVALID; }
         cells += 2LL * (L + band) * band;
-        if (fast_ok && (e->info_host[t.read].y & (kReadGenericMask | kReadHasN)) == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
+        if (precision_bits == 16 && (fl & (kReadNonACGT | kReadBadQual | kReadUnsafe16 | kReadTooLong | kReadHasN)) == 0) { fast_idx.push_back(j); Lmax = std::max(Lmax, L); }
+        else if ((fl & (kReadNonACGT | kReadBadQual)) == 0 && L <= kWideMaxReadLen) { wide_idx.push_back(j); Lmax_wide = std::max(Lmax_wide, L); }
         else gen.push_back(GenericTask {t.read, t.hap, t.win_off, t.reverse ? 1 : 0, j});
     }
     e->last_dp_cells = cells;
     CU(e->scores.ensure((size_t)n * sizeof(int)));
     int* d_scores = space == PHMM_SPACE_DEVICE ? scores : e->scores.as<int>();
+    auto by_length_and_read = [&](int a, int b) {
+        const int la = e->info_host[tk[a].read].x, lb = e->info_host[tk[b].read].x;
+        if (la != lb) return la < lb;
+        if (tk[a].read != tk[b].read) return tk[a].read < tk[b].read;
+        return a < b;
+    };
+    struct Chunk { int read, first, n, L; };
+    bool have_ev0 = false;
 
     if (!fast_idx.empty()) {
-        // group by (length, read); chunks of 32 tasks of one read; chunks of equal length are paired into one warp
-        std::sort(fast_idx.begin(), fast_idx.end(), [&](int a, int b) {
-            const int la = e->info_host[tk[a].read].x, lb = e->info_host[tk[b].read].x;
-            if (la != lb) return la < lb;
-            if (tk[a].read != tk[b].read) return tk[a].read < tk[b].read;
-            return a < b;
-        });
+        // group by (length, read); chunks of 32 / NL tasks of one read; chunks of equal length are paired into one warp
+        std::sort(fast_idx.begin(), fast_idx.end(), by_length_and_read);
         std::vector<LaneTask> lane(fast_idx.size());
-        struct Chunk { int read, first, n, L; };
         std::vector<Chunk> chunks;
         for (size_t i = 0; i < fast_idx.size(); ++i) {
             const phmm_task& t = tk[fast_idx[i]];
             lane[i] = LaneTask {s.hap_off_host[t.hap] + t.win_off, t.reverse ? 1 : 0, fast_idx[i]};
-            if (chunks.empty() || chunks.back().read != t.read || chunks.back().n == 32)
+            if (chunks.empty() || chunks.back().read != t.read || chunks.back().n == TPR)
                 chunks.push_back(Chunk {t.read, (int)i, 0, e->info_host[t.read].x});
             ++chunks.back().n;
         }
@@ -439,21 +444,51 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         const int nw = (int)works.size();
         const unsigned grid = (unsigned)((nw + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
         const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
-        CU(cudaEventRecord(e->ev0, e->stream));
+        CU(cudaEventRecord(e->ev0, e->stream)); have_ev0 = true;
+#define PHMM_PACKED_TASKS(B) \
+        { if ((rc = fast_smem_attr(e, k_packed_tasks<B>, smem))) return rc; \
+          k_packed_tasks<B><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores); }
         switch (band) {
-            case 8:
-                if ((rc = fast_smem_attr(e, k_packed_tasks<8>, smem))) return rc;
-                k_packed_tasks<8><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores);
-                break;
-            case 16:
-                if ((rc = fast_smem_attr(e, k_packed_tasks<16>, smem))) return rc;
-                k_packed_tasks<16><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores);
-                break;
-            default:
-                if ((rc = fast_smem_attr(e, k_packed_tasks<32>, smem))) return rc;
-                k_packed_tasks<32><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores);
-                break;
+            case 8: PHMM_PACKED_TASKS(8) break;     case 16: PHMM_PACKED_TASKS(16) break;   case 32: PHMM_PACKED_TASKS(32) break;
+            case 64: PHMM_PACKED_TASKS(64) break;   case 128: PHMM_PACKED_TASKS(128) break; default: PHMM_PACKED_TASKS(256) break;
         }
+#undef PHMM_PACKED_TASKS
+        LAUNCHED();
+        CU(cudaEventRecord(e->ev1, e->stream));
+        CU(cudaGetLastError());
+    }
+    if (!wide_idx.empty()) {
+        std::sort(wide_idx.begin(), wide_idx.end(), by_length_and_read);
+        std::vector<LaneTask> lane(wide_idx.size());
+        std::vector<WarpWork> works;
+        for (size_t i = 0; i < wide_idx.size(); ++i) {
+            const phmm_task& t = tk[wide_idx[i]];
+            lane[i] = LaneTask {s.hap_off_host[t.hap] + t.win_off, t.reverse ? 1 : 0, wide_idx[i]};
+            if (works.empty() || works.back().read0 != t.read || works.back().n0 == TPR) {
+                WarpWork w {};
+                w.read0 = t.read; w.read1 = -1; w.first0 = (int)i; w.n0 = 0; w.first1 = (int)i; w.n1 = 0; w.L = e->info_host[t.read].x;
+                works.push_back(w);
+            }
+            ++works.back().n0;
+        }
+        CU(e->ftasks.ensure(lane.size() * sizeof(LaneTask)));
+        CU(e->gtasks.ensure(works.size() * sizeof(WarpWork)));
+        CU(cudaMemcpyAsync(e->ftasks.p, lane.data(), lane.size() * sizeof(LaneTask), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->gtasks.p, works.data(), works.size() * sizeof(WarpWork), cudaMemcpyHostToDevice, e->stream));
+        const int row_stride = (Lmax_wide + 2) & ~1;
+        const int warps = (int)std::max<long long>(1, std::min<long long>(kFastWarpsPerBlock, (220LL << 10) / ((long long)row_stride * (long long)sizeof(RowEntry))));
+        const size_t smem = (size_t)warps * row_stride * sizeof(RowEntry);
+        const int nw = (int)works.size();
+        const unsigned grid = (unsigned)((nw + warps - 1) / warps);
+        if (!have_ev0) { CU(cudaEventRecord(e->ev0, e->stream)); have_ev0 = true; }
+#define PHMM_WIDE_TASKS(CC, NN) \
+        { if ((rc = fast_smem_attr(e, k_wide_tasks<CC, NN>, smem))) return rc; \
+          k_wide_tasks<CC, NN><<<grid, warps * 32, smem, e->stream>>>(e->gtasks.as<WarpWork>(), nw, e->ftasks.as<LaneTask>(), s.hp, s.rd, row_stride, nuc_prior, d_scores); }
+        switch (band) {
+            case 8: PHMM_WIDE_TASKS(16, 1) break;  case 16: PHMM_WIDE_TASKS(32, 1) break;  case 32: PHMM_WIDE_TASKS(32, 2) break;
+            case 64: PHMM_WIDE_TASKS(32, 4) break; case 128: PHMM_WIDE_TASKS(32, 8) break; default: PHMM_WIDE_TASKS(32, 16) break;
+        }
+#undef PHMM_WIDE_TASKS
         LAUNCHED();
         CU(cudaEventRecord(e->ev1, e->stream));
         CU(cudaGetLastError());
@@ -462,11 +497,11 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         CU(e->tasks_generic.ensure(gen.size() * sizeof(GenericTask)));
         CU(cudaMemcpyAsync(e->tasks_generic.p, gen.data(), gen.size() * sizeof(GenericTask), cudaMemcpyHostToDevice, e->stream));
         const int ng = (int)gen.size();
-        if (fast_idx.empty()) CU(cudaEventRecord(e->ev0, e->stream));
+        if (!have_ev0) CU(cudaEventRecord(e->ev0, e->stream));
         if (band <= 32) k_generic_tasks<64><<<(ng + 63) / 64, 64, 0, e->stream>>>(e->tasks_generic.as<GenericTask>(), ng, s.hp, s.rd, band, nuc_prior, d_scores);
         else k_generic_tasks<kGenericMaxDiag><<<(ng + 63) / 64, 64, 0, e->stream>>>(e->tasks_generic.as<GenericTask>(), ng, s.hp, s.rd, band, nuc_prior, d_scores);
         LAUNCHED();
-        if (fast_idx.empty()) CU(cudaEventRecord(e->ev1, e->stream));
+        if (!have_ev0) CU(cudaEventRecord(e->ev1, e->stream));
         CU(cudaGetLastError());
     }
     if (space == PHMM_SPACE_HOST) CU(cudaMemcpyAsync(scores, d_scores, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -671,19 +706,34 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     p.use_flanks = (flank && flank->has_flank && cfg->use_flank_state) ? 1 : 0;
     p.lhs_flank = p.use_flanks ? (int)flank->lhs_flank : 0;
     p.rhs_flank = p.use_flanks ? (int)flank->rhs_flank : 0;
-    int max_cand = 1;
+    // candidates a pair can have: listed / mapped positions + the original position + the shifted fallback
+    // (haplotype_likelihood_model.cpp:211-259); at most (listed + 1) of them reach a DP
+    int max_cand = 2, max_dp_per_pair = 1;
     if (positions && positions->off && positions->pos) {
-        // candidate lists: CSR offsets on the host (to size the copy), arrays on the device
+        // Candidate lists: CSR arrays on the device; the host needs the total (to size the copy) and the longest list (to size the
+        // per-read task lists: the reference accepts lists of any length) — reduced on the device, 32 bytes back.
         std::vector<long long> ends(1);
         if (space == PHMM_SPACE_HOST) ends[0] = positions->off[HR];
         else { CU(cudaMemcpyAsync(ends.data(), positions->off + HR, sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream)); CU(cudaStreamSynchronize(e->stream)); }
+        if (ends[0] < 0) { e->err = "candidate position offsets must be non-decreasing and start at 0"; return PHMM_ERR_INVALID; }
         const long long* po; const int32_t* pv;
         if ((rc = stage(e, e->c_off, (const long long*)positions->off, (size_t)HR + 1, space, &po))) return rc;
         if ((rc = stage(e, e->c_pos, positions->pos, (size_t)std::max<long long>(ends[0], 1), space, &pv))) return rc;
         p.pos_off = po; p.pos = pv;
-        max_cand = 12;   // kmer mapper emits <= 10 (haplotype_likelihood_array.hpp:103-104) + original + fallback
-    } else {
-        max_cand = cfg->map_positions ? 12 : 2;
+        OffsetSummary ps {};
+        CU(e->scores.ensure(sizeof(OffsetSummary)));
+        CU(cudaMemsetAsync(e->scores.p, 0, sizeof(OffsetSummary), e->stream));
+        k_offsets_summary<<<(unsigned)std::min<long long>((HR + 255) / 256, 2048), 256, 0, e->stream>>>(po, HR > 0x7fffffffLL ? 0x7fffffff : (int)HR, e->scores.as<OffsetSummary>());
+        LAUNCHED();
+        CU(cudaMemcpyAsync(&ps, e->scores.p, sizeof(OffsetSummary), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (ps.first != 0 || kOffsetBig - ps.inv_len_min < 0 || ps.last != ends[0]) { e->err = "candidate position offsets must be non-decreasing and start at 0"; return PHMM_ERR_INVALID; }
+        if (ps.len_max > 4096) { e->err = "more than 4096 candidate positions for one (haplotype, read) pair"; return PHMM_ERR_INVALID; }
+        max_cand = (int)ps.len_max + 2;
+        max_dp_per_pair = (int)ps.len_max + 1;
+    } else if (cfg->map_positions) {
+        max_cand = kMaxMapped + 2;   // the mapper emits <= 10 (haplotype_likelihood_array.hpp:103-104)
+        max_dp_per_pair = kMaxMapped + 1;
     }
     const bool use_mapper = !(positions && positions->off && positions->pos) && cfg->map_positions;
     int mapper_maxt = 0;
@@ -703,14 +753,26 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(cudaGetLastError());
     }
 
-    // scheduling: equal-length read pairs for the packed kernel, everything else to the generic kernel
+    // scheduling: equal-length read pairs for the packed kernels, 32-bit multi-lane kernels for what they cannot take, and the
+    // thread-per-pair generic kernel for the rest (foreign alphabet, qualities above 127, reads beyond the shared-memory budget)
     long long max_hap_len = 0;
     for (int h = 0; h < H; ++h) max_hap_len = std::max(max_hap_len, s.hap_off_host[h + 1] - s.hap_off_host[h]);
-    // the fast path packs (haplotype, window offset) into 16 + 16 bits
-    const bool fast_ok = band <= 32 && !cfg->use_int_scores && H <= 65535 && max_hap_len <= 65535;
-    // lane groups per warp of the fast kernel: with few haplotypes a read has few DP tasks, so several read pairs share a warp
-    const int groups = H >= 17 ? 1 : (H >= 9 ? 2 : 4);
-    // device-side scheduling: length buckets → equal-length read pairs (padded to multiples of `groups` per bucket) + generic list
+    // the DP task word packs (haplotype, window offset) into 16 + 16 bits
+    const bool task_word_ok = H <= 65535 && max_hap_len <= 65535;
+    const int NL = lanes_per_alignment(band);
+    // wide (32-bit) path: row entries of one read per warp in shared memory; long reads get fewer warps per block
+    const int wide_row_stride = (int)((std::min<long long>(Lmax_all, kWideMaxReadLen) + 2) & ~1LL);
+    const int wide_warps = (int)std::max<long long>(0, std::min<long long>(kFastWarpsPerBlock, (220LL << 10) / ((long long)wide_row_stride * (long long)sizeof(RowEntry))));
+    SchedMode mode {};
+    mode.packed_ok = task_word_ok ? 1 : 0;
+    mode.wide_ok = (task_word_ok && wide_warps >= 1) ? 1 : 0;
+    mode.force_wide = cfg->use_int_scores ? 1 : 0;
+    mode.n_to_wide = band > 32 ? 1 : 0;
+    mode.wide_max_len = kWideMaxReadLen;
+    const bool fast_ok = mode.packed_ok && !mode.force_wide;
+    // lane groups per warp of the packed kernel: with few haplotypes a read has few DP tasks, so several read pairs share a warp
+    const int groups = std::max(1, std::min(32 / NL, H >= 17 ? 1 : (H >= 9 ? 2 : 4)));
+    // device-side scheduling: length buckets → equal-length read pairs (padded to multiples of `groups` per bucket) + wide + generic lists
     const size_t pairs_cap = (size_t)R / 2 + (size_t)kLenBins * groups + 8;
     SchedTotals tot {};
     {
@@ -718,17 +780,18 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         CU(e->sorted.ensure((size_t)R * sizeof(int)));
         CU(e->pairs.ensure(2 * pairs_cap * sizeof(int)));
         CU(e->generic_reads.ensure((size_t)R * sizeof(int)));
+        CU(e->wide_reads.ensure((size_t)R * sizeof(int)));
         int* base = e->sched.as<int>();
         int* hist = base, *read_start = base + (kLenBins + 1), *pair_start = base + 2 * (kLenBins + 1), *cursors = base + 3 * (kLenBins + 1);
-        int* misc = base + 4 * (kLenBins + 1);          // [0] n_generic, [1] lmax_all, [2] bad
+        int* misc = base + 4 * (kLenBins + 1);          // [0] n_generic, [1] lmax_all, [2] bad, [3] packed reads with 'N', [4] n_wide
         SchedTotals* d_tot = (SchedTotals*)(misc + 16);
         CU(cudaMemsetAsync(base, 0, (size_t)(4 * (kLenBins + 1) + 16) * sizeof(int), e->stream));
-        k_sched_hist<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, fast_ok ? 1 : 0, hist, e->generic_reads.as<int>(), misc + 0, misc + 1, misc + 2);
+        k_sched_hist<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, mode, hist, e->generic_reads.as<int>(), e->wide_reads.as<int>(), misc);
         LAUNCHED();
-        k_sched_scan<<<1, kLenBins, 0, e->stream>>>(hist, groups, band, H, read_start, pair_start, cursors, misc + 0, misc + 1, misc + 2, s.rd.info,
-                                                    e->generic_reads.as<int>(), d_tot);
+        k_sched_scan<<<1, kLenBins, 0, e->stream>>>(hist, groups, band, H, read_start, pair_start, cursors, misc, s.rd.info,
+                                                    e->generic_reads.as<int>(), e->wide_reads.as<int>(), d_tot);
         LAUNCHED();
-        k_sched_scatter<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, fast_ok ? 1 : 0, read_start, cursors, e->sorted.as<int>());
+        k_sched_scatter<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, mode, read_start, cursors, e->sorted.as<int>());
         LAUNCHED();
         k_sched_pairs<<<(unsigned)((pairs_cap + 255) / 256), 256, 0, e->stream>>>(d_tot, read_start, pair_start, e->sorted.as<int>(), e->pairs.as<int>());
         LAUNCHED();
@@ -736,9 +799,12 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         p.tot = d_tot;
     }
     const SchedTotals* d_tot = p.tot;
-    // upper bounds of the two work lists (exact counts stay on the device)
+    // upper bounds of the work lists (exact counts stay on the device)
     // (a bucket of c reads holds ceil(c / 2) pairs rounded up to a multiple of `groups`)
-    const long long n_pairs = fast_ok ? std::min<long long>((long long)pairs_cap, R / 2 + len_bins * groups + 1) : 0, n_generic = R;
+    long long n_pairs = fast_ok ? std::min<long long>((long long)pairs_cap, R / 2 + len_bins * groups + 1) : 0;
+    // reads the packed path cannot take exist only if the host can see a reason (int scores, a long read) or the device finds one
+    // (quality sums, foreign bytes): the wide and generic tiles are always enqueued, their kernels clip against the device totals
+    long long n_wide = mode.wide_ok ? R : 0, n_generic = R;
     lap("sched enqueued");
 
     CU(e->best.ensure((size_t)HR * sizeof(int)));
@@ -759,25 +825,34 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
 
     // Tile size: the per-tile scratch (mapped candidate lists, DP task lists, traceback queue) must fit fixed budgets.
     const long long slow_budget = 8LL << 20;   // traceback-queue entries (16 bytes each)
-    const int max_dp_per_pair = (p.pos_off || use_mapper) ? 11 : 1;
-    p.fcap = H * max_dp_per_pair;              // a read's task list: one DP task per (haplotype, candidate position)
+    // DP tasks a pair can queue: listed / mapped positions (any number when the caller lists them) + the original position
+    p.fcap = (int)std::min<long long>(0x7fffffff, (long long)H * max_dp_per_pair);   // a read's task list: one DP task per (haplotype, candidate position)
     long long reads_per_tile = std::max<long long>(R, 2 * n_pairs);   // one tile unless a budget says otherwise
     if (use_mapper) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (1LL << 30) / (41LL * H)));   // (10 x int32 + 1 byte) per pair
-    if (n_pairs) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (160LL << 20) / p.fcap));   // two lists of 4-byte entries: <= 1.25 GiB
+    reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, (160LL << 20) / p.fcap));   // two lists of 4-byte entries: <= 1.25 GiB
     if (p.use_flanks) reads_per_tile = std::max<long long>(2, std::min<long long>(reads_per_tile, slow_budget / ((long long)H * max_cand)));
     const long long pairs_per_tile = std::max<long long>((long long)groups, ((reads_per_tile + 1) / 2 + groups - 1) / (long long)groups * (long long)groups);
+    // With several tiles per list the exact list sizes are worth one early synchronisation: empty wide / generic tiles cost a
+    // handful of launches each.
+    if (reads_per_tile < R) {
+        CU(cudaMemcpyAsync(&tot, d_tot, sizeof(SchedTotals), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        n_pairs = std::min<long long>(n_pairs, tot.n_pairs);
+        n_wide = std::min<long long>(n_wide, tot.n_wide);
+        n_generic = std::min<long long>(n_generic, tot.n_generic);
+    }
     // work-list entries one tile can hold (pair tiles: two per pair, padding entries included)
     const size_t tile_list_cap = (size_t)std::max<long long>(std::min<long long>(2 * pairs_per_tile, 2 * std::max<long long>(n_pairs, groups)), std::min<long long>(reads_per_tile, R)) + 2;
     if (use_mapper) {
         CU(e->kpos.ensure(tile_list_cap * H * kMaxMapped * sizeof(int32_t)));
         CU(e->kcnt.ensure(tile_list_cap * H));
     }
-    if (n_pairs) {
+    {
         CU(e->ftasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
         CU(e->fcnt.ensure(2 * tile_list_cap * sizeof(int)));
         p.ftasks = e->ftasks.as<uint32_t>();
         p.fcnt = e->fcnt.as<int>();
-        // the 32-bit kernel's lists (near-flank candidates, reads holding 'N'): whether any exist is only known on the device
+        // the 32-bit flank kernel's lists (near-flank candidates, reads holding 'N'): whether any exist is only known on the device
         CU(e->gtasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
         p.gtasks = e->gtasks.as<uint32_t>();
         p.gcnt = p.fcnt + tile_list_cap;
@@ -798,8 +873,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
 
     lap("buffers");
-    p.row_stride = (Lmax_fast + 2) & ~1;
-    const size_t smem = (size_t)kFastWarpsPerBlock * groups * p.row_stride * sizeof(RowEntry);
+    const int fast_row_stride = (Lmax_fast + 2) & ~1;
+    const size_t smem = (size_t)kFastWarpsPerBlock * groups * fast_row_stride * sizeof(RowEntry);
     int blocks_per_sm = 1;
     if (n_pairs) {
 #define PHMM_FAST_SETUP(B, GG) \
@@ -809,16 +884,32 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         switch (band * 10 + (int)groups) { \
             case 81: MACRO(8, 1) break;   case 82: MACRO(8, 2) break;   case 84: MACRO(8, 4) break; \
             case 161: MACRO(16, 1) break; case 162: MACRO(16, 2) break; case 164: MACRO(16, 4) break; \
-            case 321: MACRO(32, 1) break; case 322: MACRO(32, 2) break; default: MACRO(32, 4) break; }
+            case 321: MACRO(32, 1) break; case 322: MACRO(32, 2) break; case 324: MACRO(32, 4) break; \
+            case 641: MACRO(64, 1) break; case 642: MACRO(64, 2) break; case 644: MACRO(64, 4) break; \
+            case 1281: MACRO(128, 1) break; case 1282: MACRO(128, 2) break; case 1284: MACRO(128, 4) break; \
+            case 2561: MACRO(256, 1) break; default: MACRO(256, 2) break; }
         PHMM_FAST_DISPATCH(PHMM_FAST_SETUP)
         if (blocks_per_sm < 1) { e->err = "fast kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; }
+    }
+    // wide kernel: chunk / lanes by band
+    const size_t wsmem = (size_t)std::max(1, wide_warps) * wide_row_stride * sizeof(RowEntry);
+    int wide_blocks_per_sm = 1;
+#define PHMM_WIDE_DISPATCH(MACRO) \
+    switch (band) { case 8: MACRO(16, 1) break; case 16: MACRO(32, 1) break; case 32: MACRO(32, 2) break; case 64: MACRO(32, 4) break; \
+                    case 128: MACRO(32, 8) break; default: MACRO(32, 16) break; }
+#define PHMM_WIDE_SETUP(CC, NN) \
+    { if ((rc = fast_smem_attr(e, k_populate_wide<CC, NN>, wsmem))) return rc; \
+      if ((rc = blocks_per_sm_of(e, k_populate_wide<CC, NN>, wide_warps * 32, wsmem, &wide_blocks_per_sm))) return rc; }
+    if (n_wide) {
+        PHMM_WIDE_DISPATCH(PHMM_WIDE_SETUP)
+        if (wide_blocks_per_sm < 1) { e->err = "wide kernel does not fit on an SM"; return PHMM_ERR_INVALID; }
     }
 
     lap("kernel attrs");
     // k-mer mapper variant: vote-array capacity by the longest haplotype, byte counters when no read can cast > 255 votes
     const bool mapper_bytes = Lmax_all - kKmer + 1 <= 255;
-    auto launch_mapper = [&](unsigned grid, unsigned block, const int* list, int n_list, int base, int is_pairs) {
-#define PHMM_MAP_ARGS list, n_list, d_tot, base, is_pairs, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>()
+    auto launch_mapper = [&](unsigned grid, unsigned block, const int* list, int n_list, int base, int kind) {
+#define PHMM_MAP_ARGS list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>()
         if (mapper_maxt == 512) {
             if (mapper_bytes) k_kmer_map<512, uint8_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
             else k_kmer_map<512, uint16_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
@@ -828,18 +919,37 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         }
 #undef PHMM_MAP_ARGS
     };
+    // the 32-bit flank kernel over the current list (near-flank candidates, and every candidate of pair-list reads holding 'N')
+    auto launch_flank = [&](int n_entries, int row_stride) -> int {
+        if (band > 32) return PHMM_OK;              // wide bands: near-flank candidates take the traceback queue
+        const unsigned fgrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
+        const size_t fsmem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
+        int frc;
+        switch (band) {
+            case 8:  if ((frc = fast_smem_attr(e, k_populate_flank<8>, fsmem))) return frc;
+                     k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+            case 16: if ((frc = fast_smem_attr(e, k_populate_flank<16>, fsmem))) return frc;
+                     k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+            default: if ((frc = fast_smem_attr(e, k_populate_flank<32>, fsmem))) return frc;
+                     k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+        }
+        LAUNCHED();
+        return PHMM_OK;
+    };
     ChunkOrder chunk_order(e);
     bool timed = false;
     size_t n_timed = 0;
-    for (long long p0 = 0, g0 = 0; p0 < n_pairs || g0 < n_generic;) {
+    for (long long p0 = 0, w0 = 0, g0 = 0; p0 < n_pairs || w0 < n_wide || g0 < n_generic;) {
         if (p0 < n_pairs) {
             const int np = (int)std::min<long long>(pairs_per_tile, n_pairs - p0);
             p.pair_reads = e->pairs.as<int>() + 2 * p0;
             p.n_pairs = np;
             p.pair_base = (int)p0;
+            p.list = p.pair_reads; p.list_kind = 0; p.n_list = 2 * np; p.list_base = (int)(2 * p0);
+            p.row_stride = fast_row_stride;
             if (use_mapper) {
                 const long long threads = 2LL * np * H;
-                launch_mapper((unsigned)((threads + 127) / 128), 128, p.pair_reads, 2 * np, (int)p0, 1);
+                launch_mapper((unsigned)((threads + 127) / 128), 128, p.list, p.n_list, p.list_base, 0);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
@@ -852,7 +962,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 LAUNCHED();
             }
             lap(" classify queued");
-            p.units_per_pair = std::max(1, (p.fcap + (32 / groups) * kRoundsPerUnit - 1) / ((32 / groups) * kRoundsPerUnit));
+            const int tasks_per_round = (32 / groups) / NL;
+            p.units_per_pair = std::max(1, (p.fcap + tasks_per_round * kRoundsPerUnit - 1) / (tasks_per_round * kRoundsPerUnit));
             const int want_blocks = (int)std::min<long long>(1LL << 30, ((long long)(np / groups) * p.units_per_pair + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
             const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
             while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); }
@@ -864,34 +975,49 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             ++n_timed; timed = true;
             lap(" dp queued");
-            {   // near-flank candidates (and every candidate of reads holding 'N'): payload-carrying 32-bit DP; returns at once if none
-                const unsigned fgrid = (unsigned)std::max(1, std::min((2 * np + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
-                const size_t fsmem = (size_t)kFastWarpsPerBlock * p.row_stride * sizeof(RowEntry);
-                switch (band) {
-                    case 8:  if ((rc = fast_smem_attr(e, k_populate_flank<8>, fsmem))) return rc;
-                             k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
-                    case 16: if ((rc = fast_smem_attr(e, k_populate_flank<16>, fsmem))) return rc;
-                             k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
-                    default: if ((rc = fast_smem_attr(e, k_populate_flank<32>, fsmem))) return rc;
-                             k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
-                }
-                LAUNCHED();
-            }
+            if ((rc = launch_flank(2 * np, fast_row_stride))) return rc;
             p0 += np;
+        } else if (w0 < n_wide) {
+            const int nw = (int)std::min<long long>(reads_per_tile, n_wide - w0);
+            p.list = e->wide_reads.as<int>() + w0; p.list_kind = 1; p.n_list = nw; p.list_base = (int)w0;
+            p.row_stride = wide_row_stride;
+            const long long threads = (long long)nw * H;
+            const unsigned cgrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 127) / 128, (long long)e->sm_count * 64));
+            if (use_mapper) {
+                launch_mapper(cgrid, 128, p.list, nw, (int)w0, 1);
+                LAUNCHED();
+                p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
+            }
+            CU(cudaMemsetAsync(counters, 0, 3 * sizeof(int), e->stream));
+            CU(cudaMemsetAsync(p.fcnt, 0, (size_t)nw * sizeof(int), e->stream));
+            CU(cudaMemsetAsync(p.gcnt, 0, (size_t)nw * sizeof(int), e->stream));
+            k_populate_generic<64, true><<<cgrid, 128, 0, e->stream>>>(p);          // classify pass over the wide list
+            LAUNCHED();
+            const unsigned wgrid = (unsigned)std::max(1, std::min((nw + wide_warps - 1) / wide_warps, e->sm_count * wide_blocks_per_sm));
+            const bool time_wide = n_pairs == 0;
+            if (time_wide) { while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); } }
+            CU(chunk_order.wait_for_previous());
+            if (time_wide) CU(cudaEventRecord(e->tile_events[2 * n_timed], e->stream));
+#define PHMM_WIDE_LAUNCH(CC, NN) k_populate_wide<CC, NN><<<wgrid, wide_warps * 32, wsmem, e->stream>>>(p);
+            PHMM_WIDE_DISPATCH(PHMM_WIDE_LAUNCH)
+            LAUNCHED();
+            if (time_wide) { CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream)); ++n_timed; timed = true; }
+            if (wide_row_stride <= fast_row_stride + 8 || (size_t)kFastWarpsPerBlock * wide_row_stride * sizeof(RowEntry) <= (200u << 10)) {
+                if ((rc = launch_flank(nw, wide_row_stride))) return rc;
+            }
+            w0 += nw;
         } else {
             const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);
-            p.generic_reads = e->generic_reads.as<int>() + g0;
-            p.n_generic = ng;
-            p.generic_base = (int)g0;
+            p.list = e->generic_reads.as<int>() + g0; p.list_kind = 2; p.n_list = ng; p.list_base = (int)g0;
             // ng is an upper bound (normally there are no generic reads at all): grid-stride kernels on a bounded grid
             const long long threads = (long long)ng * H;
             const unsigned ggrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 63) / 64, (long long)e->sm_count * 32));
             if (use_mapper) {
-                launch_mapper(ggrid, 64, p.generic_reads, ng, (int)g0, 0);
+                launch_mapper(ggrid, 64, p.list, ng, (int)g0, 2);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            const bool time_generic = n_pairs == 0 && n_timed == 0;
+            const bool time_generic = n_pairs == 0 && n_wide == 0 && n_timed == 0;
             CU(chunk_order.wait_for_previous());
             if (time_generic) CU(cudaEventRecord(e->ev0, e->stream));
             if (band <= 32) k_populate_generic<64, false><<<ggrid, 64, 0, e->stream>>>(p);

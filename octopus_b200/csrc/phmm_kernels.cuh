@@ -34,10 +34,27 @@ constexpr int kReadNonACGT  = 1;   // read holds a byte outside ACGT → generic
 constexpr int kReadUnsafe16 = 2;   // sum of qualities too large for a 16-bit lane, or a quality > 127
 constexpr int kReadTooLong  = 4;   // longer than the fast path's shared-memory row budget
 constexpr int kReadUnsafeFlank32 = 8;   // quality sum too large for the 14-bit score field of the flank-aware kernel (fast path still fine)
-constexpr int kReadHasN = 16;           // read holds 'N' (and nothing else outside ACGT): all its DPs run on the 32-bit kernel (5th cap)
-constexpr int kReadGenericMask = 7;     // any of these → the read takes the generic (int32) path
+constexpr int kReadHasN = 16;           // read holds 'N' (and nothing else outside ACGT): all its DPs run on a 32-bit kernel (5th cap)
+constexpr int kReadBadQual = 32;        // a quality above 127 (outside the parity domain): generic path
 
-constexpr int kFastMaxReadLen = 1023;
+constexpr int kFastMaxReadLen = 1023;   // packed path: length bins of the pairing scheduler
+constexpr int kWideMaxReadLen = 28000;  // 32-bit multi-lane path: one read's row entries must fit a block's shared memory
+
+// Which kernel family serves a read (decided per call by k_sched_hist / k_sched_scatter):
+//   0 packed  two alignments per lane group in s16x2 lanes (dp_pair / dp_band<Lanes16>), reads paired by length
+//   1 wide    one alignment per lane group in 32-bit lanes (dp_band<Lanes32>): use_int_scores, reads whose quality sum could
+//             overflow a 16-bit lane, reads longer than the pairing scheduler's bins, reads with 'N' the flank kernel cannot take
+//   2 generic one thread per (read, haplotype) pair, int32, any alphabet
+struct SchedMode { int packed_ok, wide_ok, force_wide, n_to_wide, wide_max_len; };
+__host__ __device__ inline int read_route(const int2 inf, const SchedMode m)
+{
+    const int f = inf.y, L = inf.x;
+    if ((f & (kReadNonACGT | kReadBadQual)) || L < 1) return 2;
+    const bool n_wide = (f & kReadHasN) && (m.n_to_wide || (f & kReadUnsafeFlank32));
+    if (m.packed_ok && !m.force_wide && !(f & (kReadUnsafe16 | kReadTooLong)) && !n_wide) return 0;
+    if (m.wide_ok && L <= m.wide_max_len) return 1;
+    return 2;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Preparation kernels
@@ -90,7 +107,7 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
         const int q = quals[b + y];
         if (c < 0) flags |= kReadNonACGT;
         if (c == 4) flags |= kReadHasN;
-        if (q > 127) flags |= kReadUnsafe16;
+        if (q > 127) flags |= kReadBadQual;
         qsum += q;
         rowhalf[b + y] = (uint16_t)((c < 0 ? 0 : c) | (q << 8));
     }
@@ -101,8 +118,7 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
     }
     if (qsum > kMaxScore16) flags |= kReadUnsafe16;
     if (qsum > kMaxScoreFlank32) flags |= kReadUnsafeFlank32;
-    if ((flags & kReadHasN) && (flags & kReadUnsafeFlank32)) flags |= kReadNonACGT;   // an N read the 32-bit kernel cannot take → generic
-    if (L > kFastMaxReadLen || L < 1) flags |= kReadTooLong;
+    if (L > kFastMaxReadLen) flags |= kReadTooLong;
     if (lane == 0) info[r] = make_int2(L, flags);
 }
 
@@ -112,26 +128,28 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
 // pass over all reads; the host only reads back a handful of totals.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kLenBins = kFastMaxReadLen + 1;
-struct SchedTotals { int n_pairs, n_generic, lmax_fast, lmax_all, n_eligible, bad; long long cells; int n_with_n, pad; };
+struct SchedTotals { int n_pairs, n_generic, lmax_fast, lmax_all, n_eligible, bad; long long cells; int n_with_n, n_wide; };
 
-__global__ void k_sched_hist(const int R, const int2* __restrict__ info, const int fast_ok, int* __restrict__ hist,
-                             int* __restrict__ generic, int* __restrict__ n_generic, int* __restrict__ lmax_all, int* __restrict__ bad)
+// misc counters: [0] generic reads, [1] longest read, [2] bad, [3] packed reads holding 'N', [4] wide reads
+__global__ void k_sched_hist(const int R, const int2* __restrict__ info, const SchedMode mode, int* __restrict__ hist,
+                             int* __restrict__ generic, int* __restrict__ wide, int* __restrict__ misc)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const int2 inf = info[r];
-    if (inf.x < 1) atomicExch(bad, 1);
-    atomicMax(lmax_all, inf.x);
-    if (fast_ok && (inf.y & kReadGenericMask) == 0) { atomicAdd(&hist[inf.x], 1); if (inf.y & kReadHasN) atomicAdd(bad + 1, 1); }
-    else generic[atomicAdd(n_generic, 1)] = r;
+    if (inf.x < 1) atomicExch(misc + 2, 1);
+    atomicMax(misc + 1, inf.x);
+    const int route = read_route(inf, mode);
+    if (route == 0) { atomicAdd(&hist[inf.x], 1); if (inf.y & kReadHasN) atomicAdd(misc + 3, 1); }
+    else if (route == 1) wide[atomicAdd(misc + 4, 1)] = r;
+    else generic[atomicAdd(misc + 0, 1)] = r;
 }
 
 // one block of kLenBins threads: exclusive scans of the per-length read counts and padded pair counts
 __global__ void __launch_bounds__(kLenBins)
 k_sched_scan(const int* __restrict__ hist, const int G, const int band, const int H, int* __restrict__ read_start, int* __restrict__ pair_start,
-             int* __restrict__ cursors, const int* __restrict__ n_generic, const int* __restrict__ lmax_all, const int* __restrict__ bad,
-             const int2* __restrict__ info,
-             const int* __restrict__ generic, SchedTotals* __restrict__ tot)
+             int* __restrict__ cursors, const int* __restrict__ misc, const int2* __restrict__ info,
+             const int* __restrict__ generic, const int* __restrict__ wide, SchedTotals* __restrict__ tot)
 {
     __shared__ int s_reads[kLenBins], s_pairs[kLenBins];
     __shared__ unsigned long long s_cells;
@@ -153,10 +171,11 @@ k_sched_scan(const int* __restrict__ hist, const int G, const int band, const in
     cursors[l] = 0;
     if (c) atomicAdd(&s_cells, (unsigned long long)c * (unsigned long long)(2LL * (l + band) * band));
     __syncthreads();
-    // generic reads contribute to the cell count too
-    const int ng = *n_generic;
+    // generic and wide reads contribute to the cell count too
+    const int ng = misc[0], nw = misc[4];
     unsigned long long mine = 0;
     for (int i = l; i < ng; i += kLenBins) mine += (unsigned long long)(2LL * (info[generic[i]].x + band) * band);
+    for (int i = l; i < nw; i += kLenBins) mine += (unsigned long long)(2LL * (info[wide[i]].x + band) * band);
     if (mine) atomicAdd(&s_cells, mine);
     int lmax = c ? l : 0;
     for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -169,22 +188,23 @@ k_sched_scan(const int* __restrict__ hist, const int G, const int band, const in
         tot->n_pairs = s_pairs[kLenBins - 1];
         tot->n_eligible = s_reads[kLenBins - 1];
         tot->n_generic = ng;
+        tot->n_wide = nw;
         tot->lmax_fast = max(m, 1);
-        tot->lmax_all = max(*lmax_all, 1);
-        tot->bad = *bad;
-        tot->n_with_n = bad[1];
+        tot->lmax_all = max(misc[1], 1);
+        tot->bad = misc[2];
+        tot->n_with_n = misc[3];
         tot->cells = (long long)s_cells * H;
     }
     if (l == kLenBins - 1) { read_start[kLenBins] = s_reads[l]; pair_start[kLenBins] = s_pairs[l]; }
 }
 
-__global__ void k_sched_scatter(const int R, const int2* __restrict__ info, const int fast_ok, const int* __restrict__ read_start,
+__global__ void k_sched_scatter(const int R, const int2* __restrict__ info, const SchedMode mode, const int* __restrict__ read_start,
                                 int* __restrict__ cursors, int* __restrict__ sorted)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const int2 inf = info[r];
-    if (fast_ok && (inf.y & kReadGenericMask) == 0) sorted[read_start[inf.x] + atomicAdd(&cursors[inf.x], 1)] = r;
+    if (read_route(inf, mode) == 0) sorted[read_start[inf.x] + atomicAdd(&cursors[inf.x], 1)] = r;
 }
 
 // pair slot j → (read, read | -1) or (-1, -1) padding
@@ -229,26 +249,72 @@ struct WarpWork {          // one warp: read pair (equal length) and the lane-ta
 
 constexpr int kFastWarpsPerBlock = 4;
 
+// lanes that cooperate on one alignment (pair): the band's 2B diagonals in chunks of 32 (phmm_device.cuh, dp_band)
+__host__ __device__ constexpr int lanes_per_alignment(const int band) { return band <= 16 ? 1 : band / 16; }
+__host__ __device__ constexpr int chunk_of(const int band) { return band <= 8 ? 16 : 32; }
+
+// Two alignments (one per packed half) of the lane group this thread belongs to; all lanes of the warp share L.
+template <int BAND>
+__device__ __forceinline__ uint32_t packed_dp(const RowEntry* __restrict__ rows, const int L, const ColEntry* t0, const ColEntry* t1,
+                                              const uint32_t nucp, const int j)
+{
+    if constexpr (BAND <= 16) return dp_pair<BAND>(rows, L, t0, t1, nucp);
+    else {
+        const Lanes16::Tab tab {t0, t1};
+        return dp_band<Lanes16, 32, lanes_per_alignment(BAND)>(rows, L, tab, nucp, j);
+    }
+}
+
+// One warp = one read pair; its 2 x (32 / NL) tasks, NL lanes each. The host cuts a read's tasks into chunks of 32 / NL.
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
 k_packed_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTask* __restrict__ tasks,
                const DevHaps hp, const DevReads rd, const int row_stride, const uint32_t nucp, int* __restrict__ scores)
 {
     extern __shared__ RowEntry smem_rows[];
+    constexpr int NL = lanes_per_alignment(BAND);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane / NL, j = lane % NL;
     const int w = blockIdx.x * kFastWarpsPerBlock + warp;
     if (w >= n_works) return;
     const WarpWork ww = works[w];
     RowEntry* rows = smem_rows + warp * row_stride;
     fill_rows(rows, rd, ww.read0, ww.read1, ww.L, lane);
-    const bool v0 = lane < ww.n0, v1 = lane < ww.n1;
-    const LaneTask a = tasks[v0 ? ww.first0 + lane : ww.first0];
-    const LaneTask b = v1 ? tasks[ww.first1 + lane] : a;
+    const bool v0 = slot < ww.n0, v1 = slot < ww.n1;
+    const LaneTask a = tasks[v0 ? ww.first0 + slot : ww.first0];
+    const LaneTask b = v1 ? tasks[ww.first1 + slot] : a;
     const ColEntry* t0 = (a.reverse ? hp.tab_r : hp.tab_f) + a.tab_index;
     const ColEntry* t1 = (b.reverse ? hp.tab_r : hp.tab_f) + b.tab_index;
-    const uint32_t r = dp_pair<BAND>(rows, ww.L, t0, t1, nucp);
-    if (v0) scores[a.out_idx] = (int)(r & 0xFFFFu);
-    if (v1) scores[b.out_idx] = (int)(r >> 16);
+    const uint32_t r = packed_dp<BAND>(rows, ww.L, t0, t1, nucp, j);
+    if (j == 0) {
+        if (v0) scores[a.out_idx] = (int)(r & 0xFFFFu);
+        if (v1) scores[b.out_idx] = (int)(r >> 16);
+    }
+}
+
+// 32-bit lanes: one warp = one read (WarpWork.read0, tasks first0 .. first0 + n0, n0 <= 32 / NL), NL lanes per task.
+template <int C, int NL>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
+k_wide_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTask* __restrict__ tasks,
+             const DevHaps hp, const DevReads rd, const int row_stride, const int nuc_prior, int* __restrict__ scores)
+{
+    extern __shared__ RowEntry smem_rows[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane / NL, j = lane % NL;
+    const int w = blockIdx.x * warps + warp;
+    if (w >= n_works) return;
+    const WarpWork ww = works[w];
+    RowEntry* rows = smem_rows + warp * row_stride;
+    const uint16_t* hr = rd.rowhalf + rd.off[ww.read0];
+    for (int y = lane; y < ww.L; y += 32) rows[y] = make_row_entry32(hr[y]);
+    if (lane == 0) rows[ww.L] = pad_row_entry32();
+    __syncwarp();
+    const bool v = slot < ww.n0;
+    const LaneTask a = tasks[v ? ww.first0 + slot : ww.first0];
+    const Lanes32::Tab tab {(a.reverse ? hp.tab_r : hp.tab_f) + a.tab_index};
+    const uint32_t r = dp_band<Lanes32, C, NL>(rows, ww.L, tab, (uint32_t)nuc_prior, j);
+    if (v && j == 0) scores[a.out_idx] = (int)r;
 }
 
 struct GenericTask { int read, hap, win_off, reverse, out_idx; };
@@ -305,16 +371,17 @@ struct PopParams {
     // The host never waits for the scheduler: it sizes tiles by upper bounds and the kernels clip them against the
     // device-resident totals (tile_pairs / tile_generic below).
     const SchedTotals* tot;
-    int pair_base, generic_base; // first pair / generic read of the current tile
+    int pair_base;              // first pair of the current tile
     int* any_flank_tasks;       // set by the classify pass when it queues a task for k_populate_flank
     // fast path work list: read pairs of equal length (second may be -1)
     const int* pair_reads;
     int n_pairs;                // tile size (upper bound)
     int* pair_cursor;           // persistent-warp work counter
     int row_stride;             // shared-memory row entries (8 bytes) per warp
-    // generic path work list
-    const int* generic_reads;
-    int n_generic;              // tile size (upper bound)
+    // The list the current tile's per-read kernels (k-mer mapper, classify pass, 32-bit DP kernels, generic pass) walk:
+    // kind 0 = the pair list (two entries per pair, -1 = padding), 1 = wide reads, 2 = generic reads.
+    const int* list;
+    int list_kind, n_list, list_base;   // n_list: upper bound on the tile's entries; list_base: index of the tile's first entry
 };
 
 // flat index → (list slot, haplotype); 64-bit division is an expensive software routine, the index nearly always fits 32 bits
@@ -325,7 +392,8 @@ __device__ __forceinline__ void split_index(const long long i, const int H, int*
 }
 
 __device__ __forceinline__ int tile_pairs(const PopParams& p) { return max(0, min(p.n_pairs, p.tot->n_pairs - p.pair_base)); }
-__device__ __forceinline__ int tile_generic(const PopParams& p) { return max(0, min(p.n_generic, p.tot->n_generic - p.generic_base)); }
+__device__ __forceinline__ int list_total(const SchedTotals* tot, const int kind) { return kind == 0 ? 2 * tot->n_pairs : kind == 1 ? tot->n_wide : tot->n_generic; }
+__device__ __forceinline__ int tile_list(const PopParams& p) { return max(0, min(p.n_list, list_total(p.tot, p.list_kind) - p.list_base)); }
 
 __device__ __forceinline__ HapView hap_view(const DevHaps& hp, const int h, const bool reverse)
 {
@@ -436,7 +504,7 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
 // 32-bit word at a time where possible (clear, final scan). CountT = uint8_t when no diagonal can collect more than 255
 // votes (a diagonal gets at most one vote per query k-mer, so reads of <= 260 bases), else uint16_t.
 template <int MAXT, typename CountT>
-__global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int is_pairs,
+__global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int kind,
                            const DevHaps hp, const DevReads rd,
                            const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ bins, const uint16_t* __restrict__ items,
                            int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
@@ -444,7 +512,7 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, c
     constexpr int PER = 4 / (int)sizeof(CountT);
     const int H = hp.n;
     // the tile's work list: 2 entries per read pair, or the generic reads; clipped against the scheduler's totals
-    const int n_list = max(0, min(n_list_max, is_pairs ? 2 * (tot->n_pairs - base) : tot->n_generic - base));
+    const int n_list = max(0, min(n_list_max, list_total(tot, kind) - base));
     const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
         int li, h;
@@ -497,13 +565,17 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, c
 // scores into best[] with atomicMin. Nothing but the DP lives in this kernel: the register-resident band gets the whole
 // register budget. The host pads the pair list so that the G pairs of a warp share one read length ((-1,-1) = idle group).
 template <int BAND, int G>
-__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 3)
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
 k_populate_fast(const PopParams p)
 {
     extern __shared__ RowEntry smem_rows[];
+    constexpr int NL = lanes_per_alignment(BAND);       // lanes per task (pair of alignments): bands >= 32 split their diagonals
     constexpr int LG = 32 / G;                          // lanes per group
+    constexpr int TPR = LG / NL;                        // tasks per group and round (per packed half)
+    static_assert(TPR >= 1, "a lane group must hold at least one task");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / LG, gl = lane % LG;
+    const int slot = gl / NL, jl = gl % NL;
     RowEntry* rows = smem_rows + (warp * G + grp) * p.row_stride;
     const int R = p.rd.n;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
@@ -521,7 +593,7 @@ k_populate_fast(const PopParams p)
         int nmax = max(n0, n1), L = r0 >= 0 ? p.rd.info[r0].x : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); L = max(L, __shfl_xor_sync(0xffffffffu, L, o)); }
-        const int c_begin = part * kRoundsPerUnit * LG, c_end = min(nmax, c_begin + kRoundsPerUnit * LG);
+        const int c_begin = part * kRoundsPerUnit * TPR, c_end = min(nmax, c_begin + kRoundsPerUnit * TPR);
         if (c_begin >= nmax) continue;
         __syncwarp();
         if (r0 >= 0) {   // cooperative fill by the group's lanes
@@ -536,15 +608,15 @@ k_populate_fast(const PopParams p)
         const ColEntry* tab1 = (rb >= 0 && p.rd.reverse[rb]) ? p.hp.tab_r : p.hp.tab_f;
         const uint32_t* q0 = p.ftasks + (size_t)(2 * (size_t)max(j, 0)) * p.fcap;
         const uint32_t* q1 = q0 + p.fcap;
-        for (int c = c_begin; c < c_end; c += LG) {
-            const bool v0 = c + gl < n0, v1 = c + gl < n1;
+        for (int c = c_begin; c < c_end; c += TPR) {
+            const bool v0 = c + slot < n0, v1 = c + slot < n1;
             // idle half-lanes replay a valid task (result discarded): of their own group if it has one, else of any lane
             const bool have = (n0 > 0) || (n1 > 0);
             uint32_t t0 = 0, t1 = 0;
             const ColEntry *b0 = tab0, *b1 = tab1;
             if (have) {
-                t0 = n0 > 0 ? q0[v0 ? c + gl : 0] : q1[0];
-                t1 = n1 > 0 ? q1[v1 ? c + gl : 0] : t0;
+                t0 = n0 > 0 ? q0[v0 ? c + slot : 0] : q1[0];
+                t1 = n1 > 0 ? q1[v1 ? c + slot : 0] : t0;
                 if (n0 == 0) b0 = tab1;
                 if (n1 == 0) b1 = tab0;
             }
@@ -554,9 +626,11 @@ k_populate_fast(const PopParams p)
             const unsigned long long sb0 = __shfl_sync(0xffffffffu, (unsigned long long)b0, src), sb1 = __shfl_sync(0xffffffffu, (unsigned long long)b1, src);
             if (!have) { t0 = s0; t1 = s1; b0 = (const ColEntry*)sb0; b1 = (const ColEntry*)sb1; }
             const int h0 = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1 = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
-            const uint32_t res = dp_pair<BAND>(rows, L, b0 + p.hp.off[h0] + a0, b1 + p.hp.off[h1] + a1, nucp);
-            if (v0) atomicMin(p.best + (size_t)h0 * R + r0, (int)(res & 0xFFFFu));
-            if (v1) atomicMin(p.best + (size_t)h1 * R + r1, (int)(res >> 16));
+            const uint32_t res = packed_dp<BAND>(rows, L, b0 + p.hp.off[h0] + a0, b1 + p.hp.off[h1] + a1, nucp, jl);
+            if (jl == 0) {
+                if (v0) atomicMin(p.best + (size_t)h0 * R + r0, (int)(res & 0xFFFFu));
+                if (v1) atomicMin(p.best + (size_t)h1 * R + r1, (int)(res >> 16));
+            }
         }
     }
 }
@@ -573,13 +647,13 @@ k_populate_flank(const PopParams p)
     const int R = p.rd.n;
     constexpr int K = 2 * BAND;
     if (*p.any_flank_tasks == 0) return;          // the classify pass queued nothing for this kernel
-    const int n_list = 2 * tile_pairs(p);
+    const int n_list = tile_list(p);
     for (;;) {
         int li = 0;
         if (lane == 0) li = atomicAdd(p.flank_cursor, 1);
         li = __shfl_sync(0xffffffffu, li, 0);
         if (li >= n_list) break;
-        const int r = p.pair_reads[li];
+        const int r = p.list[li];
         const int n = r >= 0 ? p.gcnt[li] : 0;
         if (n == 0) continue;
         const int L = p.rd.info[r].x;
@@ -630,7 +704,7 @@ template <int MAXK, bool FASTQ>
 __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int li, const int h)
 {
     const int H = p.hp.n, R = p.rd.n;
-    const int r = FASTQ ? p.pair_reads[li] : p.generic_reads[li];
+    const int r = p.list[li];
     if (r < 0) return;
     const bool rev = p.rd.reverse[r] != 0;
     const HapView hv = hap_view(p.hp, h, rev);
@@ -649,6 +723,31 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
     int pend_a[kMaxPending];
     unsigned pend_flank = 0u;
     int n_pend = 0;
+    auto flush_pending = [&](const int count) {
+        for (int i2 = 0; i2 < count; ++i2) {
+            const int v = pend_a[i2];
+            // reads with 'N' on the pair list: every DP on the 32-bit flank kernel (its lookup has the fifth cap); on the wide
+            // list the score-only kernel has it too
+            const bool to_32bit = FASTQ && p.list_kind == 0 && (p.rd.info[r].y & kReadHasN);
+            if (!((pend_flank >> i2) & 1u) && !to_32bit) {
+                if (FASTQ) {
+                    const int slot = list_append_slot(p.fcnt, li);
+                    if (slot < p.fcap) p.ftasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
+                    else atomicOr(p.flags, 8);
+                } else {
+                    const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
+                    best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
+                }
+            } else {
+                if (FASTQ && p.band <= 32 && !(p.rd.info[r].y & kReadUnsafeFlank32)) {
+                    const int slot = list_append_slot(p.gcnt, li);
+                    if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
+                    else atomicOr(p.flags, 8);
+                    *p.any_flank_tasks = 1;
+                } else push_slow(p, r, h, v);
+            }
+        }
+    };
     for (int c = 0; c < npos + 2; ++c) {
         int pos;
         const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
@@ -657,47 +756,75 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
         int v;
         const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, p.use_flanks != 0, p.lhs_flank, p.rhs_flank, &v);
         if (kind == CAND_VALUE) best = min(best, v);
-        else if ((kind == CAND_DP || kind == CAND_DP_FLANK) && n_pend < kMaxPending) {
+        else if (kind == CAND_DP || kind == CAND_DP_FLANK) {
+            if (n_pend == kMaxPending) {      // a long caller-supplied list: queue what has been collected and go on (no pair is truncated)
+                flush_pending(n_pend);
+                n_pend = 0; pend_flank = 0u;
+            }
             pend_a[n_pend] = v;
             if (kind == CAND_DP_FLANK) pend_flank |= 1u << n_pend;
             ++n_pend;
         }
     }
     if (best == 0) n_pend = 0;
-    for (int i2 = 0; i2 < n_pend; ++i2) {
-        const int v = pend_a[i2];
-        const bool to_32bit = FASTQ && (p.rd.info[r].y & kReadHasN);   // reads with 'N': every DP on the 32-bit kernel
-        if (!((pend_flank >> i2) & 1u) && !to_32bit) {
-            if (FASTQ) {
-                const int slot = list_append_slot(p.fcnt, li);
-                if (slot < p.fcap) p.ftasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
-                else atomicOr(p.flags, 8);
-            } else {
-                const GenericModel gm {hv.seq + v, hv.snv_mask + v, hv.snv_prior + v, hv.gap_open + v, hv.gap_extend + v, p.nuc_prior};
-                best = min(best, generic_align<false, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, nullptr, 1, 0, 0, nullptr, nullptr, nullptr));
-            }
-        } else {
-            if (FASTQ && !(p.rd.info[r].y & kReadUnsafeFlank32)) {
-                const int slot = list_append_slot(p.gcnt, li);
-                if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
-                else atomicOr(p.flags, 8);
-                *p.any_flank_tasks = 1;
-            } else push_slow(p, r, h, v);
-        }
-    }
+    flush_pending(n_pend);
     if (best != kBestInf) atomicMin(p.best + (size_t)h * R + r, best);
 }
+
 
 template <int MAXK, bool FASTQ>
 __global__ void k_populate_generic(const PopParams p)
 {
     const int H = p.hp.n;
-    const int n_list = FASTQ ? 2 * tile_pairs(p) : tile_generic(p);
+    const int n_list = tile_list(p);
     const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
         int li, h;
         split_index(i, H, &li, &h);
         populate_one_pair<MAXK, FASTQ>(p, li, h);
+    }
+}
+
+// Score-only DP tasks of the wide list (32-bit lanes, dp_band<Lanes32>): persistent warps, one READ per warp (row entries in
+// shared memory), 32 / NL tasks per round with NL lanes each. Serves use_int_scores, reads whose quality sum does not fit a
+// 16-bit lane, reads beyond the pairing scheduler's length bins (long reads), and reads with 'N' at bands > 32.
+template <int C, int NL>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
+k_populate_wide(const PopParams p)
+{
+    extern __shared__ RowEntry smem_rows[];
+    constexpr int TPR = 32 / NL;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane / NL, j = lane % NL;
+    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int R = p.rd.n;
+    const int n_list = tile_list(p);
+    for (;;) {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(p.pair_cursor, 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li >= n_list) break;
+        const int r = p.list[li];
+        const int n = r >= 0 ? p.fcnt[li] : 0;
+        if (n == 0) continue;
+        const int L = p.rd.info[r].x;
+        __syncwarp();
+        {
+            const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
+            for (int y = lane; y < L; y += 32) rows[y] = make_row_entry32(hr[y]);
+            if (lane == 0) rows[L] = pad_row_entry32();
+            __syncwarp();
+        }
+        const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q = p.ftasks + (size_t)li * p.fcap;
+        for (int c = 0; c < n; c += TPR) {
+            const bool valid = c + slot < n;
+            const uint32_t t = q[valid ? c + slot : 0];
+            const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
+            const Lanes32::Tab tb {tab + p.hp.off[h] + a};
+            const uint32_t res = dp_band<Lanes32, C, NL>(rows, L, tb, (uint32_t)p.nuc_prior, j);
+            if (valid && j == 0) atomicMin(p.best + (size_t)h * R + r, (int)res);
+        }
     }
 }
 

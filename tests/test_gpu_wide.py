@@ -1,0 +1,183 @@
+"""GPU parity tests for the multi-lane band kernels (bands 32..256, packed s16x2 and 32-bit lanes), the int-score mode,
+reads the 16-bit lanes cannot take (large quality sums, long reads, 'N' at wide bands), long candidate lists and the
+BASELINE shapes round 1 never checked against the oracle (H = 1024, C4's band 32 mix)."""
+import numpy as np
+import pytest
+
+from helpers import ACGT, random_positions, random_region
+from test_gpu_parity import _close, _oracle_scores, _tasks_for
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("band", [32, 64, 128, 256])
+def test_align_scores_wide_bands_match_oracle(engine, coracle, band):
+    rng = np.random.default_rng(500 + band)
+    hap_len = 2 * band + 420
+    haps, reads = random_region(rng, band, n_haps=5, n_reads=60, hap_len=hap_len, read_len_choices=[1, 7, 40, 76, 150, 151, 300],
+                                read_n_rate=0.1, edge_reads=False)
+    tasks = _tasks_for(rng, haps, reads, band, 500)
+    want = _oracle_scores(coracle, haps, reads, band, tasks, 2)
+    for bits in (16, 32):
+        got = engine.align_scores(band, haps, reads, tasks, nuc_prior=2, precision_bits=bits)
+        assert np.array_equal(got, want), (band, bits, np.nonzero(got != want)[0][:10], got[got != want][:10], want[got != want][:10])
+
+
+def test_align_scores_long_and_high_quality_reads(engine, coracle):
+    """Reads beyond the packed path: longer than its 1023-base bins, or a quality sum that does not fit a 16-bit lane."""
+    from octopus_b200.batch import pack_haplotypes, pack_reads
+    rng = np.random.default_rng(77)
+    band = 64
+    hap_len = 2600
+    base = ACGT[rng.integers(0, 4, hap_len)]
+    seqs = []
+    for h in range(3):
+        s = base.copy()
+        s[rng.integers(0, hap_len, 20)] = ACGT[rng.integers(0, 4, 20)]
+        seqs.append(s)
+    haps = pack_haplotypes(seqs, [np.roll(s, 1) for s in seqs], [rng.integers(1, 126, hap_len).astype(np.int8) for _ in seqs],
+                           [np.roll(s, -1) for s in seqs], [rng.integers(1, 126, hap_len).astype(np.int8) for _ in seqs],
+                           [rng.integers(3, 46, hap_len).astype(np.int8) for _ in seqs], [rng.integers(1, 11, hap_len).astype(np.int8) for _ in seqs])
+    bases, quals = [], []
+    for L, q in ((800, 41), (1023, 20), (1024, 20), (1500, 30), (2300, 93), (900, 60)):
+        p = int(rng.integers(0, hap_len - L))
+        b = base[p:p + L].copy()
+        b[rng.integers(0, L, L // 25)] = ACGT[rng.integers(0, 4, L // 25)]
+        bases.append(b)
+        quals.append(np.full(L, q, np.uint8))
+    reads = pack_reads(bases, quals)
+    tasks = _tasks_for(rng, haps, reads, band, 40)
+    want = _oracle_scores(coracle, haps, reads, band, tasks, 2)
+    for bits in (16, 32):
+        got = engine.align_scores(band, haps, reads, tasks, nuc_prior=2, precision_bits=bits)
+        assert np.array_equal(got, want), (bits, got, want)
+
+
+@pytest.mark.parametrize("band_req", [33, 64, 100, 200])
+def test_populate_wide_bands_match_oracle(engine, coracle, band_req):
+    from octopus_b200 import HaplotypeLikelihoodModel
+    rng = np.random.default_rng(600 + band_req)
+    band = HaplotypeLikelihoodModel(HaplotypeLikelihoodModel.Config(max_indel_error=band_req)).pad_requirement()
+    for trial in range(4):
+        hap_len = 2 * band + int(rng.choice([200, 330]))
+        haps, reads = random_region(rng, band, n_haps=int(rng.integers(1, 24)), n_reads=int(rng.integers(1, 50)), hap_len=hap_len,
+                                    read_len_choices=[40, 76, 100, 150], read_n_rate=0.08, edge_reads=(trial % 2 == 0))
+        positions = random_positions(rng, haps, reads) if trial % 2 else None
+        flanks = (int(rng.integers(0, 90)), int(rng.integers(0, 90))) if trial == 3 else None
+        for dp_only in (False, True):
+            for int_scores in (False, True):
+                cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, disable_naive_shortcut=dp_only, map_positions=False,
+                                                      use_int_scores=int_scores)
+                rc, want, wst = coracle.populate(band, haps, reads, positions, flanks, dp_only=dp_only, map_positions=False)
+                got, st = engine.populate(cfg, haps, reads, positions, flanks, want_status=True)
+                ok_pairs = wst == 0
+                assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
+                ok, worst = _close(got[ok_pairs], want[ok_pairs])
+                assert ok, (band_req, trial, dp_only, int_scores, worst)
+
+
+def test_populate_int_scores_and_unsafe_reads_equal_the_default(engine, coracle):
+    """use_int_scores routes every read through the 32-bit lanes; reads whose quality sum overflows 16 bits go there on their
+    own. Both must give the oracle's values (band 16 and 32, flank state and device mapper included)."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    rng = np.random.default_rng(31)
+    for band in (16, 32):
+        haps, reads = random_region(rng, band, n_haps=9, n_reads=80, hap_len=1000, read_len_choices=[76, 150, 700, 760], read_n_rate=0.05)
+        reads.quals[:] = np.where(rng.random(len(reads.quals)) < 0.9, 41, reads.quals)      # long reads: quality sum ~ 30 000 > 16-bit budget
+        for flanks in (None, (120, 150)):
+            for mapit in (False, True):
+                rc, want, wst = coracle.populate(band, haps, reads, None, flanks, map_positions=mapit)
+                for int_scores in (False, True):
+                    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, use_int_scores=int_scores, map_positions=mapit)
+                    got, st = engine.populate(cfg, haps, reads, None, flanks, want_status=True)
+                    ok_pairs = wst == 0
+                    assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
+                    ok, worst = _close(got[ok_pairs], want[ok_pairs])
+                    assert ok, (band, flanks, mapit, int_scores, worst)
+
+
+def test_populate_long_candidate_lists(engine, coracle):
+    """The reference takes mapping-position lists of any length (haplotype_likelihood_model.cpp:211-237): more than the k-mer mapper's
+    10 per pair must neither be truncated nor overflow the task lists."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from octopus_b200.batch import pack_positions
+    rng = np.random.default_rng(41)
+    band = 16
+    haps, reads = random_region(rng, band, n_haps=6, n_reads=25, hap_len=400, read_len_choices=[60, 100], edge_reads=False)
+    lists = [[sorted(set(int(x) for x in rng.integers(0, 400 - reads.length(r), int(rng.integers(0, 40))))) for r in range(reads.n)] for h in range(haps.n)]
+    positions = pack_positions(lists, haps.n, reads.n)
+    for flanks in (None, (50, 60)):
+        for dp_only in (True, False):
+            cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=dp_only)
+            rc, want, wst = coracle.populate(band, haps, reads, positions, flanks, dp_only=dp_only)
+            got, st = engine.populate(cfg, haps, reads, positions, flanks, want_status=True)
+            ok_pairs = wst == 0
+            ok, worst = _close(got[ok_pairs], want[ok_pairs])
+            assert ok, (flanks, dp_only, worst)
+
+
+def test_populate_h1024_shape(engine, coracle):
+    """C5's shape: 1024 haplotypes (the 16-bit haplotype field of the DP task word, per-read task lists of 1024 entries)."""
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    haps, reads, band = synth.make_batch("C5", n_reads=48)
+    assert haps.n == 1024
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, map_positions=False)
+    got = engine.populate(cfg, haps, reads)
+    rc, want, _ = coracle.populate(band, haps, reads, dp_only=True, map_positions=False)
+    assert rc == 0
+    ok, worst = _close(got, want)
+    assert ok, worst
+
+
+def test_populate_c4_shape_vs_oracle(engine, coracle):
+    """C4: band 32 (two lanes per alignment pair), mixed 76 / 150 / 250 bp reads, 500 bp haplotypes — against the oracle."""
+    from octopus_b200 import HaplotypeLikelihoodModel, synth
+    haps, reads, band = synth.make_batch("C4", n_reads=300, n_haps=40)
+    assert band == 32
+    for dp_only in (True, False):
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=dp_only, map_positions=False)
+        got = engine.populate(cfg, haps, reads)
+        rc, want, _ = coracle.populate(band, haps, reads, dp_only=dp_only, map_positions=False)
+        ok, worst = _close(got, want)
+        assert ok, (dp_only, worst)
+
+
+def test_populate_with_error_model_penalties(engine, coracle):
+    """A region whose penalty arrays come from the reference's error models (reset()), haplotypes with tandem repeats: long constant
+    runs and low penalties inside repeats, unlike the i.i.d. synthetic arrays."""
+    from octopus_b200 import ErrorModel, HaplotypeLikelihoodModel
+    from octopus_b200.batch import pack_reads
+    rng = np.random.default_rng(53)
+    hap_len, band = 420, 16
+    base = ACGT[rng.integers(0, 4, hap_len)].copy()
+    for motif, k, at in ((b"A", 18, 60), (b"CA", 12, 150), (b"GAT", 9, 230), (b"T", 9, 330)):
+        rep = np.tile(np.frombuffer(motif, np.uint8), k)
+        base[at:at + len(rep)] = rep
+    seqs = []
+    for h in range(12):
+        s = base.copy()
+        if h % 3 == 1:
+            s = np.concatenate([s[:70], s[71:], ACGT[rng.integers(0, 4, 1)]])          # one A fewer in the homopolymer
+        if h % 3 == 2:
+            s = np.concatenate([s[:160], np.frombuffer(b"CA", np.uint8), s[160:-2]])   # one CA more
+        s[rng.integers(0, hap_len, 2)] = ACGT[rng.integers(0, 4, 2)]
+        seqs.append(s)
+    haps = ErrorModel("PCR-free.HiSeq-2500").reset(seqs, begin=np.zeros(len(seqs), np.int64))
+    bases, quals, begin = [], [], []
+    for r in range(120):
+        L = int(rng.choice([76, 100, 150]))
+        p = int(rng.integers(0, hap_len - L))
+        b = seqs[int(rng.integers(0, len(seqs)))][p:p + L].copy()
+        for _ in range(int(rng.choice([0, 0, 1, 2]))):
+            b[rng.integers(0, L)] = ACGT[rng.integers(0, 4)]
+        bases.append(b); quals.append(rng.integers(2, 42, L).astype(np.uint8)); begin.append(p)
+    reads = pack_reads(bases, quals, reverse=(rng.random(120) < 0.5).astype(np.uint8), begin=np.asarray(begin, np.int64))
+    for flanks in (None, (40, 60)):
+        for mapit in (False, True):
+            cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, map_positions=mapit)
+            got, st = engine.populate(cfg, haps, reads, None, flanks, want_status=True)
+            rc, want, wst = coracle.populate(band, haps, reads, None, flanks, map_positions=mapit)
+            ok_pairs = wst == 0
+            assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
+            ok, worst = _close(got[ok_pairs], want[ok_pairs])
+            assert ok, (flanks, mapit, worst)
