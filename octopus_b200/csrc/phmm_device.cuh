@@ -61,6 +61,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 __device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }                              // VIMNMX.S16x2
+__device__ __forceinline__ uint32_t vminu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }                             // VIMNMX.U16x2
 __device__ __forceinline__ uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }       // VIMNMX3.S16x2
 __device__ __forceinline__ uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }   // VIADDMNMX.S16x2: min(a+b, c)
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
@@ -83,6 +84,11 @@ inline int emu_hi(uint32_t v) { return (int16_t)(v >> 16); }
 inline int emu_min(int a, int b) { return a < b ? a : b; }
 inline uint32_t vmin2(uint32_t a, uint32_t b) { return emu_pack(emu_min(emu_lo(a), emu_lo(b)), emu_min(emu_hi(a), emu_hi(b))); }
 inline uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return vmin2(vmin2(a, b), c); }
+inline uint32_t vminu2(uint32_t a, uint32_t b)
+{
+    const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+    return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+}
 inline uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c)
 {
     return emu_pack(emu_min((int16_t)(emu_lo(a) + emu_lo(b)), emu_lo(c)), emu_min((int16_t)(emu_hi(a) + emu_hi(b)), emu_hi(c)));
@@ -602,6 +608,120 @@ PHMM_HD void dp_flank32(const RowEntry* __restrict__ rows, const int L, const Co
     *score_out = total;
     *flank_out = v_l + (total - v_r);
     *mask_out = y_l + (L - y_r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Flank-aware path, lean form: the payload is the in-flank penalty itself
+// ---------------------------------------------------------------------------------------------------------
+//
+// dp_flank32 above names the cells where the best path crosses the flank boundaries and looks the arrival values up afterwards;
+// it needs the boundary columns kept aside (4 x 2B registers) and measured 9.7 ALU-pipe instructions per cell (profiles/r02a:
+// ALU pipe 84 % busy — the kernel is at its formulation's floor). When at least two read bases are certain to lie outside the
+// flanks (flank_mask_cannot_zero below: the common case — the non-flank part of the window is wider than the band), the
+// reference's result is simply score - (penalty accrued inside the flanks) (pair_hmm.hpp:755-764), and that penalty can ride
+// along as an ADDITIVE payload: every transition's constant carries its penalty twice, in the score field and — in flank
+// columns only — in the payload field. Values are  [31:16] score  [15:14] label  [13:0] in-flank penalty of this cell's own best
+// path; whole-word unsigned comparisons reproduce the reference's choices exactly as in dp_flank32 (labels M 0 < I 1 < D 3).
+// Per cell: PRMT + VIMNMX.U16x2 (the emission for both fields at once: the second PRMT operand is the column's cap table, the first
+// the same table in flank columns and zero elsewhere), VIMNMX3 (S), LOP3 (clear the label), VIMNMX3 (D': three candidates, adds on the
+// FMA pipe), LOP3 (D label), VIADDMNMX (I'), LOP3 (I label; it cannot be folded into the open constant: extension and opening would
+// then tie on the label) = 8 ALU-pipe instructions against 9.7, and no boundary arrays (no local memory, 2B fewer live registers).
+// Reads must be ACGT-only (four caps per PRMT operand) with a quality sum below kMaxScoreFlank32.
+constexpr uint32_t kFAccLabelMask = 3u << 14, kFAccLabI = 1u << 14, kFAccLabD = 3u << 14;
+constexpr uint32_t kFAccInf = 0x7000u << 16;
+
+// .x = PRMT selector: byte 0 <- first operand [code] (flank copy), byte 2 <- second operand [code], bytes 1 / 3 <- 0x00 (sign
+// replication of a byte < 0x80); .y = quality in both halves
+PHMM_HD RowEntry make_row_entry_facc(uint32_t half) { const uint32_t c = half & 3u; RowEntry r; r.x = 0x8480u | c | ((4u + c) << 8); r.y = (half >> 8) | ((half >> 8) << 16); return r; }
+PHMM_HD RowEntry pad_row_entry_facc() { RowEntry r; r.x = 0x8480u | (4u << 8); r.y = 0u; return r; }
+
+// True when every path consumes at least two read bases outside the flanks: read base y is consumed at a truth index in
+// [y, y + 2B - 1], so the bases with xl <= y and y + 2B - 1 < xr are outside whatever the path. (pair_hmm.hpp:757-759 zeroes the
+// flank score otherwise; such candidates keep to dp_flank32.)
+PHMM_HD bool flank_mask_cannot_zero(const int L, const int band, const int xl, const int xr)
+{
+    const int lo = xl > 0 ? xl : 0, hi = (L - 1 < xr - 2 * band) ? L - 1 : xr - 2 * band;
+    return hi - lo + 1 >= 2;
+}
+
+template <int BAND>
+PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ tab, const int nuc_prior,
+                          const int xl, const int xr, int* score_out, int* flank_out)
+{
+    constexpr int K = 2 * BAND;
+    static_assert(K <= 64, "register band limited to 64 diagonals");
+    uint32_t M[K], D[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kFAccInf | kFAccLabD; }
+    const int W = L + K - 1;
+    ColEntry e = ldg(tab);
+    uint32_t go_prev = 0u, ge_prev = 0u;
+    const RowEntry w0 = rows[0];
+    uint32_t best = 0xFFFFFFFFu;
+
+#define PHMM_ACELL(k, CAPTURE)                                                                          \
+    {                                                                                                   \
+        const RowEntry w = rp[-(k)];                                                                    \
+        const uint32_t subw = vminu2(w.y, prmt(caps_lo, caps_hi, w.x));                                 \
+        const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                              \
+        const uint32_t S = umin3_32(m, i_run, d);                                                       \
+        CAPTURE                                                                                         \
+        M[(k) < K ? (k) : 0] = (S & ~kFAccLabelMask) + subw;                                            \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = umin3_32(d + geS, m + goS, i_run + goS) | kFAccLabD; \
+        i_run = uaddmin32(i_run, gepS, m + gopS) | kFAccLabI;                                           \
+    }
+#define PHMM_ACASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_ACELL(k, )
+#define PHMM_ACASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
+// the row-L cell: minimum over (score, label), earliest end on ties (simd_pair_hmm.hpp:285-291, 309-315)
+#define PHMM_ACAPTURE(k) if (k == klo && (S >> 14) < (best >> 14)) best = S;
+
+    for (int x = 0; x <= W; ++x) {
+        const int xn = (x + 1 < W) ? x + 1 : W - 1;
+        const ColEntry nx = ldg(tab + xn);
+        const uint32_t fl = (x < xl || x >= xr) ? 1u : 0u;         // the penalties of this column's three transitions count as in-flank
+        const uint32_t both = 0x10000u + fl;
+        const uint32_t caps_hi = e.x, caps_lo = fl ? e.x : 0u;
+        const uint32_t go = e.y & 0xFFu, ge = (e.y >> 8) & 0xFFu;
+        const uint32_t goS = go * both, geS = ge * both;
+        const uint32_t gopS = (go_prev + (uint32_t)nuc_prior) * both, gepS = (ge_prev + (uint32_t)nuc_prior) * both;
+        const RowEntry* rp = rows + x;
+        uint32_t i_run = kFAccInf | kFAccLabI;
+        if (x >= K) {
+            if (x < L) {
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) PHMM_ACELL(k, )
+            } else {
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    PHMM_ACELL(k, PHMM_ACAPTURE(k))
+                    if (k == klo) break;
+                }
+            }
+        } else {
+            const uint32_t sub0 = vminu2(w0.y, prmt(caps_lo, caps_hi, w0.x));      // the path starts here: m(x+1, 1) = sub(x, 0), in-flank or not
+            i_run = (x & 1) ? (gopS | kFAccLabI) : (kFAccInf | kFAccLabI);
+            if (x < L) {
+                switch (x) { PHMM_REP64(PHMM_ACASE_PROLOGUE) default: break; }
+            } else {
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    if (k < x && k >= klo) PHMM_ACELL(k, PHMM_ACAPTURE(k))
+                }
+            }
+            switch (x) { PHMM_REP64(PHMM_ACASE_ROW0) default: break; }
+        }
+        go_prev = go; ge_prev = ge;
+        const uint32_t z = i_run & 0x8000u;        // bit 15 of an I value is never set (label 1): pins the prefetch behind the column
+        e.x = nx.x + z; e.y = nx.y + z;
+    }
+#undef PHMM_ACELL
+#undef PHMM_ACASE_PROLOGUE
+#undef PHMM_ACASE_ROW0
+#undef PHMM_ACAPTURE
+    *score_out = (int)(best >> 16);
+    *flank_out = (int)(best & 0x3FFFu);
 }
 
 // ---------------------------------------------------------------------------------------------------------

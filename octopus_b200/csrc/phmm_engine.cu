@@ -63,7 +63,7 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, wide_reads, bp;
     DBuf tasks_lane, tasks_generic, works, scores;
-    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, gcnt, sched, sorted;
+    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, atasks, gcnt, sched, sorted;
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
     // per-kernel launch configuration already applied / queried (the runtime calls are not free and need not be repeated)
@@ -336,7 +336,7 @@ void phmm_destroy(phmm_engine* e)
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
                    &e->counters, &e->pairs, &e->generic_reads, &e->wide_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
-                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->gcnt, &e->sched, &e->sorted};
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->atasks, &e->gcnt, &e->sched, &e->sorted};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -736,12 +736,10 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         max_dp_per_pair = kMaxMapped + 1;
     }
     const bool use_mapper = !(positions && positions->off && positions->pos) && cfg->map_positions;
-    int mapper_maxt = 0;
     if (use_mapper) {
         long long max_hap = 0;
         for (int h = 0; h < H; ++h) max_hap = std::max(max_hap, s.hap_off_host[h + 1] - s.hap_off_host[h]);
-        mapper_maxt = max_hap - 5 <= 512 ? 512 : 2048;
-        if (max_hap - 5 > 2048) { e->err = "haplotype longer than 2053 bp: the device k-mer mapper cannot take it (pass explicit positions)"; return PHMM_ERR_INVALID; }
+        if (max_hap > 65535) { e->err = "haplotype longer than 65535 bp: the device k-mer mapper indexes k-mer positions with 16 bits (pass explicit positions)"; return PHMM_ERR_INVALID; }
         if (s.hap_bases > 65535LL * 65535LL) { e->err = "haplotype block too large"; return PHMM_ERR_INVALID; }
         CU(e->rhash.ensure((size_t)s.read_bases * sizeof(uint16_t)));
         CU(e->kbins.ensure((size_t)H * (kKmerBins + 1) * sizeof(int)));
@@ -822,6 +820,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     p.flank_cursor = counters + 1;
     p.any_flank_tasks = counters + 2;
     p.slow_count = counters + 3;
+    p.acc_cursor = counters + 4;
+    p.any_acc_tasks = counters + 5;
 
     // Tile size: the per-tile scratch (mapped candidate lists, DP task lists, traceback queue) must fit fixed budgets.
     const long long slow_budget = 8LL << 20;   // traceback-queue entries (16 bytes each)
@@ -849,13 +849,18 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
     {
         CU(e->ftasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
-        CU(e->fcnt.ensure(2 * tile_list_cap * sizeof(int)));
+        CU(e->fcnt.ensure(3 * tile_list_cap * sizeof(int)));
         p.ftasks = e->ftasks.as<uint32_t>();
         p.fcnt = e->fcnt.as<int>();
         // the 32-bit flank kernel's lists (near-flank candidates, reads holding 'N'): whether any exist is only known on the device
         CU(e->gtasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
         p.gtasks = e->gtasks.as<uint32_t>();
         p.gcnt = p.fcnt + tile_list_cap;
+        p.acnt = p.fcnt + 2 * tile_list_cap;
+        if (p.use_flanks && band <= 32) {            // the lean flank kernel's lists
+            CU(e->atasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
+            p.atasks = e->atasks.as<uint32_t>();
+        }
     }
     // traceback scratch: 1 byte per band cell per resident thread; very long reads get fewer threads instead of more memory
     const long long bp_per_thread = (long long)(Lmax_all + 1) * (2 * band);
@@ -908,16 +913,11 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     lap("kernel attrs");
     // k-mer mapper variant: vote-array capacity by the longest haplotype, byte counters when no read can cast > 255 votes
     const bool mapper_bytes = Lmax_all - kKmer + 1 <= 255;
-    auto launch_mapper = [&](unsigned grid, unsigned block, const int* list, int n_list, int base, int kind) {
-#define PHMM_MAP_ARGS list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>()
-        if (mapper_maxt == 512) {
-            if (mapper_bytes) k_kmer_map<512, uint8_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
-            else k_kmer_map<512, uint16_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
-        } else {
-            if (mapper_bytes) k_kmer_map<2048, uint8_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
-            else k_kmer_map<2048, uint16_t><<<grid, block, 0, e->stream>>>(PHMM_MAP_ARGS);
-        }
-#undef PHMM_MAP_ARGS
+    auto launch_mapper = [&](const int* list, int n_list, int base, int kind) {
+        const long long warps = (long long)n_list * H;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((warps + kMapWarps - 1) / kMapWarps, (long long)e->sm_count * 8));
+        if (mapper_bytes) k_kmer_map<uint8_t><<<grid, kMapWarps * 32, 0, e->stream>>>(list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+        else k_kmer_map<uint16_t><<<grid, kMapWarps * 32, 0, e->stream>>>(list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
     };
     // the 32-bit flank kernel over the current list (near-flank candidates, and every candidate of pair-list reads holding 'N')
     auto launch_flank = [&](int n_entries, int row_stride) -> int {
@@ -934,6 +934,18 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                      k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
         }
         LAUNCHED();
+        if (p.atasks) {
+            const unsigned agrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 4));
+            switch (band) {
+                case 8:  if ((frc = fast_smem_attr(e, k_populate_flank_acc<8>, fsmem))) return frc;
+                         k_populate_flank_acc<8><<<agrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                case 16: if ((frc = fast_smem_attr(e, k_populate_flank_acc<16>, fsmem))) return frc;
+                         k_populate_flank_acc<16><<<agrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                default: if ((frc = fast_smem_attr(e, k_populate_flank_acc<32>, fsmem))) return frc;
+                         k_populate_flank_acc<32><<<agrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+            }
+            LAUNCHED();
+        }
         return PHMM_OK;
     };
     ChunkOrder chunk_order(e);
@@ -948,14 +960,14 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             p.list = p.pair_reads; p.list_kind = 0; p.n_list = 2 * np; p.list_base = (int)(2 * p0);
             p.row_stride = fast_row_stride;
             if (use_mapper) {
-                const long long threads = 2LL * np * H;
-                launch_mapper((unsigned)((threads + 127) / 128), 128, p.list, p.n_list, p.list_base, 0);
+                launch_mapper(p.list, p.n_list, p.list_base, 0);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            CU(cudaMemsetAsync(counters, 0, 3 * sizeof(int), e->stream));                       // pair cursor, flank cursor, any-flank-tasks
+            CU(cudaMemsetAsync(counters, 0, 6 * sizeof(int), e->stream));                       // cursors, any-tasks flags (the traceback queue is empty between tiles)
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.gcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
+            CU(cudaMemsetAsync(p.acnt, 0, (size_t)2 * np * sizeof(int), e->stream));
             {   // classify pass: shortcut values → best[], near-flank candidates → slow queue, DP candidates → task lists
                 const long long threads = 2LL * np * H;
                 k_populate_generic<64, true><<<(unsigned)((threads + 127) / 128), 128, 0, e->stream>>>(p);
@@ -984,13 +996,14 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             const long long threads = (long long)nw * H;
             const unsigned cgrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 127) / 128, (long long)e->sm_count * 64));
             if (use_mapper) {
-                launch_mapper(cgrid, 128, p.list, nw, (int)w0, 1);
+                launch_mapper(p.list, nw, (int)w0, 1);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            CU(cudaMemsetAsync(counters, 0, 3 * sizeof(int), e->stream));
+            CU(cudaMemsetAsync(counters, 0, 6 * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)nw * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.gcnt, 0, (size_t)nw * sizeof(int), e->stream));
+            CU(cudaMemsetAsync(p.acnt, 0, (size_t)nw * sizeof(int), e->stream));
             k_populate_generic<64, true><<<cgrid, 128, 0, e->stream>>>(p);          // classify pass over the wide list
             LAUNCHED();
             const unsigned wgrid = (unsigned)std::max(1, std::min((nw + wide_warps - 1) / wide_warps, e->sm_count * wide_blocks_per_sm));
@@ -1013,7 +1026,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             const long long threads = (long long)ng * H;
             const unsigned ggrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 63) / 64, (long long)e->sm_count * 32));
             if (use_mapper) {
-                launch_mapper(ggrid, 64, p.list, ng, (int)g0, 2);
+                launch_mapper(p.list, ng, (int)g0, 2);
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }

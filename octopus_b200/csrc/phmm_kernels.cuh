@@ -352,10 +352,16 @@ struct PopParams {
     uint32_t* ftasks;
     int* fcnt;
     int fcap;
-    // near-flank candidates of fast-path reads, same layout (consumed by k_populate_flank)
+    // near-flank candidates of fast-path reads, same layout: gtasks for k_populate_flank (crossing cells as payload: any flank
+    // geometry, reads with 'N'), atasks for k_populate_flank_acc (the lean form: in-flank penalty as payload; ACGT reads whose
+    // window keeps at least two read bases outside the flanks whatever the path)
     uint32_t* gtasks;
     int* gcnt;
     int* flank_cursor;
+    uint32_t* atasks;
+    int* acnt;
+    int* acc_cursor;
+    int* any_acc_tasks;
     int units_per_pair;         // fast kernel: a read pair's task lists are cut into this many work units of kRoundsPerUnit rounds
     int band, nuc_prior;
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
@@ -420,6 +426,18 @@ __device__ __forceinline__ int list_append_slot(int* counts, const int li)
     return base + __popc(peers & ((1u << lane) - 1u));
 }
 
+// as list_append_slot, for lanes that may append to different lists (route) of the same slot
+__device__ __forceinline__ int list_append_slot2(int* counts, const int li, const int route)
+{
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, li * 4 + route);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counts + li, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void push_slow(const PopParams& p, const int r, const int h, const int a)
 {
     const int idx = atomicAdd(p.slow_count, 1);
@@ -456,8 +474,8 @@ __global__ void k_read_kmers(const long long n_bases, const int n_reads, const l
     for (int y = lane; y + kKmer <= L; y += 32) rhash[b + y] = (uint16_t)kmer_hash(bases + b + y);
 }
 
-// populate_kmer_hash_table<6> (:85-98) per haplotype: bins[h][hash] = first item | item count << 16 (both < 2^16: a haplotype
-// the mapper takes has at most 2048 k-mers), items[hap base offset + ...] = k-mer positions, ascending within a bin.
+// populate_kmer_hash_table<6> (:85-98) per haplotype: bins[h][hash] = first item | item count << 16 (both < 2^16: the mapper
+// takes haplotypes of up to 65 535 bases), items[hap base offset + ...] = k-mer positions, ascending within a bin.
 // One block per haplotype.
 __global__ void k_build_kmer_table(const int H, const long long* __restrict__ off, const char* __restrict__ seq,
                                    uint32_t* __restrict__ bins, uint16_t* __restrict__ items)
@@ -500,61 +518,94 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
 }
 
 // map_query_to_target (:120-159) for every (read of the work list, haplotype): the first <= 10 mapping begins (ascending)
-// whose vote count equals the maximum. One thread per pair; the vote counts live in a per-thread local array, handled a
-// 32-bit word at a time where possible (clear, final scan). CountT = uint8_t when no diagonal can collect more than 255
-// votes (a diagonal gets at most one vote per query k-mer, so reads of <= 260 bases), else uint16_t.
-template <int MAXT, typename CountT>
-__global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int kind,
-                           const DevHaps hp, const DevReads rd,
-                           const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ bins, const uint16_t* __restrict__ items,
-                           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
+// whose vote count equals the maximum. votes[d] = number of query k-mers qi whose k-mer also starts at target position qi + d.
+// One WARP per pair: the vote counters of a tile of kMapTile diagonals live in shared memory, packed 4 (or 2) per word and
+// updated with word atomics (no counter can overflow into its neighbour: a diagonal collects at most one vote per query k-mer;
+// CountT = uint8_t for reads of <= 260 bases, else uint16_t). Every lane walks a CONTIGUOUS block of query k-mers, so the hits a
+// well-aligned read scores on one diagonal collapse into one atomic per lane instead of one per k-mer. Haplotypes with more than
+// kMapTile k-mers are handled tile by tile (ascending diagonals, so the "first ten at the maximum" order is kept).
+// Round 1's version kept a per-THREAD vote array in local memory (<= 2048 k-mers, else an error) and was L1/L2-latency bound.
+constexpr int kMapTile = 2048;
+constexpr int kMapWarps = 8;
+
+template <typename CountT>
+__global__ void __launch_bounds__(kMapWarps * 32)
+k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int kind,
+           const DevHaps hp, const DevReads rd,
+           const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ bins, const uint16_t* __restrict__ items,
+           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
 {
-    constexpr int PER = 4 / (int)sizeof(CountT);
+    constexpr int PER = 4 / (int)sizeof(CountT), BITS = 8 * (int)sizeof(CountT);
+    constexpr uint32_t FIELD = (1u << BITS) - 1u;
+    __shared__ uint32_t s_votes[kMapWarps][kMapTile / PER];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* votes = s_votes[warp];
     const int H = hp.n;
-    // the tile's work list: 2 entries per read pair, or the generic reads; clipped against the scheduler's totals
+    // the tile's work list (pair list entries may be -1), clipped against the scheduler's totals
     const int n_list = max(0, min(n_list_max, list_total(tot, kind) - base));
-    const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const long long total = (long long)n_list * H, step = (long long)gridDim.x * kMapWarps;
+    for (long long i = (long long)blockIdx.x * kMapWarps + warp; i < total; i += step) {
         int li, h;
         split_index(i, H, &li, &h);
         const int r = list[li];
-        uint8_t n_out = 0;
+        int n_out = 0;
         if (r >= 0) {
             const long long ro = rd.off[r], ho = hp.off[h];
             const int nq = (int)(rd.off[r + 1] - ro) - kKmer + 1, nt = (int)(hp.off[h + 1] - ho) - kKmer + 1;
-            if (nq > 0 && nt > 0 && nt <= MAXT) {
-                uint32_t words[MAXT / PER];
-                CountT* counts = reinterpret_cast<CountT*>(words);
-                const int nwords = (nt + PER - 1) / PER;
-                for (int w = 0; w < nwords; ++w) words[w] = 0u;
+            if (nq > 0 && nt > 0) {
                 const uint32_t* bs = bins + (size_t)h * (kKmerBins + 1);
                 const uint16_t* it = items + ho;
-                unsigned max_hit = 0;
-                for (int qi = 0; qi < nq; ++qi) {
-                    const uint32_t bin = bs[rhash[ro + qi]];
-                    const int e0 = (int)(bin & 0xFFFFu), e1 = e0 + (int)(bin >> 16);
-                    for (int e = e0; e < e1; ++e) {
-                        const int ti = it[e];
-                        if (ti >= qi) { const unsigned c = ++counts[ti - qi]; max_hit = c > max_hit ? c : max_hit; }
-                    }
-                }
-                if (max_hit > 0) {
-                    int32_t* out = kpos + (size_t)i * kMaxMapped;
-                    for (int w = 0; w < nwords && n_out < kMaxMapped; ++w) {
-                        uint32_t v = words[w];
-                        if (v == 0u) continue;
-#pragma unroll
-                        for (int b = 0; b < PER; ++b) {
-                            const unsigned c = v & ((1u << (8 * sizeof(CountT))) - 1u);
-                            v >>= 4 * sizeof(CountT); v >>= 4 * sizeof(CountT);
-                            const int t = w * PER + b;
-                            if (c == max_hit && t < nt && n_out < kMaxMapped) out[n_out++] = t;
+                int32_t* out = kpos + (size_t)i * kMaxMapped;
+                const int per_lane = (nq + 31) / 32, q0 = min(nq, lane * per_lane), q1 = min(nq, q0 + per_lane);
+                unsigned best = 0;
+                for (int d0 = 0; d0 < nt; d0 += kMapTile) {
+                    const int dn = min(kMapTile, nt - d0), nwords = (dn + PER - 1) / PER;
+                    for (int w = lane; w < nwords; w += 32) votes[w] = 0u;
+                    __syncwarp();
+                    int run_d = -1, run_n = 0;
+                    for (int qi = q0; qi < q1; ++qi) {
+                        const uint32_t bin = bs[rhash[ro + qi]];
+                        const int e0 = (int)(bin & 0xFFFFu), e1 = e0 + (int)(bin >> 16);
+                        for (int e = e0; e < e1; ++e) {
+                            const int d = (int)it[e] - qi - d0;          // diagonal within the tile (the reference keeps target_index >= query_index)
+                            if (d < 0 || d >= dn) continue;
+                            if (d == run_d) { ++run_n; continue; }
+                            if (run_n) atomicAdd(&votes[run_d / PER], (uint32_t)run_n << (BITS * (run_d % PER)));
+                            run_d = d; run_n = 1;
                         }
                     }
+                    if (run_n) atomicAdd(&votes[run_d / PER], (uint32_t)run_n << (BITS * (run_d % PER)));
+                    __syncwarp();
+                    unsigned m = 0;
+                    for (int w = lane; w < nwords; w += 32) {
+                        uint32_t v = votes[w];
+#pragma unroll
+                        for (int b = 0; b < PER; ++b) { m = max(m, v & FIELD); v >>= BITS / 2; v >>= BITS / 2; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (m > best) { best = m; n_out = 0; }            // a higher count: what earlier tiles listed is void
+                    if (m == best && best > 0) {
+                        for (int w0 = 0; w0 < nwords && n_out < kMaxMapped; w0 += 32) {
+                            const int w = w0 + lane;
+                            uint32_t v = w < nwords ? votes[w] : 0u;
+                            unsigned hits = 0;
+#pragma unroll
+                            for (int b = 0; b < PER; ++b) { if ((v & FIELD) == best && w * PER + b < dn) hits |= 1u << b; v >>= BITS / 2; v >>= BITS / 2; }
+                            int mine = __popc(hits), incl = mine;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                            int pos = n_out + incl - mine;
+#pragma unroll
+                            for (int b = 0; b < PER; ++b) if ((hits >> b) & 1u) { if (pos < kMaxMapped) out[pos] = d0 + w * PER + b; ++pos; }
+                            n_out = min(kMaxMapped, n_out + __shfl_sync(0xffffffffu, incl, 31));
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
-        kcnt[i] = n_out;
+        if (lane == 0) kcnt[i] = (uint8_t)n_out;
     }
 }
 
@@ -696,6 +747,61 @@ k_populate_flank(const PopParams p)
     }
 }
 
+// The lean flank-aware kernel (dp_flank_acc): same shape as k_populate_flank, over the atasks lists.
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, BAND <= 16 ? 4 : 1)
+k_populate_flank_acc(const PopParams p)
+{
+    extern __shared__ RowEntry smem_rows[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int R = p.rd.n;
+    constexpr int K = 2 * BAND;
+    if (*p.any_acc_tasks == 0) return;
+    const int n_list = tile_list(p);
+    for (;;) {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(p.acc_cursor, 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li >= n_list) break;
+        const int r = p.list[li];
+        const int n = r >= 0 ? p.acnt[li] : 0;
+        if (n == 0) continue;
+        const int L = p.rd.info[r].x;
+        __syncwarp();
+        unsigned qmin = 255u;
+        {
+            const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
+            for (int y = lane; y < L; y += 32) { const uint16_t half = hr[y]; rows[y] = make_row_entry_facc(half); qmin = min(qmin, (unsigned)half >> 8); }
+            if (lane == 0) rows[L] = pad_row_entry_facc();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
+        const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
+        const int W = L + K - 1;
+        for (int c = 0; c < n; c += 32) {
+            const bool valid = c + lane < n;
+            const uint32_t t = q[valid ? c + lane : 0];
+            const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
+            const int hap_len = (int)(p.hp.off[h + 1] - p.hp.off[h]);
+            int lhs, rhs;
+            window_flanks(a, W, hap_len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+            const int xl = lhs, xr = (W - rhs >= W) ? W + 1 : W - rhs;
+            int score, flank;
+            dp_flank_acc<BAND>(rows, L, tab + p.hp.off[h] + a, p.nuc_prior, xl, xr, &score, &flank);
+            // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
+            const bool replay_differs = flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
+            if (valid) {
+                if (replay_differs) push_slow(p, r, h, a);
+                else atomicMin(p.best + (size_t)h * R + r, score - flank);
+            }
+        }
+    }
+}
+
 // Generic path of populate: reads the fast path cannot take (non-ACGT bases, 16-bit-unsafe qualities, very long reads)
 // or every read when the band is > 32 / int32 scores were requested. One thread per (haplotype, read) pair.
 // With FASTQ it is the classify pass of the fast path instead: the same candidate walk over the fast work list (the pair
@@ -740,10 +846,23 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
                 }
             } else {
                 if (FASTQ && p.band <= 32 && !(p.rd.info[r].y & kReadUnsafeFlank32)) {
-                    const int slot = list_append_slot(p.gcnt, li);
-                    if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
+                    // which flank-aware kernel: window-coordinate flanks of this candidate (pair_hmm.hpp:573-588)
+                    int route = 0;                                   // 0: crossing-cell kernel, 1: lean kernel, 2: plain score-only DP
+                    if ((pend_flank >> i2) & 1u) {
+                        const int W = rv.len + 2 * p.band - 1;
+                        int lhs, rhs;
+                        window_flanks(v, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+                        const int xl = lhs, xr = W - rhs;
+                        if (xr <= xl) route = to_32bit ? 0 : 2;      // the flanks cover the whole window: the result is the plain score (:757-759)
+                        else if (!(p.rd.info[r].y & kReadHasN) && p.atasks && flank_mask_cannot_zero(rv.len, p.band, xl, xr >= W ? W + 1 : xr)) route = 1;
+                    }
+                    uint32_t* tasks = route == 0 ? p.gtasks : route == 1 ? p.atasks : p.ftasks;
+                    int* counts = route == 0 ? p.gcnt : route == 1 ? p.acnt : p.fcnt;
+                    const int slot = list_append_slot2(counts, li, route);
+                    if (slot < p.fcap) tasks[(size_t)li * p.fcap + slot] = (uint32_t)h | ((uint32_t)v << 16);
                     else atomicOr(p.flags, 8);
-                    *p.any_flank_tasks = 1;
+                    if (route == 0) *p.any_flank_tasks = 1;
+                    if (route == 1) *p.any_acc_tasks = 1;
                 } else push_slow(p, r, h, v);
             }
         }

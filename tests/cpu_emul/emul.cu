@@ -210,3 +210,35 @@ extern "C" int emul_dp_band(int word32, int band, int L, const char* read0, cons
     *score0 = (int)(r & 0xFFFF); *score1 = (int)(r >> 16);
     return 0;
 }
+
+// dp_flank_acc<band> on the CPU (the lean flank-aware DP: the in-flank penalty rides along as an additive payload).
+// Returns 0, 1 when the candidate does not qualify (fewer than two read bases certain to lie outside the flanks, or flanks that
+// overlap: the kernel keeps those on dp_flank32 / the plain DP), 2 when the replay quirk sends it to the traceback path, -1 on a bad read base.
+extern "C" int emul_dp_flank_acc(int band, int L, const char* read, const uint8_t* q, const char* truth, const char* mask, const int8_t* prior,
+                                 const int8_t* go, const int8_t* ge, int nuc_prior, int lhs_flank, int rhs_flank, int* score, int* flank)
+{
+    const int W = L + 2 * band - 1;
+    std::vector<RowEntry> rows(L + 1);
+    bool low_quality = false;
+    for (int y = 0; y < L; ++y) {
+        const int c = base_code(read[y]);
+        if (c < 0 || c > 3) return -1;
+        rows[y] = make_row_entry_facc((uint32_t)c | ((uint32_t)q[y] << 8));
+        low_quality = low_quality || q[y] < 2;
+    }
+    rows[L] = pad_row_entry_facc();
+    std::vector<ColEntry> t(W);
+    for (int x = 0; x < W; ++x) t[x] = make_col_entry(truth[x], mask[x], prior[x], go[x], ge[x]);
+    int xl = lhs_flank, xr = W - rhs_flank;
+    if (xr <= xl) return 1;
+    if (xr >= W) xr = W + 1;
+    if (!flank_mask_cannot_zero(L, band, xl, xr)) return 1;
+    if (flank_replay_may_differ(t.data(), W, lhs_flank, rhs_flank, low_quality)) return 2;
+    switch (band) {
+        case 8:  dp_flank_acc<8>(rows.data(), L, t.data(), nuc_prior, xl, xr, score, flank); break;
+        case 16: dp_flank_acc<16>(rows.data(), L, t.data(), nuc_prior, xl, xr, score, flank); break;
+        case 32: dp_flank_acc<32>(rows.data(), L, t.data(), nuc_prior, xl, xr, score, flank); break;
+        default: return -1;
+    }
+    return 0;
+}

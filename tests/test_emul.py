@@ -173,3 +173,41 @@ def test_flank_payload_dp_matches_traceback_flank_replay(emul, coracle):
         else:
             assert (sc.value, ms.value) == (es, ems) and fl.value <= efs, (band, L, lhs, rhs)
     assert n_routed < 40                     # rare with ordinary penalties (needs an in-flank 'N' column with an SNV prior of 1)
+
+
+def test_lean_flank_dp_matches_traceback_flank_replay(emul, coracle):
+    """dp_flank_acc (the in-flank penalty carried as an additive payload) == score and flank score of the oracle's traceback +
+    replay wherever the kernel uses it: at least two read bases certain to lie outside the flanks (then the reference's
+    `read_len - mask < 2` branch cannot fire), ACGT reads."""
+    emul.emul_dp_flank_acc.argtypes = [C.c_int, C.c_int] + [vp] * 7 + [C.c_int, C.c_int, C.c_int, vp, vp]
+    rng = np.random.default_rng(23)
+    n_used = 0
+    for it in range(2500):
+        band = int(rng.choice([8, 16, 32]))
+        L = int(rng.integers(1, 200))
+        nuc = int(rng.integers(0, 5))
+        c = random_alignment_case(rng, band, L, qmax=60 if it % 5 == 0 else 41)
+        W = len(c["truth"])
+        mode = it % 4
+        if mode == 0:
+            lhs, rhs = int(rng.integers(0, W // 3 + 1)), int(rng.integers(0, W // 3 + 1))
+        elif mode == 1:
+            lhs, rhs = int(rng.integers(0, W // 2 + 1)), 0
+        elif mode == 2:
+            lhs, rhs = 0, int(rng.integers(0, W // 2 + 1))
+        else:
+            lhs, rhs = int(rng.integers(0, W + 1)), int(rng.integers(0, W + 1))
+        sc, fl = C.c_int(0), C.c_int(0)
+        rc = emul.emul_dp_flank_acc(band, L, P(c["read"]), P(c["quals"]), P(c["truth"]), P(c["snv_mask"]), P(c["snv_prior"]), P(c["gap_open"]),
+                                    P(c["gap_extend"]), nuc, lhs, rhs, C.byref(sc), C.byref(fl))
+        assert rc in (0, 1, 2)
+        if rc != 0:
+            continue
+        n_used += 1
+        q8 = c["quals"].astype(np.int8)
+        t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
+        es, efp, a1, a2 = coracle.align_tb(band, t, r, q8, c["gap_open"], c["gap_extend"], nuc, m, c["snv_prior"])
+        efs, ems = coracle.flank_score(W, lhs, rhs, r, q8, m, c["snv_prior"], c["gap_open"], c["gap_extend"], nuc, efp, a1, a2)
+        assert L - ems >= 2, (band, L, lhs, rhs, ems)          # the guarantee the kernel relies on
+        assert (sc.value, fl.value) == (es, efs), (band, L, lhs, rhs)
+    assert n_used > 800
