@@ -181,3 +181,65 @@ def test_populate_with_error_model_penalties(engine, coracle):
             assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
             ok, worst = _close(got[ok_pairs], want[ok_pairs])
             assert ok, (flanks, mapit, worst)
+
+
+def test_device_mapper_takes_long_haplotypes(engine, coracle):
+    """Round 1's mapper refused haplotypes above 2053 bp (per-thread vote arrays); the reference has no such limit. Now the votes
+    live in shared-memory tiles of 2048 diagonals: several tiles, ties across tiles, long reads (16-bit counters)."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from octopus_b200.batch import pack_haplotypes, pack_reads
+    rng = np.random.default_rng(61)
+    band = 16
+    for hap_len, read_lens in ((5200, [100, 150]), (4500, [150, 300, 420])):
+        base = ACGT[rng.integers(0, 4, hap_len)].copy()
+        base[3000:3400] = base[600:1000]                 # a 400-base duplication: equal vote counts 2400 diagonals apart
+        seqs = []
+        for h in range(5):
+            s = base.copy()
+            s[rng.integers(0, hap_len, 12)] = ACGT[rng.integers(0, 4, 12)]
+            seqs.append(s)
+        haps = pack_haplotypes(seqs, [np.roll(s, 1) for s in seqs], [rng.integers(1, 126, hap_len).astype(np.int8) for _ in seqs],
+                               [np.roll(s, -1) for s in seqs], [rng.integers(1, 126, hap_len).astype(np.int8) for _ in seqs],
+                               [rng.integers(3, 46, hap_len).astype(np.int8) for _ in seqs], [rng.integers(1, 11, hap_len).astype(np.int8) for _ in seqs],
+                               begin=np.zeros(5, np.int64))
+        bases, quals, begin = [], [], []
+        for r in range(40):
+            L = int(rng.choice(read_lens))
+            p = int(rng.choice([rng.integers(0, hap_len - L), rng.integers(600, 1000 - min(L, 399))]))
+            b = base[p:p + L].copy()
+            for _ in range(int(rng.integers(0, 3))):
+                b[rng.integers(0, L)] = ACGT[rng.integers(0, 4)]
+            bases.append(b); quals.append(rng.integers(10, 42, L).astype(np.uint8)); begin.append(p)
+        reads = pack_reads(bases, quals, begin=np.asarray(begin, np.int64))
+        for flanks in (None, (500, 700)):
+            cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, map_positions=True)
+            got, st = engine.populate(cfg, haps, reads, None, flanks, want_status=True)
+            rc, want, wst = coracle.populate(band, haps, reads, None, flanks, map_positions=True)
+            ok_pairs = wst == 0
+            assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
+            ok, worst = _close(got[ok_pairs], want[ok_pairs])
+            assert ok, (hap_len, flanks, worst)
+
+
+def test_lean_flank_kernel_geometries(engine, coracle):
+    """Flank states from none to overlapping, short and long reads, qualities down to 0: the lean flank kernel, the crossing-cell
+    kernel (narrow non-flank windows, reads with 'N'), the plain DP (flanks covering the window) and the traceback queue all meet
+    the oracle."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    rng = np.random.default_rng(71)
+    for band in (8, 16, 32):
+        for trial in range(5):
+            hap_len = int(rng.choice([300, 420]))
+            haps, reads = random_region(rng, band, n_haps=int(rng.integers(2, 30)), n_reads=int(rng.integers(5, 60)), hap_len=hap_len,
+                                        read_len_choices=[25, 40, 76, 100, 150], read_n_rate=0.1, edge_reads=(trial % 2 == 0))
+            if trial == 4:
+                reads.quals[rng.random(len(reads.quals)) < 0.1] = 0
+            for flanks in ((0, 0), (30, 40), (int(hap_len * 0.45), int(hap_len * 0.45)), (hap_len // 2, hap_len // 2 + 5), (hap_len - 10, 0), (0, hap_len - 20)):
+                for mapit in (False, True):
+                    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, map_positions=mapit)
+                    got, st = engine.populate(cfg, haps, reads, None, flanks, want_status=True)
+                    rc, want, wst = coracle.populate(band, haps, reads, None, flanks, map_positions=mapit)
+                    ok_pairs = wst == 0
+                    assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
+                    ok, worst = _close(got[ok_pairs], want[ok_pairs])
+                    assert ok, (band, trial, flanks, mapit, worst)
