@@ -46,6 +46,11 @@ def parse_args():
     ap.add_argument("--hap-len", type=int, default=None, help="override the haplotype length")
     ap.add_argument("--read-lens", default=None, help="override the read lengths, comma separated")
     ap.add_argument("--int-scores", action="store_true", help="HaplotypeLikelihoodModel::Config::use_int_scores (reference: int32 lanes)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns a batch of the config's shape; strong: the config's reads are split over the ranks (SURVEY.md §8e, C3) "
+                         "and the [H, R] matrix is re-assembled on rank 0")
+    ap.add_argument("--regions", type=int, default=None, help="regions per rank and step (C5: 1k regions over 8 GPUs = 125 per rank); each its own reads and haplotypes")
+    ap.add_argument("--error-model", default=None, help="haplotype penalty arrays from the reference's error models (reset()), e.g. PCR-free.HiSeq-2500, instead of i.i.d. draws")
     return ap.parse_args()
 
 
@@ -148,10 +153,10 @@ def reference_batch_dict(haps, reads):
                 hap_prior_rev=haps.snv_prior_rev, hap_gap_open=haps.gap_open, hap_gap_extend=haps.gap_extend, hap_off=haps.off)
 
 
-def cpu_reference_run(haps, reads, band, n_sample_reads, threads):
-    """Time the reference's own SIMD kernel (oracle/_ref; AVX2 build = what BASELINE names) — or, where that build is
-    absent, the C port — on the first n_sample_reads reads x all haplotypes, one mapping position per pair.
-    Returns (gcups, seconds, kind, isa_name, cells)."""
+def cpu_reference_run(haps, reads, band, n_sample_reads, threads, isa=None, want_scores=False):
+    """Time the reference's own SIMD kernel (oracle/_ref; the build its -march=native would select = what BASELINE names) — or,
+    where that build is absent, the C port — on the first n_sample_reads reads x all haplotypes, one mapping position per pair.
+    Returns (gcups, seconds, kind, isa_name, cells[, integer scores [n, H] or None])."""
     from oracle.oracle import COracle, RefKernel, available_ref_isas
     n = min(n_sample_reads, reads.n)
     H = haps.n
@@ -159,7 +164,7 @@ def cpu_reference_run(haps, reads, band, n_sample_reads, threads):
     cells = int((2 * (lens + band) * band).sum()) * H
     isas = available_ref_isas()
     if isas:
-        isa = isas[0]   # the widest build this host runs == what the reference's -march=native build would select (AVX2 for band 16)
+        isa = isa or isas[0]   # the widest build this host runs == what the reference's -march=native build would select
         k = RefKernel(isa)
         batch = reference_batch_dict(haps, reads)
         ridx = np.repeat(np.arange(n, dtype=np.int32), H)
@@ -170,12 +175,16 @@ def cpu_reference_run(haps, reads, band, n_sample_reads, threads):
         for strand in (False, True):
             sel = rev == strand
             if sel.any():
-                parts.append((strand, np.ascontiguousarray(ridx[sel]), np.ascontiguousarray(hidx[sel]), np.ascontiguousarray(woff[sel])))
+                parts.append((strand, sel, np.ascontiguousarray(ridx[sel]), np.ascontiguousarray(hidx[sel]), np.ascontiguousarray(woff[sel])))
+        scores = np.empty(n * H, dtype=np.int32) if want_scores else None
         t0 = time.perf_counter()
-        for strand, a, b, c in parts:
-            k.align_batch(band, batch, a, b, c, nuc_prior=2, nthreads=threads, strand_rev=strand)
+        for strand, sel, a, b, c in parts:
+            out = k.align_batch(band, batch, a, b, c, nuc_prior=2, nthreads=threads, strand_rev=strand)
+            if want_scores:
+                scores[sel] = out
         dt = time.perf_counter() - t0
-        return cells / dt / 1e9, dt, "reference", "%s<%d,short> (%s build)" % (k.name(band), band, isa), cells
+        res = (cells / dt / 1e9, dt, "reference", "%s<%d,short> (%s build)" % (k.name(band), band, isa), cells)
+        return res + (scores.reshape(n, H),) if want_scores else res
     from octopus_b200.batch import ReadBlock
     a = int(reads.off[n])
     sub = ReadBlock(reads.off[:n + 1], reads.bases[:a], reads.quals[:a], reads.mapq[:n], reads.reverse[:n], reads.begin[:n])
@@ -183,7 +192,59 @@ def cpu_reference_run(haps, reads, band, n_sample_reads, threads):
     t0 = time.perf_counter()
     o.populate(band, haps, sub, dp_only=True)
     dt = time.perf_counter() - t0
-    return cells / dt / 1e9, dt, "port", "scalar C restatement", cells
+    res = (cells / dt / 1e9, dt, "port", "scalar C restatement", cells)
+    return res + (None,) if want_scores else res
+
+
+def sample_reads(reads, n):
+    from octopus_b200.batch import ReadBlock
+    n = min(n, reads.n)
+    a = int(reads.off[n])
+    return ReadBlock(reads.off[:n + 1], reads.bases[:a], reads.quals[:a], reads.mapq[:n], reads.reverse[:n], reads.begin[:n])
+
+
+def parity_gate(eng, haps, reads, band, flank_state, shortcut, mapit, int_scores, ref_scores, n_ref):
+    """BASELINE.md §3 "parity gate before any timing counts", inside the timed run's process. Headline mode: the reference SIMD
+    kernel's INTEGER scores of the cpu_baseline sample (already computed) against the GPU's, recovered exactly from a second call on
+    the same reads with mapping-quality mixing off (ln-likelihood = -ln10/10 * integer). Other modes: the GPU's ln-likelihoods of a
+    small sample against the oracle's populate in the same mode (1e-4 relative, integers exact)."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    c = 0.230258509299404568401799145468436420760110148862877297603
+    if ref_scores is not None and flank_state is None and not shortcut and not mapit:
+        sub = sample_reads(reads, n_ref)
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, map_positions=False, use_mapping_quality=False,
+                                              use_int_scores=int_scores)
+        lnl = eng.populate(cfg, haps, sub)                       # [H, n]
+        got = np.rint(-lnl / c).astype(np.int64)
+        exact = np.abs(-c * got - lnl) <= 1e-9 * np.maximum(1.0, np.abs(lnl))
+        mism = int((got != ref_scores.T.astype(np.int64)).sum() + (~exact).sum())
+        return {"pairs": int(got.size), "mismatches": mism, "against": "reference SIMD kernel, integer scores of the cpu_baseline sample"}
+    from oracle.oracle import COracle
+    sub = sample_reads(reads, 48)
+    hs = haps
+    if haps.n > 64:                                              # keep the scalar oracle's share of the run small
+        from octopus_b200.batch import HaplotypeBlock
+        e = int(haps.off[64])
+        hs = HaplotypeBlock(haps.off[:65], haps.seq[:e], haps.snv_mask_fwd[:e], haps.snv_prior_fwd[:e], haps.snv_mask_rev[:e],
+                            haps.snv_prior_rev[:e], haps.gap_open[:e], haps.gap_extend[:e], haps.begin[:64])
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=not shortcut, map_positions=mapit, use_int_scores=int_scores)
+    got, st = eng.populate(cfg, hs, sub, flank_state=flank_state, want_status=True)
+    rc, want, wst = COracle().populate(band, hs, sub, None, flank_state, dp_only=not shortcut, map_positions=mapit)
+    ok = wst == 0
+    rel = np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-300)
+    return {"pairs": int(ok.sum()), "mismatches": int((rel > 1e-4).sum() + (st[~ok] != wst[~ok]).sum()),
+            "against": "oracle populate in the same mode (C restatement pinned to the compiled reference), 1e-4 relative"}
+
+
+def measured_traffic(config, R, H, band, mode_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
+    (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files); None when this workload was never captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("%s:%d:%d:%d:%s" % (config, R, H, band, mode_key))
+    except Exception:
+        return None
 
 
 def workload_name(config, R, lens, H, hap_len, band):
@@ -227,7 +288,7 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from octopus_b200 import HaplotypeLikelihoodModel, PairHMMEngine, shard, synth
+    from octopus_b200 import ErrorModel, HaplotypeLikelihoodModel, PairHMMEngine, shard, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,26 +299,70 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = synth.CONFIGS[args.config]
-    # weak scaling: every rank owns its own batch of the named shape (its own regions' reads), haplotypes replicated
     read_lens = tuple(int(x) for x in args.read_lens.split(",")) if args.read_lens else None
-    haps, reads, band = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=cfg["seed"] + 1000 * rank,
-                                         band=args.band, hap_len=args.hap_len, read_lens=read_lens)
+    strong = args.scaling == "strong" and world > 1
+    n_regions = args.regions if args.regions else (125 if args.config == "C5" else 1)
+
+    def make_region(seed):
+        h, r, b = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=seed, band=args.band, hap_len=args.hap_len, read_lens=read_lens)
+        if args.error_model:       # penalty arrays as the reference's error models assign them (tandem-repeat structured), not i.i.d.
+            h = ErrorModel(args.error_model).reset_block(h.off, h.seq, h.begin)
+        return h, r, b
+
+    # weak scaling: every rank owns its own batch(es) of the named shape (its own regions' reads and haplotypes);
+    # strong scaling: ONE batch of the named shape, its reads split contiguously over the ranks, haplotypes replicated
+    if strong:
+        haps, all_reads, band = make_region(cfg["seed"])
+        reads, (lo, hi) = shard.shard_reads(all_reads, world, rank)
+        regions = [(haps, reads)]
+        R_total = all_reads.n
+        cells_rank_total = synth.total_cells(haps, all_reads, band)          # the whole job's cells (all ranks together)
+    else:
+        regions = []
+        for g in range(n_regions):
+            h, r, band = make_region(cfg["seed"] + 1000 * rank + 7919 * g)
+            regions.append((h, r))
+        haps, reads = regions[0]
+        cells_rank_total = sum(synth.total_cells(h, r, band) for h, r in regions) * world
     H, R = haps.n, reads.n
-    cells = synth.total_cells(haps, reads, band)
     model_cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=not args.shortcut, map_positions=args.map,
                                                 use_int_scores=args.int_scores)
     flank_state = tuple(int(x) for x in args.flank.split(",")) if args.flank else None
     eng = PairHMMEngine(local)
-    d_haps, d_reads = haps.to_device(dev), reads.to_device(dev)
-    d_out = torch.empty((H, R), dtype=torch.float64, device=dev)
+    d_regions = [(h.to_device(dev), r.to_device(dev)) for h, r in regions]
+    # Two output buffers: the gather of step k (NCCL, asynchronous on torch's stream) reads one while populate k+1 writes the other;
+    # before populate k+2 re-uses a buffer the engine waits (on the device) for the event recorded after gather k.
+    n_buf = 2 if world > 1 else 1
+    d_out = [torch.empty((H, R), dtype=torch.float64, device=dev) for _ in range(n_buf)]
+    gather_done = [None] * n_buf
+    recv = None
+    if world > 1 and rank == 0 and not strong:
+        recv = [[torch.empty_like(d_out[0]) for _ in range(world)] for _ in range(n_buf)]
+    state = {"k": 0, "gather_ms": [], "launches": 0}
 
-    recv = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    def one_region(dh, dr):
+        b = state["k"] % n_buf
+        state["k"] += 1
+        if gather_done[b] is not None:
+            eng.wait_event(gather_done[b])
+        out = d_out[b] if (dh.n, dr.n) == (H, R) else None
+        out = eng.populate(model_cfg, dh, dr, flank_state=flank_state, out=out)
+        dp = eng.last_dp_kernel_ms()
+        state["launches"] += eng.launch_count()
+        if world > 1:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            if strong:
+                shard.gather_likelihoods(out, R_total, world, rank)            # the [H, R_total] matrix re-assembled on rank 0
+            else:
+                shard.gather_slabs(out, world, rank, recv=recv[b] if recv else None)   # per-rank matrices straight into rank 0's slabs
+            g1.record()
+            gather_done[b] = g1
+            state["gather_ms"].append((g0, g1))
+        return dp
 
     def step():
-        eng.populate(model_cfg, d_haps, d_reads, flank_state=flank_state, out=d_out)
-        if world > 1:
-            return shard.gather_slabs(d_out, world, rank, recv=recv)        # NCCL gather of the per-rank matrices to rank 0
-        return d_out
+        return sum(one_region(dh, dr) for dh, dr in d_regions)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -269,87 +374,115 @@ def main():
         step()
     sampler = ClockSampler(local)
     sync_all()
+    state["gather_ms"] = []
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dp_ms, launches = [], 0
+    dp_ms = []
+    state["launches"] = 0
     sync_all()
     ev0.record()
     for _ in range(args.steps):
-        step()
-        dp_ms.append(eng.last_dp_kernel_ms())
-        launches += eng.launch_count()
+        dp_ms.append(step())
     ev1.record()
+    launches = state["launches"]
     sync_all()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
+    gather_ms = float(np.mean([a.elapsed_time(b) for a, b in state["gather_ms"]])) if state["gather_ms"] else 0.0
     clocks = sampler.stop() if rank == 0 else None
 
-    # e2e: pinned host buffers through the C ABI, H2D + D2H inside the timed region
-    p_haps, p_reads = haps.pin(), reads.pin()
+    # e2e: the same call through the C ABI with pinned HOST buffers: H2D of the batch and D2H of the matrix inside the timed region
+    # (and, with several ranks, the gather of the host matrices' device copies is replaced by each rank's own D2H: the per-rank
+    # results land in host memory of the rank that computed them)
+    p_regions = [(h.pin(), r.pin()) for h, r in regions]
     p_out_t = torch.empty((H, R), dtype=torch.float64).pin_memory()
     p_out = p_out_t.numpy()
+
+    def e2e_step():
+        for ph, pr in p_regions:
+            eng.populate(model_cfg, ph, pr, flank_state=flank_state, out=p_out if (ph.n, pr.n) == (H, R) else None)
+
     for _ in range(2):
-        eng.populate(model_cfg, p_haps, p_reads, flank_state=flank_state, out=p_out)
+        e2e_step()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.populate(model_cfg, p_haps, p_reads, flank_state=flank_state, out=p_out)
+        e2e_step()
     e1.record()
     sync_all()
     ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_ms = float(ems.item())
-    h2d = sum(int(a.nbytes) for a in haps.arrays().values()) + sum(int(a.nbytes) for a in reads.arrays().values())
-    d2h = H * R * 8
+    h2d = sum(sum(int(a.nbytes) for a in h.arrays().values()) + sum(int(a.nbytes) for a in r.arrays().values()) for h, r in regions)
+    d2h = sum(h.n * r.n * 8 for h, r in regions)
 
     if rank == 0:
-        value = cells * world * args.steps / (total_ms / 1e3) / 1e9
-        e2e = cells * world * args.steps / (e2e_ms / 1e3) / 1e9
-        kernel_ms = float(np.mean(dp_ms))
-        # algorithmic HBM bytes of the dominant kernel (k_populate_fast) per launch, SURVEY.md §8(d):
-        # 4 B per pair (integer score out) + the read row half-words (2 B per read base, read once per read pair)
-        # + both strand column tables (16 B per haplotype base)
-        alg_bytes = 4 * H * R + 2 * int(reads.off[-1]) + 16 * int(haps.off[-1])
+        value = cells_rank_total * args.steps / (total_ms / 1e3) / 1e9
+        e2e = cells_rank_total * args.steps / (e2e_ms / 1e3) / 1e9
+        kernel_ms = float(np.mean(dp_ms))                      # DP kernel time per step on this rank (all its regions)
+        cells_rank = sum(synth.total_cells(h, r, band) for h, r in regions)
+        # algorithmic HBM bytes of the dominant DP kernel per step, SURVEY.md §8(d): 4 B per pair (integer score out) + the read row
+        # half-words (2 B per read base, read once per read pair) + both strand column tables (16 B per haplotype base)
+        alg_bytes = sum(4 * h.n * r.n + 2 * int(r.off[-1]) + 16 * int(h.off[-1]) for h, r in regions)
         peak, peak_src = peaks()
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernel per step, from the committed ncu --set full captures
-        # (profiles/r01f_populate_fast_c3_ncu_raw.csv: C3's single launch — 0.51 GB task words + 0.51 GB best[] read for the
-        # atomicMin + tables / rows in, 0.57 GB best[] out; profiles/r01c_*: C2), default sizes only
-        traffic = {("C3", 1_000_000, 128): 1.401e9 + 0.569e9, ("C2", 100_000, 64): 84.1e6 + 3.0e6}.get((args.config, R, H))
+        mode_key = "flank" if flank_state else ("ref" if (args.shortcut or args.map) else "dp")
+        traffic = measured_traffic(args.config, R, H, band, mode_key)
+        kernel_name = ("k_populate_flank_acc<%d>" % band) if flank_state and band <= 32 else \
+                      ("k_populate_wide (32-bit lanes, band %d)" % band) if args.int_scores else "k_populate_fast<%d>" % band
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int16", "data": "synthetic",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "int32" if args.int_scores else "int16", "data": "synthetic",
             "config": {"workload": workload_name(args.config, R, (args.read_lens or "/".join(map(str, cfg["read_lens"]))).replace(",", "/"), H, args.hap_len or cfg["hap_len"], band),
-                       "alignments_per_step": H * R * world, "cells_per_step": cells * world,
+                       "regions_per_rank_and_step": len(regions),
+                       "alignments_per_step": haps.n * R_total if strong else sum(h.n * r.n for h, r in regions) * world,
+                       "cells_per_step": cells_rank_total,
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
-                       "parallelism": "reads sharded over %d rank(s), haplotypes replicated, NCCL gather to rank 0" % world,
-                       "mode": {"flank_state": flank_state, "naive_shortcut": bool(args.shortcut), "kmer_mapper": bool(args.map)}},
+                       "parallelism": ("one batch, reads split over %d rank(s), [H, R] matrix re-assembled on rank 0 (NCCL gather)" % world) if strong else
+                                      ("every rank its own region(s), haplotypes per region, NCCL gather of the per-rank matrices to rank 0 (%d rank(s))" % world),
+                       "penalties": args.error_model or "i.i.d. draws from the error-model tables' value range",
+                       "mode": {"flank_state": flank_state, "naive_shortcut": bool(args.shortcut), "kmer_mapper": bool(args.map), "use_int_scores": bool(args.int_scores)}},
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
+            "gather_ms_per_region": gather_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "k_populate_fast<%d>" % band, "kernel_ms": kernel_ms,
+                         "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the path is integer-issue bound, not HBM bound (SURVEY.md F3); see DESIGN.md for the issue-rate roofline",
-                         "kernel_gcups": cells / (kernel_ms / 1e3) / 1e9},
+                         "kernel_gcups": cells_rank / (kernel_ms / 1e3) / 1e9},
             # The binding roofline: the packed cell costs 6 ALU-pipe instructions per 2 cells and the ALU pipe
             # issues 64 thread-instructions/clk/SM (profiles/r01_ubench_int.txt). In the reference's cell count 2(L+B)B per
             # alignment (the column sweep itself touches 2LB cells) the peak is 148 SMs x clock x 64/3 x (L+B)/L.
-            "issue_roofline": issue_roofline(cells / (kernel_ms / 1e3) / 1e9, reads, band, clocks),
+            "issue_roofline": issue_roofline(cells_rank / (kernel_ms / 1e3) / 1e9, reads, band, clocks),
         }
+        ref_scores, n_ref = None, 0
         if not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = args.cpu_sample_reads or calibrated_sample(haps, reads, band, threads, 12.0)
-            g, dt, kind, name, _ = cpu_reference_run(haps, reads, band, n_sample, threads)
+            g, dt, kind, name, _, ref_scores = cpu_reference_run(haps, reads, band, n_sample, threads, want_scores=True)
+            n_ref = n_sample
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
                                     "sample": "first %d reads x %d haplotypes of the same batch, %.1f s; %s" % (n_sample, H, dt, name)}
+            # one thread, and the AVX2-forced build next to what -march=native selects (they differ for band 32 on AVX-512 hosts)
+            from oracle.oracle import available_ref_isas
+            variants = {}
+            n1 = max(64, n_sample // (4 * max(1, threads)))
+            variants["1_thread"] = {"value": cpu_reference_run(haps, reads, band, n1, 1)[0], "sample_reads": n1}
+            for isa in available_ref_isas():
+                v = cpu_reference_run(haps, reads, band, max(64, n_sample // 4), threads, isa=isa)
+                variants["%s_build_all_threads" % isa] = {"value": v[0], "kernel": v[3]}
+            line["cpu_baseline"]["variants"] = variants
+        line["parity"] = parity_gate(eng, haps, reads, band, flank_state, args.shortcut, args.map, args.int_scores, ref_scores, n_ref)
         print(json.dumps(line))
+        if line["parity"]["mismatches"]:
+            sys.stderr.write("PARITY GATE FAILED: %r\n" % (line["parity"],))
     if world > 1:
         dist.destroy_process_group()
 

@@ -129,6 +129,15 @@ int         phmm_create(phmm_engine** out, int device);
 void        phmm_destroy(phmm_engine* e);
 const char* phmm_last_error(const phmm_engine* e);   /* valid until the next call on e; e may be NULL */
 
+/* Stream ordering ("synchronous unless a stream handle is passed"). Calls run on the engine's own non-blocking CUDA
+ * stream and are complete when they return, which orders them after everything the HOST has waited for. Work the caller has
+ * merely ENQUEUED on another stream — e.g. an NCCL gather still reading the buffer the next call will overwrite — is ordered by
+ * handing the engine an event recorded after that work: phmm_wait_event(e, ev) makes the engine's stream(s) wait for `ev`
+ * (a cudaEvent_t) on the device before anything enqueued by later calls runs. phmm_engine_stream returns the engine's cudaStream_t
+ * for callers that want to record or wait on it themselves. */
+int         phmm_wait_event(phmm_engine* e, void* cuda_event);
+void*       phmm_engine_stream(phmm_engine* e);
+
 /* Number of kernels of this library launched by the last call / in total (bench.py's gpu_launches). */
 int64_t     phmm_launch_count(const phmm_engine* e, int total);
 

@@ -69,6 +69,18 @@ class PairHMMEngine:
             raise TooLargeBandSizeError(rc, msg)
         raise PhmmError(rc, msg)
 
+    # -- stream ordering -----------------------------------------------------------------------------------------
+    def wait_event(self, event):
+        """Make the engine's stream wait (on the device) for a CUDA event — a torch.cuda.Event or a raw cudaEvent_t — recorded
+        after work on another stream that still reads a buffer the next call will overwrite (phmm_wait_event)."""
+        handle = getattr(event, "cuda_event", event)
+        rc = self._lib.phmm_wait_event(self._h, C.c_void_p(int(handle)))
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+
+    def stream_handle(self):
+        return int(self._lib.phmm_engine_stream(self._h) or 0)
+
     # -- statistics of the last call -------------------------------------------------------------------------
     def launch_count(self, total=False):
         return int(self._lib.phmm_launch_count(self._h, int(total)))

@@ -348,6 +348,19 @@ void phmm_destroy(phmm_engine* e)
 
 const char* phmm_last_error(const phmm_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
+// Ordering against the caller's streams. Every call runs on the engine's own stream and is complete on return; what a caller
+// cannot express that way is "the buffer this call will WRITE is still being read by work I enqueued earlier on another stream"
+// (a gather of the previous result). phmm_wait_event makes the engine's stream(s) wait, on the device, for that work.
+int phmm_wait_event(phmm_engine* e, void* cuda_event)
+{
+    if (!e || !cuda_event) return PHMM_ERR_INVALID;
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
+    CU(cudaStreamWaitEvent(e->stream, (cudaEvent_t)cuda_event, 0));
+    for (phmm_engine* sub : e->sub) if (sub) CU(cudaStreamWaitEvent(sub->stream, (cudaEvent_t)cuda_event, 0));
+    return PHMM_OK;
+}
+void* phmm_engine_stream(phmm_engine* e) { return e ? (void*)e->stream : nullptr; }
+
 int64_t phmm_launch_count(const phmm_engine* e, int total) { return e ? (total ? e->launches_total : e->launches_last) : 0; }
 double phmm_last_dp_kernel_ms(const phmm_engine* e) { return e ? e->last_dp_ms : 0.0; }
 int64_t phmm_last_dp_cells(const phmm_engine* e) { return e ? e->last_dp_cells : 0; }

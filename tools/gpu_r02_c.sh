@@ -10,6 +10,7 @@ timeout 300 $B --config C2 --flank 60,60 --steps 3 --warmup 2 > $O/bench_c2_flan
 timeout 300 $B --config C2 --shortcut --map --steps 3 --warmup 2 > $O/bench_c2_refmode.json 2> $O/bench_c2_refmode.err
 timeout 300 $B --config C2 --shortcut --map --flank 60,60 --steps 3 --warmup 2 > $O/bench_c2_prod.json 2> $O/bench_c2_prod.err
 timeout 300 $B --config C3 --flank 60,60 --steps 3 --warmup 2 > $O/bench_c3_flank.json 2> $O/bench_c3_flank.err
+timeout 400 python bench.py --steps 3 --warmup 2 > $O/bench_default.json 2> $O/bench_default.err
 NCU="ncu --set full --clock-control none --import-source on"
 timeout 600 $NCU -k regex:k_populate_flank_acc -s 1 -c 1 -o $O/flankacc16 $B --config C2 --flank 60,60 --steps 1 --warmup 1 > $O/ncu_flankacc.log 2>&1
 timeout 600 $NCU -k regex:k_kmer_map -s 2 -c 1 -o $O/kmermap $B --config C2 --shortcut --map --steps 1 --warmup 1 > $O/ncu_kmer.log 2>&1
