@@ -25,6 +25,7 @@
 #ifndef PHMM_B200_H
 #define PHMM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -137,6 +138,11 @@ const char* phmm_last_error(const phmm_engine* e);   /* valid until the next cal
  * for callers that want to record or wait on it themselves. */
 int         phmm_wait_event(phmm_engine* e, void* cuda_event);
 void*       phmm_engine_stream(phmm_engine* e);
+
+/* Page-locked host memory (cudaHostAlloc) for callers that do not link the CUDA runtime themselves: host-space calls on pinned
+ * buffers copy at full rate and overlap with compute. NULL when no GPU / out of memory (callers fall back to malloc). */
+void*       phmm_host_alloc(size_t bytes);
+void        phmm_host_free(void* p);
 
 /* Number of kernels of this library launched by the last call / in total (bench.py's gpu_launches). */
 int64_t     phmm_launch_count(const phmm_engine* e, int total);

@@ -18,7 +18,9 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -78,6 +80,63 @@ public:
     }
 private:
     std::shared_ptr<phmm_engine> handle_;
+};
+
+// Page-locked storage for the batch blocks: a std::allocator over phmm_host_alloc (cudaHostAlloc) that falls back to malloc where
+// no GPU is usable. The blocks below are vectors of this allocator, so a populate() copies straight from / to pinned memory.
+template <typename T>
+struct PinnedAllocator
+{
+    using value_type = T;
+    PinnedAllocator() = default;
+    template <typename U> PinnedAllocator(const PinnedAllocator<U>&) noexcept {}
+    T* allocate(std::size_t n)
+    {
+        // one tag word in front of the block remembers where it came from
+        const std::size_t bytes = n * sizeof(T) + kHeader;
+        char* p = static_cast<char*>(phmm_host_alloc(bytes));
+        const bool pinned = p != nullptr;
+        if (!p) p = static_cast<char*>(std::malloc(bytes));
+        if (!p) throw std::bad_alloc {};
+        *reinterpret_cast<std::size_t*>(p) = pinned ? 1 : 0;
+        return reinterpret_cast<T*>(p + kHeader);
+    }
+    void deallocate(T* q, std::size_t) noexcept
+    {
+        char* p = reinterpret_cast<char*>(q) - kHeader;
+        if (*reinterpret_cast<std::size_t*>(p)) phmm_host_free(p); else std::free(p);
+    }
+    template <typename U> bool operator==(const PinnedAllocator<U>&) const noexcept { return true; }
+    template <typename U> bool operator!=(const PinnedAllocator<U>&) const noexcept { return false; }
+private:
+    static constexpr std::size_t kHeader = 64;   // keeps the payload 64-byte aligned
+};
+template <typename T> using pinned_vector = std::vector<T, PinnedAllocator<T>>;
+
+// The reference's sequencing-error models (core/models/error/error_model_factory.cpp:531-589), i.e. what
+// HaplotypeLikelihoodModel::reset runs per haplotype (haplotype_likelihood_model.cpp:60-78) — bit-identical, in the library.
+class ErrorModel
+{
+public:
+    explicit ErrorModel(const std::string& label = "PCR-free.HiSeq-2500")
+    {
+        phmm_error_model* m = nullptr;
+        const int rc = phmm_error_model_create(&m, label.c_str());
+        if (rc != PHMM_OK) throw Error {rc, phmm_error_model_last_error()};
+        handle_.reset(m, [] (phmm_error_model* p) { phmm_error_model_destroy(p); });
+    }
+    static ErrorModel from_custom_model_text(const std::string& text)   // the contents of a --sequence-error-model file
+    {
+        phmm_error_model* m = nullptr;
+        const int rc = phmm_error_model_create_custom(&m, text.c_str());
+        if (rc != PHMM_OK) throw Error {rc, phmm_error_model_last_error()};
+        ErrorModel result {std::shared_ptr<phmm_error_model>(m, [] (phmm_error_model* p) { phmm_error_model_destroy(p); })};
+        return result;
+    }
+    const phmm_error_model* get() const noexcept { return handle_.get(); }
+private:
+    explicit ErrorModel(std::shared_ptr<phmm_error_model> h) : handle_ {std::move(h)} {}
+    std::shared_ptr<phmm_error_model> handle_;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -195,18 +254,39 @@ private:
 // ---------------------------------------------------------------------------------------------------------------------
 struct HaplotypeBlock   // what HaplotypeLikelihoodModel::reset derives per haplotype (haplotype_likelihood_model.cpp:60-78)
 {
-    std::vector<std::int64_t> off {0};
-    std::string seq, snv_mask_fwd, snv_mask_rev;
-    std::vector<std::int8_t> snv_prior_fwd, snv_prior_rev, gap_open, gap_extend;
-    std::vector<std::int64_t> begin;
+    pinned_vector<std::int64_t> off {0};
+    pinned_vector<char> seq, snv_mask_fwd, snv_mask_rev;
+    pinned_vector<std::int8_t> snv_prior_fwd, snv_prior_rev, gap_open, gap_extend;
+    pinned_vector<std::int64_t> begin;
+    pinned_vector<std::uint8_t> is_substitution;   // only used by reset(): bases that are substitutions in Haplotype::cigar()
+
+    // Sequences only; reset(model) then fills the penalty arrays (the reference's likelihood_model_.reset(haplotype) per haplotype).
+    void add(const std::string& sequence, std::int64_t mapped_begin = 0, const std::vector<bool>* substitutions = nullptr)
+    {
+        seq.insert(seq.end(), sequence.begin(), sequence.end());
+        is_substitution.resize(seq.size(), 0);
+        if (substitutions) for (std::size_t i = 0; i < substitutions->size() && i < sequence.size(); ++i) is_substitution[seq.size() - sequence.size() + i] = (*substitutions)[i] ? 1 : 0;
+        begin.push_back(mapped_begin);
+        off.push_back(static_cast<std::int64_t>(seq.size()));
+    }
+    void reset(const ErrorModel& model, int n_threads = 0)
+    {
+        const std::size_t n = seq.size();
+        snv_mask_fwd.resize(n); snv_mask_rev.resize(n); snv_prior_fwd.resize(n); snv_prior_rev.resize(n); gap_open.resize(n); gap_extend.resize(n);
+        is_substitution.resize(n, 0);
+        const int rc = phmm_reset_haplotypes(model.get(), static_cast<std::int32_t>(size()), off.data(), seq.data(), is_substitution.data(),
+                                             snv_mask_fwd.data(), snv_prior_fwd.data(), snv_mask_rev.data(), snv_prior_rev.data(),
+                                             gap_open.data(), gap_extend.data(), n_threads);
+        if (rc != PHMM_OK) throw Error {rc, phmm_error_model_last_error()};
+    }
 
     void add(const std::string& sequence, const std::vector<char>& fwd_mask, const std::vector<std::int8_t>& fwd_priors,
              const std::vector<char>& rev_mask, const std::vector<std::int8_t>& rev_priors,
              const std::vector<std::int8_t>& open, const std::vector<std::int8_t>& extend, std::int64_t mapped_begin = 0)
     {
-        seq += sequence;
-        snv_mask_fwd.append(fwd_mask.begin(), fwd_mask.end());
-        snv_mask_rev.append(rev_mask.begin(), rev_mask.end());
+        seq.insert(seq.end(), sequence.begin(), sequence.end());
+        snv_mask_fwd.insert(snv_mask_fwd.end(), fwd_mask.begin(), fwd_mask.end());
+        snv_mask_rev.insert(snv_mask_rev.end(), rev_mask.begin(), rev_mask.end());
         snv_prior_fwd.insert(snv_prior_fwd.end(), fwd_priors.begin(), fwd_priors.end());
         snv_prior_rev.insert(snv_prior_rev.end(), rev_priors.begin(), rev_priors.end());
         gap_open.insert(gap_open.end(), open.begin(), open.end());
@@ -224,15 +304,15 @@ struct HaplotypeBlock   // what HaplotypeLikelihoodModel::reset derives per hapl
 
 struct ReadBlock   // AlignedRead fields on the path (basics/aligned_read.hpp:36-39,120-146)
 {
-    std::vector<std::int64_t> off {0};
-    std::string bases;
-    std::vector<std::uint8_t> quals, mapq, reverse;
-    std::vector<std::int64_t> begin;
+    pinned_vector<std::int64_t> off {0};
+    pinned_vector<char> bases;
+    pinned_vector<std::uint8_t> quals, mapq, reverse;
+    pinned_vector<std::int64_t> begin;
 
     void add(const std::string& sequence, const std::vector<std::uint8_t>& base_qualities, std::uint8_t mapping_quality,
              bool is_marked_reverse_mapped, std::int64_t mapped_begin)
     {
-        bases += sequence;
+        bases.insert(bases.end(), sequence.begin(), sequence.end());
         quals.insert(quals.end(), base_qualities.begin(), base_qualities.end());
         mapq.push_back(mapping_quality);
         reverse.push_back(is_marked_reverse_mapped ? 1 : 0);
@@ -242,7 +322,7 @@ struct ReadBlock   // AlignedRead fields on the path (basics/aligned_read.hpp:36
     void append(const ReadBlock& other)
     {
         const auto base = static_cast<std::int64_t>(bases.size());
-        bases += other.bases;
+        bases.insert(bases.end(), other.bases.begin(), other.bases.end());
         quals.insert(quals.end(), other.quals.begin(), other.quals.end());
         mapq.insert(mapq.end(), other.mapq.begin(), other.mapq.end());
         reverse.insert(reverse.end(), other.reverse.begin(), other.reverse.end());
@@ -259,7 +339,7 @@ struct ReadBlock   // AlignedRead fields on the path (basics/aligned_read.hpp:36
 struct TemplateBlock   // AlignedTemplate containers: template t owns the reads [off[t], off[t+1]) (basics/aligned_template.hpp)
 {
     ReadBlock reads;
-    std::vector<std::int64_t> off {0};
+    pinned_vector<std::int64_t> off {0};
     void add(const ReadBlock& template_reads) { reads.append(template_reads); off.push_back(static_cast<std::int64_t>(reads.size())); }
     std::size_t size() const noexcept { return off.size() - 1; }
 };
@@ -322,7 +402,7 @@ public:
     void populate(const TemplateMap& templates, const HaplotypeBlock& haplotypes, const FlankState* flank_state = nullptr)
     {
         ReadBlock all;
-        std::vector<std::int64_t> template_off {0};
+        pinned_vector<std::int64_t> template_off {0};
         begin_samples(templates.size());
         for (const auto& p : templates) {
             add_sample(p.first, p.second.size());
@@ -394,7 +474,7 @@ public:
 private:
     Engine engine_;
     phmm_config config_;
-    std::vector<double> likelihoods_;
+    pinned_vector<double> likelihoods_;
     std::vector<SampleName> samples_;
     std::vector<std::size_t> sample_off_ {0};
     std::size_t num_haplotypes_ = 0;
@@ -419,7 +499,7 @@ private:
         if (h >= num_haplotypes_) throw std::out_of_range {"HaplotypeLikelihoodArray: haplotype index"};
         return LikelihoodSpan {likelihoods_.data() + h * total_width() + sample_off_[s], width(s)};
     }
-    void run(const ReadBlock& reads, const std::vector<std::int64_t>* template_off, const HaplotypeBlock& haplotypes,
+    void run(const ReadBlock& reads, const pinned_vector<std::int64_t>* template_off, const HaplotypeBlock& haplotypes,
              const FlankState* flank_state, const phmm_positions* positions)
     {
         const auto hv = haplotypes.view();
@@ -427,7 +507,7 @@ private:
         num_haplotypes_ = haplotypes.size();
         likelihoods_.assign(num_haplotypes_ * total_width(), 0.0);
         if (num_haplotypes_ == 0 || reads.size() == 0) return;
-        std::vector<std::int32_t> status(num_haplotypes_ * reads.size(), 0);
+        pinned_vector<std::int32_t> status(num_haplotypes_ * reads.size(), 0);
         phmm_flank_state fs {flank_state ? 1 : 0, flank_state ? flank_state->lhs_flank : 0, flank_state ? flank_state->rhs_flank : 0};
         const int rc = template_off
             ? phmm_populate_templates(engine_.get(), &config_, &hv, &rv, template_off->data(), static_cast<std::int32_t>(template_off->size() - 1),
@@ -435,12 +515,103 @@ private:
             : phmm_populate(engine_.get(), &config_, &hv, &rv, positions, &fs, likelihoods_.data(), status.data(), PHMM_SPACE_HOST);
         if (rc == PHMM_ERR_SHORT_HAPLOTYPE) {
             for (std::size_t i = 0; i < status.size(); ++i) {
-                if ((status[i] & 0xFFFF) == PHMM_STATUS_SHORT_HAP) throw ShortHaplotypeError {i / reads.size(), static_cast<unsigned>(status[i] >> 16)};
+                if ((status[i] & 0xFFFF) == PHMM_STATUS_SHORT_HAP) throw ShortHaplotypeError {i / reads.size(), static_cast<unsigned>(static_cast<std::uint32_t>(status[i]) >> 16)};
             }
         }
         engine_.check(rc);
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hmm::PairHMM<Parameters, BandSize, Score> (src/core/models/pairhmm/pair_hmm.hpp:892-1032) over the GPU kernel
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's class bundles a kernel object with a `const Parameters*` and forwards to the free templates hmm::evaluate /
+// hmm::align. Those templates are the reference's own code, so this type exists only where its header has been included before
+// this one (Octopus's build; tests/cpp/test_dropin.cpp): it differs from octopus::hmm::PairHMM in the kernel member alone.
+// The kernel is GpuPairHMM with a RUNTIME band, like simd::PairHMMWrapper (simd_pair_hmm_wrapper.hpp:218-241: smallest of
+// 8, 16, ..., 256 that holds the request; TooLargeBandSizeError beyond).
+class GpuPairHMMDyn
+{
+public:
+    using ScoreType = int;
+    constexpr static char gap_label = '-';
+    GpuPairHMMDyn() = default;
+    explicit GpuPairHMMDyn(unsigned min_band_size, Engine engine = Engine {}) : engine_ {std::move(engine)} { reset(min_band_size); }
+    void reset(unsigned min_band_size)
+    {
+        for (int b = 8; b <= 256; b <<= 1) if (min_band_size <= static_cast<unsigned>(b)) { band_ = b; return; }
+        throw TooLargeBandSizeError {min_band_size};
+    }
+    constexpr static const char* name() noexcept { return "B200"; }
+    int band_size() const noexcept { return band_; }
+    template <typename GapExtend>
+    int align(const char* truth, const char* target, const std::int8_t* qualities, int truth_len, int target_len,
+              const std::int8_t* gap_open, GapExtend gap_extend, short nuc_prior) const noexcept
+    { int fp; return run(truth, target, qualities, truth_len, target_len, nullptr, nullptr, gap_open, gap_extend, nuc_prior, fp, nullptr, nullptr); }
+    template <typename GapExtend>
+    int align(const char* truth, const char* target, const std::int8_t* qualities, int truth_len, int target_len,
+              const char* snv_mask, const std::int8_t* snv_prior, const std::int8_t* gap_open, GapExtend gap_extend, short nuc_prior) const noexcept
+    { int fp; return run(truth, target, qualities, truth_len, target_len, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior, fp, nullptr, nullptr); }
+    template <typename GapExtend>
+    int align(const char* truth, const char* target, const std::int8_t* qualities, int truth_len, int target_len,
+              const std::int8_t* gap_open, GapExtend gap_extend, short nuc_prior, int& first_pos, char* align1, char* align2) const noexcept
+    { return run(truth, target, qualities, truth_len, target_len, nullptr, nullptr, gap_open, gap_extend, nuc_prior, first_pos, align1, align2); }
+    template <typename GapExtend>
+    int align(const char* truth, const char* target, const std::int8_t* qualities, int truth_len, int target_len,
+              const char* snv_mask, const std::int8_t* snv_prior, const std::int8_t* gap_open, GapExtend gap_extend, short nuc_prior,
+              int& first_pos, char* align1, char* align2) const noexcept
+    { return run(truth, target, qualities, truth_len, target_len, snv_mask, snv_prior, gap_open, gap_extend, nuc_prior, first_pos, align1, align2); }
+    template <typename... Args>
+    int calculate_flank_score(Args&&... args) const noexcept { return GpuPairHMM<8> {engine_}.calculate_flank_score(std::forward<Args>(args)...); }   // band-independent replay
+private:
+    Engine engine_;
+    int band_ = 8;
+    static const std::int8_t* ext_ptr(const std::int8_t* p) noexcept { return p; }
+    template <typename T> static const std::int8_t* ext_ptr(T) noexcept { return nullptr; }
+    static int ext_scalar(const std::int8_t*) noexcept { return 0; }
+    template <typename T> static int ext_scalar(T v) noexcept { return static_cast<int>(v); }
+    template <typename GapExtend>
+    int run(const char* truth, const char* target, const std::int8_t* quals, int truth_len, int target_len,
+            const char* snv_mask, const std::int8_t* snv_prior, const std::int8_t* gap_open, GapExtend gap_extend, short nuc_prior,
+            int& first_pos, char* align1, char* align2) const noexcept
+    {
+        int score = 0;
+        std::vector<char> a1, a2;
+        if (!align1) { a1.assign(2 * (target_len + band_) + 1, 0); a2 = a1; align1 = a1.data(); align2 = a2.data(); }
+        const int rc = phmm_align_traceback(engine_.get(), band_, truth, target, quals, truth_len, target_len, snv_mask, snv_prior,
+                                            gap_open, ext_ptr(gap_extend), ext_scalar(gap_extend), nuc_prior, &score, &first_pos, align1, align2);
+        if (rc != PHMM_OK) first_pos = -1;
+        return score;
+    }
+};
+
+#ifdef pair_hmm_hpp   // the include guard of the reference's src/core/models/pairhmm/pair_hmm.hpp
+template <typename Parameters, int BandSize = 0>
+class PairHMM
+{
+public:
+    using ParameterType = Parameters;
+    PairHMM() = default;
+    explicit PairHMM(unsigned min_band_size) { reset(min_band_size); }
+    PairHMM(const Parameters& params, unsigned min_band_size = 8) { reset(min_band_size); set(params); }
+    int band_size() const noexcept { return hmm_.band_size(); }
+    void set(const Parameters& params) noexcept { params_ = std::addressof(params); }
+    template <typename Sequence1, typename Sequence2>
+    double evaluate(const Sequence1& target, const Sequence2& truth, const std::vector<std::uint8_t>& target_base_qualities, const std::size_t target_offset) const noexcept
+    { return octopus::hmm::evaluate(truth, target, target_base_qualities, target_offset, hmm_, *params_); }
+    template <typename Sequence1, typename Sequence2>
+    void align(const Sequence1& target, const Sequence2& truth, const std::vector<std::uint8_t>& target_base_qualities, const std::size_t target_offset,
+               octopus::hmm::Alignment& result) const
+    { octopus::hmm::align(truth, target, target_base_qualities, target_offset, hmm_, *params_, result); }
+    template <typename Sequence1, typename Sequence2>
+    octopus::hmm::Alignment align(const Sequence1& target, const Sequence2& truth, const std::vector<std::uint8_t>& target_base_qualities, const std::size_t target_offset) const
+    { octopus::hmm::Alignment result {}; this->align(target, truth, target_base_qualities, target_offset, result); return result; }
+private:
+    GpuPairHMMDyn hmm_ {BandSize > 0 ? static_cast<unsigned>(BandSize) : 8u};
+    const Parameters* params_ = nullptr;
+    void reset(unsigned min_band_size) { if (BandSize == 0) hmm_.reset(min_band_size); }
+};
+#endif
 
 } // namespace octopus_b200
 

@@ -361,6 +361,17 @@ int phmm_wait_event(phmm_engine* e, void* cuda_event)
 }
 void* phmm_engine_stream(phmm_engine* e) { return e ? (void*)e->stream : nullptr; }
 
+// Page-locked host memory for callers without the CUDA headers (the C++ adapter's blocks): a PHMM_SPACE_HOST call copies from /
+// to pinned buffers at full PCIe / C2C rate and overlaps with compute; pageable memory is staged by the driver.
+void* phmm_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void phmm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int64_t phmm_launch_count(const phmm_engine* e, int total) { return e ? (total ? e->launches_total : e->launches_last) : 0; }
 double phmm_last_dp_kernel_ms(const phmm_engine* e) { return e ? e->last_dp_ms : 0.0; }
 int64_t phmm_last_dp_cells(const phmm_engine* e) { return e ? e->last_dp_cells : 0; }

@@ -870,7 +870,7 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
     for (int c = 0; c < npos + 2; ++c) {
         int pos;
         const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
-        if (k < 0) { p.status[(size_t)h * R + r] = 2 | (pos << 16); atomicOr(p.flags, 2); continue; }
+        if (k < 0) { p.status[(size_t)h * R + r] = 2 | (min(pos, 0x7FFF) << 16); atomicOr(p.flags, 2); continue; }
         if (k == 0) continue;
         int v;
         const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, p.use_flanks != 0, p.lhs_flank, p.rhs_flank, &v);
@@ -1059,7 +1059,7 @@ __global__ void k_align_reads(const AlignParams p)
         for (int c = 0; c < npos + 2 && status == 0; ++c) {
             int pos;
             const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
-            if (k < 0) { status = 2 | (pos << 16); break; }
+            if (k < 0) { status = 2 | (min(pos, 0x7FFF) << 16); break; }
             if (k == 0) continue;
             int v; long long off; bool exact = false;
             bool eq = true;                                                   // try_naive_align (:321-340)

@@ -1,5 +1,7 @@
 // Plain C++14 client of the C ABI and the C++ adapter (no torch, no Python): built by tests/test_gpu_cpp.py with g++ and
 // run on the GPU box. Reads one KAT and one tiny populate problem from stdin-free hardcoded data, prints results.
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -71,6 +73,51 @@ int main()
             tarr.prime("S1");
             for (std::size_t h = 0; h < 2; ++h) ok = ok && tarr.num_likelihoods() == 2 && tarr[h][0] == arr[h][0] + arr[h][1] && tarr[h][1] == arr[h][0];
             std::printf("SAMPLES %s %s\n", ok ? "ok" : "MISMATCH", threw ? "throws" : "nothrow");
+        }
+        {   // reset(): penalty arrays from the library's error models, then a populate on them; pinned (adapter blocks) vs pageable host buffers
+            ErrorModel model {"PCR-free.HiSeq-2500"};
+            HaplotypeBlock hb;
+            std::string base;
+            unsigned long long x = 88172645463325252ull;
+            auto rnd = [&x] { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+            for (int i = 0; i < 300; ++i) base += "ACGT"[rnd() % 4];
+            base.replace(100, 16, "AAAAAAAAAAAAAAAA"); base.replace(180, 16, "CACACACACACACACA");
+            const int H = 64, R = 40000, L = 100;
+            for (int h = 0; h < H; ++h) { std::string s2 = base; s2[(rnd() % 280) + 10] = "ACGT"[rnd() % 4]; hb.add(s2, 0); }
+            hb.reset(model);
+            ReadBlock rb;
+            for (int r = 0; r < R; ++r) {
+                const int p = 16 + (int)(rnd() % (300 - L - 32));
+                std::string b = base.substr(p, L);
+                if (rnd() % 3 == 0) b[rnd() % L] = "ACGT"[rnd() % 4];
+                rb.add(b, std::vector<std::uint8_t>(L, (std::uint8_t)(20 + rnd() % 20)), 60, (rnd() & 1) != 0, p);
+            }
+            auto c2 = HaplotypeLikelihoodArray::default_config();
+            c2.max_indel_error = 16; c2.map_positions = 0;
+            HaplotypeLikelihoodArray big {c2};
+            big.populate(rb, hb);                                   // warm-up (allocations)
+            auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            double t0 = now();
+            for (int it = 0; it < 5; ++it) big.populate(rb, hb);
+            const double pinned_ms = (now() - t0) / 5;
+            // the same call on ordinary (pageable) std::vector storage
+            std::vector<std::int64_t> hoff(hb.off.begin(), hb.off.end()), roff(rb.off.begin(), rb.off.end()), hbeg(hb.begin.begin(), hb.begin.end()), rbeg(rb.begin.begin(), rb.begin.end());
+            std::vector<char> hseq(hb.seq.begin(), hb.seq.end()), mf(hb.snv_mask_fwd.begin(), hb.snv_mask_fwd.end()), mr(hb.snv_mask_rev.begin(), hb.snv_mask_rev.end()), bases(rb.bases.begin(), rb.bases.end());
+            std::vector<std::int8_t> pf(hb.snv_prior_fwd.begin(), hb.snv_prior_fwd.end()), pr(hb.snv_prior_rev.begin(), hb.snv_prior_rev.end()), go(hb.gap_open.begin(), hb.gap_open.end()), ge(hb.gap_extend.begin(), hb.gap_extend.end());
+            std::vector<std::uint8_t> quals(rb.quals.begin(), rb.quals.end()), mapq(rb.mapq.begin(), rb.mapq.end()), rev(rb.reverse.begin(), rb.reverse.end());
+            std::vector<double> out((std::size_t)H * R);
+            const phmm_haplotypes hv {H, hoff.data(), hseq.data(), mf.data(), pf.data(), mr.data(), pr.data(), go.data(), ge.data(), hbeg.data()};
+            const phmm_reads rv {R, roff.data(), bases.data(), quals.data(), mapq.data(), rev.data(), rbeg.data()};
+            Engine eng;
+            phmm_populate(eng.get(), &c2, &hv, &rv, nullptr, nullptr, out.data(), nullptr, PHMM_SPACE_HOST);
+            t0 = now();
+            for (int it = 0; it < 5; ++it) phmm_populate(eng.get(), &c2, &hv, &rv, nullptr, nullptr, out.data(), nullptr, PHMM_SPACE_HOST);
+            const double pageable_ms = (now() - t0) / 5;
+            bool same = true;
+            for (std::size_t h = 0; h < (std::size_t)H && same; ++h) for (std::size_t r = 0; r < (std::size_t)R; r += 997) same = same && big[h][r] == out[h * R + r];
+            int go_min = 127, go_max = 0;
+            for (const auto v : hb.gap_open) { go_min = std::min<int>(go_min, v); go_max = std::max<int>(go_max, v); }
+            std::printf("E2E pinned_ms=%.3f pageable_ms=%.3f same=%d gap_open_range=%d..%d pairs=%d\n", pinned_ms, pageable_ms, same ? 1 : 0, go_min, go_max, H * R);
         }
         // ShortHaplotypeError must surface as the reference's exception type
         ReadBlock longread;

@@ -75,12 +75,48 @@ int run(Rng& rng, int n_cases, int& n_traceback)
 
 } // namespace
 
+// octopus_b200::PairHMM<Parameters> against octopus::hmm::PairHMM<Parameters> (pair_hmm.hpp:892-1032): same constructor, set(), band_size(),
+// evaluate() and align() — the class HaplotypeLikelihoodModel holds (haplotype_likelihood_model.hpp:106), runtime band 8..256.
+int run_class(Rng& rng, int n_cases)
+{
+    using namespace octopus::hmm;
+    int bad = 0;
+    for (int it = 0; it < n_cases; ++it) {
+        const unsigned request = static_cast<unsigned>(rng.range(1, 70));
+        const int L = rng.range(8, 60);
+        octopus::hmm::PairHMM<MutationModel> cpu {request};
+        octopus_b200::PairHMM<MutationModel> gpu {request};
+        if (cpu.band_size() != gpu.band_size()) { ++bad; continue; }
+        const int band = cpu.band_size(), hap_len = L + 2 * band + rng.range(2, 40);
+        std::string truth(hap_len, 'A');
+        for (auto& b : truth) b = rng.base();
+        const int start = rng.range(band, hap_len - L - band);
+        std::string target = truth.substr(start, L);
+        for (int i = 0; i < rng.range(0, 3); ++i) target[rng.below(L)] = rng.base();
+        std::vector<std::uint8_t> quals(L);
+        for (auto& q : quals) q = static_cast<std::uint8_t>(rng.range(2, 41));
+        PenaltyVector go(hap_len), ge(hap_len), pr(hap_len);
+        NucleotideVector mask(hap_len);
+        for (int i = 0; i < hap_len; ++i) { go[i] = rng.range(3, 45); ge[i] = rng.range(1, 10); pr[i] = rng.range(1, 125); mask[i] = "ACGTN"[rng.below(5)]; }
+        const MutationModel params {go, ge, mask, pr, {}, static_cast<std::size_t>(rng.below(hap_len / 3)), static_cast<std::size_t>(rng.below(hap_len / 3)), 2};
+        cpu.set(params); gpu.set(params);
+        const std::size_t offset = static_cast<std::size_t>(start);
+        bool ok = cpu.evaluate(target, truth, quals, offset) == gpu.evaluate(target, truth, quals, offset);
+        const Alignment ac = cpu.align(target, truth, quals, offset), ag = gpu.align(target, truth, quals, offset);
+        ok = ok && ag.target_offset == ac.target_offset && ag.likelihood == ac.likelihood && cigar_text(ag.cigar) == cigar_text(ac.cigar);
+        if (!ok && ++bad <= 5) std::printf("CLASS MISMATCH case=%d band=%d L=%d\n", it, band, L);
+    }
+    bool threw = false;
+    try { octopus_b200::PairHMM<MutationModel> too_wide {300u}; } catch (const octopus_b200::TooLargeBandSizeError&) { threw = true; }
+    return bad + (threw ? 0 : 1);
+}
+
 int main()
 {
     try {
         Rng rng {20240923};
         int n_traceback = 0;
-        const int bad = run<8>(rng, 250, n_traceback) + run<16>(rng, 250, n_traceback) + run<32>(rng, 120, n_traceback);
+        const int bad = run<8>(rng, 250, n_traceback) + run<16>(rng, 250, n_traceback) + run<32>(rng, 120, n_traceback) + run_class(rng, 60);
         std::printf("DROPIN %s mismatches=%d traceback_cases=%d\n", bad == 0 ? "ok" : "FAILED", bad, n_traceback);
         return bad == 0 ? 0 : 1;
     } catch (const std::exception& e) {

@@ -41,6 +41,10 @@ def test_cpp_client_matches_oracle(coracle):
             got = float(lines["ROW%d" % hi][2 + ri])
             assert st == 0 and abs(got - want) <= 1e-4 * max(abs(want), 1e-300)
     assert lines["SHORT"][1].startswith("hap=0")
+    e2e = dict(kv.split("=") for kv in lines["E2E"][1:])
+    assert e2e["same"] == "1" and float(e2e["pinned_ms"]) > 0 and float(e2e["pageable_ms"]) > 0
+    assert e2e["gap_open_range"] != "45..45"          # reset() produced repeat-structured penalties (homopolymer / dinucleotide runs)
+    print("C++ adapter e2e (64 x 40000 pairs, L=100): pinned %.2f ms, pageable %.2f ms per populate" % (float(e2e["pinned_ms"]), float(e2e["pageable_ms"])))
     assert lines["SAMPLES"][1:] == ["ok", "throws"]          # multi-sample / template container semantics of the C++ adapter
 
 
