@@ -263,6 +263,13 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
 // Traits select the value type: Lanes16 = two alignments per lane group packed s16x2 (as dp_pair), Lanes32 = one alignment
 // in 32-bit lanes (int scores, long or high-quality-sum reads, reads holding 'N': the PRMT lookup has the fifth cap).
 PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// a + b computed as a * one + b with `one` (== 1) opaque to the compiler: an IMAD on the FMA pipe instead of an IADD that ptxas
+// would fuse into a VIADDMNMX on the (binding) ALU pipe
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b)); return d; }
+#else
+inline uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+#endif
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ uint32_t umin3_32(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }            // VIMNMX3.U32
 __device__ __forceinline__ uint32_t uaddmin32(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u32(a, b, c); }        // VIADDMNMX.U32: min(a+b, c)
@@ -646,7 +653,7 @@ PHMM_HD bool flank_mask_cannot_zero(const int L, const int band, const int xl, c
 
 template <int BAND>
 PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ tab, const int nuc_prior,
-                          const int xl, const int xr, int* score_out, int* flank_out)
+                          const int xl, const int xr, int* score_out, int* flank_out, const uint32_t one = 1u)
 {
     constexpr int K = 2 * BAND;
     static_assert(K <= 64, "register band limited to 64 diagonals");
@@ -666,9 +673,9 @@ PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const 
         const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                              \
         const uint32_t S = umin3_32(m, i_run, d);                                                       \
         CAPTURE                                                                                         \
-        M[(k) < K ? (k) : 0] = (S & ~kFAccLabelMask) + subw;                                            \
-        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = umin3_32(d + geS, m + goS, i_run + goS) | kFAccLabD; \
-        i_run = uaddmin32(i_run, gepS, m + gopS) | kFAccLabI;                                           \
+        M[(k) < K ? (k) : 0] = fma_add(S & ~kFAccLabelMask, subw, one);                                 \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = umin3_32(fma_add(d, geS, one), fma_add(m, goS, one), fma_add(i_run, goS, one)) | kFAccLabD; \
+        i_run = uaddmin32(i_run, gepS, fma_add(m, gopS, one)) | kFAccLabI;                              \
     }
 #define PHMM_ACASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_ACELL(k, )
 #define PHMM_ACASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;

@@ -725,7 +725,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
 
     PopParams p {};
     p.hp = s.hp; p.rd = s.rd;
-    p.band = band; p.nuc_prior = cfg->nuc_prior;
+    p.band = band; p.nuc_prior = cfg->nuc_prior; p.one = 1;
     p.shortcut = cfg->disable_naive_shortcut ? 0 : 1;
     p.use_flanks = (flank && flank->has_flank && cfg->use_flank_state) ? 1 : 0;
     p.lhs_flank = p.use_flanks ? (int)flank->lhs_flank : 0;
@@ -760,9 +760,11 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         max_dp_per_pair = kMaxMapped + 1;
     }
     const bool use_mapper = !(positions && positions->off && positions->pos) && cfg->map_positions;
+    int mapper_maxt = 0;
     if (use_mapper) {
         long long max_hap = 0;
         for (int h = 0; h < H; ++h) max_hap = std::max(max_hap, s.hap_off_host[h + 1] - s.hap_off_host[h]);
+        mapper_maxt = max_hap - 5 <= 512 ? 512 : 2048;       // vote-array capacity per thread (longer haplotypes: tiles of 2048 diagonals)
         if (max_hap > 65535) { e->err = "haplotype longer than 65535 bp: the device k-mer mapper indexes k-mer positions with 16 bits (pass explicit positions)"; return PHMM_ERR_INVALID; }
         if (s.hap_bases > 65535LL * 65535LL) { e->err = "haplotype block too large"; return PHMM_ERR_INVALID; }
         CU(e->rhash.ensure((size_t)s.read_bases * sizeof(uint16_t)));
@@ -938,10 +940,17 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     // k-mer mapper variant: vote-array capacity by the longest haplotype, byte counters when no read can cast > 255 votes
     const bool mapper_bytes = Lmax_all - kKmer + 1 <= 255;
     auto launch_mapper = [&](const int* list, int n_list, int base, int kind) {
-        const long long warps = (long long)n_list * H;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((warps + kMapWarps - 1) / kMapWarps, (long long)e->sm_count * 8));
-        if (mapper_bytes) k_kmer_map<uint8_t><<<grid, kMapWarps * 32, 0, e->stream>>>(list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
-        else k_kmer_map<uint16_t><<<grid, kMapWarps * 32, 0, e->stream>>>(list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>());
+        const long long threads = (long long)n_list * H;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 127) / 128, (long long)e->sm_count * 64));
+#define PHMM_MAP_ARGS list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>()
+        if (mapper_maxt == 512) {
+            if (mapper_bytes) k_kmer_map<512, uint8_t><<<grid, 128, 0, e->stream>>>(PHMM_MAP_ARGS);
+            else k_kmer_map<512, uint16_t><<<grid, 128, 0, e->stream>>>(PHMM_MAP_ARGS);
+        } else {
+            if (mapper_bytes) k_kmer_map<2048, uint8_t><<<grid, 128, 0, e->stream>>>(PHMM_MAP_ARGS);
+            else k_kmer_map<2048, uint16_t><<<grid, 128, 0, e->stream>>>(PHMM_MAP_ARGS);
+        }
+#undef PHMM_MAP_ARGS
     };
     // the 32-bit flank kernel over the current list (near-flank candidates, and every candidate of pair-list reads holding 'N')
     auto launch_flank = [&](int n_entries, int row_stride) -> int {

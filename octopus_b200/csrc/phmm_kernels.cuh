@@ -364,6 +364,7 @@ struct PopParams {
     int* any_acc_tasks;
     int units_per_pair;         // fast kernel: a read pair's task lists are cut into this many work units of kRoundsPerUnit rounds
     int band, nuc_prior;
+    int one;                    // the constant 1, opaque to the compiler (fma_add)
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
     int use_flanks;             // flank_state present && config.use_flank_state
     int lhs_flank, rhs_flank;
@@ -474,11 +475,12 @@ __global__ void k_read_kmers(const long long n_bases, const int n_reads, const l
     for (int y = lane; y + kKmer <= L; y += 32) rhash[b + y] = (uint16_t)kmer_hash(bases + b + y);
 }
 
-// populate_kmer_hash_table<6> (:85-98) per haplotype: bins[h][hash] = first item | item count << 16 (both < 2^16: the mapper
+// populate_kmer_hash_table<6> (:85-98) per haplotype, stored HASH-MAJOR: binsT[hash * H + h] = position | 1 << 16 for a bin with one
+// k-mer, first item | item count << 16 for a fuller one (0 = empty; positions, item indices and counts are < 2^16: the mapper
 // takes haplotypes of up to 65 535 bases), items[hap base offset + ...] = k-mer positions, ascending within a bin.
 // One block per haplotype.
 __global__ void k_build_kmer_table(const int H, const long long* __restrict__ off, const char* __restrict__ seq,
-                                   uint32_t* __restrict__ bins, uint16_t* __restrict__ items)
+                                   uint32_t* __restrict__ binsT, uint16_t* __restrict__ items)
 {
     __shared__ int hist[kKmerBins + 1];
     __shared__ int cursor[kKmerBins];
@@ -503,11 +505,7 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
         }
     }
     __syncthreads();
-    uint32_t* bs = bins + (size_t)h * (kKmerBins + 1);
-    for (int i = threadIdx.x; i < kKmerBins; i += blockDim.x) {
-        bs[i] = (uint32_t)hist[i] | ((uint32_t)(hist[i + 1] - hist[i]) << 16);
-        cursor[i] = hist[i];
-    }
+    for (int i = threadIdx.x; i < kKmerBins; i += blockDim.x) cursor[i] = hist[i];
     __syncthreads();
     // fill in ascending position order within a bin: the vote loop relies on nothing but the set, the order keeps runs reproducible
     for (int i = threadIdx.x; i < nt; i += blockDim.x) {
@@ -515,97 +513,91 @@ __global__ void k_build_kmer_table(const int H, const long long* __restrict__ of
         const int slot = atomicAdd(&cursor[hh], 1);
         items[o + slot] = (uint16_t)i;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kKmerBins; i += blockDim.x) {
+        const int first = hist[i], n = hist[i + 1] - hist[i];
+        uint32_t v = 0u;
+        if (n == 1) v = (uint32_t)items[o + first] | (1u << 16);
+        else if (n > 1) v = (uint32_t)first | ((uint32_t)n << 16);
+        binsT[(size_t)i * H + h] = v;
+    }
 }
 
 // map_query_to_target (:120-159) for every (read of the work list, haplotype): the first <= 10 mapping begins (ascending)
 // whose vote count equals the maximum. votes[d] = number of query k-mers qi whose k-mer also starts at target position qi + d.
-// One WARP per pair: the vote counters of a tile of kMapTile diagonals live in shared memory, packed 4 (or 2) per word and
-// updated with word atomics (no counter can overflow into its neighbour: a diagonal collects at most one vote per query k-mer;
-// CountT = uint8_t for reads of <= 260 bases, else uint16_t). Every lane walks a CONTIGUOUS block of query k-mers, so the hits a
-// well-aligned read scores on one diagonal collapse into one atomic per lane instead of one per k-mer. Haplotypes with more than
-// kMapTile k-mers are handled tile by tile (ascending diagonals, so the "first ten at the maximum" order is kept).
-// Round 1's version kept a per-THREAD vote array in local memory (<= 2048 k-mers, else an error) and was L1/L2-latency bound.
-constexpr int kMapTile = 2048;
-constexpr int kMapWarps = 8;
-
-template <typename CountT>
-__global__ void __launch_bounds__(kMapWarps * 32)
-k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int kind,
-           const DevHaps hp, const DevReads rd,
-           const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ bins, const uint16_t* __restrict__ items,
-           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
+// One THREAD per pair, consecutive lanes = consecutive haplotypes of one read: the read's k-mer hash is a broadcast load, the
+// bin lookup is ONE coalesced line because the bin table is stored hash-major (binsT[hash][haplotype], k_build_kmer_table) and a bin
+// with a single k-mer (nearly all of them: ~300 k-mers over 4096 bins) carries the position inline — no second dependent load;
+// the per-thread vote array lives in local memory (L1) and is handled a 32-bit word at a time where possible (clear, final scan).
+// CountT = uint8_t when no diagonal can collect more than 255 votes (one vote per query k-mer at most: reads of <= 260 bases),
+// else uint16_t. Haplotypes with more than MAXT k-mers are handled in tiles of MAXT diagonals, ascending, so the "first ten at the
+// maximum" order is kept (round 1 refused them).
+// Measured alternatives (profiles/README.md): round 1's haplotype-major bins (two dependent, uncoalesced L2 loads per k-mer) 6.4 ms per C2
+// step; a warp per pair with shared-memory vote tiles 13 ms (the per-pair latency chain is paid by every warp instead of being
+// spread over 32 pairs).
+template <int MAXT, typename CountT>
+__global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int kind,
+                           const DevHaps hp, const DevReads rd,
+                           const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ binsT, const uint16_t* __restrict__ items,
+                           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
 {
-    constexpr int PER = 4 / (int)sizeof(CountT), BITS = 8 * (int)sizeof(CountT);
-    constexpr uint32_t FIELD = (1u << BITS) - 1u;
-    __shared__ uint32_t s_votes[kMapWarps][kMapTile / PER];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* votes = s_votes[warp];
+    constexpr int PER = 4 / (int)sizeof(CountT);
     const int H = hp.n;
-    // the tile's work list (pair list entries may be -1), clipped against the scheduler's totals
+    // the tile's work list: 2 entries per read pair, or the wide / generic reads; clipped against the scheduler's totals
     const int n_list = max(0, min(n_list_max, list_total(tot, kind) - base));
-    const long long total = (long long)n_list * H, step = (long long)gridDim.x * kMapWarps;
-    for (long long i = (long long)blockIdx.x * kMapWarps + warp; i < total; i += step) {
+    const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
         int li, h;
         split_index(i, H, &li, &h);
         const int r = list[li];
-        int n_out = 0;
+        uint8_t n_out = 0;
         if (r >= 0) {
             const long long ro = rd.off[r], ho = hp.off[h];
             const int nq = (int)(rd.off[r + 1] - ro) - kKmer + 1, nt = (int)(hp.off[h + 1] - ho) - kKmer + 1;
             if (nq > 0 && nt > 0) {
-                const uint32_t* bs = bins + (size_t)h * (kKmerBins + 1);
+                uint32_t words[MAXT / PER];
+                CountT* counts = reinterpret_cast<CountT*>(words);
+                const uint32_t* bs = binsT + h;
                 const uint16_t* it = items + ho;
                 int32_t* out = kpos + (size_t)i * kMaxMapped;
-                const int per_lane = (nq + 31) / 32, q0 = min(nq, lane * per_lane), q1 = min(nq, q0 + per_lane);
                 unsigned best = 0;
-                for (int d0 = 0; d0 < nt; d0 += kMapTile) {
-                    const int dn = min(kMapTile, nt - d0), nwords = (dn + PER - 1) / PER;
-                    for (int w = lane; w < nwords; w += 32) votes[w] = 0u;
-                    __syncwarp();
-                    int run_d = -1, run_n = 0;
-                    for (int qi = q0; qi < q1; ++qi) {
-                        const uint32_t bin = bs[rhash[ro + qi]];
-                        const int e0 = (int)(bin & 0xFFFFu), e1 = e0 + (int)(bin >> 16);
-                        for (int e = e0; e < e1; ++e) {
-                            const int d = (int)it[e] - qi - d0;          // diagonal within the tile (the reference keeps target_index >= query_index)
-                            if (d < 0 || d >= dn) continue;
-                            if (d == run_d) { ++run_n; continue; }
-                            if (run_n) atomicAdd(&votes[run_d / PER], (uint32_t)run_n << (BITS * (run_d % PER)));
-                            run_d = d; run_n = 1;
+                for (int d0 = 0; d0 < nt; d0 += MAXT) {
+                    const int dn = min(MAXT, nt - d0), nwords = (dn + PER - 1) / PER;
+                    for (int w = 0; w < nwords; ++w) words[w] = 0u;
+                    unsigned max_hit = 0;
+                    for (int qi = 0; qi < nq; ++qi) {
+                        const uint32_t bin = bs[(size_t)rhash[ro + qi] * H];
+                        const int n = (int)(bin >> 16);
+                        if (n == 0) continue;
+                        if (n == 1) {                                        // the k-mer's position, inline
+                            const int d = (int)(bin & 0xFFFFu) - qi - d0;
+                            if (d >= 0 && d < dn) { const unsigned c = ++counts[d]; max_hit = c > max_hit ? c : max_hit; }
+                            continue;
+                        }
+                        const int e0 = (int)(bin & 0xFFFFu);
+                        for (int e = e0; e < e0 + n; ++e) {
+                            const int d = (int)it[e] - qi - d0;               // the reference keeps target_index >= query_index
+                            if (d >= 0 && d < dn) { const unsigned c = ++counts[d]; max_hit = c > max_hit ? c : max_hit; }
                         }
                     }
-                    if (run_n) atomicAdd(&votes[run_d / PER], (uint32_t)run_n << (BITS * (run_d % PER)));
-                    __syncwarp();
-                    unsigned m = 0;
-                    for (int w = lane; w < nwords; w += 32) {
-                        uint32_t v = votes[w];
+                    if (max_hit > best) { best = max_hit; n_out = 0; }       // a higher count: what earlier tiles listed is void
+                    if (max_hit == best && best > 0) {
+                        for (int w = 0; w < nwords && n_out < kMaxMapped; ++w) {
+                            uint32_t v = words[w];
+                            if (v == 0u) continue;
 #pragma unroll
-                        for (int b = 0; b < PER; ++b) { m = max(m, v & FIELD); v >>= BITS / 2; v >>= BITS / 2; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    if (m > best) { best = m; n_out = 0; }            // a higher count: what earlier tiles listed is void
-                    if (m == best && best > 0) {
-                        for (int w0 = 0; w0 < nwords && n_out < kMaxMapped; w0 += 32) {
-                            const int w = w0 + lane;
-                            uint32_t v = w < nwords ? votes[w] : 0u;
-                            unsigned hits = 0;
-#pragma unroll
-                            for (int b = 0; b < PER; ++b) { if ((v & FIELD) == best && w * PER + b < dn) hits |= 1u << b; v >>= BITS / 2; v >>= BITS / 2; }
-                            int mine = __popc(hits), incl = mine;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                            int pos = n_out + incl - mine;
-#pragma unroll
-                            for (int b = 0; b < PER; ++b) if ((hits >> b) & 1u) { if (pos < kMaxMapped) out[pos] = d0 + w * PER + b; ++pos; }
-                            n_out = min(kMaxMapped, n_out + __shfl_sync(0xffffffffu, incl, 31));
+                            for (int b = 0; b < PER; ++b) {
+                                const unsigned c = v & ((1u << (8 * sizeof(CountT))) - 1u);
+                                v >>= 4 * sizeof(CountT); v >>= 4 * sizeof(CountT);
+                                const int t = w * PER + b;
+                                if (c == best && t < dn && n_out < kMaxMapped) out[n_out++] = d0 + t;
+                            }
                         }
                     }
-                    __syncwarp();
                 }
             }
         }
-        if (lane == 0) kcnt[i] = (uint8_t)n_out;
+        kcnt[i] = n_out;
     }
 }
 
@@ -791,7 +783,7 @@ k_populate_flank_acc(const PopParams p)
             window_flanks(a, W, hap_len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
             const int xl = lhs, xr = (W - rhs >= W) ? W + 1 : W - rhs;
             int score, flank;
-            dp_flank_acc<BAND>(rows, L, tab + p.hp.off[h] + a, p.nuc_prior, xl, xr, &score, &flank);
+            dp_flank_acc<BAND>(rows, L, tab + p.hp.off[h] + a, p.nuc_prior, xl, xr, &score, &flank, (uint32_t)p.one);
             // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
             const bool replay_differs = flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
             if (valid) {
