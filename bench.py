@@ -50,6 +50,9 @@ def parse_args():
                     help="weak: every rank owns a batch of the config's shape; strong: the config's reads are split over the ranks (SURVEY.md §8e, C3) "
                          "and the [H, R] matrix is re-assembled on rank 0")
     ap.add_argument("--regions", type=int, default=None, help="regions per rank and step (C5: 1k regions over 8 GPUs = 125 per rank); each its own reads and haplotypes")
+    ap.add_argument("--batch-regions", type=int, default=None,
+                    help="regions per CALL: the rank's regions go to the GPU in one phmm_populate_regions call (Octopus's real call shape: many small "
+                         "active regions) instead of one phmm_populate call per region")
     ap.add_argument("--error-model", default=None, help="haplotype penalty arrays from the reference's error models (reset()), e.g. PCR-free.HiSeq-2500, instead of i.i.d. draws")
     return ap.parse_args()
 
@@ -301,7 +304,7 @@ def main():
     cfg = synth.CONFIGS[args.config]
     read_lens = tuple(int(x) for x in args.read_lens.split(",")) if args.read_lens else None
     strong = args.scaling == "strong" and world > 1
-    n_regions = args.regions if args.regions else (125 if args.config == "C5" else 1)
+    n_regions = args.batch_regions or (args.regions if args.regions else (125 if args.config == "C5" else 1))
 
     def make_region(seed):
         h, r, b = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=seed, band=args.band, hap_len=args.hap_len, read_lens=read_lens)
@@ -361,7 +364,19 @@ def main():
             state["gather_ms"].append((g0, g1))
         return dp
 
+    batched = None
+    if args.batch_regions:
+        from octopus_b200.batch import concat_blocks
+        bh, br, hf, rf = concat_blocks([h for h, r in regions], [r for h, r in regions])
+        batched = (bh.to_device(dev), br.to_device(dev), hf, rf, bh, br)
+        flat_out = torch.empty(int(sum(h.n * r.n for h, r in regions)), dtype=torch.float64, device=dev)
+
     def step():
+        if batched is not None:
+            eng.populate_regions(model_cfg, batched[0], batched[1], batched[2], batched[3],
+                                 flank_states=[flank_state] * len(regions) if flank_state else None, out=flat_out)
+            state["launches"] += eng.launch_count()
+            return eng.last_dp_kernel_ms()
         return sum(one_region(dh, dr) for dh, dr in d_regions)
 
     def sync_all():
@@ -401,7 +416,14 @@ def main():
     p_out_t = torch.empty((H, R), dtype=torch.float64).pin_memory()
     p_out = p_out_t.numpy()
 
+    p_batched = (batched[4].pin(), batched[5].pin()) if batched is not None else None
+    p_flat = torch.empty(int(sum(h.n * r.n for h, r in regions)), dtype=torch.float64).pin_memory().numpy() if batched is not None else None
+
     def e2e_step():
+        if batched is not None:
+            eng.populate_regions(model_cfg, p_batched[0], p_batched[1], batched[2], batched[3],
+                                 flank_states=[flank_state] * len(regions) if flank_state else None, out=p_flat)
+            return
         for ph, pr in p_regions:
             eng.populate(model_cfg, ph, pr, flank_state=flank_state, out=p_out if (ph.n, pr.n) == (H, R) else None)
 
@@ -440,7 +462,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "int32" if args.int_scores else "int16", "data": "synthetic",
             "config": {"workload": workload_name(args.config, R, (args.read_lens or "/".join(map(str, cfg["read_lens"]))).replace(",", "/"), H, args.hap_len or cfg["hap_len"], band),
-                       "regions_per_rank_and_step": len(regions),
+                       "regions_per_rank_and_step": len(regions), "regions_per_call": len(regions) if args.batch_regions else 1,
                        "alignments_per_step": haps.n * R_total if strong else sum(h.n * r.n for h, r in regions) * world,
                        "cells_per_step": cells_rank_total,
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),

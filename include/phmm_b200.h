@@ -190,6 +190,26 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
                   const phmm_positions* positions, const phmm_flank_state* flank,
                   double* out, int32_t* status, int space);
 
+/* Many regions in one call. Octopus runs populate once per ACTIVE REGION (Caller::call_variants, core/callers/caller.cpp:445-531 →
+ * compute_haplotype_likelihoods :1159-1196): a few to a few hundred haplotypes x some hundred to some thousand reads — far too small
+ * to fill a B200 (one such call is launch-latency bound). Here region g owns the haplotypes [hap_first[g], hap_first[g+1]) and the
+ * reads [read_first[g], read_first[g+1]) of the two blocks; every read is scored against the haplotypes of its own region only, all
+ * regions in ONE kernel chain. The region arrays live in HOST memory whatever `space` says (they are tiny and the host sizes the
+ * call from them). */
+typedef struct {
+    int32_t                 n;            /* regions */
+    const int32_t*          hap_first;    /* [n+1], hap_first[0] = 0, hap_first[n] = haplotypes->n */
+    const int32_t*          read_first;   /* [n+1] likewise over the reads */
+    const phmm_flank_state* flank;        /* [n] per-region flank state, or NULL (none) */
+} phmm_regions;
+
+/* out / status (optional): the regions' row-major [H_g][R_g] matrices back to back, region g starting at sum_{g' < g} H_g' * R_g'.
+ * Candidate positions come from the device k-mer mapper (config.map_positions) or are the original position only; explicit position
+ * lists and templates are not supported here. Errors and statuses as phmm_populate. At most 65535 haplotypes per call. */
+int phmm_populate_regions(phmm_engine* e, const phmm_config* cfg,
+                          const phmm_haplotypes* haps, const phmm_reads* reads, const phmm_regions* regions,
+                          double* out, int32_t* status, int space);
+
 /* Paired / linked reads: HaplotypeLikelihoodArray::populate(TemplateMap) (haplotype_likelihood_array.cpp:105-199). Template t owns
  * the reads [template_off[t], template_off[t+1]) and its value is the sum of its reads' values
  * (HaplotypeLikelihoodModel::evaluate(AlignedTemplate), haplotype_likelihood_model.cpp:306-320). out is [H][n_templates];

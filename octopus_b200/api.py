@@ -210,6 +210,53 @@ class PairHMMEngine:
             self._raise(rc)
         return out
 
+    def populate_regions(self, config, haps: HaplotypeBlock, reads: ReadBlock, hap_first, read_first, flank_states=None, out=None, want_status=False):
+        """Many regions in one call (phmm_populate_regions): region g owns haplotypes [hap_first[g], hap_first[g+1]) and reads
+        [read_first[g], read_first[g+1]). Returns the flat result vector (the regions' [H_g, R_g] matrices back to back) and the
+        per-region offsets into it; ``split_regions`` cuts it into matrices. flank_states: None or a list of (lhs, rhs) / None."""
+        dev = haps.on_device
+        assert dev == reads.on_device
+        hf = np.ascontiguousarray(hap_first, dtype=np.int32)
+        rf = np.ascontiguousarray(read_first, dtype=np.int32)
+        G = len(hf) - 1
+        sizes = (np.diff(hf).astype(np.int64) * np.diff(rf).astype(np.int64))
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        total = int(off[-1])
+        fl = None
+        if flank_states is not None:
+            fl = (_lib.FlankState * G)()
+            for g, f in enumerate(flank_states):
+                if f is not None:
+                    fl[g] = _lib.FlankState(1, int(f[0]), int(f[1]))
+        regs = _lib.Regions(G, hf.ctypes.data, rf.ctypes.data, C.addressof(fl) if fl is not None else None)
+        hs, rs = haps.c_struct(), reads.c_struct()
+        cfg = config.c_struct() if hasattr(config, "c_struct") else config
+        status = None
+        if dev:
+            import torch
+            if out is None:
+                out = torch.empty(total, dtype=torch.float64, device=haps.seq.device)
+            if want_status:
+                status = torch.empty(total, dtype=torch.int32, device=haps.seq.device)
+            op, sp = out.data_ptr(), (status.data_ptr() if want_status else None)
+        else:
+            if out is None:
+                out = np.empty(total, dtype=np.float64)
+            if want_status:
+                status = np.empty(total, dtype=np.int32)
+            op, sp = out.ctypes.data, (status.ctypes.data if want_status else None)
+        rc = self._lib.phmm_populate_regions(self._h, C.byref(cfg), C.byref(hs), C.byref(rs), C.byref(regs), op, sp,
+                                             _lib.SPACE_DEVICE if dev else _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK and not (rc == _lib.PHMM_ERR_SHORT_HAPLOTYPE and want_status):
+            self._raise(rc)
+        return (out, off, status) if want_status else (out, off)
+
+    @staticmethod
+    def split_regions(flat, off, hap_first, read_first):
+        """The per-region [H_g, R_g] views of a populate_regions result."""
+        return [flat[int(off[g]):int(off[g + 1])].reshape(int(hap_first[g + 1] - hap_first[g]), int(read_first[g + 1] - read_first[g]))
+                for g in range(len(off) - 1)]
+
     def populate(self, config, haps: HaplotypeBlock, reads: ReadBlock, positions=None, flank_state=None, out=None,
                  want_status=False):
         """Returns the (H, R) matrix of ln-likelihoods (numpy float64, or a torch CUDA tensor for device-resident blocks).

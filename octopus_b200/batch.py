@@ -169,3 +169,21 @@ def pack_positions(position_lists, H, R):
             off[i + 1] = off[i] + len(p)
             i += 1
     return off, np.asarray(flat if flat else [0], dtype=np.int32)[:max(len(flat), 1)]
+
+
+def concat_blocks(hap_blocks, read_blocks):
+    """Regions back to back for PairHMMEngine.populate_regions: (HaplotypeBlock, ReadBlock, hap_first, read_first) (host blocks)."""
+    def cat_off(blocks):
+        off, base = [np.zeros(1, dtype=np.int64)], 0
+        for b in blocks:
+            off.append(b.off[1:] + base)
+            base += int(b.off[-1])
+        return np.concatenate(off)
+    cat = lambda blocks, f: np.concatenate([getattr(b, f) for b in blocks])     # noqa: E731
+    haps = HaplotypeBlock(cat_off(hap_blocks), *[cat(hap_blocks, f) for f in HaplotypeBlock._fields[1:8]],
+                          np.concatenate([b.begin if b.begin is not None else np.zeros(b.n, dtype=np.int64) for b in hap_blocks]))
+    reads = ReadBlock(cat_off(read_blocks), cat(read_blocks, "bases"), cat(read_blocks, "quals"), cat(read_blocks, "mapq"),
+                      cat(read_blocks, "reverse"), cat(read_blocks, "begin"))
+    hap_first = np.concatenate([[0], np.cumsum([b.n for b in hap_blocks])]).astype(np.int32)
+    read_first = np.concatenate([[0], np.cumsum([b.n for b in read_blocks])]).astype(np.int32)
+    return haps, reads, hap_first, read_first

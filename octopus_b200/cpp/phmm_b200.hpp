@@ -475,6 +475,7 @@ private:
     Engine engine_;
     phmm_config config_;
     pinned_vector<double> likelihoods_;
+    pinned_vector<std::int32_t> status_;
     std::vector<SampleName> samples_;
     std::vector<std::size_t> sample_off_ {0};
     std::size_t num_haplotypes_ = 0;
@@ -505,9 +506,10 @@ private:
         const auto hv = haplotypes.view();
         const auto rv = reads.view();
         num_haplotypes_ = haplotypes.size();
-        likelihoods_.assign(num_haplotypes_ * total_width(), 0.0);
+        likelihoods_.resize(num_haplotypes_ * total_width());        // every element is written by the call (no zero fill; the storage is page-locked and kept)
         if (num_haplotypes_ == 0 || reads.size() == 0) return;
-        pinned_vector<std::int32_t> status(num_haplotypes_ * reads.size(), 0);
+        pinned_vector<std::int32_t>& status = status_;               // page-locked scratch kept across calls: allocating pinned memory costs milliseconds
+        status.resize(num_haplotypes_ * reads.size());
         phmm_flank_state fs {flank_state ? 1 : 0, flank_state ? flank_state->lhs_flank : 0, flank_state ? flank_state->rhs_flank : 0};
         const int rc = template_off
             ? phmm_populate_templates(engine_.get(), &config_, &hv, &rv, template_off->data(), static_cast<std::int32_t>(template_off->size() - 1),

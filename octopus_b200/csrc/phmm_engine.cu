@@ -61,7 +61,7 @@ struct phmm_engine {
     DBuf r_off, r_bases, r_quals, r_mapq, r_rev, r_begin;
     DBuf c_off, c_pos;
     // derived / scratch
-    DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, wide_reads, bp;
+    DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, wide_reads, bp, regs, rregion, rpbase, rpstride;
     DBuf tasks_lane, tasks_generic, works, scores;
     DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, atasks, gcnt, sched, sorted;
     std::vector<cudaEvent_t> tile_events;
@@ -335,7 +335,7 @@ void phmm_destroy(phmm_engine* e)
     DBuf* all[] = {&e->h_off, &e->h_seq, &e->h_mf, &e->h_pf, &e->h_mr, &e->h_pr, &e->h_go, &e->h_ge, &e->h_begin,
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
-                   &e->counters, &e->pairs, &e->generic_reads, &e->wide_reads, &e->bp, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
+                   &e->counters, &e->pairs, &e->generic_reads, &e->wide_reads, &e->bp, &e->regs, &e->rregion, &e->rpbase, &e->rpstride, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
                    &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->atasks, &e->gcnt, &e->sched, &e->sorted};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
@@ -689,11 +689,19 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
 // -------------------------------------------------------------------------------------------------------------
 // One synchronous pass over (all haplotypes) x (the given reads). out / status are written with a row pitch of out_pitch
 // elements (0: dense [H][R]) so that a read chunk can land in its column block of the caller's [H][R_total] matrix.
+// One region list for every call: phmm_populate is the one-region case. Host copies of the region arrays (a few KB).
+struct RegionSetup {
+    std::vector<RegionInfo> regs;
+    long long total_out = 0;
+    int Hmax = 0;
+    bool any_flank = false;
+};
+
 static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                          const phmm_haplotypes* haps, const phmm_reads* reads,
                          const phmm_positions* positions, const phmm_flank_state* flank,
                          double* out, int32_t* status, int space, long long out_pitch,
-                         const int64_t* template_off = nullptr, int n_templates = 0)
+                         const int64_t* template_off = nullptr, int n_templates = 0, const RegionSetup* multi = nullptr)
 {
     if (!e) return PHMM_ERR_INVALID;
     static const bool trace = std::getenv("PHMM_TRACE") != nullptr;
@@ -712,8 +720,30 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     Staged s;
     int rc = stage_batch(e, haps, reads, space, s, false, true);
     if (rc != PHMM_OK) return rc;
-    const int H = s.hp.n, R = s.rd.n;
-    const long long HR = (long long)H * R;
+    const int H_total = s.hp.n, R = s.rd.n;
+    RegionSetup single;
+    if (!multi) {
+        const bool fl = flank && flank->has_flank && cfg->use_flank_state;
+        RegionInfo g {};
+        g.h0 = 0; g.nH = H_total; g.r0 = 0; g.nR = R; g.out_off = 0;
+        g.use_flanks = fl ? 1 : 0; g.lhs = fl ? (int)flank->lhs_flank : 0; g.rhs = fl ? (int)flank->rhs_flank : 0;
+        single.regs.push_back(g); single.total_out = (long long)H_total * R; single.Hmax = H_total; single.any_flank = fl;
+        multi = &single;
+    }
+    const int G = (int)multi->regs.size();
+    // H: haplotype slots per read (the widest region); HR: result slots of the whole call
+    const int H = multi->Hmax;
+    const long long HR = multi->total_out;
+    {   // regions to the device; per-read region / result slot
+        CU(e->regs.ensure((size_t)G * sizeof(RegionInfo)));
+        CU(cudaMemcpyAsync(e->regs.p, multi->regs.data(), (size_t)G * sizeof(RegionInfo), cudaMemcpyHostToDevice, e->stream));
+        CU(e->rregion.ensure((size_t)R * sizeof(int)));
+        CU(e->rpbase.ensure((size_t)R * sizeof(long long)));
+        CU(e->rpstride.ensure((size_t)R * sizeof(int)));
+        k_read_regions<<<(R + 255) / 256, 256, 0, e->stream>>>(R, G, e->regs.as<RegionInfo>(), e->rregion.as<int>(), e->rpbase.as<long long>(), e->rpstride.as<int>());
+        LAUNCHED();
+        s.rd.region = e->rregion.as<int>(); s.rd.pbase = e->rpbase.as<long long>(); s.rd.pstride = e->rpstride.as<int>();
+    }
     // Everything from here to the final copy-out is enqueued without waiting for the device: sizes come from upper bounds
     // the host can derive from the offsets, the kernels clip them against the scheduler's device-resident totals.
     const long long len_min = s.read_len_min;
@@ -727,12 +757,13 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     p.hp = s.hp; p.rd = s.rd;
     p.band = band; p.nuc_prior = cfg->nuc_prior; p.one = 1;
     p.shortcut = cfg->disable_naive_shortcut ? 0 : 1;
-    p.use_flanks = (flank && flank->has_flank && cfg->use_flank_state) ? 1 : 0;
-    p.lhs_flank = p.use_flanks ? (int)flank->lhs_flank : 0;
-    p.rhs_flank = p.use_flanks ? (int)flank->rhs_flank : 0;
+    p.regs = e->regs.as<RegionInfo>();
+    p.Hmax = H;
+    p.use_flanks = multi->any_flank ? 1 : 0;
     // candidates a pair can have: listed / mapped positions + the original position + the shifted fallback
     // (haplotype_likelihood_model.cpp:211-259); at most (listed + 1) of them reach a DP
     int max_cand = 2, max_dp_per_pair = 1;
+    if (positions && positions->off && positions->pos && G > 1) { e->err = "candidate position lists are not supported with several regions"; return PHMM_ERR_INVALID; }
     if (positions && positions->off && positions->pos) {
         // Candidate lists: CSR arrays on the device; the host needs the total (to size the copy) and the longest list (to size the
         // per-read task lists: the reference accepts lists of any length) — reduced on the device, 32 bytes back.
@@ -760,19 +791,20 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         max_dp_per_pair = kMaxMapped + 1;
     }
     const bool use_mapper = !(positions && positions->off && positions->pos) && cfg->map_positions;
+    p.single_candidate = max_dp_per_pair == 1 ? 1 : 0;
     int mapper_maxt = 0;
     if (use_mapper) {
         long long max_hap = 0;
-        for (int h = 0; h < H; ++h) max_hap = std::max(max_hap, s.hap_off_host[h + 1] - s.hap_off_host[h]);
+        for (int h = 0; h < H_total; ++h) max_hap = std::max(max_hap, s.hap_off_host[h + 1] - s.hap_off_host[h]);
         mapper_maxt = max_hap - 5 <= 512 ? 512 : 2048;       // vote-array capacity per thread (longer haplotypes: tiles of 2048 diagonals)
         if (max_hap > 65535) { e->err = "haplotype longer than 65535 bp: the device k-mer mapper indexes k-mer positions with 16 bits (pass explicit positions)"; return PHMM_ERR_INVALID; }
         if (s.hap_bases > 65535LL * 65535LL) { e->err = "haplotype block too large"; return PHMM_ERR_INVALID; }
         CU(e->rhash.ensure((size_t)s.read_bases * sizeof(uint16_t)));
-        CU(e->kbins.ensure((size_t)H * (kKmerBins + 1) * sizeof(int)));
+        CU(e->kbins.ensure((size_t)H_total * (kKmerBins + 1) * sizeof(int)));
         CU(e->kitems.ensure((size_t)s.hap_bases * sizeof(uint16_t)));
         k_read_kmers<<<(unsigned)(((long long)R * 32 + 255) / 256), 256, 0, e->stream>>>(s.read_bases, R, s.rd.off, s.rd.bases, e->rhash.as<uint16_t>());
         LAUNCHED();
-        k_build_kmer_table<<<H, 256, 0, e->stream>>>(H, s.hp.off, s.hp.seq, e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>());
+        k_build_kmer_table<<<H_total, 256, 0, e->stream>>>(H_total, s.hp.off, s.hp.seq, e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>());
         LAUNCHED();
         CU(cudaGetLastError());
     }
@@ -780,9 +812,9 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     // scheduling: equal-length read pairs for the packed kernels, 32-bit multi-lane kernels for what they cannot take, and the
     // thread-per-pair generic kernel for the rest (foreign alphabet, qualities above 127, reads beyond the shared-memory budget)
     long long max_hap_len = 0;
-    for (int h = 0; h < H; ++h) max_hap_len = std::max(max_hap_len, s.hap_off_host[h + 1] - s.hap_off_host[h]);
+    for (int h = 0; h < H_total; ++h) max_hap_len = std::max(max_hap_len, s.hap_off_host[h + 1] - s.hap_off_host[h]);
     // the DP task word packs (haplotype, window offset) into 16 + 16 bits
-    const bool task_word_ok = H <= 65535 && max_hap_len <= 65535;
+    const bool task_word_ok = H_total <= 65535 && max_hap_len <= 65535;
     const int NL = lanes_per_alignment(band);
     // wide (32-bit) path: row entries of one read per warp in shared memory; long reads get fewer warps per block
     const int wide_row_stride = (int)((std::min<long long>(Lmax_all, kWideMaxReadLen) + 2) & ~1LL);
@@ -800,7 +832,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     const size_t pairs_cap = (size_t)R / 2 + (size_t)kLenBins * groups + 8;
     SchedTotals tot {};
     {
-        CU(e->sched.ensure((size_t)(4 * (kLenBins + 1) + 16) * sizeof(int) + sizeof(SchedTotals)));
+        CU(e->sched.ensure((size_t)(4 * (kLenBins + 1) + 16) * sizeof(int) + sizeof(SchedTotals) + 16));
         CU(e->sorted.ensure((size_t)R * sizeof(int)));
         CU(e->pairs.ensure(2 * pairs_cap * sizeof(int)));
         CU(e->generic_reads.ensure((size_t)R * sizeof(int)));
@@ -809,11 +841,12 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         int* hist = base, *read_start = base + (kLenBins + 1), *pair_start = base + 2 * (kLenBins + 1), *cursors = base + 3 * (kLenBins + 1);
         int* misc = base + 4 * (kLenBins + 1);          // [0] n_generic, [1] lmax_all, [2] bad, [3] packed reads with 'N', [4] n_wide
         SchedTotals* d_tot = (SchedTotals*)(misc + 16);
-        CU(cudaMemsetAsync(base, 0, (size_t)(4 * (kLenBins + 1) + 16) * sizeof(int), e->stream));
-        k_sched_hist<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, mode, hist, e->generic_reads.as<int>(), e->wide_reads.as<int>(), misc);
+        unsigned long long* d_cells = (unsigned long long*)((char*)d_tot + ((sizeof(SchedTotals) + 7) & ~size_t(7)));
+        CU(cudaMemsetAsync(base, 0, (size_t)(4 * (kLenBins + 1) + 16) * sizeof(int) + sizeof(SchedTotals) + 16, e->stream));
+        k_sched_hist<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, mode, hist, e->generic_reads.as<int>(), e->wide_reads.as<int>(), misc,
+                                                              s.rd.region, e->regs.as<RegionInfo>(), band, d_cells);
         LAUNCHED();
-        k_sched_scan<<<1, kLenBins, 0, e->stream>>>(hist, groups, band, H, read_start, pair_start, cursors, misc, s.rd.info,
-                                                    e->generic_reads.as<int>(), e->wide_reads.as<int>(), d_tot);
+        k_sched_scan<<<1, kLenBins, 0, e->stream>>>(hist, groups, read_start, pair_start, cursors, misc, d_cells, d_tot);
         LAUNCHED();
         k_sched_scatter<<<(R + 255) / 256, 256, 0, e->stream>>>(R, s.rd.info, mode, read_start, cursors, e->sorted.as<int>());
         LAUNCHED();
@@ -942,7 +975,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     auto launch_mapper = [&](const int* list, int n_list, int base, int kind) {
         const long long threads = (long long)n_list * H;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 127) / 128, (long long)e->sm_count * 64));
-#define PHMM_MAP_ARGS list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>()
+#define PHMM_MAP_ARGS list, n_list, d_tot, base, kind, s.hp, s.rd, e->rhash.as<uint16_t>(), e->kbins.as<uint32_t>(), e->kitems.as<uint16_t>(), e->kpos.as<int32_t>(), e->kcnt.as<uint8_t>(), e->regs.as<RegionInfo>(), H
         if (mapper_maxt == 512) {
             if (mapper_bytes) k_kmer_map<512, uint8_t><<<grid, 128, 0, e->stream>>>(PHMM_MAP_ARGS);
             else k_kmer_map<512, uint16_t><<<grid, 128, 0, e->stream>>>(PHMM_MAP_ARGS);
@@ -1085,10 +1118,14 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     lap("tiles enqueued");
     CU(e->out.ensure((size_t)HR * sizeof(double)));
     double* d_out = (space == PHMM_SPACE_DEVICE && !template_off) ? out : e->out.as<double>();
-    k_epilogue<<<(unsigned)((HR + 255) / 256), 256, 0, e->stream>>>(p.best, p.status, s.rd.mapq, H, R, cfg->use_mapping_quality,
-                                                                    cfg->mapping_quality_cap, cfg->mapping_quality_cap_trigger, d_out);
+    {
+        const long long threads = (long long)H * R;
+        k_epilogue<<<(unsigned)((threads + 255) / 256), 256, 0, e->stream>>>(p.best, p.status, s.rd, e->regs.as<RegionInfo>(), H, cfg->use_mapping_quality,
+                                                                             cfg->mapping_quality_cap, cfg->mapping_quality_cap_trigger, d_out);
+    }
     LAUNCHED();
     CU(cudaGetLastError());
+    if (template_off && G > 1) { e->err = "templates are not supported with several regions"; return PHMM_ERR_INVALID; }
     if (template_off) {
         // paired / linked reads: one value per (haplotype, template)
         const long long* d_toff;
@@ -1137,6 +1174,32 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     if (flags_host[0] & (4 | 8)) { e->err = "internal task queue overflow"; return PHMM_ERR_NOMEM; }
     if (flags_host[0] & 2) { e->err = "Haplotype is too short for alignment"; return PHMM_ERR_SHORT_HAPLOTYPE; }
     return PHMM_OK;
+}
+
+int phmm_populate_regions(phmm_engine* e, const phmm_config* cfg,
+                          const phmm_haplotypes* haps, const phmm_reads* reads, const phmm_regions* regions,
+                          double* out, int32_t* status, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    if (!regions || regions->n <= 0 || !regions->hap_first || !regions->read_first || !haps || !reads) { e->err = "null / empty region list"; return PHMM_ERR_INVALID; }
+    RegionSetup setup;
+    setup.regs.resize((size_t)regions->n);
+    if (regions->hap_first[0] != 0 || regions->read_first[0] != 0 || regions->hap_first[regions->n] != haps->n || regions->read_first[regions->n] != reads->n) {
+        e->err = "region ranges must cover the haplotype and read blocks exactly"; return PHMM_ERR_INVALID;
+    }
+    for (int g = 0; g < regions->n; ++g) {
+        RegionInfo& r = setup.regs[(size_t)g];
+        r.h0 = regions->hap_first[g]; r.nH = regions->hap_first[g + 1] - r.h0;
+        r.r0 = regions->read_first[g]; r.nR = regions->read_first[g + 1] - r.r0;
+        if (r.nH <= 0 || r.nR <= 0) { e->err = "every region needs at least one haplotype and one read"; return PHMM_ERR_INVALID; }
+        r.out_off = setup.total_out;
+        setup.total_out += (long long)r.nH * r.nR;
+        setup.Hmax = std::max(setup.Hmax, r.nH);
+        const bool fl = regions->flank && regions->flank[g].has_flank && cfg && cfg->use_flank_state;
+        r.use_flanks = fl ? 1 : 0; r.lhs = fl ? (int)regions->flank[g].lhs_flank : 0; r.rhs = fl ? (int)regions->flank[g].rhs_flank : 0; r.pad = 0;
+        setup.any_flank = setup.any_flank || fl;
+    }
+    return populate_impl(e, cfg, haps, reads, nullptr, nullptr, out, status, space, 0, nullptr, 0, &setup);
 }
 
 int phmm_populate_templates(phmm_engine* e, const phmm_config* cfg,

@@ -29,7 +29,14 @@ struct DevReads {
     const long long* begin;
     const uint16_t* rowhalf;    // code | qual << 8 per base, same indexing as bases
     const int2* info;           // per read: .x = length, .y = flags
+    // Regions (phmm_populate_regions): a read is scored against the haplotypes of its own region only. The result of pair (h, r) lives
+    // at slot pbase[r] + h * pstride[r] of best[] / status[] / out[] (k_read_regions; one region: pbase = r, pstride = R).
+    const int* region;          // region of each read
+    const long long* pbase;
+    const int* pstride;
 };
+struct RegionInfo { int h0, nH, r0, nR; long long out_off; int lhs, rhs, use_flanks, pad; };
+__device__ __forceinline__ long long pair_slot(const DevReads& rd, const int h, const int r) { return rd.pbase[r] + (long long)h * rd.pstride[r]; }
 constexpr int kReadNonACGT  = 1;   // read holds a byte outside ACGT → generic path
 constexpr int kReadUnsafe16 = 2;   // sum of qualities too large for a 16-bit lane, or a quality > 127
 constexpr int kReadTooLong  = 4;   // longer than the fast path's shared-memory row budget
@@ -122,6 +129,20 @@ __global__ void k_read_info(const int n_reads, const long long* __restrict__ off
     if (lane == 0) info[r] = make_int2(L, flags);
 }
 
+// Region of every read (binary search over the regions' first-read indices) and where its results go.
+__global__ void k_read_regions(const int n_reads, const int n_regions, const RegionInfo* __restrict__ regs,
+                               int* __restrict__ region, long long* __restrict__ pbase, int* __restrict__ pstride)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    int lo = 0, hi = n_regions;                 // largest g with regs[g].r0 <= r
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (regs[mid].r0 <= r) lo = mid; else hi = mid; }
+    const RegionInfo g = regs[lo];
+    region[r] = lo;
+    pbase[r] = g.out_off - (long long)g.h0 * g.nR + (r - g.r0);
+    pstride[r] = g.nR;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Device-side scheduling of the fast path: bucket the eligible reads by length (counting sort), pair reads of equal
 // length, pad every length bucket to a multiple of G pairs (a warp's G pairs share one read length). Replaces a host
@@ -132,9 +153,15 @@ struct SchedTotals { int n_pairs, n_generic, lmax_fast, lmax_all, n_eligible, ba
 
 // misc counters: [0] generic reads, [1] longest read, [2] bad, [3] packed reads holding 'N', [4] wide reads
 __global__ void k_sched_hist(const int R, const int2* __restrict__ info, const SchedMode mode, int* __restrict__ hist,
-                             int* __restrict__ generic, int* __restrict__ wide, int* __restrict__ misc)
+                             int* __restrict__ generic, int* __restrict__ wide, int* __restrict__ misc,
+                             const int* __restrict__ region, const RegionInfo* __restrict__ regs, const int band, unsigned long long* __restrict__ cells)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    // banded cells of the read against every haplotype of its region (the GCUPS numerator), one atomic per warp
+    unsigned long long mine = r < R ? (unsigned long long)(2LL * (info[r].x + band) * band) * (unsigned long long)regs[region[r]].nH : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(cells, mine);
     if (r >= R) return;
     const int2 inf = info[r];
     if (inf.x < 1) atomicExch(misc + 2, 1);
@@ -147,17 +174,14 @@ __global__ void k_sched_hist(const int R, const int2* __restrict__ info, const S
 
 // one block of kLenBins threads: exclusive scans of the per-length read counts and padded pair counts
 __global__ void __launch_bounds__(kLenBins)
-k_sched_scan(const int* __restrict__ hist, const int G, const int band, const int H, int* __restrict__ read_start, int* __restrict__ pair_start,
-             int* __restrict__ cursors, const int* __restrict__ misc, const int2* __restrict__ info,
-             const int* __restrict__ generic, const int* __restrict__ wide, SchedTotals* __restrict__ tot)
+k_sched_scan(const int* __restrict__ hist, const int G, int* __restrict__ read_start, int* __restrict__ pair_start,
+             int* __restrict__ cursors, const int* __restrict__ misc, const unsigned long long* __restrict__ cells, SchedTotals* __restrict__ tot)
 {
     __shared__ int s_reads[kLenBins], s_pairs[kLenBins];
-    __shared__ unsigned long long s_cells;
     const int l = threadIdx.x;
     const int c = hist[l];
     const int pairs = ((c + 1) / 2 + G - 1) / G * G;
     s_reads[l] = c; s_pairs[l] = pairs;
-    if (l == 0) s_cells = 0ull;
     __syncthreads();
     // Hillis-Steele inclusive scans (1024 elements)
     for (int d = 1; d < kLenBins; d <<= 1) {
@@ -169,14 +193,7 @@ k_sched_scan(const int* __restrict__ hist, const int G, const int band, const in
     read_start[l] = s_reads[l] - c;
     pair_start[l] = s_pairs[l] - pairs;
     cursors[l] = 0;
-    if (c) atomicAdd(&s_cells, (unsigned long long)c * (unsigned long long)(2LL * (l + band) * band));
-    __syncthreads();
-    // generic and wide reads contribute to the cell count too
     const int ng = misc[0], nw = misc[4];
-    unsigned long long mine = 0;
-    for (int i = l; i < ng; i += kLenBins) mine += (unsigned long long)(2LL * (info[generic[i]].x + band) * band);
-    for (int i = l; i < nw; i += kLenBins) mine += (unsigned long long)(2LL * (info[wide[i]].x + band) * band);
-    if (mine) atomicAdd(&s_cells, mine);
     int lmax = c ? l : 0;
     for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     __shared__ int s_lmax[kLenBins / 32];
@@ -193,7 +210,7 @@ k_sched_scan(const int* __restrict__ hist, const int G, const int band, const in
         tot->lmax_all = max(misc[1], 1);
         tot->bad = misc[2];
         tot->n_with_n = misc[3];
-        tot->cells = (long long)s_cells * H;
+        tot->cells = (long long)*cells;
     }
     if (l == kLenBins - 1) { read_start[kLenBins] = s_reads[l]; pair_start[kLenBins] = s_pairs[l]; }
 }
@@ -363,11 +380,13 @@ struct PopParams {
     int* acc_cursor;
     int* any_acc_tasks;
     int units_per_pair;         // fast kernel: a read pair's task lists are cut into this many work units of kRoundsPerUnit rounds
+    const RegionInfo* regs;     // regions of the call (one for phmm_populate); the flank state is per region
+    int Hmax;                   // most haplotypes any region has: per-read loops run over Hmax slots and skip the ones beyond the region
     int band, nuc_prior;
     int one;                    // the constant 1, opaque to the compiler (fma_add)
+    int single_candidate;       // every pair has at most one candidate position (no listed / mapped positions): results are stored, not min-reduced
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
-    int use_flanks;             // flank_state present && config.use_flank_state
-    int lhs_flank, rhs_flank;
+    int use_flanks;             // some region has a flank state && config.use_flank_state (the per-region values are in regs)
     int* best;                  // [H*R] integer penalties, kBestInf-initialised
     int* status;                // [H*R] zero-initialised
     int* flags;                 // [0] |= 2 on ShortHaplotypeError, |= 4 on slow-queue overflow
@@ -539,19 +558,22 @@ template <int MAXT, typename CountT>
 __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, const SchedTotals* __restrict__ tot, const int base, const int kind,
                            const DevHaps hp, const DevReads rd,
                            const uint16_t* __restrict__ rhash, const uint32_t* __restrict__ binsT, const uint16_t* __restrict__ items,
-                           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt)
+                           int32_t* __restrict__ kpos, uint8_t* __restrict__ kcnt, const RegionInfo* __restrict__ regs, const int Hmax)
 {
     constexpr int PER = 4 / (int)sizeof(CountT);
     const int H = hp.n;
     // the tile's work list: 2 entries per read pair, or the wide / generic reads; clipped against the scheduler's totals
     const int n_list = max(0, min(n_list_max, list_total(tot, kind) - base));
-    const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
+    const long long total = (long long)n_list * Hmax, step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-        int li, h;
-        split_index(i, H, &li, &h);
+        int li, hl;
+        split_index(i, Hmax, &li, &hl);
         const int r = list[li];
         uint8_t n_out = 0;
-        if (r >= 0) {
+        int h = 0;
+        bool in_region = false;
+        if (r >= 0) { const RegionInfo g = regs[rd.region[r]]; h = g.h0 + hl; in_region = hl < g.nH; }
+        if (in_region) {
             const long long ro = rd.off[r], ho = hp.off[h];
             const int nq = (int)(rd.off[r + 1] - ro) - kKmer + 1, nt = (int)(hp.off[h + 1] - ho) - kKmer + 1;
             if (nq > 0 && nt > 0) {
@@ -620,7 +642,6 @@ k_populate_fast(const PopParams p)
     const int grp = lane / LG, gl = lane % LG;
     const int slot = gl / NL, jl = gl % NL;
     RowEntry* rows = smem_rows + (warp * G + grp) * p.row_stride;
-    const int R = p.rd.n;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     const int n_pairs = tile_pairs(p);
     for (;;) {
@@ -671,8 +692,13 @@ k_populate_fast(const PopParams p)
             const int h0 = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1 = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
             const uint32_t res = packed_dp<BAND>(rows, L, b0 + p.hp.off[h0] + a0, b1 + p.hp.off[h1] + a1, nucp, jl);
             if (jl == 0) {
-                if (v0) atomicMin(p.best + (size_t)h0 * R + r0, (int)(res & 0xFFFFu));
-                if (v1) atomicMin(p.best + (size_t)h1 * R + r1, (int)(res >> 16));
+                if (p.single_candidate) {       // at most one candidate per pair: its value IS the pair's minimum — a plain store, no read of best[]
+                    if (v0) p.best[pair_slot(p.rd, h0, r0)] = (int)(res & 0xFFFFu);
+                    if (v1) p.best[pair_slot(p.rd, h1, r1)] = (int)(res >> 16);
+                } else {
+                    if (v0) atomicMin(p.best + pair_slot(p.rd, h0, r0), (int)(res & 0xFFFFu));
+                    if (v1) atomicMin(p.best + pair_slot(p.rd, h1, r1), (int)(res >> 16));
+                }
             }
         }
     }
@@ -687,7 +713,6 @@ k_populate_flank(const PopParams p)
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     RowEntry* rows = smem_rows + warp * p.row_stride;
-    const int R = p.rd.n;
     constexpr int K = 2 * BAND;
     if (*p.any_flank_tasks == 0) return;          // the classify pass queued nothing for this kernel
     const int n_list = tile_list(p);
@@ -700,6 +725,7 @@ k_populate_flank(const PopParams p)
         const int n = r >= 0 ? p.gcnt[li] : 0;
         if (n == 0) continue;
         const int L = p.rd.info[r].x;
+        const RegionInfo reg = p.regs[p.rd.region[r]];
         __syncwarp();
         unsigned qmin = 255u;
         {
@@ -720,7 +746,7 @@ k_populate_flank(const PopParams p)
             const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
             const int hap_len = (int)(p.hp.off[h + 1] - p.hp.off[h]);
             int lhs, rhs;
-            window_flanks(a, W, hap_len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+            window_flanks(a, W, hap_len, reg.lhs, reg.rhs, &lhs, &rhs);
             int xl = lhs, xr = W - rhs;
             const bool all_flank = xr <= xl;        // flanks overlap: every operation is inside a flank
             if (all_flank) { xl = 0; xr = W + 1; }
@@ -730,10 +756,10 @@ k_populate_flank(const PopParams p)
             if (all_flank) { flank = score; mask = L; }
             const int v = discount_flank(score, flank, L, mask, 0);
             // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
-            const bool replay_differs = p.use_flanks != 0 && flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
+            const bool replay_differs = reg.use_flanks != 0 && flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
             if (valid) {
                 if (replay_differs) push_slow(p, r, h, a);
-                else atomicMin(p.best + (size_t)h * R + r, v);
+                else atomicMin(p.best + pair_slot(p.rd, h, r), v);
             }
         }
     }
@@ -747,7 +773,6 @@ k_populate_flank_acc(const PopParams p)
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     RowEntry* rows = smem_rows + warp * p.row_stride;
-    const int R = p.rd.n;
     constexpr int K = 2 * BAND;
     if (*p.any_acc_tasks == 0) return;
     const int n_list = tile_list(p);
@@ -760,6 +785,7 @@ k_populate_flank_acc(const PopParams p)
         const int n = r >= 0 ? p.acnt[li] : 0;
         if (n == 0) continue;
         const int L = p.rd.info[r].x;
+        const RegionInfo reg = p.regs[p.rd.region[r]];
         __syncwarp();
         unsigned qmin = 255u;
         {
@@ -780,7 +806,7 @@ k_populate_flank_acc(const PopParams p)
             const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
             const int hap_len = (int)(p.hp.off[h + 1] - p.hp.off[h]);
             int lhs, rhs;
-            window_flanks(a, W, hap_len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+            window_flanks(a, W, hap_len, reg.lhs, reg.rhs, &lhs, &rhs);
             const int xl = lhs, xr = (W - rhs >= W) ? W + 1 : W - rhs;
             int score, flank;
             dp_flank_acc<BAND>(rows, L, tab + p.hp.off[h] + a, p.nuc_prior, xl, xr, &score, &flank, (uint32_t)p.one);
@@ -788,7 +814,7 @@ k_populate_flank_acc(const PopParams p)
             const bool replay_differs = flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
             if (valid) {
                 if (replay_differs) push_slow(p, r, h, a);
-                else atomicMin(p.best + (size_t)h * R + r, score - flank);
+                else atomicMin(p.best + pair_slot(p.rd, h, r), score - flank);
             }
         }
     }
@@ -799,19 +825,22 @@ k_populate_flank_acc(const PopParams p)
 // With FASTQ it is the classify pass of the fast path instead: the same candidate walk over the fast work list (the pair
 // list, entries may be -1), but score-only DP candidates are appended to the read's task list for k_populate_fast.
 template <int MAXK, bool FASTQ>
-__device__ __forceinline__ void populate_one_pair(const PopParams& p, const int li, const int h)
+__device__ __forceinline__ void populate_one_pair(const PopParams& p, const int li, const int hl)
 {
-    const int H = p.hp.n, R = p.rd.n;
     const int r = p.list[li];
     if (r < 0) return;
+    const RegionInfo reg = p.regs[p.rd.region[r]];
+    if (hl >= reg.nH) return;                      // a slot beyond this read's region
+    const int h = reg.h0 + hl;
+    const long long slot_hr = pair_slot(p.rd, h, r);
     const bool rev = p.rd.reverse[r] != 0;
     const HapView hv = hap_view(p.hp, h, rev);
     const ReadView rv = read_view(p.rd, r);
     const long long orig = (p.rd.begin ? p.rd.begin[r] : 0) - (p.hp.begin ? p.hp.begin[h] : 0);
     int npos = 0;
     const int32_t* pp = nullptr;
-    if (p.pos_off) { const long long o = p.pos_off[(size_t)h * R + r]; npos = (int)(p.pos_off[(size_t)h * R + r + 1] - o); pp = p.pos + o; }
-    else if (p.kcnt) { npos = p.kcnt[(size_t)li * H + h]; pp = p.kpos + ((size_t)li * H + h) * kMaxMapped; }
+    if (p.pos_off) { const long long o = p.pos_off[slot_hr]; npos = (int)(p.pos_off[slot_hr + 1] - o); pp = p.pos + o; }
+    else if (p.kcnt) { npos = p.kcnt[(size_t)li * p.Hmax + hl]; pp = p.kpos + ((size_t)li * p.Hmax + hl) * kMaxMapped; }
     EnumState st {false, false};
     int best = kBestInf;
     // DP candidates are collected first and queued after the walk: a shortcut value of 0 (exact match at some candidate
@@ -843,7 +872,7 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
                     if ((pend_flank >> i2) & 1u) {
                         const int W = rv.len + 2 * p.band - 1;
                         int lhs, rhs;
-                        window_flanks(v, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+                        window_flanks(v, W, hv.len, reg.lhs, reg.rhs, &lhs, &rhs);
                         const int xl = lhs, xr = W - rhs;
                         if (xr <= xl) route = to_32bit ? 0 : 2;      // the flanks cover the whole window: the result is the plain score (:757-759)
                         else if (!(p.rd.info[r].y & kReadHasN) && p.atasks && flank_mask_cannot_zero(rv.len, p.band, xl, xr >= W ? W + 1 : xr)) route = 1;
@@ -862,10 +891,10 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
     for (int c = 0; c < npos + 2; ++c) {
         int pos;
         const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
-        if (k < 0) { p.status[(size_t)h * R + r] = 2 | (min(pos, 0x7FFF) << 16); atomicOr(p.flags, 2); continue; }
+        if (k < 0) { p.status[slot_hr] = 2 | (min(pos, 0x7FFF) << 16); atomicOr(p.flags, 2); continue; }
         if (k == 0) continue;
         int v;
-        const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, p.use_flanks != 0, p.lhs_flank, p.rhs_flank, &v);
+        const CandKind kind = classify_candidate(hv, rv, p.band, pos, p.shortcut != 0, reg.use_flanks != 0, reg.lhs, reg.rhs, &v);
         if (kind == CAND_VALUE) best = min(best, v);
         else if (kind == CAND_DP || kind == CAND_DP_FLANK) {
             if (n_pend == kMaxPending) {      // a long caller-supplied list: queue what has been collected and go on (no pair is truncated)
@@ -879,20 +908,19 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
     }
     if (best == 0) n_pend = 0;
     flush_pending(n_pend);
-    if (best != kBestInf) atomicMin(p.best + (size_t)h * R + r, best);
+    if (best != kBestInf) atomicMin(p.best + slot_hr, best);
 }
 
 
 template <int MAXK, bool FASTQ>
 __global__ void k_populate_generic(const PopParams p)
 {
-    const int H = p.hp.n;
     const int n_list = tile_list(p);
-    const long long total = (long long)n_list * H, step = (long long)gridDim.x * blockDim.x;
+    const long long total = (long long)n_list * p.Hmax, step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-        int li, h;
-        split_index(i, H, &li, &h);
-        populate_one_pair<MAXK, FASTQ>(p, li, h);
+        int li, hl;
+        split_index(i, p.Hmax, &li, &hl);
+        populate_one_pair<MAXK, FASTQ>(p, li, hl);
     }
 }
 
@@ -908,7 +936,6 @@ k_populate_wide(const PopParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = lane / NL, j = lane % NL;
     RowEntry* rows = smem_rows + warp * p.row_stride;
-    const int R = p.rd.n;
     const int n_list = tile_list(p);
     for (;;) {
         int li = 0;
@@ -934,7 +961,7 @@ k_populate_wide(const PopParams p)
             const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
             const Lanes32::Tab tb {tab + p.hp.off[h] + a};
             const uint32_t res = dp_band<Lanes32, C, NL>(rows, L, tb, (uint32_t)p.nuc_prior, j);
-            if (valid && j == 0) atomicMin(p.best + (size_t)h * R + r, (int)res);
+            if (valid && j == 0) atomicMin(p.best + pair_slot(p.rd, h, r), (int)res);
         }
     }
 }
@@ -946,7 +973,6 @@ __global__ void k_slow_flank(const PopParams p, unsigned char* __restrict__ bp)
 {
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(*p.slow_count, p.slow_cap);
-    const int R = p.rd.n;
     for (int i = tid; i < n; i += nthreads) {
         const int4 t = p.slow[i];
         const int r = t.x, h = t.y, a = t.z;
@@ -955,11 +981,12 @@ __global__ void k_slow_flank(const PopParams p, unsigned char* __restrict__ bp)
         const int W = rv.len + 2 * p.band - 1;
         const GenericModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
         int lhs, rhs, fp, fs, ms;
-        window_flanks(a, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+        const RegionInfo reg = p.regs[p.rd.region[r]];
+        window_flanks(a, W, hv.len, reg.lhs, reg.rhs, &lhs, &rhs);
         const int score = generic_align<true, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, bp + tid, (size_t)nthreads,
                                                     lhs, rhs, &fp, &fs, &ms);
         const int v = discount_flank(score, fs, rv.len, ms, fp);
-        if (v != kBestInf) atomicMin(p.best + (size_t)h * R + r, v);
+        if (v != kBestInf) atomicMin(p.best + pair_slot(p.rd, h, r), v);
     }
 }
 
@@ -1146,17 +1173,20 @@ __global__ void k_fill_int(int* __restrict__ p, const long long n, const int v)
 }
 
 // Floating-point epilogue (haplotype_likelihood_model.cpp:285-303): out[h][r] in double.
-__global__ void k_epilogue(const int* __restrict__ best, int* __restrict__ status, const uint8_t* __restrict__ mapq,
-                           const int H, const int R, const int use_mapq, const int mapq_cap, const int mapq_trigger,
-                           double* __restrict__ out)
+__global__ void k_epilogue(const int* __restrict__ best, int* __restrict__ status, const DevReads rd, const RegionInfo* __restrict__ regs,
+                           const int Hmax, const int use_mapq, const int mapq_cap, const int mapq_trigger, double* __restrict__ out)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)H * R) return;
-    int hh, r;
-    split_index(i, R, &hh, &r);
+    // thread t = (haplotype slot, read), reads fastest: consecutive threads write consecutive outputs within a region
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Hmax * rd.n) return;
+    int hl, r;
+    split_index(t, rd.n, &hl, &r);
+    const RegionInfo g = regs[rd.region[r]];
+    if (hl >= g.nH) return;
+    const long long i = pair_slot(rd, g.h0 + hl, r);
     const int b = best[i];
     if (b == kBestInf && status[i] == 0) status[i] = 1;
-    out[i] = finish_likelihood(b, use_mapq != 0, mapq[r], mapq_cap, mapq_trigger);
+    out[i] = finish_likelihood(b, use_mapq != 0, rd.mapq[r], mapq_cap, mapq_trigger);
 }
 
 } // namespace phmm

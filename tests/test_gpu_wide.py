@@ -243,3 +243,32 @@ def test_lean_flank_kernel_geometries(engine, coracle):
                     assert np.array_equal(st[~ok_pairs], wst[~ok_pairs])
                     ok, worst = _close(got[ok_pairs], want[ok_pairs])
                     assert ok, (band, trial, flanks, mapit, worst)
+
+
+def test_populate_regions_equals_one_call_per_region(engine, coracle):
+    """phmm_populate_regions: many small regions (ragged haplotype and read counts, own flank states) in one kernel chain give, region
+    by region, what phmm_populate gives for the region alone — and the oracle's values."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from octopus_b200.batch import concat_blocks
+    rng = np.random.default_rng(83)
+    for band, mapit, dp_only in ((8, False, True), (16, True, False), (16, False, False), (32, True, False), (64, False, True)):
+        hap_blocks, read_blocks, flanks = [], [], []
+        for g in range(int(rng.integers(3, 9))):
+            hap_len = 2 * band + int(rng.choice([200, 260, 330]))
+            h, r = random_region(rng, band, n_haps=int(rng.integers(1, 45)), n_reads=int(rng.integers(1, 70)), hap_len=hap_len,
+                                 read_len_choices=[40, 76, 100, 150], read_n_rate=0.05, edge_reads=(g % 2 == 0))
+            hap_blocks.append(h); read_blocks.append(r)
+            flanks.append((int(rng.integers(0, 80)), int(rng.integers(0, 80))) if g % 3 else None)
+        haps, reads, hf, rf = concat_blocks(hap_blocks, read_blocks)
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=dp_only, map_positions=mapit)
+        flat, off, st = engine.populate_regions(cfg, haps, reads, hf, rf, flank_states=flanks, want_status=True)
+        mats = engine.split_regions(flat, off, hf, rf)
+        sts = engine.split_regions(st, off, hf, rf)
+        for g, (h, r) in enumerate(zip(hap_blocks, read_blocks)):
+            rc, want, wst = coracle.populate(band, h, r, None, flanks[g], dp_only=dp_only, map_positions=mapit)
+            ok_pairs = wst == 0
+            assert np.array_equal(sts[g][~ok_pairs], wst[~ok_pairs]), (band, g)
+            ok, worst = _close(mats[g][ok_pairs], want[ok_pairs])
+            assert ok, (band, mapit, g, worst)
+            one, _ = engine.populate(cfg, h, r, None, flanks[g], want_status=True)
+            assert np.array_equal(one[ok_pairs], mats[g][ok_pairs]), (band, g)
