@@ -182,6 +182,20 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
                      const phmm_positions* positions, const phmm_flank_state* flank,
                      int64_t* mapping_position, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space);
 
+/* hmm::align itself, batched (pair_hmm.hpp:858-874 → try_naive_align :321-340, simd_align :784-823): pair j aligns target
+ * `pairs[j].read` of the `targets` block against truth `pairs[j].hap` of the `truths` block at target offset target_offsets[j] — no
+ * candidate enumeration, no in-range rule. This is the call DeNovoModel makes per (haplotype, haplotype) pair
+ * (core/models/mutation/denovo_model.cpp:249-290: PairHMM<VariableGapExtendMutationModel, 32, int>::align(target, padded given)) and
+ * haplotype_filter's likelihood ranking builds on: pack the padded "given" haplotypes as truths (gap_open / gap_extend arrays; an SNV mask
+ * that matches no base, e.g. 0 bytes, is the no-SNV overload), the "target" haplotypes as targets with every quality = the model's
+ * scalar mismatch penalty (pair_hmm.hpp:853-856), max_indel_error = 32, use_mapping_quality = 0, offset = the band.
+ * Outputs per pair as phmm_align_reads: Alignment::target_offset, likelihood (-ln10/10 * score), CIGAR text; a window that does not fit
+ * gives {0, lowest(), ""} (:802-807); status PHMM_STATUS_HMM_OVERFLOW ↔ HMMOverflow. targets->mapq may be NULL when use_mapping_quality = 0. */
+int phmm_align_pairs(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* truths, const phmm_reads* targets,
+                     const phmm_pair* pairs, const int32_t* target_offsets, int64_t n_pairs, const phmm_flank_state* flank,
+                     int64_t* target_offset_out, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space);
+
 /* Batch boundary: out[h*R + r] == HaplotypeLikelihoodArray likelihoods_[h][sample][r] for a single-sample ReadMap
  * (haplotype_likelihood_array.cpp:77-95). status (optional, [H*R]) receives PHMM_STATUS_*.
  * Returns PHMM_ERR_SHORT_HAPLOTYPE if any pair raised ShortHaplotypeError (the reference throws out of populate). */

@@ -174,6 +174,28 @@ class PairHMMEngine:
         cigars = [bytes(cg[j * cigar_stride:(j + 1) * cigar_stride]).split(b"\0", 1)[0].decode() for j in range(n)]
         return mp, lk, cigars, st
 
+    def align_pairs(self, config, truths: HaplotypeBlock, targets: ReadBlock, pairs, target_offsets, flank_state=None, cigar_stride=None):
+        """hmm::align batched (phmm_align_pairs): pair j = (target pairs[j][0], truth pairs[j][1]) at target_offsets[j]. Host blocks.
+        Returns (target_offset[n], likelihood[n], cigars, status[n])."""
+        assert not truths.on_device and not targets.on_device
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        offs = np.ascontiguousarray(target_offsets, dtype=np.int32)
+        assert len(offs) == n
+        hs, rs, cfg = truths.c_struct(), targets.c_struct(), config.c_struct()
+        if cigar_stride is None:
+            cigar_stride = 4 * int(np.diff(targets.off).max()) + 64
+        fstruct = None if flank_state is None else _lib.FlankState(1, int(flank_state[0]), int(flank_state[1]))
+        mp, lk, st = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.int32)
+        cg = np.zeros(n * cigar_stride, dtype=np.uint8)
+        rc = self._lib.phmm_align_pairs(self._h, C.byref(cfg), C.byref(hs), C.byref(rs), pr.ctypes.data, offs.ctypes.data, n,
+                                        C.byref(fstruct) if fstruct is not None else None,
+                                        mp.ctypes.data, lk.ctypes.data, cg.ctypes.data, cigar_stride, st.ctypes.data, _lib.SPACE_HOST)
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+        cigars = [bytes(cg[j * cigar_stride:(j + 1) * cigar_stride]).split(b"\0", 1)[0].decode() for j in range(n)]
+        return mp, lk, cigars, st
+
     def genotype_likelihoods(self, lnl, genotypes):
         """ConstantMixtureGenotypeLikelihoodModel::evaluate for every row of `genotypes` ((G, ploidy) haplotype indices) over the
         (H, R) matrix `lnl` (numpy on the host, or a torch CUDA tensor left where populate produced it). Returns G doubles."""

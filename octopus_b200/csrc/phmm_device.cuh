@@ -732,6 +732,180 @@ PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Traceback in registers: HaplotypeLikelihoodModel::align / hmm::align need the alignment itself (CIGAR, first_pos)
+// ---------------------------------------------------------------------------------------------------------
+//
+// Round 1 served these through generic_align<true>: row sweep with the band in LOCAL memory and one read-modify-written back-pointer
+// byte per cell in global memory (~64 GCUPS). Here the forward pass is the same register-resident column sweep as dp_flank_acc, on
+// labelled values  [31:16] score  [15:14] label (M 0 < I 1 < D 3, compared as whole words: the reference's tie-breaks,
+// simd_pair_hmm.hpp:147-163)  [13:0] zero, and every cell writes ONE word holding the three labels a backward walk can ask for:
+//   byte 0 = label of S(x, y) << 6          who the match leaving this cell continues (state M at (x+1, y+1) asks its source cell)
+//   byte 1 = label picked for D(x+1, y) << 6    (3: extension of a deletion, 0 / 1: opened from M / I)
+//   byte 2 = label picked for I(x, y+1) << 6    (1: extension, 0: opened from M)
+// (the low 14 bits of every value are zero, so byte 1 of a value IS its label << 6: two PRMTs build the word). Cell (x, k) of a
+// thread lives at bp[(x * 2B + k) * bps]; bps = number of threads sharing the scratch (coalesced stores). The walk is
+// set_alignments + calculate_flank_score fused, as in generic_align (simd_pair_hmm.hpp:165-231, 352-430).
+constexpr uint32_t kTbLabelMask = 3u << 14, kTbLabI = 1u << 14, kTbLabD = 3u << 14;
+constexpr uint32_t kTbInf = 0x7000u << 16;
+constexpr int kMaxScoreTb = 0x7000 - 1024;       // quality-sum bound of this path (16-bit score field)
+
+// .x = PRMT selector: byte 2 <- cap of the read base (codes 0..3: first operand = the column's four caps; 4 = 'N': byte 0 of the second
+// operand), other bytes <- 0 (bytes 1..3 of the second operand); .y = quality << 16
+PHMM_HD RowEntry make_row_entry_tb(uint32_t half) { RowEntry r; r.x = 0x5055u | ((half & 7u) << 8); r.y = (half >> 8) << 16; return r; }
+PHMM_HD RowEntry pad_row_entry_tb() { RowEntry r; r.x = 0x5055u; r.y = 0u; return r; }
+
+// Row entries of the traceback kernel come either as 8-byte RowEntry (tests) or packed in 4 bytes (quality << 16 | code << 8: the
+// kernel stages one read PER THREAD in shared memory, so the footprint decides the occupancy) and are decoded at the use.
+struct TbRows8 { const RowEntry* p; PHMM_HD RowEntry at(const int i) const { return p[i]; } PHMM_HD TbRows8 shifted(const int x) const { return TbRows8 {p + x}; } };
+struct TbRows4
+{
+    const uint32_t* p;
+    PHMM_HD RowEntry at(const int i) const { const uint32_t w = p[i]; RowEntry r; r.x = 0x5055u | (w & 0x700u); r.y = w & 0xFFFF0000u; return r; }
+    PHMM_HD TbRows4 shifted(const int x) const { return TbRows4 {p + x}; }
+    static PHMM_HD uint32_t pack(const uint32_t half) { return ((half >> 8) << 16) | ((half & 7u) << 8); }     // from the read's row half-word (code | qual << 8)
+};
+
+template <int BAND, class RowsT>
+PHMM_HD void dp_traceback_forward(const RowsT rows, const int L, const ColEntry* __restrict__ tab, const int nuc_prior,
+                                  uint32_t* __restrict__ bp, const size_t bps, int* score_out, int* x_end_out, int* state_out)
+{
+    constexpr int K = 2 * BAND;
+    static_assert(K <= 64, "register band limited to 64 diagonals");
+    uint32_t M[K], D[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kTbInf | kTbLabD; }
+    const int W = L + K - 1;
+    ColEntry e = ldg(tab);
+    uint32_t go_prev = 0u, ge_prev = 0u;
+    const RowEntry w0 = rows.at(0);
+    uint32_t best = 0xFFFFFFFFu;
+    int x_end = -1;
+
+#define PHMM_TCELL(k, CAPTURE)                                                                          \
+    {                                                                                                   \
+        const RowEntry w = rp.at(-(k));                                                                    \
+        const uint32_t subw = umin32(w.y, prmt(caps, cap_n, w.x));                                      \
+        const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                              \
+        const uint32_t S = umin3_32(m, i_run, d);                                                       \
+        CAPTURE                                                                                         \
+        M[(k) < K ? (k) : 0] = (S & ~kTbLabelMask) + subw;                                              \
+        const uint32_t Draw = umin3_32(d + geS, m + goS, i_run + goS);                                  \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = Draw | kTbLabD;                               \
+        const uint32_t Iraw = uaddmin32(i_run, gepS, m + gopS);                                         \
+        i_run = Iraw | kTbLabI;                                                                         \
+        bcol[(size_t)((k) < K ? (k) : 0) * bps] = prmt(prmt(S, Draw, 0x1151u), Iraw, 0x4510u);          \
+    }
+#define PHMM_TCASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_TCELL(k, )
+#define PHMM_TCASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
+#define PHMM_TCAPTURE(k) if (k == klo && (S >> 14) < (best >> 14)) { best = S; x_end = x; }
+
+    for (int x = 0; x <= W; ++x) {
+        const int xn = (x + 1 < W) ? x + 1 : W - 1;
+        const ColEntry nx = ldg(tab + xn);
+        const uint32_t caps = e.x, cap_n = (e.y >> 16) & 0xFFu;
+        const uint32_t goS = (e.y & 0xFFu) << 16, geS = ((e.y >> 8) & 0xFFu) << 16;
+        const uint32_t gopS = go_prev + ((uint32_t)nuc_prior << 16), gepS = ge_prev + ((uint32_t)nuc_prior << 16);
+        const RowsT rp = rows.shifted(x);
+        uint32_t* bcol = bp + (size_t)x * K * bps;
+        uint32_t i_run = kTbInf | kTbLabI;
+        if (x >= K) {
+            if (x < L) {
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) PHMM_TCELL(k, )
+            } else {
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    PHMM_TCELL(k, PHMM_TCAPTURE(k))
+                    if (k == klo) break;
+                }
+            }
+        } else {
+            const uint32_t sub0 = umin32(w0.y, prmt(caps, cap_n, w0.x));
+            i_run = (x & 1) ? (gopS | kTbLabI) : (kTbInf | kTbLabI);
+            if (x < L) {
+                switch (x) { PHMM_REP64(PHMM_TCASE_PROLOGUE) default: break; }
+            } else {
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    if (k < x && k >= klo) PHMM_TCELL(k, PHMM_TCAPTURE(k))
+                }
+            }
+            switch (x) { PHMM_REP64(PHMM_TCASE_ROW0) default: break; }
+        }
+        go_prev = goS; ge_prev = geS;
+        const uint32_t z = i_run & 0x8000u;
+        e.x = nx.x + z; e.y = nx.y + z;
+    }
+#undef PHMM_TCELL
+#undef PHMM_TCASE_PROLOGUE
+#undef PHMM_TCASE_ROW0
+#undef PHMM_TCAPTURE
+    *score_out = (int)(best >> 16);
+    *x_end_out = x_end;
+    *state_out = (int)((best >> 14) & 3u);
+}
+
+// The backward walk over the words dp_traceback_forward wrote. Same outputs as generic_align<true>: first_pos (-1 if the path
+// leaves the band), the flank score and in-flank read bases of the forward replay's rules, optionally the two alignment strings.
+struct TbModel { const char* truth; const char* snv_mask; const int8_t* snv_prior; const int8_t* gap_open; const int8_t* gap_extend; int nuc_prior; };
+template <int BAND>
+PHMM_HD void traceback_walk(const uint32_t* __restrict__ bp, const size_t bps, const TbModel& gm, const char* target, const uint8_t* quals, const int L,
+                            int x, int state, const int lhs_flank, const int rhs_flank,
+                            int* first_pos, int* flank_score, int* mask_size, char* align1, char* align2)
+{
+    constexpr int K = 2 * BAND;
+    constexpr int LM = 0, LI = 1, LD = 3;
+    const int W = L + K - 1, rhs_begin = W - rhs_flank;
+    int y = L, fs = 0, ms = 0, n = 0;
+    bool ok = x >= 0;
+    while (ok && y > 0) {
+        int ns;
+        if (state == LM) {
+            --x; --y;
+            const int k = x - y;
+            if (k < 0 || k >= K || x < 0) { ok = false; break; }
+            ns = (int)((bp[((size_t)x * K + k) * bps] >> 6) & 3u);
+            if (align1) { align1[n] = gm.truth[x]; align2[n] = target[y]; }
+            if (x < lhs_flank || x >= rhs_begin) {
+                const char t = gm.truth[x], r = target[y];
+                if (t != r) {
+                    if (t != 'N') { int q = quals[y]; if (gm.snv_mask[x] == r && (int)gm.snv_prior[x] < q) q = (int)gm.snv_prior[x]; fs += q; }
+                    else fs += 2;
+                }
+                ++ms;
+            }
+        } else if (state == LI) {
+            --y;
+            const int k = x - y;
+            if (k < 0 || k >= K) { ok = false; break; }
+            ns = (int)((bp[((size_t)x * K + k) * bps] >> 22) & 3u);
+            if (align1) { align1[n] = '-'; align2[n] = target[y]; }
+            if (x < lhs_flank || x >= rhs_begin) { fs += (ns == LI ? (int)gm.gap_extend[x - 1] : (int)gm.gap_open[x - 1]) + gm.nuc_prior; ++ms; }
+        } else {
+            --x;
+            const int k = x - y;
+            if (k < 0 || k >= K || x < 0) { ok = false; break; }
+            ns = (int)((bp[((size_t)x * K + k) * bps] >> 14) & 3u);
+            if (align1) { align1[n] = gm.truth[x]; align2[n] = '-'; }
+            if (x < lhs_flank || x >= rhs_begin) fs += (ns == LD ? (int)gm.gap_extend[x] : (int)gm.gap_open[x]);
+        }
+        state = ns;
+        ++n;
+    }
+    if (!ok) { *first_pos = -1; *flank_score = 0; *mask_size = 0; if (align1) { align1[0] = 0; align2[0] = 0; } return; }
+    if (align1) {
+        align1[n] = 0; align2[n] = 0;
+        for (int a = 0, b = n - 1; a < b; ++a, --b) {
+            char t = align1[a]; align1[a] = align1[b]; align1[b] = t;
+            t = align2[a]; align2[a] = align2[b]; align2[b] = t;
+        }
+    }
+    *first_pos = x; *flank_score = fs; *mask_size = ms;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Generic path: int32, any band / alphabet, optional traceback + flank replay (one thread per alignment)
 // ---------------------------------------------------------------------------------------------------------
 

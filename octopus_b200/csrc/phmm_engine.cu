@@ -612,25 +612,30 @@ int phmm_genotype_likelihoods(phmm_engine* e, const double* lnl, int32_t H, int3
 // -------------------------------------------------------------------------------------------------------------
 // phmm_align_reads
 // -------------------------------------------------------------------------------------------------------------
-int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
-                     const phmm_haplotypes* haps, const phmm_reads* reads,
-                     const phmm_pair* pairs, int64_t n_pairs,
-                     const phmm_positions* positions, const phmm_flank_state* flank,
-                     int64_t* mapping_position, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space)
+// Shared by phmm_align_reads (HaplotypeLikelihoodModel::align: candidate positions, in-range rule, fallback) and phmm_align_pairs
+// (hmm::align: one explicit offset per pair).
+static int align_impl(phmm_engine* e, const phmm_config* cfg, const phmm_haplotypes* haps, const phmm_reads* reads,
+                      const phmm_pair* pairs, int64_t n_pairs, const phmm_positions* positions, const int32_t* raw_offsets,
+                      const phmm_flank_state* flank,
+                      int64_t* mapping_position, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space)
 {
     if (!e) return PHMM_ERR_INVALID;
     e->err.clear(); e->launches_last = 0; e->last_dp_ms = 0.0; e->last_dp_cells = 0;
     if (cudaSetDevice(e->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return PHMM_ERR_CUDA; }
     if (!cfg || !pairs || !mapping_position || !likelihood || !cigar || !status || cigar_stride < 8) { e->err = "null argument / cigar_stride < 8"; return PHMM_ERR_INVALID; }
     if (cfg->max_indel_error > 256) { e->err = "max_indel_error > 256"; return PHMM_ERR_BAND; }
+    if (cfg->nuc_prior < 0 || cfg->nuc_prior > 127) { e->err = "nuc_prior outside [0,127]"; return PHMM_ERR_INVALID; }
     if (n_pairs < 0 || n_pairs > 0x7fffffff) { e->err = "pair count out of range"; return PHMM_ERR_INVALID; }
     if (n_pairs == 0) return PHMM_OK;
-    if (!reads || !reads->mapq || !reads->reverse) { e->err = "reads->mapq / reads->reverse required"; return PHMM_ERR_INVALID; }
+    if (!reads || !reads->reverse || (!reads->mapq && cfg->use_mapping_quality)) { e->err = "reads->mapq / reads->reverse required"; return PHMM_ERR_INVALID; }
     const int band = round_band(std::max(1, cfg->max_indel_error));
     Staged s;
     int rc = stage_batch(e, haps, reads, space, s);
     if (rc != PHMM_OK) return rc;
     const int n = (int)n_pairs;
+    if (space == PHMM_SPACE_HOST) {      // indices are checked where they are cheap to read
+        for (int i = 0; i < n; ++i) if (pairs[i].read < 0 || pairs[i].read >= s.rd.n || pairs[i].hap < 0 || pairs[i].hap >= s.hp.n) { e->err = "pair index out of range"; return PHMM_ERR_INVALID; }
+    }
     AlignParams p {};
     p.hp = s.hp; p.rd = s.rd; p.n_pairs = n;
     p.band = band; p.nuc_prior = cfg->nuc_prior;
@@ -641,7 +646,11 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
     const int2* d_pairs;
     if ((rc = stage(e, e->pairs, (const int2*)pairs, (size_t)n, space, &d_pairs))) return rc;
     p.pairs = d_pairs;
-    if (positions && positions->off && positions->pos) {
+    if (raw_offsets) {
+        const int32_t* pv;
+        if ((rc = stage(e, e->c_pos, raw_offsets, (size_t)n, space, &pv))) return rc;
+        p.pos = pv; p.raw_offsets = 1;
+    } else if (positions && positions->off && positions->pos) {
         std::vector<long long> ends(1);
         if (space == PHMM_SPACE_HOST) ends[0] = positions->off[n];
         else { CU(cudaMemcpyAsync(ends.data(), positions->off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream)); CU(cudaStreamSynchronize(e->stream)); }
@@ -652,11 +661,37 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
     }
     int Lmax = 1;
     for (int r = 0; r < s.rd.n; ++r) Lmax = std::max(Lmax, e->info_host[r].x);
-    const int threads_total = std::min(e->sm_count * 256, ((n + 63) / 64) * 64);
+    // Register traceback for bands up to 32 (one thread per pair, its read in shared memory, one back-pointer word per cell);
+    // the generic kernel for wider bands and the reads the register kernel cannot take.
+    const int K = 2 * band;
+    p.fast_band = band <= 32 ? band : 0;
+    const int fast_cap = (int)((200 << 10) / (kAlignFastThreads * (int)sizeof(uint32_t))) - 2;      // one block's rows in shared memory
+    p.fast_max_len = std::min(Lmax, fast_cap);
+    p.fast_row_stride = (p.fast_max_len + 1) | 1;
+    const size_t fsmem = (size_t)kAlignFastThreads * p.fast_row_stride * sizeof(uint32_t);
+    int fast_blocks_per_sm = 1;
+    if (p.fast_band) {
+        switch (band) {
+            case 8:  if ((rc = fast_smem_attr(e, k_align_reads_fast<8>, fsmem)) || (rc = blocks_per_sm_of(e, k_align_reads_fast<8>, kAlignFastThreads, fsmem, &fast_blocks_per_sm))) return rc; break;
+            case 16: if ((rc = fast_smem_attr(e, k_align_reads_fast<16>, fsmem)) || (rc = blocks_per_sm_of(e, k_align_reads_fast<16>, kAlignFastThreads, fsmem, &fast_blocks_per_sm))) return rc; break;
+            default: if ((rc = fast_smem_attr(e, k_align_reads_fast<32>, fsmem)) || (rc = blocks_per_sm_of(e, k_align_reads_fast<32>, kAlignFastThreads, fsmem, &fast_blocks_per_sm))) return rc; break;
+        }
+        if (fast_blocks_per_sm < 1) p.fast_band = 0;
+    }
+    // threads: bounded by the pairs and by the scratch budgets (byte back-pointers of the generic kernel; words of the register kernel)
+    const long long words_per_thread = (long long)(p.fast_max_len + K) * K;
+    int fast_threads = p.fast_band ? std::min(e->sm_count * fast_blocks_per_sm * kAlignFastThreads, ((n + kAlignFastThreads - 1) / kAlignFastThreads) * kAlignFastThreads) : 0;
+    if (p.fast_band) fast_threads = (int)std::max<long long>(kAlignFastThreads, std::min<long long>(fast_threads, ((6LL << 30) / (4 * words_per_thread)) / kAlignFastThreads * kAlignFastThreads));
+    const long long bp_per_thread = (long long)(Lmax + 1) * K;
+    int slow_threads = std::min(e->sm_count * 256, ((n + 63) / 64) * 64);
+    slow_threads = (int)std::max<long long>(64, std::min<long long>(slow_threads, ((4LL << 30) / bp_per_thread) / 64 * 64));
+    const int threads_total = std::max(fast_threads, slow_threads);
     p.str_cap = 2 * (Lmax + band) + 2;
-    CU(e->bp.ensure((size_t)threads_total * (size_t)(Lmax + 1) * (size_t)(2 * band)));
+    CU(e->bp.ensure((size_t)slow_threads * (size_t)bp_per_thread));
+    if (p.fast_band) CU(e->ftasks.ensure((size_t)fast_threads * (size_t)words_per_thread * sizeof(uint32_t)));
     CU(e->slow.ensure((size_t)threads_total * 4 * p.str_cap));
     p.bp = e->bp.as<unsigned char>();
+    p.bp32 = e->ftasks.as<uint32_t>();
     p.strings = e->slow.as<char>();
     // outputs
     const bool dev = space == PHMM_SPACE_DEVICE;
@@ -669,10 +704,23 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
     p.status = dev ? status : e->status.as<int>();
     p.cigar = dev ? cigar : e->kpos.as<char>();
     p.cigar_stride = cigar_stride;
-    const unsigned grid = (unsigned)(threads_total / 64);
-    if (band <= 32) k_align_reads<64><<<grid, 64, 0, e->stream>>>(p);
-    else k_align_reads<kGenericMaxDiag><<<grid, 64, 0, e->stream>>>(p);
-    LAUNCHED();
+    CU(cudaEventRecord(e->ev0, e->stream));
+    if (p.fast_band) {
+        const unsigned fgrid = (unsigned)(fast_threads / kAlignFastThreads);
+        switch (band) {
+            case 8:  k_align_reads_fast<8><<<fgrid, kAlignFastThreads, fsmem, e->stream>>>(p); break;
+            case 16: k_align_reads_fast<16><<<fgrid, kAlignFastThreads, fsmem, e->stream>>>(p); break;
+            default: k_align_reads_fast<32><<<fgrid, kAlignFastThreads, fsmem, e->stream>>>(p); break;
+        }
+        LAUNCHED();
+    }
+    {
+        const unsigned grid = (unsigned)(slow_threads / 64);
+        if (band <= 32) k_align_reads<64><<<grid, 64, 0, e->stream>>>(p);
+        else k_align_reads<kGenericMaxDiag><<<grid, 64, 0, e->stream>>>(p);
+        LAUNCHED();
+    }
+    CU(cudaEventRecord(e->ev1, e->stream));
     CU(cudaGetLastError());
     if (!dev) {
         CU(cudaMemcpyAsync(mapping_position, p.mapping_position, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
@@ -681,7 +729,28 @@ int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
         CU(cudaMemcpyAsync(cigar, p.cigar, (size_t)n * cigar_stride, cudaMemcpyDeviceToHost, e->stream));
     }
     CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_dp_ms = ms;
     return PHMM_OK;
+}
+
+int phmm_align_reads(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* haps, const phmm_reads* reads,
+                     const phmm_pair* pairs, int64_t n_pairs,
+                     const phmm_positions* positions, const phmm_flank_state* flank,
+                     int64_t* mapping_position, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space)
+{
+    return align_impl(e, cfg, haps, reads, pairs, n_pairs, positions, nullptr, flank, mapping_position, likelihood, cigar, cigar_stride, status, space);
+}
+
+int phmm_align_pairs(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* truths, const phmm_reads* targets,
+                     const phmm_pair* pairs, const int32_t* target_offsets, int64_t n_pairs, const phmm_flank_state* flank,
+                     int64_t* target_offset_out, double* likelihood, char* cigar, int32_t cigar_stride, int32_t* status, int space)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    if (!target_offsets) { e->err = "null target offsets"; return PHMM_ERR_INVALID; }
+    return align_impl(e, cfg, truths, targets, pairs, n_pairs, nullptr, target_offsets, flank, target_offset_out, likelihood, cigar, cigar_stride, status, space);
 }
 
 // -------------------------------------------------------------------------------------------------------------

@@ -692,13 +692,9 @@ k_populate_fast(const PopParams p)
             const int h0 = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1 = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
             const uint32_t res = packed_dp<BAND>(rows, L, b0 + p.hp.off[h0] + a0, b1 + p.hp.off[h1] + a1, nucp, jl);
             if (jl == 0) {
-                if (p.single_candidate) {       // at most one candidate per pair: its value IS the pair's minimum — a plain store, no read of best[]
-                    if (v0) p.best[pair_slot(p.rd, h0, r0)] = (int)(res & 0xFFFFu);
-                    if (v1) p.best[pair_slot(p.rd, h1, r1)] = (int)(res >> 16);
-                } else {
-                    if (v0) atomicMin(p.best + pair_slot(p.rd, h0, r0), (int)(res & 0xFFFFu));
-                    if (v1) atomicMin(p.best + pair_slot(p.rd, h1, r1), (int)(res >> 16));
-                }
+                // at most one candidate per pair (single_candidate): its value IS the pair's minimum — a plain store, no read of best[]
+                if (v0) { int* dst = p.best + pair_slot(p.rd, h0, r0); const int v = (int)(res & 0xFFFFu); if (p.single_candidate) *dst = v; else atomicMin(dst, v); }
+                if (v1) { int* dst = p.best + pair_slot(p.rd, h1, r1); const int v = (int)(res >> 16); if (p.single_candidate) *dst = v; else atomicMin(dst, v); }
             }
         }
     }
@@ -1025,6 +1021,10 @@ struct AlignParams {
     unsigned char* bp;          // interleaved back-pointer scratch: cell c of thread t at bp[c * nthreads + t]
     char* strings;              // per thread 4 * str_cap bytes
     int str_cap;
+    int raw_offsets;            // 1: hmm::align semantics — pos[i] is pair i's target offset (phmm_align_pairs)
+    // register traceback kernel (k_align_reads_fast): 0 = unused, else its band; longest read it takes; shared row stride; word scratch
+    int fast_band, fast_max_len, fast_row_stride;
+    uint32_t* bp32;
 };
 
 __device__ __forceinline__ int cigar_emit(char* out, int w, const int cap, int len, const char op)
@@ -1057,72 +1057,130 @@ __device__ inline bool make_cigar_text(const char* a1, const char* a2, char* out
     return w < cap - 1;
 }
 
+// One pair of the align list. RunDP(hv, rv, a, lhs, rhs, &fp, &fs, &ms, cur1, cur2) -> score runs the traceback DP of the window at
+// offset a and leaves the two alignment strings in cur1 / cur2 (fp == -1: the path left the band).
+// p.raw_offsets != 0 selects hmm::align itself (pair_hmm.hpp:858-874: ONE explicit target offset per pair — pos[i] — no in-range rule,
+// no fallback; what DeNovoModel / haplotype_filter call): a window that does not fit yields {offset 0, lowest(), empty CIGAR}.
+template <typename RunDP>
+__device__ __forceinline__ void align_pair(const AlignParams& p, const int i, char* s0, RunDP&& run_dp)
+{
+    const int r = p.pairs[i].x, h = p.pairs[i].y;
+    const HapView hv = hap_view(p.hp, h, p.rd.reverse[r] != 0);
+    const ReadView rv = read_view(p.rd, r);
+    const long long orig = (p.rd.begin ? p.rd.begin[r] : 0) - (p.hp.begin ? p.hp.begin[h] : 0);
+    int npos = 0;
+    const int32_t* pp = nullptr;
+    if (p.pos_off) { const long long o = p.pos_off[i]; npos = (int)(p.pos_off[i + 1] - o); pp = p.pos + o; }
+    char *cur1 = s0, *cur2 = s0 + p.str_cap, *best1 = s0 + 2 * p.str_cap, *best2 = s0 + 3 * p.str_cap;
+    EnumState st {false, false};
+    int best = kBestInf, status = 0;
+    long long best_off = 0;
+    bool best_exact = false, have = false;
+    const int n_slots = p.raw_offsets ? 1 : npos + 2;
+    for (int c = 0; c < n_slots && status == 0; ++c) {
+        int pos;
+        if (p.raw_offsets) pos = p.pos[i];
+        else {
+            const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
+            if (k < 0) { status = 2 | (min(pos, 0x7FFF) << 16); break; }
+            if (k == 0) continue;
+        }
+        int v; long long off; bool exact = false;
+        bool eq = pos >= 0 && pos + rv.len <= hv.len;                         // try_naive_align (:321-340)
+        for (int a = 0; eq && a < rv.len; ++a) if (rv.bases[a] != hv.seq[pos + a]) eq = false;
+        if (eq) { v = 0; off = pos; exact = true; }
+        else {
+            const int W = rv.len + 2 * p.band - 1;
+            const int a = pos - p.band > 0 ? pos - p.band : 0;
+            if (pos < 0 || a + W > hv.len) { v = kBestInf; off = 0; cur1[0] = 0; cur2[0] = 0; }          // :802-807
+            else {
+                const bool near_flank = p.use_flanks && (pos < p.lhs_flank + p.band || pos + rv.len + p.band > hv.len - p.rhs_flank);
+                int lhs = 0, rhs = 0, fp, fs, ms;
+                if (near_flank) window_flanks(a, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
+                int score = run_dp(hv, rv, a, lhs, rhs, &fp, &fs, &ms, cur1, cur2);
+                if (fp == -1) { status = 4; break; }                                             // HMMOverflow (:815-817)
+                if (near_flank) { if (rv.len - ms < 2) fs = 0; score = fs <= score ? score - fs : score + fs; }   // :659-672
+                v = score; off = (long long)pos - p.band + fp;                                    // :820
+            }
+        }
+        // :355 listed positions win on '>', :365 the original position on '>=', :388-391 the fallback unconditionally
+        const bool take = p.raw_offsets ? true : (c < npos ? (v < best) : (c == npos ? (v <= best) : true));
+        if (take || !have) {
+            if (take) {
+                best = v; best_off = off; best_exact = exact; have = true;
+                char* t = cur1; cur1 = best1; best1 = t; t = cur2; cur2 = best2; best2 = t;
+            }
+        }
+    }
+    p.status[i] = status;
+    char* cg = p.cigar + (size_t)i * p.cigar_stride;
+    cg[0] = 0;
+    if (status == 0) {
+        p.mapping_position[i] = best_off;
+        p.likelihood[i] = finish_likelihood(best, p.use_mapq != 0, p.rd.mapq ? p.rd.mapq[r] : 0, p.mapq_cap, p.mapq_trigger);
+        bool ok = true;
+        if (best_exact) { const int w = cigar_emit(cg, 0, p.cigar_stride, rv.len, '='); cg[w] = 0; }
+        else if (best != kBestInf) ok = make_cigar_text(best1, best2, cg, p.cigar_stride);
+        if (!ok) p.status[i] = 3;
+    } else {
+        p.mapping_position[i] = 0;
+        p.likelihood[i] = -1.7976931348623157e308;
+    }
+}
+
+// Reads the register traceback can take: alphabet ACGTN, qualities <= 127, quality sum inside the 16-bit score field, row entries
+// of every thread of a block in shared memory.
+__device__ __forceinline__ bool align_fast_ok(const AlignParams& p, const int r)
+{
+    const int2 inf = p.rd.info[r];
+    return p.fast_band != 0 && (inf.y & (kReadNonACGT | kReadBadQual | kReadUnsafe16)) == 0 && inf.x >= 1 && inf.x <= p.fast_max_len;
+}
+
+// Generic traceback (any band / alphabet): one thread per pair, band in local memory, byte back-pointers. Serves what the register
+// kernel below cannot take.
 template <int MAXK>
 __global__ void k_align_reads(const AlignParams p)
 {
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     char* s0 = p.strings + (size_t)tid * 4 * p.str_cap;
     for (int i = tid; i < p.n_pairs; i += nthreads) {
-        const int r = p.pairs[i].x, h = p.pairs[i].y;
-        const HapView hv = hap_view(p.hp, h, p.rd.reverse[r] != 0);
-        const ReadView rv = read_view(p.rd, r);
-        const long long orig = (p.rd.begin ? p.rd.begin[r] : 0) - (p.hp.begin ? p.hp.begin[h] : 0);
-        int npos = 0;
-        const int32_t* pp = nullptr;
-        if (p.pos_off) { const long long o = p.pos_off[i]; npos = (int)(p.pos_off[i + 1] - o); pp = p.pos + o; }
-        char *cur1 = s0, *cur2 = s0 + p.str_cap, *best1 = s0 + 2 * p.str_cap, *best2 = s0 + 3 * p.str_cap;
-        EnumState st {false, false};
-        int best = kBestInf, status = 0;
-        long long best_off = 0;
-        bool best_exact = false, have = false;
-        for (int c = 0; c < npos + 2 && status == 0; ++c) {
-            int pos;
-            const int k = candidate_slot(c, npos, pp, orig, rv.len, hv.len, p.band, st, &pos);
-            if (k < 0) { status = 2 | (min(pos, 0x7FFF) << 16); break; }
-            if (k == 0) continue;
-            int v; long long off; bool exact = false;
-            bool eq = true;                                                   // try_naive_align (:321-340)
-            for (int a = 0; a < rv.len; ++a) if (rv.bases[a] != hv.seq[pos + a]) { eq = false; break; }
-            if (eq) { v = 0; off = pos; exact = true; }
-            else {
-                const int W = rv.len + 2 * p.band - 1;
-                const int a = pos - p.band > 0 ? pos - p.band : 0;
-                if (a + W > hv.len) { v = kBestInf; off = 0; cur1[0] = 0; cur2[0] = 0; }          // :802-807
-                else {
-                    const GenericModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
-                    const bool near_flank = p.use_flanks && (pos < p.lhs_flank + p.band || pos + rv.len + p.band > hv.len - p.rhs_flank);
-                    int lhs = 0, rhs = 0, fp, fs, ms;
-                    if (near_flank) window_flanks(a, W, hv.len, p.lhs_flank, p.rhs_flank, &lhs, &rhs);
-                    int score = generic_align<true, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, p.bp + tid, (size_t)nthreads,
-                                                          lhs, rhs, &fp, &fs, &ms, cur1, cur2);
-                    if (fp == -1) { status = 4; break; }                                             // HMMOverflow (:815-817)
-                    if (near_flank) { if (rv.len - ms < 2) fs = 0; score = fs <= score ? score - fs : score + fs; }   // :659-672
-                    v = score; off = (long long)pos - p.band + fp;                                    // :820
-                }
-            }
-            // :355 listed positions win on '>', :365 the original position on '>=', :388-391 the fallback unconditionally
-            const bool take = c < npos ? (v < best) : (c == npos ? (v <= best) : true);
-            if (take || !have) {
-                if (take) {
-                    best = v; best_off = off; best_exact = exact; have = true;
-                    char* t = cur1; cur1 = best1; best1 = t; t = cur2; cur2 = best2; best2 = t;
-                }
-            }
+        if (align_fast_ok(p, p.pairs[i].x)) continue;            // k_align_reads_fast's
+        align_pair(p, i, s0, [&](const HapView& hv, const ReadView& rv, const int a, const int lhs, const int rhs, int* fp, int* fs, int* ms, char* c1, char* c2) {
+            const GenericModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
+            return generic_align<true, MAXK>(p.band, gm, rv.bases, (const int8_t*)rv.quals, rv.len, p.bp + tid, (size_t)nthreads, lhs, rhs, fp, fs, ms, c1, c2);
+        });
+    }
+}
+
+// Register traceback (dp_traceback_forward + traceback_walk): one thread per pair, the band in registers, one back-pointer word
+// per cell (coalesced across the threads), the thread's read staged in shared memory.
+constexpr int kAlignFastThreads = 64;
+template <int BAND>
+__global__ void __launch_bounds__(kAlignFastThreads)
+k_align_reads_fast(const AlignParams p)
+{
+    extern __shared__ uint32_t smem_rows32[];
+    uint32_t* rows = smem_rows32 + (size_t)threadIdx.x * p.fast_row_stride;     // stride odd: the threads of a warp hit distinct banks
+    const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    char* s0 = p.strings + (size_t)tid * 4 * p.str_cap;
+    for (int i = tid; i < p.n_pairs; i += nthreads) {
+        const int r = p.pairs[i].x;
+        if (!align_fast_ok(p, r)) continue;
+        {
+            const long long ro = p.rd.off[r];
+            const int L = p.rd.info[r].x;
+            for (int y = 0; y < L; ++y) rows[y] = TbRows4::pack(p.rd.rowhalf[ro + y]);
+            rows[L] = 0u;                                                        // the pad row: code 0, quality 0
         }
-        p.status[i] = status;
-        char* cg = p.cigar + (size_t)i * p.cigar_stride;
-        cg[0] = 0;
-        if (status == 0) {
-            p.mapping_position[i] = best_off;
-            p.likelihood[i] = finish_likelihood(best, p.use_mapq != 0, p.rd.mapq[r], p.mapq_cap, p.mapq_trigger);
-            bool ok = true;
-            if (best_exact) { const int w = cigar_emit(cg, 0, p.cigar_stride, rv.len, '='); cg[w] = 0; }
-            else if (best != kBestInf) ok = make_cigar_text(best1, best2, cg, p.cigar_stride);
-            if (!ok) p.status[i] = 3;
-        } else {
-            p.mapping_position[i] = 0;
-            p.likelihood[i] = -1.7976931348623157e308;
-        }
+        const ColEntry* tabs = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const int h = p.pairs[i].y;
+        align_pair(p, i, s0, [&](const HapView& hv, const ReadView& rv, const int a, const int lhs, const int rhs, int* fp, int* fs, int* ms, char* c1, char* c2) {
+            int score, x_end, state;
+            dp_traceback_forward<BAND>(TbRows4 {rows}, rv.len, tabs + p.hp.off[h] + a, p.nuc_prior, p.bp32 + tid, (size_t)nthreads, &score, &x_end, &state);
+            const TbModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
+            traceback_walk<BAND>(p.bp32 + tid, (size_t)nthreads, gm, rv.bases, rv.quals, rv.len, x_end, state, lhs, rhs, fp, fs, ms, c1, c2);
+            return score;
+        });
     }
 }
 

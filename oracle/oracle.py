@@ -361,6 +361,21 @@ class RefHMM:
         return off.value, lk.value, cig.value.decode()
 
 
+    def align_mutation_model(self, truth, target, mismatch, gap_open, gap_extend):
+        """hmm::PairHMM<VariableGapExtendMutationModel, 32, int>::align(target, truth) (DeNovoModel's call). Returns (rc, target_offset, likelihood, cigar)."""
+        t, r = _b(truth), _b(target)
+        go, gop = _i8(gap_open)
+        ge, gep = _i8(gap_extend)
+        off, lk = C.c_longlong(0), C.c_double(0)
+        cap = 8 * (len(r) + 128) + 64
+        cig = C.create_string_buffer(cap)
+        f = self.lib.ref_hmm_align_mutation_model
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, _i8p, _i8p, C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.c_char_p, C.c_int]
+        rc = f(t, len(t) - 1, r, len(r) - 1, int(mismatch), gop, gep, C.byref(off), C.byref(lk), cig, cap)
+        return rc, off.value, lk.value, cig.value.decode()
+
+
 class _Model(C.Structure):
     _fields_ = [("snv_mask", C.c_char_p), ("snv_prior", _i8p), ("gap_open", _i8p), ("gap_extend", _i8p),
                 ("gap_open_scalar", C.c_int), ("gap_extend_scalar", C.c_int), ("nuc_prior", C.c_int)]

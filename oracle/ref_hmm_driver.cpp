@@ -113,6 +113,29 @@ int ref_hmm_align(int min_band, int use_int32, const char* truth, int truth_len,
 // The candidate-position mapping HaplotypeLikelihoodArray::populate makes per (read, haplotype)
 // (haplotype_likelihood_array.cpp:76-93): hashes of the read, hash table + vote counts of the haplotype,
 // map_query_to_target(..., maxMappingPositions). Returns the number of positions written.
+// DeNovoModel's call (core/models/mutation/denovo_model.cpp:249-262): hmm::PairHMM<VariableGapExtendMutationModel, 32, int> — no SNV mask, a scalar
+// mismatch penalty in place of base qualities, gap_open / gap_extend arrays — align(target, padded given) at offset = band (pair_hmm.hpp:876-890).
+// Returns 0, 1 if the CIGAR does not fit, 2 on HMMOverflow.
+int ref_hmm_align_mutation_model(const char* truth, int truth_len, const char* target, int target_len, int mismatch,
+                                 const std::int8_t* gap_open, const std::int8_t* gap_extend,
+                                 long long* out_target_offset, double* out_likelihood, char* cigar, int cigar_cap)
+{
+    const std::string tr(truth, truth + truth_len), tg(target, target + target_len);
+    const PenaltyVector go(gap_open, gap_open + truth_len), ge(gap_extend, gap_extend + truth_len);
+    const VariableGapExtendMutationModel params {go, ge, {}, {}, static_cast<Penalty>(mismatch)};
+    octopus::hmm::PairHMM<VariableGapExtendMutationModel, 32, int> hmm {};
+    hmm.set(params);
+    Alignment result {};
+    try { hmm.align(tg, tr, result); } catch (const HMMOverflow&) { return 2; }
+    *out_target_offset = static_cast<long long>(result.target_offset);
+    *out_likelihood = result.likelihood;
+    std::string text;
+    for (const auto& op : result.cigar) { text += std::to_string(op.size()); text += static_cast<char>(op.flag()); }
+    if (static_cast<int>(text.size()) + 1 > cigar_cap) return 1;
+    std::memcpy(cigar, text.c_str(), text.size() + 1);
+    return 0;
+}
+
 int ref_kmer_map(const char* query, int query_len, const char* target, int target_len, int max_positions, long long* out_positions)
 {
     constexpr unsigned char K = 6;                        // HaplotypeLikelihoodArray::mapperKmerSize (haplotype_likelihood_array.hpp:103)

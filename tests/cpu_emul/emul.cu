@@ -242,3 +242,33 @@ extern "C" int emul_dp_flank_acc(int band, int L, const char* read, const uint8_
     }
     return 0;
 }
+
+// dp_traceback_forward + traceback_walk on the CPU: score, first_pos, flank score, in-flank read bases and the two alignment strings.
+extern "C" int emul_traceback(int band, int L, const char* read, const uint8_t* q, const char* truth, const char* mask, const int8_t* prior,
+                              const int8_t* go, const int8_t* ge, int nuc_prior, int lhs_flank, int rhs_flank,
+                              int* score, int* first_pos, int* flank, int* mask_size, char* align1, char* align2)
+{
+    const int W = L + 2 * band - 1;
+    std::vector<RowEntry> rows(L + 1);
+    for (int y = 0; y < L; ++y) {
+        const int c = base_code(read[y]);
+        if (c < 0) return -1;
+        rows[y] = make_row_entry_tb((uint32_t)c | ((uint32_t)q[y] << 8));
+    }
+    rows[L] = pad_row_entry_tb();
+    std::vector<ColEntry> t(W);
+    for (int x = 0; x < W; ++x) t[x] = make_col_entry(truth[x], mask[x], prior[x], go[x], ge[x]);
+    std::vector<uint32_t> bp((size_t)(W + 1) * 2 * band, 0u);
+    int x_end = -1, state = 0;
+    const TbModel gm {truth, mask, prior, go, ge, nuc_prior};
+    switch (band) {
+        case 8:  dp_traceback_forward<8>(TbRows8 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
+                 traceback_walk<8>(bp.data(), 1, gm, read, q, L, x_end, state, lhs_flank, rhs_flank, first_pos, flank, mask_size, align1, align2); break;
+        case 16: dp_traceback_forward<16>(TbRows8 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
+                 traceback_walk<16>(bp.data(), 1, gm, read, q, L, x_end, state, lhs_flank, rhs_flank, first_pos, flank, mask_size, align1, align2); break;
+        case 32: dp_traceback_forward<32>(TbRows8 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
+                 traceback_walk<32>(bp.data(), 1, gm, read, q, L, x_end, state, lhs_flank, rhs_flank, first_pos, flank, mask_size, align1, align2); break;
+        default: return -1;
+    }
+    return 0;
+}

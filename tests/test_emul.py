@@ -211,3 +211,29 @@ def test_lean_flank_dp_matches_traceback_flank_replay(emul, coracle):
         assert L - ems >= 2, (band, L, lhs, rhs, ems)          # the guarantee the kernel relies on
         assert (sc.value, fl.value) == (es, efs), (band, L, lhs, rhs)
     assert n_used > 800
+
+
+def test_register_traceback_matches_oracle(emul, coracle):
+    """dp_traceback_forward + traceback_walk (register-band forward pass writing one back-pointer word per cell, backward walk) ==
+    the oracle's traceback: score, first_pos, both alignment strings, flank score and in-flank read bases; reads with 'N' included."""
+    emul.emul_traceback.argtypes = [C.c_int, C.c_int] + [vp] * 7 + [C.c_int, C.c_int, C.c_int] + [vp] * 6
+    rng = np.random.default_rng(29)
+    for it in range(1500):
+        band = int(rng.choice([8, 16, 32]))
+        L = int(rng.integers(1, 180))
+        nuc = int(rng.integers(0, 5))
+        c = random_alignment_case(rng, band, L, read_n=(it % 4 == 0))
+        W = len(c["truth"])
+        lhs, rhs = (int(rng.integers(0, W + 1)), int(rng.integers(0, W + 1))) if it % 2 else (0, 0)
+        sc, fp, fl, ms = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        n = 2 * (L + band) + 8
+        a1, a2 = C.create_string_buffer(n), C.create_string_buffer(n)
+        rc = emul.emul_traceback(band, L, P(c["read"]), P(c["quals"]), P(c["truth"]), P(c["snv_mask"]), P(c["snv_prior"]), P(c["gap_open"]),
+                                 P(c["gap_extend"]), nuc, lhs, rhs, C.byref(sc), C.byref(fp), C.byref(fl), C.byref(ms), a1, a2)
+        assert rc == 0
+        q8 = c["quals"].astype(np.int8)
+        t, r, m = c["truth"].tobytes(), c["read"].tobytes(), c["snv_mask"].tobytes()
+        es, efp, e1, e2 = coracle.align_tb(band, t, r, q8, c["gap_open"], c["gap_extend"], nuc, m, c["snv_prior"])
+        efs, ems = coracle.flank_score(W, lhs, rhs, r, q8, m, c["snv_prior"], c["gap_open"], c["gap_extend"], nuc, efp, e1, e2)
+        assert (sc.value, fp.value, a1.value.decode(), a2.value.decode()) == (es, efp, e1, e2), (band, L)
+        assert (fl.value, ms.value) == (efs, ems), (band, L, lhs, rhs)

@@ -272,3 +272,77 @@ def test_populate_regions_equals_one_call_per_region(engine, coracle):
             assert ok, (band, mapit, g, worst)
             one, _ = engine.populate(cfg, h, r, None, flanks[g], want_status=True)
             assert np.array_equal(one[ok_pairs], mats[g][ok_pairs]), (band, g)
+
+
+def test_align_reads_register_traceback_and_fallbacks(engine, coracle):
+    """phmm_align_reads with the register traceback kernel (bands <= 32) and the generic kernel side by side: long reads beyond the
+    register kernel's shared-memory budget, reads with 'N', wide bands — each pair against HaplotypeLikelihoodModel::align (oracle)."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from test_gpu_parity import REL_TOL
+    rng = np.random.default_rng(97)
+    for band_req, lens, hap_len in ((8, [30, 76], 300), (16, [76, 150, 900], 1200), (32, [100, 250], 600), (64, [100, 150], 500)):
+        band = HaplotypeLikelihoodModel(HaplotypeLikelihoodModel.Config(max_indel_error=band_req)).pad_requirement()
+        haps, reads = random_region(rng, band, n_haps=5, n_reads=50, hap_len=hap_len, read_len_choices=lens, read_n_rate=0.15, edge_reads=True)
+        pairs = np.array([(int(rng.integers(0, reads.n)), int(rng.integers(0, haps.n))) for _ in range(250)], dtype=np.int32)
+        lists, off = [], [0]
+        for r, h in pairs:
+            p0 = int(reads.begin[r])
+            ps = sorted({int(np.clip(p0 + rng.integers(-10, 11), 0, haps.length(h))) for _ in range(int(rng.integers(0, 4)))})
+            lists.extend(ps); off.append(len(lists))
+        positions = (np.asarray(off, np.int64), np.asarray(lists if lists else [0], np.int32))
+        flanks = (int(rng.integers(0, 80)), int(rng.integers(0, 80))) if band_req != 16 else None
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req)
+        mp, lk, cig, st = engine.align_reads(cfg, haps, reads, pairs, positions, flanks)
+        for j, (r, h) in enumerate(pairs):
+            hp = haps.hap(int(h)); b, q = reads.read(int(r)); rev = bool(reads.reverse[r])
+            wst, wmp, wlk, wcig, wext = coracle.model_align(band, hp["seq"].tobytes(), b.tobytes(), q, hp["gap_open"], hp["gap_extend"],
+                                                            hp["snv_mask_rev" if rev else "snv_mask_fwd"].tobytes(), hp["snv_prior_rev" if rev else "snv_prior_fwd"],
+                                                            positions[1][off[j]:off[j + 1]], int(reads.begin[r]), mapping_quality=int(reads.mapq[r]), flanks=flanks)
+            if wst == 1:
+                assert (st[j] & 0xFFFF) == 2 and (st[j] >> 16) == wext
+                continue
+            assert wst == 0 and st[j] == 0, (band_req, j, wst, st[j])
+            assert mp[j] == wmp and cig[j] == wcig, (band_req, j, mp[j], wmp, cig[j], wcig)
+            assert abs(lk[j] - wlk) <= REL_TOL * max(abs(wlk), 1e-300)
+
+
+def test_align_pairs_equals_the_mutation_model_hmm(engine, refhmm):
+    """N4: phmm_align_pairs on (target haplotype, padded given haplotype) pairs == hmm::PairHMM<VariableGapExtendMutationModel, 32, int>::align,
+    the call DeNovoModel makes (denovo_model.cpp:249-262): no SNV mask, scalar mismatch penalty, band 32, offset = band."""
+    if refhmm is None:
+        pytest.skip("oracle/_ref/libref_hmm.so not present")
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from octopus_b200.batch import pack_haplotypes, pack_reads
+    rng = np.random.default_rng(101)
+    band, mismatch = 32, 40
+    truths, targets, pairs = [], [], []
+    base = ACGT[rng.integers(0, 4, 260)]
+    for h in range(12):
+        s = base.copy()
+        for _ in range(int(rng.integers(0, 4))):
+            s[rng.integers(0, len(s))] = ACGT[rng.integers(0, 4)]
+        if h % 3 == 1:
+            i = int(rng.integers(20, 200)); s = np.concatenate([s[:i], s[i + int(rng.integers(1, 8)):]])
+        if h % 3 == 2:
+            i = int(rng.integers(20, 200)); s = np.concatenate([s[:i], ACGT[rng.integers(0, 4, int(rng.integers(1, 8)))], s[i:]])
+        targets.append(s)
+        truths.append(np.concatenate([np.full(band, ord("N"), np.uint8), s, np.full(band, ord("N"), np.uint8)]))     # pad_given (denovo_model.cpp:206-220)
+    go = [rng.integers(20, 60, len(t)).astype(np.int8) for t in truths]
+    ge = [rng.integers(1, 11, len(t)).astype(np.int8) for t in truths]
+    tb = pack_haplotypes(truths, [np.zeros(len(t), np.uint8) for t in truths], [np.full(len(t), 100, np.int8) for t in truths],
+                         [np.zeros(len(t), np.uint8) for t in truths], [np.full(len(t), 100, np.int8) for t in truths], go, ge)
+    rb = pack_reads(targets, [np.full(len(t), mismatch, np.uint8) for t in targets])
+    for a in range(12):
+        for b in range(12):
+            if abs(len(targets[a]) - (len(truths[b]) - 2 * band)) < band:              # can_try_align_with_hmm (:244-247)
+                pairs.append((a, b))
+    pairs = np.asarray(pairs, np.int32)
+    cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, use_mapping_quality=False, use_int_scores=True)
+    off, lk, cig, st = engine.align_pairs(cfg, tb, rb, pairs, np.full(len(pairs), band, np.int32))
+    for j, (a, b) in enumerate(pairs):
+        rc, woff, wlk, wcig = refhmm.align_mutation_model(truths[b].tobytes(), targets[a].tobytes(), mismatch, go[b], ge[b])
+        if rc == 2:
+            assert st[j] == 4
+            continue
+        assert rc == 0 and st[j] == 0, (j, rc, st[j])
+        assert (off[j], cig[j]) == (woff, wcig) and lk[j] == wlk, (j, off[j], woff, cig[j], wcig, lk[j], wlk)
