@@ -664,7 +664,8 @@ static int align_impl(phmm_engine* e, const phmm_config* cfg, const phmm_haploty
     // Register traceback for bands up to 32 (one thread per pair, its read in shared memory, one back-pointer word per cell);
     // the generic kernel for wider bands and the reads the register kernel cannot take.
     const int K = 2 * band;
-    p.fast_band = band <= 32 ? band : 0;
+    static const bool no_fast_align = std::getenv("PHMM_NO_FAST_ALIGN") != nullptr;      // measurement hook: the generic traceback kernel for everything
+    p.fast_band = (band <= 32 && !no_fast_align) ? band : 0;
     const int fast_cap = (int)((200 << 10) / (kAlignFastThreads * (int)sizeof(uint32_t))) - 2;      // one block's rows in shared memory
     p.fast_max_len = std::min(Lmax, fast_cap);
     p.fast_row_stride = (p.fast_max_len + 1) | 1;
