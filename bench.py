@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--batch-regions", type=int, default=None,
                     help="regions per CALL: the rank's regions go to the GPU in one phmm_populate_regions call (Octopus's real call shape: many small "
                          "active regions) instead of one phmm_populate call per region")
+    ap.add_argument("--reserve-sms", type=int, default=None,
+                    help="SMs kept free of persistent DP blocks for the gather that runs beside the next call (default: 8 with several ranks, else 0)")
     ap.add_argument("--error-model", default=None, help="haplotype penalty arrays from the reference's error models (reset()), e.g. PCR-free.HiSeq-2500, instead of i.i.d. draws")
     return ap.parse_args()
 
@@ -332,10 +334,14 @@ def main():
                                                 use_int_scores=args.int_scores)
     flank_state = tuple(int(x) for x in args.flank.split(",")) if args.flank else None
     eng = PairHMMEngine(local)
+    reserve = args.reserve_sms if args.reserve_sms is not None else (8 if world > 1 else 0)
+    eng.reserve_sms(reserve)
     d_regions = [(h.to_device(dev), r.to_device(dev)) for h, r in regions]
-    # Two output buffers: the gather of step k (NCCL, asynchronous on torch's stream) reads one while populate k+1 writes the other;
-    # before populate k+2 re-uses a buffer the engine waits (on the device) for the event recorded after gather k.
-    n_buf = 2 if world > 1 else 1
+    # A ring of output buffers: the gather of step k (NCCL, asynchronous on torch's stream) reads one while populate k+1, k+2 write
+    # the others; before populate k+3 re-uses a buffer the engine waits (on the device) for the event recorded after gather k.
+    # The gather runs BESIDE the next populate on the SMs phmm_reserve_sms keeps free of persistent DP blocks.
+    n_buf = 3 if world > 1 else 1
+    gather_buffers = [dict() for _ in range(n_buf)]
     d_out = [torch.empty((H, R), dtype=torch.float64, device=dev) for _ in range(n_buf)]
     gather_done = [None] * n_buf
     recv = None
@@ -356,7 +362,7 @@ def main():
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             if strong:
-                shard.gather_likelihoods(out, R_total, world, rank)            # the [H, R_total] matrix re-assembled on rank 0
+                shard.gather_likelihoods(out, R_total, world, rank, buffers=gather_buffers[b])   # the [H, R_total] matrix re-assembled on rank 0
             else:
                 shard.gather_slabs(out, world, rank, recv=recv[b] if recv else None)   # per-rank matrices straight into rank 0's slabs
             g1.record()
@@ -468,6 +474,7 @@ def main():
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
                        "parallelism": ("one batch, reads split over %d rank(s), [H, R] matrix re-assembled on rank 0 (NCCL gather)" % world) if strong else
                                       ("every rank its own region(s), haplotypes per region, NCCL gather of the per-rank matrices to rank 0 (%d rank(s))" % world),
+                       "reserved_sms": reserve,
                        "penalties": args.error_model or "i.i.d. draws from the error-model tables' value range",
                        "mode": {"flank_state": flank_state, "naive_shortcut": bool(args.shortcut), "kmer_mapper": bool(args.map), "use_int_scores": bool(args.int_scores)}},
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},

@@ -138,6 +138,9 @@ const char* phmm_last_error(const phmm_engine* e);   /* valid until the next cal
  * for callers that want to record or wait on it themselves. */
 int         phmm_wait_event(phmm_engine* e, void* cuda_event);
 void*       phmm_engine_stream(phmm_engine* e);
+/* The persistent DP kernels occupy every SM; a collective the caller runs BESIDE the next call (the gather of the previous result) then
+ * waits for them. n_sms > 0 keeps the first n_sms SMs free of DP blocks (cost: n_sms / 148 of the DP throughput); 0 (default) = none. */
+int         phmm_reserve_sms(phmm_engine* e, int n_sms);
 
 /* Page-locked host memory (cudaHostAlloc) for callers that do not link the CUDA runtime themselves: host-space calls on pinned
  * buffers copy at full rate and overlap with compute. NULL when no GPU / out of memory (callers fall back to malloc). */

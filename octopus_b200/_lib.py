@@ -11,7 +11,7 @@ SPACE_HOST, SPACE_DEVICE = 0, 1
 EXPORTS = ["phmm_version", "phmm_default_config", "phmm_create", "phmm_destroy", "phmm_last_error", "phmm_launch_count",
            "phmm_last_dp_kernel_ms", "phmm_last_dp_cells", "phmm_align_scores", "phmm_align_traceback", "phmm_align_reads", "phmm_align_pairs", "phmm_genotype_likelihoods", "phmm_populate", "phmm_populate_templates", "phmm_populate_regions",
            "phmm_error_model_create", "phmm_error_model_create_custom", "phmm_error_model_destroy", "phmm_error_model_last_error",
-           "phmm_reset_haplotypes", "phmm_tandem_repeats", "phmm_wait_event", "phmm_engine_stream", "phmm_host_alloc", "phmm_host_free"]
+           "phmm_reset_haplotypes", "phmm_tandem_repeats", "phmm_wait_event", "phmm_engine_stream", "phmm_reserve_sms", "phmm_host_alloc", "phmm_host_free"]
 
 
 class Config(C.Structure):
@@ -98,6 +98,8 @@ def load():
                                             C.POINTER(Positions), C.POINTER(FlankState), C.c_void_p, C.c_void_p, C.c_int]
     lib.phmm_wait_event.restype = C.c_int
     lib.phmm_wait_event.argtypes = [C.c_void_p, C.c_void_p]
+    lib.phmm_reserve_sms.restype = C.c_int
+    lib.phmm_reserve_sms.argtypes = [C.c_void_p, C.c_int]
     lib.phmm_engine_stream.restype = C.c_void_p
     lib.phmm_engine_stream.argtypes = [C.c_void_p]
     lib.phmm_host_alloc.restype = C.c_void_p

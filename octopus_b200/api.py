@@ -78,6 +78,12 @@ class PairHMMEngine:
         if rc != _lib.PHMM_OK:
             self._raise(rc)
 
+    def reserve_sms(self, n):
+        """Keep the first n SMs free of persistent DP blocks, for a collective running beside the next call (phmm_reserve_sms)."""
+        rc = self._lib.phmm_reserve_sms(self._h, int(n))
+        if rc != _lib.PHMM_OK:
+            self._raise(rc)
+
     def stream_handle(self):
         return int(self._lib.phmm_engine_stream(self._h) or 0)
 

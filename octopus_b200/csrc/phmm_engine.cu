@@ -50,6 +50,7 @@ int round_band(int requested)
 struct phmm_engine {
     int device = 0;
     int sm_count = 148;
+    int reserved_sms = 0;       // phmm_reserve_sms
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
@@ -361,6 +362,14 @@ int phmm_wait_event(phmm_engine* e, void* cuda_event)
 }
 void* phmm_engine_stream(phmm_engine* e) { return e ? (void*)e->stream : nullptr; }
 
+int phmm_reserve_sms(phmm_engine* e, int n_sms)
+{
+    if (!e || n_sms < 0) return PHMM_ERR_INVALID;
+    e->reserved_sms = std::min(n_sms, std::max(0, e->sm_count - 1));
+    for (phmm_engine* sub : e->sub) if (sub) sub->reserved_sms = e->reserved_sms;
+    return PHMM_OK;
+}
+
 // Page-locked host memory for callers without the CUDA headers (the C++ adapter's blocks): a PHMM_SPACE_HOST call copies from /
 // to pinned buffers at full PCIe / C2C rate and overlaps with compute; pageable memory is staged by the driver.
 void* phmm_host_alloc(size_t bytes)
@@ -553,6 +562,7 @@ int phmm_align_traceback(phmm_engine* e, int band,
         e->err = "bad argument (truth_len must be target_len + 2*band - 1)";
         return PHMM_ERR_INVALID;
     }
+    if (snv_mask && !snv_prior) { e->err = "snv_mask given without snv_prior"; return PHMM_ERR_INVALID; }
     const int W = truth_len, L = target_len;
     std::vector<char> host((size_t)5 * W + 2 * L);
     std::memcpy(host.data(), truth, W);
@@ -862,6 +872,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
     const bool use_mapper = !(positions && positions->off && positions->pos) && cfg->map_positions;
     p.single_candidate = max_dp_per_pair == 1 ? 1 : 0;
+    p.reserved_sms = e->reserved_sms;
     int mapper_maxt = 0;
     if (use_mapper) {
         long long max_hap = 0;
@@ -1314,7 +1325,13 @@ int phmm_populate(phmm_engine* e, const phmm_config* cfg,
             if (rc != PHMM_OK) { e->err = std::string("sub-engine: ") + phmm_last_error(nullptr); return rc; }
             sub->is_sub = true;
             sub->parent = e;
-            if (cudaEventCreateWithFlags(&sub->order_ev, cudaEventDisableTiming) != cudaSuccess) { e->err = "sub-engine: event creation failed"; return PHMM_ERR_CUDA; }
+            sub->reserved_sms = e->reserved_sms;
+            if (cudaEventCreateWithFlags(&sub->order_ev, cudaEventDisableTiming) != cudaSuccess) {
+                phmm_destroy(sub);          // a sub-engine without its ordering event must not survive into the next call
+                sub = nullptr;
+                e->err = "sub-engine: event creation failed";
+                return PHMM_ERR_CUDA;
+            }
         }
     }
     e->sub[0]->peer = e->sub[1]; e->sub[1]->peer = e->sub[0];

@@ -385,6 +385,7 @@ struct PopParams {
     int band, nuc_prior;
     int one;                    // the constant 1, opaque to the compiler (fma_add)
     int single_candidate;       // every pair has at most one candidate position (no listed / mapped positions): results are stored, not min-reduced
+    int reserved_sms;           // the persistent DP kernels leave the SMs with %smid < reserved_sms to others (a collective running beside them)
     int shortcut;               // 1: reference behaviour (try_naive_evaluate first)
     int use_flanks;             // some region has a flank state && config.use_flank_state (the per-region values are in regs)
     int* best;                  // [H*R] integer penalties, kBestInf-initialised
@@ -415,6 +416,17 @@ __device__ __forceinline__ void split_index(const long long i, const int H, int*
 {
     if (i <= 0xFFFFFFFFll) { const unsigned u = (unsigned)i, q = u / (unsigned)H; *li = (int)q; *h = (int)(u - q * (unsigned)H); }
     else { *li = (int)(i / H); *h = (int)(i % H); }
+}
+
+// Persistent DP kernels fill every SM's register file; a collective (NCCL gather of the previous result) launched beside them finds no
+// SM to run on until they finish. With reserved_sms > 0 the blocks that land on the first SMs exit at once (the work queue is dynamic:
+// the others take it all), which leaves those SMs to the collective at a cost of reserved / 148 of the DP throughput.
+__device__ __forceinline__ bool on_reserved_sm(const PopParams& p)
+{
+    if (p.reserved_sms <= 0) return false;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    return (int)smid < p.reserved_sms;
 }
 
 __device__ __forceinline__ int tile_pairs(const PopParams& p) { return max(0, min(p.n_pairs, p.tot->n_pairs - p.pair_base)); }
@@ -641,6 +653,7 @@ k_populate_fast(const PopParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / LG, gl = lane % LG;
     const int slot = gl / NL, jl = gl % NL;
+    if (on_reserved_sm(p)) return;
     RowEntry* rows = smem_rows + (warp * G + grp) * p.row_stride;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     const int n_pairs = tile_pairs(p);
@@ -770,7 +783,7 @@ k_populate_flank_acc(const PopParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     RowEntry* rows = smem_rows + warp * p.row_stride;
     constexpr int K = 2 * BAND;
-    if (*p.any_acc_tasks == 0) return;
+    if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
     for (;;) {
         int li = 0;
@@ -932,6 +945,7 @@ k_populate_wide(const PopParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = lane / NL, j = lane % NL;
     RowEntry* rows = smem_rows + warp * p.row_stride;
+    if (on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
     for (;;) {
         int li = 0;

@@ -40,24 +40,38 @@ def shard_positions(positions, H, R, lo, hi):
     return new_off, (flat if len(flat) else np.zeros(1, dtype=np.int32))
 
 
-def gather_likelihoods(local, R_total, world, rank, group=None):
+def gather_likelihoods(local, R_total, world, rank, group=None, buffers=None):
     """Gather the per-rank [H, R_rank] slabs into the [H, R_total] matrix on rank 0 (returns None elsewhere).
 
-    ``local`` is a torch tensor (CUDA with the nccl backend, CPU with gloo). Slabs are padded to the largest share so a
-    single fixed-size gather suffices; the column ranges are those of ``split_range``."""
+    ``local`` is a torch tensor (CUDA with the nccl backend, CPU with gloo); the column ranges are those of ``split_range``.
+    Equal shares are gathered straight from ``local``; unequal ones are padded to the largest. ``buffers``: an optional dict the
+    caller keeps across calls (receive slabs, output matrix, padding slab) so that a step allocates nothing."""
     import torch
     import torch.distributed as dist
-    H = local.shape[0]
-    width = (R_total + world - 1) // world
-    send = torch.zeros((H, width), dtype=local.dtype, device=local.device)
-    send[:, :local.shape[1]] = local
     if world == 1:
         return local
-    recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    H = local.shape[0]
+    width = (R_total + world - 1) // world
+    buffers = buffers if buffers is not None else {}
+    equal = R_total % world == 0
+    if equal:
+        send = local.contiguous()
+    else:
+        send = buffers.get("send")
+        if send is None or send.shape != (H, width) or send.device != local.device:
+            send = buffers["send"] = torch.zeros((H, width), dtype=local.dtype, device=local.device)
+        send[:, :local.shape[1]] = local
+    recv = None
+    if rank == 0:
+        recv = buffers.get("recv")
+        if recv is None or len(recv) != world or recv[0].shape != (H, width) or recv[0].device != local.device:
+            recv = buffers["recv"] = [torch.empty((H, width), dtype=local.dtype, device=local.device) for _ in range(world)]
     dist.gather(send, recv, dst=0, group=group)
     if rank != 0:
         return None
-    out = torch.empty((H, R_total), dtype=local.dtype, device=local.device)
+    out = buffers.get("out")
+    if out is None or out.shape != (H, R_total) or out.device != local.device:
+        out = buffers["out"] = torch.empty((H, R_total), dtype=local.dtype, device=local.device)
     for k in range(world):
         lo, hi = split_range(R_total, world, k)
         out[:, lo:hi] = recv[k][:, :hi - lo]

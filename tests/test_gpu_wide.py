@@ -245,6 +245,26 @@ def test_lean_flank_kernel_geometries(engine, coracle):
                     assert ok, (band, trial, flanks, mapit, worst)
 
 
+def test_reserved_sms_leave_results_unchanged(coracle):
+    """phmm_reserve_sms: the DP blocks that land on reserved SMs exit and the others take their work; every mode's result is what it
+    is without the reservation (and the oracle's)."""
+    from octopus_b200 import HaplotypeLikelihoodModel, PairHMMEngine
+    rng = np.random.default_rng(97)
+    eng = PairHMMEngine(0)
+    for band, flanks, mapit in ((16, None, False), (16, (30, 40), True), (32, None, True), (64, None, False)):
+        haps, reads = random_region(rng, band, n_haps=40, n_reads=3000, hap_len=2 * band + 300, read_len_choices=[76, 100, 150], read_n_rate=0.02)
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=not mapit, map_positions=mapit)
+        eng.reserve_sms(0)
+        base = eng.populate(cfg, haps, reads, None, flanks)
+        for n in (8, 100, 147, 10**6):
+            eng.reserve_sms(n)
+            assert np.array_equal(eng.populate(cfg, haps, reads, None, flanks), base), (band, n)
+        rc, want, wst = coracle.populate(band, haps, reads, None, flanks, dp_only=not mapit, map_positions=mapit)
+        ok, worst = _close(base[wst == 0], want[wst == 0])
+        assert ok, (band, worst)
+    eng.close()
+
+
 def test_populate_regions_equals_one_call_per_region(engine, coracle):
     """phmm_populate_regions: many small regions (ragged haplotype and read counts, own flank states) in one kernel chain give, region
     by region, what phmm_populate gives for the region alone — and the oracle's values."""
