@@ -53,8 +53,12 @@ def parse_args():
     ap.add_argument("--batch-regions", type=int, default=None,
                     help="regions per CALL: the rank's regions go to the GPU in one phmm_populate_regions call (Octopus's real call shape: many small "
                          "active regions) instead of one phmm_populate call per region")
-    ap.add_argument("--reserve-sms", type=int, default=None,
-                    help="SMs kept free of persistent DP blocks for the gather that runs beside the next call (default: 8 with several ranks, else 0)")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="SMs kept free of persistent DP blocks for a collective that runs beside the next call (phmm_reserve_sms)")
+    ap.add_argument("--unordered-penalties", action="store_true",
+                    help="draw gap_extend without the cap at gap_open (only the PacBio / custom error models produce such arrays); the DP kernels detect it and run their general (6 ALU-op) deletion update")
+    ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
+                    help="several ranks: how the values reach rank 0 — peer (each rank's epilogue stores into rank 0's HBM through a CUDA IPC mapping) or nccl (gather collective)")
     ap.add_argument("--error-model", default=None, help="haplotype penalty arrays from the reference's error models (reset()), e.g. PCR-free.HiSeq-2500, instead of i.i.d. draws")
     return ap.parse_args()
 
@@ -265,7 +269,7 @@ def run_reference_arm(args):
     cfg = synth.CONFIGS[args.config]
     threads = host_threads()
     # a bounded sample of the workload per step: sized so that the whole --steps/--warmup run takes about a minute
-    haps, reads, band = synth.make_batch(args.config, n_reads=min(cfg["n_reads"], 200_000), n_haps=args.haps)
+    haps, reads, band = synth.make_batch(args.config, n_reads=min(cfg["n_reads"], 200_000), n_haps=args.haps, ordered_penalties=not args.unordered_penalties)
     n_sample = args.cpu_sample_reads or calibrated_sample(haps, reads, band, threads, 60.0 / max(1, args.steps + args.warmup))
     for _ in range(max(1, args.warmup)):
         cpu_reference_run(haps, reads, band, n_sample, threads)
@@ -309,7 +313,8 @@ def main():
     n_regions = args.batch_regions or (args.regions if args.regions else (125 if args.config == "C5" else 1))
 
     def make_region(seed):
-        h, r, b = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=seed, band=args.band, hap_len=args.hap_len, read_lens=read_lens)
+        h, r, b = synth.make_batch(args.config, n_reads=args.reads, n_haps=args.haps, seed=seed, band=args.band, hap_len=args.hap_len, read_lens=read_lens,
+                                   ordered_penalties=not args.unordered_penalties)
         if args.error_model:       # penalty arrays as the reference's error models assign them (tandem-repeat structured), not i.i.d.
             h = ErrorModel(args.error_model).reset_block(h.off, h.seq, h.begin)
         return h, r, b
@@ -334,24 +339,49 @@ def main():
                                                 use_int_scores=args.int_scores)
     flank_state = tuple(int(x) for x in args.flank.split(",")) if args.flank else None
     eng = PairHMMEngine(local)
-    reserve = args.reserve_sms if args.reserve_sms is not None else (8 if world > 1 else 0)
+    reserve = args.reserve_sms
     eng.reserve_sms(reserve)
     d_regions = [(h.to_device(dev), r.to_device(dev)) for h, r in regions]
-    # A ring of output buffers: the gather of step k (NCCL, asynchronous on torch's stream) reads one while populate k+1, k+2 write
-    # the others; before populate k+3 re-uses a buffer the engine waits (on the device) for the event recorded after gather k.
-    # The gather runs BESIDE the next populate on the SMs phmm_reserve_sms keeps free of persistent DP blocks.
+    # Several ranks: the values have to end up on rank 0.
+    #   --gather peer (default): rank 0 owns a ring of result slots mapped into every rank (CUDA IPC); each rank's epilogue kernel
+    #     stores its slab — its columns of the [H, R_total] matrix (strong) or its [H, R] matrix of the per-rank stack (weak) —
+    #     straight into rank 0's HBM over NVLink; one barrier per step tells rank 0 the step has landed (octopus_b200/peer.py).
+    #   --gather nccl: a ring of local output buffers and an NCCL gather per step, asynchronous on torch's stream; before a buffer is
+    #     re-used the engine waits (on the device) for the event recorded after its gather.
     n_buf = 3 if world > 1 else 1
+    peer_ring = None
+    max_region_bytes = max(h.n * r.n for h, r in regions) * 8
+    if world > 1 and args.gather == "peer":
+        from octopus_b200.peer import PeerRing
+        slot_bytes = H * R_total * 8 if strong else world * max_region_bytes
+        peer_ring = PeerRing(slot_bytes, local, rank, world, n_buf=n_buf)
     gather_buffers = [dict() for _ in range(n_buf)]
-    d_out = [torch.empty((H, R), dtype=torch.float64, device=dev) for _ in range(n_buf)]
+    d_out = [torch.empty((H, R), dtype=torch.float64, device=dev) for _ in range(n_buf)] if peer_ring is None else None
     gather_done = [None] * n_buf
     recv = None
-    if world > 1 and rank == 0 and not strong:
+    if world > 1 and rank == 0 and not strong and peer_ring is None:
         recv = [[torch.empty_like(d_out[0]) for _ in range(world)] for _ in range(n_buf)]
     state = {"k": 0, "gather_ms": [], "launches": 0}
 
     def one_region(dh, dr):
-        b = state["k"] % n_buf
+        k = state["k"]
+        b = k % n_buf
         state["k"] += 1
+        if peer_ring is not None:
+            peer_ring.wait_slot(eng, k)
+            if strong:
+                lo, _ = shard.split_range(R_total, world, rank)
+                out = peer_ring.window(k, lo * 8, dh.n, dr.n, ld=R_total)
+            else:
+                out = peer_ring.window(k, rank * max_region_bytes, dh.n, dr.n)
+            eng.populate(model_cfg, dh, dr, flank_state=flank_state, out=out)
+            dp = eng.last_dp_kernel_ms()
+            state["launches"] += eng.launch_count()
+            g0 = torch.cuda.Event(enable_timing=True)
+            g0.record()
+            g1 = peer_ring.publish(k)
+            state["gather_ms"].append((g0, g1))        # here: the barrier alone (the stores are part of the populate call)
+            return dp
         if gather_done[b] is not None:
             eng.wait_event(gather_done[b])
         out = d_out[b] if (dh.n, dr.n) == (H, R) else None
@@ -415,6 +445,31 @@ def main():
     gather_ms = float(np.mean([a.elapsed_time(b) for a, b in state["gather_ms"]])) if state["gather_ms"] else 0.0
     clocks = sampler.stop() if rank == 0 else None
 
+    # Did every rank's values land on rank 0? Each rank recomputes its last region locally; rank 0 compares an order-independent bit
+    # digest (int64 sum of the float64 bit patterns) of every rank's window of the last slot with that rank's own digest.
+    gather_check = None
+    if peer_ring is not None:
+        k_last = state["k"] - 1
+        dh, dr = d_regions[-1]
+        mine = eng.populate(model_cfg, dh, dr, flank_state=flank_state)
+        dig = torch.stack([mine.view(torch.int64).sum(), torch.tensor(dh.n, device=dev), torch.tensor(dr.n, device=dev)]).to(torch.int64)
+        digs = [torch.zeros_like(dig) for _ in range(world)] if rank == 0 else None
+        dist.gather(dig, digs, dst=0)
+        if rank == 0:
+            torch.cuda.synchronize()
+            bad = 0
+            for k in range(world):
+                want, rows, cols = (int(x) for x in digs[k].tolist())
+                if strong:
+                    lo, hi = shard.split_range(R_total, world, k)
+                    win = peer_ring.owner_slot(k_last, (H, R_total))[:, lo:hi].contiguous()
+                else:
+                    win = peer_ring.owner_slot(k_last, (rows, cols), byte_offset=k * max_region_bytes)
+                bad += int(tuple(win.shape) != (rows, cols) or int(win.view(torch.int64).sum().item()) != want)
+            gather_check = {"ranks_checked": world, "ranks_mismatched": bad,
+                            "what": "bit digest of every rank's window of rank 0's last result slot vs the rank's own recomputation"}
+        sync_all()
+
     # e2e: the same call through the C ABI with pinned HOST buffers: H2D of the batch and D2H of the matrix inside the timed region
     # (and, with several ranks, the gather of the host matrices' device copies is replaced by each rank's own D2H: the per-rank
     # results land in host memory of the rank that computed them)
@@ -463,6 +518,8 @@ def main():
         traffic = measured_traffic(args.config, R, H, band, mode_key)
         kernel_name = ("k_populate_flank_acc<%d>" % band) if flank_state and band <= 32 else \
                       ("k_populate_wide (32-bit lanes, band %d)" % band) if args.int_scores else "k_populate_fast<%d>" % band
+        how = "none: one rank" if world == 1 else ("peer stores: every rank's epilogue kernel writes into rank 0's HBM through a CUDA IPC mapping, one barrier per step"
+                                                   if peer_ring is not None else "NCCL gather per step, overlapped with the next step's compute")
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -472,10 +529,13 @@ def main():
                        "alignments_per_step": haps.n * R_total if strong else sum(h.n * r.n for h, r in regions) * world,
                        "cells_per_step": cells_rank_total,
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
-                       "parallelism": ("one batch, reads split over %d rank(s), [H, R] matrix re-assembled on rank 0 (NCCL gather)" % world) if strong else
-                                      ("every rank its own region(s), haplotypes per region, NCCL gather of the per-rank matrices to rank 0 (%d rank(s))" % world),
+                       "parallelism": ("one batch, reads split over %d rank(s), [H, R_total] matrix assembled on rank 0 (%s)" % (world, how)) if strong else
+                                      ("every rank its own region(s), haplotypes per region, the per-rank matrices collected on rank 0 (%d rank(s), %s)" % (world, how)),
+                       "gather": (args.gather if world > 1 else None),
                        "reserved_sms": reserve,
-                       "penalties": args.error_model or "i.i.d. draws from the error-model tables' value range",
+                       "penalties": args.error_model or ("i.i.d. draws from the error-model tables' value range" +
+                                                         (", gap_extend unconstrained (general deletion update)" if args.unordered_penalties else
+                                                          ", gap_extend capped at gap_open as in every short-read error model")),
                        "mode": {"flank_state": flank_state, "naive_shortcut": bool(args.shortcut), "kmer_mapper": bool(args.map), "use_int_scores": bool(args.int_scores)}},
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
@@ -508,6 +568,10 @@ def main():
                 v = cpu_reference_run(haps, reads, band, max(64, n_sample // 4), threads, isa=isa)
                 variants["%s_build_all_threads" % isa] = {"value": v[0], "kernel": v[3]}
             line["cpu_baseline"]["variants"] = variants
+        if gather_check is not None:
+            line["gather_check"] = gather_check
+            if gather_check["ranks_mismatched"]:
+                sys.stderr.write("GATHER CHECK FAILED: %r\n" % (gather_check,))
         line["parity"] = parity_gate(eng, haps, reads, band, flank_state, args.shortcut, args.map, args.int_scores, ref_scores, n_ref)
         print(json.dumps(line))
         if line["parity"]["mismatches"]:

@@ -227,6 +227,26 @@ int phmm_populate_regions(phmm_engine* e, const phmm_config* cfg,
                           const phmm_haplotypes* haps, const phmm_reads* reads, const phmm_regions* regions,
                           double* out, int32_t* status, int space);
 
+/* phmm_populate with device-resident inputs and an output row stride: out[h * out_ld + r], out_ld >= R (status, optional, stays dense
+ * [H][R]). `out` is any device-accessible address — in particular a window of ANOTHER GPU's matrix mapped with phmm_ipc_open: the
+ * epilogue kernel then stores this rank's columns of a read-sharded [H, R_total] matrix (or its slab of a per-rank stack) straight
+ * into the owner's HBM over NVLink / NVSwitch, and no gather collective follows. */
+int phmm_populate_ld(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* haps, const phmm_reads* reads,
+                     const phmm_positions* positions, const phmm_flank_state* flank,
+                     double* out, int64_t out_ld, int32_t* status);
+
+/* Peer output memory (one node, one process per GPU). The owner allocates the result matrix with phmm_device_alloc (cudaMalloc, the
+ * allocation CUDA IPC can export), exports it once, and sends the 64 handle bytes to the other processes by any means; they map it
+ * with phmm_ipc_open (peer access is enabled on demand) and pass addresses inside it to phmm_populate_ld. A writer's stores are
+ * complete when its call has returned; the owner learns that through the caller's own barrier. phmm_ipc_close unmaps. */
+#define PHMM_IPC_HANDLE_BYTES 64
+int phmm_device_alloc(int device, size_t bytes, void** dev_ptr);
+int phmm_device_free(void* dev_ptr);
+int phmm_ipc_export(const void* dev_ptr, unsigned char handle[PHMM_IPC_HANDLE_BYTES]);
+int phmm_ipc_open(int device, const unsigned char handle[PHMM_IPC_HANDLE_BYTES], void** dev_ptr);
+int phmm_ipc_close(void* dev_ptr);
+
 /* Paired / linked reads: HaplotypeLikelihoodArray::populate(TemplateMap) (haplotype_likelihood_array.cpp:105-199). Template t owns
  * the reads [template_off[t], template_off[t+1]) and its value is the sum of its reads' values
  * (HaplotypeLikelihoodModel::evaluate(AlignedTemplate), haplotype_likelihood_model.cpp:306-320). out is [H][n_templates];

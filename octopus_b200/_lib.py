@@ -11,7 +11,8 @@ SPACE_HOST, SPACE_DEVICE = 0, 1
 EXPORTS = ["phmm_version", "phmm_default_config", "phmm_create", "phmm_destroy", "phmm_last_error", "phmm_launch_count",
            "phmm_last_dp_kernel_ms", "phmm_last_dp_cells", "phmm_align_scores", "phmm_align_traceback", "phmm_align_reads", "phmm_align_pairs", "phmm_genotype_likelihoods", "phmm_populate", "phmm_populate_templates", "phmm_populate_regions",
            "phmm_error_model_create", "phmm_error_model_create_custom", "phmm_error_model_destroy", "phmm_error_model_last_error",
-           "phmm_reset_haplotypes", "phmm_tandem_repeats", "phmm_wait_event", "phmm_engine_stream", "phmm_reserve_sms", "phmm_host_alloc", "phmm_host_free"]
+           "phmm_reset_haplotypes", "phmm_tandem_repeats", "phmm_wait_event", "phmm_engine_stream", "phmm_reserve_sms", "phmm_host_alloc", "phmm_host_free",
+           "phmm_populate_ld", "phmm_device_alloc", "phmm_device_free", "phmm_ipc_export", "phmm_ipc_open", "phmm_ipc_close"]
 
 
 class Config(C.Structure):
@@ -96,6 +97,19 @@ def load():
     lib.phmm_populate_templates.restype = C.c_int
     lib.phmm_populate_templates.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Haplotypes), C.POINTER(Reads), C.c_void_p, C.c_int32,
                                             C.POINTER(Positions), C.POINTER(FlankState), C.c_void_p, C.c_void_p, C.c_int]
+    lib.phmm_populate_ld.restype = C.c_int
+    lib.phmm_populate_ld.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Haplotypes), C.POINTER(Reads),
+                                     C.POINTER(Positions), C.POINTER(FlankState), C.c_void_p, C.c_int64, C.c_void_p]
+    lib.phmm_device_alloc.restype = C.c_int
+    lib.phmm_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.phmm_device_free.restype = C.c_int
+    lib.phmm_device_free.argtypes = [C.c_void_p]
+    lib.phmm_ipc_export.restype = C.c_int
+    lib.phmm_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    lib.phmm_ipc_open.restype = C.c_int
+    lib.phmm_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.phmm_ipc_close.restype = C.c_int
+    lib.phmm_ipc_close.argtypes = [C.c_void_p]
     lib.phmm_wait_event.restype = C.c_int
     lib.phmm_wait_event.argtypes = [C.c_void_p, C.c_void_p]
     lib.phmm_reserve_sms.restype = C.c_int

@@ -319,6 +319,16 @@ class PairHMMEngine:
             if want_status:
                 status = torch.empty((H, R), dtype=torch.int32, device=haps.seq.device)
             op, sp = out.data_ptr(), (status.data_ptr() if want_status else None)
+            if tuple(out.shape) != (H, R) or out.dtype != torch.float64 or (R > 1 and out.stride(1) != 1):
+                raise ValueError("out must be a float64 [H, R] tensor with unit column stride")
+            if H > 1 and out.stride(0) != R:
+                # a column window of a wider matrix — possibly another GPU's (octopus_b200.peer): phmm_populate_ld
+                rc = self._lib.phmm_populate_ld(self._h, C.byref(cfg), C.byref(hs), C.byref(rs),
+                                                C.byref(pstruct) if pstruct is not None else None,
+                                                C.byref(fstruct) if fstruct is not None else None, op, int(out.stride(0)), sp)
+                if rc != _lib.PHMM_OK and not (rc == _lib.PHMM_ERR_SHORT_HAPLOTYPE and want_status):
+                    self._raise(rc)
+                return (out, status) if want_status else out
         else:
             if out is None:
                 out = np.empty((H, R), dtype=np.float64)

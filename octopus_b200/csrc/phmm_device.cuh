@@ -42,6 +42,7 @@ constexpr uint32_t kCapInf   = 127u;      // "no cap": min(q, 127) == q for ever
 constexpr uint32_t kInf16    = 0x7000u;   // +inf of the packed 16-bit lanes; kInf16 + 2*127 + nuc stays < 0x8000
 constexpr uint32_t kInf16x2  = kInf16 | (kInf16 << 16);
 constexpr int      kInf32    = 1 << 28;   // +inf of the int32 kernel
+constexpr int      kFlagOpenBelowExtend = 16;    // engine flag word: some haplotype base has gap_open < gap_extend (see dp_pair, OGE)
 constexpr int      kMaxScore16 = 0x7000 - 1024;  // a read whose sum of qualities is below this cannot overflow a 16-bit lane
 
 // Read row half-word: code | qual << 8 (code: A0 C1 G2 T3, N4). Reads with an 'N' are served by the 32-bit kernel (its
@@ -134,6 +135,14 @@ PHMM_HD ColEntry make_col_entry(const char truth, const char snv_mask, const int
     return e;
 }   // code 0 / qual 0 for both halves: sub = min(0, cap) = 0
 
+// a + b computed as a * one + b with `one` (== 1) opaque to the compiler: an IMAD on the FMA pipe instead of an IADD that ptxas
+// would fuse into a VIADDMNMX on the (binding) ALU pipe
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b)); return d; }
+#else
+inline uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // Fast path: two alignments per thread, s16x2 lanes, band state in registers
 // ---------------------------------------------------------------------------------------------------------
@@ -156,10 +165,17 @@ PHMM_HD ColEntry make_col_entry(const char truth, const char snv_mask, const int
 #define PHMM_REP8(F, b)  F(b + 7) F(b + 6) F(b + 5) F(b + 4) F(b + 3) F(b + 2) F(b + 1) F(b + 0)
 #define PHMM_REP64(F)    PHMM_REP8(F, 56) PHMM_REP8(F, 48) PHMM_REP8(F, 40) PHMM_REP8(F, 32) PHMM_REP8(F, 24) PHMM_REP8(F, 16) PHMM_REP8(F, 8) PHMM_REP8(F, 0)
 
-template <int BAND>
+// OGE ("open >= extend"): the caller knows gap_open[x] >= gap_extend[x] for every column of both windows (true of every penalty
+// array the reference's short-read error models produce — the PacBio tables break it inside long homopolymers, custom models may;
+// k_build_tables raises kFlagOpenBelowExtend for such arrays and the kernels then instantiate OGE = false). Then
+//   min(d + ge, min(m, i) + go) == min(d + ge, min(m, i, d) + go)        (d + go >= d + ge)
+// and the deletion update re-uses S = min(m, i, d), which the match update needs anyway: 5 ALU-pipe instructions per cell pair
+// instead of 6 (the ALU pipe is what binds this kernel).
+template <int BAND, bool OGE = false>
 PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
                          const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
-                         const uint32_t nucp /* nuc_prior in both halves */)
+                         const uint32_t nucp /* nuc_prior in both halves */,
+                         const uint32_t one = 1u /* the kernels pass an opaque 1: the cell's additions become IMADs on the FMA pipe (fma_add) */)
 {
     constexpr int K = 2 * BAND;
     static_assert(K <= 64, "register band limited to 64 diagonals");
@@ -176,9 +192,10 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
         const RowEntry w   = rp[-(k)];                                                      \
         const uint32_t sub = vmin2(w.y, prmt(caps0, caps1, w.x));                           \
         const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                  \
-        M[(k) < K ? (k) : 0] = vmin3(m, i_run, d) + sub;                                    \
-        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = vaddmin(d, ge, vmin2(m, i_run) + go); \
-        i_run = vaddmin(i_run, gep, m + gop);                                               \
+        const uint32_t s = vmin3(m, i_run, d);                                              \
+        M[(k) < K ? (k) : 0] = fma_add(s, sub, one);                                        \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = vaddmin(d, ge, fma_add(OGE ? s : vmin2(m, i_run), go, one)); \
+        i_run = vaddmin(i_run, gep, fma_add(m, gop, one));                                  \
     }
 #define PHMM_CASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_CELL(k)
 #define PHMM_CASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
@@ -263,13 +280,6 @@ PHMM_HD uint32_t dp_pair(const RowEntry* __restrict__ rows, const int L,
 // Traits select the value type: Lanes16 = two alignments per lane group packed s16x2 (as dp_pair), Lanes32 = one alignment
 // in 32-bit lanes (int scores, long or high-quality-sum reads, reads holding 'N': the PRMT lookup has the fifth cap).
 PHMM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
-// a + b computed as a * one + b with `one` (== 1) opaque to the compiler: an IMAD on the FMA pipe instead of an IADD that ptxas
-// would fuse into a VIADDMNMX on the (binding) ALU pipe
-#ifdef __CUDA_ARCH__
-__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b)); return d; }
-#else
-inline uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
-#endif
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ uint32_t umin3_32(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }            // VIMNMX3.U32
 __device__ __forceinline__ uint32_t uaddmin32(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u32(a, b, c); }        // VIADDMNMX.U32: min(a+b, c)
@@ -348,7 +358,7 @@ PHMM_HD void band_lane_init(BandLane<T, C>& s, const typename T::Tab& tab, const
 
 // Phase 1 of a step: column operands and the top cell (diagonal C-1 of the chunk), which exists from local column C on.
 // xl = column relative to the lane's first column, x = xl + first_col the window column, W the window length.
-template <class T, int C>
+template <class T, int C, bool OGE = false>
 PHMM_HD void band_lane_top(BandLane<T, C>& s, const RowEntry* __restrict__ rows, const int L, const int xl, const int x, const int W,
                            const typename T::Tab& tab, const typename T::V nucp, const bool is_top_lane)
 {
@@ -363,14 +373,15 @@ PHMM_HD void band_lane_top(BandLane<T, C>& s, const RowEntry* __restrict__ rows,
     if (xl >= C) {
         const RowEntry w = rows[xl - (C - 1)];
         const typename T::V sub = T::sub(w, s.col), m = s.M[C - 1], d = s.D[C - 1];
-        s.M[C - 1] = T::min3(m, s.i_run, d) + sub;
-        s.d_out = T::addmin(d, s.col.ge, T::min2(m, s.i_run) + s.col.go);
+        const typename T::V sm = T::min3(m, s.i_run, d);
+        s.M[C - 1] = sm + sub;
+        s.d_out = T::addmin(d, s.col.ge, (OGE ? sm : T::min2(m, s.i_run)) + s.col.go);      // OGE: see dp_pair
         s.i_run = T::addmin(s.i_run, s.gep, m + s.gop);
     }
 }
 
 // Phase 2: the remaining cells of the column. d_in = the d_out of the lane below (same step); ignored by the bottom lane.
-template <class T, int C>
+template <class T, int C, bool OGE = false>
 PHMM_HD void band_lane_rest(BandLane<T, C>& s, const RowEntry* __restrict__ rows, const int L, const int xl, const int x,
                             const typename T::V d_in, const bool is_bottom_lane)
 {
@@ -385,8 +396,9 @@ PHMM_HD void band_lane_rest(BandLane<T, C>& s, const RowEntry* __restrict__ rows
         const RowEntry w = rp[-(k)];                                                            \
         const typename T::V sub = T::sub(w, col);                                               \
         const typename T::V m = s.M[(k) < C ? (k) : 0], d = s.D[(k) < C ? (k) : 0];            \
-        s.M[(k) < C ? (k) : 0] = T::min3(m, i_run, d) + sub;                                    \
-        if ((k) + 1 < C) s.D[((k) + 1) < C ? (k) + 1 : 0] = T::addmin(d, col.ge, T::min2(m, i_run) + col.go); \
+        const typename T::V sm = T::min3(m, i_run, d);                                          \
+        s.M[(k) < C ? (k) : 0] = sm + sub;                                                      \
+        if ((k) + 1 < C) s.D[((k) + 1) < C ? (k) + 1 : 0] = T::addmin(d, col.ge, (OGE ? sm : T::min2(m, i_run)) + col.go); \
         i_run = T::addmin(i_run, gep, m + gop);                                                 \
     }
 #define PHMM_BCASE_PROLOGUE(k) case (k) + 1: if ((k) + 1 < C) PHMM_BCELL(k)
@@ -438,7 +450,7 @@ PHMM_HD typename T::V band_lane_result(const BandLane<T, C>& s)
 #ifdef __CUDACC__
 // Device driver. Lanes j = 0..NL-1 of a group are NL consecutive lanes of the warp (group-aligned); every lane of the warp
 // must call this with the same L (the loop and its shuffles are warp-wide). Returns the group's result in all of its lanes.
-template <class T, int C, int NL>
+template <class T, int C, int NL, bool OGE = false>
 __device__ __forceinline__ typename T::V dp_band(const RowEntry* __restrict__ rows, const int L, const typename T::Tab& tab,
                                                  const typename T::V nucp, const int j)
 {
@@ -447,10 +459,10 @@ __device__ __forceinline__ typename T::V dp_band(const RowEntry* __restrict__ ro
     band_lane_init<T, C>(s, tab, j * C);
     for (int t = 0; t <= W; ++t) {
         const int x = t - (NL - 1 - j), xl = x - j * C;
-        band_lane_top<T, C>(s, rows, L, xl, x, W, tab, nucp, j == NL - 1);
+        band_lane_top<T, C, OGE>(s, rows, L, xl, x, W, tab, nucp, j == NL - 1);
         typename T::V d_in = T::inf();
         if (NL > 1) d_in = __shfl_up_sync(0xffffffffu, s.d_out, 1);
-        band_lane_rest<T, C>(s, rows, L, xl, x, d_in, j == 0);
+        band_lane_rest<T, C, OGE>(s, rows, L, xl, x, d_in, j == 0);
         if (NL > 1) { const typename T::V v = __shfl_down_sync(0xffffffffu, s.i_run, 1); s.i_run = (j == NL - 1) ? T::inf() : v; }
     }
     typename T::V best = band_lane_result<T, C>(s);

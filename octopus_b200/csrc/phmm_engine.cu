@@ -480,7 +480,7 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         CU(cudaEventRecord(e->ev0, e->stream)); have_ev0 = true;
 #define PHMM_PACKED_TASKS(B) \
         { if ((rc = fast_smem_attr(e, k_packed_tasks<B>, smem))) return rc; \
-          k_packed_tasks<B><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores); }
+          k_packed_tasks<B><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(e->works.as<WarpWork>(), nw, e->tasks_lane.as<LaneTask>(), s.hp, s.rd, row_stride, nucp, d_scores, e->flags.as<int>(), 1u); }
         switch (band) {
             case 8: PHMM_PACKED_TASKS(8) break;     case 16: PHMM_PACKED_TASKS(16) break;   case 32: PHMM_PACKED_TASKS(32) break;
             case 64: PHMM_PACKED_TASKS(64) break;   case 128: PHMM_PACKED_TASKS(128) break; default: PHMM_PACKED_TASKS(256) break;
@@ -516,7 +516,7 @@ int phmm_align_scores(phmm_engine* e, int band, int precision_bits, int nuc_prio
         if (!have_ev0) { CU(cudaEventRecord(e->ev0, e->stream)); have_ev0 = true; }
 #define PHMM_WIDE_TASKS(CC, NN) \
         { if ((rc = fast_smem_attr(e, k_wide_tasks<CC, NN>, smem))) return rc; \
-          k_wide_tasks<CC, NN><<<grid, warps * 32, smem, e->stream>>>(e->gtasks.as<WarpWork>(), nw, e->ftasks.as<LaneTask>(), s.hp, s.rd, row_stride, nuc_prior, d_scores); }
+          k_wide_tasks<CC, NN><<<grid, warps * 32, smem, e->stream>>>(e->gtasks.as<WarpWork>(), nw, e->ftasks.as<LaneTask>(), s.hp, s.rd, row_stride, nuc_prior, d_scores, e->flags.as<int>()); }
         switch (band) {
             case 8: PHMM_WIDE_TASKS(16, 1) break;  case 16: PHMM_WIDE_TASKS(32, 1) break;  case 32: PHMM_WIDE_TASKS(32, 2) break;
             case 64: PHMM_WIDE_TASKS(32, 4) break; case 128: PHMM_WIDE_TASKS(32, 8) break; default: PHMM_WIDE_TASKS(32, 16) break;
@@ -1202,7 +1202,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     {
         const long long threads = (long long)H * R;
         k_epilogue<<<(unsigned)((threads + 255) / 256), 256, 0, e->stream>>>(p.best, p.status, s.rd, e->regs.as<RegionInfo>(), H, cfg->use_mapping_quality,
-                                                                             cfg->mapping_quality_cap, cfg->mapping_quality_cap_trigger, d_out);
+                                                                             cfg->mapping_quality_cap, cfg->mapping_quality_cap_trigger, d_out,
+                                                                             d_out == out && space == PHMM_SPACE_DEVICE && out_pitch > R ? out_pitch - R : 0LL);
     }
     LAUNCHED();
     CU(cudaGetLastError());
@@ -1281,6 +1282,61 @@ int phmm_populate_regions(phmm_engine* e, const phmm_config* cfg,
         setup.any_flank = setup.any_flank || fl;
     }
     return populate_impl(e, cfg, haps, reads, nullptr, nullptr, out, status, space, 0, nullptr, 0, &setup);
+}
+
+int phmm_populate_ld(phmm_engine* e, const phmm_config* cfg,
+                     const phmm_haplotypes* haps, const phmm_reads* reads,
+                     const phmm_positions* positions, const phmm_flank_state* flank,
+                     double* out, int64_t out_ld, int32_t* status)
+{
+    if (!e) return PHMM_ERR_INVALID;
+    if (!reads || out_ld < reads->n) { e->err = "out_ld must be at least the number of reads"; return PHMM_ERR_INVALID; }
+    return populate_impl(e, cfg, haps, reads, positions, flank, out, status, PHMM_SPACE_DEVICE, (long long)out_ld);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Peer output: one rank's matrix mapped into the other ranks' address spaces (CUDA IPC over NVLink / NVSwitch)
+// -------------------------------------------------------------------------------------------------------------
+int phmm_device_alloc(int device, size_t bytes, void** dev_ptr)
+{
+    if (!dev_ptr || bytes == 0) return PHMM_ERR_INVALID;
+    *dev_ptr = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return PHMM_ERR_CUDA; }
+    if (cudaMalloc(dev_ptr, bytes) != cudaSuccess) { cudaGetLastError(); *dev_ptr = nullptr; return PHMM_ERR_NOMEM; }
+    return PHMM_OK;
+}
+
+int phmm_device_free(void* dev_ptr)
+{
+    if (dev_ptr && cudaFree(dev_ptr) != cudaSuccess) { cudaGetLastError(); return PHMM_ERR_CUDA; }
+    return PHMM_OK;
+}
+
+int phmm_ipc_export(const void* dev_ptr, unsigned char handle[PHMM_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == PHMM_IPC_HANDLE_BYTES, "handle size");
+    if (!dev_ptr || !handle) return PHMM_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)) != cudaSuccess) { cudaGetLastError(); return PHMM_ERR_CUDA; }
+    std::memcpy(handle, &h, sizeof(h));
+    return PHMM_OK;
+}
+
+int phmm_ipc_open(int device, const unsigned char handle[PHMM_IPC_HANDLE_BYTES], void** dev_ptr)
+{
+    if (!handle || !dev_ptr) return PHMM_ERR_INVALID;
+    *dev_ptr = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return PHMM_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    if (cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); *dev_ptr = nullptr; return PHMM_ERR_CUDA; }
+    return PHMM_OK;
+}
+
+int phmm_ipc_close(void* dev_ptr)
+{
+    if (dev_ptr && cudaIpcCloseMemHandle(dev_ptr) != cudaSuccess) { cudaGetLastError(); return PHMM_ERR_CUDA; }
+    return PHMM_OK;
 }
 
 int phmm_populate_templates(phmm_engine* e, const phmm_config* cfg,

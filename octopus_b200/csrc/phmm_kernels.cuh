@@ -78,6 +78,10 @@ __global__ void k_build_tables(const long long n_bases, const char* __restrict__
     if (i >= n_bases) return;
     const int pf = prior_f[i], pr = prior_r[i], o = go[i], e = ge[i];
     if ((pf | pr | o | e) < 0) atomicOr(flags, 1);
+    {   // one atomic per warp that saw a base with gap_open < gap_extend: the DP kernels then keep the general deletion update
+        const unsigned act = __activemask();
+        if (__any_sync(act, o < e) && (int)(threadIdx.x & 31) == __ffs(act) - 1) atomicOr(flags, kFlagOpenBelowExtend);
+    }
     tab_f[i] = make_col_entry(seq[i], mask_f[i], pf & 127, o & 127, e & 127);
     tab_r[i] = make_col_entry(seq[i], mask_r[i], pr & 127, o & 127, e & 127);
 }
@@ -271,22 +275,26 @@ __host__ __device__ constexpr int lanes_per_alignment(const int band) { return b
 __host__ __device__ constexpr int chunk_of(const int band) { return band <= 8 ? 16 : 32; }
 
 // Two alignments (one per packed half) of the lane group this thread belongs to; all lanes of the warp share L.
-template <int BAND>
+template <int BAND, bool OGE>
 __device__ __forceinline__ uint32_t packed_dp(const RowEntry* __restrict__ rows, const int L, const ColEntry* t0, const ColEntry* t1,
-                                              const uint32_t nucp, const int j)
+                                              const uint32_t nucp, const int j, const uint32_t one)
 {
-    if constexpr (BAND <= 16) return dp_pair<BAND>(rows, L, t0, t1, nucp);
+    if constexpr (BAND <= 16) return dp_pair<BAND, OGE>(rows, L, t0, t1, nucp, one);
     else {
         const Lanes16::Tab tab {t0, t1};
-        return dp_band<Lanes16, 32, lanes_per_alignment(BAND)>(rows, L, tab, nucp, j);
+        return dp_band<Lanes16, 32, lanes_per_alignment(BAND), OGE>(rows, L, tab, nucp, j);
     }
 }
+
+// warp-uniform: do the tables of this call allow the shorter deletion update (dp_pair, OGE)?
+__device__ __forceinline__ bool open_ge_extend(const int* __restrict__ flags) { return (*flags & kFlagOpenBelowExtend) == 0; }
 
 // One warp = one read pair; its 2 x (32 / NL) tasks, NL lanes each. The host cuts a read's tasks into chunks of 32 / NL.
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
 k_packed_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTask* __restrict__ tasks,
-               const DevHaps hp, const DevReads rd, const int row_stride, const uint32_t nucp, int* __restrict__ scores)
+               const DevHaps hp, const DevReads rd, const int row_stride, const uint32_t nucp, int* __restrict__ scores,
+               const int* __restrict__ flags, const uint32_t one)
 {
     extern __shared__ RowEntry smem_rows[];
     constexpr int NL = lanes_per_alignment(BAND);
@@ -302,7 +310,7 @@ k_packed_tasks(const WarpWork* __restrict__ works, const int n_works, const Lane
     const LaneTask b = v1 ? tasks[ww.first1 + slot] : a;
     const ColEntry* t0 = (a.reverse ? hp.tab_r : hp.tab_f) + a.tab_index;
     const ColEntry* t1 = (b.reverse ? hp.tab_r : hp.tab_f) + b.tab_index;
-    const uint32_t r = packed_dp<BAND>(rows, ww.L, t0, t1, nucp, j);
+    const uint32_t r = open_ge_extend(flags) ? packed_dp<BAND, true>(rows, ww.L, t0, t1, nucp, j, one) : packed_dp<BAND, false>(rows, ww.L, t0, t1, nucp, j, one);
     if (j == 0) {
         if (v0) scores[a.out_idx] = (int)(r & 0xFFFFu);
         if (v1) scores[b.out_idx] = (int)(r >> 16);
@@ -313,7 +321,8 @@ k_packed_tasks(const WarpWork* __restrict__ works, const int n_works, const Lane
 template <int C, int NL>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
 k_wide_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTask* __restrict__ tasks,
-             const DevHaps hp, const DevReads rd, const int row_stride, const int nuc_prior, int* __restrict__ scores)
+             const DevHaps hp, const DevReads rd, const int row_stride, const int nuc_prior, int* __restrict__ scores,
+             const int* __restrict__ flags)
 {
     extern __shared__ RowEntry smem_rows[];
     const int warps = blockDim.x >> 5;
@@ -330,7 +339,8 @@ k_wide_tasks(const WarpWork* __restrict__ works, const int n_works, const LaneTa
     const bool v = slot < ww.n0;
     const LaneTask a = tasks[v ? ww.first0 + slot : ww.first0];
     const Lanes32::Tab tab {(a.reverse ? hp.tab_r : hp.tab_f) + a.tab_index};
-    const uint32_t r = dp_band<Lanes32, C, NL>(rows, ww.L, tab, (uint32_t)nuc_prior, j);
+    const uint32_t r = open_ge_extend(flags) ? dp_band<Lanes32, C, NL, true>(rows, ww.L, tab, (uint32_t)nuc_prior, j)
+                                             : dp_band<Lanes32, C, NL, false>(rows, ww.L, tab, (uint32_t)nuc_prior, j);
     if (v && j == 0) scores[a.out_idx] = (int)r;
 }
 
@@ -657,6 +667,7 @@ k_populate_fast(const PopParams p)
     RowEntry* rows = smem_rows + (warp * G + grp) * p.row_stride;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     const int n_pairs = tile_pairs(p);
+    const bool oge = open_ge_extend(p.flags);
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(p.pair_cursor, 1);
@@ -703,7 +714,8 @@ k_populate_fast(const PopParams p)
             const unsigned long long sb0 = __shfl_sync(0xffffffffu, (unsigned long long)b0, src), sb1 = __shfl_sync(0xffffffffu, (unsigned long long)b1, src);
             if (!have) { t0 = s0; t1 = s1; b0 = (const ColEntry*)sb0; b1 = (const ColEntry*)sb1; }
             const int h0 = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1 = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
-            const uint32_t res = packed_dp<BAND>(rows, L, b0 + p.hp.off[h0] + a0, b1 + p.hp.off[h1] + a1, nucp, jl);
+            const ColEntry *c0 = b0 + p.hp.off[h0] + a0, *c1 = b1 + p.hp.off[h1] + a1;
+            const uint32_t res = oge ? packed_dp<BAND, true>(rows, L, c0, c1, nucp, jl, (uint32_t)p.one) : packed_dp<BAND, false>(rows, L, c0, c1, nucp, jl, (uint32_t)p.one);
             if (jl == 0) {
                 // at most one candidate per pair (single_candidate): its value IS the pair's minimum — a plain store, no read of best[]
                 if (v0) { int* dst = p.best + pair_slot(p.rd, h0, r0); const int v = (int)(res & 0xFFFFu); if (p.single_candidate) *dst = v; else atomicMin(dst, v); }
@@ -947,6 +959,7 @@ k_populate_wide(const PopParams p)
     RowEntry* rows = smem_rows + warp * p.row_stride;
     if (on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
+    const bool oge = open_ge_extend(p.flags);
     for (;;) {
         int li = 0;
         if (lane == 0) li = atomicAdd(p.pair_cursor, 1);
@@ -970,7 +983,8 @@ k_populate_wide(const PopParams p)
             const uint32_t t = q[valid ? c + slot : 0];
             const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
             const Lanes32::Tab tb {tab + p.hp.off[h] + a};
-            const uint32_t res = dp_band<Lanes32, C, NL>(rows, L, tb, (uint32_t)p.nuc_prior, j);
+            const uint32_t res = oge ? dp_band<Lanes32, C, NL, true>(rows, L, tb, (uint32_t)p.nuc_prior, j)
+                                     : dp_band<Lanes32, C, NL, false>(rows, L, tb, (uint32_t)p.nuc_prior, j);
             if (valid && j == 0) atomicMin(p.best + pair_slot(p.rd, h, r), (int)res);
         }
     }
@@ -1246,7 +1260,8 @@ __global__ void k_fill_int(int* __restrict__ p, const long long n, const int v)
 
 // Floating-point epilogue (haplotype_likelihood_model.cpp:285-303): out[h][r] in double.
 __global__ void k_epilogue(const int* __restrict__ best, int* __restrict__ status, const DevReads rd, const RegionInfo* __restrict__ regs,
-                           const int Hmax, const int use_mapq, const int mapq_cap, const int mapq_trigger, double* __restrict__ out)
+                           const int Hmax, const int use_mapq, const int mapq_cap, const int mapq_trigger, double* __restrict__ out,
+                           const long long out_row_extra /* single region only: output row stride minus the read count */)
 {
     // thread t = (haplotype slot, read), reads fastest: consecutive threads write consecutive outputs within a region
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1258,7 +1273,8 @@ __global__ void k_epilogue(const int* __restrict__ best, int* __restrict__ statu
     const long long i = pair_slot(rd, g.h0 + hl, r);
     const int b = best[i];
     if (b == kBestInf && status[i] == 0) status[i] = 1;
-    out[i] = finish_likelihood(b, use_mapq != 0, rd.mapq[r], mapq_cap, mapq_trigger);
+    // `out` may be another GPU's memory (a peer mapping, phmm_ipc_open): plain coalesced stores, nothing is read back
+    out[i + hl * out_row_extra] = finish_likelihood(b, use_mapq != 0, rd.mapq[r], mapq_cap, mapq_trigger);
 }
 
 } // namespace phmm

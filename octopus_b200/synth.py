@@ -3,7 +3,10 @@
 Haplotypes: a uniform random ACGT "reference" per region with per-haplotype SNVs (~1/100 bp) and short indels
 (~1/150 bp), cut to exactly ``hap_len``; 1 % of haplotypes carry one 'N'. Penalties are drawn from the value range of
 the reference's error-model tables (core/models/error/error_model_factory.cpp:220-523): gap_open 3..45,
-gap_extend 1..10, snv_prior 1..125; snv_mask is the neighbouring base (repeat_based_snv_error_model.cpp:174-178).
+gap_extend 1..10 capped at the position's gap_open (no short-read error model makes an extension dearer than the opening,
+tests/test_error_model.py; ``ordered_penalties=False`` drops the cap and the DP kernels then run their general deletion
+update, phmm_device.cuh dp_pair OGE), snv_prior 1..125; snv_mask is the neighbouring base
+(repeat_based_snv_error_model.cpp:174-178).
 Reads: source haplotype uniform, start uniform in [band, hap_len - L - band] (the in-range rule,
 haplotype_likelihood_model.cpp:187-207), substitutions at 10^(-q/10), one indel with probability ~2e-3 * L,
 strand 50/50, mapq 60. All generation is vectorised numpy; seeds are fixed per config.
@@ -24,7 +27,7 @@ CONFIGS = {
 }
 
 
-def make_haplotypes(rng, n_haps, hap_len):
+def make_haplotypes(rng, n_haps, hap_len, ordered_penalties=True):
     slack = 16
     base = _ACGT[rng.integers(0, 4, hap_len + slack)]
     seqs = np.empty((n_haps, hap_len), dtype=np.uint8)
@@ -50,10 +53,11 @@ def make_haplotypes(rng, n_haps, hap_len):
     mask_f = np.roll(seqs, 1, axis=1).reshape(-1).copy()     # seq[i-1]
     mask_r = np.roll(seqs, -1, axis=1).reshape(-1).copy()    # seq[i+1]
     off = np.arange(n_haps + 1, dtype=np.int64) * hap_len
-    return HaplotypeBlock(off, flat.copy(), mask_f, rng.integers(1, 126, total).astype(np.int8),
-                          mask_r, rng.integers(1, 126, total).astype(np.int8),
-                          rng.integers(3, 46, total).astype(np.int8), rng.integers(1, 11, total).astype(np.int8),
-                          np.zeros(n_haps, dtype=np.int64))
+    prior_f, prior_r = rng.integers(1, 126, total).astype(np.int8), rng.integers(1, 126, total).astype(np.int8)
+    gap_open, gap_extend = rng.integers(3, 46, total).astype(np.int8), rng.integers(1, 11, total).astype(np.int8)
+    if ordered_penalties:
+        gap_extend = np.minimum(gap_extend, gap_open)
+    return HaplotypeBlock(off, flat.copy(), mask_f, prior_f, mask_r, prior_r, gap_open, gap_extend, np.zeros(n_haps, dtype=np.int64))
 
 
 def _qualities(rng, n, L, profile):
@@ -122,7 +126,7 @@ def make_reads(rng, haps: HaplotypeBlock, n_reads, read_lens, band, profile):
     return ReadBlock(off, bases, quals, np.full(n_reads, 60, dtype=np.uint8), reverse, begin)
 
 
-def make_batch(config="C1", n_reads=None, n_haps=None, seed=None, band=None, hap_len=None, read_lens=None):
+def make_batch(config="C1", n_reads=None, n_haps=None, seed=None, band=None, hap_len=None, read_lens=None, ordered_penalties=True):
     """(haplotypes, reads, band) for a named BASELINE config, optionally down-sized (same shapes, fewer reads / haplotypes)
     or re-shaped (band / haplotype length / read lengths overridden: the wide-band and long-read diagnostics)."""
     c = dict(CONFIGS[config])
@@ -137,7 +141,7 @@ def make_batch(config="C1", n_reads=None, n_haps=None, seed=None, band=None, hap
     if n_haps is not None:
         c["n_haps"] = int(n_haps)
     rng = np.random.default_rng(c["seed"] if seed is None else seed)
-    haps = make_haplotypes(rng, c["n_haps"], c["hap_len"])
+    haps = make_haplotypes(rng, c["n_haps"], c["hap_len"], ordered_penalties)
     reads = make_reads(rng, haps, c["n_reads"], c["read_lens"], c["band"], c["quals"])
     return haps, reads, c["band"]
 

@@ -7,10 +7,21 @@
 
 using namespace phmm;
 
-template <int BAND>
-static uint32_t run_pair(int L, const std::vector<RowEntry>& rows, const ColEntry* t0, const ColEntry* t1, uint32_t nucp)
+// Which deletion update the emulated cores use: -1 = as the kernels choose it (the shorter OGE form when no column of the
+// windows has gap_open < gap_extend, kFlagOpenBelowExtend), 0 = always the general form, 1 = always the OGE form.
+static int g_form = -1;
+extern "C" void emul_force_form(int v) { g_form = v; }
+static bool use_oge(const int8_t* go0, const int8_t* ge0, const int8_t* go1, const int8_t* ge1, int W)
 {
-    return dp_pair<BAND>(rows.data(), L, t0, t1, nucp);
+    if (g_form >= 0) return g_form != 0;
+    for (int x = 0; x < W; ++x) if (go0[x] < ge0[x] || (go1 && go1[x] < ge1[x])) return false;
+    return true;
+}
+
+template <int BAND>
+static uint32_t run_pair(int L, const std::vector<RowEntry>& rows, const ColEntry* t0, const ColEntry* t1, uint32_t nucp, bool oge)
+{
+    return oge ? dp_pair<BAND, true>(rows.data(), L, t0, t1, nucp) : dp_pair<BAND, false>(rows.data(), L, t0, t1, nucp);
 }
 
 extern "C" {
@@ -37,10 +48,11 @@ int emul_dp_pair(int band, int L, const char* read0, const uint8_t* q0, const ch
     }
     const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
     uint32_t r;
+    const bool oge = use_oge(go0, ge0, go1, ge1, W);
     switch (band) {
-        case 8:  r = run_pair<8>(L, rows, t0.data(), t1.data(), nucp); break;
-        case 16: r = run_pair<16>(L, rows, t0.data(), t1.data(), nucp); break;
-        case 32: r = run_pair<32>(L, rows, t0.data(), t1.data(), nucp); break;
+        case 8:  r = run_pair<8>(L, rows, t0.data(), t1.data(), nucp, oge); break;
+        case 16: r = run_pair<16>(L, rows, t0.data(), t1.data(), nucp, oge); break;
+        case 32: r = run_pair<32>(L, rows, t0.data(), t1.data(), nucp, oge); break;
         default: return -1;
     }
     *score0 = (int)(r & 0xFFFF);
@@ -138,23 +150,30 @@ extern "C" int emul_dp_flank32(int band, int L, const char* read, const uint8_t*
 
 // The multi-lane band core (band_lane_* in phmm_device.cuh) with its NL lanes stepped in lock-step on the CPU: the two
 // exchanges dp_band performs with shuffles are done by hand between the phases.
-template <class T, int C, int NL>
-static typename T::V run_band(const RowEntry* rows, int L, const typename T::Tab& tab, typename T::V nucp)
+template <class T, int C, int NL, bool OGE>
+static typename T::V run_band_form(const RowEntry* rows, int L, const typename T::Tab& tab, typename T::V nucp)
 {
     static BandLane<T, C> s[NL];
     const int W = L + NL * C - 1;
     for (int j = 0; j < NL; ++j) band_lane_init<T, C>(s[j], tab, j * C);
     for (int t = 0; t <= W; ++t) {
         typename T::V d_in[NL], i_in[NL];
-        for (int j = 0; j < NL; ++j) { const int x = t - (NL - 1 - j); band_lane_top<T, C>(s[j], rows, L, x - j * C, x, W, tab, nucp, j == NL - 1); }
+        for (int j = 0; j < NL; ++j) { const int x = t - (NL - 1 - j); band_lane_top<T, C, OGE>(s[j], rows, L, x - j * C, x, W, tab, nucp, j == NL - 1); }
         for (int j = 0; j < NL; ++j) d_in[j] = j > 0 ? s[j - 1].d_out : T::inf();
-        for (int j = 0; j < NL; ++j) { const int x = t - (NL - 1 - j); band_lane_rest<T, C>(s[j], rows, L, x - j * C, x, d_in[j], j == 0); }
+        for (int j = 0; j < NL; ++j) { const int x = t - (NL - 1 - j); band_lane_rest<T, C, OGE>(s[j], rows, L, x - j * C, x, d_in[j], j == 0); }
         for (int j = 0; j < NL; ++j) i_in[j] = j < NL - 1 ? s[j + 1].i_run : T::inf();
         for (int j = 0; j < NL; ++j) s[j].i_run = i_in[j];
     }
     typename T::V best = band_lane_result<T, C>(s[0]);
     for (int j = 1; j < NL; ++j) best = T::min2(best, band_lane_result<T, C>(s[j]));
     return best;
+}
+
+static bool g_band_oge = false;      // set by emul_dp_band before run_band_any
+template <class T, int C, int NL>
+static typename T::V run_band(const RowEntry* rows, int L, const typename T::Tab& tab, typename T::V nucp)
+{
+    return g_band_oge ? run_band_form<T, C, NL, true>(rows, L, tab, nucp) : run_band_form<T, C, NL, false>(rows, L, tab, nucp);
 }
 
 template <class T>
@@ -185,6 +204,7 @@ extern "C" int emul_dp_band(int word32, int band, int L, const char* read0, cons
         t0[x] = make_col_entry(truth0[x], mask0[x], prior0[x], go0[x], ge0[x]);
         t1[x] = make_col_entry(truth1[x], mask1[x], prior1[x], go1[x], ge1[x]);
     }
+    g_band_oge = word32 ? use_oge(go0, ge0, nullptr, nullptr, W) : use_oge(go0, ge0, go1, ge1, W);
     if (word32) {
         for (int y = 0; y < L; ++y) {
             const int c = base_code(read0[y]);

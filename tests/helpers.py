@@ -4,7 +4,7 @@ import numpy as np
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-def random_alignment_case(rng, band, L, n_rate=0.2, qmax=41, read_n=False):
+def random_alignment_case(rng, band, L, n_rate=0.2, qmax=41, read_n=False, open_ge_extend=False):
     """One raw-kernel input: truth window (W = L + 2*band - 1) and a read derived from it with subs / indels."""
     W = L + 2 * band - 1
     truth = ACGT[rng.integers(0, 4, W)].copy()
@@ -28,11 +28,15 @@ def random_alignment_case(rng, band, L, n_rate=0.2, qmax=41, read_n=False):
     read = np.array(read[:L], dtype=np.uint8)
     if read_n and L > 2:
         read[rng.integers(0, L)] = ord("N")
+    gap_open = rng.integers(3, 46, W).astype(np.int8)
+    gap_extend = rng.integers(1, 11, W).astype(np.int8)
+    if open_ge_extend:          # what every built-in error model produces: an extension never costs more than the opening
+        gap_extend = np.minimum(gap_extend, gap_open)
     return dict(
         truth=truth, read=read,
         quals=rng.integers(2, qmax + 1, L).astype(np.uint8),
-        gap_open=rng.integers(3, 46, W).astype(np.int8),
-        gap_extend=rng.integers(1, 11, W).astype(np.int8),
+        gap_open=gap_open,
+        gap_extend=gap_extend,
         snv_mask=np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, W)].copy(),
         snv_prior=rng.integers(1, 126, W).astype(np.int8),
     )

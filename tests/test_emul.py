@@ -19,6 +19,8 @@ def emul():
     lib.emul_generic.argtypes = [C.c_int, C.c_int, C.c_int] + [vp] * 7 + [C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.emul_pair_evaluate.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,
                                        C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.emul_dp_band.argtypes = [C.c_int, C.c_int, C.c_int] + [vp] * 14 + [C.c_int, vp, vp]
+    lib.emul_force_form.argtypes = [C.c_int]
     return lib
 
 
@@ -43,6 +45,73 @@ def test_packed_dp_pair_matches_oracle(emul, coracle):
         e = [coracle.align(band, c["truth"].tobytes(), c["read"].tobytes(), c["quals"].astype(np.int8), c["gap_open"], c["gap_extend"],
                            nuc, c["snv_mask"].tobytes(), c["snv_prior"]) for c in (a, b)]
         assert [s0.value, s1.value] == e, (band, L, nuc)
+
+
+def _oracle_pair(coracle, band, nuc, cases):
+    return [coracle.align(band, c["truth"].tobytes(), c["read"].tobytes(), c["quals"].astype(np.int8), c["gap_open"], c["gap_extend"],
+                          nuc, c["snv_mask"].tobytes(), c["snv_prior"]) for c in cases]
+
+
+def test_open_ge_extend_form_of_the_deletion_update(emul, coracle):
+    """dp_pair<.., OGE> / dp_band<.., OGE>: with gap_open >= gap_extend in every column the deletion update re-uses min(m, i, d)
+    and must give the oracle's score (this is the form the kernels run on every error-model penalty array); the general form on
+    the same inputs agrees; and on inputs that break the precondition the kernels' own choice (the general form) is exact while
+    the OGE form is allowed to differ — at least once in this sample it does, which is why the flag exists."""
+    rng = np.random.default_rng(411)
+    differs = 0
+    for it in range(900):
+        band = int(rng.choice([8, 16, 32, 64]))
+        L = int(rng.integers(1, 180))
+        nuc = int(rng.integers(0, 5))
+        ordered = it % 3 != 0
+        a = random_alignment_case(rng, band, L, open_ge_extend=ordered)
+        b = random_alignment_case(rng, band, L, open_ge_extend=ordered)
+        if it % 7 == 0:      # equality everywhere: the boundary of the precondition
+            a["gap_extend"] = a["gap_open"].copy()
+        want = _oracle_pair(coracle, band, nuc, (a, b))
+        args = [P(a["read"]), P(a["quals"]), P(b["read"]), P(b["quals"]),
+                P(a["truth"]), P(a["snv_mask"]), P(a["snv_prior"]), P(a["gap_open"]), P(a["gap_extend"]),
+                P(b["truth"]), P(b["snv_mask"]), P(b["snv_prior"]), P(b["gap_open"]), P(b["gap_extend"])]
+        for form in ((-1, 1, 0) if ordered else (-1, 0, 1)):
+            emul.emul_force_form(form)
+            got = []
+            s0, s1 = C.c_int(0), C.c_int(0)
+            if band <= 32:
+                assert emul.emul_dp_pair(band, L, *args, nuc, C.byref(s0), C.byref(s1)) == 0
+                got.append([s0.value, s1.value])
+            assert emul.emul_dp_band(0, band, L, *args, nuc, C.byref(s0), C.byref(s1)) == 0
+            got.append([s0.value, s1.value])
+            assert emul.emul_dp_band(1, band, L, *args, nuc, C.byref(s0), C.byref(s1)) == 0
+            got.append([s0.value, want[1]])
+            if ordered or form != 1:
+                assert all(g == want for g in got), (band, L, nuc, form, got, want)
+            else:
+                differs += any(g != want for g in got)
+        emul.emul_force_form(-1)
+    assert differs > 0
+
+
+def test_multi_lane_band_matches_oracle(emul, coracle):
+    """dp_band (the band's diagonals split over lanes, stepped in lock-step here): packed and 32-bit lanes, bands 8 .. 256."""
+    rng = np.random.default_rng(412)
+    for it in range(500):
+        band = int(rng.choice([8, 16, 32, 64, 128, 256]))
+        L = int(rng.integers(1, 260))
+        nuc = int(rng.integers(0, 5))
+        a = random_alignment_case(rng, band, L, open_ge_extend=(it % 2 == 0))
+        b = random_alignment_case(rng, band, L, open_ge_extend=(it % 2 == 0))
+        want = _oracle_pair(coracle, band, nuc, (a, b))
+        args = [P(a["read"]), P(a["quals"]), P(b["read"]), P(b["quals"]),
+                P(a["truth"]), P(a["snv_mask"]), P(a["snv_prior"]), P(a["gap_open"]), P(a["gap_extend"]),
+                P(b["truth"]), P(b["snv_mask"]), P(b["snv_prior"]), P(b["gap_open"]), P(b["gap_extend"])]
+        s0, s1 = C.c_int(0), C.c_int(0)
+        assert emul.emul_dp_band(0, band, L, *args, nuc, C.byref(s0), C.byref(s1)) == 0
+        assert [s0.value, s1.value] == want, (band, L, nuc)
+        n = random_alignment_case(rng, band, L, read_n=True)
+        wn = _oracle_pair(coracle, band, nuc, (n,))[0]
+        nargs = [P(n["read"]), P(n["quals"]), P(n["read"]), P(n["quals"])] + [P(n[k]) for k in ("truth", "snv_mask", "snv_prior", "gap_open", "gap_extend")] * 2
+        assert emul.emul_dp_band(1, band, L, *nargs, nuc, C.byref(s0), C.byref(s1)) == 0
+        assert s0.value == wn, (band, L, nuc)
 
 
 def test_packed_dp_pair_reference_kats(emul, kats):

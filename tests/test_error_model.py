@@ -75,6 +75,24 @@ def test_every_builtin_model_equals_the_reference(ref):
         assert ref.reset(b"ACGT", bad)["rc"] < 0
 
 
+def test_short_read_models_never_make_an_extension_dearer_than_the_opening():
+    """gap_open[x] >= gap_extend[x] at every position of every short-read model's output (HiSeq / X10 / NovaSeq / BGISEQ, all
+    library preparations): the precondition of the DP kernels' shorter deletion update (phmm_device.cuh dp_pair, OGE). The PacBio
+    models break it inside long homopolymers, as a custom model may: such arrays raise kFlagOpenBelowExtend on the device and the
+    call runs the general update. This test records which built-in models are on which side."""
+    from octopus_b200 import ErrorModel
+    rng = np.random.default_rng(99)
+    seqs = [repeat_rich_sequence(rng, 600) for _ in range(150)]
+    for period in (1, 2, 3, 4, 5, 6):                       # long pure repeats: the lowest opening penalties of every table
+        seqs.append(np.tile(ACGT[rng.integers(0, 4, period)], 400 // period))
+    violating = set()
+    for label in LABELS:
+        block = ErrorModel(label).reset(seqs, n_threads=3)
+        if any((block.hap(h)["gap_open"] < block.hap(h)["gap_extend"]).any() for h in range(len(seqs))):
+            violating.add(label)
+    assert violating and all("PacBio" in label for label in violating), violating
+
+
 def test_custom_model_text_equals_the_reference(ref):
     from octopus_b200 import ErrorModel, PhmmError
     rng = np.random.default_rng(11)
