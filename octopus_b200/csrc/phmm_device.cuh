@@ -340,13 +340,15 @@ struct BandLane {
     typename T::Ent e, next;  // table entries of the column being processed / prefetched for the next one
     typename T::Col col;
     typename T::V gop, gep, go_prev, ge_prev;
+    uint32_t one;             // 1; opaque to the compiler in the kernels, so that the cells' additions are IMADs on the FMA pipe (fma_add)
     bool active;
 };
 
 // first_col: the first window column this lane processes (j * C); the penalties of the column before it feed its insertions
 template <class T, int C>
-PHMM_HD void band_lane_init(BandLane<T, C>& s, const typename T::Tab& tab, const int first_col)
+PHMM_HD void band_lane_init(BandLane<T, C>& s, const typename T::Tab& tab, const int first_col, const uint32_t one = 1u)
 {
+    s.one = one;
 #pragma unroll
     for (int k = 0; k < C; ++k) { s.M[k] = 0u; s.D[k] = T::inf(); }
     s.i_run = T::inf(); s.d_out = T::inf();
@@ -374,9 +376,9 @@ PHMM_HD void band_lane_top(BandLane<T, C>& s, const RowEntry* __restrict__ rows,
         const RowEntry w = rows[xl - (C - 1)];
         const typename T::V sub = T::sub(w, s.col), m = s.M[C - 1], d = s.D[C - 1];
         const typename T::V sm = T::min3(m, s.i_run, d);
-        s.M[C - 1] = sm + sub;
-        s.d_out = T::addmin(d, s.col.ge, (OGE ? sm : T::min2(m, s.i_run)) + s.col.go);      // OGE: see dp_pair
-        s.i_run = T::addmin(s.i_run, s.gep, m + s.gop);
+        s.M[C - 1] = fma_add(sm, sub, s.one);
+        s.d_out = T::addmin(d, s.col.ge, fma_add(OGE ? sm : T::min2(m, s.i_run), s.col.go, s.one));      // OGE: see dp_pair
+        s.i_run = T::addmin(s.i_run, s.gep, fma_add(m, s.gop, s.one));
     }
 }
 
@@ -390,6 +392,7 @@ PHMM_HD void band_lane_rest(BandLane<T, C>& s, const RowEntry* __restrict__ rows
     const RowEntry* rp = rows + xl;
     const typename T::Col col = s.col;
     const typename T::V gop = s.gop, gep = s.gep;
+    const uint32_t one = s.one;
     typename T::V i_run = s.i_run;
 #define PHMM_BCELL(k)                                                                          \
     {                                                                                           \
@@ -397,9 +400,9 @@ PHMM_HD void band_lane_rest(BandLane<T, C>& s, const RowEntry* __restrict__ rows
         const typename T::V sub = T::sub(w, col);                                               \
         const typename T::V m = s.M[(k) < C ? (k) : 0], d = s.D[(k) < C ? (k) : 0];            \
         const typename T::V sm = T::min3(m, i_run, d);                                          \
-        s.M[(k) < C ? (k) : 0] = sm + sub;                                                      \
-        if ((k) + 1 < C) s.D[((k) + 1) < C ? (k) + 1 : 0] = T::addmin(d, col.ge, (OGE ? sm : T::min2(m, i_run)) + col.go); \
-        i_run = T::addmin(i_run, gep, m + gop);                                                 \
+        s.M[(k) < C ? (k) : 0] = fma_add(sm, sub, one);                                         \
+        if ((k) + 1 < C) s.D[((k) + 1) < C ? (k) + 1 : 0] = T::addmin(d, col.ge, fma_add(OGE ? sm : T::min2(m, i_run), col.go, one)); \
+        i_run = T::addmin(i_run, gep, fma_add(m, gop, one));                                    \
     }
 #define PHMM_BCASE_PROLOGUE(k) case (k) + 1: if ((k) + 1 < C) PHMM_BCELL(k)
 #define PHMM_BCASE_ROW0(k)     case (k): if ((k) < C) s.M[(k) < C ? (k) : 0] = sub0; break;
@@ -452,11 +455,11 @@ PHMM_HD typename T::V band_lane_result(const BandLane<T, C>& s)
 // must call this with the same L (the loop and its shuffles are warp-wide). Returns the group's result in all of its lanes.
 template <class T, int C, int NL, bool OGE = false>
 __device__ __forceinline__ typename T::V dp_band(const RowEntry* __restrict__ rows, const int L, const typename T::Tab& tab,
-                                                 const typename T::V nucp, const int j)
+                                                 const typename T::V nucp, const int j, const uint32_t one = 1u)
 {
     BandLane<T, C> s;
     const int W = L + NL * C - 1;
-    band_lane_init<T, C>(s, tab, j * C);
+    band_lane_init<T, C>(s, tab, j * C, one);
     for (int t = 0; t <= W; ++t) {
         const int x = t - (NL - 1 - j), xl = x - j * C;
         band_lane_top<T, C, OGE>(s, rows, L, xl, x, W, tab, nucp, j == NL - 1);
@@ -766,8 +769,9 @@ constexpr int kMaxScoreTb = 0x7000 - 1024;       // quality-sum bound of this pa
 PHMM_HD RowEntry make_row_entry_tb(uint32_t half) { RowEntry r; r.x = 0x5055u | ((half & 7u) << 8); r.y = (half >> 8) << 16; return r; }
 PHMM_HD RowEntry pad_row_entry_tb() { RowEntry r; r.x = 0x5055u; r.y = 0u; return r; }
 
-// Row entries of the traceback kernel come either as 8-byte RowEntry (tests) or packed in 4 bytes (quality << 16 | code << 8: the
-// kernel stages one read PER THREAD in shared memory, so the footprint decides the occupancy) and are decoded at the use.
+// Row entries of the traceback kernel come as 8-byte RowEntry (tests), packed in 4 bytes (quality << 16 | code << 8) or as the read's
+// 2-byte row half-words (TbRows2, what the kernel uses: it stages one read PER THREAD in shared memory, so the footprint decides the
+// occupancy) and are decoded at the use.
 struct TbRows8 { const RowEntry* p; PHMM_HD RowEntry at(const int i) const { return p[i]; } PHMM_HD TbRows8 shifted(const int x) const { return TbRows8 {p + x}; } };
 struct TbRows4
 {
@@ -775,6 +779,14 @@ struct TbRows4
     PHMM_HD RowEntry at(const int i) const { const uint32_t w = p[i]; RowEntry r; r.x = 0x5055u | (w & 0x700u); r.y = w & 0xFFFF0000u; return r; }
     PHMM_HD TbRows4 shifted(const int x) const { return TbRows4 {p + x}; }
     static PHMM_HD uint32_t pack(const uint32_t half) { return ((half >> 8) << 16) | ((half & 7u) << 8); }     // from the read's row half-word (code | qual << 8)
+};
+
+// the read's row half-words themselves (code | qual << 8), 2 bytes per read base: 302 B per 150 bp read and thread
+struct TbRows2
+{
+    const uint16_t* p;
+    PHMM_HD RowEntry at(const int i) const { const uint32_t t = (uint32_t)p[i] << 8; RowEntry r; r.x = 0x5055u | (t & 0x700u); r.y = t & 0xFFFF0000u; return r; }
+    PHMM_HD TbRows2 shifted(const int x) const { return TbRows2 {p + x}; }
 };
 
 template <int BAND, class RowsT>

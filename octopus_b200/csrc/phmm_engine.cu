@@ -676,10 +676,10 @@ static int align_impl(phmm_engine* e, const phmm_config* cfg, const phmm_haploty
     const int K = 2 * band;
     static const bool no_fast_align = std::getenv("PHMM_NO_FAST_ALIGN") != nullptr;      // measurement hook: the generic traceback kernel for everything
     p.fast_band = (band <= 32 && !no_fast_align) ? band : 0;
-    const int fast_cap = (int)((200 << 10) / (kAlignFastThreads * (int)sizeof(uint32_t))) - 2;      // one block's rows in shared memory
+    const int fast_cap = (int)((200 << 10) / (kAlignFastThreads * (int)sizeof(uint16_t))) - 4;      // one block's rows in shared memory
     p.fast_max_len = std::min(Lmax, fast_cap);
-    p.fast_row_stride = (p.fast_max_len + 1) | 1;
-    const size_t fsmem = (size_t)kAlignFastThreads * p.fast_row_stride * sizeof(uint32_t);
+    p.fast_row_stride = 2 * (((p.fast_max_len + 2) / 2) | 1);                                      // in half-words; 2 * odd (bank spread)
+    const size_t fsmem = (size_t)kAlignFastThreads * p.fast_row_stride * sizeof(uint16_t);
     int fast_blocks_per_sm = 1;
     if (p.fast_band) {
         switch (band) {

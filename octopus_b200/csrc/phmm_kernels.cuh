@@ -282,7 +282,7 @@ __device__ __forceinline__ uint32_t packed_dp(const RowEntry* __restrict__ rows,
     if constexpr (BAND <= 16) return dp_pair<BAND, OGE>(rows, L, t0, t1, nucp, one);
     else {
         const Lanes16::Tab tab {t0, t1};
-        return dp_band<Lanes16, 32, lanes_per_alignment(BAND), OGE>(rows, L, tab, nucp, j);
+        return dp_band<Lanes16, 32, lanes_per_alignment(BAND), OGE>(rows, L, tab, nucp, j, one);
     }
 }
 
@@ -983,8 +983,8 @@ k_populate_wide(const PopParams p)
             const uint32_t t = q[valid ? c + slot : 0];
             const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
             const Lanes32::Tab tb {tab + p.hp.off[h] + a};
-            const uint32_t res = oge ? dp_band<Lanes32, C, NL, true>(rows, L, tb, (uint32_t)p.nuc_prior, j)
-                                     : dp_band<Lanes32, C, NL, false>(rows, L, tb, (uint32_t)p.nuc_prior, j);
+            const uint32_t res = oge ? dp_band<Lanes32, C, NL, true>(rows, L, tb, (uint32_t)p.nuc_prior, j, (uint32_t)p.one)
+                                     : dp_band<Lanes32, C, NL, false>(rows, L, tb, (uint32_t)p.nuc_prior, j, (uint32_t)p.one);
             if (valid && j == 0) atomicMin(p.best + pair_slot(p.rd, h, r), (int)res);
         }
     }
@@ -1187,8 +1187,8 @@ template <int BAND>
 __global__ void __launch_bounds__(kAlignFastThreads)
 k_align_reads_fast(const AlignParams p)
 {
-    extern __shared__ uint32_t smem_rows32[];
-    uint32_t* rows = smem_rows32 + (size_t)threadIdx.x * p.fast_row_stride;     // stride odd: the threads of a warp hit distinct banks
+    extern __shared__ uint16_t smem_rows16[];
+    uint16_t* rows = smem_rows16 + (size_t)threadIdx.x * p.fast_row_stride;     // stride = 2 * odd: the threads of a warp hit distinct banks
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     char* s0 = p.strings + (size_t)tid * 4 * p.str_cap;
     for (int i = tid; i < p.n_pairs; i += nthreads) {
@@ -1197,14 +1197,14 @@ k_align_reads_fast(const AlignParams p)
         {
             const long long ro = p.rd.off[r];
             const int L = p.rd.info[r].x;
-            for (int y = 0; y < L; ++y) rows[y] = TbRows4::pack(p.rd.rowhalf[ro + y]);
-            rows[L] = 0u;                                                        // the pad row: code 0, quality 0
+            for (int y = 0; y < L; ++y) rows[y] = p.rd.rowhalf[ro + y];
+            rows[L] = 0;                                                         // the pad row: code 0, quality 0
         }
         const ColEntry* tabs = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
         const int h = p.pairs[i].y;
         align_pair(p, i, s0, [&](const HapView& hv, const ReadView& rv, const int a, const int lhs, const int rhs, int* fp, int* fs, int* ms, char* c1, char* c2) {
             int score, x_end, state;
-            dp_traceback_forward<BAND>(TbRows4 {rows}, rv.len, tabs + p.hp.off[h] + a, p.nuc_prior, p.bp32 + tid, (size_t)nthreads, &score, &x_end, &state);
+            dp_traceback_forward<BAND>(TbRows2 {rows}, rv.len, tabs + p.hp.off[h] + a, p.nuc_prior, p.bp32 + tid, (size_t)nthreads, &score, &x_end, &state);
             const TbModel gm {hv.seq + a, hv.snv_mask + a, hv.snv_prior + a, hv.gap_open + a, hv.gap_extend + a, p.nuc_prior};
             traceback_walk<BAND>(p.bp32 + tid, (size_t)nthreads, gm, rv.bases, rv.quals, rv.len, x_end, state, lhs, rhs, fp, fs, ms, c1, c2);
             return score;

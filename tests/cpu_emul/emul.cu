@@ -269,24 +269,29 @@ extern "C" int emul_traceback(int band, int L, const char* read, const uint8_t* 
                               int* score, int* first_pos, int* flank, int* mask_size, char* align1, char* align2)
 {
     const int W = L + 2 * band - 1;
-    std::vector<RowEntry> rows(L + 1);
+    std::vector<uint16_t> rows(L + 1);                      // the kernel's staging: the read's row half-words (TbRows2), pad row 0
     for (int y = 0; y < L; ++y) {
         const int c = base_code(read[y]);
         if (c < 0) return -1;
-        rows[y] = make_row_entry_tb((uint32_t)c | ((uint32_t)q[y] << 8));
+        rows[y] = (uint16_t)((uint32_t)c | ((uint32_t)q[y] << 8));
+        const RowEntry a = TbRows2 {rows.data()}.at(y), b = make_row_entry_tb(rows[y]);
+        if (a.x != b.x || a.y != b.y) return -2;            // the three row layouts decode to the same entry
+        const uint32_t w4 = TbRows4::pack(rows[y]);
+        const RowEntry c4 = TbRows4 {&w4}.at(0);
+        if (c4.x != b.x || c4.y != b.y) return -2;
     }
-    rows[L] = pad_row_entry_tb();
+    rows[L] = 0;
     std::vector<ColEntry> t(W);
     for (int x = 0; x < W; ++x) t[x] = make_col_entry(truth[x], mask[x], prior[x], go[x], ge[x]);
     std::vector<uint32_t> bp((size_t)(W + 1) * 2 * band, 0u);
     int x_end = -1, state = 0;
     const TbModel gm {truth, mask, prior, go, ge, nuc_prior};
     switch (band) {
-        case 8:  dp_traceback_forward<8>(TbRows8 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
+        case 8:  dp_traceback_forward<8>(TbRows2 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
                  traceback_walk<8>(bp.data(), 1, gm, read, q, L, x_end, state, lhs_flank, rhs_flank, first_pos, flank, mask_size, align1, align2); break;
-        case 16: dp_traceback_forward<16>(TbRows8 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
+        case 16: dp_traceback_forward<16>(TbRows2 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
                  traceback_walk<16>(bp.data(), 1, gm, read, q, L, x_end, state, lhs_flank, rhs_flank, first_pos, flank, mask_size, align1, align2); break;
-        case 32: dp_traceback_forward<32>(TbRows8 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
+        case 32: dp_traceback_forward<32>(TbRows2 {rows.data()}, L, t.data(), nuc_prior, bp.data(), 1, score, &x_end, &state);
                  traceback_walk<32>(bp.data(), 1, gm, read, q, L, x_end, state, lhs_flank, rhs_flank, first_pos, flank, mask_size, align1, align2); break;
         default: return -1;
     }
