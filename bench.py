@@ -75,13 +75,19 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def issue_roofline(kernel_gcups, reads, band, clocks):
+def issue_roofline(kernel_gcups, reads, band, clocks, alu_ops):
+    """The binding roofline of the packed DP: `alu_ops` half-rate ALU-pipe instructions per cell pair (5 when
+    gap_open >= gap_extend everywhere — the OGE deletion update — else 6) at 64 thread-instructions/clk/SM; beside it the issue
+    bound of the steady-state loop (9.6 warp instructions per cell pair, SASS). Both in the reference's cell count 2(L+B)B per
+    alignment (the column sweep itself touches 2LB cells)."""
     lens = np.diff(np.asarray(reads.off))
     mean_ratio = float(((lens + band) / lens).mean())
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    peak = 148 * mhz * 1e6 * (64.0 / 3.0) * mean_ratio / 1e9
+    peak = 148 * mhz * 1e6 * (64.0 * 2.0 / alu_ops) * mean_ratio / 1e9
+    issue_peak = 148 * mhz * 1e6 * (4 * 64.0 / 9.6) * mean_ratio / 1e9
     return {"bound": "alu-pipe (DPX packed-16)", "achieved": kernel_gcups, "peak": peak, "unit": "GCUPS", "frac": kernel_gcups / peak,
-            "alu_instr_per_cell_pair": 6, "alu_thread_instr_per_clk_per_sm": 64, "sm_mhz": mhz}
+            "alu_instr_per_cell_pair": alu_ops, "alu_thread_instr_per_clk_per_sm": 64, "sm_mhz": mhz,
+            "issue_peak": issue_peak, "issue_frac": kernel_gcups / issue_peak, "warp_instr_per_cell_pair": 9.6}
 
 
 class ClockSampler:
@@ -546,10 +552,10 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the path is integer-issue bound, not HBM bound (SURVEY.md F3); see DESIGN.md for the issue-rate roofline",
                          "kernel_gcups": cells_rank / (kernel_ms / 1e3) / 1e9},
-            # The binding roofline: the packed cell costs 6 ALU-pipe instructions per 2 cells and the ALU pipe
-            # issues 64 thread-instructions/clk/SM (profiles/r01_ubench_int.txt). In the reference's cell count 2(L+B)B per
-            # alignment (the column sweep itself touches 2LB cells) the peak is 148 SMs x clock x 64/3 x (L+B)/L.
-            "issue_roofline": issue_roofline(cells_rank / (kernel_ms / 1e3) / 1e9, reads, band, clocks),
+            # The binding roofline: the packed cell costs 5 (6 for unordered penalties) ALU-pipe instructions per 2 cells
+            # and the ALU pipe issues 64 thread-instructions/clk/SM (profiles/r01_ubench_int.txt).
+            "issue_roofline": issue_roofline(cells_rank / (kernel_ms / 1e3) / 1e9, reads, band, clocks,
+                                             5 if all(bool((np.asarray(h.gap_open) >= np.asarray(h.gap_extend)).all()) for h, _ in regions) else 6),
         }
         ref_scores, n_ref = None, 0
         if not args.no_cpu_baseline:
