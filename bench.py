@@ -522,8 +522,10 @@ def main():
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
         mode_key = "flank" if flank_state else ("ref" if (args.shortcut or args.map) else "dp")
         traffic = measured_traffic(args.config, R, H, band, mode_key)
+        role_warps = band in (32, 64) and H >= 17 and not os.environ.get("PHMM_NO_ROLE_WARPS")     # the engine's own rule (populate_impl)
         kernel_name = ("k_populate_flank_acc<%d>" % band) if flank_state and band <= 32 else \
-                      ("k_populate_wide (32-bit lanes, band %d)" % band) if args.int_scores else "k_populate_fast<%d>" % band
+                      ("k_populate_wide (32-bit lanes, band %d)" % band) if args.int_scores else \
+                      ("k_populate_roles<%d> (one warp per 32 diagonals)" % band) if role_warps else "k_populate_fast<%d>" % band
         how = "none: one rank" if world == 1 else ("peer stores: every rank's epilogue kernel writes into rank 0's HBM through a CUDA IPC mapping, one barrier per step"
                                                    if peer_ring is not None else "NCCL gather per step, overlapped with the next step's compute")
         line = {

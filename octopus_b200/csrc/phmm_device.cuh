@@ -473,6 +473,52 @@ __device__ __forceinline__ typename T::V dp_band(const RowEntry* __restrict__ ro
     for (int o = 1; o < NL; o <<= 1) best = T::min2(best, __shfl_xor_sync(0xffffffffu, best, o));
     return best;
 }
+
+// The same band with one WARP per chunk ("role") instead of one lane: warp j of a group of NL warps owns chunk j of 32 tasks (one per
+// lane), the two hand-overs go through shared memory and a named barrier each. Why: with the chunks in neighbouring lanes, the lane
+// that owns the upper diagonals is ~C columns behind the lower one in PHASE (still in its prologue / already in its epilogue while the
+// other runs the steady body) and lanes in different column bodies are divergent — the warp runs both bodies one after the other, 70 %
+// lane efficiency at L = 150, C = 32, NL = 2. A warp per role has every lane of a warp in the same body, and a role that has nothing to
+// do in a step only waits at the barriers, where it costs no issue slot.
+//   xchg: shared memory of the group, 3 * NL * 32 words: [0] D hand-over, [1] I hand-over, [2] the roles' partial results.
+//   All 32 lanes of all NL warps must call this with the same L (the loop and its barriers are group-wide).
+__device__ __forceinline__ void group_barrier(const int id, const int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+template <class T, int C, int NL, bool OGE = false>
+__device__ __forceinline__ typename T::V dp_band_roles(const RowEntry* __restrict__ rows, const int L, const typename T::Tab& tab,
+                                                       const typename T::V nucp, const int j, const int lane, const uint32_t one,
+                                                       typename T::V* xchg, const int barrier_id)
+{
+    BandLane<T, C> s;
+    const int W = L + NL * C - 1;
+    band_lane_init<T, C>(s, tab, j * C, one);
+    typename T::V* d_slots = xchg + lane;
+    typename T::V* i_slots = xchg + NL * 32 + lane;
+    typename T::V* r_slots = xchg + 2 * NL * 32 + lane;
+    for (int t = 0; t <= W; ++t) {
+        const int x = t - (NL - 1 - j), xl = x - j * C;
+        band_lane_top<T, C, OGE>(s, rows, L, xl, x, W, tab, nucp, j == NL - 1);
+        if (j < NL - 1) d_slots[j * 32] = s.d_out;
+        group_barrier(barrier_id, NL * 32);
+        const typename T::V d_in = j > 0 ? d_slots[(j - 1) * 32] : T::inf();
+        band_lane_rest<T, C, OGE>(s, rows, L, xl, x, d_in, j == 0);
+        if (j > 0) i_slots[j * 32] = s.i_run;
+        group_barrier(barrier_id, NL * 32);
+        s.i_run = j < NL - 1 ? i_slots[(j + 1) * 32] : T::inf();
+    }
+    // the next call's first write to r_slots is two barriers (at least one whole step) away from the reads below
+    typename T::V best = band_lane_result<T, C>(s);
+    if (j > 0) r_slots[j * 32] = best;
+    group_barrier(barrier_id, NL * 32);
+    if (j == 0) {
+#pragma unroll
+        for (int o = 1; o < NL; ++o) best = T::min2(best, r_slots[o * 32]);
+    }
+    return best;          // complete in role 0 only
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------------------

@@ -68,7 +68,6 @@ struct phmm_engine {
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
     // per-kernel launch configuration already applied / queried (the runtime calls are not free and need not be repeated)
-    std::map<const void*, size_t> smem_set;
     std::map<std::pair<const void*, size_t>, int> occupancy;
     // host-space calls on large batches are pipelined over two sub-engines (own stream + buffers each), driven by two host
     // threads, so that the H2D / D2H copies of one read chunk overlap the kernels of the other
@@ -253,11 +252,17 @@ int stage_batch(phmm_engine* e, const phmm_haplotypes* haps, const phmm_reads* r
     return PHMM_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (device, kernel) pair, not to an engine: several engines of one process
+// (the two pipeline sub-engines, an application's own) share it, and setting it to a smaller value LOWERS the limit another engine's
+// next launch relies on. So the high-water mark is kept per process and the attribute is only ever raised.
 template <typename F>
 int fast_smem_attr(phmm_engine* e, F kernel, size_t bytes)
 {
-    size_t& have = e->smem_set[(const void*)kernel];
-    if (bytes <= have && have != 0) return PHMM_OK;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> high_water;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = high_water[std::make_pair(e->device, (const void*)kernel)];
+    if (bytes <= have) return PHMM_OK;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     have = bytes;
     return PHMM_OK;
@@ -1036,6 +1041,17 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         PHMM_FAST_DISPATCH(PHMM_FAST_SETUP)
         if (blocks_per_sm < 1) { e->err = "fast kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; }
     }
+    // bands 32 / 64 with enough tasks per read to fill a warp: one WARP per chunk of the band (k_populate_roles) instead of one lane
+    static const bool no_role_warps = std::getenv("PHMM_NO_ROLE_WARPS") != nullptr;       // measurement hook: the lane-per-chunk kernel for every band
+    bool role_warps = n_pairs && (band == 32 || band == 64) && groups == 1 && !no_role_warps;
+    const int role_groups = kFastWarpsPerBlock / std::max(1, NL);
+    const size_t role_smem = role_warps ? (size_t)role_groups * fast_row_stride * sizeof(RowEntry) + (size_t)role_groups * kRoleWordsPerGroup(NL) * sizeof(uint32_t) : 0;
+    int role_blocks_per_sm = 0;
+    if (role_warps) {
+        if (band == 32) { if ((rc = fast_smem_attr(e, k_populate_roles<32>, role_smem)) || (rc = blocks_per_sm_of(e, k_populate_roles<32>, kFastWarpsPerBlock * 32, role_smem, &role_blocks_per_sm))) return rc; }
+        else            { if ((rc = fast_smem_attr(e, k_populate_roles<64>, role_smem)) || (rc = blocks_per_sm_of(e, k_populate_roles<64>, kFastWarpsPerBlock * 32, role_smem, &role_blocks_per_sm))) return rc; }
+        if (role_blocks_per_sm < 1) role_warps = false;
+    }
     // wide kernel: chunk / lanes by band
     const size_t wsmem = (size_t)std::max(1, wide_warps) * wide_row_stride * sizeof(RowEntry);
     int wide_blocks_per_sm = 1;
@@ -1121,15 +1137,18 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 LAUNCHED();
             }
             lap(" classify queued");
-            const int tasks_per_round = (32 / groups) / NL;
+            const int tasks_per_round = role_warps ? 32 : (32 / groups) / NL;
             p.units_per_pair = std::max(1, (p.fcap + tasks_per_round * kRoundsPerUnit - 1) / (tasks_per_round * kRoundsPerUnit));
-            const int want_blocks = (int)std::min<long long>(1LL << 30, ((long long)(np / groups) * p.units_per_pair + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock);
-            const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * blocks_per_sm));
+            const int claimers_per_block = role_warps ? role_groups : kFastWarpsPerBlock;      // groups of warps / warps that claim work units
+            const int want_blocks = (int)std::min<long long>(1LL << 30, ((long long)(np / groups) * p.units_per_pair + claimers_per_block - 1) / claimers_per_block);
+            const unsigned grid = (unsigned)std::max(1, std::min(want_blocks, e->sm_count * (role_warps ? role_blocks_per_sm : blocks_per_sm)));
             while (e->tile_events.size() < 2 * (n_timed + 1)) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->tile_events.push_back(ev); }
             CU(chunk_order.wait_for_previous());
             CU(cudaEventRecord(e->tile_events[2 * n_timed], e->stream));
 #define PHMM_FAST_LAUNCH(B, GG) k_populate_fast<B, GG><<<grid, kFastWarpsPerBlock * 32, smem, e->stream>>>(p);
-            PHMM_FAST_DISPATCH(PHMM_FAST_LAUNCH)
+            if (role_warps && band == 32) k_populate_roles<32><<<grid, kFastWarpsPerBlock * 32, role_smem, e->stream>>>(p);
+            else if (role_warps) k_populate_roles<64><<<grid, kFastWarpsPerBlock * 32, role_smem, e->stream>>>(p);
+            else { PHMM_FAST_DISPATCH(PHMM_FAST_LAUNCH) }
             LAUNCHED();
             CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             ++n_timed; timed = true;

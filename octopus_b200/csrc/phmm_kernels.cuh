@@ -725,6 +725,72 @@ k_populate_fast(const PopParams p)
     }
 }
 
+// The packed DP of bands 32 and 64 with one WARP per chunk of 32 diagonals (dp_band_roles): a group of NL = B / 16 warps owns a read
+// pair; lane l of every warp of the group works on the group's task l of the round (32 + 32 tasks per round), warp j on chunk j.
+// Same work list, task words and result stores as k_populate_fast<B, 1>; used when a read has enough tasks to fill 32 lanes (H >= 17).
+__host__ __device__ constexpr int kRoleWordsPerGroup(const int nl) { return 3 * nl * 32 + 32; }
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
+k_populate_roles(const PopParams p)
+{
+    extern __shared__ RowEntry smem_rows[];
+    constexpr int NL = lanes_per_alignment(BAND);
+    static_assert(NL == 2 || NL == 4, "role warps: bands 32 and 64");
+    constexpr int NG = kFastWarpsPerBlock / NL;         // groups per block
+    constexpr int GT = NL * 32;                         // threads per group
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp / NL, role = warp % NL, gt = role * 32 + lane;
+    if (on_reserved_sm(p)) return;
+    RowEntry* rows = smem_rows + grp * p.row_stride;
+    uint32_t* xchg = reinterpret_cast<uint32_t*>(smem_rows + NG * p.row_stride) + grp * kRoleWordsPerGroup(NL);
+    volatile int* claim = reinterpret_cast<volatile int*>(xchg + 3 * NL * 32);
+    const int bar = 1 + grp;
+    const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
+    const int n_pairs = tile_pairs(p);
+    const bool oge = open_ge_extend(p.flags);
+    for (;;) {
+        if (gt == 0) *claim = atomicAdd(p.pair_cursor, 1);
+        group_barrier(bar, GT);
+        const int u = *claim;
+        const int j = u / p.units_per_pair, part = u % p.units_per_pair;
+        if (j >= n_pairs) break;
+        const int r0 = p.pair_reads[2 * j];
+        const int r1 = r0 >= 0 ? p.pair_reads[2 * j + 1] : -1;
+        const int n0 = r0 >= 0 ? p.fcnt[2 * j] : 0, n1 = r1 >= 0 ? p.fcnt[2 * j + 1] : 0;
+        const int nmax = max(n0, n1), L = r0 >= 0 ? p.rd.info[r0].x : 0;
+        const int c_begin = part * kRoundsPerUnit * 32, c_end = min(nmax, c_begin + kRoundsPerUnit * 32);
+        if (c_begin < nmax) {
+            const uint16_t* h0 = p.rd.rowhalf + p.rd.off[r0];
+            const uint16_t* h1 = r1 >= 0 ? p.rd.rowhalf + p.rd.off[r1] : nullptr;
+            for (int y = gt; y < L; y += GT) rows[y] = make_row_entry(h0[y], h1 ? (uint32_t)h1[y] : 0u);
+            if (gt == 0) rows[L] = pad_row_entry();
+            group_barrier(bar, GT);
+            const int rb = r1 >= 0 ? r1 : r0;
+            const ColEntry* tab0 = p.rd.reverse[r0] ? p.hp.tab_r : p.hp.tab_f;
+            const ColEntry* tab1 = p.rd.reverse[rb] ? p.hp.tab_r : p.hp.tab_f;
+            const uint32_t* q0 = p.ftasks + (size_t)(2 * (size_t)j) * p.fcap;
+            const uint32_t* q1 = q0 + p.fcap;
+            for (int c = c_begin; c < c_end; c += 32) {
+                const bool v0 = c + lane < n0, v1 = c + lane < n1;
+                // idle half-lanes replay a valid task (result discarded); nmax > c_begin, so at least one of the lists is not empty
+                const uint32_t t0 = n0 > 0 ? q0[v0 ? c + lane : 0] : q1[0];
+                const uint32_t t1 = n1 > 0 ? q1[v1 ? c + lane : 0] : t0;
+                const ColEntry* b0 = n0 > 0 ? tab0 : tab1;
+                const ColEntry* b1 = n1 > 0 ? tab1 : b0;
+                const int h0i = (int)(t0 & 0xFFFFu), a0 = (int)(t0 >> 16), h1i = (int)(t1 & 0xFFFFu), a1 = (int)(t1 >> 16);
+                const Lanes16::Tab tab {b0 + p.hp.off[h0i] + a0, b1 + p.hp.off[h1i] + a1};
+                const uint32_t res = oge ? dp_band_roles<Lanes16, 32, NL, true>(rows, L, tab, nucp, role, lane, (uint32_t)p.one, xchg, bar)
+                                         : dp_band_roles<Lanes16, 32, NL, false>(rows, L, tab, nucp, role, lane, (uint32_t)p.one, xchg, bar);
+                if (role == 0) {
+                    if (v0) { int* dst = p.best + pair_slot(p.rd, h0i, r0); const int v = (int)(res & 0xFFFFu); if (p.single_candidate) *dst = v; else atomicMin(dst, v); }
+                    if (v1) { int* dst = p.best + pair_slot(p.rd, h1i, r1); const int v = (int)(res >> 16); if (p.single_candidate) *dst = v; else atomicMin(dst, v); }
+                }
+            }
+        }
+        group_barrier(bar, GT);        // the rows and the claim word are free again
+    }
+}
+
 // Near-flank candidates of fast-path reads: the payload-carrying 32-bit DP (dp_flank32), one alignment per lane, one READ
 // per warp (row entries broadcast from shared memory), persistent warps over the tile's work list.
 template <int BAND>

@@ -265,6 +265,23 @@ def test_reserved_sms_leave_results_unchanged(coracle):
     eng.close()
 
 
+def test_two_engines_share_the_kernels_shared_memory_limit(engine):
+    """The dynamic shared-memory limit of a kernel is per process: a second engine that needs LESS than the first must not lower it
+    (the first engine's next launch would fail with 'invalid argument'). Regression test of the engine's high-water bookkeeping."""
+    from octopus_b200 import HaplotypeLikelihoodModel, PairHMMEngine
+    rng = np.random.default_rng(131)
+    other = PairHMMEngine(0)
+    for band in (16, 32):
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band, disable_naive_shortcut=True, map_positions=False)
+        long_h, long_r = random_region(rng, band, n_haps=24, n_reads=400, hap_len=2 * band + 420, read_len_choices=[250], read_n_rate=0.0)
+        short_h, short_r = random_region(rng, band, n_haps=24, n_reads=400, hap_len=2 * band + 120, read_len_choices=[40], read_n_rate=0.0)
+        first = engine.populate(cfg, long_h, long_r)
+        other.populate(cfg, short_h, short_r)
+        assert np.array_equal(engine.populate(cfg, long_h, long_r), first), band
+        assert np.array_equal(other.populate(cfg, long_h, long_r), first), band
+    other.close()
+
+
 def test_populate_regions_equals_one_call_per_region(engine, coracle):
     """phmm_populate_regions: many small regions (ragged haplotype and read counts, own flank states) in one kernel chain give, region
     by region, what phmm_populate gives for the region alone — and the oracle's values."""
