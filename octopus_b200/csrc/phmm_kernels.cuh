@@ -651,8 +651,21 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, c
 // dp_pair over the pairs' task lists (32/G + 32/G tasks per group and round, two alignments per lane), folding the
 // scores into best[] with atomicMin. Nothing but the DP lives in this kernel: the register-resident band gets the whole
 // register budget. The host pads the pair list so that the G pairs of a warp share one read length ((-1,-1) = idle group).
+// Resident blocks per SM the register allocation is held to. Band 16 fits its steady-state loop in 96 registers (5 blocks, the handful
+// of spills are in the per-task set-up), band 8 in 80 (6 blocks); 80 registers for band 16 spill 22 local accesses per column.
+#ifndef PHMM_FAST_MIN_BLOCKS_16
+#define PHMM_FAST_MIN_BLOCKS_16 5
+#endif
+#ifndef PHMM_FAST_MIN_BLOCKS_8
+#define PHMM_FAST_MIN_BLOCKS_8 6
+#endif
+#ifndef PHMM_FAST_MIN_BLOCKS_32
+#define PHMM_FAST_MIN_BLOCKS_32 4
+#endif
+__host__ __device__ constexpr int fast_min_blocks(const int band) { return band <= 8 ? PHMM_FAST_MIN_BLOCKS_8 : band == 16 ? PHMM_FAST_MIN_BLOCKS_16 : PHMM_FAST_MIN_BLOCKS_32; }
+
 template <int BAND, int G>
-__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, fast_min_blocks(BAND))
 k_populate_fast(const PopParams p)
 {
     extern __shared__ RowEntry smem_rows[];
@@ -730,7 +743,7 @@ k_populate_fast(const PopParams p)
 // Same work list, task words and result stores as k_populate_fast<B, 1>; used when a read has enough tasks to fill 32 lanes (H >= 17).
 __host__ __device__ constexpr int kRoleWordsPerGroup(const int nl) { return 3 * nl * 32 + 32; }
 template <int BAND>
-__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, PHMM_FAST_MIN_BLOCKS_32)
 k_populate_roles(const PopParams p)
 {
     extern __shared__ RowEntry smem_rows[];
