@@ -357,10 +357,23 @@ def main():
     n_buf = 3 if world > 1 else 1
     peer_ring = None
     max_region_bytes = max(h.n * r.n for h, r in regions) * 8
+    gather_note = None
     if world > 1 and args.gather == "peer":
         from octopus_b200.peer import PeerRing
         slot_bytes = H * R_total * 8 if strong else world * max_region_bytes
-        peer_ring = PeerRing(slot_bytes, local, rank, world, n_buf=n_buf)
+        try:
+            peer_ring = PeerRing(slot_bytes, local, rank, world, n_buf=n_buf)
+            ok = 1
+        except (RuntimeError, MemoryError) as exc:       # no peer access between these GPUs / IPC refused in this container
+            peer_ring, ok, gather_note = None, 0, str(exc)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
+        if int(flag.item()) == 0:
+            if peer_ring is not None:
+                peer_ring.close()
+                peer_ring = None
+            gather_note = "peer mapping unavailable on some rank (%s): NCCL gather instead" % (gather_note or "another rank")
+            sys.stderr.write(gather_note + "\n")
     gather_buffers = [dict() for _ in range(n_buf)]
     d_out = [torch.empty((H, R), dtype=torch.float64, device=dev) for _ in range(n_buf)] if peer_ring is None else None
     gather_done = [None] * n_buf
@@ -539,7 +552,7 @@ def main():
                        "l2": "inputs+outputs (%.0f MB) larger than the 126 MB L2" % ((h2d + d2h + 4 * H * R) / 1e6),
                        "parallelism": ("one batch, reads split over %d rank(s), [H, R_total] matrix assembled on rank 0 (%s)" % (world, how)) if strong else
                                       ("every rank its own region(s), haplotypes per region, the per-rank matrices collected on rank 0 (%d rank(s), %s)" % (world, how)),
-                       "gather": (args.gather if world > 1 else None),
+                       "gather": (None if world == 1 else ("peer" if peer_ring is not None else "nccl")), "gather_note": gather_note,
                        "reserved_sms": reserve,
                        "penalties": args.error_model or ("i.i.d. draws from the error-model tables' value range" +
                                                          (", gap_extend unconstrained (general deletion update)" if args.unordered_penalties else

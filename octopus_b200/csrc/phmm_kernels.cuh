@@ -651,13 +651,16 @@ __global__ void k_kmer_map(const int* __restrict__ list, const int n_list_max, c
 // dp_pair over the pairs' task lists (32/G + 32/G tasks per group and round, two alignments per lane), folding the
 // scores into best[] with atomicMin. Nothing but the DP lives in this kernel: the register-resident band gets the whole
 // register budget. The host pads the pair list so that the G pairs of a warp share one read length ((-1,-1) = idle group).
-// Resident blocks per SM the register allocation is held to. Band 16 fits its steady-state loop in 96 registers (5 blocks, the handful
-// of spills are in the per-task set-up), band 8 in 80 (6 blocks); 80 registers for band 16 spill 22 local accesses per column.
+// Resident blocks per SM the register allocation of the packed kernels is held to: 4 (128 registers). Measured alternatives
+// (profiles/r02m_*): band 16 at 5 blocks / 96 registers keeps its steady-state loop spill-free (310 instructions per column against 308)
+// and is still 9 % SLOWER on C3 (4 772 vs 5 244 GCUPS); 6 blocks / 80 registers spill 22 local accesses per column (-38 %); band 8 at
+// 6 blocks -14 %; bands >= 32 at 5 blocks spill heavily (-39 % on C4). More warps do not help an ALU-pipe-bound loop, and the tighter
+// allocation costs register-bank conflicts. The macros stay as a measurement hook (tools/gpu_r02_m.sh builds the variants).
 #ifndef PHMM_FAST_MIN_BLOCKS_16
-#define PHMM_FAST_MIN_BLOCKS_16 5
+#define PHMM_FAST_MIN_BLOCKS_16 4
 #endif
 #ifndef PHMM_FAST_MIN_BLOCKS_8
-#define PHMM_FAST_MIN_BLOCKS_8 6
+#define PHMM_FAST_MIN_BLOCKS_8 4
 #endif
 #ifndef PHMM_FAST_MIN_BLOCKS_32
 #define PHMM_FAST_MIN_BLOCKS_32 4

@@ -49,21 +49,26 @@ class PeerBuffer:
         self._lib = _lib.load()
         self.nbytes, self.device, self.rank, self.world, self.owner = int(nbytes), int(device), int(rank), int(world), int(owner)
         self.ptr, self._mapped = 0, False
-        handle = None
+        handle, err = None, None
         if rank == owner:
             p = C.c_void_p()
             rc = self._lib.phmm_device_alloc(self.device, self.nbytes, C.byref(p))
             if rc != _lib.PHMM_OK:
-                raise MemoryError("phmm_device_alloc(%d bytes) failed: %d" % (self.nbytes, rc))
-            self.ptr = int(p.value)
-            buf = C.create_string_buffer(64)
-            if self._lib.phmm_ipc_export(self.ptr, buf) != _lib.PHMM_OK:
-                raise RuntimeError("phmm_ipc_export failed")
-            handle = buf.raw
-        if world > 1:
-            box = [handle]
+                err = "phmm_device_alloc(%d bytes) failed: %d" % (self.nbytes, rc)
+            else:
+                self.ptr = int(p.value)
+                buf = C.create_string_buffer(64)
+                if self._lib.phmm_ipc_export(self.ptr, buf) != _lib.PHMM_OK:
+                    err = "phmm_ipc_export failed"
+                else:
+                    handle = buf.raw
+        if world > 1:                       # the owner's failure reaches every rank: nobody is left waiting in the broadcast
+            box = [handle, err]
             dist.broadcast_object_list(box, src=owner, group=group)
-            handle = box[0]
+            handle, err = box
+        if err is not None:
+            self.close()
+            raise RuntimeError(err)
         if rank != owner:
             p = C.c_void_p()
             rc = self._lib.phmm_ipc_open(self.device, handle, C.byref(p))
