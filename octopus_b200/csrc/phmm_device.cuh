@@ -793,6 +793,255 @@ PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Flank-aware path, packed: forward pass up to a flank boundary + backward pass down to it (dp_flank_fb)
+// ---------------------------------------------------------------------------------------------------------
+//
+// dp_flank32 / dp_flank_acc above reproduce the reference's traceback decisions with labelled 32-bit values — one alignment per
+// thread, ~14 instructions per cell, 0.36 of the score-only kernel. What hmm::evaluate needs from the traceback
+// (pair_hmm.hpp:743-764, replay simd_pair_hmm.hpp:352-430) is only WHERE the chosen path crosses the two flank boundaries: the path is
+// monotone in x, so its in-flank penalty is  V(first arrival at column xl) + total - V(first arrival at column xr)  and its
+// in-flank read bases are  y_l + L - y_r. The forward value F of a cell does not depend on the path chosen after it, and the
+// cost-to-go B of a cell (the same recurrence run from the end row backwards) does not depend on the path before it; every optimal
+// path crosses column xb at a cell where F + B equals the total score. So: the plain packed forward DP (dp_pair's cell, two
+// alignments per thread, no labels) over the columns BEFORE the boundary, a packed backward DP over the columns FROM the window end
+// down to the boundary, and the crossing cell is the argmin of F + B in that column — each column of the window is swept about
+// once, at the packed kernels' cost per cell.
+// The reference breaks score ties by state label (simd_pair_hmm.hpp:147-163); F + B cannot see which of several co-optimal paths its
+// traceback would follow. When the minimisers of a boundary column disagree on (arrival value, read row) — the only things the
+// discount depends on — the candidate is reported as `tie` and the kernel hands it to the exact labelled DP (dp_flank32) instead;
+// when they agree, every co-optimal path gives the same discount and so does the reference's (~1-2 % of random candidates tie).
+//
+// Backward recurrence (cost-to-go by arrival state; transitions as in the header comment of this file; go/ge = column x,
+// gop/gep = column x-1 plus nuc_prior):
+//   A     = sub(x, y) + Bm(x+1, y+1)
+//   Bd    = min(A, ge + Bd(x+1, y))                        a deletion can only be extended or left by a match
+//   t     = min(A, go + Bd(x+1, y))                        M and I may open a deletion (I -> D allowed)
+//   Bm    = min(t, gop + Bi(x, y+1))                       only M opens an insertion ...
+//   Bi    = min(t, gep + Bi(x, y+1))                       ... I extends it (no D -> I)
+//   B(x, L) = 0 in every state (free end);  start cell (x, 0): total = min(A, x odd ? gop + Bi(x, 1) : inf)  (the initialiser quirk)
+// Per cell pair: PRMT, VIMNMX (sub), 4 VIADDMNMX on the ALU pipe, one IMAD — the band sweeps columns downwards and diagonals
+// upwards, so that Bm stays in place, Bd moves one diagonal down and the insertion chain runs through one register.
+//
+// Boundaries: b[0], b[1] = xl, xr of the low half's alignment, b[2], b[3] of the high half's; a boundary is a window column in
+// [1, W-1], anything else (0, negative, >= W) means "no such flank". At each boundary column the forward arrivals (M, D) and the
+// backward values (Bm, Bd) of the whole band go to scratch (word ((slot * 4 + array) * 2B + k) * stride), and fb_decide reads them
+// back. Requires L >= 2B (the kernels route shorter reads to dp_flank32), ACGT reads, 16-bit-safe quality sums.
+#define PHMM_REP8A(F, b)  F(b + 0) F(b + 1) F(b + 2) F(b + 3) F(b + 4) F(b + 5) F(b + 6) F(b + 7)
+#define PHMM_REP64A(F)    PHMM_REP8A(F, 0) PHMM_REP8A(F, 8) PHMM_REP8A(F, 16) PHMM_REP8A(F, 24) PHMM_REP8A(F, 32) PHMM_REP8A(F, 40) PHMM_REP8A(F, 48) PHMM_REP8A(F, 56)
+
+constexpr int kFbSlots = 4, kFbArrays = 4;
+PHMM_HD size_t fb_scratch_words(const int band) { return (size_t)kFbSlots * kFbArrays * 2 * (size_t)band; }
+PHMM_HD bool fb_boundary_valid(const int b, const int W) { return b >= 1 && b <= W - 1; }
+
+struct FbResult { int score, flank, mask, tie; };
+
+// One boundary column of one half: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k),
+// the paths that ended before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or
+// beyond it (k >= xb: the backward pass left the start cell's total in Bm[k]).
+PHMM_HD void fb_decide(const uint32_t* __restrict__ scr, const size_t stride, const int K, const int slot, const int half,
+                       const int xb, const int L, int* total, int* v_out, int* y_out, int* tie)
+{
+    const uint32_t* fm = scr + (size_t)(slot * kFbArrays + 0) * K * stride;
+    const uint32_t* fd = scr + (size_t)(slot * kFbArrays + 1) * K * stride;
+    const uint32_t* bm = scr + (size_t)(slot * kFbArrays + 2) * K * stride;
+    const uint32_t* bd = scr + (size_t)(slot * kFbArrays + 3) * K * stride;
+    const int sh = half * 16;
+    int T = 0x7fffffff, v = 0, y = 0, t = 0;
+    for (int k = 0; k < K; ++k) {
+        const int FM = (int)((fm[(size_t)k * stride] >> sh) & 0xFFFFu), BM = (int)((bm[(size_t)k * stride] >> sh) & 0xFFFFu);
+        int tot, cv, cy;
+        if (k < xb - L) { tot = FM; cv = FM; cy = L; }
+        else if (k >= xb) { tot = BM; cv = 0; cy = 0; }
+        else {
+            const int FD = (int)((fd[(size_t)k * stride] >> sh) & 0xFFFFu), BD = (int)((bd[(size_t)k * stride] >> sh) & 0xFFFFu);
+            cy = xb - k;
+            tot = FD + BD; cv = FD;
+            if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
+            else if (tot == T && (cv != v || cy != y)) t = 1;
+            tot = FM + BM; cv = FM;
+        }
+        if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
+        else if (tot == T && (cv != v || cy != y)) t = 1;
+    }
+    *total = T; *v_out = v; *y_out = y; *tie = t;
+}
+
+template <int BAND, bool OGE>
+PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+                         const uint32_t nucp, const int b0, const int b1, const int b2, const int b3,
+                         uint32_t* __restrict__ scr, const size_t stride, FbResult* res0, FbResult* res1, const uint32_t one = 1u)
+{
+    constexpr int K = 2 * BAND;
+    static_assert(K <= 64, "register band limited to 64 diagonals");
+    const int W = L + K - 1;
+    const int c0 = fb_boundary_valid(b0, W) ? b0 : -1, c1 = fb_boundary_valid(b1, W) ? b1 : -1;
+    const int c2 = fb_boundary_valid(b2, W) ? b2 : -1, c3 = fb_boundary_valid(b3, W) ? b3 : -1;
+    int fe = c0 > c1 ? c0 : c1; { const int m2 = c2 > c3 ? c2 : c3; if (m2 > fe) fe = m2; }        // the forward pass covers columns [0, fe)
+    const int kBig = 0x7fffffff;
+    int be = kBig;                                                                                   // the backward pass covers columns [be, W]
+    if (c0 > 0 && c0 < be) be = c0;
+    if (c1 > 0 && c1 < be) be = c1;
+    if (c2 > 0 && c2 < be) be = c2;
+    if (c3 > 0 && c3 < be) be = c3;
+    const RowEntry w0 = rows[0];
+#define PHMM_FB_NEXT_ABOVE(v) { int n_ = kBig; if (c0 > (v) && c0 < n_) n_ = c0; if (c1 > (v) && c1 < n_) n_ = c1; if (c2 > (v) && c2 < n_) n_ = c2; if (c3 > (v) && c3 < n_) n_ = c3; next = n_; }
+#define PHMM_FB_NEXT_BELOW(v) { int n_ = -1; if (c0 < (v) && c0 > n_) n_ = c0; if (c1 < (v) && c1 > n_) n_ = c1; if (c2 < (v) && c2 > n_) n_ = c2; if (c3 < (v) && c3 > n_) n_ = c3; next = n_; }
+#define PHMM_FB_STORE(slot, arr0, A0, A1)                                                              \
+    {                                                                                                   \
+        uint32_t* dst_ = scr + (size_t)((slot) * kFbArrays + (arr0)) * K * stride;                      \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) { dst_[(size_t)k * stride] = A0[k]; dst_[(size_t)(K + k) * stride] = A1[k]; } \
+    }
+
+    // ---- forward: dp_pair's column sweep over [0, fe) ----
+    if (fe > 0) {
+        uint32_t M[K], D[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kInf16x2; }
+        ColEntry e0 = ldg(t0), e1 = ldg(t1);
+        uint32_t go_prev = 0u, ge_prev = 0u;
+        int next;
+        PHMM_FB_NEXT_ABOVE(0)
+#define PHMM_CELL(k)                                                                        \
+    {                                                                                       \
+        const RowEntry w   = rp[-(k)];                                                      \
+        const uint32_t sub = vmin2(w.y, prmt(caps0, caps1, w.x));                           \
+        const uint32_t m = M[(k) < K ? (k) : 0], d = D[(k) < K ? (k) : 0];                  \
+        const uint32_t s = vmin3(m, i_run, d);                                              \
+        M[(k) < K ? (k) : 0] = fma_add(s, sub, one);                                        \
+        if ((k) + 1 < K) D[((k) + 1) < K ? (k) + 1 : 0] = vaddmin(d, ge, fma_add(OGE ? s : vmin2(m, i_run), go, one)); \
+        i_run = vaddmin(i_run, gep, fma_add(m, gop, one));                                  \
+    }
+#define PHMM_CASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_CELL(k)
+#define PHMM_CASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
+        for (int x = 0; x < fe; ++x) {
+            const int xn = (x + 1 < W) ? x + 1 : W - 1;
+            const ColEntry n0 = ldg(t0 + xn), n1 = ldg(t1 + xn);
+            const uint32_t caps0 = e0.x, caps1 = e1.x;
+            const uint32_t go = prmt(e0.y, e1.y, 0x3430u), ge = prmt(e0.y, e1.y, 0x3531u);
+            const uint32_t gop = go_prev + nucp, gep = ge_prev + nucp;
+            const RowEntry* rp = rows + x;
+            uint32_t i_run = kInf16x2;
+            if (x >= K) {
+                if (x <= L) {
+#pragma unroll
+                    for (int k = K - 1; k >= 0; --k) PHMM_CELL(k)
+                } else {
+                    const int klo = x - L;
+#pragma unroll
+                    for (int k = K - 1; k >= 0; --k) {
+                        PHMM_CELL(k)
+                        if (k == klo) break;
+                    }
+                }
+            } else {
+                const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));
+                i_run = (x & 1) ? gop : kInf16x2;
+                switch (x) { PHMM_REP64(PHMM_CASE_PROLOGUE) default: break; }
+                switch (x) { PHMM_REP64(PHMM_CASE_ROW0) default: break; }
+            }
+            go_prev = go; ge_prev = ge;
+            if (x + 1 == next) {                 // M / D now hold the arrivals of column x + 1: a flank boundary of one of the halves
+                if (c0 == next) PHMM_FB_STORE(0, 0, M, D)
+                if (c1 == next) PHMM_FB_STORE(1, 0, M, D)
+                if (c2 == next) PHMM_FB_STORE(2, 0, M, D)
+                if (c3 == next) PHMM_FB_STORE(3, 0, M, D)
+                PHMM_FB_NEXT_ABOVE(x + 1)
+            }
+            const uint32_t z = i_run & 0x80008000u;          // see dp_pair: keeps the prefetch out of e0 / e1 until the column is done
+            e0.x = n0.x + z; e0.y = n0.y + z; e1.x = n1.x + z; e1.y = n1.y + z;
+        }
+#undef PHMM_CELL
+#undef PHMM_CASE_PROLOGUE
+#undef PHMM_CASE_ROW0
+    }
+
+    // ---- backward: cost-to-go over [be, W], columns downwards, diagonals upwards ----
+    if (be != kBig) {
+        uint32_t BM[K], BD[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { BM[k] = kInf16x2; BD[k] = kInf16x2; }
+        ColEntry p0 = ldg(t0 + (W - 1)), p1 = ldg(t1 + (W - 1));      // entries of column x - 1
+        uint32_t caps0 = 0u, caps1 = 0u, go = 0u, ge = 0u;             // column x (column W holds the end cell only)
+        int next;
+        PHMM_FB_NEXT_BELOW(W)
+#define PHMM_BKCELL(k)                                                                      \
+    {                                                                                       \
+        const RowEntry w   = rp[-(k)];                                                      \
+        const uint32_t sub = vmin2(w.y, prmt(caps0, caps1, w.x));                           \
+        const uint32_t a   = fma_add(BM[(k) < K ? (k) : 0], sub, one);                      \
+        const uint32_t dd  = ((k) + 1 < K) ? BD[((k) + 1) < K ? (k) + 1 : 0] : kInf16x2;    \
+        BD[(k) < K ? (k) : 0] = vaddmin(dd, ge, a);                                         \
+        const uint32_t t   = vaddmin(dd, go, a);                                            \
+        BM[(k) < K ? (k) : 0] = vaddmin(i_run, gop, t);                                     \
+        i_run = vaddmin(i_run, gep, t);                                                     \
+    }
+#define PHMM_BCASE_ROWL(k)  case (k): if ((k) < K) { BM[(k) < K ? (k) : 0] = 0u; BD[(k) < K ? (k) : 0] = 0u; } break;
+#define PHMM_BCASE_EPI(k)   case (k) - 1: if ((k) >= 1 && (k) < K) PHMM_BKCELL(k)
+#define PHMM_BCASE_START(k) case (k): if ((k) < K) { const uint32_t a = fma_add(BM[(k) < K ? (k) : 0], sub0, one); BM[(k) < K ? (k) : 0] = (x & 1) ? vaddmin(i_run, gop, a) : a; } break;
+        for (int x = W; x >= be; --x) {
+            const int xp = x >= 2 ? x - 2 : 0;
+            const ColEntry n0 = ldg(t0 + xp), n1 = ldg(t1 + xp);
+            const uint32_t go_p = prmt(p0.y, p1.y, 0x3430u), ge_p = prmt(p0.y, p1.y, 0x3531u);     // column x - 1
+            const uint32_t gop = go_p + nucp, gep = ge_p + nucp;
+            const RowEntry* rp = rows + x;
+            uint32_t i_run;
+            if (x >= L) {
+                const int klo = x - L;           // the end-row cell: cost-to-go 0 in every state
+                switch (klo) { PHMM_REP64A(PHMM_BCASE_ROWL) default: break; }
+                i_run = 0u;
+                switch (klo) { PHMM_REP64A(PHMM_BCASE_EPI) default: break; }
+            } else if (x >= K) {
+                i_run = kInf16x2;
+#pragma unroll
+                for (int k = 0; k < K; ++k) PHMM_BKCELL(k)
+            } else {
+                i_run = kInf16x2;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (k == x) break;
+                    PHMM_BKCELL(k)
+                }
+                const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));       // the start cell (x, 0): its total stays in BM[x]
+                switch (x) { PHMM_REP64A(PHMM_BCASE_START) default: break; }
+            }
+            if (x == next) {
+                if (c0 == next) PHMM_FB_STORE(0, 2, BM, BD)
+                if (c1 == next) PHMM_FB_STORE(1, 2, BM, BD)
+                if (c2 == next) PHMM_FB_STORE(2, 2, BM, BD)
+                if (c3 == next) PHMM_FB_STORE(3, 2, BM, BD)
+                PHMM_FB_NEXT_BELOW(x)
+            }
+            const uint32_t z = i_run & 0x80008000u;
+            caps0 = p0.x; caps1 = p1.x; go = go_p; ge = ge_p;
+            p0.x = n0.x + z; p0.y = n0.y + z; p1.x = n1.x + z; p1.y = n1.y + z;
+        }
+#undef PHMM_BKCELL
+#undef PHMM_BCASE_ROWL
+#undef PHMM_BCASE_EPI
+#undef PHMM_BCASE_START
+    }
+#undef PHMM_FB_NEXT_ABOVE
+#undef PHMM_FB_NEXT_BELOW
+#undef PHMM_FB_STORE
+
+    // ---- the crossing cells ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int xl = half ? c2 : c0, xr = half ? c3 : c1;
+        int T = 0, Tl = 0, Tr = 0, v_l = 0, y_l = 0, v_r = 0, y_r = L, tl = 0, tr = 0;
+        if (xl > 0) { fb_decide(scr, stride, K, 2 * half, half, xl, L, &Tl, &v_l, &y_l, &tl); T = Tl; }
+        if (xr > 0) { fb_decide(scr, stride, K, 2 * half + 1, half, xr, L, &Tr, &v_r, &y_r, &tr); T = Tr; }
+        else v_r = T;
+        FbResult r;
+        r.score = T;
+        r.flank = v_l + (T - v_r);
+        r.mask = y_l + (L - y_r);
+        r.tie = tl | tr | ((xl > 0 && xr > 0 && Tl != Tr) ? 1 : 0);
+        if (half) *res1 = r; else *res0 = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Traceback in registers: HaplotypeLikelihoodModel::align / hmm::align need the alignment itself (CIGAR, first_pos)
 // ---------------------------------------------------------------------------------------------------------
 //

@@ -297,3 +297,47 @@ extern "C" int emul_traceback(int band, int L, const char* read, const uint8_t* 
     }
     return 0;
 }
+
+// dp_flank_fb<band> on the CPU: two alignments of equal read length packed as the kernel packs them (forward pass to the flank
+// boundary, backward pass from the window end, crossing cells from F + B). Flanks per alignment in window coordinates.
+// out[a] = {score, flank, mask, tie}. Returns 0, 1 when the kernel would not route the pair here (L < 2*band, overlapping flanks,
+// no flank at all), -1 on a bad read base.
+extern "C" int emul_dp_flank_fb(int band, int L, const char* read0, const uint8_t* q0, const char* read1, const uint8_t* q1,
+                                const char* truth0, const char* mask0, const int8_t* prior0, const int8_t* go0, const int8_t* ge0,
+                                const char* truth1, const char* mask1, const int8_t* prior1, const int8_t* go1, const int8_t* ge1,
+                                int nuc_prior, int lhs0, int rhs0, int lhs1, int rhs1, int* out0, int* out1)
+{
+    const int W = L + 2 * band - 1;
+    if (L < 2 * band) return 1;
+    if (W - rhs0 <= lhs0 || W - rhs1 <= lhs1) return 1;
+    if ((lhs0 == 0 && rhs0 == 0) || (lhs1 == 0 && rhs1 == 0)) return 1;
+    std::vector<RowEntry> rows(L + 1);
+    for (int y = 0; y < L; ++y) {
+        const int c0 = base_code(read0[y]), c1 = base_code(read1[y]);
+        if (c0 < 0 || c1 < 0 || c0 > 3 || c1 > 3) return -1;
+        rows[y] = make_row_entry((uint32_t)c0 | ((uint32_t)q0[y] << 8), (uint32_t)c1 | ((uint32_t)q1[y] << 8));
+    }
+    rows[L] = pad_row_entry();
+    std::vector<ColEntry> t0(W), t1(W);
+    for (int x = 0; x < W; ++x) {
+        t0[x] = make_col_entry(truth0[x], mask0[x], prior0[x], go0[x], ge0[x]);
+        t1[x] = make_col_entry(truth1[x], mask1[x], prior1[x], go1[x], ge1[x]);
+    }
+    const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
+    const bool oge = use_oge(go0, ge0, go1, ge1, W);
+    std::vector<uint32_t> scr(fb_scratch_words(band), 0xDEADBEEFu);
+    FbResult r0, r1;
+    const int b0 = lhs0, b1 = W - rhs0, b2 = lhs1, b3 = W - rhs1;
+#define RUN_FB(B) { if (oge) dp_flank_fb<B, true>(rows.data(), L, t0.data(), t1.data(), nucp, b0, b1, b2, b3, scr.data(), 1, &r0, &r1); \
+                    else dp_flank_fb<B, false>(rows.data(), L, t0.data(), t1.data(), nucp, b0, b1, b2, b3, scr.data(), 1, &r0, &r1); }
+    switch (band) {
+        case 8:  RUN_FB(8) break;
+        case 16: RUN_FB(16) break;
+        case 32: RUN_FB(32) break;
+        default: return -1;
+    }
+#undef RUN_FB
+    out0[0] = r0.score; out0[1] = r0.flank; out0[2] = r0.mask; out0[3] = r0.tie;
+    out1[0] = r1.score; out1[1] = r1.flank; out1[2] = r1.mask; out1[3] = r1.tie;
+    return 0;
+}
