@@ -835,10 +835,17 @@ PHMM_HD bool fb_boundary_valid(const int b, const int W) { return b >= 1 && b <=
 
 struct FbResult { int score, flank, mask, tie; };
 
+template <int K>
+PHMM_HD void fb_store(uint32_t* __restrict__ dst, const size_t stride, const uint32_t (&a0)[K], const uint32_t (&a1)[K])
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) { dst[(size_t)k * stride] = a0[k]; dst[(size_t)(K + k) * stride] = a1[k]; }
+}
+
 // One boundary column of one half: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k),
 // the paths that ended before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or
 // beyond it (k >= xb: the backward pass left the start cell's total in Bm[k]).
-PHMM_HD void fb_decide(const uint32_t* __restrict__ scr, const size_t stride, const int K, const int slot, const int half,
+PHMM_HD void fb_decide(const uint32_t* scr /* written earlier by this very thread: no __restrict__, the loads must stay coherent */, const size_t stride, const int K, const int slot, const int half,
                        const int xb, const int L, int* total, int* v_out, int* y_out, int* tie)
 {
     const uint32_t* fm = scr + (size_t)(slot * kFbArrays + 0) * K * stride;
@@ -886,10 +893,13 @@ PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const C
     const RowEntry w0 = rows[0];
 #define PHMM_FB_NEXT_ABOVE(v) { int n_ = kBig; if (c0 > (v) && c0 < n_) n_ = c0; if (c1 > (v) && c1 < n_) n_ = c1; if (c2 > (v) && c2 < n_) n_ = c2; if (c3 > (v) && c3 < n_) n_ = c3; next = n_; }
 #define PHMM_FB_NEXT_BELOW(v) { int n_ = -1; if (c0 < (v) && c0 > n_) n_ = c0; if (c1 < (v) && c1 > n_) n_ = c1; if (c2 < (v) && c2 > n_) n_ = c2; if (c3 < (v) && c3 > n_) n_ = c3; next = n_; }
-#define PHMM_FB_STORE(slot, arr0, A0, A1)                                                              \
+// the band's two arrays of a boundary column → scratch, once per slot whose boundary this column is (rolled over the slots)
+#define PHMM_FB_STORE(arr0, A0, A1)                                                                     \
     {                                                                                                   \
-        uint32_t* dst_ = scr + (size_t)((slot) * kFbArrays + (arr0)) * K * stride;                      \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) { dst_[(size_t)k * stride] = A0[k]; dst_[(size_t)(K + k) * stride] = A1[k]; } \
+        _Pragma("unroll 1") for (int s_ = 0; s_ < kFbSlots; ++s_) {                                     \
+            const int cs_ = s_ == 0 ? c0 : s_ == 1 ? c1 : s_ == 2 ? c2 : c3;                            \
+            if (cs_ == next) fb_store<K>(scr + (size_t)(s_ * kFbArrays + (arr0)) * K * stride, stride, A0, A1); \
+        }                                                                                               \
     }
 
     // ---- forward: dp_pair's column sweep over [0, fe) ----
@@ -941,10 +951,7 @@ PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const C
             }
             go_prev = go; ge_prev = ge;
             if (x + 1 == next) {                 // M / D now hold the arrivals of column x + 1: a flank boundary of one of the halves
-                if (c0 == next) PHMM_FB_STORE(0, 0, M, D)
-                if (c1 == next) PHMM_FB_STORE(1, 0, M, D)
-                if (c2 == next) PHMM_FB_STORE(2, 0, M, D)
-                if (c3 == next) PHMM_FB_STORE(3, 0, M, D)
+                PHMM_FB_STORE(0, M, D)
                 PHMM_FB_NEXT_ABOVE(x + 1)
             }
             const uint32_t z = i_run & 0x80008000u;          // see dp_pair: keeps the prefetch out of e0 / e1 until the column is done
@@ -1005,10 +1012,7 @@ PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const C
                 switch (x) { PHMM_REP64A(PHMM_BCASE_START) default: break; }
             }
             if (x == next) {
-                if (c0 == next) PHMM_FB_STORE(0, 2, BM, BD)
-                if (c1 == next) PHMM_FB_STORE(1, 2, BM, BD)
-                if (c2 == next) PHMM_FB_STORE(2, 2, BM, BD)
-                if (c3 == next) PHMM_FB_STORE(3, 2, BM, BD)
+                PHMM_FB_STORE(2, BM, BD)
                 PHMM_FB_NEXT_BELOW(x)
             }
             const uint32_t z = i_run & 0x80008000u;

@@ -64,7 +64,7 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, wide_reads, bp, regs, rregion, rpbase, rpstride;
     DBuf tasks_lane, tasks_generic, works, scores;
-    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, atasks, gcnt, sched, sorted;
+    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, atasks, gcnt, sched, sorted, fb_scratch;
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
     // per-kernel launch configuration already applied / queried (the runtime calls are not free and need not be repeated)
@@ -342,7 +342,7 @@ void phmm_destroy(phmm_engine* e)
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
                    &e->counters, &e->pairs, &e->generic_reads, &e->wide_reads, &e->bp, &e->regs, &e->rregion, &e->rpbase, &e->rpstride, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
-                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->atasks, &e->gcnt, &e->sched, &e->sorted};
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->atasks, &e->gcnt, &e->sched, &e->sorted, &e->fb_scratch};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1083,8 +1083,25 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
 #undef PHMM_MAP_ARGS
     };
     // the 32-bit flank kernel over the current list (near-flank candidates, and every candidate of pair-list reads holding 'N')
+    static const bool no_flank_fb = std::getenv("PHMM_NO_FLANK_FB") != nullptr;           // measurement hook: the labelled one-alignment-per-thread flank kernels only
+    const bool flank_fb_ok = !no_flank_fb && band <= kFlankFbMaxBand;
     auto launch_flank = [&](int n_entries, int row_stride) -> int {
         if (band > 32) return PHMM_OK;              // wide bands: near-flank candidates take the traceback queue
+        if (p.atasks && p.fb_route) {
+            // the packed forward / backward flank kernel over the atasks lists; it runs BEFORE k_populate_flank, which also resolves
+            // the candidates this kernel reports as tied (appended to the gtasks lists)
+            const size_t fbsmem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
+            int fb_blocks = 1, frc2;
+#define PHMM_FB_LAUNCH(B) \
+            { if ((frc2 = fast_smem_attr(e, k_populate_flank_fb<B>, fbsmem)) || (frc2 = blocks_per_sm_of(e, k_populate_flank_fb<B>, kFastWarpsPerBlock * 32, fbsmem, &fb_blocks))) return frc2; \
+              if (fb_blocks < 1) { e->err = "flank kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; } \
+              const unsigned bgrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * fb_blocks)); \
+              if (cudaError_t ce = e->fb_scratch.ensure((size_t)bgrid * kFastWarpsPerBlock * 32 * fb_scratch_words(B) * sizeof(uint32_t))) { e->err = cudaGetErrorString(ce); return PHMM_ERR_NOMEM; } \
+              k_populate_flank_fb<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_scratch.as<uint32_t>()); }
+            if (band == 8) PHMM_FB_LAUNCH(8) else PHMM_FB_LAUNCH(16)
+#undef PHMM_FB_LAUNCH
+            LAUNCHED();
+        }
         const unsigned fgrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
         const size_t fsmem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
         int frc;
@@ -1097,7 +1114,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                      k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
         }
         LAUNCHED();
-        if (p.atasks) {
+        if (p.atasks && !p.fb_route) {
             const unsigned agrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 4));
             switch (band) {
                 case 8:  if ((frc = fast_smem_attr(e, k_populate_flank_acc<8>, fsmem))) return frc;
@@ -1122,6 +1139,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             p.pair_base = (int)p0;
             p.list = p.pair_reads; p.list_kind = 0; p.n_list = 2 * np; p.list_base = (int)(2 * p0);
             p.row_stride = fast_row_stride;
+            p.fb_route = (p.atasks && flank_fb_ok) ? 1 : 0;
             if (use_mapper) {
                 launch_mapper(p.list, p.n_list, p.list_base, 0);
                 LAUNCHED();
@@ -1150,15 +1168,18 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
             else if (role_warps) k_populate_roles<64><<<grid, kFastWarpsPerBlock * 32, role_smem, e->stream>>>(p);
             else { PHMM_FAST_DISPATCH(PHMM_FAST_LAUNCH) }
             LAUNCHED();
-            CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
-            ++n_timed; timed = true;
+            // with a flank state the tile's DP work is split between the score-only kernel and the flank-aware kernels: time them together
+            if (!p.use_flanks) CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
             lap(" dp queued");
             if ((rc = launch_flank(2 * np, fast_row_stride))) return rc;
+            if (p.use_flanks) CU(cudaEventRecord(e->tile_events[2 * n_timed + 1], e->stream));
+            ++n_timed; timed = true;
             p0 += np;
         } else if (w0 < n_wide) {
             const int nw = (int)std::min<long long>(reads_per_tile, n_wide - w0);
             p.list = e->wide_reads.as<int>() + w0; p.list_kind = 1; p.n_list = nw; p.list_base = (int)w0;
             p.row_stride = wide_row_stride;
+            p.fb_route = 0;
             const long long threads = (long long)nw * H;
             const unsigned cgrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 127) / 128, (long long)e->sm_count * 64));
             if (use_mapper) {
@@ -1188,6 +1209,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         } else {
             const int ng = (int)std::min<long long>(reads_per_tile, n_generic - g0);
             p.list = e->generic_reads.as<int>() + g0; p.list_kind = 2; p.n_list = ng; p.list_base = (int)g0;
+            p.fb_route = 0;
             // ng is an upper bound (normally there are no generic reads at all): grid-stride kernels on a bounded grid
             const long long threads = (long long)ng * H;
             const unsigned ggrid = (unsigned)std::max<long long>(1, std::min<long long>((threads + 63) / 64, (long long)e->sm_count * 32));

@@ -389,6 +389,7 @@ struct PopParams {
     int* acnt;
     int* acc_cursor;
     int* any_acc_tasks;
+    int fb_route;               // the atasks lists of this tile go to k_populate_flank_fb (pair list, bands <= 16): any flank geometry, reads of >= 2*band bases
     int units_per_pair;         // fast kernel: a read pair's task lists are cut into this many work units of kRoundsPerUnit rounds
     const RegionInfo* regs;     // regions of the call (one for phmm_populate); the flank state is per region
     int Hmax;                   // most haplotypes any region has: per-read loops run over Hmax slots and skip the ones beyond the region
@@ -923,6 +924,80 @@ k_populate_flank_acc(const PopParams p)
     }
 }
 
+constexpr int kFlankFbMaxBand = 16;     // widest band served by k_populate_flank_fb: its register band holds 2 * band diagonals (band 32 spills: it keeps the lean labelled kernel)
+// The packed forward / backward flank kernel (dp_flank_fb): one READ per warp — both packed halves carry the same read, so a lane
+// works on TWO of the read's near-flank candidates (two haplotype windows) at once, 64 per round. Boundary columns of the two
+// windows go through `scratch` (fb_scratch_words(BAND) words per thread, thread-interleaved). A candidate whose co-optimal paths
+// cross a flank boundary at different cells (FbResult::tie, ~1 %) is appended to the read's gtasks list: k_populate_flank, launched
+// after this kernel, resolves it with the labelled DP.
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
+k_populate_flank_fb(const PopParams p, uint32_t* __restrict__ scratch)
+{
+    extern __shared__ RowEntry smem_rows[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RowEntry* rows = smem_rows + warp * p.row_stride;
+    constexpr int K = 2 * BAND;
+    if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
+    const int n_list = tile_list(p);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint32_t* scr = scratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
+    const bool oge = open_ge_extend(p.flags);
+    for (;;) {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(p.acc_cursor, 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li >= n_list) break;
+        const int r = p.list[li];
+        const int n = r >= 0 ? p.acnt[li] : 0;
+        if (n == 0) continue;
+        const int L = p.rd.info[r].x;
+        const RegionInfo reg = p.regs[p.rd.region[r]];
+        __syncwarp();
+        unsigned qmin = 255u;
+        {
+            const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
+            for (int y = lane; y < L; y += 32) { const uint32_t half = hr[y]; rows[y] = make_row_entry(half, half); qmin = min(qmin, half >> 8); }
+            if (lane == 0) rows[L] = pad_row_entry();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
+        const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
+        const int W = L + K - 1;
+        for (int c = 0; c < n; c += 64) {
+            const int i0 = c + 2 * lane, i1 = i0 + 1;
+            const bool v0 = i0 < n, v1 = i1 < n;
+            const uint32_t w0 = q[v0 ? i0 : 0], w1 = v1 ? q[i1] : w0;        // idle halves replay a valid task (result discarded)
+            const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
+            int lhs0, rhs0, lhs1, rhs1;
+            window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
+            window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
+            const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
+            FbResult f0, f1;
+            if (oge) dp_flank_fb<BAND, true>(rows, L, c0, c1, nucp, lhs0, W - rhs0, lhs1, W - rhs1, scr, stride, &f0, &f1, (uint32_t)p.one);
+            else dp_flank_fb<BAND, false>(rows, L, c0, c1, nucp, lhs0, W - rhs0, lhs1, W - rhs1, scr, stride, &f0, &f1, (uint32_t)p.one);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (!(half ? v1 : v0)) continue;
+                const FbResult f = half ? f1 : f0;
+                const int h = half ? h1 : h0, a = half ? a1 : a0;
+                // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
+                if (flank_replay_may_differ(half ? c1 : c0, W, half ? lhs1 : lhs0, half ? rhs1 : rhs0, low_quality)) push_slow(p, r, h, a);
+                else if (f.tie) {
+                    const int slot = atomicAdd(p.gcnt + li, 1);
+                    if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = half ? w1 : w0;
+                    else atomicOr(p.flags, 8);
+                    *p.any_flank_tasks = 1;
+                } else atomicMin(p.best + pair_slot(p.rd, h, r), discount_flank(f.score, f.flank, L, f.mask, 0));
+            }
+        }
+    }
+}
+
 // Generic path of populate: reads the fast path cannot take (non-ACGT bases, 16-bit-unsafe qualities, very long reads)
 // or every read when the band is > 32 / int32 scores were requested. One thread per (haplotype, read) pair.
 // With FASTQ it is the classify pass of the fast path instead: the same candidate walk over the fast work list (the pair
@@ -978,7 +1053,9 @@ __device__ __forceinline__ void populate_one_pair(const PopParams& p, const int 
                         window_flanks(v, W, hv.len, reg.lhs, reg.rhs, &lhs, &rhs);
                         const int xl = lhs, xr = W - rhs;
                         if (xr <= xl) route = to_32bit ? 0 : 2;      // the flanks cover the whole window: the result is the plain score (:757-759)
-                        else if (!(p.rd.info[r].y & kReadHasN) && p.atasks && flank_mask_cannot_zero(rv.len, p.band, xl, xr >= W ? W + 1 : xr)) route = 1;
+                        else if (lhs == 0 && rhs == 0 && !to_32bit) route = 2;   // no flank column inside the window: nothing to discount
+                        else if (!(p.rd.info[r].y & kReadHasN) && p.atasks &&
+                                 (p.fb_route ? rv.len >= 2 * p.band : flank_mask_cannot_zero(rv.len, p.band, xl, xr >= W ? W + 1 : xr))) route = 1;
                     }
                     uint32_t* tasks = route == 0 ? p.gtasks : route == 1 ? p.atasks : p.ftasks;
                     int* counts = route == 0 ? p.gcnt : route == 1 ? p.acnt : p.fcnt;

@@ -1,0 +1,28 @@
+#!/bin/bash
+# round 2, GPU call N: the packed forward / backward flank kernel (k_populate_flank_fb): parity tests, flank / production-mode
+# bench lines with and without it (PHMM_NO_FLANK_FB=1 = the labelled kernels of call L), launch list, one ncu capture
+set -x
+O=gpurun_out/r02n
+mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_flank_fb.py tests/test_gpu_parity.py tests/test_gpu_wide.py -m gpu -x -q > $O/pytest_gpu_flank.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu_flank.log
+tail -6 $O/pytest_gpu_flank.log | cut -c1-400
+B="python bench.py --no-cpu-baseline --steps 3 --warmup 3"
+timeout 200 $B --config C2 --flank 60,60 > $O/bench_c2_flank.json 2> $O/bench_c2_flank.err
+PHMM_NO_FLANK_FB=1 timeout 200 $B --config C2 --flank 60,60 > $O/bench_c2_flank_nofb.json 2> $O/bench_c2_flank_nofb.err
+timeout 200 $B --config C2 --shortcut --map --flank 60,60 > $O/bench_c2_prod.json 2> $O/bench_c2_prod.err
+PHMM_NO_FLANK_FB=1 timeout 200 $B --config C2 --shortcut --map --flank 60,60 > $O/bench_c2_prod_nofb.json 2> $O/bench_c2_prod_nofb.err
+timeout 200 $B --config C2 --shortcut --map --flank 60,60 --error-model PCR-free.HiSeq-2500 > $O/bench_c2_prod_errmodel.json 2> $O/bench_c2_prod_errmodel.err
+timeout 200 $B --config C3 --flank 60,60 > $O/bench_c3_flank.json 2> $O/bench_c3_flank.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_c2_prod.csv $B --config C2 --shortcut --map --flank 60,60 --steps 1 --warmup 1 > $O/launches_prod.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_populate_flank_fb -s 1 -c 1 -o $O/flankfb16 $B --config C2 --flank 60,60 --steps 1 --warmup 1 > $O/ncu_flankfb.log 2>&1
+for f in $O/bench_*.json; do python - "$f" <<'PY'
+import sys, json
+f=sys.argv[1]
+try:
+    d=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, 'value %.0f e2e %.0f ms/step %.2f kernel %.2f parity %s' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['parity']))
+except Exception as e:
+    print(f, 'ERR', e)
+PY
+done
+ls -la $O
