@@ -824,16 +824,47 @@ PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const 
 //
 // Boundaries: b[0], b[1] = xl, xr of the low half's alignment, b[2], b[3] of the high half's; a boundary is a window column in
 // [1, W-1], anything else (0, negative, >= W) means "no such flank". At each boundary column the forward arrivals (M, D) and the
-// backward values (Bm, Bd) of the whole band go to scratch (word ((slot * 4 + array) * 2B + k) * stride), and fb_decide reads them
-// back. Requires L >= 2B (the kernels route shorter reads to dp_flank32), ACGT reads, 16-bit-safe quality sums.
+// backward values (Bm, Bd) of the whole band go to scratch (word ((slot * 2 + array) * 2B + k) * stride of the pass's own
+// scratch), and fb_decide reads them back. Requires L >= 2B (the kernels route shorter reads to dp_flank32), ACGT reads,
+// 16-bit-safe quality sums. The two passes are separate functions — and separate kernels (k_flank_fwd, k_flank_bwd): fused
+// into one kernel their unrolled column bodies (6 x ~5 KB of code + jump tables, ~80 KB) overflow the SM's 32 KB instruction
+// cache as soon as the resident warps are in different phases, and the kernel spends 11 stall cycles per issued instruction
+// waiting for instructions (profiles/r02n_flankfb16_fused_ncu_raw.csv: issue slots 26 % used).
 #define PHMM_REP8A(F, b)  F(b + 0) F(b + 1) F(b + 2) F(b + 3) F(b + 4) F(b + 5) F(b + 6) F(b + 7)
 #define PHMM_REP64A(F)    PHMM_REP8A(F, 0) PHMM_REP8A(F, 8) PHMM_REP8A(F, 16) PHMM_REP8A(F, 24) PHMM_REP8A(F, 32) PHMM_REP8A(F, 40) PHMM_REP8A(F, 48) PHMM_REP8A(F, 56)
 
-constexpr int kFbSlots = 4, kFbArrays = 4;
-PHMM_HD size_t fb_scratch_words(const int band) { return (size_t)kFbSlots * kFbArrays * 2 * (size_t)band; }
+constexpr int kFbSlots = 4;            // boundary slots of a lane's two alignments: xl / xr of the low half, xl / xr of the high half
+PHMM_HD size_t fb_scratch_words(const int band) { return (size_t)kFbSlots * 2 * 2 * (size_t)band; }     // per pass: slots x {M, D} x 2B diagonals
 PHMM_HD bool fb_boundary_valid(const int b, const int W) { return b >= 1 && b <= W - 1; }
 
 struct FbResult { int score, flank, mask, tie; };
+// c[s]: boundary column of slot s, or -1; the forward pass covers the columns [0, fe), the backward pass [be, W]
+struct FbBounds { int c0, c1, c2, c3, fe, be; };
+PHMM_HD FbBounds fb_bounds(const int b0, const int b1, const int b2, const int b3, const int W)
+{
+    FbBounds g;
+    g.c0 = fb_boundary_valid(b0, W) ? b0 : -1; g.c1 = fb_boundary_valid(b1, W) ? b1 : -1;
+    g.c2 = fb_boundary_valid(b2, W) ? b2 : -1; g.c3 = fb_boundary_valid(b3, W) ? b3 : -1;
+    int fe = g.c0 > g.c1 ? g.c0 : g.c1; { const int m2 = g.c2 > g.c3 ? g.c2 : g.c3; if (m2 > fe) fe = m2; }
+    int be = 0x7fffffff;
+    if (g.c0 > 0 && g.c0 < be) be = g.c0;
+    if (g.c1 > 0 && g.c1 < be) be = g.c1;
+    if (g.c2 > 0 && g.c2 < be) be = g.c2;
+    if (g.c3 > 0 && g.c3 < be) be = g.c3;
+    g.fe = fe; g.be = be;
+    return g;
+}
+PHMM_HD int fb_slot_column(const FbBounds& g, const int s) { return s == 0 ? g.c0 : s == 1 ? g.c1 : s == 2 ? g.c2 : g.c3; }
+// Slots that name the same column share one copy of the band (the packed words hold both halves anyway): the representative of
+// slot s is the first slot with its column — the usual case is ONE stored column for a lane's two alignments.
+PHMM_HD int fb_slot_rep(const FbBounds& g, const int s)
+{
+    const int c = fb_slot_column(g, s);
+    if (s >= 1 && g.c0 == c) return 0;
+    if (s >= 2 && g.c1 == c) return 1;
+    if (s >= 3 && g.c2 == c) return 2;
+    return s;
+}
 
 template <int K>
 PHMM_HD void fb_store(uint32_t* __restrict__ dst, const size_t stride, const uint32_t (&a0)[K], const uint32_t (&a1)[K])
@@ -841,76 +872,33 @@ PHMM_HD void fb_store(uint32_t* __restrict__ dst, const size_t stride, const uin
 #pragma unroll
     for (int k = 0; k < K; ++k) { dst[(size_t)k * stride] = a0[k]; dst[(size_t)(K + k) * stride] = a1[k]; }
 }
-
-// One boundary column of one half: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k),
-// the paths that ended before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or
-// beyond it (k >= xb: the backward pass left the start cell's total in Bm[k]).
-PHMM_HD void fb_decide(const uint32_t* scr /* written earlier by this very thread: no __restrict__, the loads must stay coherent */, const size_t stride, const int K, const int slot, const int half,
-                       const int xb, const int L, int* total, int* v_out, int* y_out, int* tie)
-{
-    const uint32_t* fm = scr + (size_t)(slot * kFbArrays + 0) * K * stride;
-    const uint32_t* fd = scr + (size_t)(slot * kFbArrays + 1) * K * stride;
-    const uint32_t* bm = scr + (size_t)(slot * kFbArrays + 2) * K * stride;
-    const uint32_t* bd = scr + (size_t)(slot * kFbArrays + 3) * K * stride;
-    const int sh = half * 16;
-    int T = 0x7fffffff, v = 0, y = 0, t = 0;
-    for (int k = 0; k < K; ++k) {
-        const int FM = (int)((fm[(size_t)k * stride] >> sh) & 0xFFFFu), BM = (int)((bm[(size_t)k * stride] >> sh) & 0xFFFFu);
-        int tot, cv, cy;
-        if (k < xb - L) { tot = FM; cv = FM; cy = L; }
-        else if (k >= xb) { tot = BM; cv = 0; cy = 0; }
-        else {
-            const int FD = (int)((fd[(size_t)k * stride] >> sh) & 0xFFFFu), BD = (int)((bd[(size_t)k * stride] >> sh) & 0xFFFFu);
-            cy = xb - k;
-            tot = FD + BD; cv = FD;
-            if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
-            else if (tot == T && (cv != v || cy != y)) t = 1;
-            tot = FM + BM; cv = FM;
-        }
-        if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
-        else if (tot == T && (cv != v || cy != y)) t = 1;
+// the band's two arrays of a boundary column → scratch, once per slot whose boundary this column is (rolled over the slots)
+#define PHMM_FB_STORE(A0, A1)                                                                           \
+    {                                                                                                   \
+        _Pragma("unroll 1") for (int s_ = 0; s_ < kFbSlots; ++s_)                                       \
+            if (fb_slot_column(g, s_) == next && fb_slot_rep(g, s_) == s_) fb_store<K>(scr + (size_t)(s_ * 2) * K * stride, stride, A0, A1); \
     }
-    *total = T; *v_out = v; *y_out = y; *tie = t;
-}
+#define PHMM_FB_NEXT_ABOVE(v) { int n_ = 0x7fffffff; if (g.c0 > (v) && g.c0 < n_) n_ = g.c0; if (g.c1 > (v) && g.c1 < n_) n_ = g.c1; if (g.c2 > (v) && g.c2 < n_) n_ = g.c2; if (g.c3 > (v) && g.c3 < n_) n_ = g.c3; next = n_; }
+#define PHMM_FB_NEXT_BELOW(v) { int n_ = -1; if (g.c0 < (v) && g.c0 > n_) n_ = g.c0; if (g.c1 < (v) && g.c1 > n_) n_ = g.c1; if (g.c2 < (v) && g.c2 > n_) n_ = g.c2; if (g.c3 < (v) && g.c3 > n_) n_ = g.c3; next = n_; }
 
+// Forward pass: dp_pair's column sweep over [0, fe); at every boundary column the arrivals (M, D) of the band go to
+// scr[((slot * 2 + {0, 1}) * 2B + k) * stride].
 template <int BAND, bool OGE>
-PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
-                         const uint32_t nucp, const int b0, const int b1, const int b2, const int b3,
-                         uint32_t* __restrict__ scr, const size_t stride, FbResult* res0, FbResult* res1, const uint32_t one = 1u)
+PHMM_HD void dp_flank_fwd(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+                          const uint32_t nucp, const FbBounds g, uint32_t* __restrict__ scr, const size_t stride, const uint32_t one = 1u)
 {
     constexpr int K = 2 * BAND;
     static_assert(K <= 64, "register band limited to 64 diagonals");
     const int W = L + K - 1;
-    const int c0 = fb_boundary_valid(b0, W) ? b0 : -1, c1 = fb_boundary_valid(b1, W) ? b1 : -1;
-    const int c2 = fb_boundary_valid(b2, W) ? b2 : -1, c3 = fb_boundary_valid(b3, W) ? b3 : -1;
-    int fe = c0 > c1 ? c0 : c1; { const int m2 = c2 > c3 ? c2 : c3; if (m2 > fe) fe = m2; }        // the forward pass covers columns [0, fe)
-    const int kBig = 0x7fffffff;
-    int be = kBig;                                                                                   // the backward pass covers columns [be, W]
-    if (c0 > 0 && c0 < be) be = c0;
-    if (c1 > 0 && c1 < be) be = c1;
-    if (c2 > 0 && c2 < be) be = c2;
-    if (c3 > 0 && c3 < be) be = c3;
+    if (g.fe <= 0) return;
     const RowEntry w0 = rows[0];
-#define PHMM_FB_NEXT_ABOVE(v) { int n_ = kBig; if (c0 > (v) && c0 < n_) n_ = c0; if (c1 > (v) && c1 < n_) n_ = c1; if (c2 > (v) && c2 < n_) n_ = c2; if (c3 > (v) && c3 < n_) n_ = c3; next = n_; }
-#define PHMM_FB_NEXT_BELOW(v) { int n_ = -1; if (c0 < (v) && c0 > n_) n_ = c0; if (c1 < (v) && c1 > n_) n_ = c1; if (c2 < (v) && c2 > n_) n_ = c2; if (c3 < (v) && c3 > n_) n_ = c3; next = n_; }
-// the band's two arrays of a boundary column → scratch, once per slot whose boundary this column is (rolled over the slots)
-#define PHMM_FB_STORE(arr0, A0, A1)                                                                     \
-    {                                                                                                   \
-        _Pragma("unroll 1") for (int s_ = 0; s_ < kFbSlots; ++s_) {                                     \
-            const int cs_ = s_ == 0 ? c0 : s_ == 1 ? c1 : s_ == 2 ? c2 : c3;                            \
-            if (cs_ == next) fb_store<K>(scr + (size_t)(s_ * kFbArrays + (arr0)) * K * stride, stride, A0, A1); \
-        }                                                                                               \
-    }
-
-    // ---- forward: dp_pair's column sweep over [0, fe) ----
-    if (fe > 0) {
-        uint32_t M[K], D[K];
+    uint32_t M[K], D[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kInf16x2; }
-        ColEntry e0 = ldg(t0), e1 = ldg(t1);
-        uint32_t go_prev = 0u, ge_prev = 0u;
-        int next;
-        PHMM_FB_NEXT_ABOVE(0)
+    for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kInf16x2; }
+    ColEntry e0 = ldg(t0), e1 = ldg(t1);
+    uint32_t go_prev = 0u, ge_prev = 0u;
+    int next;
+    PHMM_FB_NEXT_ABOVE(0)
 #define PHMM_CELL(k)                                                                        \
     {                                                                                       \
         const RowEntry w   = rp[-(k)];                                                      \
@@ -923,54 +911,63 @@ PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const C
     }
 #define PHMM_CASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_CELL(k)
 #define PHMM_CASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
-        for (int x = 0; x < fe; ++x) {
-            const int xn = (x + 1 < W) ? x + 1 : W - 1;
-            const ColEntry n0 = ldg(t0 + xn), n1 = ldg(t1 + xn);
-            const uint32_t caps0 = e0.x, caps1 = e1.x;
-            const uint32_t go = prmt(e0.y, e1.y, 0x3430u), ge = prmt(e0.y, e1.y, 0x3531u);
-            const uint32_t gop = go_prev + nucp, gep = ge_prev + nucp;
-            const RowEntry* rp = rows + x;
-            uint32_t i_run = kInf16x2;
-            if (x >= K) {
-                if (x <= L) {
+    for (int x = 0; x < g.fe; ++x) {
+        const int xn = (x + 1 < W) ? x + 1 : W - 1;
+        const ColEntry n0 = ldg(t0 + xn), n1 = ldg(t1 + xn);
+        const uint32_t caps0 = e0.x, caps1 = e1.x;
+        const uint32_t go = prmt(e0.y, e1.y, 0x3430u), ge = prmt(e0.y, e1.y, 0x3531u);
+        const uint32_t gop = go_prev + nucp, gep = ge_prev + nucp;
+        const RowEntry* rp = rows + x;
+        uint32_t i_run = kInf16x2;
+        if (x >= K) {
+            if (x <= L) {
 #pragma unroll
-                    for (int k = K - 1; k >= 0; --k) PHMM_CELL(k)
-                } else {
-                    const int klo = x - L;
-#pragma unroll
-                    for (int k = K - 1; k >= 0; --k) {
-                        PHMM_CELL(k)
-                        if (k == klo) break;
-                    }
-                }
+                for (int k = K - 1; k >= 0; --k) PHMM_CELL(k)
             } else {
-                const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));
-                i_run = (x & 1) ? gop : kInf16x2;
-                switch (x) { PHMM_REP64(PHMM_CASE_PROLOGUE) default: break; }
-                switch (x) { PHMM_REP64(PHMM_CASE_ROW0) default: break; }
+                const int klo = x - L;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    PHMM_CELL(k)
+                    if (k == klo) break;
+                }
             }
-            go_prev = go; ge_prev = ge;
-            if (x + 1 == next) {                 // M / D now hold the arrivals of column x + 1: a flank boundary of one of the halves
-                PHMM_FB_STORE(0, M, D)
-                PHMM_FB_NEXT_ABOVE(x + 1)
-            }
-            const uint32_t z = i_run & 0x80008000u;          // see dp_pair: keeps the prefetch out of e0 / e1 until the column is done
-            e0.x = n0.x + z; e0.y = n0.y + z; e1.x = n1.x + z; e1.y = n1.y + z;
+        } else {
+            const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));
+            i_run = (x & 1) ? gop : kInf16x2;
+            switch (x) { PHMM_REP64(PHMM_CASE_PROLOGUE) default: break; }
+            switch (x) { PHMM_REP64(PHMM_CASE_ROW0) default: break; }
         }
+        go_prev = go; ge_prev = ge;
+        if (x + 1 == next) {                 // M / D now hold the arrivals of column x + 1: a flank boundary of one of the halves
+            PHMM_FB_STORE(M, D)
+            PHMM_FB_NEXT_ABOVE(x + 1)
+        }
+        const uint32_t z = i_run & 0x80008000u;          // see dp_pair: keeps the prefetch out of e0 / e1 until the column is done
+        e0.x = n0.x + z; e0.y = n0.y + z; e1.x = n1.x + z; e1.y = n1.y + z;
+    }
 #undef PHMM_CELL
 #undef PHMM_CASE_PROLOGUE
 #undef PHMM_CASE_ROW0
-    }
+}
 
-    // ---- backward: cost-to-go over [be, W], columns downwards, diagonals upwards ----
-    if (be != kBig) {
-        uint32_t BM[K], BD[K];
+// Backward pass: cost-to-go over [be, W], columns downwards, diagonals upwards; at every boundary column (Bm, Bd) of the band go
+// to scr[((slot * 2 + {0, 1}) * 2B + k) * stride]. Independent of the deletion-update form (OGE).
+template <int BAND>
+PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+                          const uint32_t nucp, const FbBounds g, uint32_t* __restrict__ scr, const size_t stride, const uint32_t one = 1u)
+{
+    constexpr int K = 2 * BAND;
+    static_assert(K <= 64, "register band limited to 64 diagonals");
+    const int W = L + K - 1;
+    if (g.be == 0x7fffffff) return;
+    const RowEntry w0 = rows[0];
+    uint32_t BM[K], BD[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) { BM[k] = kInf16x2; BD[k] = kInf16x2; }
-        ColEntry p0 = ldg(t0 + (W - 1)), p1 = ldg(t1 + (W - 1));      // entries of column x - 1
-        uint32_t caps0 = 0u, caps1 = 0u, go = 0u, ge = 0u;             // column x (column W holds the end cell only)
-        int next;
-        PHMM_FB_NEXT_BELOW(W)
+    for (int k = 0; k < K; ++k) { BM[k] = kInf16x2; BD[k] = kInf16x2; }
+    ColEntry p0 = ldg(t0 + (W - 1)), p1 = ldg(t1 + (W - 1));      // entries of column x - 1
+    uint32_t caps0 = 0u, caps1 = 0u, go = 0u, ge = 0u;             // column x (column W holds the end cell only)
+    int next;
+    PHMM_FB_NEXT_BELOW(W)
 #define PHMM_BKCELL(k)                                                                      \
     {                                                                                       \
         const RowEntry w   = rp[-(k)];                                                      \
@@ -985,64 +982,116 @@ PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const C
 #define PHMM_BCASE_ROWL(k)  case (k): if ((k) < K) { BM[(k) < K ? (k) : 0] = 0u; BD[(k) < K ? (k) : 0] = 0u; } break;
 #define PHMM_BCASE_EPI(k)   case (k) - 1: if ((k) >= 1 && (k) < K) PHMM_BKCELL(k)
 #define PHMM_BCASE_START(k) case (k): if ((k) < K) { const uint32_t a = fma_add(BM[(k) < K ? (k) : 0], sub0, one); BM[(k) < K ? (k) : 0] = (x & 1) ? vaddmin(i_run, gop, a) : a; } break;
-        for (int x = W; x >= be; --x) {
-            const int xp = x >= 2 ? x - 2 : 0;
-            const ColEntry n0 = ldg(t0 + xp), n1 = ldg(t1 + xp);
-            const uint32_t go_p = prmt(p0.y, p1.y, 0x3430u), ge_p = prmt(p0.y, p1.y, 0x3531u);     // column x - 1
-            const uint32_t gop = go_p + nucp, gep = ge_p + nucp;
-            const RowEntry* rp = rows + x;
-            uint32_t i_run;
-            if (x >= L) {
-                const int klo = x - L;           // the end-row cell: cost-to-go 0 in every state
-                switch (klo) { PHMM_REP64A(PHMM_BCASE_ROWL) default: break; }
-                i_run = 0u;
-                switch (klo) { PHMM_REP64A(PHMM_BCASE_EPI) default: break; }
-            } else if (x >= K) {
-                i_run = kInf16x2;
+    for (int x = W; x >= g.be; --x) {
+        const int xp = x >= 2 ? x - 2 : 0;
+        const ColEntry n0 = ldg(t0 + xp), n1 = ldg(t1 + xp);
+        const uint32_t go_p = prmt(p0.y, p1.y, 0x3430u), ge_p = prmt(p0.y, p1.y, 0x3531u);     // column x - 1
+        const uint32_t gop = go_p + nucp, gep = ge_p + nucp;
+        const RowEntry* rp = rows + x;
+        uint32_t i_run;
+        if (x >= L) {
+            const int klo = x - L;           // the end-row cell: cost-to-go 0 in every state
+            switch (klo) { PHMM_REP64A(PHMM_BCASE_ROWL) default: break; }
+            i_run = 0u;
+            switch (klo) { PHMM_REP64A(PHMM_BCASE_EPI) default: break; }
+        } else if (x >= K) {
+            i_run = kInf16x2;
 #pragma unroll
-                for (int k = 0; k < K; ++k) PHMM_BKCELL(k)
-            } else {
-                i_run = kInf16x2;
+            for (int k = 0; k < K; ++k) PHMM_BKCELL(k)
+        } else {
+            i_run = kInf16x2;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    if (k == x) break;
-                    PHMM_BKCELL(k)
-                }
-                const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));       // the start cell (x, 0): its total stays in BM[x]
-                switch (x) { PHMM_REP64A(PHMM_BCASE_START) default: break; }
+            for (int k = 0; k < K; ++k) {
+                if (k == x) break;
+                PHMM_BKCELL(k)
             }
-            if (x == next) {
-                PHMM_FB_STORE(2, BM, BD)
-                PHMM_FB_NEXT_BELOW(x)
-            }
-            const uint32_t z = i_run & 0x80008000u;
-            caps0 = p0.x; caps1 = p1.x; go = go_p; ge = ge_p;
-            p0.x = n0.x + z; p0.y = n0.y + z; p1.x = n1.x + z; p1.y = n1.y + z;
+            const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));       // the start cell (x, 0): its total stays in BM[x]
+            switch (x) { PHMM_REP64A(PHMM_BCASE_START) default: break; }
         }
+        if (x == next) {
+            PHMM_FB_STORE(BM, BD)
+            PHMM_FB_NEXT_BELOW(x)
+        }
+        const uint32_t z = i_run & 0x80008000u;
+        caps0 = p0.x; caps1 = p1.x; go = go_p; ge = ge_p;
+        p0.x = n0.x + z; p0.y = n0.y + z; p1.x = n1.x + z; p1.y = n1.y + z;
+    }
 #undef PHMM_BKCELL
 #undef PHMM_BCASE_ROWL
 #undef PHMM_BCASE_EPI
 #undef PHMM_BCASE_START
-    }
+}
 #undef PHMM_FB_NEXT_ABOVE
 #undef PHMM_FB_NEXT_BELOW
 #undef PHMM_FB_STORE
 
-    // ---- the crossing cells ----
-#pragma unroll
+// One boundary column of one half: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k),
+// the paths that ended before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or
+// beyond it (k >= xb: the backward pass left the start cell's total in Bm[k]). fscr / bscr: the slot's forward / backward arrays
+// (written earlier by this very thread or by the forward kernel: no __restrict__, the loads must stay coherent).
+PHMM_HD void fb_decide(const uint32_t* fscr, const size_t fstride, const uint32_t* bscr, const size_t bstride, const int K, const int half,
+                       const int xb, const int L, int* total, int* v_out, int* y_out, int* tie)
+{
+    const int sh = half * 16;
+    int T = 0x7fffffff, v = 0, y = 0, t = 0;
+    for (int k = 0; k < K; ++k) {
+        const int FM = (int)((fscr[(size_t)k * fstride] >> sh) & 0xFFFFu), BM = (int)((bscr[(size_t)k * bstride] >> sh) & 0xFFFFu);
+        int tot, cv, cy;
+        if (k < xb - L) { tot = FM; cv = FM; cy = L; }
+        else if (k >= xb) { tot = BM; cv = 0; cy = 0; }
+        else {
+            const int FD = (int)((fscr[(size_t)(K + k) * fstride] >> sh) & 0xFFFFu), BD = (int)((bscr[(size_t)(K + k) * bstride] >> sh) & 0xFFFFu);
+            cy = xb - k;
+            tot = FD + BD; cv = FD;
+            if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
+            else if (tot == T && (cv != v || cy != y)) t = 1;
+            tot = FM + BM; cv = FM;
+        }
+        if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
+        else if (tot == T && (cv != v || cy != y)) t = 1;
+    }
+    *total = T; *v_out = v; *y_out = y; *tie = t;
+}
+
+// The crossing cells of both halves from the two passes' boundary columns → score, in-flank penalty, in-flank read bases, tie.
+PHMM_HD void fb_finish(const int K, const int L, const FbBounds& g, const uint32_t* fscr, const size_t fstride,
+                       const uint32_t* bscr, const size_t bstride, FbResult* res0, FbResult* res1)
+{
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-        const int xl = half ? c2 : c0, xr = half ? c3 : c1;
-        int T = 0, Tl = 0, Tr = 0, v_l = 0, y_l = 0, v_r = 0, y_r = L, tl = 0, tr = 0;
-        if (xl > 0) { fb_decide(scr, stride, K, 2 * half, half, xl, L, &Tl, &v_l, &y_l, &tl); T = Tl; }
-        if (xr > 0) { fb_decide(scr, stride, K, 2 * half + 1, half, xr, L, &Tr, &v_r, &y_r, &tr); T = Tr; }
-        else v_r = T;
+        int T = 0, Tx[2] = {0, 0}, v[2] = {0, 0}, y[2] = {0, L}, t[2] = {0, 0};
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const int slot = 2 * half + side, xb = fb_slot_column(g, slot);
+            if (xb > 0) {
+                int Ts, vs, ys, ts;
+                const int rep = fb_slot_rep(g, slot);
+                fb_decide(fscr + (size_t)(rep * 2) * K * fstride, fstride, bscr + (size_t)(rep * 2) * K * bstride, bstride, K, half, xb, L, &Ts, &vs, &ys, &ts);
+                if (side == 0) { Tx[0] = Ts; v[0] = vs; y[0] = ys; t[0] = ts; } else { Tx[1] = Ts; v[1] = vs; y[1] = ys; t[1] = ts; }
+                T = Ts;
+            }
+        }
+        const int xl = fb_slot_column(g, 2 * half), xr = fb_slot_column(g, 2 * half + 1);
+        if (xr <= 0) v[1] = T;                  // no right flank inside the window: nothing beyond xr to discount
         FbResult r;
         r.score = T;
-        r.flank = v_l + (T - v_r);
-        r.mask = y_l + (L - y_r);
-        r.tie = tl | tr | ((xl > 0 && xr > 0 && Tl != Tr) ? 1 : 0);
+        r.flank = v[0] + (T - v[1]);
+        r.mask = y[0] + (L - y[1]);
+        r.tie = t[0] | t[1] | ((xl > 0 && xr > 0 && Tx[0] != Tx[1]) ? 1 : 0);
         if (half) *res1 = r; else *res0 = r;
     }
+}
+
+// Both passes and the decision in one call (tests/cpu_emul; the kernels run the passes in two launches: k_flank_fwd / k_flank_bwd).
+template <int BAND, bool OGE>
+PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+                         const uint32_t nucp, const int b0, const int b1, const int b2, const int b3,
+                         uint32_t* fscr, const size_t fstride, uint32_t* bscr, const size_t bstride, FbResult* res0, FbResult* res1, const uint32_t one = 1u)
+{
+    const FbBounds g = fb_bounds(b0, b1, b2, b3, L + 2 * BAND - 1);
+    dp_flank_fwd<BAND, OGE>(rows, L, t0, t1, nucp, g, fscr, fstride, one);
+    dp_flank_bwd<BAND>(rows, L, t0, t1, nucp, g, bscr, bstride, one);
+    fb_finish(2 * BAND, L, g, fscr, fstride, bscr, bstride, res0, res1);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -64,7 +64,7 @@ struct phmm_engine {
     // derived / scratch
     DBuf tab_f, tab_r, rowhalf, info, flags, best, status, out, slow, counters, pairs, generic_reads, wide_reads, bp, regs, rregion, rpbase, rpstride;
     DBuf tasks_lane, tasks_generic, works, scores;
-    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, atasks, gcnt, sched, sorted, fb_scratch;
+    DBuf rhash, kbins, kitems, kpos, kcnt, ftasks, fcnt, gtasks, atasks, gcnt, sched, sorted, fb_scratch, fb_pairs;
     std::vector<cudaEvent_t> tile_events;
     std::vector<int2> info_host;
     // per-kernel launch configuration already applied / queried (the runtime calls are not free and need not be repeated)
@@ -342,7 +342,7 @@ void phmm_destroy(phmm_engine* e)
                    &e->r_off, &e->r_bases, &e->r_quals, &e->r_mapq, &e->r_rev, &e->r_begin, &e->c_off, &e->c_pos,
                    &e->tab_f, &e->tab_r, &e->rowhalf, &e->info, &e->flags, &e->best, &e->status, &e->out, &e->slow,
                    &e->counters, &e->pairs, &e->generic_reads, &e->wide_reads, &e->bp, &e->regs, &e->rregion, &e->rpbase, &e->rpstride, &e->tasks_lane, &e->tasks_generic, &e->works, &e->scores,
-                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->atasks, &e->gcnt, &e->sched, &e->sorted, &e->fb_scratch};
+                   &e->rhash, &e->kbins, &e->kitems, &e->kpos, &e->kcnt, &e->ftasks, &e->fcnt, &e->gtasks, &e->atasks, &e->gcnt, &e->sched, &e->sorted, &e->fb_scratch, &e->fb_pairs};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t ev : e->tile_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -967,6 +967,8 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     p.slow_count = counters + 3;
     p.acc_cursor = counters + 4;
     p.any_acc_tasks = counters + 5;
+    p.fb_cursor = counters + 6;
+    p.fb_rounds = counters + 7;
 
     // Tile size: the per-tile scratch (mapped candidate lists, DP task lists, traceback queue) must fit fixed budgets.
     const long long slow_budget = 8LL << 20;   // traceback-queue entries (16 bytes each)
@@ -994,7 +996,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     }
     {
         CU(e->ftasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
-        CU(e->fcnt.ensure(3 * tile_list_cap * sizeof(int)));
+        CU(e->fcnt.ensure(4 * tile_list_cap * sizeof(int)));
         p.ftasks = e->ftasks.as<uint32_t>();
         p.fcnt = e->fcnt.as<int>();
         // the 32-bit flank kernel's lists (near-flank candidates, reads holding 'N'): whether any exist is only known on the device
@@ -1002,6 +1004,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         p.gtasks = e->gtasks.as<uint32_t>();
         p.gcnt = p.fcnt + tile_list_cap;
         p.acnt = p.fcnt + 2 * tile_list_cap;
+        p.fb_round_base = p.fcnt + 3 * tile_list_cap;
         if (p.use_flanks && band <= 32) {            // the lean flank kernel's lists
             CU(e->atasks.ensure(tile_list_cap * p.fcap * sizeof(uint32_t)));
             p.atasks = e->atasks.as<uint32_t>();
@@ -1088,16 +1091,26 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
     auto launch_flank = [&](int n_entries, int row_stride) -> int {
         if (band > 32) return PHMM_OK;              // wide bands: near-flank candidates take the traceback queue
         if (p.atasks && p.fb_route) {
-            // the packed forward / backward flank kernel over the atasks lists; it runs BEFORE k_populate_flank, which also resolves
-            // the candidates this kernel reports as tied (appended to the gtasks lists)
+            // the packed forward / backward flank kernels over the atasks lists; they run BEFORE k_populate_flank, which also resolves the
+            // candidates they report as tied or could not place in the forward scratch (appended to the gtasks lists)
             const size_t fbsmem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
+            // forward scratch: one round (64 candidates) per fb_round_words; worst case = every list slot's full task list, capped at 4 GiB
+            const long long rounds_worst = (long long)n_entries * ((p.fcap + 63) / 64);
             int fb_blocks = 1, frc2;
 #define PHMM_FB_LAUNCH(B) \
-            { if ((frc2 = fast_smem_attr(e, k_populate_flank_fb<B>, fbsmem)) || (frc2 = blocks_per_sm_of(e, k_populate_flank_fb<B>, kFastWarpsPerBlock * 32, fbsmem, &fb_blocks))) return frc2; \
+            { if ((frc2 = fast_smem_attr(e, k_flank_fwd<B>, fbsmem)) || (frc2 = fast_smem_attr(e, k_flank_bwd<B>, fbsmem)) || \
+                  (frc2 = blocks_per_sm_of(e, k_flank_bwd<B>, kFastWarpsPerBlock * 32, fbsmem, &fb_blocks))) return frc2; \
               if (fb_blocks < 1) { e->err = "flank kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; } \
               const unsigned bgrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * fb_blocks)); \
-              if (cudaError_t ce = e->fb_scratch.ensure((size_t)bgrid * kFastWarpsPerBlock * 32 * fb_scratch_words(B) * sizeof(uint32_t))) { e->err = cudaGetErrorString(ce); return PHMM_ERR_NOMEM; } \
-              k_populate_flank_fb<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_scratch.as<uint32_t>()); }
+              const size_t round_bytes = fb_round_words(B) * sizeof(uint32_t); \
+              const long long cap = std::max<long long>(1, std::min<long long>(rounds_worst, (long long)((4ull << 30) / round_bytes))); \
+              cudaError_t ce = e->fb_pairs.ensure((size_t)cap * round_bytes); \
+              if (ce == cudaSuccess) ce = e->fb_scratch.ensure((size_t)bgrid * kFastWarpsPerBlock * 32 * fb_scratch_words(B) * sizeof(uint32_t)); \
+              if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return PHMM_ERR_NOMEM; } \
+              p.fb_round_cap = (int)std::min<long long>(0x7fffffff, (long long)(e->fb_pairs.cap / round_bytes)); \
+              k_flank_fwd<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_pairs.as<uint32_t>()); \
+              LAUNCHED(); \
+              k_flank_bwd<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_pairs.as<uint32_t>(), e->fb_scratch.as<uint32_t>()); }
             if (band == 8) PHMM_FB_LAUNCH(8) else PHMM_FB_LAUNCH(16)
 #undef PHMM_FB_LAUNCH
             LAUNCHED();
@@ -1145,7 +1158,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            CU(cudaMemsetAsync(counters, 0, 6 * sizeof(int), e->stream));                       // cursors, any-tasks flags (the traceback queue is empty between tiles)
+            CU(cudaMemsetAsync(counters, 0, 8 * sizeof(int), e->stream));                       // cursors, any-tasks flags (the traceback queue is empty between tiles)
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.gcnt, 0, (size_t)2 * np * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.acnt, 0, (size_t)2 * np * sizeof(int), e->stream));
@@ -1187,7 +1200,7 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
                 LAUNCHED();
                 p.kpos = e->kpos.as<int32_t>(); p.kcnt = e->kcnt.as<uint8_t>();
             }
-            CU(cudaMemsetAsync(counters, 0, 6 * sizeof(int), e->stream));
+            CU(cudaMemsetAsync(counters, 0, 8 * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.fcnt, 0, (size_t)nw * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.gcnt, 0, (size_t)nw * sizeof(int), e->stream));
             CU(cudaMemsetAsync(p.acnt, 0, (size_t)nw * sizeof(int), e->stream));

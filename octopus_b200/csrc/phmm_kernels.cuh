@@ -389,7 +389,11 @@ struct PopParams {
     int* acnt;
     int* acc_cursor;
     int* any_acc_tasks;
-    int fb_route;               // the atasks lists of this tile go to k_populate_flank_fb (pair list, bands <= 16): any flank geometry, reads of >= 2*band bases
+    int fb_route;               // the atasks lists of this tile go to k_flank_fwd / k_flank_bwd (pair list, bands <= 16): any flank geometry, reads of >= 2*band bases
+    int* fb_cursor;             // work counter of k_flank_bwd (k_flank_fwd uses acc_cursor)
+    int* fb_rounds;             // rounds of forward scratch handed out so far (this tile)
+    int* fb_round_base;         // per list slot: first round of the read's forward scratch, -1 = none left
+    int fb_round_cap;
     int units_per_pair;         // fast kernel: a read pair's task lists are cut into this many work units of kRoundsPerUnit rounds
     const RegionInfo* regs;     // regions of the call (one for phmm_populate); the flank state is per region
     int Hmax;                   // most haplotypes any region has: per-read loops run over Hmax slots and skip the ones beyond the region
@@ -924,15 +928,23 @@ k_populate_flank_acc(const PopParams p)
     }
 }
 
-constexpr int kFlankFbMaxBand = 16;     // widest band served by k_populate_flank_fb: its register band holds 2 * band diagonals (band 32 spills: it keeps the lean labelled kernel)
-// The packed forward / backward flank kernel (dp_flank_fb): one READ per warp — both packed halves carry the same read, so a lane
-// works on TWO of the read's near-flank candidates (two haplotype windows) at once, 64 per round. Boundary columns of the two
-// windows go through `scratch` (fb_scratch_words(BAND) words per thread, thread-interleaved). A candidate whose co-optimal paths
-// cross a flank boundary at different cells (FbResult::tie, ~1 %) is appended to the read's gtasks list: k_populate_flank, launched
-// after this kernel, resolves it with the labelled DP.
+constexpr int kFlankFbMaxBand = 16;     // widest band served by k_flank_fwd / k_flank_bwd: their register band holds 2 * band diagonals (band 32 spills: it keeps the lean labelled kernel)
+// words of one round's forward arrays: 64 candidates = 32 lanes x (4 boundary slots x {M, D} x 2B diagonals), lane-interleaved
+__host__ __device__ constexpr size_t fb_round_words(const int band) { return (size_t)kFbSlots * 2 * 2 * (size_t)band * 32; }
+
+// The packed forward / backward flank kernels (dp_flank_fwd / dp_flank_bwd): one READ per warp — both packed halves carry the same
+// read, so a lane works on TWO of the read's near-flank candidates (two haplotype windows) at once, 64 per round. Two launches over the
+// same atasks lists with the same (list slot, round, lane, half) → candidate mapping:
+//   k_flank_fwd  forward pass up to the last flank boundary of the lane's two windows; the band's arrivals at the boundary columns go
+//                to `pair_scratch` (fb_round_words(BAND) words per round, handed out by an atomic counter; a read that finds no room
+//                is marked and k_flank_bwd sends its candidates to the labelled DP);
+//   k_flank_bwd  backward pass from the window end down to the first boundary, crossing cells from F + B (fb_finish), flank discount,
+//                minimum into best[]. A candidate whose co-optimal paths cross a boundary at different cells (FbResult::tie, ~1 %) is
+//                appended to the read's gtasks list: k_populate_flank, launched after these two, resolves it with the labelled DP.
+// (One fused kernel measured 0.9 x the labelled kernel: its code overflows the instruction cache, profiles/r02n.)
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
-k_populate_flank_fb(const PopParams p, uint32_t* __restrict__ scratch)
+k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch)
 {
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -940,8 +952,6 @@ k_populate_flank_fb(const PopParams p, uint32_t* __restrict__ scratch)
     constexpr int K = 2 * BAND;
     if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    uint32_t* scr = scratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     const bool oge = open_ge_extend(p.flags);
     for (;;) {
@@ -952,6 +962,76 @@ k_populate_flank_fb(const PopParams p, uint32_t* __restrict__ scratch)
         const int r = p.list[li];
         const int n = r >= 0 ? p.acnt[li] : 0;
         if (n == 0) continue;
+        const int rounds = (n + 63) >> 6;
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(p.fb_rounds, rounds);
+            if (base + rounds > p.fb_round_cap) base = -1;
+            p.fb_round_base[li] = base;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base < 0) continue;                               // no scratch left: k_flank_bwd hands the read's candidates to the labelled DP
+        const int L = p.rd.info[r].x;
+        const RegionInfo reg = p.regs[p.rd.region[r]];
+        __syncwarp();
+        {
+            const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
+            for (int y = lane; y < L; y += 32) { const uint32_t half = hr[y]; rows[y] = make_row_entry(half, half); }
+            if (lane == 0) rows[L] = pad_row_entry();
+            __syncwarp();
+        }
+        const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
+        const int W = L + K - 1;
+        for (int c = 0; c < n; c += 64) {
+            const int i0 = c + 2 * lane, i1 = i0 + 1;
+            const bool v0 = i0 < n, v1 = i1 < n;
+            const uint32_t w0 = q[v0 ? i0 : 0], w1 = v1 ? q[i1] : w0;        // idle halves replay a valid task (result discarded)
+            const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
+            int lhs0, rhs0, lhs1, rhs1;
+            window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
+            window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
+            const FbBounds g = fb_bounds(lhs0, W - rhs0, lhs1, W - rhs1, W);
+            const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
+            uint32_t* fscr = pair_scratch + (size_t)(base + (c >> 6)) * fb_round_words(BAND) + lane;
+            if (oge) dp_flank_fwd<BAND, true>(rows, L, c0, c1, nucp, g, fscr, 32, (uint32_t)p.one);
+            else dp_flank_fwd<BAND, false>(rows, L, c0, c1, nucp, g, fscr, 32, (uint32_t)p.one);
+        }
+    }
+}
+
+template <int BAND>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
+k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restrict__ thread_scratch)
+{
+    extern __shared__ RowEntry smem_rows[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RowEntry* rows = smem_rows + warp * p.row_stride;
+    constexpr int K = 2 * BAND;
+    if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
+    const int n_list = tile_list(p);
+    const size_t bstride = (size_t)gridDim.x * blockDim.x;
+    uint32_t* bscr = thread_scratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
+    for (;;) {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(p.fb_cursor, 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li >= n_list) break;
+        const int r = p.list[li];
+        const int n = r >= 0 ? p.acnt[li] : 0;
+        if (n == 0) continue;
+        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
+        const int base = p.fb_round_base[li];
+        if (base < 0) {                                       // the forward kernel found no scratch for this read: labelled DP for all its candidates
+            for (int i = lane; i < n; i += 32) {
+                const int slot = atomicAdd(p.gcnt + li, 1);
+                if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = q[i];
+                else atomicOr(p.flags, 8);
+            }
+            if (lane == 0) *p.any_flank_tasks = 1;
+            continue;
+        }
         const int L = p.rd.info[r].x;
         const RegionInfo reg = p.regs[p.rd.region[r]];
         __syncwarp();
@@ -966,20 +1046,20 @@ k_populate_flank_fb(const PopParams p, uint32_t* __restrict__ scratch)
         for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
         const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
-        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
         const int W = L + K - 1;
         for (int c = 0; c < n; c += 64) {
             const int i0 = c + 2 * lane, i1 = i0 + 1;
             const bool v0 = i0 < n, v1 = i1 < n;
-            const uint32_t w0 = q[v0 ? i0 : 0], w1 = v1 ? q[i1] : w0;        // idle halves replay a valid task (result discarded)
+            const uint32_t w0 = q[v0 ? i0 : 0], w1 = v1 ? q[i1] : w0;        // the forward kernel's mapping, exactly
             const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
             int lhs0, rhs0, lhs1, rhs1;
             window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
             window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
+            const FbBounds g = fb_bounds(lhs0, W - rhs0, lhs1, W - rhs1, W);
             const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
+            dp_flank_bwd<BAND>(rows, L, c0, c1, nucp, g, bscr, bstride, (uint32_t)p.one);
             FbResult f0, f1;
-            if (oge) dp_flank_fb<BAND, true>(rows, L, c0, c1, nucp, lhs0, W - rhs0, lhs1, W - rhs1, scr, stride, &f0, &f1, (uint32_t)p.one);
-            else dp_flank_fb<BAND, false>(rows, L, c0, c1, nucp, lhs0, W - rhs0, lhs1, W - rhs1, scr, stride, &f0, &f1, (uint32_t)p.one);
+            fb_finish(K, L, g, pair_scratch + (size_t)(base + (c >> 6)) * fb_round_words(BAND) + lane, 32, bscr, bstride, &f0, &f1);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (!(half ? v1 : v0)) continue;

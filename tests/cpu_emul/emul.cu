@@ -325,11 +325,11 @@ extern "C" int emul_dp_flank_fb(int band, int L, const char* read0, const uint8_
     }
     const uint32_t nucp = (uint32_t)nuc_prior | ((uint32_t)nuc_prior << 16);
     const bool oge = use_oge(go0, ge0, go1, ge1, W);
-    std::vector<uint32_t> scr(fb_scratch_words(band), 0xDEADBEEFu);
+    std::vector<uint32_t> fscr(fb_scratch_words(band), 0xDEADBEEFu), bscr(fb_scratch_words(band), 0xDEADBEEFu);
     FbResult r0, r1;
     const int b0 = lhs0, b1 = W - rhs0, b2 = lhs1, b3 = W - rhs1;
-#define RUN_FB(B) { if (oge) dp_flank_fb<B, true>(rows.data(), L, t0.data(), t1.data(), nucp, b0, b1, b2, b3, scr.data(), 1, &r0, &r1); \
-                    else dp_flank_fb<B, false>(rows.data(), L, t0.data(), t1.data(), nucp, b0, b1, b2, b3, scr.data(), 1, &r0, &r1); }
+#define RUN_FB(B) { if (oge) dp_flank_fb<B, true>(rows.data(), L, t0.data(), t1.data(), nucp, b0, b1, b2, b3, fscr.data(), 1, bscr.data(), 1, &r0, &r1); \
+                    else dp_flank_fb<B, false>(rows.data(), L, t0.data(), t1.data(), nucp, b0, b1, b2, b3, fscr.data(), 1, bscr.data(), 1, &r0, &r1); }
     switch (band) {
         case 8:  RUN_FB(8) break;
         case 16: RUN_FB(16) break;

@@ -1,20 +1,18 @@
 #!/bin/bash
-# round 2, GPU call N: the packed forward / backward flank kernel: parity tests, flank / production-mode
-# bench lines with and without it (PHMM_NO_FLANK_FB=1 = the labelled kernels of call L), launch list, one ncu capture
+# round 2, GPU call O: the packed forward / backward flank kernel: parity tests, flank / production-mode
+# split into k_flank_fwd + k_flank_bwd (the fused kernel of call N was instruction-cache bound); bench lines with and without (PHMM_NO_FLANK_FB=1), launch list, ncu of both kernels
 set -x
-O=gpurun_out/r02n
+O=gpurun_out/r02o
 mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_flank_fb.py tests/test_gpu_parity.py tests/test_gpu_wide.py -m gpu -x -q > $O/pytest_gpu_flank.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu_flank.log
 tail -6 $O/pytest_gpu_flank.log | cut -c1-400
 B="python bench.py --no-cpu-baseline --steps 3 --warmup 3"
 timeout 200 $B --config C2 --flank 60,60 > $O/bench_c2_flank.json 2> $O/bench_c2_flank.err
-PHMM_NO_FLANK_FB=1 timeout 200 $B --config C2 --flank 60,60 > $O/bench_c2_flank_nofb.json 2> $O/bench_c2_flank_nofb.err
 timeout 200 $B --config C2 --shortcut --map --flank 60,60 > $O/bench_c2_prod.json 2> $O/bench_c2_prod.err
-PHMM_NO_FLANK_FB=1 timeout 200 $B --config C2 --shortcut --map --flank 60,60 > $O/bench_c2_prod_nofb.json 2> $O/bench_c2_prod_nofb.err
 timeout 200 $B --config C2 --shortcut --map --flank 60,60 --error-model PCR-free.HiSeq-2500 > $O/bench_c2_prod_errmodel.json 2> $O/bench_c2_prod_errmodel.err
 timeout 200 $B --config C3 --flank 60,60 > $O/bench_c3_flank.json 2> $O/bench_c3_flank.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_c2_prod.csv $B --config C2 --shortcut --map --flank 60,60 --steps 1 --warmup 1 > $O/launches_prod.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_populate_flank_fb -s 1 -c 1 -o $O/flankfb16 $B --config C2 --flank 60,60 --steps 1 --warmup 1 > $O/ncu_flankfb.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_flank_ -s 2 -c 2 -o $O/flank_fwd_bwd16 $B --config C2 --flank 60,60 --steps 1 --warmup 1 > $O/ncu_flankfb.log 2>&1
 for f in $O/bench_*.json; do python - "$f" <<'PY'
 import sys, json
 f=sys.argv[1]
