@@ -564,6 +564,27 @@ PHMM_HD bool flank_replay_may_differ(const ColEntry* __restrict__ tab, const int
     return false;
 }
 
+// The same test from per-haplotype prefix counts (k_ncol_prefix): pre[i] = counts over the haplotype's bases up to and including
+// base i — low half: 'N'-like columns (all four caps <= 3) whose caps are not all exactly 2, high half: all 'N'-like columns.
+// preh points at the haplotype's first base, a is the window start inside the haplotype. Four loads instead of a loop over the
+// flank columns (which a lane of the flank kernels runs with a dependent load per column).
+PHMM_HD bool flank_replay_may_differ_pre(const uint32_t* __restrict__ preh, const int a, const int W, const int lhs, const int rhs,
+                                         const bool read_has_quality_below_2)
+{
+    const int l_end = lhs < W ? (lhs > 0 ? lhs : 0) : W;
+    int r_beg = W - (rhs > 0 ? rhs : 0);
+    if (r_beg < l_end) r_beg = l_end;
+    const int i0 = a, i1 = a + l_end, i2 = a + r_beg, i3 = a + W;           // flank columns: [i0, i1) and [i2, i3)
+    const uint32_t c = ((i1 > 0 ? ldg(preh + i1 - 1) : 0u) - (i0 > 0 ? ldg(preh + i0 - 1) : 0u)) +
+                       ((i3 > 0 ? ldg(preh + i3 - 1) : 0u) - (i2 > 0 ? ldg(preh + i2 - 1) : 0u));
+    return (c & 0xFFFFu) != 0u || (read_has_quality_below_2 && (c >> 16) != 0u);
+}
+PHMM_HD uint32_t ncol_class(const uint32_t caps)   // bit 0: counts for the low half, bit 16: for the high half
+{
+    if ((caps & 0xFCFCFCFCu) != 0u) return 0u;
+    return caps != 0x02020202u ? 0x00010001u : 0x00010000u;
+}
+
 // rows: shared-memory row entries (make_row_entry32), rows[L] = pad_row_entry32().
 // tab : column table of the window. xl / xr: first non-flank column and first right-flank column (0 <= xl < xr <= W);
 // xl == 0 / xr > W mean "no left / right flank". Outputs the integer score, the in-flank penalty and the in-flank read bases.
@@ -819,8 +840,9 @@ PHMM_HD void dp_flank_acc(const RowEntry* __restrict__ rows, const int L, const 
 //   Bm    = min(t, gop + Bi(x, y+1))                       only M opens an insertion ...
 //   Bi    = min(t, gep + Bi(x, y+1))                       ... I extends it (no D -> I)
 //   B(x, L) = 0 in every state (free end);  start cell (x, 0): total = min(A, x odd ? gop + Bi(x, 1) : inf)  (the initialiser quirk)
-// Per cell pair: PRMT, VIMNMX (sub), 4 VIADDMNMX on the ALU pipe, one IMAD — the band sweeps columns downwards and diagonals
-// upwards, so that Bm stays in place, Bd moves one diagonal down and the insertion chain runs through one register.
+// Per cell pair: PRMT, VIMNMX (sub), VIADDMNMX (Bd), 2 VIMNMX3 (Bm, Bi) on the ALU pipe and 4 additions as IMADs on the FMA pipe
+// (5 + 4, as the forward cell's 5 + 3) — the band sweeps columns downwards and diagonals upwards, so that Bm stays in place, Bd moves
+// one diagonal down and the insertion chain runs through one register.
 //
 // Boundaries: b[0], b[1] = xl, xr of the low half's alignment, b[2], b[3] of the high half's; a boundary is a window column in
 // [1, W-1], anything else (0, negative, >= W) means "no such flank". At each boundary column the forward arrivals (M, D) and the
@@ -975,9 +997,9 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const 
         const uint32_t a   = fma_add(BM[(k) < K ? (k) : 0], sub, one);                      \
         const uint32_t dd  = ((k) + 1 < K) ? BD[((k) + 1) < K ? (k) + 1 : 0] : kInf16x2;    \
         BD[(k) < K ? (k) : 0] = vaddmin(dd, ge, a);                                         \
-        const uint32_t t   = vaddmin(dd, go, a);                                            \
-        BM[(k) < K ? (k) : 0] = vaddmin(i_run, gop, t);                                     \
-        i_run = vaddmin(i_run, gep, t);                                                     \
+        const uint32_t od  = fma_add(dd, go, one);        /* open a deletion */             \
+        BM[(k) < K ? (k) : 0] = vmin3(a, od, fma_add(i_run, gop, one));                     \
+        i_run = vmin3(a, od, fma_add(i_run, gep, one));                                     \
     }
 #define PHMM_BCASE_ROWL(k)  case (k): if ((k) < K) { BM[(k) < K ? (k) : 0] = 0u; BD[(k) < K ? (k) : 0] = 0u; } break;
 #define PHMM_BCASE_EPI(k)   case (k) - 1: if ((k) >= 1 && (k) < K) PHMM_BKCELL(k)
@@ -1025,60 +1047,79 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const 
 #undef PHMM_FB_NEXT_BELOW
 #undef PHMM_FB_STORE
 
-// One boundary column of one half: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k),
-// the paths that ended before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or
-// beyond it (k >= xb: the backward pass left the start cell's total in Bm[k]). fscr / bscr: the slot's forward / backward arrays
-// (written earlier by this very thread or by the forward kernel: no __restrict__, the loads must stay coherent).
-PHMM_HD void fb_decide(const uint32_t* fscr, const size_t fstride, const uint32_t* bscr, const size_t bstride, const int K, const int half,
-                       const int xb, const int L, int* total, int* v_out, int* y_out, int* tie)
+// One boundary column: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k), the paths that ended
+// before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or beyond it (k >= xb: the
+// backward pass left the start cell's total in Bm[k]). A candidate that ties with the running minimum but names another (arrival
+// value, row) raises `tie`.
+struct FbPick { int T, v, y, tie; };
+PHMM_HD void fb_pick(FbPick& s, const int tot, const int cv, const int cy)
 {
-    const int sh = half * 16;
-    int T = 0x7fffffff, v = 0, y = 0, t = 0;
-    for (int k = 0; k < K; ++k) {
-        const int FM = (int)((fscr[(size_t)k * fstride] >> sh) & 0xFFFFu), BM = (int)((bscr[(size_t)k * bstride] >> sh) & 0xFFFFu);
-        int tot, cv, cy;
-        if (k < xb - L) { tot = FM; cv = FM; cy = L; }
-        else if (k >= xb) { tot = BM; cv = 0; cy = 0; }
-        else {
-            const int FD = (int)((fscr[(size_t)(K + k) * fstride] >> sh) & 0xFFFFu), BD = (int)((bscr[(size_t)(K + k) * bstride] >> sh) & 0xFFFFu);
-            cy = xb - k;
-            tot = FD + BD; cv = FD;
-            if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
-            else if (tot == T && (cv != v || cy != y)) t = 1;
-            tot = FM + BM; cv = FM;
+    if (tot < s.T) { s.T = tot; s.v = cv; s.y = cy; s.tie = 0; }
+    else if (tot == s.T && (cv != s.v || cy != s.y)) s.tie = 1;
+}
+PHMM_HD void fb_candidates(FbPick& s, const int k, const int xb, const int L, const int FM, const int FD, const int BM, const int BD)
+{
+    if (k < xb - L) fb_pick(s, FM, FM, L);
+    else if (k >= xb) fb_pick(s, BM, 0, 0);
+    else { fb_pick(s, FD + BD, FD, xb - k); fb_pick(s, FM + BM, FM, xb - k); }
+}
+// fscr / bscr: the slot's forward / backward arrays ({M, D} / {Bm, Bd}, K words each; written earlier by this very thread or by the
+// forward kernel: no __restrict__, the loads must stay coherent). The packed words hold both halves: when the lane's two alignments
+// share the boundary column (xb0 == xb1, the usual case) one sweep serves both; xb <= 0 = that half is not asked for. Loads are
+// issued eight diagonals at a time ahead of their use (a rolled one-diagonal loop waits for DRAM 2B times over).
+PHMM_HD void fb_decide(const uint32_t* fscr, const size_t fstride, const uint32_t* bscr, const size_t bstride, const int K,
+                       const int xb0, const int xb1, const int L, FbPick* out0, FbPick* out1)
+{
+    FbPick s0 {0x7fffffff, 0, 0, 0}, s1 {0x7fffffff, 0, 0, 0};
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t fm[8], fd[8], bm[8], bd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            fm[j] = fscr[(size_t)(k0 + j) * fstride]; fd[j] = fscr[(size_t)(K + k0 + j) * fstride];
+            bm[j] = bscr[(size_t)(k0 + j) * bstride]; bd[j] = bscr[(size_t)(K + k0 + j) * bstride];
         }
-        if (tot < T) { T = tot; v = cv; y = cy; t = 0; }
-        else if (tot == T && (cv != v || cy != y)) t = 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (xb0 > 0) fb_candidates(s0, k0 + j, xb0, L, (int)(fm[j] & 0xFFFFu), (int)(fd[j] & 0xFFFFu), (int)(bm[j] & 0xFFFFu), (int)(bd[j] & 0xFFFFu));
+            if (xb1 > 0) fb_candidates(s1, k0 + j, xb1, L, (int)(fm[j] >> 16), (int)(fd[j] >> 16), (int)(bm[j] >> 16), (int)(bd[j] >> 16));
+        }
     }
-    *total = T; *v_out = v; *y_out = y; *tie = t;
+    *out0 = s0; *out1 = s1;
 }
 
 // The crossing cells of both halves from the two passes' boundary columns → score, in-flank penalty, in-flank read bases, tie.
+// Up to four sweeps (side x half; one per side when the halves share the column), rolled so that fb_decide exists once in the code.
 PHMM_HD void fb_finish(const int K, const int L, const FbBounds& g, const uint32_t* fscr, const size_t fstride,
                        const uint32_t* bscr, const size_t bstride, FbResult* res0, FbResult* res1)
 {
+    FbPick l0 {0, 0, 0, 0}, l1 {0, 0, 0, 0}, r0 {0, 0, L, 0}, r1 {0, 0, L, 0};      // [side][half]: "no such flank" defaults
 #pragma unroll 1
+    for (int job = 0; job < 4; ++job) {
+        const int side = job >> 1, second = job & 1;
+        const int xa = fb_slot_column(g, side), xb = fb_slot_column(g, 2 + side);      // this side's column of the low / high half
+        const int ra = fb_slot_rep(g, side), rb = fb_slot_rep(g, 2 + side);
+        const bool shared = xa > 0 && xb > 0 && ra == rb;
+        int rep, q0, q1;
+        if (!second) { if (xa <= 0) continue; rep = ra; q0 = xa; q1 = shared ? xb : -1; }
+        else { if (xb <= 0 || shared) continue; rep = rb; q0 = -1; q1 = xb; }
+        FbPick o0, o1;
+        fb_decide(fscr + (size_t)(rep * 2) * K * fstride, fstride, bscr + (size_t)(rep * 2) * K * bstride, bstride, K, q0, q1, L, &o0, &o1);
+        if (q0 > 0) { if (side) r0 = o0; else l0 = o0; }
+        if (q1 > 0) { if (side) r1 = o1; else l1 = o1; }
+    }
+#pragma unroll
     for (int half = 0; half < 2; ++half) {
-        int T = 0, Tx[2] = {0, 0}, v[2] = {0, 0}, y[2] = {0, L}, t[2] = {0, 0};
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            const int slot = 2 * half + side, xb = fb_slot_column(g, slot);
-            if (xb > 0) {
-                int Ts, vs, ys, ts;
-                const int rep = fb_slot_rep(g, slot);
-                fb_decide(fscr + (size_t)(rep * 2) * K * fstride, fstride, bscr + (size_t)(rep * 2) * K * bstride, bstride, K, half, xb, L, &Ts, &vs, &ys, &ts);
-                if (side == 0) { Tx[0] = Ts; v[0] = vs; y[0] = ys; t[0] = ts; } else { Tx[1] = Ts; v[1] = vs; y[1] = ys; t[1] = ts; }
-                T = Ts;
-            }
-        }
         const int xl = fb_slot_column(g, 2 * half), xr = fb_slot_column(g, 2 * half + 1);
-        if (xr <= 0) v[1] = T;                  // no right flank inside the window: nothing beyond xr to discount
-        FbResult r;
-        r.score = T;
-        r.flank = v[0] + (T - v[1]);
-        r.mask = y[0] + (L - y[1]);
-        r.tie = t[0] | t[1] | ((xl > 0 && xr > 0 && Tx[0] != Tx[1]) ? 1 : 0);
-        if (half) *res1 = r; else *res0 = r;
+        const FbPick l = half ? l1 : l0, r = half ? r1 : r0;
+        const int T = xr > 0 ? r.T : l.T;
+        const int v_r = xr > 0 ? r.v : T;          // no right flank inside the window: nothing beyond xr to discount
+        FbResult o;
+        o.score = T;
+        o.flank = l.v + (T - v_r);
+        o.mask = l.y + (L - r.y);
+        o.tie = l.tie | r.tie | ((xl > 0 && xr > 0 && l.T != r.T) ? 1 : 0);
+        if (half) *res1 = o; else *res0 = o;
     }
 }
 

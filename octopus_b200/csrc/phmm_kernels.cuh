@@ -18,6 +18,8 @@ struct DevHaps {
     const long long* begin;     // may be null
     const ColEntry* tab_f;      // column tables, same indexing as seq
     const ColEntry* tab_r;
+    const uint32_t* npre_f;     // per-haplotype prefix counts of 'N'-like columns (flank_replay_may_differ_pre), or null
+    const uint32_t* npre_r;
 };
 struct DevReads {
     int n;
@@ -84,6 +86,28 @@ __global__ void k_build_tables(const long long n_bases, const char* __restrict__
     }
     tab_f[i] = make_col_entry(seq[i], mask_f[i], pf & 127, o & 127, e & 127);
     tab_r[i] = make_col_entry(seq[i], mask_r[i], pr & 127, o & 127, e & 127);
+}
+
+// One warp per (haplotype, strand): inclusive prefix counts of the 'N'-like columns of the strand's table (ncol_class), restarting at
+// every haplotype (lengths <= 65535: each half-word count fits).
+__global__ void k_ncol_prefix(const int H, const long long* __restrict__ off, const ColEntry* __restrict__ tab_f, const ColEntry* __restrict__ tab_r,
+                              uint32_t* __restrict__ pre_f, uint32_t* __restrict__ pre_r)
+{
+    const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int h = w >> 1;
+    if (h >= H) return;
+    const ColEntry* tab = (w & 1) ? tab_r : tab_f;
+    uint32_t* pre = (w & 1) ? pre_r : pre_f;
+    const long long end = off[h + 1];
+    uint32_t run = 0u;
+    const unsigned le = 0xffffffffu >> (31 - lane);
+    for (long long i0 = off[h]; i0 < end; i0 += 32) {
+        const long long i = i0 + lane;
+        const uint32_t cls = i < end ? ncol_class(tab[i].x) : 0u;
+        const unsigned b_lo = __ballot_sync(0xffffffffu, (cls & 1u) != 0u), b_hi = __ballot_sync(0xffffffffu, cls != 0u);
+        if (i < end) pre[i] = run + (uint32_t)__popc(b_lo & le) + ((uint32_t)__popc(b_hi & le) << 16);
+        run += (uint32_t)__popc(b_lo) + ((uint32_t)__popc(b_hi) << 16);
+    }
 }
 
 // What the host needs to know about a device-resident offset array: ends, longest and shortest item (the shortest as
@@ -1010,8 +1034,9 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
     constexpr int K = 2 * BAND;
     if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
-    const size_t bstride = (size_t)gridDim.x * blockDim.x;
-    uint32_t* bscr = thread_scratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // the backward arrays of this thread: lane-interleaved within the warp's own region (constant stride: immediate store offsets)
+    constexpr size_t bstride = 32;
+    uint32_t* bscr = thread_scratch + (size_t)(blockIdx.x * kFastWarpsPerBlock + warp) * fb_scratch_words(BAND) * 32 + lane;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     for (;;) {
         int li = 0;
@@ -1046,6 +1071,7 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
         for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
         const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
+        const uint32_t* npre = p.rd.reverse[r] ? p.hp.npre_r : p.hp.npre_f;
         const int W = L + K - 1;
         for (int c = 0; c < n; c += 64) {
             const int i0 = c + 2 * lane, i1 = i0 + 1;
@@ -1066,7 +1092,7 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
                 const FbResult f = half ? f1 : f0;
                 const int h = half ? h1 : h0, a = half ? a1 : a0;
                 // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
-                if (flank_replay_may_differ(half ? c1 : c0, W, half ? lhs1 : lhs0, half ? rhs1 : rhs0, low_quality)) push_slow(p, r, h, a);
+                if (flank_replay_may_differ_pre(npre + p.hp.off[h], a, W, half ? lhs1 : lhs0, half ? rhs1 : rhs0, low_quality)) push_slow(p, r, h, a);
                 else if (f.tie) {
                     const int slot = atomicAdd(p.gcnt + li, 1);
                     if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = half ? w1 : w0;

@@ -341,3 +341,25 @@ extern "C" int emul_dp_flank_fb(int band, int L, const char* read0, const uint8_
     out1[0] = r1.score; out1[1] = r1.flank; out1[2] = r1.mask; out1[3] = r1.tie;
     return 0;
 }
+
+// flank_replay_may_differ (loop over the flank columns) against flank_replay_may_differ_pre (per-haplotype prefix counts, as
+// k_ncol_prefix builds them) on one haplotype's table: returns the number of disagreements over all window placements tried.
+extern "C" int emul_replay_prefix_check(int hap_len, const char* truth, const char* mask, const int8_t* prior, const int8_t* go, const int8_t* ge,
+                                        int n_queries, const int* a, const int* W, const int* lhs, const int* rhs, const int* lowq)
+{
+    std::vector<ColEntry> t(hap_len);
+    std::vector<uint32_t> pre(hap_len);
+    uint32_t run = 0;
+    for (int x = 0; x < hap_len; ++x) {
+        t[x] = make_col_entry(truth[x], mask[x], prior[x], go[x], ge[x]);
+        run += ncol_class(t[x].x);
+        pre[x] = run;
+    }
+    int bad = 0;
+    for (int i = 0; i < n_queries; ++i) {
+        const bool want = flank_replay_may_differ(t.data() + a[i], W[i], lhs[i], rhs[i], lowq[i] != 0);
+        const bool got = flank_replay_may_differ_pre(pre.data(), a[i], W[i], lhs[i], rhs[i], lowq[i] != 0);
+        bad += want != got;
+    }
+    return bad;
+}

@@ -372,3 +372,28 @@ def test_forward_backward_flank_dp_matches_traceback_flank_replay(emul, coracle)
                 continue
             assert (o[1], o[2]) == (efs, ems), (band, L, lhs, rhs, tuple(o), (es, efs, ems))
     assert n_used == 3600 and n_tie < 0.04 * n_used and n_quirk < 20, (n_used, n_tie, n_quirk)
+
+
+def test_replay_quirk_test_from_prefix_counts_equals_the_column_scan(emul):
+    """flank_replay_may_differ_pre (four loads of per-haplotype prefix counts of 'N'-like table columns) == flank_replay_may_differ
+    (scan of the window's flank columns) for every window placement and flank geometry, N-rich haplotypes with SNV priors 0 / 1 / 2."""
+    emul.emul_replay_prefix_check.argtypes = [C.c_int] + [vp] * 5 + [C.c_int] + [vp] * 5
+    rng = np.random.default_rng(31)
+    n_true = 0
+    for it in range(60):
+        hap_len = int(rng.integers(40, 400))
+        truth = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, hap_len)].copy()
+        truth[rng.random(hap_len) < (0.0 if it % 4 == 0 else 0.03)] = ord("N")
+        mask = np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, hap_len)].copy()
+        prior = rng.choice([0, 1, 2, 3, 30, 125], hap_len).astype(np.int8)
+        go = rng.integers(3, 46, hap_len).astype(np.int8); ge = rng.integers(1, 11, hap_len).astype(np.int8)
+        nq = 400
+        W = rng.integers(1, hap_len + 1, nq).astype(np.int32)
+        a = (rng.random(nq) * (hap_len - W + 1)).astype(np.int32)
+        lhs = rng.integers(-5, W + 10).astype(np.int32); rhs = rng.integers(-5, W + 10).astype(np.int32)
+        lhs[::3] = 0; rhs[1::3] = 0
+        lowq = rng.integers(0, 2, nq).astype(np.int32)
+        # the kernels only pass non-negative flank sizes (window_flanks)
+        lhs = np.maximum(lhs, 0); rhs = np.maximum(rhs, 0)
+        bad = emul.emul_replay_prefix_check(hap_len, P(truth), P(mask), P(prior), P(go), P(ge), nq, P(a), P(W), P(lhs), P(rhs), P(lowq))
+        assert bad == 0, (it, bad)
