@@ -63,6 +63,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 __device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }                              // VIMNMX.S16x2
 __device__ __forceinline__ uint32_t vminu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }                             // VIMNMX.U16x2
+__device__ __forceinline__ uint32_t vmaxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }                             // VIMNMX.U16x2 (max)
 __device__ __forceinline__ uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }       // VIMNMX3.S16x2
 __device__ __forceinline__ uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }   // VIADDMNMX.S16x2: min(a+b, c)
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
@@ -89,6 +90,11 @@ inline uint32_t vminu2(uint32_t a, uint32_t b)
 {
     const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
     return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+}
+inline uint32_t vmaxu2(uint32_t a, uint32_t b)
+{
+    const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+    return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
 }
 inline uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -974,8 +980,14 @@ PHMM_HD void dp_flank_fwd(const RowEntry* __restrict__ rows, const int L, const 
 
 // Backward pass: cost-to-go over [be, W], columns downwards, diagonals upwards; at every boundary column (Bm, Bd) of the band go
 // to scr[((slot * 2 + {0, 1}) * 2B + k) * stride]. Independent of the deletion-update form (OGE).
+// The end row needs no special column body: rows[L .. L + 2B - 1] are pad entries (emission 0) and the band starts at 0, so every
+// "cell" on or below row L computes cost-to-go 0 in all three states from zeros (a = 0 + 0, Bd = min(0 + ge, 0), Bm = Bi =
+// min3(0, ..)) — exactly B(x, L) = 0, and the cells above it see the free end. The columns x >= L therefore run the plain steady
+// body (their sub-row cells are wasted work, about as much as the jump-table body they replace cost in extra instructions — but 1 000
+// instructions less code for the instruction cache). Band entries k > x keep the start cells' totals, entries k < x - L stay 0.
 template <int BAND>
-PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
+PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows /* rows[0 .. L-1] real, rows[L .. L + 2*BAND - 1] pad */, const int L,
+                          const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
                           const uint32_t nucp, const FbBounds g, uint32_t* __restrict__ scr, const size_t stride, const uint32_t one = 1u)
 {
     constexpr int K = 2 * BAND;
@@ -985,9 +997,9 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const 
     const RowEntry w0 = rows[0];
     uint32_t BM[K], BD[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) { BM[k] = kInf16x2; BD[k] = kInf16x2; }
+    for (int k = 0; k < K; ++k) { BM[k] = 0u; BD[k] = 0u; }
     ColEntry p0 = ldg(t0 + (W - 1)), p1 = ldg(t1 + (W - 1));      // entries of column x - 1
-    uint32_t caps0 = 0u, caps1 = 0u, go = 0u, ge = 0u;             // column x (column W holds the end cell only)
+    uint32_t caps0 = 0u, caps1 = 0u, go = 0u, ge = 0u;             // column x (column W: sub-row cells only, any penalties do)
     int next;
     PHMM_FB_NEXT_BELOW(W)
 #define PHMM_BKCELL(k)                                                                      \
@@ -1001,8 +1013,6 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const 
         BM[(k) < K ? (k) : 0] = vmin3(a, od, fma_add(i_run, gop, one));                     \
         i_run = vmin3(a, od, fma_add(i_run, gep, one));                                     \
     }
-#define PHMM_BCASE_ROWL(k)  case (k): if ((k) < K) { BM[(k) < K ? (k) : 0] = 0u; BD[(k) < K ? (k) : 0] = 0u; } break;
-#define PHMM_BCASE_EPI(k)   case (k) - 1: if ((k) >= 1 && (k) < K) PHMM_BKCELL(k)
 #define PHMM_BCASE_START(k) case (k): if ((k) < K) { const uint32_t a = fma_add(BM[(k) < K ? (k) : 0], sub0, one); BM[(k) < K ? (k) : 0] = (x & 1) ? vaddmin(i_run, gop, a) : a; } break;
     for (int x = W; x >= g.be; --x) {
         const int xp = x >= 2 ? x - 2 : 0;
@@ -1010,18 +1020,11 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const 
         const uint32_t go_p = prmt(p0.y, p1.y, 0x3430u), ge_p = prmt(p0.y, p1.y, 0x3531u);     // column x - 1
         const uint32_t gop = go_p + nucp, gep = ge_p + nucp;
         const RowEntry* rp = rows + x;
-        uint32_t i_run;
-        if (x >= L) {
-            const int klo = x - L;           // the end-row cell: cost-to-go 0 in every state
-            switch (klo) { PHMM_REP64A(PHMM_BCASE_ROWL) default: break; }
-            i_run = 0u;
-            switch (klo) { PHMM_REP64A(PHMM_BCASE_EPI) default: break; }
-        } else if (x >= K) {
-            i_run = kInf16x2;
+        uint32_t i_run = kInf16x2;           // nothing below diagonal 0
+        if (x >= K) {
 #pragma unroll
             for (int k = 0; k < K; ++k) PHMM_BKCELL(k)
         } else {
-            i_run = kInf16x2;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (k == x) break;
@@ -1039,53 +1042,61 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows, const int L, const 
         p0.x = n0.x + z; p0.y = n0.y + z; p1.x = n1.x + z; p1.y = n1.y + z;
     }
 #undef PHMM_BKCELL
-#undef PHMM_BCASE_ROWL
-#undef PHMM_BCASE_EPI
 #undef PHMM_BCASE_START
 }
 #undef PHMM_FB_NEXT_ABOVE
 #undef PHMM_FB_NEXT_BELOW
 #undef PHMM_FB_STORE
 
-// One boundary column: the candidates are the band's cells of column xb (arrival by M or D at row y = xb - k), the paths that ended
-// before the column (k < xb - L: the forward pass left S(L + k, L) in M[k]) and the paths that start at or beyond it (k >= xb: the
-// backward pass left the start cell's total in Bm[k]). A candidate that ties with the running minimum but names another (arrival
-// value, row) raises `tie`.
+// One boundary column, both halves of the packed words at once. The candidates of a half are, for every diagonal k, the arrival by M
+// and by D at cell (xb, y = xb - k): total F + B, in-flank value F, read row y. The band arrays make the three kinds of diagonal
+// uniform (no case distinction here):
+//   k < xb - L   the path ended before the column: the forward pass left S(L + k, L) in M[k] (and d(L + k, L) >= it in D[k]), the
+//                backward band is 0 there; y clamps to L
+//   k >= xb      the path starts at or beyond the column: forward M[k] is still 0 and D[k] +inf, the backward pass left the start
+//                cell's total in Bm[k]; y clamps to 0
+//   otherwise    a cell of the column.
+// Two sweeps over the 2B diagonals: the packed minimum T of all totals, then — over the candidates whose total equals T — the packed
+// minimum and maximum of their F values and rows: the minimisers agree on (F, y) iff min == max for both. fscr / bscr: the slot's
+// forward / backward arrays ({M, D} / {Bm, Bd}, K words each; written earlier by this very thread or by the forward kernel: no
+// __restrict__, the loads must stay coherent). xb0 / xb1: the column as the low / high half sees it (<= 0: that half is not asked
+// for; its lanes then hold another column's data and its result is ignored).
 struct FbPick { int T, v, y, tie; };
-PHMM_HD void fb_pick(FbPick& s, const int tot, const int cv, const int cy)
+PHMM_HD uint32_t fb_rows_of(const int xb0, const int xb1, const int k, const int L)
 {
-    if (tot < s.T) { s.T = tot; s.v = cv; s.y = cy; s.tie = 0; }
-    else if (tot == s.T && (cv != s.v || cy != s.y)) s.tie = 1;
+    int y0 = xb0 - k, y1 = xb1 - k;
+    y0 = y0 < 0 ? 0 : (y0 > L ? L : y0);
+    y1 = y1 < 0 ? 0 : (y1 > L ? L : y1);
+    return (uint32_t)y0 | ((uint32_t)y1 << 16);
 }
-PHMM_HD void fb_candidates(FbPick& s, const int k, const int xb, const int L, const int FM, const int FD, const int BM, const int BD)
-{
-    if (k < xb - L) fb_pick(s, FM, FM, L);
-    else if (k >= xb) fb_pick(s, BM, 0, 0);
-    else { fb_pick(s, FD + BD, FD, xb - k); fb_pick(s, FM + BM, FM, xb - k); }
-}
-// fscr / bscr: the slot's forward / backward arrays ({M, D} / {Bm, Bd}, K words each; written earlier by this very thread or by the
-// forward kernel: no __restrict__, the loads must stay coherent). The packed words hold both halves: when the lane's two alignments
-// share the boundary column (xb0 == xb1, the usual case) one sweep serves both; xb <= 0 = that half is not asked for. Loads are
-// issued eight diagonals at a time ahead of their use (a rolled one-diagonal loop waits for DRAM 2B times over).
 PHMM_HD void fb_decide(const uint32_t* fscr, const size_t fstride, const uint32_t* bscr, const size_t bstride, const int K,
                        const int xb0, const int xb1, const int L, FbPick* out0, FbPick* out1)
 {
-    FbPick s0 {0x7fffffff, 0, 0, 0}, s1 {0x7fffffff, 0, 0, 0};
-#pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += 8) {
-        uint32_t fm[8], fd[8], bm[8], bd[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            fm[j] = fscr[(size_t)(k0 + j) * fstride]; fd[j] = fscr[(size_t)(K + k0 + j) * fstride];
-            bm[j] = bscr[(size_t)(k0 + j) * bstride]; bd[j] = bscr[(size_t)(K + k0 + j) * bstride];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (xb0 > 0) fb_candidates(s0, k0 + j, xb0, L, (int)(fm[j] & 0xFFFFu), (int)(fd[j] & 0xFFFFu), (int)(bm[j] & 0xFFFFu), (int)(bd[j] & 0xFFFFu));
-            if (xb1 > 0) fb_candidates(s1, k0 + j, xb1, L, (int)(fm[j] >> 16), (int)(fd[j] >> 16), (int)(bm[j] >> 16), (int)(bd[j] >> 16));
-        }
+    uint32_t T = 0xFFFFFFFFu;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const uint32_t tm = fscr[(size_t)k * fstride] + bscr[(size_t)k * bstride];                  // < 0xE200 per half: no carry
+        const uint32_t td = fscr[(size_t)(K + k) * fstride] + bscr[(size_t)(K + k) * bstride];
+        T = vminu2(T, vminu2(tm, td));
     }
-    *out0 = s0; *out1 = s1;
+    const uint32_t ones = 0x00010001u;
+    uint32_t v_lo = 0xFFFFFFFFu, v_hi = 0u, y_lo = 0xFFFFFFFFu, y_hi = 0u;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const uint32_t fm = fscr[(size_t)k * fstride], fd = fscr[(size_t)(K + k) * fstride];
+        const uint32_t tm = fm + bscr[(size_t)k * bstride], td = fd + bscr[(size_t)(K + k) * bstride];
+        const uint32_t nm = vminu2(tm - T, ones), nd = vminu2(td - T, ones);     // per half: 0 = this candidate attains T, 1 = it does not
+        const uint32_t km = 0xFFFFFFFFu - nm * 0xFFFFu, kd = 0xFFFFFFFFu - nd * 0xFFFFu;            // per half: 0xFFFF / 0
+        v_lo = vminu2(v_lo, vminu2(fm + nm * 0x8000u, fd + nd * 0x8000u));      // F < 0x7200: a non-minimiser moves beyond every real value
+        v_hi = vmaxu2(v_hi, vmaxu2(fm & km, fd & kd));
+        const uint32_t yk = fb_rows_of(xb0, xb1, k, L), nk = vminu2(nm, nd);    // the row is shared by the diagonal's two candidates
+        y_lo = vminu2(y_lo, yk + nk * 0x8000u);
+        y_hi = vmaxu2(y_hi, yk & (0xFFFFFFFFu - nk * 0xFFFFu));
+    }
+    out0->T = (int)(T & 0xFFFFu); out0->v = (int)(v_lo & 0xFFFFu); out0->y = (int)(y_lo & 0xFFFFu);
+    out0->tie = ((v_lo ^ v_hi) & 0xFFFFu) != 0u || ((y_lo ^ y_hi) & 0xFFFFu) != 0u;
+    out1->T = (int)(T >> 16); out1->v = (int)(v_lo >> 16); out1->y = (int)(y_lo >> 16);
+    out1->tie = ((v_lo ^ v_hi) >> 16) != 0u || ((y_lo ^ y_hi) >> 16) != 0u;
 }
 
 // The crossing cells of both halves from the two passes' boundary columns → score, in-flank penalty, in-flank read bases, tie.

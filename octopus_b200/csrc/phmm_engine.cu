@@ -1101,24 +1101,29 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
         if (p.atasks && p.fb_route) {
             // the packed forward / backward flank kernels over the atasks lists; they run BEFORE k_populate_flank, which also resolves the
             // candidates they report as tied or could not place in the forward scratch (appended to the gtasks lists)
-            const size_t fbsmem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
-            // forward scratch: one round (64 candidates) per fb_round_words; worst case = every list slot's full task list, capped at 4 GiB
-            const long long rounds_worst = (long long)n_entries * ((p.fcap + 63) / 64);
+            // lane groups: a read's candidates (about one per haplotype) should fill its group's 2 * LG half-lanes; rows must fit 4 blocks / SM
+            const int fb_stride = (row_stride + 2 * band + 1) & ~1;                  // + the backward pass's pad rows
+            int lg = 5;
+            while (lg > 2 && (1 << lg) >= H && (size_t)kFastWarpsPerBlock * (32 >> (lg - 1)) * fb_stride * sizeof(RowEntry) <= (48u << 10)) --lg;
+            const int fbG = 32 >> lg;
+            const size_t fbsmem = (size_t)kFastWarpsPerBlock * fbG * fb_stride * sizeof(RowEntry);
+            // forward scratch: one warp-round (64 candidates) per fb_round_words; worst case = every claim's longest task list, capped at 4 GiB
+            const long long rounds_worst = ((long long)n_entries / fbG + 1) * ((p.fcap + (2 << lg) - 1) >> (lg + 1));
             int fb_blocks = 1, frc2;
 #define PHMM_FB_LAUNCH(B) \
             { if ((frc2 = fast_smem_attr(e, k_flank_fwd<B>, fbsmem)) || (frc2 = fast_smem_attr(e, k_flank_bwd<B>, fbsmem)) || \
                   (frc2 = blocks_per_sm_of(e, k_flank_bwd<B>, kFastWarpsPerBlock * 32, fbsmem, &fb_blocks))) return frc2; \
               if (fb_blocks < 1) { e->err = "flank kernel does not fit on an SM (read too long?)"; return PHMM_ERR_INVALID; } \
-              const unsigned bgrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * fb_blocks)); \
+              const unsigned bgrid = (unsigned)std::max(1, std::min((n_entries / fbG + kFastWarpsPerBlock) / kFastWarpsPerBlock, e->sm_count * fb_blocks)); \
               const size_t round_bytes = fb_round_words(B) * sizeof(uint32_t); \
               const long long cap = std::max<long long>(1, std::min<long long>(rounds_worst, (long long)((4ull << 30) / round_bytes))); \
               cudaError_t ce = e->fb_pairs.ensure((size_t)cap * round_bytes); \
               if (ce == cudaSuccess) ce = e->fb_scratch.ensure((size_t)bgrid * kFastWarpsPerBlock * 32 * fb_scratch_words(B) * sizeof(uint32_t)); \
               if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return PHMM_ERR_NOMEM; } \
               p.fb_round_cap = (int)std::min<long long>(0x7fffffff, (long long)(e->fb_pairs.cap / round_bytes)); \
-              k_flank_fwd<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_pairs.as<uint32_t>()); \
+              k_flank_fwd<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_pairs.as<uint32_t>(), fb_stride, lg); \
               LAUNCHED(); \
-              k_flank_bwd<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_pairs.as<uint32_t>(), e->fb_scratch.as<uint32_t>()); }
+              k_flank_bwd<B><<<bgrid, kFastWarpsPerBlock * 32, fbsmem, e->stream>>>(p, e->fb_pairs.as<uint32_t>(), e->fb_scratch.as<uint32_t>(), fb_stride, lg); }
             if (band == 8) PHMM_FB_LAUNCH(8) else PHMM_FB_LAUNCH(16)
 #undef PHMM_FB_LAUNCH
             LAUNCHED();

@@ -956,68 +956,88 @@ constexpr int kFlankFbMaxBand = 16;     // widest band served by k_flank_fwd / k
 // words of one round's forward arrays: 64 candidates = 32 lanes x (4 boundary slots x {M, D} x 2B diagonals), lane-interleaved
 __host__ __device__ constexpr size_t fb_round_words(const int band) { return (size_t)kFbSlots * 2 * 2 * (size_t)band * 32; }
 
-// The packed forward / backward flank kernels (dp_flank_fwd / dp_flank_bwd): one READ per warp — both packed halves carry the same
-// read, so a lane works on TWO of the read's near-flank candidates (two haplotype windows) at once, 64 per round. Two launches over the
-// same atasks lists with the same (list slot, round, lane, half) → candidate mapping:
+// The packed forward / backward flank kernels (dp_flank_fwd / dp_flank_bwd). Both packed halves carry the SAME read, so a lane works
+// on TWO of a read's near-flank candidates (two haplotype windows) at once. A warp is cut into G = 32 >> lg lane groups of LG = 1 << lg
+// lanes; a group owns one read (list slot) at a time — its row entries in its own shared-memory region — and handles 2 * LG of the
+// read's candidates per round: the host picks lg from the haplotype count so that regions with few haplotypes still fill the lanes
+// (the fast kernel's G, for the same reason). Two launches over the same atasks lists with the same (list slot, round, lane, half)
+// → candidate mapping:
 //   k_flank_fwd  forward pass up to the last flank boundary of the lane's two windows; the band's arrivals at the boundary columns go
-//                to `pair_scratch` (fb_round_words(BAND) words per round, handed out by an atomic counter; a read that finds no room
-//                is marked and k_flank_bwd sends its candidates to the labelled DP);
+//                to `pair_scratch` (fb_round_words(BAND) words per warp-round, handed out by an atomic counter; reads that find no
+//                room are marked and k_flank_bwd sends their candidates to the labelled DP);
 //   k_flank_bwd  backward pass from the window end down to the first boundary, crossing cells from F + B (fb_finish), flank discount,
 //                minimum into best[]. A candidate whose co-optimal paths cross a boundary at different cells (FbResult::tie, ~1 %) is
 //                appended to the read's gtasks list: k_populate_flank, launched after these two, resolves it with the labelled DP.
 // (One fused kernel measured 0.9 x the labelled kernel: its code overflows the instruction cache, profiles/r02n.)
+struct FbClaim { int li, r, n, L, rounds, base; };
+// A warp claims G consecutive list slots; every lane learns its group's slot, read, candidate count and the warp's round count.
+__device__ __forceinline__ FbClaim fb_claim(const PopParams& p, int* cursor, const int n_list, const int lane, const int lg)
+{
+    const int G = 32 >> lg;
+    int li0 = 0;
+    if (lane == 0) li0 = atomicAdd(cursor, G);
+    li0 = __shfl_sync(0xffffffffu, li0, 0);
+    FbClaim c;
+    c.li = li0 + (lane >> lg);
+    if (li0 >= n_list) { c.li = -1; c.r = -1; c.n = 0; c.L = 0; c.rounds = -1; c.base = -1; return c; }
+    c.r = c.li < n_list ? p.list[c.li] : -1;
+    c.n = c.r >= 0 ? p.acnt[c.li] : 0;
+    c.L = c.n > 0 ? p.rd.info[c.r].x : 0;
+    int rounds = (c.n + (2 << lg) - 1) >> (lg + 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+    c.rounds = rounds; c.base = -1;
+    return c;
+}
+
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
-k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch)
+k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch, const int row_stride, const int lg)
 {
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int LG = 1 << lg, gl = lane & (LG - 1);
+    RowEntry* rows = smem_rows + (size_t)(warp * (32 >> lg) + (lane >> lg)) * row_stride;
     constexpr int K = 2 * BAND;
     if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     const bool oge = open_ge_extend(p.flags);
     for (;;) {
-        int li = 0;
-        if (lane == 0) li = atomicAdd(p.acc_cursor, 1);
-        li = __shfl_sync(0xffffffffu, li, 0);
-        if (li >= n_list) break;
-        const int r = p.list[li];
-        const int n = r >= 0 ? p.acnt[li] : 0;
-        if (n == 0) continue;
-        const int rounds = (n + 63) >> 6;
-        int base = 0;
+        FbClaim cl = fb_claim(p, p.acc_cursor, n_list, lane, lg);
+        if (cl.rounds < 0) break;
+        if (cl.rounds == 0) continue;
         if (lane == 0) {
-            base = atomicAdd(p.fb_rounds, rounds);
-            if (base + rounds > p.fb_round_cap) base = -1;
-            p.fb_round_base[li] = base;
+            cl.base = atomicAdd(p.fb_rounds, cl.rounds);
+            if (cl.base + cl.rounds > p.fb_round_cap) cl.base = -1;
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base < 0) continue;                               // no scratch left: k_flank_bwd hands the read's candidates to the labelled DP
-        const int L = p.rd.info[r].x;
-        const RegionInfo reg = p.regs[p.rd.region[r]];
+        cl.base = __shfl_sync(0xffffffffu, cl.base, 0);
+        if (gl == 0 && cl.li < n_list) p.fb_round_base[cl.li] = cl.base;
+        if (cl.base < 0) continue;                            // no scratch left: k_flank_bwd hands these reads' candidates to the labelled DP
+        const int L = cl.L, n = cl.n, r = cl.r;
         __syncwarp();
-        {
+        if (n > 0) {
             const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
-            for (int y = lane; y < L; y += 32) { const uint32_t half = hr[y]; rows[y] = make_row_entry(half, half); }
-            if (lane == 0) rows[L] = pad_row_entry();
-            __syncwarp();
+            for (int y = gl; y < L; y += LG) { const uint32_t half = hr[y]; rows[y] = make_row_entry(half, half); }
+            if (gl == 0) rows[L] = pad_row_entry();
         }
+        __syncwarp();
+        if (n == 0) continue;       // (no warp-level operation below: a group without candidates just waits for the next claim)
+        const RegionInfo reg = p.regs[p.rd.region[r]];
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
-        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
+        const uint32_t* q = p.atasks + (size_t)cl.li * p.fcap;
         const int W = L + K - 1;
-        for (int c = 0; c < n; c += 64) {
-            const int i0 = c + 2 * lane, i1 = i0 + 1;
-            const bool v0 = i0 < n, v1 = i1 < n;
-            const uint32_t w0 = q[v0 ? i0 : 0], w1 = v1 ? q[i1] : w0;        // idle halves replay a valid task (result discarded)
+        for (int c = 0; c < cl.rounds; ++c) {
+            const int i0 = (c << (lg + 1)) + 2 * gl, i1 = i0 + 1;
+            if (i0 >= n) continue;
+            const uint32_t w0 = q[i0], w1 = i1 < n ? q[i1] : w0;             // an odd last candidate is replayed in the idle half (result discarded)
             const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
             int lhs0, rhs0, lhs1, rhs1;
             window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
             window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
             const FbBounds g = fb_bounds(lhs0, W - rhs0, lhs1, W - rhs1, W);
             const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
-            uint32_t* fscr = pair_scratch + (size_t)(base + (c >> 6)) * fb_round_words(BAND) + lane;
+            uint32_t* fscr = pair_scratch + (size_t)(cl.base + c) * fb_round_words(BAND) + lane;
             if (oge) dp_flank_fwd<BAND, true>(rows, L, c0, c1, nucp, g, fscr, 32, (uint32_t)p.one);
             else dp_flank_fwd<BAND, false>(rows, L, c0, c1, nucp, g, fscr, 32, (uint32_t)p.one);
         }
@@ -1026,11 +1046,12 @@ k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch)
 
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
-k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restrict__ thread_scratch)
+k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restrict__ thread_scratch, const int row_stride, const int lg)
 {
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int LG = 1 << lg, gl = lane & (LG - 1);
+    RowEntry* rows = smem_rows + (size_t)(warp * (32 >> lg) + (lane >> lg)) * row_stride;
     constexpr int K = 2 * BAND;
     if (*p.any_acc_tasks == 0 || on_reserved_sm(p)) return;
     const int n_list = tile_list(p);
@@ -1039,44 +1060,42 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
     uint32_t* bscr = thread_scratch + (size_t)(blockIdx.x * kFastWarpsPerBlock + warp) * fb_scratch_words(BAND) * 32 + lane;
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     for (;;) {
-        int li = 0;
-        if (lane == 0) li = atomicAdd(p.fb_cursor, 1);
-        li = __shfl_sync(0xffffffffu, li, 0);
-        if (li >= n_list) break;
-        const int r = p.list[li];
-        const int n = r >= 0 ? p.acnt[li] : 0;
-        if (n == 0) continue;
-        const uint32_t* q = p.atasks + (size_t)li * p.fcap;
-        const int base = p.fb_round_base[li];
-        if (base < 0) {                                       // the forward kernel found no scratch for this read: labelled DP for all its candidates
-            for (int i = lane; i < n; i += 32) {
-                const int slot = atomicAdd(p.gcnt + li, 1);
-                if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = q[i];
+        FbClaim cl = fb_claim(p, p.fb_cursor, n_list, lane, lg);
+        if (cl.rounds < 0) break;
+        if (cl.rounds == 0) continue;
+        const int L = cl.L, n = cl.n, r = cl.r;
+        const uint32_t* q = p.atasks + (size_t)max(cl.li, 0) * p.fcap;
+        int base = cl.li < n_list ? p.fb_round_base[cl.li] : 0;
+        base = __shfl_sync(0xffffffffu, base, 0);             // one value per claim (lane 0's slot always exists)
+        if (base < 0) {                                       // the forward kernel found no scratch for this claim: labelled DP for all its candidates
+            for (int i = gl; i < n; i += LG) {
+                const int slot = atomicAdd(p.gcnt + cl.li, 1);
+                if (slot < p.fcap) p.gtasks[(size_t)cl.li * p.fcap + slot] = q[i];
                 else atomicOr(p.flags, 8);
             }
-            if (lane == 0) *p.any_flank_tasks = 1;
+            if (n > 0) *p.any_flank_tasks = 1;
             continue;
         }
-        const int L = p.rd.info[r].x;
-        const RegionInfo reg = p.regs[p.rd.region[r]];
         __syncwarp();
         unsigned qmin = 255u;
-        {
+        if (n > 0) {
             const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
-            for (int y = lane; y < L; y += 32) { const uint32_t half = hr[y]; rows[y] = make_row_entry(half, half); qmin = min(qmin, half >> 8); }
-            if (lane == 0) rows[L] = pad_row_entry();
-            __syncwarp();
+            for (int y = gl; y < L; y += LG) { const uint32_t half = hr[y]; rows[y] = make_row_entry(half, half); qmin = min(qmin, half >> 8); }
+            for (int y = L + gl; y < L + K; y += LG) rows[y] = pad_row_entry();     // the backward pass reads pad rows down to L + 2B - 1
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        __syncwarp();
+        for (int o = LG >> 1; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        if (n == 0) continue;       // (no warp-level operation below)
         const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
+        const RegionInfo reg = p.regs[p.rd.region[r]];
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
         const uint32_t* npre = p.rd.reverse[r] ? p.hp.npre_r : p.hp.npre_f;
         const int W = L + K - 1;
-        for (int c = 0; c < n; c += 64) {
-            const int i0 = c + 2 * lane, i1 = i0 + 1;
-            const bool v0 = i0 < n, v1 = i1 < n;
-            const uint32_t w0 = q[v0 ? i0 : 0], w1 = v1 ? q[i1] : w0;        // the forward kernel's mapping, exactly
+        for (int c = 0; c < cl.rounds; ++c) {
+            const int i0 = (c << (lg + 1)) + 2 * gl, i1 = i0 + 1;
+            if (i0 >= n) continue;
+            const bool v1 = i1 < n;
+            const uint32_t w0 = q[i0], w1 = v1 ? q[i1] : w0;                 // the forward kernel's mapping, exactly
             const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
             int lhs0, rhs0, lhs1, rhs1;
             window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
@@ -1085,17 +1104,17 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
             const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
             dp_flank_bwd<BAND>(rows, L, c0, c1, nucp, g, bscr, bstride, (uint32_t)p.one);
             FbResult f0, f1;
-            fb_finish(K, L, g, pair_scratch + (size_t)(base + (c >> 6)) * fb_round_words(BAND) + lane, 32, bscr, bstride, &f0, &f1);
+            fb_finish(K, L, g, pair_scratch + (size_t)(base + c) * fb_round_words(BAND) + lane, 32, bscr, bstride, &f0, &f1);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                if (!(half ? v1 : v0)) continue;
+                if (half && !v1) continue;
                 const FbResult f = half ? f1 : f0;
                 const int h = half ? h1 : h0, a = half ? a1 : a0;
                 // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
                 if (flank_replay_may_differ_pre(npre + p.hp.off[h], a, W, half ? lhs1 : lhs0, half ? rhs1 : rhs0, low_quality)) push_slow(p, r, h, a);
                 else if (f.tie) {
-                    const int slot = atomicAdd(p.gcnt + li, 1);
-                    if (slot < p.fcap) p.gtasks[(size_t)li * p.fcap + slot] = half ? w1 : w0;
+                    const int slot = atomicAdd(p.gcnt + cl.li, 1);
+                    if (slot < p.fcap) p.gtasks[(size_t)cl.li * p.fcap + slot] = half ? w1 : w0;
                     else atomicOr(p.flags, 8);
                     *p.any_flank_tasks = 1;
                 } else atomicMin(p.best + pair_slot(p.rd, h, r), discount_flank(f.score, f.flank, L, f.mask, 0));

@@ -311,7 +311,7 @@ extern "C" int emul_dp_flank_fb(int band, int L, const char* read0, const uint8_
     if (L < 2 * band) return 1;
     if (W - rhs0 <= lhs0 || W - rhs1 <= lhs1) return 1;
     if ((lhs0 == 0 && rhs0 == 0) || (lhs1 == 0 && rhs1 == 0)) return 1;
-    std::vector<RowEntry> rows(L + 1);
+    std::vector<RowEntry> rows(L + 2 * band, pad_row_entry());       // the backward pass reads pad rows down to L + 2*band - 1
     for (int y = 0; y < L; ++y) {
         const int c0 = base_code(read0[y]), c1 = base_code(read1[y]);
         if (c0 < 0 || c1 < 0 || c0 > 3 || c1 > 3) return -1;

@@ -1,4 +1,4 @@
-"""The packed forward / backward flank kernel (k_populate_flank_fb → dp_flank_fb) against the oracle's populate with a flank state:
+"""The packed forward / backward flank kernels (k_flank_fwd + k_flank_bwd → dp_flank_fwd / dp_flank_bwd / fb_finish) against the oracle's populate with a flank state:
 the path hmm::evaluate takes for every candidate near a haplotype flank (pair_hmm.hpp:743-764: traceback DP + calculate_flank_score).
 Shapes chosen so that the kernel's own corners are hit: both flanks inside one window, boundaries inside the first / last 2B columns,
 co-optimal paths that cross a boundary at different cells (repeat-rich haplotypes: the kernel hands those to the labelled DP),
@@ -97,3 +97,31 @@ def test_flank_state_with_mapped_candidate_positions(engine, coracle):
     haps, reads = _repeat_region(rng, hap_len=300, n_haps=16, n_reads=200, read_lens=[60, 100, 150], band=16)
     for flanks in ((70, 80), (150, 40)):
         _compare(engine, coracle, 16, haps, reads, flanks, mapit=True, dp_only=False)
+
+
+@pytest.mark.parametrize("band_req", [8, 16])
+def test_flank_state_over_many_regions_with_few_haplotypes(engine, coracle, band_req):
+    """The call shape Octopus really has (one small region after the other, a handful of haplotypes each): phmm_populate_regions cuts a
+    warp of the flank kernels into lane groups, each with its own read (different lengths, regions and flank states in one warp)."""
+    from octopus_b200 import HaplotypeLikelihoodModel
+    from octopus_b200.batch import concat_blocks
+    from helpers import random_region
+    rng = np.random.default_rng(990 + band_req)
+    hap_blocks, read_blocks, flanks = [], [], []
+    for g in range(14):
+        h, r = random_region(rng, band_req, n_haps=int(rng.choice([1, 2, 3, 5, 8])), n_reads=int(rng.integers(3, 60)),
+                             hap_len=2 * band_req + int(rng.choice([180, 240, 300])), read_len_choices=[2 * band_req, 50, 76, 101, 150],
+                             read_n_rate=0.03, edge_reads=(g % 2 == 0))
+        hap_blocks.append(h); read_blocks.append(r)
+        flanks.append((int(rng.integers(0, 100)), int(rng.integers(0, 100))) if g % 4 else None)
+    haps, reads, hf, rf = concat_blocks(hap_blocks, read_blocks)
+    for mapit, dp_only in ((False, True), (True, False)):
+        cfg = HaplotypeLikelihoodModel.Config(max_indel_error=band_req, use_mapping_quality=False, disable_naive_shortcut=dp_only, map_positions=mapit)
+        flat, off, st = engine.populate_regions(cfg, haps, reads, hf, rf, flank_states=flanks, want_status=True)
+        mats = engine.split_regions(flat, off, hf, rf)
+        sts = engine.split_regions(st, off, hf, rf)
+        for g, (h, r) in enumerate(zip(hap_blocks, read_blocks)):
+            rc, want, wst = coracle.populate(band_req, h, r, None, flanks[g], use_mapping_quality=False, dp_only=dp_only, map_positions=mapit)
+            ok = wst == 0
+            assert np.array_equal(sts[g][~ok], wst[~ok]), (band_req, g)
+            assert np.array_equal(mats[g][ok], want[ok]), (band_req, mapit, g)
