@@ -866,31 +866,55 @@ PHMM_HD size_t fb_scratch_words(const int band) { return (size_t)kFbSlots * 2 * 
 PHMM_HD bool fb_boundary_valid(const int b, const int W) { return b >= 1 && b <= W - 1; }
 
 struct FbResult { int score, flank, mask, tie; };
-// c[s]: boundary column of slot s, or -1; the forward pass covers the columns [0, fe), the backward pass [be, W]
-struct FbBounds { int c0, c1, c2, c3, fe, be; };
+// The four boundary columns of a lane's two alignments, two per word (16 bits each, 0 = no such boundary: a valid column is >= 1) —
+// the passes keep them in two registers next to the band. The forward pass covers the columns [0, fb_fwd_end), the backward pass
+// [fb_bwd_end, W].
+struct FbBounds { uint32_t lo, hi; };          // lo = xl | xr << 16 of the low half's alignment, hi = of the high half's
 PHMM_HD FbBounds fb_bounds(const int b0, const int b1, const int b2, const int b3, const int W)
 {
     FbBounds g;
-    g.c0 = fb_boundary_valid(b0, W) ? b0 : -1; g.c1 = fb_boundary_valid(b1, W) ? b1 : -1;
-    g.c2 = fb_boundary_valid(b2, W) ? b2 : -1; g.c3 = fb_boundary_valid(b3, W) ? b3 : -1;
-    int fe = g.c0 > g.c1 ? g.c0 : g.c1; { const int m2 = g.c2 > g.c3 ? g.c2 : g.c3; if (m2 > fe) fe = m2; }
-    int be = 0x7fffffff;
-    if (g.c0 > 0 && g.c0 < be) be = g.c0;
-    if (g.c1 > 0 && g.c1 < be) be = g.c1;
-    if (g.c2 > 0 && g.c2 < be) be = g.c2;
-    if (g.c3 > 0 && g.c3 < be) be = g.c3;
-    g.fe = fe; g.be = be;
+    g.lo = (fb_boundary_valid(b0, W) ? (uint32_t)b0 : 0u) | ((fb_boundary_valid(b1, W) ? (uint32_t)b1 : 0u) << 16);
+    g.hi = (fb_boundary_valid(b2, W) ? (uint32_t)b2 : 0u) | ((fb_boundary_valid(b3, W) ? (uint32_t)b3 : 0u) << 16);
     return g;
 }
-PHMM_HD int fb_slot_column(const FbBounds& g, const int s) { return s == 0 ? g.c0 : s == 1 ? g.c1 : s == 2 ? g.c2 : g.c3; }
+PHMM_HD int fb_slot_column(const FbBounds& g, const int s) { const uint32_t w = s < 2 ? g.lo : g.hi; return (int)((s & 1) ? w >> 16 : w & 0xFFFFu); }
+PHMM_HD int fb_fwd_end(const FbBounds& g)      // 0: nothing to do
+{
+    int e = fb_slot_column(g, 0);
+#pragma unroll
+    for (int s = 1; s < 4; ++s) { const int c = fb_slot_column(g, s); e = c > e ? c : e; }
+    return e;
+}
+PHMM_HD int fb_bwd_end(const FbBounds& g)      // 0x7fffffff: nothing to do
+{
+    int e = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { const int c = fb_slot_column(g, s); if (c > 0 && c < e) e = c; }
+    return e;
+}
+// the next boundary column above / below v (0x7fffffff / 0: none)
+PHMM_HD int fb_next_above(const FbBounds& g, const int v)
+{
+    int n = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { const int c = fb_slot_column(g, s); if (c > v && c < n) n = c; }
+    return n;
+}
+PHMM_HD int fb_next_below(const FbBounds& g, const int v)
+{
+    int n = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { const int c = fb_slot_column(g, s); if (c < v && c > n) n = c; }
+    return n;
+}
 // Slots that name the same column share one copy of the band (the packed words hold both halves anyway): the representative of
 // slot s is the first slot with its column — the usual case is ONE stored column for a lane's two alignments.
 PHMM_HD int fb_slot_rep(const FbBounds& g, const int s)
 {
     const int c = fb_slot_column(g, s);
-    if (s >= 1 && g.c0 == c) return 0;
-    if (s >= 2 && g.c1 == c) return 1;
-    if (s >= 3 && g.c2 == c) return 2;
+    if (s >= 1 && fb_slot_column(g, 0) == c) return 0;
+    if (s >= 2 && fb_slot_column(g, 1) == c) return 1;
+    if (s >= 3 && fb_slot_column(g, 2) == c) return 2;
     return s;
 }
 
@@ -904,22 +928,24 @@ PHMM_HD void fb_store(uint32_t* __restrict__ dst, const size_t stride, const uin
 #define PHMM_FB_STORE(A0, A1)                                                                           \
     {                                                                                                   \
         _Pragma("unroll 1") for (int s_ = 0; s_ < kFbSlots; ++s_)                                       \
-            if (fb_slot_column(g, s_) == next && fb_slot_rep(g, s_) == s_) fb_store<K>(scr + (size_t)(s_ * 2) * K * stride, stride, A0, A1); \
+            if (fb_slot_column(g, s_) == next && fb_slot_rep(g, s_) == s_) fb_store<K>(scr_fn() + (size_t)(s_ * 2) * K * stride, stride, A0, A1); \
     }
-#define PHMM_FB_NEXT_ABOVE(v) { int n_ = 0x7fffffff; if (g.c0 > (v) && g.c0 < n_) n_ = g.c0; if (g.c1 > (v) && g.c1 < n_) n_ = g.c1; if (g.c2 > (v) && g.c2 < n_) n_ = g.c2; if (g.c3 > (v) && g.c3 < n_) n_ = g.c3; next = n_; }
-#define PHMM_FB_NEXT_BELOW(v) { int n_ = -1; if (g.c0 < (v) && g.c0 > n_) n_ = g.c0; if (g.c1 < (v) && g.c1 > n_) n_ = g.c1; if (g.c2 < (v) && g.c2 > n_) n_ = g.c2; if (g.c3 < (v) && g.c3 > n_) n_ = g.c3; next = n_; }
+#define PHMM_FB_NEXT_ABOVE(v) { next = fb_next_above(g, (v)); }
+#define PHMM_FB_NEXT_BELOW(v) { next = fb_next_below(g, (v)); }
 
 // Forward pass: dp_pair's column sweep over [0, fe); at every boundary column the arrivals (M, D) of the band go to
 // scr[((slot * 2 + {0, 1}) * 2B + k) * stride].
-template <int BAND, bool OGE>
+// scr_fn() returns the scratch pointer; it is called at the boundary columns only, so that a pointer the caller can re-derive from
+// its indices does not occupy two registers through the sweep.
+template <int BAND, bool OGE, class ScrFn>
 PHMM_HD void dp_flank_fwd(const RowEntry* __restrict__ rows, const int L, const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
-                          const uint32_t nucp, const FbBounds g, uint32_t* __restrict__ scr, const size_t stride, const uint32_t one = 1u)
+                          const uint32_t nucp, const FbBounds g, ScrFn scr_fn, const size_t stride, const uint32_t one = 1u)
 {
     constexpr int K = 2 * BAND;
     static_assert(K <= 64, "register band limited to 64 diagonals");
     const int W = L + K - 1;
-    if (g.fe <= 0) return;
-    const RowEntry w0 = rows[0];
+    const int fe = fb_fwd_end(g);
+    if (fe <= 0) return;
     uint32_t M[K], D[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { M[k] = 0u; D[k] = kInf16x2; }
@@ -939,7 +965,7 @@ PHMM_HD void dp_flank_fwd(const RowEntry* __restrict__ rows, const int L, const 
     }
 #define PHMM_CASE_PROLOGUE(k) case (k) + 1: if ((k) < K) PHMM_CELL(k)
 #define PHMM_CASE_ROW0(k)     case (k): if ((k) < K) M[(k) < K ? (k) : 0] = sub0; break;
-    for (int x = 0; x < g.fe; ++x) {
+    for (int x = 0; x < fe; ++x) {
         const int xn = (x + 1 < W) ? x + 1 : W - 1;
         const ColEntry n0 = ldg(t0 + xn), n1 = ldg(t1 + xn);
         const uint32_t caps0 = e0.x, caps1 = e1.x;
@@ -960,6 +986,7 @@ PHMM_HD void dp_flank_fwd(const RowEntry* __restrict__ rows, const int L, const 
                 }
             }
         } else {
+            const RowEntry w0 = rows[0];     // (loaded here, not kept in registers through the steady columns)
             const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));
             i_run = (x & 1) ? gop : kInf16x2;
             switch (x) { PHMM_REP64(PHMM_CASE_PROLOGUE) default: break; }
@@ -985,20 +1012,23 @@ PHMM_HD void dp_flank_fwd(const RowEntry* __restrict__ rows, const int L, const 
 // min3(0, ..)) — exactly B(x, L) = 0, and the cells above it see the free end. The columns x >= L therefore run the plain steady
 // body (their sub-row cells are wasted work, about as much as the jump-table body they replace cost in extra instructions — but 1 000
 // instructions less code for the instruction cache). Band entries k > x keep the start cells' totals, entries k < x - L stay 0.
-template <int BAND>
+template <int BAND, class ScrFn>
 PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows /* rows[0 .. L-1] real, rows[L .. L + 2*BAND - 1] pad */, const int L,
                           const ColEntry* __restrict__ t0, const ColEntry* __restrict__ t1,
-                          const uint32_t nucp, const FbBounds g, uint32_t* __restrict__ scr, const size_t stride, const uint32_t one = 1u)
+                          const uint32_t nucp, const FbBounds g, ScrFn scr_fn, const size_t stride, const uint32_t one = 1u)
 {
     constexpr int K = 2 * BAND;
     static_assert(K <= 64, "register band limited to 64 diagonals");
     const int W = L + K - 1;
-    if (g.be == 0x7fffffff) return;
-    const RowEntry w0 = rows[0];
+    const int be = fb_bwd_end(g);
+    if (be == 0x7fffffff) return;
     uint32_t BM[K], BD[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { BM[k] = 0u; BD[k] = 0u; }
-    ColEntry p0 = ldg(t0 + (W - 1)), p1 = ldg(t1 + (W - 1));      // entries of column x - 1
+    // Column operands, held as in the forward pass (6 registers + 4 loads in flight): caps / go / ge of column x, the penalty words of
+    // column x - 1 (they make this column's insertion penalties and the next column's go / ge); each column issues the loads of the
+    // next column's caps (column x - 1) and of the penalty words after it (column x - 2).
+    uint32_t py0 = ldg(&t0[W - 1].y), py1 = ldg(&t1[W - 1].y);
     uint32_t caps0 = 0u, caps1 = 0u, go = 0u, ge = 0u;             // column x (column W: sub-row cells only, any penalties do)
     int next;
     PHMM_FB_NEXT_BELOW(W)
@@ -1014,11 +1044,10 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows /* rows[0 .. L-1] re
         i_run = vmin3(a, od, fma_add(i_run, gep, one));                                     \
     }
 #define PHMM_BCASE_START(k) case (k): if ((k) < K) { const uint32_t a = fma_add(BM[(k) < K ? (k) : 0], sub0, one); BM[(k) < K ? (k) : 0] = (x & 1) ? vaddmin(i_run, gop, a) : a; } break;
-    for (int x = W; x >= g.be; --x) {
-        const int xp = x >= 2 ? x - 2 : 0;
-        const ColEntry n0 = ldg(t0 + xp), n1 = ldg(t1 + xp);
-        const uint32_t go_p = prmt(p0.y, p1.y, 0x3430u), ge_p = prmt(p0.y, p1.y, 0x3531u);     // column x - 1
-        const uint32_t gop = go_p + nucp, gep = ge_p + nucp;
+    for (int x = W; x >= be; --x) {
+        const int x1 = x >= 1 ? x - 1 : 0, x2 = x >= 2 ? x - 2 : 0;
+        const uint32_t nx0 = ldg(&t0[x1].x), nx1 = ldg(&t1[x1].x), ny0 = ldg(&t0[x2].y), ny1 = ldg(&t1[x2].y);
+        const uint32_t gop = prmt(py0, py1, 0x3430u) + nucp, gep = prmt(py0, py1, 0x3531u) + nucp;      // column x - 1
         const RowEntry* rp = rows + x;
         uint32_t i_run = kInf16x2;           // nothing below diagonal 0
         if (x >= K) {
@@ -1030,6 +1059,7 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows /* rows[0 .. L-1] re
                 if (k == x) break;
                 PHMM_BKCELL(k)
             }
+            const RowEntry w0 = rows[0];
             const uint32_t sub0 = vmin2(w0.y, prmt(caps0, caps1, w0.x));       // the start cell (x, 0): its total stays in BM[x]
             switch (x) { PHMM_REP64A(PHMM_BCASE_START) default: break; }
         }
@@ -1037,9 +1067,9 @@ PHMM_HD void dp_flank_bwd(const RowEntry* __restrict__ rows /* rows[0 .. L-1] re
             PHMM_FB_STORE(BM, BD)
             PHMM_FB_NEXT_BELOW(x)
         }
-        const uint32_t z = i_run & 0x80008000u;
-        caps0 = p0.x; caps1 = p1.x; go = go_p; ge = ge_p;
-        p0.x = n0.x + z; p0.y = n0.y + z; p1.x = n1.x + z; p1.y = n1.y + z;
+        const uint32_t z = i_run & 0x80008000u;          // see dp_pair: keeps the prefetched words out of the live registers until the column is done
+        caps0 = nx0 + z; caps1 = nx1 + z; go = gop - nucp; ge = gep - nucp;
+        py0 = ny0 + z; py1 = ny1 + z;
     }
 #undef PHMM_BKCELL
 #undef PHMM_BCASE_START
@@ -1141,8 +1171,8 @@ PHMM_HD void dp_flank_fb(const RowEntry* __restrict__ rows, const int L, const C
                          uint32_t* fscr, const size_t fstride, uint32_t* bscr, const size_t bstride, FbResult* res0, FbResult* res1, const uint32_t one = 1u)
 {
     const FbBounds g = fb_bounds(b0, b1, b2, b3, L + 2 * BAND - 1);
-    dp_flank_fwd<BAND, OGE>(rows, L, t0, t1, nucp, g, fscr, fstride, one);
-    dp_flank_bwd<BAND>(rows, L, t0, t1, nucp, g, bscr, bstride, one);
+    dp_flank_fwd<BAND, OGE>(rows, L, t0, t1, nucp, g, [=]() { return fscr; }, fstride, one);
+    dp_flank_bwd<BAND>(rows, L, t0, t1, nucp, g, [=]() { return bscr; }, bstride, one);
     fb_finish(2 * BAND, L, g, fscr, fstride, bscr, bstride, res0, res1);
 }
 

@@ -1037,7 +1037,7 @@ k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch, const int ro
             window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
             const FbBounds g = fb_bounds(lhs0, W - rhs0, lhs1, W - rhs1, W);
             const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
-            uint32_t* fscr = pair_scratch + (size_t)(cl.base + c) * fb_round_words(BAND) + lane;
+            const auto fscr = [&]() { return pair_scratch + (size_t)(cl.base + c) * fb_round_words(BAND) + (threadIdx.x & 31); };
             if (oge) dp_flank_fwd<BAND, true>(rows, L, c0, c1, nucp, g, fscr, 32, (uint32_t)p.one);
             else dp_flank_fwd<BAND, false>(rows, L, c0, c1, nucp, g, fscr, 32, (uint32_t)p.one);
         }
@@ -1057,7 +1057,7 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
     const int n_list = tile_list(p);
     // the backward arrays of this thread: lane-interleaved within the warp's own region (constant stride: immediate store offsets)
     constexpr size_t bstride = 32;
-    uint32_t* bscr = thread_scratch + (size_t)(blockIdx.x * kFastWarpsPerBlock + warp) * fb_scratch_words(BAND) * 32 + lane;
+    const auto bscr_fn = [&]() { return thread_scratch + (size_t)(blockIdx.x * kFastWarpsPerBlock + (threadIdx.x >> 5)) * fb_scratch_words(BAND) * 32 + (threadIdx.x & 31); };
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     for (;;) {
         FbClaim cl = fb_claim(p, p.fb_cursor, n_list, lane, lg);
@@ -1087,37 +1087,55 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
         for (int o = LG >> 1; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
         if (n == 0) continue;       // (no warp-level operation below)
         const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
-        const RegionInfo reg = p.regs[p.rd.region[r]];
-        const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
-        const uint32_t* npre = p.rd.reverse[r] ? p.hp.npre_r : p.hp.npre_f;
-        const int W = L + K - 1;
         for (int c = 0; c < cl.rounds; ++c) {
+            // Register discipline: the band takes 64 of the 128 registers and ptxas issues a cell's row-entry load ahead of its use only if it
+            // finds ~8 spare ones (LDS-to-use distance 2 instructions and short_scoreboard 1.6 stalls per issue without them, profiles/r02q —
+            // the forward kernel, with nothing to do after its DP, loads three cells ahead). So nothing but the list slot, the read, its two
+            // sizes and the two task words lives across the DP: each side of it derives what it needs from OPAQUE copies of those.
+            int li_o = cl.li, r_o = r, n_o = n, L_o = L;
+            asm volatile("" : "+r"(li_o), "+r"(r_o), "+r"(n_o), "+r"(L_o));
             const int i0 = (c << (lg + 1)) + 2 * gl, i1 = i0 + 1;
-            if (i0 >= n) continue;
-            const bool v1 = i1 < n;
-            const uint32_t w0 = q[i0], w1 = v1 ? q[i1] : w0;                 // the forward kernel's mapping, exactly
-            const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
+            if (i0 >= n_o) continue;
+            uint32_t x0, x1;
+            {
+                const uint32_t* q = p.atasks + (size_t)li_o * p.fcap;
+                const uint32_t w0 = q[i0], w1 = i1 < n_o ? q[i1] : w0;           // the forward kernel's mapping, exactly
+                const RegionInfo reg = p.regs[p.rd.region[r_o]];
+                const ColEntry* tab = p.rd.reverse[r_o] ? p.hp.tab_r : p.hp.tab_f;
+                const int W = L_o + K - 1;
+                const int h0 = (int)(w0 & 0xFFFFu), a0 = (int)(w0 >> 16), h1 = (int)(w1 & 0xFFFFu), a1 = (int)(w1 >> 16);
+                int lhs0, rhs0, lhs1, rhs1;
+                window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
+                window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
+                const FbBounds g = fb_bounds(lhs0, W - rhs0, lhs1, W - rhs1, W);
+                dp_flank_bwd<BAND>(rows, L_o, tab + p.hp.off[h0] + a0, tab + p.hp.off[h1] + a1, nucp, g, bscr_fn, bstride, (uint32_t)p.one);
+                x0 = w0; x1 = w1;
+            }
+            asm volatile("" : "+r"(li_o), "+r"(r_o), "+r"(n_o), "+r"(L_o), "+r"(x0), "+r"(x1));
+            const bool v1 = i1 < n_o;
+            const int W = L_o + K - 1;
+            const RegionInfo reg = p.regs[p.rd.region[r_o]];
+            const uint32_t* npre = p.rd.reverse[r_o] ? p.hp.npre_r : p.hp.npre_f;
+            const int h0 = (int)(x0 & 0xFFFFu), a0 = (int)(x0 >> 16), h1 = (int)(x1 & 0xFFFFu), a1 = (int)(x1 >> 16);
             int lhs0, rhs0, lhs1, rhs1;
             window_flanks(a0, W, (int)(p.hp.off[h0 + 1] - p.hp.off[h0]), reg.lhs, reg.rhs, &lhs0, &rhs0);
             window_flanks(a1, W, (int)(p.hp.off[h1 + 1] - p.hp.off[h1]), reg.lhs, reg.rhs, &lhs1, &rhs1);
             const FbBounds g = fb_bounds(lhs0, W - rhs0, lhs1, W - rhs1, W);
-            const ColEntry *c0 = tab + p.hp.off[h0] + a0, *c1 = tab + p.hp.off[h1] + a1;
-            dp_flank_bwd<BAND>(rows, L, c0, c1, nucp, g, bscr, bstride, (uint32_t)p.one);
             FbResult f0, f1;
-            fb_finish(K, L, g, pair_scratch + (size_t)(base + c) * fb_round_words(BAND) + lane, 32, bscr, bstride, &f0, &f1);
+            fb_finish(K, L_o, g, pair_scratch + (size_t)(base + c) * fb_round_words(BAND) + lane, 32, bscr_fn(), bstride, &f0, &f1);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (half && !v1) continue;
                 const FbResult f = half ? f1 : f0;
                 const int h = half ? h1 : h0, a = half ? a1 : a0;
                 // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
-                if (flank_replay_may_differ_pre(npre + p.hp.off[h], a, W, half ? lhs1 : lhs0, half ? rhs1 : rhs0, low_quality)) push_slow(p, r, h, a);
+                if (flank_replay_may_differ_pre(npre + p.hp.off[h], a, W, half ? lhs1 : lhs0, half ? rhs1 : rhs0, low_quality)) push_slow(p, r_o, h, a);
                 else if (f.tie) {
-                    const int slot = atomicAdd(p.gcnt + cl.li, 1);
-                    if (slot < p.fcap) p.gtasks[(size_t)cl.li * p.fcap + slot] = half ? w1 : w0;
+                    const int slot = atomicAdd(p.gcnt + li_o, 1);
+                    if (slot < p.fcap) p.gtasks[(size_t)li_o * p.fcap + slot] = half ? x1 : x0;
                     else atomicOr(p.flags, 8);
                     *p.any_flank_tasks = 1;
-                } else atomicMin(p.best + pair_slot(p.rd, h, r), discount_flank(f.score, f.flank, L, f.mask, 0));
+                } else atomicMin(p.best + pair_slot(p.rd, h, r_o), discount_flank(f.score, f.flank, L_o, f.mask, 0));
             }
         }
     }
