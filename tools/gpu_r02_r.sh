@@ -9,15 +9,12 @@ tail -4 $O/pytest_gpu.log | cut -c1-300
 timeout 120 python __graft_entry__.py --smoke > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log; tail -2 $O/smoke.log
 timeout 300 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 B="python bench.py --no-cpu-baseline --steps 3 --warmup 3"
-timeout 120 $B --config C2 > $O/bench_c2.json 2> $O/bench_c2.err
-timeout 120 $B --config C2 --shortcut --map > $O/bench_c2_refmode.json 2> $O/bench_c2_refmode.err
 timeout 120 $B --config C4 > $O/bench_c4.json 2> $O/bench_c4.err
 timeout 120 $B --config C2 --flank 60,60 > $O/bench_c2_flank.json 2> $O/bench_c2_flank.err
 timeout 120 $B --config C2 --shortcut --map --flank 60,60 > $O/bench_c2_prod.json 2> $O/bench_c2_prod.err
 timeout 120 $B --config C3 --flank 60,60 > $O/bench_c3_flank.json 2> $O/bench_c3_flank.err
-timeout 120 $B --config C4 --flank 100,100 > $O/bench_c4_flank.json 2> $O/bench_c4_flank.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_c2_flank.csv $B --config C2 --flank 60,60 --steps 1 --warmup 1 > $O/launches_flank.log 2>&1
-timeout 240 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_flank_fb.py -m gpu -x -q -k "16 and (benchmark or regions)" > $O/memcheck_flank.log 2>&1; echo "memcheck rc=$?" >> $O/memcheck_flank.log
+timeout 100 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_flank_fb.py -m gpu -x -q -k "16 and regions" > $O/memcheck_flank.log 2>&1; echo "memcheck rc=$?" >> $O/memcheck_flank.log
 tail -5 $O/memcheck_flank.log | cut -c1-300
 for f in $O/bench_*.json; do python - "$f" <<'PY'
 import sys, json
