@@ -1128,16 +1128,21 @@ static int populate_impl(phmm_engine* e, const phmm_config* cfg,
 #undef PHMM_FB_LAUNCH
             LAUNCHED();
         }
-        const unsigned fgrid = (unsigned)std::max(1, std::min((n_entries + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock, e->sm_count * 3));
-        const size_t fsmem = (size_t)kFastWarpsPerBlock * row_stride * sizeof(RowEntry);
+        // the labelled kernel: whole warps per read when its lists are dense, groups of 4 lanes when they only hold what the packed kernels
+        // passed on (ties: one or two candidates per read; the rare reads with 'N' or shorter than 2 * band then take more rounds)
+        int flg = 5;
+        if (p.atasks && p.fb_route) { flg = 2; while (flg < 5 && (size_t)kFastWarpsPerBlock * (32 >> flg) * row_stride * sizeof(RowEntry) > (48u << 10)) ++flg; }
+        const int fG = 32 >> flg;
+        const unsigned fgrid = (unsigned)std::max(1, std::min((n_entries / fG + kFastWarpsPerBlock) / kFastWarpsPerBlock, e->sm_count * 3));
+        const size_t fsmem = (size_t)kFastWarpsPerBlock * fG * row_stride * sizeof(RowEntry);
         int frc;
         switch (band) {
             case 8:  if ((frc = fast_smem_attr(e, k_populate_flank<8>, fsmem))) return frc;
-                     k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                     k_populate_flank<8><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p, row_stride, flg); break;
             case 16: if ((frc = fast_smem_attr(e, k_populate_flank<16>, fsmem))) return frc;
-                     k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                     k_populate_flank<16><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p, row_stride, flg); break;
             default: if ((frc = fast_smem_attr(e, k_populate_flank<32>, fsmem))) return frc;
-                     k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p); break;
+                     k_populate_flank<32><<<fgrid, kFastWarpsPerBlock * 32, fsmem, e->stream>>>(p, row_stride, flg); break;
         }
         LAUNCHED();
         if (p.atasks && !p.fb_route) {

@@ -836,45 +836,71 @@ k_populate_roles(const PopParams p)
     }
 }
 
-// Near-flank candidates of fast-path reads: the payload-carrying 32-bit DP (dp_flank32), one alignment per lane, one READ
-// per warp (row entries broadcast from shared memory), persistent warps over the tile's work list.
+// Work claim of the per-read flank kernels: a warp is cut into G = 32 >> lg lane groups of 1 << lg lanes and claims G consecutive list
+// slots; a group owns one read (its row entries in its own shared-memory region). Every lane learns its group's slot, read, task count
+// (counts[slot]) and read length, and the warp's round count (a lane takes `per_lane` tasks per round). rounds < 0: the list is exhausted.
+struct FbClaim { int li, r, n, L, rounds, base; };
+__device__ __forceinline__ FbClaim fb_claim(const PopParams& p, int* cursor, const int* __restrict__ counts, const int n_list, const int lane, const int lg,
+                                            const int per_lane)
+{
+    const int G = 32 >> lg;
+    int li0 = 0;
+    if (lane == 0) li0 = atomicAdd(cursor, G);
+    li0 = __shfl_sync(0xffffffffu, li0, 0);
+    FbClaim c;
+    c.li = li0 + (lane >> lg);
+    if (li0 >= n_list) { c.li = -1; c.r = -1; c.n = 0; c.L = 0; c.rounds = -1; c.base = -1; return c; }
+    c.r = c.li < n_list ? p.list[c.li] : -1;
+    c.n = c.r >= 0 ? counts[c.li] : 0;
+    c.L = c.n > 0 ? p.rd.info[c.r].x : 0;
+    const int per_round = per_lane << lg;
+    int rounds = (c.n + per_round - 1) / per_round;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+    c.rounds = rounds; c.base = -1;
+    return c;
+}
+
+// Near-flank candidates the packed flank kernels do not take (reads with 'N', reads shorter than 2 * band, candidates they report
+// as tied; band 32: every candidate that is not lean): the payload-carrying 32-bit DP (dp_flank32), one alignment per lane, persistent
+// warps over the tile's work list. A lane group owns a read (row entries broadcast from its shared-memory region): whole warps
+// (lg = 5) when the lists are dense, groups of 4 lanes when they hold the packed kernels' ties — one or two per read, which a warp per
+// read served with one or two of its 32 lanes (9 % of a flank-state step for 1 % of its candidates, profiles/r02r_launches_C2_flank.csv).
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32)
-k_populate_flank(const PopParams p)
+k_populate_flank(const PopParams p, const int row_stride, const int lg)
 {
     extern __shared__ RowEntry smem_rows[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RowEntry* rows = smem_rows + warp * p.row_stride;
+    const int LG = 1 << lg, gl = lane & (LG - 1);
+    RowEntry* rows = smem_rows + (size_t)(warp * (32 >> lg) + (lane >> lg)) * row_stride;
     constexpr int K = 2 * BAND;
-    if (*p.any_flank_tasks == 0) return;          // the classify pass queued nothing for this kernel
+    if (*p.any_flank_tasks == 0) return;          // nothing was queued for this kernel
     const int n_list = tile_list(p);
     for (;;) {
-        int li = 0;
-        if (lane == 0) li = atomicAdd(p.flank_cursor, 1);
-        li = __shfl_sync(0xffffffffu, li, 0);
-        if (li >= n_list) break;
-        const int r = p.list[li];
-        const int n = r >= 0 ? p.gcnt[li] : 0;
-        if (n == 0) continue;
-        const int L = p.rd.info[r].x;
-        const RegionInfo reg = p.regs[p.rd.region[r]];
+        const FbClaim cl = fb_claim(p, p.flank_cursor, p.gcnt, n_list, lane, lg, 1);
+        if (cl.rounds < 0) break;
+        if (cl.rounds == 0) continue;
+        const int r = cl.r, n = cl.n, L = cl.L;
         __syncwarp();
         unsigned qmin = 255u;
-        {
+        if (n > 0) {
             const uint16_t* hr = p.rd.rowhalf + p.rd.off[r];
-            for (int y = lane; y < L; y += 32) { const uint16_t half = hr[y]; rows[y] = make_row_entry32(half); qmin = min(qmin, (unsigned)half >> 8); }
-            if (lane == 0) rows[L] = pad_row_entry32();
-            __syncwarp();
+            for (int y = gl; y < L; y += LG) { const uint16_t half = hr[y]; rows[y] = make_row_entry32(half); qmin = min(qmin, (unsigned)half >> 8); }
+            if (gl == 0) rows[L] = pad_row_entry32();
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        __syncwarp();
+        for (int o = LG >> 1; o > 0; o >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        if (n == 0) continue;       // (no warp-level operation below)
         const bool low_quality = qmin < 2u;                 // see flank_replay_may_differ
+        const RegionInfo reg = p.regs[p.rd.region[r]];
         const ColEntry* tab = p.rd.reverse[r] ? p.hp.tab_r : p.hp.tab_f;
-        const uint32_t* q = p.gtasks + (size_t)li * p.fcap;
+        const uint32_t* q = p.gtasks + (size_t)cl.li * p.fcap;
         const int W = L + K - 1;
-        for (int c = 0; c < n; c += 32) {
-            const bool valid = c + lane < n;
-            const uint32_t t = q[valid ? c + lane : 0];
+        for (int c = 0; c < cl.rounds; ++c) {
+            const int i = (c << lg) + gl;
+            if (i >= n) continue;
+            const uint32_t t = q[i];
             const int h = (int)(t & 0xFFFFu), a = (int)(t >> 16);
             const int hap_len = (int)(p.hp.off[h + 1] - p.hp.off[h]);
             int lhs, rhs;
@@ -889,10 +915,8 @@ k_populate_flank(const PopParams p)
             const int v = discount_flank(score, flank, L, mask, 0);
             // an in-flank 'N' column the DP may have charged less than the reference's replay does: exact traceback path instead
             const bool replay_differs = reg.use_flanks != 0 && flank_replay_may_differ(tab + p.hp.off[h] + a, W, lhs, rhs, low_quality);
-            if (valid) {
-                if (replay_differs) push_slow(p, r, h, a);
-                else atomicMin(p.best + pair_slot(p.rd, h, r), v);
-            }
+            if (replay_differs) push_slow(p, r, h, a);
+            else atomicMin(p.best + pair_slot(p.rd, h, r), v);
         }
     }
 }
@@ -969,27 +993,6 @@ __host__ __device__ constexpr size_t fb_round_words(const int band) { return (si
 //                minimum into best[]. A candidate whose co-optimal paths cross a boundary at different cells (FbResult::tie, ~1 %) is
 //                appended to the read's gtasks list: k_populate_flank, launched after these two, resolves it with the labelled DP.
 // (One fused kernel measured 0.9 x the labelled kernel: its code overflows the instruction cache, profiles/r02n.)
-struct FbClaim { int li, r, n, L, rounds, base; };
-// A warp claims G consecutive list slots; every lane learns its group's slot, read, candidate count and the warp's round count.
-__device__ __forceinline__ FbClaim fb_claim(const PopParams& p, int* cursor, const int n_list, const int lane, const int lg)
-{
-    const int G = 32 >> lg;
-    int li0 = 0;
-    if (lane == 0) li0 = atomicAdd(cursor, G);
-    li0 = __shfl_sync(0xffffffffu, li0, 0);
-    FbClaim c;
-    c.li = li0 + (lane >> lg);
-    if (li0 >= n_list) { c.li = -1; c.r = -1; c.n = 0; c.L = 0; c.rounds = -1; c.base = -1; return c; }
-    c.r = c.li < n_list ? p.list[c.li] : -1;
-    c.n = c.r >= 0 ? p.acnt[c.li] : 0;
-    c.L = c.n > 0 ? p.rd.info[c.r].x : 0;
-    int rounds = (c.n + (2 << lg) - 1) >> (lg + 1);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
-    c.rounds = rounds; c.base = -1;
-    return c;
-}
-
 template <int BAND>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, 4)
 k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch, const int row_stride, const int lg)
@@ -1004,7 +1007,7 @@ k_flank_fwd(const PopParams p, uint32_t* __restrict__ pair_scratch, const int ro
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     const bool oge = open_ge_extend(p.flags);
     for (;;) {
-        FbClaim cl = fb_claim(p, p.acc_cursor, n_list, lane, lg);
+        FbClaim cl = fb_claim(p, p.acc_cursor, p.acnt, n_list, lane, lg, 2);
         if (cl.rounds < 0) break;
         if (cl.rounds == 0) continue;
         if (lane == 0) {
@@ -1060,7 +1063,7 @@ k_flank_bwd(const PopParams p, const uint32_t* pair_scratch, uint32_t* __restric
     const auto bscr_fn = [&]() { return thread_scratch + (size_t)(blockIdx.x * kFastWarpsPerBlock + (threadIdx.x >> 5)) * fb_scratch_words(BAND) * 32 + (threadIdx.x & 31); };
     const uint32_t nucp = (uint32_t)p.nuc_prior | ((uint32_t)p.nuc_prior << 16);
     for (;;) {
-        FbClaim cl = fb_claim(p, p.fb_cursor, n_list, lane, lg);
+        FbClaim cl = fb_claim(p, p.fb_cursor, p.acnt, n_list, lane, lg, 2);
         if (cl.rounds < 0) break;
         if (cl.rounds == 0) continue;
         const int L = cl.L, n = cl.n, r = cl.r;
