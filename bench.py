@@ -537,7 +537,7 @@ def main():
         traffic = measured_traffic(args.config, R, H, band, mode_key)
         role_warps = band in (32, 64) and H >= 17 and not os.environ.get("PHMM_NO_ROLE_WARPS")     # the engine's own rule (populate_impl)
         flank_fb = band <= 16 and not args.int_scores and not os.environ.get("PHMM_NO_FLANK_FB")          # the engine's own rule (populate_impl)
-        kernel_name = ("k_populate_flank_fb<%d> (+ score-only and labelled flank kernels of the tile)" % band) if flank_state and flank_fb else \
+        kernel_name = ("k_flank_fwd<%d> + k_flank_bwd<%d> (+ score-only and labelled flank kernels of the tile)" % (band, band)) if flank_state and flank_fb else \
                       ("k_populate_flank_acc<%d> (+ score-only and crossing-cell flank kernels of the tile)" % band) if flank_state and band <= 32 else \
                       ("k_populate_wide (32-bit lanes, band %d)" % band) if args.int_scores else \
                       ("k_populate_roles<%d> (one warp per 32 diagonals)" % band) if role_warps else "k_populate_fast<%d>" % band
