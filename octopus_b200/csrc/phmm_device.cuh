@@ -11,11 +11,16 @@
 //   transitions of even-x cells are computed before the initialiser touches them, :282-283 vs :317-319)
 //   result = min over x of S(x, L)                               (:285-291, :309-315, :323)
 //
-// Two implementations live here:
+// The implementations that live here:
 //   * dp_pair<BAND>  — the fast path. One THREAD owns TWO alignments packed as s16x2 in every register and sweeps
 //     the band column by column (x outer, diagonal k = x-y unrolled in registers). No shuffles, no shared-memory
 //     DP state. The per-cell work is 10 integer instructions for 2 cells using Blackwell's DPX packed-16 ops
 //     (VIMNMX3.S16x2, VIADDMNMX.S16x2, VIMNMX.S16x2) and PRMT byte-table lookups for the emission.
+//   * dp_band / dp_band_roles — the same cell with the band's diagonals split over lanes or warps (bands 32 ... 256, 32-bit lanes).
+//   * dp_flank_fwd / dp_flank_bwd / fb_finish — the flank-aware path, packed: forward pass to the flank boundary, backward pass
+//     (cost-to-go) from the window end, crossing cell = argmin F + B; dp_flank32 / dp_flank_acc — the labelled one-alignment-per-
+//     thread forms that reproduce the reference's traceback tie-breaks (fallback for ties, reads with 'N', short reads, band 32).
+//   * dp_traceback_forward + traceback_walk — best alignment + CIGAR (register band, one back-pointer word per cell).
 //   * generic_align  — int32, any band, any alphabet, optional traceback + flank replay. Exactness fallback.
 #pragma once
 
